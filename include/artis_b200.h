@@ -1,0 +1,166 @@
+/* artis_b200.h — C ABI of the B200-native replacement for ARTIS's per-timestep packet propagation.
+ *
+ * The reference has no plugin/FFI API for this path: the boundary is the ordinary C++ call
+ *     void update_packets(int nts, std::span<Packet> packets);      (reference update_packets.h:10,
+ *                                                                    called at sn3d.cc:790)
+ * plus global read-only state (atomic data, grid geometry, per-timestep cell state) and global estimator
+ * arrays that the call accumulates into.  This header is the flattened, plain-C form of
+ * that boundary: every implicit global becomes a named array handed over with artisb200_set_array(),
+ * and the call itself becomes artisb200_update_packets_host().  integration/update_packets_b200.cc is the
+ * reference-side binding (it provides the C++ symbol update_packets and forwards here).
+ *
+ * Conventions
+ *   - all pointers are HOST pointers unless a name says "device"; the library owns the device copies
+ *   - every function returns 0 on success, nonzero on error; artisb200_last_error() describes the error.
+ *     The reference's convention is assert_always -> log -> abort() (mpi_logging.h:123-130); the binding
+ *     reproduces it by aborting when a call returns nonzero.
+ *   - there is NO CPU fallback: artisb200_create() fails if no CUDA device is usable.
+ *
+ * Named arrays (dtype codes: 'd' f64, 'f' f32, 'i' i32, 'q' i64, 'B' u8, 'Q' u64).  Nc = non-empty model
+ * cells, Nion/Nlev/L/Nbf/Ng as in SURVEY.md §8.  Each name cites the reference global it mirrors.
+ *
+ *  scalars (count 1)
+ *   scalar.grid_type 'q'      GridType of the propagation grid 0=SPHERICAL1D 1=CYLINDRICAL2D 2=CARTESIAN3D (constants.h:76-80, grid.cc:192)
+ *   scalar.ncoordgrid 'q'[3]  grid.cc:64
+ *   scalar.tmin/rmax/vmax 'd' globals.h:346-349
+ *   scalar.nphixspoints 'q', scalar.nphixsnuincrement 'd', scalar.last_phixs_nuovernuedge 'd'   globals.h:273-274, atomic.h:30
+ *   scalar.tablesize 'q', scalar.options_hash 'q'
+ *   scalar.max_path_step 'd'  (per timestep; globals.h:142)
+ *  static tables
+ *   grid.coord_pos_min_tmin{0,1,2} 'd'   grid.cc:82        grid.propcell_nonemptymgi 'i'[ngrid] grid.cc:87
+ *   cell.ffegrp 'f'[Nc]                  grid.cc:110 via get_ffegrp(mgi)
+ *   elem.anumber/nions/lowest_ionstage/uniqueionindexstart 'i'[nelements]            globals.h:59-66
+ *   ion.nlevels/nlevels_ionising/maxrecombininglevel/coolingoffset/ncoolingterms/uniquelevelindexstart/
+ *       groundcontindex/nlevels_excited_nlte/allnltelevelsindexstart 'i'[Nion], ion.ionpot 'd'  globals.h:44-57
+ *   level.epsilon 'd', level.statweight 'f', level.alltrans_startdown/ndowntrans/nuptrans/closestgroundlevelcont/
+ *       phixsstart/nphixstargets/phixstargetstart/bflist_start/matransblock_start 'i'[Nlev]      globals.h:173-216
+ *   trans.lineindex/targetlevelindex 'i', trans.einstein_A/coll_str/osc_strength 'f', trans.forbidden 'B'  globals.h:148-155
+ *   line.nu 'd', line.elementindex/ionindex/lower/upper 'i', line.B_ul/B_lu 'f' [L]           globals.h:223-232
+ *   cont.nu_edge 'd', cont.element/ion/level/phixstargetindex/upperlevel/uniquelevelindex 'i', cont.probability 'd',
+ *       cont.groundcontestimindex/bfestimindex 'i' [Nbf]                                      globals.h:247-262
+ *   phixs.table 'f'  globals.h:146     phixstarget.levelindex 'i', phixstarget.probability 'd'  globals.h:169-171
+ *   groundcont.nu_edge 'd'[Ng] globals.h:266      bfestim.nu_edge 'd' globals.h:245
+ *   lut.spontrecomb/corrphotoion/bfcooling 'd'[Nbf*TABLESIZE], lut.temperature_grid 'd'[TABLESIZE+1]  ratecoeff.cc:40-72
+ *   cooling.type 'B', cooling.level 'i', cooling.phixstargetindex 'i' [ncoolingterms]        kpkt.cc:44-46
+ *   timesteps.start/width/mid 'd'[ntimesteps]                                               globals.h:73-76
+ *  per-timestep cell state (set before artisb200_begin_timestep)
+ *   cell.rho/Te/TJ/TR/W/nne/nnetot/kappagrey/clumpfactor 'f'[Nc], cell.thick 'i'[Nc]        grid.h:19-36
+ *   cell.elem_massfracs 'f'[Nc*nelements] grid.h:45   cell.ion_groundlevelpops/ion_partfuncts 'f'[Nc*Nion] grid.h:47-48
+ *   cell.ion_cooling_contribs 'd'[Nc*Nion] kpkt.h:18  cell.corrphotoionrenorm 'd'[Nc*Ng] globals.h:124
+ *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
+ *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132
+ *   est.gamma/bfheating 'd'[Nc*Ng] globals.h:126-129   est.dep_gamma/dep_positron/dep_electron/dep_alpha 'd'[Nc] globals.h:118-121
+ *   ts.scalars 'd'[ARTISB200_NTSSCALARS] (order below; globals.h:73-113 and nonthermal.cc:200)   ts.pellet_decays 'q'
+ *   counters 'q'[34]  (stats.h:14-50; INTERACTIONS is index 26)      diag 'q'[ARTISB200_NDIAG]
+ */
+#ifndef ARTIS_B200_H
+#define ARTIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct artisb200_ctx artisb200_ctx;
+
+/* order of ts.scalars */
+enum {
+  ARTISB200_TS_GAMMA_DEP_DISCRETE = 0,
+  ARTISB200_TS_POSITRON_DEP_DISCRETE = 1,
+  ARTISB200_TS_POSITRON_EMISSION = 2,
+  ARTISB200_TS_ELECTRON_DEP_DISCRETE = 3,
+  ARTISB200_TS_ELECTRON_EMISSION = 4,
+  ARTISB200_TS_ALPHA_DEP_DISCRETE = 5,
+  ARTISB200_TS_ALPHA_EMISSION = 6,
+  ARTISB200_TS_SPFISSION_DEP_DISCRETE = 7,
+  ARTISB200_TS_GAMMA_EMISSION = 8,
+  ARTISB200_TS_NT_ENERGY_DEPOSITED = 9,
+  ARTISB200_NTSSCALARS = 10
+};
+
+/* order of diag (device-side work counters used for the roofline's algorithmic bytes) */
+enum {
+  ARTISB200_DIAG_RPKT_STEPS = 0,      /* do_rpkt_step calls */
+  ARTISB200_DIAG_LINES_VISITED = 1,   /* lines tested in get_possible_event */
+  ARTISB200_DIAG_CONT_EVALS = 2,      /* calculate_chi_rpkt_cont evaluations (cache misses) */
+  ARTISB200_DIAG_CONT_TERMS = 3,      /* kept continua summed in those evaluations */
+  ARTISB200_DIAG_BINSEARCH_STEPS = 4, /* binary-search probe loads (linelist, allcont, cumulative tables) */
+  ARTISB200_DIAG_ESTIMATOR_ADDS = 5,  /* f64 estimator read-modify-writes */
+  ARTISB200_DIAG_MA_STEPS = 6,        /* macro-atom transitions selected */
+  ARTISB200_DIAG_K_STEPS = 7,         /* k-packet cooling selections */
+  ARTISB200_DIAG_GAMMA_STEPS = 8,     /* transport_gamma calls */
+  ARTISB200_DIAG_GAMMA_EVENTS = 9,    /* physical gamma events (Compton/photoelectric/pair) */
+  ARTISB200_DIAG_KERNEL_LAUNCHES = 10,/* propagation kernel launches in the last update_packets */
+  ARTISB200_DIAG_PACKET_SEGMENTS = 11,/* packet (re)loads: one per packet per launch */
+  ARTISB200_NDIAG = 16
+};
+
+/* flags for artisb200_set_option */
+#define ARTISB200_RNG_PHILOX 0   /* production: Philox4x32-10 keyed by (seed, packet number), counter (nts, draw) */
+#define ARTISB200_RNG_XOSHIRO 1  /* parity: the reference's per-packet Xoshiro128++ state carried in a 256-byte GPU_ON Packet (packet.h:110-114, random.h:103-138) */
+
+/* Create a context on CUDA device `device_ordinal`. Fails (nonzero) when there is no usable device. */
+int artisb200_create(artisb200_ctx** out, int device_ordinal);
+void artisb200_destroy(artisb200_ctx* ctx);
+const char* artisb200_last_error(const artisb200_ctx* ctx); /* ctx may be NULL: returns the last create() error */
+
+/* Hash of the compile-time options this library was built with (the hot-path subset of artisoptions.h).
+ * The binding compares it with its own to catch preset mismatches. */
+uint64_t artisb200_options_hash(void);
+const char* artisb200_options_summary(void);
+
+/* Hand a named host array (see table above) to the library; it is copied to the device.
+ * Scalars are arrays of count 1. Unknown names are an error. */
+int artisb200_set_array(artisb200_ctx* ctx, const char* name, char dtype, const void* host_data, int64_t count);
+/* Copy a named device array (estimators, counters, built per-cell tables) back to the host.
+ * `count` must equal the array's length (query with artisb200_array_count). */
+int artisb200_get_array(artisb200_ctx* ctx, const char* name, char dtype, void* host_out, int64_t count);
+int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name); /* -1 if unknown / unset */
+
+/* Runtime options: "rng_mode" (ARTISB200_RNG_*), "seed", "max_steps_per_launch" (0 = whole history in one
+ * launch, the order-independent parity mode), "sort_packets" (0/1), "rank", "nranks". */
+int artisb200_set_option(artisb200_ctx* ctx, const char* name, int64_t value);
+
+/* Validate that all required static tables are present and build derived static tables.
+ * Replaces nothing in the reference; corresponds to the end of start-up (after sn3d.cc setup_cellcache). */
+int artisb200_commit_static(artisb200_ctx* ctx);
+
+/* Called once per timestep after the per-timestep cell state has been set: zeroes the estimators
+ * (sn3d.cc:718-742 zero_estimators) and builds the per-cell tables on the device
+ * (update_packets.cc:397-464 cellcacheslot_populate for every cell, as the reference's GPU_ON mode does
+ * at update_packets.cc:551-563). */
+int artisb200_begin_timestep(artisb200_ctx* ctx, int nts);
+
+/* Packet transfer between the reference's AoS Packet array and the device SoA.
+ * stride_bytes is sizeof(Packet): 240 (CPU build) or 256 (GPU_ON build with the 16-byte rngstate prefix). */
+int artisb200_upload_packets(artisb200_ctx* ctx, const void* packets_aos, int64_t npackets, int stride_bytes);
+int artisb200_download_packets(artisb200_ctx* ctx, void* packets_aos, int64_t npackets, int stride_bytes);
+
+/* Propagate the device-resident packets to the end of timestep nts (update_packets.cc:530-640). */
+int artisb200_update_packets(artisb200_ctx* ctx, int nts);
+
+/* The drop-in call: upload + artisb200_update_packets + download, i.e. exactly what
+ * update_packets(nts, packets) does to the caller's array (order of packets is preserved here). */
+int artisb200_update_packets_host(artisb200_ctx* ctx, int nts, void* packets_aos, int64_t npackets, int stride_bytes);
+
+/* Device-resident snapshot/restore of the packet state, for benchmarks that replay one timestep. */
+int artisb200_save_packets_device(artisb200_ctx* ctx);
+int artisb200_restore_packets_device(artisb200_ctx* ctx);
+
+/* One packed device buffer [J|nuJ|ffheating|colheating|gamma|bfheating|dep_*|ts.scalars] of f64 for the
+ * per-timestep all-reduce (replaces the MPI_Allreduce calls at sn3d.cc:565-625 and radfield.cc:988-1030).
+ * The caller (torch.distributed / NCCL) reduces it in place. */
+int artisb200_estimator_device_buffer(artisb200_ctx* ctx, void** device_ptr, int64_t* count_f64);
+
+/* Device time [ms] of the last artisb200_update_packets measured with CUDA events on the library's stream,
+ * split as total / propagation kernels / scheduling (sort, compaction). */
+int artisb200_last_timing_ms(artisb200_ctx* ctx, double* total_ms, double* propagate_ms, double* schedule_ms);
+
+/* Raw CUDA stream handle (cudaStream_t) the library launches on, for event timing by the caller. */
+void* artisb200_stream(artisb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTIS_B200_H */

@@ -1,0 +1,37 @@
+// Accessors added around the reference translation units by integration/ref_access/ref_*.cc.
+#pragma once
+#include <array>
+#include <cstddef>
+#include <span>
+
+#include "constants.h"
+
+namespace grid {
+auto b200_ncoordgrid() -> std::array<int, 3>;
+auto b200_coord_pos_min_tmin(int axis) -> std::span<const double>;
+auto b200_propcell_nonemptymgi() -> std::span<const int>;
+auto b200_propgridtype() -> GridType;
+}  // namespace grid
+
+auto b200_lut_spontrecombcoeffs() -> std::span<const double>;
+auto b200_lut_corrphotoioncoeffs() -> std::span<const double>;
+auto b200_lut_bfcooling_coeffs() -> std::span<const double>;
+auto b200_lut_temperature_grid() -> std::span<const double>;
+
+namespace kpkt {
+auto b200_coolinglist_type(int i) -> int;
+auto b200_coolinglist_level(int i) -> int;
+auto b200_coolinglist_phixstargetindex(int i) -> int;
+}  // namespace kpkt
+
+namespace radfield {
+auto b200_J() -> std::span<double>;
+auto b200_nuJ() -> std::span<double>;
+auto b200_bins_J_raw() -> std::span<double>;
+auto b200_bins_nuJ_raw() -> std::span<double>;
+auto b200_bfrate_raw() -> std::span<double>;
+}  // namespace radfield
+
+namespace stats {
+void b200_add_counter(int i, std::ptrdiff_t n);
+}  // namespace stats

@@ -1,0 +1,569 @@
+// Reference-side binding for the B200 packet-propagation library.
+//
+// This translation unit is compiled INSIDE the reference's source environment (its headers on the include
+// path) and provides the C++ symbol
+//     void update_packets(int nts, std::span<Packet> packets)            (update_packets.h:10)
+// in place of the reference's update_packets.cc.  It flattens the reference's global state into the named
+// arrays of include/artis_b200.h, forwards the call through the C ABI (loaded with dlopen so that the
+// host binary has no link-time CUDA dependency), and folds the returned estimators and counters back
+// into the reference's globals so that the rest of do_timestep() (sn3d.cc:790-838) runs unchanged.
+//
+// Build variants (integration/Makefile, oracle/Makefile):
+//   default                       the drop-in: GPU path only, reference update_packets.cc NOT linked.
+//   -DARTISB200_WITH_REFERENCE    oracle build: additionally embeds the reference's own update_packets.cc
+//                                 (renamed) so that it can be run and its inputs/outputs dumped as
+//                                 snapshots for the parity tests.  Test infrastructure, never shipped.
+//
+// Environment variables
+//   ARTISB200_MODE       gpu (default in the drop-in) | ref | ref_perpacket  (oracle build only)
+//   ARTISB200_LIB        path of libartis_b200_<preset>.so (gpu mode)
+//   ARTISB200_DUMP_DIR   directory for snapshots; ARTISB200_DUMP_TS = comma list of timesteps or "all"
+//   ARTISB200_RNG        philox (default) | xoshiro (needs a -DGPU_ON build: Packet carries rngstate)
+//   ARTISB200_MAXSTEPS   max packet steps per kernel launch (0 = whole history per launch)
+//   ARTISB200_DEVICE     CUDA device ordinal (default: LOCAL_RANK or 0)
+
+#ifdef ARTISB200_WITH_REFERENCE
+#define update_packets update_packets_reference_impl
+#include "update_packets.cc"  // NOLINT: reference TU, resolved via -I<artis source dir>
+#undef update_packets
+#endif
+
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <span>
+#include <string>
+#include <vector>
+
+#include "artis_b200.h"
+#include "artisoptions.h"
+#include "atomic.h"
+#include "b200_access.h"
+#include "b200_snapshot.h"
+#include "decay.h"
+#include "globals.h"
+#include "grid.h"
+#include "kpkt.h"
+#include "mpi_logging.h"
+#include "nonthermal.h"
+#include "packet.h"
+#include "radfield.h"
+#include "stats.h"
+#include "update_packets.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// flattening of the reference globals into named arrays (generic over the sink)
+// ---------------------------------------------------------------------------------------------------
+
+template <class Sink>
+void emit_static(Sink& s) {
+  const auto ncoord = grid::b200_ncoordgrid();
+  const int64_t ncoord64[3] = {ncoord[0], ncoord[1], ncoord[2]};
+  s.i64("scalar.grid_type", static_cast<int64_t>(grid::b200_propgridtype()));
+  s.arr("scalar.ncoordgrid", ncoord64, 3);
+  s.f64("scalar.tmin", globals::tmin);
+  s.f64("scalar.rmax", globals::rmax);
+  s.f64("scalar.vmax", globals::vmax);
+  s.i64("scalar.nphixspoints", globals::NPHIXSPOINTS);
+  s.f64("scalar.nphixsnuincrement", globals::NPHIXSNUINCREMENT);
+  s.f64("scalar.last_phixs_nuovernuedge", last_phixs_nuovernuedge);
+  s.i64("scalar.tablesize", TABLESIZE);
+
+  for (int axis = 0; axis < 3; axis++) {
+    const auto coords = grid::b200_coord_pos_min_tmin(axis);
+    const std::string name = "grid.coord_pos_min_tmin" + std::to_string(axis);
+    s.arr(name.c_str(), coords.data(), static_cast<int64_t>(coords.size()));
+  }
+  const auto propcell_nonemptymgi = grid::b200_propcell_nonemptymgi();
+  s.arr("grid.propcell_nonemptymgi", propcell_nonemptymgi.data(), static_cast<int64_t>(propcell_nonemptymgi.size()));
+
+  const int nc = grid::get_nonempty_npts_model();
+  std::vector<float> ffegrp(nc);
+  for (int nonemptymgi = 0; nonemptymgi < nc; nonemptymgi++) {
+    ffegrp[nonemptymgi] = grid::get_ffegrp(grid::get_mgi_of_nonemptymgi(nonemptymgi));
+  }
+  s.arr("cell.ffegrp", ffegrp.data(), nc);
+
+  // elements and ions
+  const int nelements = get_nelements();
+  std::vector<int> e_anumber(nelements);
+  std::vector<int> e_nions(nelements);
+  std::vector<int> e_lowest(nelements);
+  std::vector<int> e_uniqueionstart(nelements);
+  const int nions = get_includedions();
+  std::vector<int> i_nlevels(nions);
+  std::vector<int> i_nlevels_ionising(nions);
+  std::vector<int> i_maxrecomb(nions);
+  std::vector<int> i_coolingoffset(nions);
+  std::vector<int> i_ncoolingterms(nions);
+  std::vector<int> i_levelstart(nions);
+  std::vector<int> i_groundcontindex(nions);
+  std::vector<int> i_nlevels_nlte(nions);
+  std::vector<int> i_nltestart(nions);
+  std::vector<double> i_ionpot(nions);
+  for (int element = 0; element < nelements; element++) {
+    const auto& el = globals::elements[element];
+    e_anumber[element] = el.anumber;
+    e_nions[element] = get_nions(element);
+    e_lowest[element] = el.lowest_ionstage;
+    e_uniqueionstart[element] = el.uniqueionindexstart;
+    for (int ion = 0; ion < get_nions(element); ion++) {
+      const auto& io = el.ions[ion];
+      const int u = get_uniqueionindex(element, ion);
+      i_nlevels[u] = io.nlevels;
+      i_nlevels_ionising[u] = io.nlevels_ionising;
+      i_maxrecomb[u] = io.maxrecombininglevel;
+      i_coolingoffset[u] = io.coolingoffset;
+      i_ncoolingterms[u] = io.ncoolingterms;
+      i_levelstart[u] = io.uniquelevelindexstart;
+      i_groundcontindex[u] = io.groundcontindex;
+      i_nlevels_nlte[u] = io.nlevels_excited_nlte;
+      i_nltestart[u] = io.allnltelevelsindexstart;
+      i_ionpot[u] = io.ionpot;
+    }
+  }
+  s.arr("elem.anumber", e_anumber.data(), nelements);
+  s.arr("elem.nions", e_nions.data(), nelements);
+  s.arr("elem.lowest_ionstage", e_lowest.data(), nelements);
+  s.arr("elem.uniqueionindexstart", e_uniqueionstart.data(), nelements);
+  s.arr("ion.nlevels", i_nlevels.data(), nions);
+  s.arr("ion.nlevels_ionising", i_nlevels_ionising.data(), nions);
+  s.arr("ion.maxrecombininglevel", i_maxrecomb.data(), nions);
+  s.arr("ion.coolingoffset", i_coolingoffset.data(), nions);
+  s.arr("ion.ncoolingterms", i_ncoolingterms.data(), nions);
+  s.arr("ion.uniquelevelindexstart", i_levelstart.data(), nions);
+  s.arr("ion.groundcontindex", i_groundcontindex.data(), nions);
+  s.arr("ion.nlevels_excited_nlte", i_nlevels_nlte.data(), nions);
+  s.arr("ion.allnltelevelsindexstart", i_nltestart.data(), nions);
+  s.arr("ion.ionpot", i_ionpot.data(), nions);
+
+  // levels
+  const auto& lv = globals::alllevels;
+  const int64_t nlev = get_includedlevels();
+  s.arr("level.epsilon", lv.epsilon.data(), nlev);
+  s.arr("level.statweight", lv.statweight.data(), nlev);
+  s.arr("level.alltrans_startdown", lv.alltrans_startdown.data(), nlev);
+  s.arr("level.ndowntrans", lv.ndowntrans.data(), nlev);
+  s.arr("level.nuptrans", lv.nuptrans.data(), nlev);
+  s.arr("level.closestgroundlevelcont", lv.closestgroundlevelcont.data(), nlev);
+  s.arr("level.phixsstart", lv.phixsstart.data(), nlev);
+  s.arr("level.nphixstargets", lv.nphixstargets.data(), nlev);
+  s.arr("level.phixstargetstart", lv.phixstargetstart.data(), nlev);
+  s.arr("level.bflist_start", lv.bflist_start.data(), nlev);
+  s.arr("level.matransblock_start", lv.matransblock_start.data(), nlev);
+
+  // transitions (per level: [down...][up...])
+  const auto& tr = globals::alltrans;
+  const auto ntrans = static_cast<int64_t>(tr.lineindex.size());
+  s.arr("trans.lineindex", tr.lineindex.data(), ntrans);
+  s.arr("trans.targetlevelindex", tr.targetlevelindex.data(), ntrans);
+  s.arr("trans.einstein_A", tr.einstein_A.data(), ntrans);
+  s.arr("trans.coll_str", tr.coll_str.data(), ntrans);
+  s.arr("trans.osc_strength", tr.osc_strength.data(), ntrans);
+  s.arr("trans.forbidden", tr.forbidden.data(), ntrans);
+
+  // line list (descending nu)
+  const auto& ll = globals::linelist;
+  const int64_t nlines = globals::nlines;
+  s.arr("line.nu", ll.nu.data(), nlines);
+  s.arr("line.elementindex", ll.elementindex.data(), nlines);
+  s.arr("line.ionindex", ll.ionindex.data(), nlines);
+  s.arr("line.lower", ll.uniquelevelindex_lower.data(), nlines);
+  s.arr("line.upper", ll.uniquelevelindex_upper.data(), nlines);
+  s.arr("line.B_ul", ll.B_ul.data(), nlines);
+  s.arr("line.B_lu", ll.B_lu.data(), nlines);
+
+  // bound-free continua (ascending nu_edge)
+  const auto& ac = globals::allcont;
+  const int64_t nbf = globals::nbfcontinua;
+  s.arr("cont.nu_edge", ac.nu_edge.data(), nbf);
+  s.arr("cont.element", ac.element.data(), nbf);
+  s.arr("cont.ion", ac.ion.data(), nbf);
+  s.arr("cont.level", ac.level.data(), nbf);
+  s.arr("cont.phixstargetindex", ac.phixstargetindex.data(), nbf);
+  s.arr("cont.upperlevel", ac.upperlevel.data(), nbf);
+  s.arr("cont.uniquelevelindex", ac.uniquelevelindex.data(), nbf);
+  s.arr("cont.probability", ac.probability.data(), nbf);
+  s.arr("cont.groundcontestimindex", ac.groundcontestimindex.data(), nbf);
+  s.arr("cont.bfestimindex", ac.bfestimindex.data(), nbf);
+
+  s.arr("phixs.table", globals::allphixs.data(), static_cast<int64_t>(globals::allphixs.size()));
+  s.arr("phixstarget.levelindex", globals::allphixstargets_levelindex.data(),
+        static_cast<int64_t>(globals::allphixstargets_levelindex.size()));
+  s.arr("phixstarget.probability", globals::allphixstargets_probability.data(),
+        static_cast<int64_t>(globals::allphixstargets_probability.size()));
+  s.arr("groundcont.nu_edge", globals::groundcont_nu_edge.data(), static_cast<int64_t>(globals::groundcont_nu_edge.size()));
+  s.arr("bfestim.nu_edge", globals::bfestim_nu_edge.data(), static_cast<int64_t>(globals::bfestim_nu_edge.size()));
+
+  const auto lut_sp = b200_lut_spontrecombcoeffs();
+  const auto lut_cp = b200_lut_corrphotoioncoeffs();
+  const auto lut_bc = b200_lut_bfcooling_coeffs();
+  const auto lut_tg = b200_lut_temperature_grid();
+  s.arr("lut.spontrecomb", lut_sp.data(), static_cast<int64_t>(lut_sp.size()));
+  s.arr("lut.corrphotoion", lut_cp.data(), static_cast<int64_t>(lut_cp.size()));
+  s.arr("lut.bfcooling", lut_bc.data(), static_cast<int64_t>(lut_bc.size()));
+  s.arr("lut.temperature_grid", lut_tg.data(), static_cast<int64_t>(lut_tg.size()));
+
+  const int ncool = kpkt::ncoolingterms;
+  std::vector<unsigned char> c_type(ncool);
+  std::vector<int> c_level(ncool);
+  std::vector<int> c_target(ncool);
+  for (int i = 0; i < ncool; i++) {
+    c_type[i] = static_cast<unsigned char>(kpkt::b200_coolinglist_type(i));
+    c_level[i] = kpkt::b200_coolinglist_level(i);
+    c_target[i] = kpkt::b200_coolinglist_phixstargetindex(i);
+  }
+  s.arr("cooling.type", c_type.data(), ncool);
+  s.arr("cooling.level", c_level.data(), ncool);
+  s.arr("cooling.phixstargetindex", c_target.data(), ncool);
+
+  const auto nts_total = static_cast<int64_t>(globals::timesteps.size());
+  std::vector<double> t_start(nts_total);
+  std::vector<double> t_width(nts_total);
+  std::vector<double> t_mid(nts_total);
+  for (int64_t i = 0; i < nts_total; i++) {
+    t_start[i] = globals::timesteps[i].start;
+    t_width[i] = globals::timesteps[i].width;
+    t_mid[i] = globals::timesteps[i].mid;
+  }
+  s.arr("timesteps.start", t_start.data(), nts_total);
+  s.arr("timesteps.width", t_width.data(), nts_total);
+  s.arr("timesteps.mid", t_mid.data(), nts_total);
+}
+
+template <class Sink>
+void emit_timestep_state(Sink& s, const int nts) {
+  const int64_t nc = grid::get_nonempty_npts_model();
+  s.i64("scalar.nts", nts);
+  s.i64("scalar.globals_timestep", globals::timestep);
+  s.f64("scalar.max_path_step", globals::max_path_step);
+  s.arr("cell.rho", grid::rho_allcells.data(), nc);
+  s.arr("cell.Te", grid::Te_allcells.data(), nc);
+  s.arr("cell.TJ", grid::TJ_allcells.data(), nc);
+  s.arr("cell.TR", grid::TR_allcells.data(), nc);
+  s.arr("cell.W", grid::W_allcells.data(), nc);
+  s.arr("cell.nne", grid::nne_allcells.data(), nc);
+  s.arr("cell.nnetot", grid::nnetot_allcells.data(), nc);
+  s.arr("cell.kappagrey", grid::kappagrey_allcells.data(), nc);
+  static_assert(sizeof(grid::CellThickness) == sizeof(int));
+  s.arr("cell.thick", reinterpret_cast<const int*>(grid::thick_allcells.data()), nc);
+  std::vector<float> clump(nc);
+  for (int64_t i = 0; i < nc; i++) {
+    clump[i] = grid::get_clumpfactor(static_cast<int>(i));
+  }
+  s.arr("cell.clumpfactor", clump.data(), nc);
+  s.arr("cell.elem_massfracs", grid::elem_massfracs_allcells.data(),
+        static_cast<int64_t>(grid::elem_massfracs_allcells.size()));
+  s.arr("cell.ion_groundlevelpops", grid::ion_groundlevelpops_allcells.data(),
+        static_cast<int64_t>(grid::ion_groundlevelpops_allcells.size()));
+  s.arr("cell.ion_partfuncts", grid::ion_partfuncts_allcells.data(),
+        static_cast<int64_t>(grid::ion_partfuncts_allcells.size()));
+  s.arr("cell.ion_cooling_contribs", kpkt::ion_cooling_contribs_allcells.data(),
+        static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
+  s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
+        static_cast<int64_t>(globals::corrphotoionrenorm.size()));
+}
+
+void fill_ts_scalars(const int nts, double* out) {
+  const auto& ts = globals::timesteps[nts];
+  out[ARTISB200_TS_GAMMA_DEP_DISCRETE] = ts.gamma_dep_discrete;
+  out[ARTISB200_TS_POSITRON_DEP_DISCRETE] = ts.positron_dep_discrete;
+  out[ARTISB200_TS_POSITRON_EMISSION] = ts.positron_emission;
+  out[ARTISB200_TS_ELECTRON_DEP_DISCRETE] = ts.electron_dep_discrete;
+  out[ARTISB200_TS_ELECTRON_EMISSION] = ts.electron_emission;
+  out[ARTISB200_TS_ALPHA_DEP_DISCRETE] = ts.alpha_dep_discrete;
+  out[ARTISB200_TS_ALPHA_EMISSION] = ts.alpha_emission;
+  out[ARTISB200_TS_SPFISSION_DEP_DISCRETE] = ts.spfission_dep_discrete;
+  out[ARTISB200_TS_GAMMA_EMISSION] = ts.gamma_emission;
+  out[ARTISB200_TS_NT_ENERGY_DEPOSITED] = 0.;  // nonthermal.cc:200 is file-static and only logged
+}
+
+template <class Sink>
+void emit_estimators(Sink& s, const int nts) {
+  const auto j = radfield::b200_J();
+  const auto nuj = radfield::b200_nuJ();
+  s.arr("est.J", j.data(), static_cast<int64_t>(j.size()));
+  s.arr("est.nuJ", nuj.data(), static_cast<int64_t>(nuj.size()));
+  s.arr("est.ffheating", globals::ffheatingestimator.data(), static_cast<int64_t>(globals::ffheatingestimator.size()));
+  s.arr("est.colheating", globals::colheatingestimator.data(), static_cast<int64_t>(globals::colheatingestimator.size()));
+  s.arr("est.gamma", globals::gammaestimator.data(), static_cast<int64_t>(globals::gammaestimator.size()));
+  s.arr("est.bfheating", globals::bfheatingestimator.data(), static_cast<int64_t>(globals::bfheatingestimator.size()));
+  s.arr("est.dep_gamma", globals::dep_estimator_gamma.data(), static_cast<int64_t>(globals::dep_estimator_gamma.size()));
+  s.arr("est.dep_positron", globals::dep_estimator_positron.data(), static_cast<int64_t>(globals::dep_estimator_positron.size()));
+  s.arr("est.dep_electron", globals::dep_estimator_electron.data(), static_cast<int64_t>(globals::dep_estimator_electron.size()));
+  s.arr("est.dep_alpha", globals::dep_estimator_alpha.data(), static_cast<int64_t>(globals::dep_estimator_alpha.size()));
+  double tss[ARTISB200_NTSSCALARS];
+  fill_ts_scalars(nts, tss);
+  s.arr("ts.scalars", tss, ARTISB200_NTSSCALARS);
+  s.i64("ts.pellet_decays", globals::timesteps[nts].pellet_decays);
+  int64_t counters[static_cast<int>(stats::Counter::COUNT)];
+  for (int i = 0; i < static_cast<int>(stats::Counter::COUNT); i++) {
+    counters[i] = stats::get_counter(static_cast<stats::Counter>(i));
+  }
+  s.arr("counters", counters, static_cast<int>(stats::Counter::COUNT));
+}
+
+template <class Sink>
+void emit_packets(Sink& s, const std::span<const Packet> packets) {
+  s.i64("packets.count", static_cast<int64_t>(packets.size()));
+  s.i64("packets.stride", static_cast<int64_t>(sizeof(Packet)));
+  s.arr("packets.aos", reinterpret_cast<const unsigned char*>(packets.data()),
+        static_cast<int64_t>(packets.size() * sizeof(Packet)));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the library, loaded at run time
+// ---------------------------------------------------------------------------------------------------
+
+struct Lib {
+  void* handle{nullptr};
+  decltype(&artisb200_create) create{};
+  decltype(&artisb200_last_error) last_error{};
+  decltype(&artisb200_set_array) set_array{};
+  decltype(&artisb200_get_array) get_array{};
+  decltype(&artisb200_array_count) array_count{};
+  decltype(&artisb200_set_option) set_option{};
+  decltype(&artisb200_commit_static) commit_static{};
+  decltype(&artisb200_begin_timestep) begin_timestep{};
+  decltype(&artisb200_update_packets_host) update_packets_host{};
+  decltype(&artisb200_last_timing_ms) last_timing_ms{};
+  decltype(&artisb200_options_summary) options_summary{};
+  artisb200_ctx* ctx{nullptr};
+};
+
+Lib lib;
+
+template <class F>
+void load_symbol(F& fn, const char* name) {
+  fn = reinterpret_cast<F>(dlsym(lib.handle, name));
+  if (fn == nullptr) {
+    printlnlog("[fatal] artis_b200: symbol {} missing from library", name);
+    std::abort();
+  }
+}
+
+void check(const int rc, const char* what) {
+  if (rc != 0) {
+    // same convention as assert_always (mpi_logging.h:123-130): log, then abort
+    printlnlog("[fatal] artis_b200: {} failed: {}", what, lib.last_error(lib.ctx));
+    std::fprintf(stderr, "[fatal] artis_b200: %s failed: %s\n", what, lib.last_error(lib.ctx));
+    std::abort();
+  }
+}
+
+struct LibSink {
+  template <class T>
+  void arr(const char* name, const T* data, const int64_t count) {
+    check(lib.set_array(lib.ctx, name, b200::dtype_of<T>::code, data, count), name);
+  }
+  void f64(const char* name, const double v) { arr(name, &v, 1); }
+  void i64(const char* name, const int64_t v) { arr(name, &v, 1); }
+};
+
+auto env_or(const char* name, const char* fallback) -> std::string {
+  const char* v = std::getenv(name);
+  return (v != nullptr) ? std::string(v) : std::string(fallback);
+}
+
+void lib_init() {
+  const auto path = env_or("ARTISB200_LIB", "libartis_b200.so");
+  lib.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (lib.handle == nullptr) {
+    printlnlog("[fatal] artis_b200: cannot load {}: {}", path, dlerror());
+    std::fprintf(stderr, "[fatal] artis_b200: cannot load %s\n", path.c_str());
+    std::abort();
+  }
+  load_symbol(lib.create, "artisb200_create");
+  load_symbol(lib.last_error, "artisb200_last_error");
+  load_symbol(lib.set_array, "artisb200_set_array");
+  load_symbol(lib.get_array, "artisb200_get_array");
+  load_symbol(lib.array_count, "artisb200_array_count");
+  load_symbol(lib.set_option, "artisb200_set_option");
+  load_symbol(lib.commit_static, "artisb200_commit_static");
+  load_symbol(lib.begin_timestep, "artisb200_begin_timestep");
+  load_symbol(lib.update_packets_host, "artisb200_update_packets_host");
+  load_symbol(lib.last_timing_ms, "artisb200_last_timing_ms");
+  load_symbol(lib.options_summary, "artisb200_options_summary");
+
+  const int device = std::atoi(env_or("ARTISB200_DEVICE", env_or("LOCAL_RANK", "0").c_str()).c_str());
+  if (lib.create(&lib.ctx, device) != 0) {
+    printlnlog("[fatal] artis_b200: create failed: {}", lib.last_error(nullptr));
+    std::fprintf(stderr, "[fatal] artis_b200: create failed: %s\n", lib.last_error(nullptr));
+    std::abort();
+  }
+  printlnlog("artis_b200: library {} on device {} options [{}]", path, device, lib.options_summary());
+  const bool xoshiro = env_or("ARTISB200_RNG", "philox") == "xoshiro";
+#ifndef GPU_ON
+  if (xoshiro) {
+    printlnlog("[fatal] artis_b200: ARTISB200_RNG=xoshiro needs a -DGPU_ON host build (per-packet rngstate)");
+    std::abort();
+  }
+#endif
+  check(lib.set_option(lib.ctx, "rng_mode", xoshiro ? ARTISB200_RNG_XOSHIRO : ARTISB200_RNG_PHILOX), "rng_mode");
+  check(lib.set_option(lib.ctx, "rank", globals::my_rank), "rank");
+  check(lib.set_option(lib.ctx, "nranks", globals::nprocs), "nranks");
+  check(lib.set_option(lib.ctx, "max_steps_per_launch", std::atoll(env_or("ARTISB200_MAXSTEPS", "-1").c_str())),
+        "max_steps_per_launch");
+  LibSink sink;
+  emit_static(sink);
+  check(lib.commit_static(lib.ctx), "commit_static");
+}
+
+template <class T>
+void fetch_add(const char* name, std::span<T> dest) {
+  if (dest.empty()) {
+    return;
+  }
+  static std::vector<T> tmp;
+  tmp.resize(dest.size());
+  check(lib.get_array(lib.ctx, name, b200::dtype_of<T>::code, tmp.data(), static_cast<int64_t>(dest.size())), name);
+  for (size_t i = 0; i < dest.size(); i++) {
+    dest[i] += tmp[i];
+  }
+}
+
+void update_packets_gpu(const int nts, std::span<Packet> packets) {
+  if (lib.ctx == nullptr) {
+    lib_init();
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  LibSink sink;
+  emit_timestep_state(sink, nts);
+  check(lib.begin_timestep(lib.ctx, nts), "begin_timestep");
+  check(lib.update_packets_host(lib.ctx, nts, packets.data(), static_cast<int64_t>(packets.size()),
+                                static_cast<int>(sizeof(Packet))),
+        "update_packets_host");
+
+  // fold the device estimators into the (zeroed, sn3d.cc:718) host estimators
+  fetch_add<double>("est.J", radfield::b200_J());
+  fetch_add<double>("est.nuJ", radfield::b200_nuJ());
+  fetch_add<double>("est.ffheating", globals::ffheatingestimator);
+  fetch_add<double>("est.colheating", globals::colheatingestimator);
+  fetch_add<double>("est.gamma", globals::gammaestimator);
+  fetch_add<double>("est.bfheating", globals::bfheatingestimator);
+  fetch_add<double>("est.dep_gamma", globals::dep_estimator_gamma);
+  fetch_add<double>("est.dep_positron", globals::dep_estimator_positron);
+  fetch_add<double>("est.dep_electron", globals::dep_estimator_electron);
+  fetch_add<double>("est.dep_alpha", globals::dep_estimator_alpha);
+  double tss[ARTISB200_NTSSCALARS];
+  check(lib.get_array(lib.ctx, "ts.scalars", 'd', tss, ARTISB200_NTSSCALARS), "ts.scalars");
+  auto& ts = globals::timesteps[nts];
+  ts.gamma_dep_discrete += tss[ARTISB200_TS_GAMMA_DEP_DISCRETE];
+  ts.positron_dep_discrete += tss[ARTISB200_TS_POSITRON_DEP_DISCRETE];
+  ts.positron_emission += tss[ARTISB200_TS_POSITRON_EMISSION];
+  ts.electron_dep_discrete += tss[ARTISB200_TS_ELECTRON_DEP_DISCRETE];
+  ts.electron_emission += tss[ARTISB200_TS_ELECTRON_EMISSION];
+  ts.alpha_dep_discrete += tss[ARTISB200_TS_ALPHA_DEP_DISCRETE];
+  ts.alpha_emission += tss[ARTISB200_TS_ALPHA_EMISSION];
+  ts.spfission_dep_discrete += tss[ARTISB200_TS_SPFISSION_DEP_DISCRETE];
+  ts.gamma_emission += tss[ARTISB200_TS_GAMMA_EMISSION];
+  int64_t pellet_decays = 0;
+  check(lib.get_array(lib.ctx, "ts.pellet_decays", 'q', &pellet_decays, 1), "ts.pellet_decays");
+  ts.pellet_decays += static_cast<int>(pellet_decays);
+  int64_t counters[static_cast<int>(stats::Counter::COUNT)];
+  check(lib.get_array(lib.ctx, "counters", 'q', counters, static_cast<int>(stats::Counter::COUNT)), "counters");
+  for (int i = 0; i < static_cast<int>(stats::Counter::COUNT); i++) {
+    stats::b200_add_counter(i, counters[i]);
+  }
+  double total_ms = 0.;
+  double prop_ms = 0.;
+  double sched_ms = 0.;
+  lib.last_timing_ms(lib.ctx, &total_ms, &prop_ms, &sched_ms);
+  const auto wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  stats::pkt_action_counters_printout(nts);
+  printlnlog(
+      "timestep {}: finished update_packets for rank {} on B200 (took {:.3f} seconds wall; device {:.3f} ms total, "
+      "{:.3f} ms propagate, {:.3f} ms schedule)",
+      nts, globals::my_rank, wall, total_ms, prop_ms, sched_ms);
+}
+
+#ifdef ARTISB200_WITH_REFERENCE
+// Reference physics in an order-independent schedule: every packet is run through the reference's own
+// do_packet() (update_packets.cc:257) from the start to the end of the timestep with its own fresh
+// continuum-opacity cache. With the GPU_ON build (per-packet RNG state, every cell's cache slot
+// precomputed, update_packets.cc:551-563) a packet's history then depends on nothing but the packet
+// itself, which is what makes packet-by-packet comparison with the device path possible.
+void update_packets_reference_perpacket(const int nts, std::span<Packet> packets) {
+  static_assert(!cellcache_singleslot, "the per-packet oracle schedule needs the GPU_ON (multi-slot cell cache) build");
+  const double ts_end = globals::timesteps[nts].start + globals::timesteps[nts].width;
+  const auto nonempty_npts_model = grid::get_nonempty_npts_model();
+  for (int nonemptymgi = 0; nonemptymgi < nonempty_npts_model; nonemptymgi++) {
+    cellcacheslot_populate(globals::cellcache.at(nonemptymgi), nonemptymgi);
+  }
+  for (auto& pkt : packets) {
+    ContinuumOpacity chi_rpkt_cont{};
+    while (packetprop_update_required(pkt, ts_end)) {
+      do_packet(pkt, ts_end, nts, chi_rpkt_cont);
+    }
+  }
+  stats::pkt_action_counters_printout(nts);
+}
+#endif
+
+auto dump_requested(const int nts) -> bool {
+  const char* dir = std::getenv("ARTISB200_DUMP_DIR");
+  if (dir == nullptr) {
+    return false;
+  }
+  const auto list = env_or("ARTISB200_DUMP_TS", "all");
+  if (list == "all") {
+    return true;
+  }
+  const std::string needle = "," + std::to_string(nts) + ",";
+  return ("," + list + ",").find(needle) != std::string::npos;
+}
+
+}  // anonymous namespace
+
+void update_packets(const int nts, std::span<Packet> packets) {
+#ifdef ARTISB200_WITH_REFERENCE
+  const auto mode = env_or("ARTISB200_MODE", "ref");
+#else
+  const auto mode = env_or("ARTISB200_MODE", "gpu");
+#endif
+  const bool dump = dump_requested(nts);
+  const auto dumpdir = env_or("ARTISB200_DUMP_DIR", ".");
+  if (dump) {
+    static bool static_written = false;
+    if (!static_written) {
+      b200::SnapshotWriter w(dumpdir + "/static.abt");
+      emit_static(w);
+      static_written = true;
+    }
+    b200::SnapshotWriter w(dumpdir + "/ts" + std::to_string(nts) + "_before.abt");
+    emit_timestep_state(w, nts);
+    emit_packets(w, packets);
+    emit_estimators(w, nts);  // the pre-existing (normally zero) values, so that "after - before" is this call's work
+  }
+
+  const auto t0 = std::chrono::steady_clock::now();
+  if (mode == "gpu") {
+    update_packets_gpu(nts, packets);
+#ifdef ARTISB200_WITH_REFERENCE
+  } else if (mode == "ref") {
+    update_packets_reference_impl(nts, packets);
+  } else if (mode == "ref_perpacket") {
+    update_packets_reference_perpacket(nts, packets);
+#endif
+  } else {
+    printlnlog("[fatal] artis_b200: unknown ARTISB200_MODE '{}' for this build", mode);
+    std::abort();
+  }
+  const auto wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // machine-readable line used by bench.py's cpu_baseline / reference arm
+  printlnlog("ARTISB200_TIMING nts {} mode {} npackets {} wall_s {:.6f} interactions {}", nts, mode, packets.size(), wall,
+             stats::get_counter(stats::Counter::INTERACTIONS));
+
+  if (dump) {
+    b200::SnapshotWriter w(dumpdir + "/ts" + std::to_string(nts) + "_after.abt");
+    emit_packets(w, packets);
+    emit_estimators(w, nts);
+  }
+  MPI_Barrier_allranks();  // update_packets.cc:631
+}

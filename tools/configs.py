@@ -1,0 +1,97 @@
+"""Named synthetic workloads (BASELINE.json `configs`, plus toy-sized variants for parity tests).
+
+Every config names the reference preset (`artisoptions_<preset>.h`), the compile-time option
+overrides applied to it (the same `sed` edits the reference's tests/setup_*.sh scripts make,
+e.g. tests/setup_classicmode_1d_3dgrid.sh:27-34), and the parameters of the synthetic model and
+atomic data that tools/gen_inputs.py writes in the reference's input file formats
+(SURVEY.md Appendix B).
+"""
+
+# option override -> replacement source line (matched on the declaration prefix before '=' / ';')
+def _opts(mpkts, grid_override=None, cuboid=None, extra=None):
+    o = {"constexpr int MPKTS": f"constexpr int MPKTS = {int(mpkts)};"}
+    if grid_override:
+        o["constexpr std::optional<GridType> GRID_TYPE_OVERRIDE"] = (
+            f"constexpr std::optional<GridType> GRID_TYPE_OVERRIDE = GridType::{grid_override};"
+        )
+    if cuboid:
+        for ax in "XYZ":
+            o[f"constexpr int CUBOID_NCOORDGRID_{ax}"] = f"constexpr int CUBOID_NCOORDGRID_{ax} = {int(cuboid)};"
+    if extra:
+        o.update(extra)
+    return o
+
+
+_FEGROUP = [(26, 55.845), (27, 58.9332), (28, 58.6934)]
+_CLASSIC_ELEMS = [(8, 15.999), (14, 28.085), (16, 32.06), (20, 40.078), (26, 55.845), (27, 58.9332), (28, 58.6934)]
+_KN_ELEMS = [(26, 55.845), (38, 87.62), (58, 140.116), (60, 144.242), (92, 238.029)]
+
+CONFIGS = {
+    # ---- toy-sized parity cases (run in seconds on one CPU core) -------------------------------
+    "classic_toy": dict(
+        preset="classic",
+        opts=_opts(4000, "CARTESIAN3D", 20),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=1e-12, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+    ),
+    "classic_toy_1d": dict(
+        preset="classic",
+        opts=_opts(4000),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=1e-12, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+    ),
+    "kilonova_toy": dict(
+        preset="kilonova_lte",
+        opts=_opts(4000, None, None, {
+            "constexpr int TABLESIZE": "constexpr int TABLESIZE = 20;",
+            "constexpr double MINTEMP": "constexpr double MINTEMP = 1000.;",
+            "constexpr double MAXTEMP": "constexpr double MAXTEMP = 20000.;",
+        }),
+        atomic=dict(elements=_KN_ELEMS, nions=3, nlevels=8, trans_frac=0.6, seed=2),
+        model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
+        run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
+    ),
+    "classic3d_toy": dict(
+        preset="classic",
+        opts=_opts(4000),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="3d", n=10, vmax_kmps=20000.0, t_model_days=2.0, mass_msun=1.0, seed=3),
+        run=dict(seed=10, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+    ),
+    # ---- BASELINE.json configs (bench-sized) ----------------------------------------------------
+    # configs[0]: classic LTE W7-like 1D model on a 3D grid, 1e5 packets
+    "classic_1d3d": dict(
+        preset="classic",
+        opts=_opts(100000, "CARTESIAN3D", 100),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, seed=20260101),
+        model=dict(kind="1d", ncell=100, vmax_kmps=25000.0, t_model_days=2.0, rho0=None, mass_msun=1.4,
+                   v_e_kmps=2700.0, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=12, thick=8.0, ngrey=3, nlte_ts=5),
+    ),
+    # configs[1]: kilonova LTE 2D cylindrical r-process ejecta, 1e7 packets  (the bench workload)
+    "kilonova_2d": dict(
+        preset="kilonova_lte",
+        opts=_opts(10000000),
+        atomic=dict(elements=_KN_ELEMS, nions=4, nlevels=60, trans_frac=0.15, seed=20260101),
+        model=dict(kind="2d", nr=50, nz=100, vmax_c=0.3, t_model_days=0.1, mass_msun=0.02, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=40, tmin=0.1, tmax=10.0, nts_run=16, thick=0.0, ngrey=2, nlte_ts=999),
+    ),
+    # reduced packet count variant of configs[1] used for CPU-side parity and the cpu_baseline sample
+    "kilonova_2d_small": dict(
+        preset="kilonova_lte",
+        opts=_opts(200000),
+        atomic=dict(elements=_KN_ELEMS, nions=4, nlevels=60, trans_frac=0.15, seed=20260101),
+        model=dict(kind="2d", nr=50, nz=100, vmax_c=0.3, t_model_days=0.1, mass_msun=0.02, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=40, tmin=0.1, tmax=10.0, nts_run=16, thick=0.0, ngrey=2, nlte_ts=999),
+    ),
+}
+
+
+def get(name):
+    if name not in CONFIGS:
+        raise KeyError(f"unknown config {name!r}; known: {sorted(CONFIGS)}")
+    c = dict(CONFIGS[name])
+    c["name"] = name
+    return c
