@@ -1,0 +1,405 @@
+// CUDA backend (sm_100a) and C ABI of the B200 packet-propagation library.
+//
+// Kernels
+//   k_propagate        one thread per packet history, persistent grid (a multiple of the SM count) with a
+//                      per-thread dynamic work fetch so that lanes whose packet finishes early pick up the next
+//                      one; event counters / timestep scalars are accumulated thread-privately, reduced per block
+//                      in shared memory and flushed with one global atomic per block and counter.
+//   k_build_*          the per-cell tables (level populations, continuum keep-bitmaps, macro-atom cumulative
+//                      rates, cooling contributions): one work item per (cell, level | ion | 64 continua).
+//   k_aos_to_soa / k_soa_to_aos   the reference's 240/256-byte Packet <-> SoA.
+// There is no host execution path in this library: artisb200_create() fails without a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "convert.h"
+#include "engine.h"
+#include "propagate.h"
+
+namespace {
+
+using ab::Tables;
+
+constexpr int PROP_BLOCK = 128;
+
+__global__ void k_aos_to_soa(const __grid_constant__ Tables T, const unsigned char* aos, const long long n, const int stride) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::aos_to_soa_one(T, aos, stride, i);
+  }
+}
+
+__global__ void k_soa_to_aos(const __grid_constant__ Tables T, unsigned char* aos, const long long n, const int stride) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::soa_to_aos_one(T, aos, stride, i);
+  }
+}
+
+__global__ void k_reset_philox(const __grid_constant__ Tables T, const long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::reset_philox_one(T, i);
+  }
+}
+
+__global__ void k_build_levelpops(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  if (idx < total) {
+    ab::build_levelpop_item(T, static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+  }
+}
+
+__global__ void k_build_percell_misc(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  if (idx < total) {
+    const int cell = static_cast<int>(idx / T.nlevels);
+    const int ulev = static_cast<int>(idx % T.nlevels);
+    ab::build_corrphotoion_item(T, cell, ulev);
+    if (ulev == 0) {
+      T.cell_chi_ff_nnionpart[cell] = ab::calculate_chi_ffheat_nnionpart(T, cell);
+    }
+  }
+}
+
+__global__ void k_build_keepwords(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.ncells) * T.keepwords;
+  if (idx < total) {
+    ab::build_keepword_item(T, static_cast<int>(idx / T.keepwords), static_cast<int>(idx % T.keepwords));
+  }
+}
+
+__global__ void k_build_macroatom(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  if (idx < total) {
+    ab::build_macroatom_level(T, static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+  }
+}
+
+__global__ void k_build_cooling(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.ncells) * T.nions;
+  if (idx < total) {
+    ab::build_cooling_ion(T, static_cast<int>(idx / T.nions), static_cast<int>(idx % T.nions));
+  }
+}
+
+// queue[0]: next packet index to hand out; queue[1]: packets that still need work after this launch
+__global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const long long n,
+                                                          unsigned long long* queue) {
+  __shared__ unsigned long long s_cnt[ab::CNT_COUNT];
+  __shared__ unsigned long long s_diag[ab::NDIAG];
+  __shared__ double s_tss[ab::NTSSCALARS];
+  __shared__ unsigned long long s_misc[2];  // pellet decays, still-active packets
+  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
+    s_cnt[k] = 0ULL;
+  }
+  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
+    s_diag[k] = 0ULL;
+  }
+  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
+    s_tss[k] = 0.;
+  }
+  if (threadIdx.x < 2) {
+    s_misc[threadIdx.x] = 0ULL;
+  }
+  __syncthreads();
+
+  int cnt[ab::CNT_COUNT];
+  long long diag[ab::NDIAG];
+  double tss[ab::NTSSCALARS];
+  long long pellet_decays = 0;
+  long long still_active = 0;
+#pragma unroll
+  for (int k = 0; k < ab::CNT_COUNT; k++) {
+    cnt[k] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < ab::NDIAG; k++) {
+    diag[k] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < ab::NTSSCALARS; k++) {
+    tss[k] = 0.;
+  }
+
+  const long long tid = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const double ts_end = T.ts_end;
+  while (true) {
+    const long long i = static_cast<long long>(atomicAdd(&queue[0], 1ULL));
+    if (i >= n) {
+      break;
+    }
+    if (T.pkt.type[i] == ab::TYPE_ESCAPE || !(T.pkt.prop_time[i] < ts_end)) {
+      continue;
+    }
+    ab::Pkt p;
+    ab::load_pkt(p, T, i);
+    const ab::Ctx c{T, i, tid, cnt, diag, tss, &pellet_decays};
+    diag[ab::DIAG_PACKET_SEGMENTS]++;
+    if (ab::propagate_packet(p, c, T.max_steps_per_launch)) {
+      still_active++;
+    }
+    ab::store_pkt(p, T, i);
+  }
+
+  // block-level reduction in shared memory, then one global atomic per block and counter
+  for (int k = 0; k < ab::CNT_COUNT; k++) {
+    if (cnt[k] != 0) {
+      atomicAdd(&s_cnt[k], static_cast<unsigned long long>(cnt[k]));
+    }
+  }
+  for (int k = 0; k < ab::NDIAG; k++) {
+    if (diag[k] != 0) {
+      atomicAdd(&s_diag[k], static_cast<unsigned long long>(diag[k]));
+    }
+  }
+  for (int k = 0; k < ab::NTSSCALARS; k++) {
+    if (tss[k] != 0.) {
+      atomicAdd(&s_tss[k], tss[k]);
+    }
+  }
+  if (pellet_decays != 0) {
+    atomicAdd(&s_misc[0], static_cast<unsigned long long>(pellet_decays));
+  }
+  if (still_active != 0) {
+    atomicAdd(&s_misc[1], static_cast<unsigned long long>(still_active));
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
+    if (s_cnt[k] != 0ULL) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&T.counters[k]), s_cnt[k]);
+    }
+  }
+  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
+    if (s_diag[k] != 0ULL) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&T.diag[k]), s_diag[k]);
+    }
+  }
+  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
+    if (s_tss[k] != 0.) {
+      atomicAdd(&T.ts_scalars[k], s_tss[k]);
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (s_misc[0] != 0ULL) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(T.ts_pellet_decays), s_misc[0]);
+    }
+    if (s_misc[1] != 0ULL) {
+      atomicAdd(&queue[1], s_misc[1]);
+    }
+  }
+}
+
+struct CudaBackend {
+  std::string error;
+  int device{-1};
+  int sm_count{0};
+  cudaStream_t stream{nullptr};
+  cudaEvent_t ev_start{nullptr};
+  cudaEvent_t ev_stop{nullptr};
+  unsigned long long* d_queue{nullptr};
+  double* d_scratch{nullptr};
+  long long scratch_elems{0};
+
+  bool ok(const cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+      error = std::string(what) + ": " + cudaGetErrorString(e);
+      return false;
+    }
+    return true;
+  }
+
+  bool init(const int device_ordinal) {
+    int ndev = 0;
+    if (!ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev <= 0) {
+      if (error.empty()) {
+        error = "no CUDA device available (this library has no CPU execution path)";
+      }
+      return false;
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) {
+      error = "device ordinal " + std::to_string(device_ordinal) + " out of range (" + std::to_string(ndev) + " devices)";
+      return false;
+    }
+    device = device_ordinal;
+    if (!ok(cudaSetDevice(device), "cudaSetDevice")) {
+      return false;
+    }
+    cudaDeviceProp prop{};
+    if (!ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
+      return false;
+    }
+    sm_count = prop.multiProcessorCount;
+    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+      return false;
+    }
+    if (!ok(cudaEventCreate(&ev_start), "cudaEventCreate") || !ok(cudaEventCreate(&ev_stop), "cudaEventCreate")) {
+      return false;
+    }
+    if (!ok(cudaMalloc(&d_queue, 2 * sizeof(unsigned long long)), "cudaMalloc(queue)")) {
+      return false;
+    }
+    return true;
+  }
+
+  void shutdown() {
+    if (device >= 0) {
+      cudaSetDevice(device);
+      cudaStreamSynchronize(stream);
+      cudaFree(d_queue);
+      cudaFree(d_scratch);
+      cudaEventDestroy(ev_start);
+      cudaEventDestroy(ev_stop);
+      cudaStreamDestroy(stream);
+    }
+  }
+
+  std::string last_error() const { return error; }
+  void* stream_handle() { return stream; }
+
+  void* alloc(const int64_t nbytes) {
+    cudaSetDevice(device);
+    void* p = nullptr;
+    if (!ok(cudaMalloc(&p, static_cast<size_t>(nbytes)), "cudaMalloc")) {
+      return nullptr;
+    }
+    return p;
+  }
+  void free(void* p) {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(stream);
+    cudaFree(p);
+  }
+  bool h2d(void* d, const void* h, const int64_t n) {
+    cudaSetDevice(device);
+    return ok(cudaMemcpyAsync(d, h, static_cast<size_t>(n), cudaMemcpyHostToDevice, stream), "cudaMemcpy H2D") &&
+           ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  }
+  bool d2h(void* h, const void* d, const int64_t n) {
+    cudaSetDevice(device);
+    return ok(cudaMemcpyAsync(h, d, static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream), "cudaMemcpy D2H") &&
+           ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  }
+  bool d2d(void* dst, const void* src, const int64_t n) {
+    cudaSetDevice(device);
+    return ok(cudaMemcpyAsync(dst, src, static_cast<size_t>(n), cudaMemcpyDeviceToDevice, stream), "cudaMemcpy D2D");
+  }
+  void zero(void* d, const int64_t n) {
+    cudaSetDevice(device);
+    cudaMemsetAsync(d, 0, static_cast<size_t>(n), stream);
+  }
+
+  static unsigned int blocks_for(const long long n, const int block) { return static_cast<unsigned int>((n + block - 1) / block); }
+
+  bool build_cell_tables(const Tables& T) {
+    cudaSetDevice(device);
+    constexpr int B = 128;
+    const long long ncl = static_cast<long long>(T.ncells) * T.nlevels;
+    if (ncl > 0) {
+      k_build_levelpops<<<blocks_for(ncl, B), B, 0, stream>>>(T);
+      k_build_percell_misc<<<blocks_for(ncl, B), B, 0, stream>>>(T);
+    }
+    const long long nkw = static_cast<long long>(T.ncells) * T.keepwords;
+    if (nkw > 0) {
+      k_build_keepwords<<<blocks_for(nkw, B), B, 0, stream>>>(T);
+    }
+    if (ncl > 0) {
+      k_build_macroatom<<<blocks_for(ncl, B), B, 0, stream>>>(T);
+    }
+    const long long nci = static_cast<long long>(T.ncells) * T.nions;
+    if (nci > 0) {
+      k_build_cooling<<<blocks_for(nci, B), B, 0, stream>>>(T);
+    }
+    // stats::Counter::UPDATECELL counts one cell-cache fill per cell (update_packets.cc:399)
+    const long long ncells = T.ncells;
+    cudaMemcpyAsync(&T.counters[ab::CNT_UPDATECELL], &ncells, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    return ok(cudaStreamSynchronize(stream), "build_cell_tables") && ok(cudaGetLastError(), "build_cell_tables");
+  }
+
+  bool aos_to_soa(const Tables& T, const void* aos, const int64_t n, const int stride) {
+    cudaSetDevice(device);
+    if (n > 0) {
+      k_aos_to_soa<<<blocks_for(n, 256), 256, 0, stream>>>(T, static_cast<const unsigned char*>(aos), n, stride);
+    }
+    return ok(cudaGetLastError(), "k_aos_to_soa");
+  }
+
+  bool soa_to_aos(const Tables& T, void* aos, const int64_t n, const int stride) {
+    cudaSetDevice(device);
+    if (n > 0) {
+      k_soa_to_aos<<<blocks_for(n, 256), 256, 0, stream>>>(T, static_cast<unsigned char*>(aos), n, stride);
+    }
+    return ok(cudaGetLastError(), "k_soa_to_aos");
+  }
+
+  bool propagate(Tables& T, const int64_t n, bool /*sort*/, double* total_ms, double* prop_ms, double* sched_ms) {
+    cudaSetDevice(device);
+    // persistent grid: a multiple of the SM count, sized for the resident blocks per SM of this kernel
+    int blocks_per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_propagate, PROP_BLOCK, 0);
+    if (blocks_per_sm < 1) {
+      blocks_per_sm = 1;
+    }
+    long long nblocks = static_cast<long long>(sm_count) * blocks_per_sm;
+    const long long needed = (n + PROP_BLOCK - 1) / PROP_BLOCK;
+    if (nblocks > needed) {
+      nblocks = needed;
+    }
+    const long long nthreads = nblocks * PROP_BLOCK;
+    const long long ng = T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1;
+    if (scratch_elems < nthreads * ng) {
+      cudaFree(d_scratch);
+      d_scratch = nullptr;
+      if (!ok(cudaMalloc(&d_scratch, static_cast<size_t>(nthreads * ng) * sizeof(double)), "cudaMalloc(scratch)")) {
+        return false;
+      }
+      scratch_elems = nthreads * ng;
+    }
+    T.scratch_groundcont = d_scratch;
+    T.scratch_stride = nthreads;
+
+    cudaEventRecord(ev_start, stream);
+    if (T.rng_mode == ab::RNG_PHILOX) {
+      k_reset_philox<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
+    }
+    long long launches = 0;
+    unsigned long long hq[2] = {0ULL, 1ULL};
+    while (hq[1] > 0ULL) {
+      cudaMemsetAsync(d_queue, 0, 2 * sizeof(unsigned long long), stream);
+      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, n, d_queue);
+      launches++;
+      if (!ok(cudaMemcpyAsync(hq, d_queue, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
+          !ok(cudaStreamSynchronize(stream), "k_propagate")) {
+        return false;
+      }
+      if (T.max_steps_per_launch <= 0 && hq[1] > 0ULL) {
+        error = "k_propagate left active packets in whole-history mode";
+        return false;
+      }
+    }
+    cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    cudaEventRecord(ev_stop, stream);
+    if (!ok(cudaEventSynchronize(ev_stop), "cudaEventSynchronize")) {
+      return false;
+    }
+    float ms = 0.F;
+    cudaEventElapsedTime(&ms, ev_start, ev_stop);
+    *total_ms = ms;
+    *prop_ms = ms;
+    *sched_ms = 0.;
+    return ok(cudaGetLastError(), "propagate");
+  }
+};
+
+}  // namespace
+
+using ActiveBackend = CudaBackend;
+#include "capi_impl.h"

@@ -1,0 +1,246 @@
+// Accessors over the flat atomic-data tables, level populations, photoionisation cross sections and the
+// rate-coefficient LUT interpolation. Mirrors reference atomic.h (accessors, phixs table lookup 202-252),
+// ltepop.h:56-113 / ltepop.cc:395-423 (populations), ratecoeff.cc:54-64, 523-539, 679-875 (LUTs).
+#pragma once
+#include "hd.h"
+#include "options.h"
+#include "tables.h"
+
+namespace ab {
+
+AHD int uniqueion(const Tables& T, const int element, const int ion) { return T.elem_uniqueionindexstart[element] + ion; }
+AHD int nions_of(const Tables& T, const int element) { return T.elem_nions[element]; }
+AHD int ionstage_of(const Tables& T, const int element, const int ion) { return T.elem_lowest_ionstage[element] + ion; }
+AHD int levelstart(const Tables& T, const int element, const int ion) { return T.ion_levelstart[uniqueion(T, element, ion)]; }
+AHD int uniquelevel(const Tables& T, const int element, const int ion, const int level) {
+  return levelstart(T, element, ion) + level;
+}
+AHD int nlevels_of(const Tables& T, const int element, const int ion) { return T.ion_nlevels[uniqueion(T, element, ion)]; }
+AHD int nlevels_ionising(const Tables& T, const int element, const int ion) {
+  return T.ion_nlevels_ionising[uniqueion(T, element, ion)];
+}
+AHD double epsilon(const Tables& T, const int ulev) { return T.level_epsilon[ulev]; }
+AHD double statw(const Tables& T, const int ulev) { return static_cast<double>(T.level_statweight[ulev]); }
+AHD int alltrans_startup(const Tables& T, const int ulev) {
+  return T.level_alltrans_startdown[ulev] + T.level_ndowntrans[ulev];
+}
+AHD int phixsupperlevel(const Tables& T, const int ulev, const int phixstargetindex) {
+  return T.phixstarget_levelindex[T.level_phixstargetstart[ulev] + phixstargetindex];
+}
+AHD double phixsprobability(const Tables& T, const int ulev, const int phixstargetindex) {
+  return T.phixstarget_probability[T.level_phixstargetstart[ulev] + phixstargetindex];
+}
+AHD const float* phixs_table(const Tables& T, const int ulev) {
+  return T.phixs_table + (static_cast<long long>(T.level_phixsstart[ulev]) * T.nphixspoints);
+}
+AHD int find_phixstargetindex(const Tables& T, const int ulev, const int upperionlevel) {  // atomic.h:499-508
+  const int n = T.level_nphixstargets[ulev];
+  for (int i = 0; i < n; i++) {
+    if (upperionlevel == phixsupperlevel(T, ulev, i)) {
+      return i;
+    }
+  }
+  return -1;
+}
+AHD int emtype_continuum(const Tables& T, const int ulev, const int phixstargetindex) {  // atomic.h:513-518
+  return -1 - T.level_bflist_start[ulev] - phixstargetindex;
+}
+// photoionisation threshold energy [erg] (atomic.h:534-542)
+AHD double phixs_threshold(const Tables& T, const int element, const int ion, const int level,
+                           const int phixstargetindex) {
+  const int ulev = uniquelevel(T, element, ion, level);
+  const int upperlevel = phixsupperlevel(T, ulev, phixstargetindex);
+  return epsilon(T, uniquelevel(T, element, ion + 1, upperlevel)) - epsilon(T, ulev);
+}
+
+// photoionisation cross-section from the table (atomic.h:202-252); returns float like the reference
+AHD float photoionisation_crosssection_fromtable(const Tables& T, const float* photoion_xs, const double nu_edge,
+                                                 const double nu) {
+  const int npts = static_cast<int>(T.nphixspoints);
+  float sigma_bf = 0.;
+  if constexpr (opt::PHIXS_CLASSIC_NO_INTERPOLATION) {
+    if (nu < nu_edge) {
+      sigma_bf = 0.;
+    } else if (nu == nu_edge) {
+      sigma_bf = photoion_xs[0];
+    } else if (nu < nu_edge * (1 + (T.nphixsnuincrement * npts))) {
+      int i = static_cast<int>((nu - nu_edge) / (T.nphixsnuincrement * nu_edge));
+      i = (npts - 1 < i) ? npts - 1 : i;
+      sigma_bf = photoion_xs[i];
+    } else {
+      sigma_bf = static_cast<float>(photoion_xs[npts - 1] * pow(nu_edge * (1 + (T.nphixsnuincrement * npts)) / nu, 3));
+    }
+    return sigma_bf;
+  }
+  const double ireal = ((nu / nu_edge) - 1.0) / T.nphixsnuincrement;
+  const int i = static_cast<int>(floor(ireal));
+  if (i < 0) {
+    sigma_bf = 0.;
+  } else if (i < npts - 1) {
+    const double sigma_bf_a = photoion_xs[i];
+    const double sigma_bf_b = photoion_xs[i + 1];
+    const double factor_b = ireal - i;
+    sigma_bf = static_cast<float>(((1. - factor_b) * sigma_bf_a) + (factor_b * sigma_bf_b));
+  } else {
+    const double nu_max_phixs = nu_edge * T.last_phixs_nuovernuedge;
+    sigma_bf = static_cast<float>(photoion_xs[npts - 1] * pow3(nu_max_phixs / nu));
+  }
+  return sigma_bf;
+}
+
+// ---- cell state ----------------------------------------------------------------------------------
+
+AHD float elem_massfrac(const Tables& T, const int cell, const int element) {
+  return T.elem_massfracs[(static_cast<long long>(cell) * T.nelements) + element];
+}
+
+// ground level population with the MINPOP floor (ltepop.h:75-87)
+AHD double groundlevelpop(const Tables& T, const int cell, const int element, const int ion) {
+  const double nn = T.ion_groundlevelpops[(static_cast<long long>(cell) * T.nions) + uniqueion(T, element, ion)];
+  if (nn < opt::MINPOP) {
+    if (elem_massfrac(T, cell, element) > 0) {
+      return opt::MINPOP;
+    }
+    return 0.;
+  }
+  return nn;
+}
+
+// ion population from ground population and partition function (ltepop.h:107-113)
+AHD double nnion(const Tables& T, const int cell, const int element, const int ion) {
+  const int u = uniqueion(T, element, ion);
+  return groundlevelpop(T, cell, element, ion) * T.ion_partfuncts[(static_cast<long long>(cell) * T.nions) + u] /
+         statw(T, T.ion_levelstart[u]);
+}
+
+// LTE (Boltzmann) level population with the MINPOP floor (ltepop.cc:395-423; NLTE populations not implemented)
+AHD double calculate_levelpop(const Tables& T, const int cell, const int element, const int ion, const int level) {
+  double nn;
+  const double nnground = groundlevelpop(T, cell, element, ion);
+  if (level == 0) {
+    nn = nnground;
+  } else {
+    const auto T_exc = opt::LTEPOP_EXCITATION_USE_TJ ? T.TJ[cell] : T.Te[cell];
+    const int ustart = levelstart(T, element, ion);
+    const double E_aboveground = epsilon(T, ustart + level) - epsilon(T, ustart);
+    nn = (nnground * statw(T, ustart + level) / statw(T, ustart) * exp(-E_aboveground / KB / T_exc));
+  }
+  if (nn < opt::MINPOP) {
+    if (elem_massfrac(T, cell, element) > 0) {
+      return opt::MINPOP;
+    }
+    return 0.;
+  }
+  return nn;
+}
+
+AHD double cell_levelpop(const Tables& T, const int cell, const int ulev) {  // ltepop.h:58-65
+  return T.cell_levelpops[(static_cast<long long>(cell) * T.nlevels) + ulev];
+}
+
+AHD float clumpednne(const Tables& T, const int cell) { return T.clumpfactor[cell] * T.nne[cell]; }
+
+// ---- rate-coefficient LUTs -------------------------------------------------------------------------
+
+// index of the first temperature grid point above `temperature`, == upper_bound on the grid (ratecoeff.cc:54-64)
+AHD int temperature_gridupperindex(const Tables& T, const double temperature) {
+  const int gridsize = static_cast<int>(T.tablesize) + 1;
+  const double* grid = T.lut_temperature_grid;
+  int index = static_cast<int>(log(temperature / grid[0]) / T.T_step_log) + 1;
+  index = (index < 0) ? 0 : ((gridsize < index) ? gridsize : index);
+  while (index > 0 && grid[index - 1] > temperature) {
+    index--;
+  }
+  while (index < gridsize && grid[index] <= temperature) {
+    index++;
+  }
+  return index;
+}
+
+// linear interpolation in T of a [continuum][TABLESIZE] LUT (ratecoeff.cc:523-539, 123-131)
+AHD double lerp_or_last(const Tables& T, const double* table, const int ulev, const int phixstargetindex,
+                        const double temperature) {
+  const int tablesize = static_cast<int>(T.tablesize);
+  const long long base = static_cast<long long>(T.level_bflist_start[ulev] + phixstargetindex) * tablesize;
+  const int upperindex = temperature_gridupperindex(T, temperature);
+  if (upperindex == 0) {
+    return table[base];
+  }
+  if (upperindex < tablesize) {
+    const double T_lower = T.lut_temperature_grid[upperindex - 1];
+    const double T_upper = T.lut_temperature_grid[upperindex];
+    const double f_lower = table[base + upperindex - 1];
+    const double f_upper = table[base + upperindex];
+    return (f_lower + ((f_upper - f_lower) / (T_upper - T_lower) * (temperature - T_lower)));
+  }
+  return table[base + tablesize - 1];
+}
+
+AHD double spontrecombcoeff(const Tables& T, const int ulev, const int phixstargetindex, const float T_e) {
+  return lerp_or_last(T, T.lut_spontrecomb, ulev, phixstargetindex, T_e);
+}
+AHD double bfcoolingcoeff(const Tables& T, const int ulev, const int phixstargetindex, const float T_e) {
+  return lerp_or_last(T, T.lut_bfcooling, ulev, phixstargetindex, T_e);
+}
+
+// stimulated-recombination-corrected photoionisation rate coefficient, LUT branch (ratecoeff.cc:840-875)
+AHD double calc_corrphotoioncoeff(const Tables& T, const int cell, const int ulev, const int phixstargetindex) {
+  static_assert(opt::USE_LUT_PHOTOION, "only the USE_LUT_PHOTOION branch of get_corrphotoioncoeff is implemented");
+  const double W = T.W[cell];
+  const double T_R = T.TR[cell];
+  double gammacorr = W * lerp_or_last(T, T.lut_corrphotoion, ulev, phixstargetindex, T_R);
+  const int index_in_groundlevelcontestimator = T.level_closestgroundlevelcont[ulev];
+  if (index_in_groundlevelcontestimator >= 0) {
+    gammacorr *= T.corrphotoionrenorm[(static_cast<long long>(cell) * T.nbfcontinua_ground) +
+                                      index_in_groundlevelcontestimator];
+  }
+  return gammacorr;
+}
+
+AHD double cell_corrphotoioncoeff(const Tables& T, const int cell, const int ulev, const int phixstargetindex) {
+  return T.cell_corrphotoioncoeff[(static_cast<long long>(cell) * T.nphixstargets_total) +
+                                  T.level_phixstargetstart[ulev] + phixstargetindex];
+}
+
+// Planck function B_nu(T) (radfield.h:49-51)
+AHD double planck(const double nu, const double temperature) {
+  return 2 * H * pow3(nu) / pow2(CLIGHT) / expm1(HOVERKB * nu / temperature);
+}
+
+// mean intensity model J_nu: single dilute blackbody (radfield.cc:786-801 without the multibin branch)
+AHD double radfield_J(const Tables& T, const double nu, const int cell) {
+  return T.W[cell] * planck(nu, T.TR[cell]);
+}
+
+// std::upper_bound / lower_bound index helpers over plain arrays (sn3d.h:85-101)
+AHD int upper_bound_idx(const double* a, const int n, const double target) {
+  int lo = 0;
+  int len = n;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (!(target < a[lo + half])) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo;
+}
+
+AHD int lower_bound_idx(const double* a, const int n, const double target) {
+  int lo = 0;
+  int len = n;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (a[lo + half] < target) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo;
+}
+
+}  // namespace ab

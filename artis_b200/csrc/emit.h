@@ -1,0 +1,208 @@
+// Emission of r-packets: isotropic re-emission, electron scattering (isotropic or polarised dipole), and
+// sampling of emission frequencies (free-bound continuum, Planck function).
+// Reference: rpkt.cc:331-410 (electron_scatter_rpkt), 991-1018 (emit_rpkt); ratecoeff.cc:563-638
+// (select_continuum_nu); kpkt.cc:266-276 (sample_planck_montecarlo).
+#pragma once
+#include "atomicdata.h"
+#include "hd.h"
+#include "options.h"
+#include "packet.h"
+#include "vec.h"
+
+namespace ab {
+
+// rpkt.cc:991-1018
+AHD void emit_rpkt(Pkt& p, const Ctx& c) {
+  p.type = TYPE_RPKT;
+  double dir_cmf[3];
+  rand_isotropic_unitvec(p.rng, dir_cmf);
+  double vel_vec[3];
+  get_velocity(p.pos, -p.prop_time, vel_vec);  // negative time: backwards transformation cmf -> rest frame
+  angle_ab(dir_cmf, vel_vec, p.dir);
+  set_pkt_restframe_from_cmf(p);
+  if constexpr (opt::POL_ON) {
+    p.stokes_u = 0.;
+    p.stokes_q = 0.;
+  }
+  set_em_here(p, c);
+}
+
+// rpkt.cc:331-410
+AHD void electron_scatter_rpkt(Pkt& p) {
+  p.type = TYPE_RPKT;
+  double vel_vec[3];
+  get_velocity(p.pos, p.prop_time, vel_vec);
+
+  double old_dir_cmf[3];
+  double q_i_cmf = 0.;
+  double u_i_cmf = 0.;
+  if constexpr (opt::POL_ON) {
+    frame_transform(p.dir, p.stokes_q, p.stokes_u, vel_vec, old_dir_cmf, q_i_cmf, u_i_cmf);
+  } else {
+    angle_ab(p.dir, vel_vec, old_dir_cmf);
+  }
+
+  double M = 0.;
+  double phisc = 0.;
+  if constexpr (opt::DIPOLE) {
+    // rejection sampling of the dipole phase function (rpkt.cc:347-368): 3 draws per trial
+    double prob = 0.;
+    double x = 1.;
+    while (x > prob) {
+      M = (2. * p.rng.uniform_pos()) - 1.;
+      const double musquared = pow2(M);
+      phisc = 2 * PI * p.rng.uniform();
+      prob = (musquared + 1) + ((musquared - 1) * ((cos(2 * phisc) * q_i_cmf) + (sin(2 * phisc) * u_i_cmf)));
+      x = 2. * p.rng.uniform();
+    }
+  } else {
+    M = (2. * p.rng.uniform()) - 1.;
+    phisc = 2 * PI * p.rng.uniform();
+  }
+
+  double new_dir_cmf[3];
+  const double cos_tsc = M;
+  const double sin_tsc = sqrt(1. - pow2(M));
+  if (fabs(old_dir_cmf[2]) < 0.99999) {
+    const double sin_polar = sqrt(1. - pow2(old_dir_cmf[2]));
+    const double common_factor = sin_tsc / sin_polar;
+    const double cos_phisc = cos(phisc);
+    const double sin_phisc = sin(phisc);
+    new_dir_cmf[0] = (common_factor * ((old_dir_cmf[1] * sin_phisc) - (old_dir_cmf[0] * old_dir_cmf[2] * cos_phisc))) +
+                     (old_dir_cmf[0] * cos_tsc);
+    new_dir_cmf[1] = (common_factor * ((-old_dir_cmf[0] * sin_phisc) - (old_dir_cmf[1] * old_dir_cmf[2] * cos_phisc))) +
+                     (old_dir_cmf[1] * cos_tsc);
+    new_dir_cmf[2] = (sin_tsc * cos_phisc * sin_polar) + (old_dir_cmf[2] * cos_tsc);
+  } else {
+    new_dir_cmf[0] = sin_tsc * cos(phisc);
+    new_dir_cmf[1] = sin_tsc * sin(phisc);
+    new_dir_cmf[2] = (old_dir_cmf[2] > 0) ? cos_tsc : -cos_tsc;
+  }
+
+  if constexpr (opt::POL_ON) {
+    double new_dir_rf[3];
+    double q_rf = 0.;
+    double u_rf = 0.;
+    scatter_polarisation_to_rf(old_dir_cmf, new_dir_cmf, q_i_cmf, u_i_cmf, vel_vec, new_dir_rf, q_rf, u_rf);
+    p.dir[0] = new_dir_rf[0];
+    p.dir[1] = new_dir_rf[1];
+    p.dir[2] = new_dir_rf[2];
+    p.stokes_q = q_rf;
+    p.stokes_u = u_rf;
+  } else {
+    const double negvel[3] = {-vel_vec[0], -vel_vec[1], -vel_vec[2]};
+    double newdir[3];
+    angle_ab(new_dir_cmf, negvel, newdir);
+    p.dir[0] = newdir[0];
+    p.dir[1] = newdir[1];
+    p.dir[2] = newdir[2];
+  }
+  set_pkt_restframe_from_cmf(p);
+}
+
+// kpkt.cc:266-276: Planck-distributed frequency in [NU_MIN_R, NU_MAX_R] by rejection (2 draws per trial)
+AHD double sample_planck_montecarlo(const double T, Rng& rng) {
+  const double nu_peak = 5.879e10 * T;
+  const double B_peak = planck(nu_peak, T);
+  while (true) {
+    const double nu = opt::NU_MIN_R + (rng.uniform() * (opt::NU_MAX_R - opt::NU_MIN_R));
+    if (rng.uniform() * B_peak <= planck(nu, T)) {
+      return nu;
+    }
+  }
+}
+
+// energy-weighted free-bound emissivity integrand (ratecoeff.cc:84-90)
+AHD double alpha_sp_E_integrand(const Tables& T, const double nu_minus_nu_edge, const double nu_edge, const float T_e,
+                                const float* photoion_xs) {
+  const double nu = nu_edge + nu_minus_nu_edge;
+  const float sigma_bf = photoionisation_crosssection_fromtable(T, photoion_xs, nu_edge, nu);
+  return (2 / CLIGHTSQUARED) * sigma_bf * pow3(nu) / nu_edge * exp(-HOVERKB * nu_minus_nu_edge / T_e);
+}
+
+// integral of the emissivity over [a, b], split at the knots of the cross-section table (where the tabulated
+// cross section has kinks, or steps with PHIXS_CLASSIC_NO_INTERPOLATION) with 5-point Gauss-Legendre on each part
+AHD double emissivity_piece_integral(const Tables& T, const double a, const double b, const double nu_edge,
+                                     const float T_e, const float* photoion_xs) {
+  constexpr double gl_x[5] = {-0.9061798459386640, -0.5384693101056831, 0.0, 0.5384693101056831, 0.9061798459386640};
+  constexpr double gl_w[5] = {0.2369268850561891, 0.4786286704993665, 0.5688888888888889, 0.4786286704993665,
+                              0.2369268850561891};
+  const double knotspacing = T.nphixsnuincrement * nu_edge;
+  double total = 0.;
+  double lo = a;
+  long long k = static_cast<long long>(floor(a / knotspacing)) + 1;
+  while (lo < b) {
+    double hi = static_cast<double>(k) * knotspacing;
+    if (!(hi < b)) {
+      hi = b;
+    }
+    if (hi > lo) {
+      const double half = 0.5 * (hi - lo);
+      const double mid = 0.5 * (hi + lo);
+      double s = 0.;
+#pragma unroll
+      for (int q = 0; q < 5; q++) {
+        s += gl_w[q] * alpha_sp_E_integrand(T, mid + (half * gl_x[q]), nu_edge, T_e, photoion_xs);
+      }
+      total += s * half;
+    }
+    lo = hi;
+    k++;
+  }
+  return total;
+}
+
+// Sample the frequency of a free-bound emission into (element, lowerion, lower) from the target
+// phixstargetindex (ratecoeff.cc:563-638). The reference evaluates up to NPHIXSPOINTS adaptive 31-point
+// Gauss-Kronrod tail integrals per call (relative accuracy 1e-3); here the same tail integrals at the same
+// piece boundaries come from one pass of fixed-order quadrature over the pieces, and the selection and the
+// in-piece linear interpolation follow the reference exactly. One draw.
+AHD double select_continuum_nu(const Tables& T, const int element, const int lowerion, const int lower,
+                               const int phixstargetindex, const float T_e, Rng& rng) {
+  const int lower_ulev = uniquelevel(T, element, lowerion, lower);
+  const double E_threshold = phixs_threshold(T, element, lowerion, lower, phixstargetindex);
+  const double nu_threshold = (1. / H) * E_threshold;
+  const double nu_max_phixs = nu_threshold * T.last_phixs_nuovernuedge;
+  const int npieces = static_cast<int>(T.nphixspoints);
+  const float* photoion_xs = phixs_table(T, lower_ulev);
+
+  const double zrand = 1. - rng.uniform();  // 0 < zrand <= 1
+
+  const double nu_range = nu_max_phixs - nu_threshold;
+  const double deltanu = nu_range / npieces;
+
+  double emissivity_integral_total = 0.;
+  for (int j = 0; j < npieces; j++) {
+    emissivity_integral_total +=
+        emissivity_piece_integral(T, j * deltanu, (j + 1) * deltanu, nu_threshold, T_e, photoion_xs);
+  }
+  if (!(emissivity_integral_total > 0.) || !is_finite(emissivity_integral_total)) {
+    return nu_threshold;
+  }
+
+  double emissivity_tailintegral_prev = emissivity_integral_total;
+  double emissivity_tailintegral = emissivity_integral_total;
+  double prefix = 0.;
+  int i = 1;
+  for (; i < npieces; i++) {
+    emissivity_tailintegral_prev = emissivity_tailintegral;
+    prefix += emissivity_piece_integral(T, (i - 1) * deltanu, i * deltanu, nu_threshold, T_e, photoion_xs);
+    emissivity_tailintegral = dmax(emissivity_integral_total - prefix, 0.);
+    if (zrand >= emissivity_tailintegral / emissivity_integral_total) {
+      break;
+    }
+  }
+
+  double nuoffset = 0.;
+  if (i < npieces) {
+    nuoffset = (emissivity_tailintegral != emissivity_tailintegral_prev)
+                   ? ((emissivity_integral_total * zrand) - emissivity_tailintegral_prev) /
+                         (emissivity_tailintegral - emissivity_tailintegral_prev) * deltanu
+                   : 0.;
+  } else if (emissivity_tailintegral > 0.) {
+    nuoffset = (emissivity_tailintegral - (emissivity_integral_total * zrand)) / emissivity_tailintegral * deltanu;
+  }
+  return nu_threshold + ((i - 1) * deltanu) + nuoffset;
+}
+
+}  // namespace ab

@@ -1,0 +1,607 @@
+// Host-side engine behind the C ABI (include/artis_b200.h): owns the device copies of every table, the SoA
+// packet state and the estimator buffers, and sequences one timestep
+//     begin_timestep : zero estimators, build the per-cell tables on the device
+//     update_packets : (re)launch the propagation kernel until no packet needs further work
+// It is a template over a Backend that supplies memory operations and kernel launches. The product backend
+// is CUDA (artis_b200.cu). tests/hostsim/hostsim.cc provides a single-threaded host backend that exists only
+// so that packet histories can be debugged against the oracle in a container without a GPU.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "options.h"
+#include "packet.h"
+#include "tables.h"
+
+namespace ab {
+
+template <class T> struct dcode;
+template <> struct dcode<double> { static constexpr char v = 'd'; };
+template <> struct dcode<float> { static constexpr char v = 'f'; };
+template <> struct dcode<int> { static constexpr char v = 'i'; };
+template <> struct dcode<long long> { static constexpr char v = 'q'; };
+template <> struct dcode<unsigned char> { static constexpr char v = 'B'; };
+template <> struct dcode<unsigned long long> { static constexpr char v = 'Q'; };
+template <> struct dcode<unsigned int> { static constexpr char v = 'I'; };
+
+inline size_t dsize(const char dtype) {
+  switch (dtype) {
+    case 'd': case 'q': case 'Q': return 8;
+    case 'f': case 'i': case 'I': return 4;
+    case 'B': return 1;
+    default: return 0;
+  }
+}
+
+enum class FieldKind { INPUT, SCALAR, OUTPUT };
+struct FieldDesc {
+  const char* name;
+  char dtype;
+  size_t offset;
+  FieldKind kind;
+};
+
+inline const std::vector<FieldDesc>& field_registry() {
+  static const std::vector<FieldDesc> reg = [] {
+    std::vector<FieldDesc> r;
+#define X(type, member, pub) r.push_back({pub, dcode<type>::v, offsetof(Tables, member), FieldKind::INPUT});
+    AB_INPUT_ARRAYS(X)
+#undef X
+#define X(type, member, pub) r.push_back({pub, dcode<type>::v, offsetof(Tables, member), FieldKind::SCALAR});
+    AB_INPUT_SCALARS(X)
+#undef X
+#define X(type, member, pub) r.push_back({pub, dcode<type>::v, offsetof(Tables, member), FieldKind::OUTPUT});
+    AB_OUTPUT_ARRAYS(X)
+#undef X
+    return r;
+  }();
+  return reg;
+}
+
+inline const FieldDesc* find_field(const std::string& name) {
+  for (const auto& f : field_registry()) {
+    if (name == f.name) {
+      return &f;
+    }
+  }
+  return nullptr;
+}
+
+// FNV-1a over the canonical option string; the reference-side binding builds the same string from artisoptions.h
+inline std::string options_summary_string() {
+  char buf[1024];
+  std::snprintf(buf, sizeof(buf),
+                "preset=%s;POL_ON=%d;DIPOLE=%d;RELDOPPLER=%d;PHIXS_CLASSIC=%d;LUT_PHOTOION=%d;ION_BFHEAT=%d;"
+                "DETAILED_BF=%d;MULTIBIN=%d;DIRECT_COL_HEAT=%d;NT_ON=%d;TJ_EXC=%d;BFCOOL_LEVELPOP=%d;"
+                "PARTICLE_SCHEME=%d;GAMMA_SCHEME=%d;MINPOP=%g;NU_MIN_R=%g;NU_MAX_R=%g",
+                ARTISB200_PRESET_NAME, opt::POL_ON, opt::DIPOLE, opt::USE_RELATIVISTIC_DOPPLER_SHIFT,
+                opt::PHIXS_CLASSIC_NO_INTERPOLATION, opt::USE_LUT_PHOTOION, opt::USE_ION_BFHEATING_ESTIMATORS,
+                opt::DETAILED_BF_ESTIMATORS_ON, opt::MULTIBIN_RADFIELD_MODEL_ON, opt::DIRECT_COL_HEAT, opt::NT_ON,
+                opt::LTEPOP_EXCITATION_USE_TJ, opt::BFCOOLING_USELEVELPOPNOTIONPOP, opt::PARTICLE_THERMALISATION_SCHEME,
+                opt::GAMMA_THERMALISATION_SCHEME, opt::MINPOP, opt::NU_MIN_R, opt::NU_MAX_R);
+  return buf;
+}
+
+inline uint64_t options_hash_value() {
+  const std::string s = options_summary_string();
+  const auto start = s.find(';');  // the preset NAME is not part of the hash, only the values
+  uint64_t h = 1469598103934665603ULL;
+  for (size_t i = start; i < s.size(); i++) {
+    h ^= static_cast<unsigned char>(s[i]);
+    h *= 1099511628211ULL;
+  }
+  return h;
+}
+
+struct ArrayRec {
+  void* dptr{nullptr};
+  char dtype{0};
+  int64_t count{0};
+  int64_t capacity_bytes{0};
+  bool owned{true};
+  std::vector<unsigned char> hostcopy;  // kept for small structural tables only
+};
+
+template <class Backend>
+class Engine {
+ public:
+  Backend be;
+  Tables T{};
+  std::map<std::string, ArrayRec> arrays;
+  std::string err;
+  bool static_committed{false};
+  bool timestep_begun{false};
+  bool outputs_allocated{false};
+
+  int64_t npackets{0};
+  int64_t packet_capacity{0};
+  int aos_stride{0};
+  void* aos_staging{nullptr};
+  int64_t aos_staging_bytes{0};
+  std::vector<void*> soa_save;  // device-resident copy of the SoA for benchmark replay
+  int64_t soa_save_count{0};
+
+  void* estimator_pack{nullptr};
+  int64_t estimator_pack_count{0};
+
+  // options
+  int rank{0};
+  int nranks{1};
+  long long sort_packets{0};
+
+  double last_total_ms{0.};
+  double last_propagate_ms{0.};
+  double last_schedule_ms{0.};
+
+  int fail(const std::string& msg) {
+    err = msg;
+    return 1;
+  }
+
+  static bool keep_hostcopy(const std::string& name) {
+    return name.rfind("elem.", 0) == 0 || name.rfind("ion.", 0) == 0 || name.rfind("level.", 0) == 0 ||
+           name.rfind("timesteps.", 0) == 0 || name == "lut.temperature_grid";
+  }
+
+  template <class U>
+  const U* host(const std::string& name) const {
+    const auto it = arrays.find(name);
+    return (it == arrays.end() || it->second.hostcopy.empty()) ? nullptr : reinterpret_cast<const U*>(it->second.hostcopy.data());
+  }
+
+  int64_t count_of(const std::string& name) const {
+    const auto it = arrays.find(name);
+    return (it == arrays.end()) ? -1 : it->second.count;
+  }
+
+  int set_array(const char* name_c, const char dtype, const void* data, const int64_t count) {
+    const std::string name(name_c);
+    if (name == "scalar.ncoordgrid") {
+      if (dtype != 'q' || count != 3) {
+        return fail("scalar.ncoordgrid must be 'q'[3]");
+      }
+      const auto* v = static_cast<const long long*>(data);
+      T.ncoord[0] = static_cast<int>(v[0]);
+      T.ncoord[1] = static_cast<int>(v[1]);
+      T.ncoord[2] = static_cast<int>(v[2]);
+      return 0;
+    }
+    const FieldDesc* f = find_field(name);
+    if (f == nullptr) {
+      return fail("unknown array name '" + name + "'");
+    }
+    if (f->dtype != dtype) {
+      return fail("array '" + name + "' has dtype '" + std::string(1, f->dtype) + "', got '" + std::string(1, dtype) + "'");
+    }
+    if (count < 0 || (count > 0 && data == nullptr)) {
+      return fail("array '" + name + "': bad count or null data");
+    }
+    auto* base = reinterpret_cast<unsigned char*>(&T);
+    if (f->kind == FieldKind::SCALAR) {
+      if (count != 1) {
+        return fail("scalar '" + name + "' needs count 1");
+      }
+      std::memcpy(base + f->offset, data, dsize(dtype));
+      return 0;
+    }
+    if (f->kind == FieldKind::OUTPUT) {
+      return fail("array '" + name + "' is an output of the library and cannot be set");
+    }
+    ArrayRec& rec = arrays[name];
+    const int64_t nbytes = count * static_cast<int64_t>(dsize(dtype));
+    if (rec.dptr == nullptr || rec.capacity_bytes < nbytes) {
+      if (rec.dptr != nullptr) {
+        be.free(rec.dptr);
+      }
+      rec.dptr = be.alloc(nbytes > 0 ? nbytes : 8);
+      if (rec.dptr == nullptr) {
+        return fail("device allocation failed for '" + name + "': " + be.last_error());
+      }
+      rec.capacity_bytes = nbytes > 0 ? nbytes : 8;
+    }
+    if (nbytes > 0 && !be.h2d(rec.dptr, data, nbytes)) {
+      return fail("host-to-device copy failed for '" + name + "': " + be.last_error());
+    }
+    rec.dtype = dtype;
+    rec.count = count;
+    if (keep_hostcopy(name)) {
+      rec.hostcopy.assign(static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + nbytes);
+    }
+    std::memcpy(base + f->offset, &rec.dptr, sizeof(void*));
+    return 0;
+  }
+
+  int get_array(const char* name_c, const char dtype, void* out, const int64_t count) {
+    const std::string name(name_c);
+    const FieldDesc* f = find_field(name);
+    if (f == nullptr) {
+      return fail("unknown array name '" + name + "'");
+    }
+    if (f->kind == FieldKind::SCALAR) {
+      if (dtype != f->dtype || count != 1) {
+        return fail("scalar '" + name + "': dtype/count mismatch");
+      }
+      std::memcpy(out, reinterpret_cast<unsigned char*>(&T) + f->offset, dsize(dtype));
+      return 0;
+    }
+    const auto it = arrays.find(name);
+    if (it == arrays.end() || it->second.dptr == nullptr) {
+      return fail("array '" + name + "' has not been set/allocated");
+    }
+    if (dtype != it->second.dtype || count != it->second.count) {
+      return fail("array '" + name + "': dtype/count mismatch (have '" + std::string(1, it->second.dtype) + "' x " +
+                  std::to_string(it->second.count) + ")");
+    }
+    if (count > 0 && !be.d2h(out, it->second.dptr, count * static_cast<int64_t>(dsize(dtype)))) {
+      return fail("device-to-host copy failed for '" + name + "': " + be.last_error());
+    }
+    return 0;
+  }
+
+  int set_option(const char* name_c, const long long value) {
+    const std::string name(name_c);
+    if (name == "rng_mode") {
+      T.rng_mode = static_cast<int>(value);
+    } else if (name == "seed") {
+      T.seed = static_cast<unsigned long long>(value);
+    } else if (name == "max_steps_per_launch") {
+      T.max_steps_per_launch = value;
+    } else if (name == "sort_packets") {
+      sort_packets = value;
+    } else if (name == "rank") {
+      rank = static_cast<int>(value);
+    } else if (name == "nranks") {
+      nranks = static_cast<int>(value);
+    } else {
+      return fail("unknown option '" + name + "'");
+    }
+    return 0;
+  }
+
+  template <class U>
+  bool make_derived(const char* name, const std::vector<U>& v, const U** slot) {
+    ArrayRec& rec = arrays[name];
+    const int64_t nbytes = static_cast<int64_t>(v.size() * sizeof(U));
+    if (rec.dptr != nullptr) {
+      be.free(rec.dptr);
+    }
+    rec.dptr = be.alloc(nbytes > 0 ? nbytes : 8);
+    if (rec.dptr == nullptr || (nbytes > 0 && !be.h2d(rec.dptr, v.data(), nbytes))) {
+      return false;
+    }
+    rec.dtype = dcode<U>::v;
+    rec.count = static_cast<int64_t>(v.size());
+    rec.capacity_bytes = nbytes;
+    *slot = static_cast<const U*>(rec.dptr);
+    return true;
+  }
+
+  int commit_static() {
+    static const char* required[] = {
+        "grid.coord_pos_min_tmin0", "grid.propcell_nonemptymgi", "cell.ffegrp", "elem.anumber", "elem.nions",
+        "elem.lowest_ionstage", "elem.uniqueionindexstart", "ion.nlevels", "ion.nlevels_ionising",
+        "ion.maxrecombininglevel", "ion.coolingoffset", "ion.ncoolingterms", "ion.uniquelevelindexstart",
+        "level.epsilon", "level.statweight", "level.alltrans_startdown", "level.ndowntrans", "level.nuptrans",
+        "level.closestgroundlevelcont", "level.phixsstart", "level.nphixstargets", "level.phixstargetstart",
+        "level.bflist_start", "level.matransblock_start", "trans.lineindex", "trans.targetlevelindex",
+        "trans.einstein_A", "trans.coll_str", "trans.osc_strength", "trans.forbidden", "line.nu",
+        "line.elementindex", "line.ionindex", "line.lower", "line.upper", "line.B_ul", "line.B_lu", "cont.nu_edge",
+        "cont.element", "cont.ion", "cont.level", "cont.phixstargetindex", "cont.upperlevel",
+        "cont.uniquelevelindex", "cont.probability", "cont.groundcontestimindex", "phixs.table",
+        "phixstarget.levelindex", "phixstarget.probability", "groundcont.nu_edge", "lut.spontrecomb",
+        "lut.corrphotoion", "lut.bfcooling", "lut.temperature_grid", "cooling.type", "cooling.level",
+        "cooling.phixstargetindex", "timesteps.start", "timesteps.width", "timesteps.mid"};
+    for (const char* name : required) {
+      if (count_of(name) < 0) {
+        return fail(std::string("commit_static: required table '") + name + "' has not been set");
+      }
+    }
+    T.ngrid = static_cast<int>(count_of("grid.propcell_nonemptymgi"));
+    T.ncells = static_cast<int>(count_of("cell.ffegrp"));
+    T.nelements = static_cast<int>(count_of("elem.anumber"));
+    T.nions = static_cast<int>(count_of("ion.nlevels"));
+    T.nlevels = static_cast<int>(count_of("level.epsilon"));
+    T.nlines = static_cast<int>(count_of("line.nu"));
+    T.ntrans = static_cast<int>(count_of("trans.lineindex"));
+    T.nbfcontinua = static_cast<int>(count_of("cont.nu_edge"));
+    T.nbfcontinua_ground = static_cast<int>(count_of("groundcont.nu_edge"));
+    T.nphixstargets_total = static_cast<int>(count_of("phixstarget.levelindex"));
+    T.ncoolingterms = static_cast<int>(count_of("cooling.type"));
+    T.ntimesteps = static_cast<int>(count_of("timesteps.start"));
+    T.keepwords = (T.nbfcontinua + 63) / 64;
+    T.log2_nbf = 1;
+    while ((1 << T.log2_nbf) < T.nbfcontinua) {
+      T.log2_nbf++;
+    }
+    if (T.grid_type < 0 || T.grid_type > 2) {
+      return fail("commit_static: scalar.grid_type must be 0, 1 or 2");
+    }
+    const int ndim = (T.grid_type == GRID_SPHERICAL1D) ? 1 : ((T.grid_type == GRID_CYLINDRICAL2D) ? 2 : 3);
+    long long ngrid_expected = 1;
+    for (int d = 0; d < ndim; d++) {
+      const std::string nm = "grid.coord_pos_min_tmin" + std::to_string(d);
+      if (count_of(nm) != T.ncoord[d]) {
+        return fail("commit_static: " + nm + " length does not match scalar.ncoordgrid");
+      }
+      ngrid_expected *= T.ncoord[d];
+    }
+    if (ngrid_expected != T.ngrid) {
+      return fail("commit_static: grid.propcell_nonemptymgi length does not match the product of scalar.ncoordgrid");
+    }
+    if (!(T.tmin > 0) || !(T.rmax > 0)) {
+      return fail("commit_static: scalar.tmin / scalar.rmax not set");
+    }
+    if (count_of("lut.temperature_grid") != T.tablesize + 1) {
+      return fail("commit_static: lut.temperature_grid must have tablesize + 1 entries");
+    }
+    const auto* tgrid = host<double>("lut.temperature_grid");
+    T.T_step_log = (std::log(tgrid[T.tablesize - 1]) - std::log(tgrid[0])) / (static_cast<double>(T.tablesize) - 1.);
+
+    // derived structural tables
+    const auto* e_nions = host<int>("elem.nions");
+    const auto* e_start = host<int>("elem.uniqueionindexstart");
+    const auto* i_nlevels = host<int>("ion.nlevels");
+    const auto* i_levelstart = host<int>("ion.uniquelevelindexstart");
+    std::vector<int> ion_element(T.nions, -1);
+    std::vector<int> ion_index(T.nions, -1);
+    for (int e = 0; e < T.nelements; e++) {
+      for (int i = 0; i < e_nions[e]; i++) {
+        ion_element[e_start[e] + i] = e;
+        ion_index[e_start[e] + i] = i;
+      }
+    }
+    std::vector<int> level_uniqueion(T.nlevels, -1);
+    for (int u = 0; u < T.nions; u++) {
+      for (int l = 0; l < i_nlevels[u]; l++) {
+        level_uniqueion[i_levelstart[u] + l] = u;
+      }
+    }
+    const auto* l_ndown = host<int>("level.ndowntrans");
+    const auto* l_nup = host<int>("level.nuptrans");
+    long long matrans_total = 0;
+    for (int l = 0; l < T.nlevels; l++) {
+      matrans_total += (2LL * l_ndown[l]) + l_nup[l];
+    }
+    T.matrans_total = static_cast<int>(matrans_total);
+    if (!make_derived("derived.ion_element", ion_element, &T.ion_element) ||
+        !make_derived("derived.ion_index", ion_index, &T.ion_index) ||
+        !make_derived("derived.level_uniqueion", level_uniqueion, &T.level_uniqueion)) {
+      return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
+    }
+    static_committed = true;
+    return 0;
+  }
+
+  bool alloc_output(const char* name, const char dtype, const int64_t count, void* slot_in_T) {
+    ArrayRec& rec = arrays[name];
+    const int64_t nbytes = count * static_cast<int64_t>(dsize(dtype));
+    if (rec.dptr == nullptr || rec.capacity_bytes < nbytes) {
+      if (rec.dptr != nullptr && rec.owned) {
+        be.free(rec.dptr);
+      }
+      rec.dptr = be.alloc(nbytes > 0 ? nbytes : 8);
+      rec.capacity_bytes = nbytes > 0 ? nbytes : 8;
+      rec.owned = true;
+      if (rec.dptr == nullptr) {
+        return false;
+      }
+    }
+    rec.dtype = dtype;
+    rec.count = count;
+    std::memcpy(slot_in_T, &rec.dptr, sizeof(void*));
+    return true;
+  }
+
+  int allocate_outputs() {
+    const int64_t nc = T.ncells;
+    const int64_t ng = T.nbfcontinua_ground;
+    // one packed f64 buffer for everything that is summed over ranks (see artisb200_estimator_device_buffer)
+    const int64_t sizes[11] = {nc, nc, nc, nc, nc * ng, nc * ng, nc, nc, nc, nc, NTSSCALARS};
+    const char* names[11] = {"est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating",
+                             "est.dep_gamma", "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars"};
+    double** slots[11] = {&T.est_J, &T.est_nuJ, &T.est_ffheating, &T.est_colheating, &T.est_gamma, &T.est_bfheating,
+                          &T.est_dep_gamma, &T.est_dep_positron, &T.est_dep_electron, &T.est_dep_alpha, &T.ts_scalars};
+    int64_t total = 0;
+    for (const auto s : sizes) {
+      total += s;
+    }
+    if (estimator_pack != nullptr) {
+      be.free(estimator_pack);
+    }
+    estimator_pack = be.alloc(total * 8);
+    if (estimator_pack == nullptr) {
+      return fail("allocation of the estimator buffer failed: " + be.last_error());
+    }
+    estimator_pack_count = total;
+    int64_t off = 0;
+    for (int k = 0; k < 11; k++) {
+      ArrayRec& rec = arrays[names[k]];
+      rec.dptr = static_cast<double*>(estimator_pack) + off;
+      rec.dtype = 'd';
+      rec.count = sizes[k];
+      rec.capacity_bytes = sizes[k] * 8;
+      rec.owned = false;
+      *slots[k] = static_cast<double*>(rec.dptr);
+      off += sizes[k];
+    }
+    bool ok = true;
+    ok = ok && alloc_output("ts.pellet_decays", 'q', 1, &T.ts_pellet_decays);
+    ok = ok && alloc_output("counters", 'q', CNT_COUNT, &T.counters);
+    ok = ok && alloc_output("diag", 'q', NDIAG, &T.diag);
+    ok = ok && alloc_output("built.levelpops", 'd', nc * T.nlevels, &T.cell_levelpops);
+    ok = ok && alloc_output("built.maprocessrates", 'd', nc * T.nlevels * MA_ACTION_COUNT, &T.cell_maprocessrates);
+    ok = ok && alloc_output("built.matrans", 'd', nc * static_cast<int64_t>(T.matrans_total), &T.cell_matrans);
+    ok = ok && alloc_output("built.cooling_contrib", 'd', nc * T.ncoolingterms, &T.cell_cooling_contrib);
+    ok = ok && alloc_output("built.cont_nnlevel", 'd', nc * T.nbfcontinua, &T.cell_cont_nnlevel);
+    ok = ok && alloc_output("built.cont_keepbits", 'Q', nc * T.keepwords, &T.cell_cont_keepbits);
+    ok = ok && alloc_output("built.cont_departure", 'd', nc * T.nbfcontinua, &T.cell_cont_departure);
+    ok = ok && alloc_output("built.cont_edgepart", 'd', nc * T.nbfcontinua, &T.cell_cont_edgepart);
+    ok = ok && alloc_output("built.chi_ff_nnionpart", 'd', nc, &T.cell_chi_ff_nnionpart);
+    ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nc * static_cast<int64_t>(T.nphixstargets_total),
+                            &T.cell_corrphotoioncoeff);
+    if (!ok) {
+      return fail("allocation of the per-cell tables failed (Nc x table sizes too large for this device?): " +
+                  be.last_error());
+    }
+    outputs_allocated = true;
+    return 0;
+  }
+
+  int begin_timestep(const int nts) {
+    if (!static_committed) {
+      return fail("begin_timestep: commit_static has not been called");
+    }
+    static const char* required[] = {"cell.rho", "cell.Te", "cell.TJ", "cell.TR", "cell.W", "cell.nne", "cell.nnetot",
+                                     "cell.kappagrey", "cell.clumpfactor", "cell.thick", "cell.elem_massfracs",
+                                     "cell.ion_groundlevelpops", "cell.ion_partfuncts", "cell.ion_cooling_contribs",
+                                     "cell.corrphotoionrenorm"};
+    for (const char* name : required) {
+      if (count_of(name) < 0) {
+        return fail(std::string("begin_timestep: per-timestep array '") + name + "' has not been set");
+      }
+    }
+    if (count_of("cell.rho") != T.ncells || count_of("cell.ion_groundlevelpops") != static_cast<int64_t>(T.ncells) * T.nions) {
+      return fail("begin_timestep: cell-state array lengths do not match the static tables");
+    }
+    if (nts < 0 || nts >= T.ntimesteps) {
+      return fail("begin_timestep: nts out of range");
+    }
+    T.nts = nts;
+    T.ts_begin = host<double>("timesteps.start")[nts];
+    T.ts_widthcur = host<double>("timesteps.width")[nts];
+    T.ts_middle = host<double>("timesteps.mid")[nts];
+    T.ts_end = T.ts_begin + T.ts_widthcur;
+    if (!outputs_allocated) {
+      const int rc = allocate_outputs();
+      if (rc != 0) {
+        return rc;
+      }
+    }
+    be.zero(estimator_pack, estimator_pack_count * 8);
+    be.zero(T.ts_pellet_decays, 8);
+    be.zero(T.counters, CNT_COUNT * 8);
+    be.zero(T.diag, NDIAG * 8);
+    if (!be.build_cell_tables(T)) {
+      return fail("begin_timestep: building the per-cell tables failed: " + be.last_error());
+    }
+    timestep_begun = true;
+    return 0;
+  }
+
+  int ensure_packet_capacity(const int64_t n, const int stride) {
+    if (n > packet_capacity) {
+      PacketSoA& s = T.pkt;
+#define X(type, name)                                                 \
+  if (s.name != nullptr) {                                            \
+    be.free(s.name);                                                  \
+  }                                                                   \
+  s.name = static_cast<type*>(be.alloc(n * static_cast<int64_t>(sizeof(type)))); \
+  if (s.name == nullptr) {                                            \
+    return fail("packet SoA allocation failed: " + be.last_error());  \
+  }
+      AB_PACKET_FIELDS(X)
+#undef X
+      packet_capacity = n;
+    }
+    const int64_t need = n * stride;
+    if (need > aos_staging_bytes) {
+      if (aos_staging != nullptr) {
+        be.free(aos_staging);
+      }
+      aos_staging = be.alloc(need);
+      if (aos_staging == nullptr) {
+        return fail("packet staging allocation failed: " + be.last_error());
+      }
+      aos_staging_bytes = need;
+    }
+    return 0;
+  }
+
+  int upload_packets(const void* aos, const int64_t n, const int stride) {
+    if (stride != AosLayout::size && stride != AosLayout::size + 16) {
+      return fail("upload_packets: stride must be 240 (CPU Packet) or 256 (GPU_ON Packet)");
+    }
+    if (T.rng_mode == RNG_XOSHIRO && stride != AosLayout::size + 16) {
+      return fail("upload_packets: rng_mode xoshiro needs the 256-byte GPU_ON Packet layout carrying rngstate");
+    }
+    const int rc = ensure_packet_capacity(n, stride);
+    if (rc != 0) {
+      return rc;
+    }
+    if (n > 0 && !be.h2d(aos_staging, aos, n * stride)) {
+      return fail("upload_packets: host-to-device copy failed: " + be.last_error());
+    }
+    npackets = n;
+    aos_stride = stride;
+    if (!be.aos_to_soa(T, aos_staging, n, stride)) {
+      return fail("upload_packets: conversion kernel failed: " + be.last_error());
+    }
+    return 0;
+  }
+
+  int download_packets(void* aos, const int64_t n, const int stride) {
+    if (n != npackets || stride != aos_stride) {
+      return fail("download_packets: count/stride differ from the uploaded packets");
+    }
+    if (!be.soa_to_aos(T, aos_staging, n, stride)) {
+      return fail("download_packets: conversion kernel failed: " + be.last_error());
+    }
+    if (n > 0 && !be.d2h(aos, aos_staging, n * stride)) {
+      return fail("download_packets: device-to-host copy failed: " + be.last_error());
+    }
+    return 0;
+  }
+
+  int update_packets(const int nts) {
+    if (!timestep_begun || nts != T.nts) {
+      return fail("update_packets: begin_timestep(nts) must be called first");
+    }
+    if (npackets <= 0) {
+      return fail("update_packets: no packets uploaded");
+    }
+    if (!be.propagate(T, npackets, sort_packets != 0, &last_total_ms, &last_propagate_ms, &last_schedule_ms)) {
+      return fail("update_packets: propagation failed: " + be.last_error());
+    }
+    return 0;
+  }
+
+  int save_packets_device() {
+    if (npackets <= 0) {
+      return fail("save_packets_device: no packets");
+    }
+    if (soa_save_count < npackets) {
+      for (void* ptr : soa_save) {
+        be.free(ptr);
+      }
+      soa_save.clear();
+#define X(type, name) soa_save.push_back(be.alloc(npackets * static_cast<int64_t>(sizeof(type))));
+      AB_PACKET_FIELDS(X)
+#undef X
+      soa_save_count = npackets;
+    }
+    size_t k = 0;
+#define X(type, name) be.d2d(soa_save[k++], T.pkt.name, npackets * static_cast<int64_t>(sizeof(type)));
+    AB_PACKET_FIELDS(X)
+#undef X
+    return 0;
+  }
+
+  int restore_packets_device() {
+    if (soa_save.empty() || soa_save_count < npackets) {
+      return fail("restore_packets_device: nothing saved");
+    }
+    size_t k = 0;
+#define X(type, name) be.d2d(T.pkt.name, soa_save[k++], npackets * static_cast<int64_t>(sizeof(type)));
+    AB_PACKET_FIELDS(X)
+#undef X
+    return 0;
+  }
+};
+
+}  // namespace ab

@@ -1,0 +1,261 @@
+// Macro-atom random walk (Lucy 2002/2003 transition-probability scheme) on the precomputed per-cell tables.
+// Reference: macroatom.cc:360-596 (do_macroatom), 204-244 (raddeexcitation), 248-294 (radrecomb),
+// 298-322 (ionisation), 44-62 (cumulative-array views); sn3d.h:85-92 (index_upperbound).
+#pragma once
+#include "atomicdata.h"
+#include "emit.h"
+#include "hd.h"
+#include "options.h"
+#include "packet.h"
+#include "rates.h"
+
+namespace ab {
+
+// first index in [0, n) whose value is > target (std::upper_bound); counts probe loads for the roofline
+AHD int index_upperbound(const double* a, const int n, const double target, const Ctx& c) {
+  int lo = 0;
+  int len = n;
+  int probes = 0;
+  while (len > 0) {
+    const int half = len >> 1;
+    probes++;
+    if (!(target < a[lo + half])) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  c.work(DIAG_BINSEARCH_STEPS, probes);
+  return lo;
+}
+
+AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
+  const Tables& T = c.T;
+  const int cell = T.propcell_nonemptymgi[p.cellindex];
+  const auto T_e = T.Te[cell];
+  const auto clumpednne_ = T.clumpfactor[cell] * T.nne[cell];
+
+  const int element = mastate.element;
+  int ion = mastate.ion;
+  int level = mastate.level;
+  const int activatingline = mastate.activatingline;
+
+  const double* cellrates = T.cell_maprocessrates + (static_cast<long long>(cell) * T.nlevels * MA_ACTION_COUNT);
+  const double* cellmatrans = T.cell_matrans + (static_cast<long long>(cell) * T.matrans_total);
+
+  bool end_packet = false;
+  while (!end_packet) {
+    const int ustart = levelstart(T, element, ion);
+    const int ulev = ustart + level;
+    const double epsilon_current = epsilon(T, ulev);
+    const double* levelrates = cellrates + (static_cast<long long>(ulev) * MA_ACTION_COUNT);
+
+    // partial sums of the 9 process rates (macroatom.cc:424-425) and selection by upper_bound (433-437)
+    double cumulative[MA_ACTION_COUNT];
+    double running = 0.;
+#pragma unroll
+    for (int a = 0; a < MA_ACTION_COUNT; a++) {
+      running = (a == 0) ? levelrates[0] : running + levelrates[a];
+      cumulative[a] = running;
+    }
+    const double total_rate = cumulative[MA_ACTION_COUNT - 1];
+    const double randomrate = p.rng.uniform() * total_rate;
+    int selected_action = 0;
+#pragma unroll
+    for (int a = 0; a < MA_ACTION_COUNT; a++) {
+      selected_action += (!(randomrate < cumulative[a])) ? 1 : 0;  // == upper_bound on a sorted array
+    }
+    selected_action = (selected_action < MA_ACTION_COUNT - 1) ? selected_action : MA_ACTION_COUNT - 1;
+
+    c.count(CNT_INTERACTIONS);
+    c.work(DIAG_MA_STEPS);
+
+    const int ndowntrans = T.level_ndowntrans[ulev];
+    const double* transblock = cellmatrans + T.level_matransblock_start[ulev];
+
+    switch (selected_action) {
+      case MA_ACTION_RADDEEXC: {
+        // macroatom.cc:204-244
+        const double targetval = p.rng.uniform() * levelrates[MA_ACTION_RADDEEXC];
+        const int downtransindex = index_upperbound(transblock, ndowntrans - 1, targetval, c);
+        const int alltrans_startdown = T.level_alltrans_startdown[ulev];
+        const int lineindex = T.trans_lineindex[alltrans_startdown + downtransindex];
+        if (lineindex == activatingline) {
+          c.count(CNT_RESONANCESCATTERINGS);
+        }
+        const int ulevlower = ustart + T.trans_targetlevelindex[alltrans_startdown + downtransindex];
+        const double epsilon_trans = epsilon_current - epsilon(T, ulevlower);
+        const double oldnucmf = p.nu_cmf;
+        p.nu_cmf = epsilon_trans / H;
+        if (activatingline >= 0) {
+          c.count((oldnucmf < p.nu_cmf) ? CNT_UPSCATTER : CNT_DOWNSCATTER);
+        }
+        c.count(CNT_MA_STAT_DEACTIVATION_BB);
+        emit_rpkt(p, c);
+        p.next_trans = lineindex + 1;
+        T.pkt.emissiontype[c.ip] = lineindex;
+        T.pkt.nscatterings[c.ip] = 0;
+        end_packet = true;
+        break;
+      }
+
+      case MA_ACTION_COLDEEXC: {
+        c.count(CNT_MA_STAT_DEACTIVATION_COLLDEEXC);
+        p.type = TYPE_KPKT;
+        end_packet = true;
+        if constexpr (!opt::DIRECT_COL_HEAT) {
+          atomic_add(&T.est_colheating[cell], p.e_cmf);
+          c.work(DIAG_ESTIMATOR_ADDS);
+        }
+        break;
+      }
+
+      case MA_ACTION_INTERNALDOWNSAME: {
+        const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALDOWNSAME];
+        const int downtransindex = index_upperbound(transblock + ndowntrans, ndowntrans - 1, targetval, c);
+        level = T.trans_targetlevelindex[T.level_alltrans_startdown[ulev] + downtransindex];
+        break;
+      }
+
+      case MA_ACTION_RADRECOMB: {
+        // macroatom.cc:248-294
+        const double targetval = p.rng.uniform() * levelrates[MA_ACTION_RADRECOMB];
+        double rate = 0;
+        const int nlevels = nlevels_ionising(T, element, ion - 1);
+        const int lowerionstart = levelstart(T, element, ion - 1);
+        int lowerionlevel = -1;
+        int selected_phixstargetindex = -1;
+        for (int tmp = 0; tmp < nlevels; tmp++) {
+          const int phixstargetindex = find_phixstargetindex(T, lowerionstart + tmp, level);
+          if (phixstargetindex < 0) {
+            continue;
+          }
+          const double epsilon_trans = epsilon_current - epsilon(T, lowerionstart + tmp);
+          const double R = rad_recombination_ratecoeff(T, T_e, clumpednne_, element, ion, tmp, phixstargetindex);
+          rate += R * epsilon_trans;
+          if (targetval < rate) {
+            lowerionlevel = tmp;
+            selected_phixstargetindex = phixstargetindex;
+            break;
+          }
+        }
+        if (lowerionlevel < 0) {
+          // cannot happen for consistent tables (reference: assert_always). Deactivate to the last possible
+          // continuum rather than looping forever.
+          for (int tmp = nlevels - 1; tmp >= 0 && lowerionlevel < 0; tmp--) {
+            const int phixstargetindex = find_phixstargetindex(T, lowerionstart + tmp, level);
+            if (phixstargetindex >= 0) {
+              lowerionlevel = tmp;
+              selected_phixstargetindex = phixstargetindex;
+            }
+          }
+        }
+        const int lowerion = ion - 1;
+        p.nu_cmf = select_continuum_nu(T, element, lowerion, lowerionlevel, selected_phixstargetindex, T_e, p.rng);
+        c.count(CNT_MA_STAT_DEACTIVATION_FB);
+        emit_rpkt(p, c);
+        p.next_trans = -1;
+        T.pkt.emissiontype[c.ip] = emtype_continuum(T, lowerionstart + lowerionlevel, selected_phixstargetindex);
+        T.pkt.nscatterings[c.ip] = 0;
+        level = lowerionlevel;
+        ion -= 1;
+        end_packet = true;
+        break;
+      }
+
+      case MA_ACTION_COLRECOMB: {
+        c.count(CNT_MA_STAT_DEACTIVATION_COLLRECOMB);
+        p.type = TYPE_KPKT;
+        end_packet = true;
+        if constexpr (!opt::DIRECT_COL_HEAT) {
+          atomic_add(&T.est_colheating[cell], p.e_cmf);
+          c.work(DIAG_ESTIMATOR_ADDS);
+        }
+        break;
+      }
+
+      case MA_ACTION_INTERNALDOWNLOWER: {
+        c.count(CNT_MA_STAT_INTERNALDOWNLOWER);
+        const double targetrate = p.rng.uniform() * levelrates[MA_ACTION_INTERNALDOWNLOWER];
+        double rate = 0.;
+        const int nlevels = nlevels_ionising(T, element, ion - 1);
+        int lower = -1;
+        const int lowerionstart = levelstart(T, element, ion - 1);
+        for (int tmp = 0; tmp < nlevels; tmp++) {
+          const int phixstargetindex = find_phixstargetindex(T, lowerionstart + tmp, level);
+          if (phixstargetindex < 0) {
+            continue;
+          }
+          const double epsilon_target = epsilon(T, lowerionstart + tmp);
+          const double epsilon_trans = epsilon_current - epsilon_target;
+          const double R = rad_recombination_ratecoeff(T, T_e, clumpednne_, element, ion, tmp, phixstargetindex);
+          const double C = col_recombination_ratecoeff(T, T_e, clumpednne_, element, ion, tmp, phixstargetindex, epsilon_trans);
+          rate += (R + C) * epsilon_target;
+          if (rate > targetrate) {
+            lower = tmp;
+            break;
+          }
+        }
+        if (lower < 0) {
+          lower = 0;  // reference: assert_always(lower >= 0)
+        }
+        ion--;
+        level = lower;
+        break;
+      }
+
+      case MA_ACTION_INTERNALUPSAME: {
+        const int nuptrans = T.level_nuptrans[ulev];
+        const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALUPSAME];
+        const int uptransindex = index_upperbound(transblock + (2 * ndowntrans), nuptrans - 1, targetval, c);
+        level = T.trans_targetlevelindex[alltrans_startup(T, ulev) + uptransindex];
+        break;
+      }
+
+      case MA_ACTION_INTERNALUPHIGHER: {
+        // macroatom.cc:298-322
+        c.count(CNT_MA_STAT_INTERNALUPHIGHER);
+        const double targetrate = p.rng.uniform() * levelrates[MA_ACTION_INTERNALUPHIGHER];
+        double rate = 0.;
+        const int nphixstargets = T.level_nphixstargets[ulev];
+        int newlevel = -1;
+        for (int phixstargetindex = 0; phixstargetindex < nphixstargets; phixstargetindex++) {
+          const double epsilon_trans = phixs_threshold(T, element, ion, level, phixstargetindex);
+          const double R = cell_corrphotoioncoeff(T, cell, ulev, phixstargetindex);
+          const double C = col_ionisation_ratecoeff(T, T_e, clumpednne_, element, ion, level, phixstargetindex, epsilon_trans);
+          rate += (R + C) * epsilon_current;
+          if (rate > targetrate) {
+            newlevel = phixsupperlevel(T, ulev, phixstargetindex);
+            break;
+          }
+        }
+        if (newlevel < 0) {
+          newlevel = phixsupperlevel(T, ulev, nphixstargets - 1);  // reference: assert_always(false)
+        }
+        level = newlevel;
+        ion += 1;
+        break;
+      }
+
+      default: {  // MA_ACTION_INTERNALUPHIGHERNT: nt_random_upperion without Spencer-Fano gives ion + 1
+        ion = ion + 1;
+        level = 0;
+        c.count(CNT_MA_STAT_INTERNALUPHIGHERNT);
+        break;
+      }
+    }
+  }
+
+  if (p.type == TYPE_RPKT) {
+    // macroatom.cc:579-590
+    if (T.pkt.trueemissiontype[c.ip] == EMTYPE_NOTSET) {
+      T.pkt.trueemissiontype[c.ip] = T.pkt.emissiontype[c.ip];
+      set_trueem_here(p, c);
+    }
+  } else {
+    T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
+  }
+}
+
+}  // namespace ab

@@ -1,0 +1,425 @@
+// r-packet transport: continuum opacity, Sobolev line walk, event handling and estimator accumulation.
+// Reference: rpkt.cc:54-68 (get_nu_cmf_abort), 75-100 (get_tau_sobolev), 106-219 (get_possible_event),
+// 422-497 (rpkt_event_continuum), 502-538 (update_estimators), 542-693 (do_rpkt_step), 697-710
+// (calculate_chi_ffheating), 721-928 (calculate_chi_bf_gammacontr), 1020-1044 (calculate_chi_rpkt_cont);
+// rpkt.h:117-135 (get_linedistance), 144-176 (closest_transition); radfield.cc:745-771 (update_estimators).
+#pragma once
+#include "atomicdata.h"
+#include "emit.h"
+#include "geometry.h"
+#include "hd.h"
+#include "macroatom.h"
+#include "options.h"
+#include "packet.h"
+#include "vec.h"
+
+namespace ab {
+
+// next line redder than nu_cmf, or -1 (rpkt.h:144-176). linelist nu is sorted descending.
+AHD int closest_transition(const Tables& T, const double nu_cmf, const int next_trans, const Ctx& c) {
+  const int nlines = T.nlines;
+  if (next_trans > (nlines - 1)) {
+    return -1;
+  }
+  if (nu_cmf < T.line_nu[nlines - 1]) {
+    return -1;
+  }
+  if (next_trans > 0) {
+    return next_trans;
+  }
+  if (nu_cmf >= T.line_nu[0]) {
+    return 0;
+  }
+  // lower_bound with std::greater: first index where !(nu[i] > nu_cmf)
+  int lo = 0;
+  int len = nlines;
+  int probes = 0;
+  while (len > 0) {
+    const int half = len >> 1;
+    probes++;
+    if (T.line_nu[lo + half] > nu_cmf) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  c.work(DIAG_BINSEARCH_STEPS, probes);
+  return lo;
+}
+
+// rpkt.h:117-135
+AHD double get_linedistance(const double prop_time, const double nu_cmf, const double nu_trans,
+                            const double dnu_on_dl) {
+  if (nu_cmf <= nu_trans) {
+    return 0.;
+  }
+  const double delta_nu = nu_cmf - nu_trans;
+  if constexpr (opt::USE_RELATIVISTIC_DOPPLER_SHIFT) {
+    return -delta_nu / dnu_on_dl;
+  }
+  return CLIGHT * prop_time * delta_nu / nu_trans;
+}
+
+// rpkt.cc:54-68: comoving frequency at the abort distance, moved in two halves like do_rpkt_step
+AHD double get_nu_cmf_abort(const double* pos, const double* dir, const double prop_time, const double nu_rf,
+                            const double abort_dist) {
+  const double half_abort_dist = abort_dist / 2.;
+  const double abort_time = prop_time + (half_abort_dist / CLIGHT_PROP) + (half_abort_dist / CLIGHT_PROP);
+  const double abort_pos[3] = {
+      pos[0] + (dir[0] * half_abort_dist) + (dir[0] * half_abort_dist),
+      pos[1] + (dir[1] * half_abort_dist) + (dir[1] * half_abort_dist),
+      pos[2] + (dir[2] * half_abort_dist) + (dir[2] * half_abort_dist),
+  };
+  return nu_rf * doppler_nucmf_on_nurf(abort_pos, dir, abort_time);
+}
+
+// rpkt.cc:75-100 with the cell's level-population table
+AHD double get_tau_sobolev(const Tables& T, const double* cellpops, const int lineindex, const double t_current) {
+  const double n_l = cellpops[T.line_lower[lineindex]];
+  const double n_u = cellpops[T.line_upper[lineindex]];
+  const double B_ul = T.line_B_ul[lineindex];
+  const double B_lu = T.line_B_lu[lineindex];
+  return dmax(((B_lu * n_l) - (B_ul * n_u)) * HCLIGHTOVERFOURPI * t_current, 0.);
+}
+
+// rpkt.cc:697-710
+AHD double calculate_chi_ffheating(const Tables& T, const int cell, const double nu) {
+  const auto clumpednne_ = T.nne[cell] * T.clumpfactor[cell];
+  const auto T_e = T.Te[cell];
+  const double chi_ff_nnionpart = T.cell_chi_ff_nnionpart[cell];
+  return chi_ff_nnionpart / pow3(nu) * clumpednne_ * (1 - exp(-HOVERKB * nu / T_e));
+}
+
+// Sum the bound-free opacity at nu over the window of continua with nu_edge <= nu <= nu_edge * last_phixs_nuovernuedge,
+// walking the cell's keep-bitmap a 64-bit word at a time (rpkt.cc:721-928).
+//   SELECT == false: returns chi_bf and records the per-ground-continuum sigma contributions in the thread's scratch
+//   SELECT == true : returns (as a double) the index of the continuum at which the running sum first exceeds
+//                    `threshold` (or the last continuum of the window), writes nothing
+template <bool SELECT>
+AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const double nu, const double threshold) {
+  const Tables& T = c.T;
+  double chi_bf_sum = 0.;
+  const int ng = T.nbfcontinua_ground;
+  if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
+    for (int i = 0; i < ng; i++) {
+      *c.groundcont_contr(i) = 0.;
+    }
+  }
+  const auto T_e = T.Te[cell];
+  const double exp_minus_hnu_over_kte = exp(-HOVERKB * nu / T_e);
+  const bool stimfactor_split_usable = (exp_minus_hnu_over_kte >= DBL_MIN_);
+
+  const double* nu_edge_arr = T.cont_nu_edge;
+  const int allcontend = upper_bound_idx(nu_edge_arr, T.nbfcontinua, nu);
+  const int allcontbegin = lower_bound_idx(nu_edge_arr, allcontend, nu / T.last_phixs_nuovernuedge);
+  c.work(DIAG_BINSEARCH_STEPS, 2 * T.log2_nbf);
+
+  const long long base = static_cast<long long>(cell) * T.nbfcontinua;
+  const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
+  int nterms = 0;
+
+  for (int word = allcontbegin / 64; word * 64 < allcontend; word++) {
+    unsigned long long bits = keepbits[word];
+    if (word == (allcontbegin / 64)) {
+      bits &= ~0ULL << static_cast<unsigned>(allcontbegin % 64);
+    }
+    if (((word + 1) * 64) > allcontend) {
+      bits &= ~0ULL >> static_cast<unsigned>(64 - (allcontend % 64));
+    }
+    while (bits != 0) {
+      const int i = (word * 64) + lowest_set_bit(bits);
+      bits &= bits - 1;
+      nterms++;
+
+      const double nnlevel = T.cell_cont_nnlevel[base + i];
+      const double nu_edge = nu_edge_arr[i];
+      const double sigma_bf =
+          photoionisation_crosssection_fromtable(T, phixs_table(T, T.cont_uniquelevelindex[i]), nu_edge, nu);
+
+      const double stimfactor_edgepart = T.cell_cont_edgepart[base + i];
+      double stimfactor;
+      if (stimfactor_edgepart >= 0. && stimfactor_split_usable) {
+        stimfactor = stimfactor_edgepart * exp_minus_hnu_over_kte;
+      } else {
+        stimfactor = T.cell_cont_departure[base + i] * exp(-HOVERKB * (nu - nu_edge) / T_e);
+      }
+      const double corrfactor = dmax(0., 1 - stimfactor);
+      const double sigma_contr = sigma_bf * T.cont_probability[i] * corrfactor;
+
+      if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
+        const int g = T.cont_groundcontestimindex[i];
+        if (g >= 0) {
+          *c.groundcont_contr(g) = sigma_contr;
+        }
+      }
+      chi_bf_sum += nnlevel * sigma_contr;
+      if constexpr (SELECT) {
+        if (chi_bf_sum > threshold) {
+          return static_cast<double>(i);
+        }
+      }
+    }
+  }
+  if constexpr (SELECT) {
+    return static_cast<double>(allcontend - 1);
+  }
+  c.work(DIAG_CONT_TERMS, nterms);
+  return chi_bf_sum;
+}
+
+// rpkt.cc:1020-1044: (re)evaluate the continuum opacity unless the cached value is for the same cell and a
+// frequency within 1e-4 (the cache lives for one packet within one timestep)
+AHD void calculate_chi_rpkt_cont(const Ctx& c, const double nu_cmf, ChiCont& chi, const int cell) {
+  if ((cell == chi.nonemptymgi) && (fabs((chi.nu / nu_cmf) - 1.0) < 1e-4)) {
+    return;
+  }
+  const Tables& T = c.T;
+  const auto nne = T.nne[cell];
+  chi.chi_freefree_heat = calculate_chi_ffheating(T, cell, nu_cmf);
+  chi.chi_escatter = SIGMA_T * nne;
+  chi.chi_boundfree = calculate_chi_bf_gammacontr<false>(c, cell, nu_cmf, 0.);
+  chi.nonemptymgi = cell;
+  chi.nu = nu_cmf;
+  c.work(DIAG_CONT_EVALS);
+}
+
+struct PossibleEvent {
+  double edist;
+  int next_trans;
+  bool is_boundbound;
+};
+
+// rpkt.cc:106-219: walk red-ward through the line list accumulating Sobolev + continuum optical depth
+AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p, const ChiCont& chi,
+                                     MacroAtomState& mastate, const double tau_rnd, const double abort_dist,
+                                     const double nu_cmf_abort, const double dnu_on_dl, const double doppler) {
+  const Tables& T = c.T;
+  double pos[3] = {p.pos[0], p.pos[1], p.pos[2]};
+  double nu_cmf = p.nu_cmf;
+  double e_cmf = p.e_cmf;
+  double prop_time = p.prop_time;
+  int next_trans = p.next_trans;
+  const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
+
+  const double chi_cont = chi.total() * doppler;
+  double tau = 0.;
+  double dist = 0.;
+  long long nvisited = 0;
+  while (true) {
+    const int lineindex = closest_transition(T, nu_cmf, next_trans, c);
+    if (lineindex < 0) {
+      c.work(DIAG_LINES_VISITED, nvisited);
+      const double tau_cont = chi_cont * (abort_dist - dist);
+      if (tau_rnd - tau > tau_cont) {
+        return {DBL_MAX_, next_trans, false};
+      }
+      return {dist + ((tau_rnd - tau) / chi_cont), T.nlines + 1, false};
+    }
+    nvisited++;
+    const double nu_trans = T.line_nu[lineindex];
+    next_trans = lineindex + 1;
+    const double ldist = get_linedistance(prop_time, nu_cmf, nu_trans, dnu_on_dl);
+    const double tau_cont = chi_cont * ldist;
+
+    if (tau_rnd - tau > tau_cont) {
+      if (nu_trans < nu_cmf_abort) {
+        c.work(DIAG_LINES_VISITED, nvisited);
+        return {DBL_MAX_, next_trans - 1, false};
+      }
+      const double tau_line = get_tau_sobolev(T, cellpops, lineindex, prop_time);
+      if ((tau_rnd - tau) <= (tau_cont + tau_line)) {
+        const int element = T.line_elementindex[lineindex];
+        const int ion = T.line_ionindex[lineindex];
+        const int upper = T.line_upper[lineindex] - levelstart(T, element, ion);
+        mastate = {element, ion, upper, lineindex};
+        c.work(DIAG_LINES_VISITED, nvisited);
+        return {dist + ldist, next_trans, true};
+      }
+      dist += ldist;
+      tau += tau_cont + tau_line;
+      if constexpr (!opt::USE_RELATIVISTIC_DOPPLER_SHIFT) {
+        move_withtime(pos, p.dir, prop_time, p.nu_rf, nu_cmf, p.e_rf, e_cmf, ldist);
+      } else {
+        pos[0] += (p.dir[0] * ldist);
+        pos[1] += (p.dir[1] * ldist);
+        pos[2] += (p.dir[2] * ldist);
+        prop_time += ldist / CLIGHT_PROP;
+        nu_cmf = p.nu_cmf + (dnu_on_dl * dist);
+      }
+    } else {
+      c.work(DIAG_LINES_VISITED, nvisited);
+      return {dist + ((tau_rnd - tau) / chi_cont), next_trans - 1, false};
+    }
+  }
+}
+
+// radfield.cc:745-771 + rpkt.cc:502-538
+AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf, const double distance, const int cell,
+                           const ChiCont& chi, const bool thickcell) {
+  const Tables& T = c.T;
+  const double distance_e_cmf = distance * e_cmf;
+  if (distance_e_cmf != 0) {
+    atomic_add(&T.est_J[cell], distance_e_cmf);
+    atomic_add(&T.est_nuJ[cell], distance_e_cmf * nu_cmf);
+    c.work(DIAG_ESTIMATOR_ADDS, 2);
+  }
+  if (thickcell) {
+    return;
+  }
+  atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
+  c.work(DIAG_ESTIMATOR_ADDS, 1);
+
+  if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
+    const int ng = T.nbfcontinua_ground;
+    for (int i = 0; i < ng; i++) {
+      const double nu_edge = T.groundcont_nu_edge[i];
+      if (nu_cmf <= nu_edge) {
+        return;
+      }
+      const long long ionestimindex = (static_cast<long long>(cell) * ng) + i;
+      const double contr = *c.groundcont_contr(i);
+      if constexpr (opt::USE_LUT_PHOTOION) {
+        atomic_add(&T.est_gamma[ionestimindex], contr * (distance_e_cmf / nu_cmf));
+      }
+      if constexpr (opt::USE_ION_BFHEATING_ESTIMATORS) {
+        atomic_add(&T.est_bfheating[ionestimindex], contr * distance_e_cmf * (1. - (nu_edge / nu_cmf)));
+      }
+      c.work(DIAG_ESTIMATOR_ADDS, 2);
+    }
+  }
+}
+
+// rpkt.cc:422-497
+AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
+  const Tables& T = c.T;
+  const double nu = p.nu_cmf;
+  const double dopplerfactor = doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
+  const double chi_cont = chi.total() * dopplerfactor;
+  const double chi_escatter = chi.chi_escatter * dopplerfactor;
+  const double chi_ff = chi.chi_freefree_heat * dopplerfactor;
+  const double chi_bf = chi.chi_boundfree * dopplerfactor;
+
+  const double chi_rnd = p.rng.uniform() * chi_cont;
+  if (chi_rnd < chi_escatter) {
+    T.pkt.nscatterings[c.ip]++;
+    c.count(CNT_ELECTRON_SCATTERINGS);
+    electron_scatter_rpkt(p);
+    set_em_here(p, c);
+  } else if (chi_rnd < chi_escatter + chi_ff) {
+    c.count(CNT_K_STAT_FROM_FF);
+    p.type = TYPE_KPKT;
+    T.pkt.absorptiontype[c.ip] = ABSTYPE_FREEFREE;
+  } else {
+    // reference asserts chi_rnd < chi_escatter + chi_ff + chi_bf; within rounding it always is
+    (void)chi_bf;
+    T.pkt.absorptiontype[c.ip] = ABSTYPE_BOUNDFREE;
+    const double chi_bf_rand = p.rng.uniform() * chi.chi_boundfree;
+    const int allcontindex = static_cast<int>(calculate_chi_bf_gammacontr<true>(c, chi.nonemptymgi, chi.nu, chi_bf_rand));
+    const double nu_edge = T.cont_nu_edge[allcontindex];
+    const int element = T.cont_element[allcontindex];
+    const int ion = T.cont_ion[allcontindex];
+    const int level = T.cont_level[allcontindex];
+    const int phixstargetindex = T.cont_phixstargetindex[allcontindex];
+    if (p.rng.uniform() < nu_edge / nu) {
+      c.count(CNT_MA_STAT_ACTIVATION_BF);
+      do_macroatom(p, c, {element, ion + 1, phixsupperlevel(T, uniquelevel(T, element, ion, level), phixstargetindex), -99});
+    } else {
+      c.count(CNT_K_STAT_FROM_BF);
+      p.type = TYPE_KPKT;
+    }
+  }
+}
+
+// One r-packet step (rpkt.cc:542-693). Returns true if the packet can keep going in this call: still an
+// r-packet and not at the end of the timestep. (The reference additionally returns to its scheduler on a
+// change of model cell, a CPU cell-cache artefact that the all-cells-resident device tables do not need.)
+AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
+  const Tables& T = c.T;
+  const int cell = T.propcell_nonemptymgi[p.cellindex];
+  MacroAtomState pktmastate = {-1, -1, -1, -99};
+  c.work(DIAG_RPKT_STEPS);
+
+  const double tau_rnd = -log(static_cast<double>(p.rng.uniform_pos()));
+
+  const BoundaryHit hit = boundary_distance(T, p.dir, p.pos, p.prop_time, p.cellindex);
+  const double boundarydist = hit.distance;
+  const int next_cellindex = hit.next_cellindex;
+
+  if (boundarydist == 0) {
+    change_cell_or_escape(p, c, next_cellindex);
+    return (p.type == TYPE_RPKT);
+  }
+
+  const double tdist = (t2 - p.prop_time) * CLIGHT_PROP;
+  const double abort_dist = dmin(tdist, boundarydist);
+
+  double edist = -1;
+  bool event_is_boundbound = true;
+  const bool thickcell = (cell >= 0) && (T.thick[cell] == CELL_THICK);
+  if (cell < 0) {
+    edist = DBL_MAX_;
+    p.next_trans = -1;
+  } else if (thickcell) {
+    const double chi_grey = T.kappagrey[cell] * T.rho[cell] * doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
+    edist = tau_rnd / chi_grey;
+    p.next_trans = -1;
+  } else {
+    calculate_chi_rpkt_cont(c, p.nu_cmf, chi, cell);
+    const double nu_cmf_abort = get_nu_cmf_abort(p.pos, p.dir, p.prop_time, p.nu_rf, abort_dist);
+    const double dnu_on_dl = (nu_cmf_abort - p.nu_cmf) / abort_dist;
+    const double doppler = doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
+    const PossibleEvent ev =
+        get_possible_event(c, cell, p, chi, pktmastate, tau_rnd, abort_dist, nu_cmf_abort, dnu_on_dl, doppler);
+    edist = ev.edist;
+    p.next_trans = ev.next_trans;
+    event_is_boundbound = ev.is_boundbound;
+  }
+
+  if ((edist < boundarydist) && (edist <= tdist)) {
+    move_pkt_withtime(p, edist / 2.);
+    update_estimators(c, p.e_cmf, p.nu_cmf, edist, cell, chi, thickcell);
+    move_pkt_withtime(p, edist / 2.);
+
+    c.count(CNT_INTERACTIONS);
+    if (thickcell) {
+      T.pkt.nscatterings[c.ip]++;
+      c.count(CNT_ELECTRON_SCATTERINGS);
+      emit_rpkt(p, c);
+    } else if (!event_is_boundbound) {
+      rpkt_event_continuum(p, c, chi);
+    } else {
+      c.count(CNT_MA_STAT_ACTIVATION_BB);
+      T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
+      T.pkt.absorptionfreq[c.ip] = p.nu_rf;
+      do_macroatom(p, c, pktmastate);
+    }
+    return (p.type == TYPE_RPKT);
+  }
+
+  if ((boundarydist <= tdist) && (boundarydist <= edist)) {
+    move_pkt_withtime(p, boundarydist / 2.);
+    if (cell >= 0) {
+      update_estimators(c, p.e_cmf, p.nu_cmf, boundarydist, cell, chi, thickcell);
+    }
+    move_pkt_withtime(p, boundarydist / 2.);
+    if (next_cellindex != p.cellindex) {
+      change_cell_or_escape(p, c, next_cellindex);
+      if (next_cellindex < 0) {
+        return false;
+      }
+    }
+    return true;
+  }
+
+  // end of timestep reached before a boundary or an interaction
+  move_pkt_withtime(p, tdist / 2.);
+  if (cell >= 0) {
+    update_estimators(c, p.e_cmf, p.nu_cmf, tdist, cell, chi, thickcell);
+  }
+  move_pkt_withtime(p, tdist / 2.);
+  p.prop_time = t2;
+  return false;
+}
+
+}  // namespace ab

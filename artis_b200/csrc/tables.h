@@ -1,0 +1,274 @@
+// The flat table set the kernels read: every implicit global of the reference's update_packets() path
+//  as a raw pointer or scalar. One instance lives on the host (pointers are DEVICE pointers
+// in the product build) and is passed to each kernel by value as a __grid_constant__ parameter.
+//
+// Data layout in HBM: all tables are structure-of-arrays, exactly mirroring the reference's
+// SoA globals (globals.h:146-263) so that the named arrays of include/artis_b200.h upload without
+// conversion; per-cell tables built on the device are cell-major ([cell][level], [cell][continuum], ...).
+#pragma once
+#include <cstdint>
+
+#include "hd.h"
+
+namespace ab {
+
+// X(type, member, "public name")   — input arrays handed over with artisb200_set_array()
+#define AB_INPUT_ARRAYS(X)                                            \
+  X(double, coord0, "grid.coord_pos_min_tmin0")                       \
+  X(double, coord1, "grid.coord_pos_min_tmin1")                       \
+  X(double, coord2, "grid.coord_pos_min_tmin2")                       \
+  X(int, propcell_nonemptymgi, "grid.propcell_nonemptymgi")           \
+  X(float, ffegrp, "cell.ffegrp")                                     \
+  X(int, elem_anumber, "elem.anumber")                                \
+  X(int, elem_nions, "elem.nions")                                    \
+  X(int, elem_lowest_ionstage, "elem.lowest_ionstage")                \
+  X(int, elem_uniqueionindexstart, "elem.uniqueionindexstart")        \
+  X(int, ion_nlevels, "ion.nlevels")                                  \
+  X(int, ion_nlevels_ionising, "ion.nlevels_ionising")                \
+  X(int, ion_maxrecombininglevel, "ion.maxrecombininglevel")          \
+  X(int, ion_coolingoffset, "ion.coolingoffset")                      \
+  X(int, ion_ncoolingterms, "ion.ncoolingterms")                      \
+  X(int, ion_levelstart, "ion.uniquelevelindexstart")                 \
+  X(int, ion_groundcontindex, "ion.groundcontindex")                  \
+  X(int, ion_nlevels_excited_nlte, "ion.nlevels_excited_nlte")        \
+  X(int, ion_allnltelevelsindexstart, "ion.allnltelevelsindexstart")  \
+  X(double, ion_ionpot, "ion.ionpot")                                 \
+  X(double, level_epsilon, "level.epsilon")                           \
+  X(float, level_statweight, "level.statweight")                      \
+  X(int, level_alltrans_startdown, "level.alltrans_startdown")        \
+  X(int, level_ndowntrans, "level.ndowntrans")                        \
+  X(int, level_nuptrans, "level.nuptrans")                            \
+  X(int, level_closestgroundlevelcont, "level.closestgroundlevelcont")\
+  X(int, level_phixsstart, "level.phixsstart")                        \
+  X(int, level_nphixstargets, "level.nphixstargets")                  \
+  X(int, level_phixstargetstart, "level.phixstargetstart")            \
+  X(int, level_bflist_start, "level.bflist_start")                    \
+  X(int, level_matransblock_start, "level.matransblock_start")        \
+  X(int, trans_lineindex, "trans.lineindex")                          \
+  X(int, trans_targetlevelindex, "trans.targetlevelindex")            \
+  X(float, trans_einstein_A, "trans.einstein_A")                      \
+  X(float, trans_coll_str, "trans.coll_str")                          \
+  X(float, trans_osc_strength, "trans.osc_strength")                  \
+  X(unsigned char, trans_forbidden, "trans.forbidden")                \
+  X(double, line_nu, "line.nu")                                       \
+  X(int, line_elementindex, "line.elementindex")                      \
+  X(int, line_ionindex, "line.ionindex")                              \
+  X(int, line_lower, "line.lower")                                    \
+  X(int, line_upper, "line.upper")                                    \
+  X(float, line_B_ul, "line.B_ul")                                    \
+  X(float, line_B_lu, "line.B_lu")                                    \
+  X(double, cont_nu_edge, "cont.nu_edge")                             \
+  X(int, cont_element, "cont.element")                                \
+  X(int, cont_ion, "cont.ion")                                        \
+  X(int, cont_level, "cont.level")                                    \
+  X(int, cont_phixstargetindex, "cont.phixstargetindex")              \
+  X(int, cont_upperlevel, "cont.upperlevel")                          \
+  X(int, cont_uniquelevelindex, "cont.uniquelevelindex")              \
+  X(double, cont_probability, "cont.probability")                     \
+  X(int, cont_groundcontestimindex, "cont.groundcontestimindex")      \
+  X(int, cont_bfestimindex, "cont.bfestimindex")                      \
+  X(float, phixs_table, "phixs.table")                                \
+  X(int, phixstarget_levelindex, "phixstarget.levelindex")            \
+  X(double, phixstarget_probability, "phixstarget.probability")       \
+  X(double, groundcont_nu_edge, "groundcont.nu_edge")                 \
+  X(double, bfestim_nu_edge, "bfestim.nu_edge")                       \
+  X(double, lut_spontrecomb, "lut.spontrecomb")                       \
+  X(double, lut_corrphotoion, "lut.corrphotoion")                     \
+  X(double, lut_bfcooling, "lut.bfcooling")                           \
+  X(double, lut_temperature_grid, "lut.temperature_grid")             \
+  X(unsigned char, cooling_type, "cooling.type")                      \
+  X(int, cooling_level, "cooling.level")                              \
+  X(int, cooling_phixstargetindex, "cooling.phixstargetindex")        \
+  X(double, ts_start, "timesteps.start")                              \
+  X(double, ts_width, "timesteps.width")                              \
+  X(double, ts_mid, "timesteps.mid")                                  \
+  X(float, rho, "cell.rho")                                           \
+  X(float, Te, "cell.Te")                                             \
+  X(float, TJ, "cell.TJ")                                             \
+  X(float, TR, "cell.TR")                                             \
+  X(float, W, "cell.W")                                               \
+  X(float, nne, "cell.nne")                                           \
+  X(float, nnetot, "cell.nnetot")                                     \
+  X(float, kappagrey, "cell.kappagrey")                               \
+  X(float, clumpfactor, "cell.clumpfactor")                           \
+  X(int, thick, "cell.thick")                                         \
+  X(float, elem_massfracs, "cell.elem_massfracs")                     \
+  X(float, ion_groundlevelpops, "cell.ion_groundlevelpops")           \
+  X(float, ion_partfuncts, "cell.ion_partfuncts")                     \
+  X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
+  X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")
+
+// X(type, member, "public name")   — scalars
+#define AB_INPUT_SCALARS(X)                                  \
+  X(long long, grid_type, "scalar.grid_type")                \
+  X(double, tmin, "scalar.tmin")                             \
+  X(double, rmax, "scalar.rmax")                             \
+  X(double, vmax, "scalar.vmax")                             \
+  X(long long, nphixspoints, "scalar.nphixspoints")          \
+  X(double, nphixsnuincrement, "scalar.nphixsnuincrement")   \
+  X(double, last_phixs_nuovernuedge, "scalar.last_phixs_nuovernuedge") \
+  X(long long, tablesize, "scalar.tablesize")                \
+  X(long long, nts_host, "scalar.nts")                       \
+  X(long long, globals_timestep, "scalar.globals_timestep")  \
+  X(double, max_path_step, "scalar.max_path_step")
+
+// device-side output / work arrays that can be read back with artisb200_get_array()
+#define AB_OUTPUT_ARRAYS(X)                       \
+  X(double, est_J, "est.J")                       \
+  X(double, est_nuJ, "est.nuJ")                   \
+  X(double, est_ffheating, "est.ffheating")       \
+  X(double, est_colheating, "est.colheating")     \
+  X(double, est_gamma, "est.gamma")               \
+  X(double, est_bfheating, "est.bfheating")       \
+  X(double, est_dep_gamma, "est.dep_gamma")       \
+  X(double, est_dep_positron, "est.dep_positron") \
+  X(double, est_dep_electron, "est.dep_electron") \
+  X(double, est_dep_alpha, "est.dep_alpha")       \
+  X(double, ts_scalars, "ts.scalars")             \
+  X(long long, ts_pellet_decays, "ts.pellet_decays") \
+  X(long long, counters, "counters")              \
+  X(long long, diag, "diag")                      \
+  X(double, cell_levelpops, "built.levelpops")    \
+  X(double, cell_maprocessrates, "built.maprocessrates") \
+  X(double, cell_matrans, "built.matrans")        \
+  X(double, cell_cooling_contrib, "built.cooling_contrib") \
+  X(double, cell_cont_nnlevel, "built.cont_nnlevel") \
+  X(unsigned long long, cell_cont_keepbits, "built.cont_keepbits") \
+  X(double, cell_cont_departure, "built.cont_departure") \
+  X(double, cell_cont_edgepart, "built.cont_edgepart") \
+  X(double, cell_chi_ff_nnionpart, "built.chi_ff_nnionpart") \
+  X(double, cell_corrphotoioncoeff, "built.corrphotoioncoeff")
+
+constexpr int NTSSCALARS = 10;  // ARTISB200_NTSSCALARS
+constexpr int NDIAG = 16;       // ARTISB200_NDIAG
+enum : int {
+  TS_GAMMA_DEP_DISCRETE = 0,
+  TS_POSITRON_DEP_DISCRETE = 1,
+  TS_POSITRON_EMISSION = 2,
+  TS_ELECTRON_DEP_DISCRETE = 3,
+  TS_ELECTRON_EMISSION = 4,
+  TS_ALPHA_DEP_DISCRETE = 5,
+  TS_ALPHA_EMISSION = 6,
+  TS_SPFISSION_DEP_DISCRETE = 7,
+  TS_GAMMA_EMISSION = 8,
+  TS_NT_ENERGY_DEPOSITED = 9,
+};
+enum : int {
+  DIAG_RPKT_STEPS = 0,
+  DIAG_LINES_VISITED = 1,
+  DIAG_CONT_EVALS = 2,
+  DIAG_CONT_TERMS = 3,
+  DIAG_BINSEARCH_STEPS = 4,
+  DIAG_ESTIMATOR_ADDS = 5,
+  DIAG_MA_STEPS = 6,
+  DIAG_K_STEPS = 7,
+  DIAG_GAMMA_STEPS = 8,
+  DIAG_GAMMA_EVENTS = 9,
+  DIAG_KERNEL_LAUNCHES = 10,
+  DIAG_PACKET_SEGMENTS = 11,
+};
+
+// SoA packet state (device resident across timesteps). Field set = reference Packet (packet.h:109-156).
+#define AB_PACKET_FIELDS(X)   \
+  X(double, prop_time)        \
+  X(double, pos_x)            \
+  X(double, pos_y)            \
+  X(double, pos_z)            \
+  X(double, dir_x)            \
+  X(double, dir_y)            \
+  X(double, dir_z)            \
+  X(double, nu_cmf)           \
+  X(double, e_cmf)            \
+  X(double, nu_rf)            \
+  X(double, e_rf)             \
+  X(int, next_trans)          \
+  X(int, nscatterings)        \
+  X(int, emissiontype)        \
+  X(double, em_pos_x)         \
+  X(double, em_pos_y)         \
+  X(double, em_pos_z)         \
+  X(float, em_time)           \
+  X(int, absorptiontype)      \
+  X(double, absorptionfreq)   \
+  X(double, stokes_q)         \
+  X(double, stokes_u)         \
+  X(int, trueemissiontype)    \
+  X(double, trueem_pos_x)     \
+  X(double, trueem_pos_y)     \
+  X(double, trueem_pos_z)     \
+  X(float, trueem_time)       \
+  X(int, type)                \
+  X(int, cellindex)           \
+  X(int, escape_type)         \
+  X(float, escape_time)       \
+  X(double, tdecay)           \
+  X(int, number)              \
+  X(int, originated_from_particlenotgamma) \
+  X(int, pellet_decaytype)    \
+  X(int, pellet_nucindex)     \
+  X(unsigned int, rng0)       \
+  X(unsigned int, rng1)       \
+  X(unsigned int, rng2)       \
+  X(unsigned int, rng3)
+
+struct PacketSoA {
+#define X(type, name) type* name;
+  AB_PACKET_FIELDS(X)
+#undef X
+};
+
+struct Tables {
+#define X(type, name, pub) const type* name;
+  AB_INPUT_ARRAYS(X)
+#undef X
+#define X(type, name, pub) type name;
+  AB_INPUT_SCALARS(X)
+#undef X
+#define X(type, name, pub) type* name;
+  AB_OUTPUT_ARRAYS(X)
+#undef X
+  PacketSoA pkt;
+
+  // sizes
+  int ncoord[3];
+  int ngrid;
+  int ncells;  // non-empty model cells (Nc)
+  int nelements;
+  int nions;
+  int nlevels;
+  int nlines;
+  int ntrans;
+  int nbfcontinua;
+  int nbfcontinua_ground;
+  int nphixstargets_total;
+  int ncoolingterms;
+  int ntimesteps;
+  int matrans_total;   // sum over levels of (2*ndown + nup)
+  int keepwords;       // ceil(nbfcontinua / 64)
+  int log2_nbf;        // probes of one binary search over the continuum list
+
+  // current timestep
+  int nts;
+  double ts_begin;
+  double ts_end;
+  double ts_middle;
+  double ts_widthcur;
+  double T_step_log;   // spacing of lut.temperature_grid in log T (ratecoeff.cc:39)
+
+  // derived static tables (built by commit_static)
+  const int* level_uniqueion;   // [nlevels] unique ion index of each level
+  const int* ion_element;       // [nions]
+  const int* ion_index;         // [nions] ion index within its element
+  const int* cont_bflistindex;  // unused placeholder for future lookups
+
+  // run options
+  int rng_mode;
+  unsigned long long seed;
+  long long max_steps_per_launch;
+
+  // per-launch scratch: per-thread ground-continuum contributions [nbfcontinua_ground][nthreads]
+  double* scratch_groundcont;
+  long long scratch_stride;
+};
+
+}  // namespace ab

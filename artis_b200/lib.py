@@ -1,0 +1,167 @@
+"""ctypes binding of the C ABI in include/artis_b200.h.
+
+The product library is artis_b200/_build/libartis_b200_<preset>.so (CUDA, sm_100a). There is no CPU
+fallback: if the library is missing or no CUDA device is usable, construction raises."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import snapshot as snap_mod
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path(preset):
+    return os.path.join(_HERE, "_build", f"libartis_b200_{preset}.so")
+
+
+class ArtisB200Error(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "artisb200_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "artisb200_destroy": (None, [ctypes.c_void_p]),
+    "artisb200_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "artisb200_options_hash": (ctypes.c_uint64, []),
+    "artisb200_options_summary": (ctypes.c_char_p, []),
+    "artisb200_set_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64]),
+    "artisb200_get_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64]),
+    "artisb200_array_count": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p]),
+    "artisb200_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "artisb200_commit_static": (ctypes.c_int, [ctypes.c_void_p]),
+    "artisb200_begin_timestep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "artisb200_upload_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "artisb200_download_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "artisb200_update_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "artisb200_update_packets_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "artisb200_save_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
+    "artisb200_restore_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
+    "artisb200_estimator_device_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
+    "artisb200_last_timing_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "artisb200_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+ESTIMATOR_NAMES = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
+                   "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "ts.pellet_decays", "counters", "diag"]
+_OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "built.cont_keepbits": np.uint64}
+
+
+def load_library(path):
+    if not os.path.exists(path):
+        raise ArtisB200Error(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+class ArtisB200:
+    """One library context on one device. Mirrors the call sequence of the reference driver:
+    static tables once -> per timestep (cell state, begin_timestep, update_packets, read estimators)."""
+
+    def __init__(self, preset=None, device=0, libpath=None):
+        self.libpath = libpath or library_path(preset)
+        self.lib = load_library(self.libpath)
+        handle = ctypes.c_void_p()
+        if self.lib.artisb200_create(ctypes.byref(handle), device) != 0:
+            raise ArtisB200Error(self.lib.artisb200_last_error(None).decode())
+        self.ctx = handle
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.artisb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise ArtisB200Error(f"{what}: {self.lib.artisb200_last_error(self.ctx).decode()}")
+
+    def options_summary(self):
+        return self.lib.artisb200_options_summary().decode()
+
+    def set_option(self, name, value):
+        self._check(self.lib.artisb200_set_option(self.ctx, name.encode(), int(value)), f"set_option({name})")
+
+    def set_array(self, name, arr):
+        arr = np.ascontiguousarray(arr)
+        code = snap_mod.dtype_code(arr).encode()
+        self._check(self.lib.artisb200_set_array(self.ctx, name.encode(), code, arr.ctypes.data_as(ctypes.c_void_p), arr.size),
+                    f"set_array({name})")
+
+    def set_arrays(self, arrays, skip_prefixes=("packets.", "est.", "ts.", "counters", "diag")):
+        for name, arr in arrays.items():
+            if name.startswith(skip_prefixes):
+                continue
+            self.set_array(name, arr)
+
+    def array_count(self, name):
+        return int(self.lib.artisb200_array_count(self.ctx, name.encode()))
+
+    def get_array(self, name, dtype=None):
+        n = self.array_count(name)
+        if n < 0:
+            raise ArtisB200Error(f"array {name} not available")
+        dt = np.dtype(dtype or _OUT_DTYPES.get(name, np.float64))
+        out = np.empty(n, dtype=dt)
+        code = snap_mod.dtype_code(out).encode()
+        self._check(self.lib.artisb200_get_array(self.ctx, name.encode(), code, out.ctypes.data_as(ctypes.c_void_p), n),
+                    f"get_array({name})")
+        return out
+
+    def commit_static(self):
+        self._check(self.lib.artisb200_commit_static(self.ctx), "commit_static")
+
+    def begin_timestep(self, nts):
+        self._check(self.lib.artisb200_begin_timestep(self.ctx, int(nts)), "begin_timestep")
+
+    def upload_packets(self, aos_bytes, npackets, stride):
+        aos_bytes = np.ascontiguousarray(aos_bytes)
+        self._check(self.lib.artisb200_upload_packets(self.ctx, aos_bytes.ctypes.data_as(ctypes.c_void_p), npackets, stride),
+                    "upload_packets")
+
+    def download_packets(self, aos_bytes, npackets, stride):
+        self._check(self.lib.artisb200_download_packets(self.ctx, aos_bytes.ctypes.data_as(ctypes.c_void_p), npackets, stride),
+                    "download_packets")
+
+    def update_packets(self, nts):
+        self._check(self.lib.artisb200_update_packets(self.ctx, int(nts)), "update_packets")
+
+    def update_packets_host(self, nts, aos_bytes, npackets, stride):
+        """the drop-in call: host AoS packets in, propagated host AoS packets out (in place)"""
+        self._check(self.lib.artisb200_update_packets_host(self.ctx, int(nts), aos_bytes.ctypes.data_as(ctypes.c_void_p),
+                                                           npackets, stride), "update_packets_host")
+
+    def save_packets_device(self):
+        self._check(self.lib.artisb200_save_packets_device(self.ctx), "save_packets_device")
+
+    def restore_packets_device(self):
+        self._check(self.lib.artisb200_restore_packets_device(self.ctx), "restore_packets_device")
+
+    def estimator_device_buffer(self):
+        ptr = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        self._check(self.lib.artisb200_estimator_device_buffer(self.ctx, ctypes.byref(ptr), ctypes.byref(n)), "estimator buffer")
+        return ptr.value, n.value
+
+    def last_timing_ms(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self.lib.artisb200_last_timing_ms(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return a.value, b.value, c.value
+
+    def stream(self):
+        return self.lib.artisb200_stream(self.ctx)
+
+    def estimators(self):
+        return {name: self.get_array(name) for name in ESTIMATOR_NAMES}
