@@ -91,6 +91,14 @@ __global__ void k_build_cooling(const __grid_constant__ Tables T) {
   }
 }
 
+__global__ void k_test_kernel(const __grid_constant__ Tables T, const int which, const long long n, const double* in_f64,
+                              const int* in_i32, double* out_f64, int* out_i32) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::test_kernel_item(T, which, i, i, in_f64, in_i32, out_f64, out_i32);
+  }
+}
+
 // queue[0]: next packet index to hand out; queue[1]: packets that still need work after this launch
 __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const long long n,
                                                           unsigned long long* queue) {
@@ -322,6 +330,23 @@ struct CudaBackend {
     const long long ncells = T.ncells;
     cudaMemcpyAsync(&T.counters[ab::CNT_UPDATECELL], &ncells, sizeof(long long), cudaMemcpyHostToDevice, stream);
     return ok(cudaStreamSynchronize(stream), "build_cell_tables") && ok(cudaGetLastError(), "build_cell_tables");
+  }
+
+  bool run_test_kernel(Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,
+                       double* out_f64, int* out_i32) {
+    cudaSetDevice(device);
+    const long long ng = T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1;
+    double* scratch = nullptr;
+    if (!ok(cudaMalloc(&scratch, static_cast<size_t>(n * ng) * sizeof(double)), "cudaMalloc(test scratch)")) {
+      return false;
+    }
+    T.scratch_groundcont = scratch;
+    T.scratch_stride = n;
+    k_test_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(T, which, n, in_f64, in_i32, out_f64, out_i32);
+    const bool good = ok(cudaStreamSynchronize(stream), "k_test_kernel") && ok(cudaGetLastError(), "k_test_kernel");
+    cudaFree(scratch);
+    T.scratch_groundcont = nullptr;
+    return good;
   }
 
   bool aos_to_soa(const Tables& T, const void* aos, const int64_t n, const int stride) {

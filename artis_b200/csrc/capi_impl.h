@@ -120,6 +120,11 @@ int artisb200_last_timing_ms(artisb200_ctx* ctx, double* total_ms, double* propa
   return 0;
 }
 
+int artisb200_test_kernel(artisb200_ctx* ctx, const char* which, const int64_t n, const double* in_f64, const int32_t* in_i32,
+                          double* out_f64, int32_t* out_i32) {
+  return ctx->eng.test_kernel(which, n, in_f64, in_i32, out_f64, out_i32);
+}
+
 void* artisb200_stream(artisb200_ctx* ctx) { return ctx->eng.be.stream_handle(); }
 
 }  // extern "C"

@@ -141,8 +141,46 @@ AHD void reset_philox_one(const Tables& T, const long long i) {
 }  // namespace ab
 
 #include "rates.h"
+#include "rpkt.h"
 
 namespace ab {
+
+enum : int { TESTK_BOUNDARY_DISTANCE = 0, TESTK_CLOSEST_TRANSITION = 1, TESTK_CHI_RPKT_CONT = 2 };
+
+// one element of artisb200_test_kernel()
+AHD void test_kernel_item(const Tables& T, const int which, const long long i, const long long tid, const double* in_f64,
+                          const int* in_i32, double* out_f64, int* out_i32) {
+  int cnt[CNT_COUNT];
+  long long diag[NDIAG];
+  double tss[NTSSCALARS];
+  long long pellet_decays = 0;
+  for (int k = 0; k < CNT_COUNT; k++) {
+    cnt[k] = 0;
+  }
+  for (int k = 0; k < NDIAG; k++) {
+    diag[k] = 0;
+  }
+  const Ctx c{T, 0, tid, cnt, diag, tss, &pellet_decays};
+  if (which == TESTK_BOUNDARY_DISTANCE) {
+    const double* rec = in_f64 + (i * 7);
+    const BoundaryHit hit = boundary_distance(T, rec + 3, rec, rec[6], in_i32[i]);
+    out_f64[i] = hit.distance;
+    out_i32[i] = hit.next_cellindex;
+  } else if (which == TESTK_CLOSEST_TRANSITION) {
+    out_i32[i] = closest_transition(T, in_f64[i], in_i32[i], c);
+  } else {
+    ChiCont chi;
+    chi.nu = -1.;
+    chi.nonemptymgi = -1;
+    chi.chi_escatter = 0.;
+    chi.chi_freefree_heat = 0.;
+    chi.chi_boundfree = 0.;
+    calculate_chi_rpkt_cont(c, in_f64[i], chi, in_i32[i]);
+    out_f64[(i * 3) + 0] = chi.chi_escatter;
+    out_f64[(i * 3) + 1] = chi.chi_freefree_heat;
+    out_f64[(i * 3) + 2] = chi.chi_boundfree;
+  }
+}
 
 AHD void build_levelpop_item(const Tables& T, const int cell, const int ulev) {
   const int uion = T.level_uniqueion[ulev];

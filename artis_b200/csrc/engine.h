@@ -571,6 +571,52 @@ class Engine {
     return 0;
   }
 
+  int test_kernel(const char* which_c, const int64_t n, const double* in_f64, const int* in_i32, double* out_f64,
+                  int* out_i32) {
+    const std::string which(which_c);
+    int code = -1;
+    int64_t nf_in = 0;
+    int64_t nf_out = 0;
+    int64_t ni_out = 0;
+    if (which == "boundary_distance") {
+      code = 0; nf_in = 7 * n; nf_out = n; ni_out = n;
+    } else if (which == "closest_transition") {
+      code = 1; nf_in = n; ni_out = n;
+    } else if (which == "chi_rpkt_cont") {
+      code = 2; nf_in = n; nf_out = 3 * n;
+      if (!timestep_begun) {
+        return fail("test_kernel(chi_rpkt_cont): begin_timestep must be called first");
+      }
+    } else {
+      return fail("test_kernel: unknown kernel '" + which + "'");
+    }
+    if (!static_committed) {
+      return fail("test_kernel: commit_static must be called first");
+    }
+    if (n <= 0) {
+      return 0;
+    }
+    void* d_inf = be.alloc(nf_in * 8);
+    void* d_ini = be.alloc(n * 4);
+    void* d_outf = be.alloc((nf_out > 0 ? nf_out : 1) * 8);
+    void* d_outi = be.alloc((ni_out > 0 ? ni_out : 1) * 4);
+    bool okay = d_inf != nullptr && d_ini != nullptr && d_outf != nullptr && d_outi != nullptr;
+    okay = okay && be.h2d(d_inf, in_f64, nf_in * 8) && be.h2d(d_ini, in_i32, n * 4);
+    okay = okay && be.run_test_kernel(T, code, n, static_cast<const double*>(d_inf), static_cast<const int*>(d_ini),
+                                      static_cast<double*>(d_outf), static_cast<int*>(d_outi));
+    if (okay && nf_out > 0 && out_f64 != nullptr) {
+      okay = be.d2h(out_f64, d_outf, nf_out * 8);
+    }
+    if (okay && ni_out > 0 && out_i32 != nullptr) {
+      okay = be.d2h(out_i32, d_outi, ni_out * 4);
+    }
+    be.free(d_inf);
+    be.free(d_ini);
+    be.free(d_outf);
+    be.free(d_outi);
+    return okay ? 0 : fail("test_kernel failed: " + be.last_error());
+  }
+
   int save_packets_device() {
     if (npackets <= 0) {
       return fail("save_packets_device: no packets");

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "artisb200_restore_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_estimator_device_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "artisb200_last_timing_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "artisb200_test_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "artisb200_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
 }
 
@@ -162,6 +164,18 @@ class ArtisB200:
 
     def stream(self):
         return self.lib.artisb200_stream(self.ctx)
+
+    def test_kernel(self, which, in_f64, in_i32):
+        """element-wise evaluation of a deterministic device function (see include/artis_b200.h)"""
+        in_f64 = np.ascontiguousarray(in_f64, dtype=np.float64)
+        in_i32 = np.ascontiguousarray(in_i32, dtype=np.int32)
+        n = in_i32.size
+        out_f64 = np.zeros(3 * n if which == "chi_rpkt_cont" else n, dtype=np.float64)
+        out_i32 = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.artisb200_test_kernel(self.ctx, which.encode(), n, in_f64.ctypes.data_as(ctypes.c_void_p),
+                                                   in_i32.ctypes.data_as(ctypes.c_void_p), out_f64.ctypes.data_as(ctypes.c_void_p),
+                                                   out_i32.ctypes.data_as(ctypes.c_void_p)), f"test_kernel({which})")
+        return out_f64, out_i32
 
     def estimators(self):
         return {name: self.get_array(name) for name in ESTIMATOR_NAMES}

@@ -157,6 +157,18 @@ int artisb200_estimator_device_buffer(artisb200_ctx* ctx, void** device_ptr, int
  * split as total / propagation kernels / scheduling (sort, compaction). */
 int artisb200_last_timing_ms(artisb200_ctx* ctx, double* total_ms, double* propagate_ms, double* schedule_ms);
 
+/* Element-wise evaluation of the deterministic device functions on caller-supplied inputs, used by the
+ * parity tests (north_star: "boundary_distance, closest_transition indices, cell opacities ... must match
+ * the reference bit-exact for indices and within 1e-12 relative for doubles"). All arrays are host arrays.
+ *   which = "boundary_distance" : in_f64[n*7] = pos xyz, dir xyz, tstart; in_i32[n] = cellindex;
+ *                                 out_f64[n] = distance, out_i32[n] = next cell index (-99 = escape)   (grid.cc:2480)
+ *   which = "closest_transition": in_f64[n] = nu_cmf; in_i32[n] = next_trans; out_i32[n] = line index   (rpkt.h:144)
+ *   which = "chi_rpkt_cont"     : in_f64[n] = nu_cmf; in_i32[n] = nonemptymgi; out_f64[n*3] = chi_escatter,
+ *                                 chi_freefree_heat, chi_boundfree (needs begin_timestep)               (rpkt.cc:1020)
+ * Unused output pointers may be NULL. */
+int artisb200_test_kernel(artisb200_ctx* ctx, const char* which, int64_t n, const double* in_f64, const int32_t* in_i32,
+                          double* out_f64, int32_t* out_i32);
+
 /* Raw CUDA stream handle (cudaStream_t) the library launches on, for event timing by the caller. */
 void* artisb200_stream(artisb200_ctx* ctx);
 

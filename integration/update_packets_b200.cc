@@ -34,7 +34,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <array>
+#include <cmath>
 #include <cstring>
+#include <limits>
 #include <span>
 #include <string>
 #include <vector>
@@ -52,6 +55,7 @@
 #include "nonthermal.h"
 #include "packet.h"
 #include "radfield.h"
+#include "rpkt.h"
 #include "stats.h"
 #include "update_packets.h"
 
@@ -490,7 +494,10 @@ void update_packets_gpu(const int nts, std::span<Packet> packets) {
 // precomputed, update_packets.cc:551-563) a packet's history then depends on nothing but the packet
 // itself, which is what makes packet-by-packet comparison with the device path possible.
 void update_packets_reference_perpacket(const int nts, std::span<Packet> packets) {
-  static_assert(!cellcache_singleslot, "the per-packet oracle schedule needs the GPU_ON (multi-slot cell cache) build");
+  if constexpr (cellcache_singleslot) {
+    printlnlog("[fatal] artis_b200: ARTISB200_MODE=ref_perpacket needs the -DGPU_ON (multi-slot cell cache) oracle build");
+    std::abort();
+  }
   const double ts_end = globals::timesteps[nts].start + globals::timesteps[nts].width;
   const auto nonempty_npts_model = grid::get_nonempty_npts_model();
   for (int nonemptymgi = 0; nonemptymgi < nonempty_npts_model; nonemptymgi++) {
@@ -503,6 +510,195 @@ void update_packets_reference_perpacket(const int nts, std::span<Packet> packets
     }
   }
   stats::pkt_action_counters_printout(nts);
+}
+#endif
+
+
+#ifdef ARTISB200_WITH_REFERENCE
+// Deterministic golden vectors straight from the reference's own functions, evaluated on seeded inputs in
+// the state of timestep nts: grid::boundary_distance (grid.cc:2480), closest_transition (rpkt.h:144),
+// calculate_chi_rpkt_cont<true> (rpkt.cc:1020), and the reference's per-cell cache tables
+// (update_packets.cc:397-464; macroatom.cc:64-200; kpkt.cc:57-229). Inputs are stored next to outputs.
+struct KatRng {
+  std::uint64_t s;
+  auto next() -> double {  // 53-bit LCG-derived uniform in [0,1)
+    s = (s * 6364136223846793005ULL) + 1442695040888963407ULL;
+    return static_cast<double>(s >> 11U) * 0x1.0p-53;
+  }
+};
+
+template <class Sink>
+void emit_reference_kats(Sink& s, const int nts) {
+  KatRng rng{0x9E3779B97F4A7C15ULL + static_cast<std::uint64_t>(nts)};
+  const double tstart_base = globals::timesteps[nts].start;
+  const double twidth = globals::timesteps[nts].width;
+  const auto ncoord = grid::b200_ncoordgrid();
+  const auto gridtype = grid::b200_propgridtype();
+  const int ndim = (gridtype == GridType::SPHERICAL1D) ? 1 : ((gridtype == GridType::CYLINDRICAL2D) ? 2 : 3);
+  const auto ngrid = static_cast<int>(grid::ngrid);
+
+  // ---- boundary_distance ----
+  // (evaluated without the max_path_step cap of grid.cc:2750 so that real face distances are pinned; the
+  //  cap itself is exercised by every packet history)
+  const double saved_max_path_step = globals::max_path_step;
+  globals::max_path_step = std::numeric_limits<double>::max();
+  s.f64("kat.bd.max_path_step", globals::max_path_step);
+  constexpr int NBD = 4000;
+  std::vector<double> bd_in(static_cast<size_t>(NBD) * 7);
+  std::vector<int> bd_cell(NBD);
+  std::vector<double> bd_dist(NBD);
+  std::vector<int> bd_next(NBD);
+  for (int k = 0; k < NBD; k++) {
+    const int cellindex = static_cast<int>(rng.next() * ngrid) % ngrid;
+    const double t = tstart_base + (rng.next() * twidth);
+    const double trat = t / globals::tmin;
+    std::array<int, 3> idx{};
+    int rem = cellindex;
+    std::array<double, 3> cmin{};
+    std::array<double, 3> cmax{};
+    for (int d = 0; d < ndim; d++) {
+      idx[d] = rem % ncoord[d];
+      rem /= ncoord[d];
+      const auto coords = grid::b200_coord_pos_min_tmin(d);
+      cmin[d] = coords[idx[d]];
+      cmax[d] = (idx[d] < ncoord[d] - 1) ? coords[idx[d] + 1] : globals::rmax;
+    }
+    Vec3d pos{};
+    // a fraction of the points sit exactly on / a rounding error beyond a face to exercise the tolerance branch
+    const auto pick = [&](const double lo, const double hi) {
+      const double u = rng.next();
+      if (gridtype == GridType::CARTESIAN3D) {  // curved faces have no valid "exactly on the face" state in general
+        if (u < 0.03) { return lo; }
+        if (u < 0.06) { return hi; }
+        if (u < 0.08) { return hi * (1. + 2e-16); }
+      }
+      return lo + ((hi - lo) * rng.next());
+    };
+    if (gridtype == GridType::CARTESIAN3D) {
+      for (int d = 0; d < 3; d++) {
+        pos[d] = pick(cmin[d], cmax[d]) * trat;
+      }
+    } else if (gridtype == GridType::CYLINDRICAL2D) {
+      const double rcyl = pick(cmin[0], cmax[0]) * trat;
+      const double phi = 2 * PI * rng.next();
+      pos = {rcyl * std::cos(phi), rcyl * std::sin(phi), pick(cmin[1], cmax[1]) * trat};
+    } else {
+      const double r = pick(cmin[0], cmax[0]) * trat;
+      const double mu = (2 * rng.next()) - 1;
+      const double phi = 2 * PI * rng.next();
+      const double st = std::sqrt(1 - (mu * mu));
+      pos = {r * st * std::cos(phi), r * st * std::sin(phi), r * mu};
+    }
+    const double mu = (2 * rng.next()) - 1;
+    const double phi = 2 * PI * rng.next();
+    const double st = std::sqrt(1 - (mu * mu));
+    Vec3d dir{st * std::cos(phi), st * std::sin(phi), mu};
+    if (rng.next() < 0.02) {
+      dir = {0., 0., (mu > 0) ? 1. : -1.};  // exactly along z: the dirxylen == 0 branch of the 2D grid
+    }
+    const auto [dist, next] = grid::boundary_distance(dir, pos, t, cellindex);
+    for (int d = 0; d < 3; d++) {
+      bd_in[(static_cast<size_t>(k) * 7) + d] = pos[d];
+      bd_in[(static_cast<size_t>(k) * 7) + 3 + d] = dir[d];
+    }
+    bd_in[(static_cast<size_t>(k) * 7) + 6] = t;
+    bd_cell[k] = cellindex;
+    bd_dist[k] = dist;
+    bd_next[k] = next;
+  }
+  globals::max_path_step = saved_max_path_step;
+  s.arr("kat.bd.in", bd_in.data(), static_cast<int64_t>(bd_in.size()));
+  s.arr("kat.bd.cell", bd_cell.data(), NBD);
+  s.arr("kat.bd.dist", bd_dist.data(), NBD);
+  s.arr("kat.bd.next", bd_next.data(), NBD);
+
+  // ---- closest_transition ----
+  constexpr int NCT = 4000;
+  std::vector<double> ct_nu(NCT);
+  std::vector<int> ct_next(NCT);
+  std::vector<int> ct_out(NCT);
+  const auto linenu = globals::linelist.nu.span();
+  const double lognumax = std::log(linenu.front() * 1.05);
+  const double lognumin = std::log(linenu.back() * 0.95);
+  for (int k = 0; k < NCT; k++) {
+    double nu = std::exp(lognumin + ((lognumax - lognumin) * rng.next()));
+    const double u = rng.next();
+    if (u < 0.1) {
+      nu = linenu[static_cast<size_t>(rng.next() * globals::nlines) % globals::nlines];  // exactly on a line
+    }
+    int next_trans = -1;
+    const double v = rng.next();
+    if (v < 0.2) {
+      next_trans = static_cast<int>(rng.next() * globals::nlines);
+    } else if (v < 0.25) {
+      next_trans = globals::nlines + 1;
+    } else if (v < 0.3) {
+      next_trans = 0;
+    }
+    ct_nu[k] = nu;
+    ct_next[k] = next_trans;
+    ct_out[k] = closest_transition(nu, next_trans, linenu);
+  }
+  s.arr("kat.ct.nu", ct_nu.data(), NCT);
+  s.arr("kat.ct.next_trans", ct_next.data(), NCT);
+  s.arr("kat.ct.out", ct_out.data(), NCT);
+
+  // ---- continuum opacity ----
+  constexpr int NCHI = 2000;
+  std::vector<double> chi_nu;
+  std::vector<int> chi_cell;
+  std::vector<double> chi_out;
+  const int nc = grid::get_nonempty_npts_model();
+  ContinuumOpacity chi{};
+  for (int k = 0; k < NCHI; k++) {
+    const int cell = static_cast<int>(rng.next() * nc) % nc;
+    if (grid::thick_allcells[cell] == grid::CellThickness::THICK) {
+      continue;
+    }
+    const double nu = std::exp(std::log(NU_MIN_R) + ((std::log(NU_MAX_R) - std::log(NU_MIN_R)) * rng.next()));
+    chi.nonemptymgi = -1;  // force an evaluation
+    calculate_chi_rpkt_cont<true>(nu, chi, cell);
+    chi_nu.push_back(nu);
+    chi_cell.push_back(cell);
+    chi_out.push_back(chi.chi_escatter);
+    chi_out.push_back(chi.chi_freefree_heat);
+    chi_out.push_back(chi.chi_boundfree);
+  }
+  s.arr("kat.chi.nu", chi_nu.data(), static_cast<int64_t>(chi_nu.size()));
+  s.arr("kat.chi.cell", chi_cell.data(), static_cast<int64_t>(chi_cell.size()));
+  s.arr("kat.chi.out", chi_out.data(), static_cast<int64_t>(chi_out.size()));
+}
+
+// the reference's own per-cell cache tables (GPU_ON: one slot per cell, all filled up front)
+template <class Sink>
+void emit_reference_cellcache(Sink& s) {
+  if constexpr (!cellcache_singleslot) {
+    const int nc = grid::get_nonempty_npts_model();
+    std::vector<double> pops;
+    std::vector<double> marates;
+    std::vector<double> matrans;
+    std::vector<double> cooling;
+    std::vector<double> nnlevel;
+    std::vector<std::uint64_t> keepbits;
+    std::vector<double> chiff;
+    for (int cell = 0; cell < nc; cell++) {
+      const auto& slot = globals::cellcache.at(cell);
+      pops.insert(pops.end(), slot.alllevels_pops.begin(), slot.alllevels_pops.end());
+      marates.insert(marates.end(), slot.alllevels_maprocessrates.begin(), slot.alllevels_maprocessrates.end());
+      matrans.insert(matrans.end(), slot.allmacroatomictransitions.begin(), slot.allmacroatomictransitions.end());
+      cooling.insert(cooling.end(), slot.cooling_contrib.begin(), slot.cooling_contrib.end());
+      nnlevel.insert(nnlevel.end(), slot.allcont_nnlevel.begin(), slot.allcont_nnlevel.end());
+      keepbits.insert(keepbits.end(), slot.allcont_keepbits.begin(), slot.allcont_keepbits.end());
+      chiff.push_back(slot.chi_ff_nnionpart[0]);
+    }
+    s.arr("ref.levelpops", pops.data(), static_cast<int64_t>(pops.size()));
+    s.arr("ref.maprocessrates", marates.data(), static_cast<int64_t>(marates.size()));
+    s.arr("ref.matrans", matrans.data(), static_cast<int64_t>(matrans.size()));
+    s.arr("ref.cooling_contrib", cooling.data(), static_cast<int64_t>(cooling.size()));
+    s.arr("ref.cont_nnlevel", nnlevel.data(), static_cast<int64_t>(nnlevel.size()));
+    s.arr("ref.cont_keepbits", keepbits.data(), static_cast<int64_t>(keepbits.size()));
+    s.arr("ref.chi_ff_nnionpart", chiff.data(), static_cast<int64_t>(chiff.size()));
+  }
 }
 #endif
 
@@ -564,6 +760,12 @@ void update_packets(const int nts, std::span<Packet> packets) {
     b200::SnapshotWriter w(dumpdir + "/ts" + std::to_string(nts) + "_after.abt");
     emit_packets(w, packets);
     emit_estimators(w, nts);
+#ifdef ARTISB200_WITH_REFERENCE
+    if (mode == "ref_perpacket") {
+      emit_reference_cellcache(w);
+      emit_reference_kats(w, nts);
+    }
+#endif
   }
   MPI_Barrier_allranks();  // update_packets.cc:631
 }

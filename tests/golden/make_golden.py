@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""Generate the committed oracle fixtures from the reference itself (development container only).
+
+For each toy config the UNMODIFIED reference (oracle/_ref/<config>/parity/sn3d_ref: the reference's own
+sources compiled with -DGPU_ON and its REPRODUCIBLE flags, plus the snapshot hooks of
+integration/update_packets_b200.cc) is run on the synthetic inputs written by tools/gen_inputs.py, in the
+order-independent per-packet schedule (every packet driven through the reference's do_packet() with its own
+RNG stream). The inputs of update_packets() (static tables, cell state, packets) and its outputs (packets,
+estimators, counters) are stored as
+    tests/golden/<config>_static.npz, tests/golden/<config>_ts<N>.npz  (keys "before/<name>", "after/<name>")
+Usage: python tests/golden/make_golden.py   (needs `python __graft_entry__.py build` to have built oracle/_ref)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import run_oracle  # noqa: E402
+from artis_b200 import snapshot as snap  # noqa: E402
+
+GOLDEN = {
+    "classic_toy": [0, 3],
+    "classic_toy_1d": [0, 3],
+    "classic3d_toy": [0, 2],
+    "kilonova_toy": [1, 4],
+}
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for config, timesteps in GOLDEN.items():
+        rundir = run_oracle.run(config, "parity", "ref_perpacket", ",".join(str(t) for t in timesteps))
+        dump = os.path.join(rundir, "dump")
+        static = snap.read_snapshot(os.path.join(dump, "static.abt"))
+        np.savez_compressed(os.path.join(here, f"{config}_static.npz"), **static)
+        for nts in timesteps:
+            before = snap.read_snapshot(os.path.join(dump, f"ts{nts}_before.abt"))
+            after = snap.read_snapshot(os.path.join(dump, f"ts{nts}_after.abt"))
+            arrays = {f"before/{k}": v for k, v in before.items()}
+            arrays.update({f"after/{k}": v for k, v in after.items()})
+            out = os.path.join(here, f"{config}_ts{nts}.npz")
+            np.savez_compressed(out, **arrays)
+            print(f"{out}: {os.path.getsize(out) / 1024:.0f} KiB, interactions {int(after['counters'][26])}")
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,19 @@ struct HostBackend {
         ab::build_cooling_ion(T, cell, uion);
       }
     }
+    T.counters[ab::CNT_UPDATECELL] = T.ncells;  // one cell-cache fill per cell (update_packets.cc:399)
+    return true;
+  }
+
+  bool run_test_kernel(ab::Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,
+                       double* out_f64, int* out_i32) {
+    std::vector<double> scratch(static_cast<size_t>(T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1));
+    T.scratch_groundcont = scratch.data();
+    T.scratch_stride = 1;
+    for (int64_t i = 0; i < n; i++) {
+      ab::test_kernel_item(T, which, i, 0, in_f64, in_i32, out_f64, out_i32);
+    }
+    T.scratch_groundcont = nullptr;
     return true;
   }
 

@@ -30,21 +30,21 @@ CONFIGS = {
     # ---- toy-sized parity cases (run in seconds on one CPU core) -------------------------------
     "classic_toy": dict(
         preset="classic",
-        opts=_opts(4000, "CARTESIAN3D", 20),
+        opts=_opts(1500, "CARTESIAN3D", 20),
         atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
-        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=1e-12, v_e_kmps=3000.0, seed=1),
-        run=dict(seed=8, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=5, thick=8.0, ngrey=2, nlte_ts=5),
     ),
     "classic_toy_1d": dict(
         preset="classic",
-        opts=_opts(4000),
+        opts=_opts(1500),
         atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
-        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=1e-12, v_e_kmps=3000.0, seed=1),
-        run=dict(seed=8, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=5, thick=8.0, ngrey=2, nlte_ts=5),
     ),
     "kilonova_toy": dict(
         preset="kilonova_lte",
-        opts=_opts(4000, None, None, {
+        opts=_opts(1000, None, None, {
             "constexpr int TABLESIZE": "constexpr int TABLESIZE = 20;",
             "constexpr double MINTEMP": "constexpr double MINTEMP = 1000.;",
             "constexpr double MAXTEMP": "constexpr double MAXTEMP = 20000.;",
@@ -55,10 +55,10 @@ CONFIGS = {
     ),
     "classic3d_toy": dict(
         preset="classic",
-        opts=_opts(4000),
+        opts=_opts(1500),
         atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
-        model=dict(kind="3d", n=10, vmax_kmps=20000.0, t_model_days=2.0, mass_msun=1.0, seed=3),
-        run=dict(seed=10, ntimesteps=8, tmin=3.0, tmax=8.0, nts_run=4, thick=8.0, ngrey=999, nlte_ts=5),
+        model=dict(kind="3d", n=10, vmax_kmps=20000.0, t_model_days=2.0, mass_msun=0.6, seed=3),
+        run=dict(seed=10, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=5, thick=8.0, ngrey=2, nlte_ts=5),
     ),
     # ---- BASELINE.json configs (bench-sized) ----------------------------------------------------
     # configs[0]: classic LTE W7-like 1D model on a 3D grid, 1e5 packets
