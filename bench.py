@@ -1,0 +1,423 @@
+#!/usr/bin/env python3
+"""Benchmark of the update_packets() hot path (BASELINE.json metric: packet-interactions/sec per timestep).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm: the CUDA library through its C ABI
+  python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's own CPU update_packets
+
+Workload (config.workload): BASELINE.json configs[1], the kilonova LTE 2D cylindrical model with 1e7 packets, one
+timestep of it. The state at the start of that timestep (static tables, cell state, 1e7 packets) is produced on the
+box by the drop-in host binary (the reference's own driver and grid update with update_packets() bound to this
+library, integration/), saved as a snapshot, and every "step" replays update_packets() for that timestep:
+begin_timestep (zero estimators + per-cell table build, which the reference's GPU_ON update_packets also does up
+front, update_packets.cc:551-563) followed by the propagation of all packets to the end of the timestep.
+
+  value      interactions / device time with the packets already resident in HBM (CUDA events on the library stream)
+  e2e        the same through artisb200_update_packets_host with pinned HOST packet buffers: H2D of the AoS packets,
+             propagation, D2H of the packets and of the estimators inside the timed region
+  roofline   algorithmic bytes (SURVEY.md 8d formula, from the device work counters) / propagation-kernel time
+  cpu_baseline  the compiled reference (oracle/_ref, production flags) timed on this box on a bounded packet sample
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+WORKLOAD = os.environ.get("ARTISB200_BENCH_CONFIG", "kilonova_2d")
+PRESET = "kilonova_lte"
+BENCH_TS = int(os.environ.get("ARTISB200_BENCH_TS", "2"))
+CPU_SAMPLE_CONFIG = os.environ.get("ARTISB200_BENCH_CPU_CONFIG", "kilonova_2d_cpu")
+FLAVOR = os.environ.get("ARTISB200_BENCH_FLAVOR", "fast")
+CPU_FLAVOR = os.environ.get("ARTISB200_BENCH_CPU_FLAVOR", "fast")
+CACHE = os.environ.get("ARTISB200_BENCH_CACHE", os.path.join(ROOT, "gpurun_out", "bench_cache"))
+INTERACTIONS = 26
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload preparation (host driver with the GPU update_packets; not timed)
+# ------------------------------------------------------------------------------------------------------------
+
+def prepare_workload(device=0):
+    """run the drop-in host binary up to BENCH_TS and snapshot the inputs of update_packets(BENCH_TS)"""
+    dump = os.path.join(CACHE, f"{WORKLOAD}_ts{BENCH_TS}")
+    static_path = os.path.join(dump, "static.abt")
+    before_path = os.path.join(dump, f"ts{BENCH_TS}_before.abt")
+    if os.path.exists(static_path) and os.path.exists(before_path):
+        return static_path, before_path
+    bdir = os.path.join(ROOT, "integration", "_build", WORKLOAD, FLAVOR)
+    binary = os.path.join(bdir, "sn3d_b200")
+    if not os.path.exists(binary):
+        raise RuntimeError(f"{binary} missing (python __graft_entry__.py build in the development container)")
+    rundir = os.path.join(CACHE, f"{WORKLOAD}_run")
+    if os.path.isdir(rundir):
+        shutil.rmtree(rundir)
+    shutil.copytree(os.path.join(bdir, "inputs"), rundir)
+    os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
+    # run only timesteps 0..BENCH_TS
+    inp = os.path.join(rundir, "input.txt")
+    lines = open(inp).read().split("\n")
+    lines[2] = f"000 {BENCH_TS + 1:03d}".ljust(24) + " #  2"
+    open(inp, "w").write("\n".join(lines))
+    os.makedirs(dump, exist_ok=True)
+    from artis_b200 import lib as ablib
+    env = dict(os.environ, ARTISB200_LIB=ablib.library_path(PRESET), ARTISB200_DUMP_DIR=dump, ARTISB200_DUMP_TS=str(BENCH_TS),
+               ARTISB200_DEVICE=str(device), ARTISB200_MODE="gpu")
+    t0 = time.time()
+    log(f"preparing workload: {binary} (timesteps 0..{BENCH_TS}) ...")
+    with open(os.path.join(rundir, "stdout.txt"), "w") as out:
+        subprocess.run([binary], cwd=rundir, env=env, stdout=out, stderr=subprocess.STDOUT, check=True)
+    log(f"workload prepared in {time.time() - t0:.1f} s")
+    for f in os.listdir(dump):  # the *_after snapshot is not needed
+        if f.endswith("_after.abt"):
+            os.remove(os.path.join(dump, f))
+    return static_path, before_path
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=5)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# roofline
+# ------------------------------------------------------------------------------------------------------------
+
+def algorithmic_bytes(diag, counters, log2_lines, nions, mean_ncoolingterms_log2, mean_ntrans_log2):
+    """minimum compulsory traffic of one update_packets call, from the device work counters"""
+    n_step_r, n_line, n_conteval, n_contterm, n_binsearch, n_est, n_ma, n_k, n_step_g = (int(diag[i]) for i in range(9))
+    b = 0
+    b += n_step_r * (2 * 144 + 24)      # packet hot state read+write, cell scalars
+    b += n_line * 40                    # line data (24 B) + two level populations (16 B)
+    b += n_contterm * 40                # kept continuum terms
+    b += n_binsearch * 8                # binary-search probes (linelist, continuum list, cumulative tables)
+    b += n_est * 16                     # f64 estimator read-modify-writes
+    b += n_ma * 72                      # 9 macro-atom process rates per transition (search probes counted above)
+    b += n_k * 0                        # k-packet selection = two searches, counted in n_binsearch
+    b += n_step_g * (2 * 112 + 16)      # gamma step: packet hot state + rho, nnetot, ffegrp
+    return b
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from artis_b200 import lib as ablib
+    from artis_b200 import snapshot as snap
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the library has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # workload: rank 0 prepares the snapshot, everybody loads it (weak scaling: every rank propagates its own
+    # 1e7 packets with rank-distinct Philox keys, as every MPI rank of the reference owns its own MPKTS packets)
+    if rank == 0:
+        prepare_workload(local_rank)
+    if world > 1:
+        dist.barrier()
+    static_path, before_path = prepare_workload(local_rank)
+    static = snap.read_snapshot(static_path)
+    before = snap.read_snapshot(before_path)
+    n = int(before["packets.count"][0])
+    stride = int(before["packets.stride"][0])
+
+    eng = ablib.ArtisB200(preset=PRESET, device=local_rank)
+    eng.set_option("rng_mode", 0)
+    eng.set_option("seed", 20260101 + (rank << 32))
+    eng.set_option("rank", rank)
+    eng.set_option("nranks", world)
+    eng.set_option("max_steps_per_launch", int(os.environ.get("ARTISB200_MAXSTEPS", "0")))
+    eng.set_arrays(static)
+    eng.commit_static()
+    eng.set_arrays(before)
+    eng.begin_timestep(BENCH_TS)
+
+    host_packets = torch.from_numpy(before["packets.aos"]).pin_memory()
+    work = host_packets.clone().pin_memory()
+    eng.upload_packets(host_packets.numpy(), n, stride)
+    eng.save_packets_device()
+
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    est_ptr, est_count = eng.estimator_device_buffer()
+
+    def reduce_estimators():
+        if world > 1:
+            # one packed all-reduce replaces the per-array MPI_Allreduce calls of sn3d.cc:565-625 / radfield.cc:988-1030
+            t = _as_tensor(est_ptr, est_count, local_rank)
+            dist.all_reduce(t)
+
+    def step_device():
+        eng.restore_packets_device()
+        eng.begin_timestep(BENCH_TS)
+        eng.update_packets(BENCH_TS)
+        reduce_estimators()
+
+    def timed(fn, restore=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            fn()
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1)
+
+    def device_step_timed():
+        eng.restore_packets_device()   # not part of update_packets: resets the replayed timestep's input state
+        torch.cuda.synchronize()
+
+        def body():
+            eng.begin_timestep(BENCH_TS)
+            eng.update_packets(BENCH_TS)
+            reduce_estimators()
+        return timed(body)
+
+    log(f"rank {rank}: {n} packets, stride {stride}; warm-up {args.warmup} steps")
+    for _ in range(args.warmup):
+        device_step_timed()
+
+    step_ms, prop_ms, interactions = [], [], []
+    diag_sum = None
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            step_ms.append(device_step_timed())
+            prop_ms.append(eng.last_timing_ms()[1])
+            est = eng.estimators()
+            interactions.append(int(est["counters"][INTERACTIONS]))
+            diag_sum = est["diag"] if diag_sum is None else diag_sum + est["diag"]
+            counters = est["counters"]
+    clock_summary = clocks.summary()
+
+    # end-to-end through the host-buffer call (the drop-in signature): H2D packets, propagate, D2H packets + estimators
+    e2e_ms = []
+    for it in range(max(1, min(args.steps, 3))):
+        work.copy_(host_packets)
+        torch.cuda.synchronize()
+
+        def body():
+            eng.begin_timestep(BENCH_TS)
+            eng.update_packets_host(BENCH_TS, work.numpy(), n, stride)
+            reduce_estimators()
+            eng.estimators()
+        e2e_ms.append(timed(body))
+
+    t_step = sum(step_ms) / len(step_ms)
+    t_prop = sum(prop_ms) / len(prop_ms)
+    t_e2e = sum(e2e_ms) / len(e2e_ms)
+    n_int = sum(interactions) / len(interactions)
+    vals = torch.tensor([t_step, t_prop, t_e2e, n_int], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = vals.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = vals.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_step, t_prop, t_e2e = (float(x) for x in tmax[:3])
+        n_int_total = float(tsum[3])
+    else:
+        n_int_total = n_int
+
+    if rank == 0:
+        nlines = static["line.nu"].size
+        diag_mean = diag_sum / len(step_ms)
+        b_alg = algorithmic_bytes(diag_mean, counters, np.log2(max(nlines, 2)), static["ion.nlevels"].size, 0, 0)
+        peak, peak_kind = measured_peak_gbs()
+        achieved = b_alg / (t_prop * 1e-3) / 1e9
+        launches = int(diag_mean[10])
+        ncells = static["cell.ffegrp"].size
+        out = {
+            "metric": "packet-interactions/sec per timestep", "value": n_int_total / (t_step * 1e-3), "unit": "interactions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}",
+                       "packets_per_gpu": n, "model_cells": int(ncells), "lines": int(nlines), "levels": int(static["level.epsilon"].size),
+                       "bf_continua": int(static["cont.nu_edge"].size), "rng": "philox4x32-10",
+                       "interactions_per_step_per_gpu": n_int, "l2_policy": "inputs larger than L2 (packet SoA + per-cell tables > 126 MB)"},
+            "e2e": {"value": n_int_total / (t_e2e * 1e-3), "unit": "interactions/s", "h2d_bytes_per_step": int(n * stride),
+                    "d2h_bytes_per_step": int(n * stride + est_count * 8), "ms_per_step": t_e2e},
+            # per step: k_propagate launches + k_reset_philox + the 5 per-cell table-build kernels of begin_timestep
+            "gpu_launches": int(launches + 1 + 5),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind, "kernel": "k_propagate", "kernel_ms": t_prop, "algorithmic_bytes": int(b_alg)},
+            "clocks": clock_summary,
+            "work_counters": {k: int(diag_mean[i]) for i, k in enumerate(
+                ["rpkt_steps", "lines_visited", "cont_evals", "cont_terms", "binsearch_probes", "estimator_adds", "ma_steps",
+                 "k_steps", "gamma_steps", "gamma_events", "launches", "packet_segments"])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                out["cpu_baseline"] = cpu_baseline(cores=1)
+            except Exception as e:  # the baseline must never take the bench line down
+                out["cpu_baseline"] = {"value": None, "unit": "interactions/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _as_tensor(ptr, count, device_index):
+    """wrap the library's packed estimator buffer (device pointer) as a torch tensor without copying"""
+    import torch
+
+    class _Holder:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3}
+    return torch.as_tensor(_Holder(ptr, count), device=torch.device("cuda", device_index))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the compiled reference's own update_packets on this box
+# ------------------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(nproc, rundir_root):
+    """nproc concurrent single-rank reference processes (the reference's production parallelism is one MPI rank per
+    core with no communication inside update_packets, update_packets.cc:561/631), each on its own packets"""
+    import run_oracle
+    odir = run_oracle.oracle_dir(CPU_SAMPLE_CONFIG, CPU_FLAVOR)
+    binary = os.path.join(odir, "sn3d_ref")
+    if not os.path.exists(binary):
+        raise RuntimeError(f"{binary} missing")
+    procs = []
+    for r in range(nproc):
+        rundir = os.path.join(rundir_root, f"cpu_rank{r}")
+        if os.path.isdir(rundir):
+            shutil.rmtree(rundir)
+        shutil.copytree(os.path.join(odir, "inputs"), rundir)
+        os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
+        inp = os.path.join(rundir, "input.txt")
+        lines = open(inp).read().split("\n")
+        lines[0] = f"{20260101 + 1000 * r}".ljust(24) + " #  0"
+        lines[2] = f"000 {BENCH_TS + 1:03d}".ljust(24) + " #  2"
+        open(inp, "w").write("\n".join(lines))
+        env = dict(os.environ, ARTISB200_MODE="ref")
+        env.pop("ARTISB200_DUMP_DIR", None)
+        out = open(os.path.join(rundir, "stdout.txt"), "w")
+        procs.append((rundir, subprocess.Popen([binary], cwd=rundir, env=env, stdout=out, stderr=subprocess.STDOUT)))
+    res = []
+    for rundir, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError(f"reference process failed in {rundir}")
+        res.append([t for t in run_oracle.timing_lines(rundir) if t["nts"] == BENCH_TS][0])
+    return res
+
+
+def cpu_baseline(cores=1):
+    import configs
+    root = os.path.join(CACHE, "cpu_baseline")
+    os.makedirs(root, exist_ok=True)
+    res = cpu_reference_run(cores, root)
+    total_int = sum(r["interactions"] for r in res)
+    wall = max(r["wall_s"] for r in res)
+    npk = res[0]["npackets"]
+    return {"value": total_int / wall, "unit": "interactions/s", "cores": cores, "kind": "reference",
+            "sample": f"{CPU_SAMPLE_CONFIG}: {npk} packets per process of the same model and atomic data, timestep {BENCH_TS} "
+                      f"after evolving timesteps 0..{BENCH_TS - 1} on the CPU; update_packets wall {wall:.2f} s, "
+                      f"{total_int} interactions", "wall_s": wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    root = os.path.join(CACHE, "reference_arm")
+    os.makedirs(root, exist_ok=True)
+    values, walls = [], []
+    for _ in range(args.warmup + args.steps):
+        res = cpu_reference_run(cores, root)
+        values.append(sum(r["interactions"] for r in res) / max(r["wall_s"] for r in res))
+        walls.append(max(r["wall_s"] for r in res))
+        if len(values) >= 1 + args.steps or sum(walls) > 240:   # bounded: each pass re-evolves timesteps 0..k-1 as well
+            break
+    use = values[-args.steps:] if len(values) > args.steps else values
+    v = sum(use) / len(use)
+    npk = res[0]["npackets"]
+    sample = (f"{CPU_SAMPLE_CONFIG}: {cores} concurrent single-rank reference processes x {npk} packets, timestep {BENCH_TS}")
+    out = {"impl": "reference", "metric": "packet-interactions/sec per timestep", "value": v, "unit": "interactions/s",
+           "n_gpus": args.gpus, "steps": len(use), "warmup": max(0, len(values) - len(use)), "ms_per_step": 1e3 * sum(walls[-len(use):]) / len(use),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}"},
+           "cpu_baseline": {"value": v, "unit": "interactions/s", "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": v, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -424,10 +424,17 @@ void fetch_add(const char* name, std::span<T> dest) {
   if (dest.empty()) {
     return;
   }
+  // the reference allocates some per-cell estimators with one spare element (nonempty_npts_model + 1); the
+  // library's arrays have exactly one entry per non-empty cell
+  const int64_t have = lib.array_count(lib.ctx, name);
+  if (have < 0 || have > static_cast<int64_t>(dest.size())) {
+    printlnlog("[fatal] artis_b200: estimator {} has {} entries, host array has {}", name, have, dest.size());
+    std::abort();
+  }
   static std::vector<T> tmp;
-  tmp.resize(dest.size());
-  check(lib.get_array(lib.ctx, name, b200::dtype_of<T>::code, tmp.data(), static_cast<int64_t>(dest.size())), name);
-  for (size_t i = 0; i < dest.size(); i++) {
+  tmp.resize(static_cast<size_t>(have));
+  check(lib.get_array(lib.ctx, name, b200::dtype_of<T>::code, tmp.data(), have), name);
+  for (int64_t i = 0; i < have; i++) {
     dest[i] += tmp[i];
   }
 }

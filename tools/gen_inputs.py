@@ -69,8 +69,20 @@ def write_atomic(cfg, outdir):
             pairs.sort()
             tr.write(f"{Z} {stage} {len(pairs)}\n")
             for lo, up in pairs:
-                forb = rng.random() < 0.3
-                A = 10 ** rng.uniform(-2, 1) if forb else 10 ** rng.uniform(5, 8.5)
+                forb = rng.random() < a.get("forb_frac", 0.3)
+                if "f_perm_log10" in a:
+                    # physically consistent permitted lines: draw the absorption oscillator strength and derive
+                    # A_ul = 6.670e15 f_lu (g_l / g_u) / lambda[Angstrom]^2, so that low-energy transitions get small A
+                    # (drawing A independently of the wavelength gives f >> 1 for closely spaced levels, and with it
+                    # absurd van Regemorter collision rates)
+                    lo_f, hi_f = a["f_perm_log10"]
+                    f_lu = 10 ** rng.uniform(lo_f, hi_f)
+                    lam_angstrom = 12398.42 / max(en[up] - en[lo], 1e-4)
+                    a_perm = 6.670e15 * f_lu * g[lo] / g[up] / lam_angstrom**2
+                else:
+                    lo_a, hi_a = a.get("A_perm_log10", (5.0, 8.5))
+                    a_perm = 10 ** rng.uniform(lo_a, hi_a)
+                A = 10 ** rng.uniform(-2, 1) if forb else a_perm
                 tr.write(f"{lo + 1} {up + 1} {A:.4e} {-2.0 if forb else -1.0} {1 if forb else 0}\n")
             tr.write("\n")
             nlines_total += len(pairs)
