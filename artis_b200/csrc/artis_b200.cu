@@ -91,6 +91,74 @@ __global__ void k_build_cooling(const __grid_constant__ Tables T) {
   }
 }
 
+// ---- cell-sorted packet queue: counting sort of the active packets by (packet class, model cell) -------------
+// The propagation kernel hands packets out in this order, so that the lanes of a warp start in the same cell and
+// on the same kind of packet (coalesced/broadcast table loads, same thick/thin branch); it mirrors the reference's
+// own sort of the packets by cell before each pass (update_packets.cc:363-394, 570-572) without moving the packets.
+__device__ __forceinline__ int sort_bucket_of(const Tables& T, const long long i, const int nbuckets_per_class) {
+  const int type = T.pkt.type[i];
+  if (type == ab::TYPE_ESCAPE || !(T.pkt.prop_time[i] < T.ts_end)) {
+    return -1;  // nothing to do this timestep
+  }
+  const int cls = (type == ab::TYPE_RPKT) ? 0 : ((type == ab::TYPE_KPKT) ? 1 : 2);
+  const int cell = T.propcell_nonemptymgi[T.pkt.cellindex[i]];
+  return (cls * nbuckets_per_class) + cell + 1;  // empty cells (-1) -> 0
+}
+
+__global__ void k_sort_count(const __grid_constant__ Tables T, const long long n, const int nbuckets_per_class, int* keys,
+                             unsigned int* bucket_count) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const int b = sort_bucket_of(T, i, nbuckets_per_class);
+    keys[i] = b;
+    if (b >= 0) {
+      atomicAdd(&bucket_count[b], 1U);
+    }
+  }
+}
+
+// exclusive scan of the bucket counts (a few thousand entries): one block, each thread scans a contiguous chunk
+__global__ void k_sort_scan(unsigned int* bucket_count, unsigned int* bucket_start, const int nbuckets, unsigned long long* queue) {
+  __shared__ unsigned int chunk_total[1024];
+  const int nthreads = blockDim.x;
+  const int chunk = (nbuckets + nthreads - 1) / nthreads;
+  const int begin = threadIdx.x * chunk;
+  const int end = min(begin + chunk, nbuckets);
+  unsigned int sum = 0U;
+  for (int b = begin; b < end; b++) {
+    sum += bucket_count[b];
+  }
+  chunk_total[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int running = 0U;
+    for (int t = 0; t < nthreads; t++) {
+      const unsigned int v = chunk_total[t];
+      chunk_total[t] = running;
+      running += v;
+    }
+    queue[2] = running;  // number of active packets
+  }
+  __syncthreads();
+  unsigned int running = chunk_total[threadIdx.x];
+  for (int b = begin; b < end; b++) {
+    bucket_start[b] = running;
+    running += bucket_count[b];
+    bucket_count[b] = 0U;  // reused as the scatter cursor
+  }
+}
+
+__global__ void k_sort_scatter(const long long n, const int* keys, const unsigned int* bucket_start, unsigned int* bucket_cursor,
+                               int* order) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const int b = keys[i];
+    if (b >= 0) {
+      order[bucket_start[b] + atomicAdd(&bucket_cursor[b], 1U)] = static_cast<int>(i);
+    }
+  }
+}
+
 __global__ void k_test_kernel(const __grid_constant__ Tables T, const int which, const long long n, const double* in_f64,
                               const int* in_i32, double* out_f64, int* out_i32) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
@@ -99,8 +167,9 @@ __global__ void k_test_kernel(const __grid_constant__ Tables T, const int which,
   }
 }
 
-// queue[0]: next packet index to hand out; queue[1]: packets that still need work after this launch
-__global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const long long n,
+// queue[0]: next queue position to hand out; queue[1]: packets that still need work after this launch;
+// queue[2]: number of active packets in `order`
+__global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const int* __restrict__ order,
                                                           unsigned long long* queue) {
   __shared__ unsigned long long s_cnt[ab::CNT_COUNT];
   __shared__ unsigned long long s_diag[ab::NDIAG];
@@ -140,22 +209,74 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
 
   const long long tid = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   const double ts_end = T.ts_end;
+  // Warp-synchronous phase machine. Every lane owns one packet at a time; each iteration of the loop takes the
+  // warp through the same sequence of phases with a convergence point (__syncwarp) before each, so that lanes
+  // in the same phase execute it together instead of being scattered over unrelated points of a long history
+  // (measured on the first version of this kernel, which ran each history straight through: 4.1 of 32 lanes
+  // active per issued instruction, profiles/r1_k_propagate_v1.md):
+  //   refill   lanes whose packet is finished fetch the next active packet from the global queue
+  //   phase A  one step of the rare packet types (pellet, gamma, k-packet, non-thermal)
+  //   phase B  one r-packet transport step (boundary / line walk / continuum / event selection)
+  //   phase C  macro-atom walks activated in phases A/B, run to deactivation
+  constexpr unsigned FULL = 0xffffffffU;
+  const long long max_steps = T.max_steps_per_launch;
+  const unsigned long long nactive = queue[2];
+  ab::Pkt p;
+  ab::ChiCont chi;
+  ab::init_chicont(chi);
+  p.type = ab::TYPE_ESCAPE;
+  p.ma_pending = 0;
+  long long ip = 0;
+  long long steps = 0;
+  bool have = false;
+  bool exhausted = false;
   while (true) {
-    const long long i = static_cast<long long>(atomicAdd(&queue[0], 1ULL));
-    if (i >= n) {
+    __syncwarp();
+    if (!have && !exhausted) {
+      while (true) {
+        const unsigned long long q = atomicAdd(&queue[0], 1ULL);
+        if (q >= nactive) {
+          exhausted = true;
+          break;
+        }
+        const long long i = order[q];
+        ip = i;
+        ab::load_pkt(p, T, ip);
+        ab::init_chicont(chi);
+        steps = 0;
+        have = true;
+        diag[ab::DIAG_PACKET_SEGMENTS]++;
+        break;
+      }
+    }
+    if (__all_sync(FULL, !have)) {
       break;
     }
-    if (T.pkt.type[i] == ab::TYPE_ESCAPE || !(T.pkt.prop_time[i] < ts_end)) {
-      continue;
+    const ab::Ctx c{T, ip, tid, cnt, diag, tss, &pellet_decays};
+    if (have && p.type != ab::TYPE_RPKT) {  // phase A
+      ab::do_packet(p, c, ts_end, chi);
+      steps++;
     }
-    ab::Pkt p;
-    ab::load_pkt(p, T, i);
-    const ab::Ctx c{T, i, tid, cnt, diag, tss, &pellet_decays};
-    diag[ab::DIAG_PACKET_SEGMENTS]++;
-    if (ab::propagate_packet(p, c, T.max_steps_per_launch)) {
-      still_active++;
+    __syncwarp();
+    if (have && p.type == ab::TYPE_RPKT && p.ma_pending == 0 && ab::packetprop_update_required(p, ts_end)) {  // phase B
+      ab::do_rpkt_step(p, c, ts_end, chi);
+      steps++;
     }
-    ab::store_pkt(p, T, i);
+    __syncwarp();
+    if (have && p.ma_pending != 0) {  // phase C
+      ab::finish_macroatom(p, c);
+    }
+    if (have) {
+      const bool more = ab::packetprop_update_required(p, ts_end);
+      const bool yield = more && max_steps > 0 && steps >= max_steps;
+      if (!more || yield) {
+        ab::store_pkt(p, T, ip);
+        have = false;
+        if (yield) {
+          still_active++;
+        }
+      }
+    }
   }
 
   // block-level reduction in shared memory, then one global atomic per block and counter
@@ -213,9 +334,17 @@ struct CudaBackend {
   cudaStream_t stream{nullptr};
   cudaEvent_t ev_start{nullptr};
   cudaEvent_t ev_stop{nullptr};
+  cudaEvent_t ev_sched0{nullptr};
+  cudaEvent_t ev_sched1{nullptr};
   unsigned long long* d_queue{nullptr};
   double* d_scratch{nullptr};
   long long scratch_elems{0};
+  int* d_keys{nullptr};
+  int* d_order{nullptr};
+  long long sort_capacity{0};
+  unsigned int* d_bucket_count{nullptr};
+  unsigned int* d_bucket_start{nullptr};
+  int bucket_capacity{0};
 
   bool ok(const cudaError_t e, const char* what) {
     if (e != cudaSuccess) {
@@ -249,10 +378,11 @@ struct CudaBackend {
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
       return false;
     }
-    if (!ok(cudaEventCreate(&ev_start), "cudaEventCreate") || !ok(cudaEventCreate(&ev_stop), "cudaEventCreate")) {
+    if (!ok(cudaEventCreate(&ev_start), "cudaEventCreate") || !ok(cudaEventCreate(&ev_stop), "cudaEventCreate") ||
+        !ok(cudaEventCreate(&ev_sched0), "cudaEventCreate") || !ok(cudaEventCreate(&ev_sched1), "cudaEventCreate")) {
       return false;
     }
-    if (!ok(cudaMalloc(&d_queue, 2 * sizeof(unsigned long long)), "cudaMalloc(queue)")) {
+    if (!ok(cudaMalloc(&d_queue, 4 * sizeof(unsigned long long)), "cudaMalloc(queue)")) {
       return false;
     }
     return true;
@@ -264,6 +394,10 @@ struct CudaBackend {
       cudaStreamSynchronize(stream);
       cudaFree(d_queue);
       cudaFree(d_scratch);
+      cudaFree(d_keys);
+      cudaFree(d_order);
+      cudaFree(d_bucket_count);
+      cudaFree(d_bucket_start);
       cudaEventDestroy(ev_start);
       cudaEventDestroy(ev_stop);
       cudaStreamDestroy(stream);
@@ -391,20 +525,56 @@ struct CudaBackend {
     T.scratch_groundcont = d_scratch;
     T.scratch_stride = nthreads;
 
+    const int nbuckets_per_class = T.ncells + 1;
+    const int nbuckets = 3 * nbuckets_per_class;
+    if (sort_capacity < n) {
+      cudaFree(d_keys);
+      cudaFree(d_order);
+      d_keys = nullptr;
+      d_order = nullptr;
+      if (!ok(cudaMalloc(&d_keys, static_cast<size_t>(n) * sizeof(int)), "cudaMalloc(sort keys)") ||
+          !ok(cudaMalloc(&d_order, static_cast<size_t>(n) * sizeof(int)), "cudaMalloc(sort order)")) {
+        return false;
+      }
+      sort_capacity = n;
+    }
+    if (bucket_capacity < nbuckets) {
+      cudaFree(d_bucket_count);
+      cudaFree(d_bucket_start);
+      d_bucket_count = nullptr;
+      d_bucket_start = nullptr;
+      if (!ok(cudaMalloc(&d_bucket_count, static_cast<size_t>(nbuckets) * sizeof(unsigned int)), "cudaMalloc(buckets)") ||
+          !ok(cudaMalloc(&d_bucket_start, static_cast<size_t>(nbuckets) * sizeof(unsigned int)), "cudaMalloc(buckets)")) {
+        return false;
+      }
+      bucket_capacity = nbuckets;
+    }
+
     cudaEventRecord(ev_start, stream);
     if (T.rng_mode == ab::RNG_PHILOX) {
       k_reset_philox<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
     }
     long long launches = 0;
-    unsigned long long hq[2] = {0ULL, 1ULL};
+    float sched_total = 0.F;
+    unsigned long long hq[4] = {0ULL, 1ULL, 0ULL, 0ULL};
     while (hq[1] > 0ULL) {
-      cudaMemsetAsync(d_queue, 0, 2 * sizeof(unsigned long long), stream);
-      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, n, d_queue);
+      // (re)build the cell-sorted queue of the packets that still need work
+      cudaEventRecord(ev_sched0, stream);
+      cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
+      cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
+      k_sort_count<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, nbuckets_per_class, d_keys, d_bucket_count);
+      k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, d_queue);
+      k_sort_scatter<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_keys, d_bucket_start, d_bucket_count, d_order);
+      cudaEventRecord(ev_sched1, stream);
+      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, d_order, d_queue);
       launches++;
-      if (!ok(cudaMemcpyAsync(hq, d_queue, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
+      if (!ok(cudaMemcpyAsync(hq, d_queue, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
           !ok(cudaStreamSynchronize(stream), "k_propagate")) {
         return false;
       }
+      float sms = 0.F;
+      cudaEventElapsedTime(&sms, ev_sched0, ev_sched1);
+      sched_total += sms;
       if (T.max_steps_per_launch <= 0 && hq[1] > 0ULL) {
         error = "k_propagate left active packets in whole-history mode";
         return false;
@@ -418,8 +588,8 @@ struct CudaBackend {
     float ms = 0.F;
     cudaEventElapsedTime(&ms, ev_start, ev_stop);
     *total_ms = ms;
-    *prop_ms = ms;
-    *sched_ms = 0.;
+    *prop_ms = ms - sched_total;
+    *sched_ms = sched_total;
     return ok(cudaGetLastError(), "propagate");
   }
 };

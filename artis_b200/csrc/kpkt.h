@@ -117,7 +117,7 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
     c.count(CNT_K_STAT_TO_MA_COLLEXC);
     T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
     set_trueem_pos_nan(c);
-    do_macroatom(p, c, {element, ion, upper, -99});
+    activate_macroatom(p, {element, ion, upper, -99});
   } else {  // COOLING_COLLION
     const int upperion = ion + 1;
     const int upper = phixsupperlevel(T, uniquelevel(T, element, ion, T.cooling_level[i]), T.cooling_phixstargetindex[i]);
@@ -125,7 +125,7 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
     c.count(CNT_K_STAT_TO_MA_COLLION);
     T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
     set_trueem_pos_nan(c);
-    do_macroatom(p, c, {element, upperion, upper, -99});
+    activate_macroatom(p, {element, upperion, upper, -99});
   }
 }
 

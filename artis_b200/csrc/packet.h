@@ -12,6 +12,13 @@
 
 namespace ab {
 
+struct MacroAtomState {  // packet.h:96-105
+  int element;
+  int ion;
+  int level;
+  int activatingline;
+};
+
 struct Pkt {
   double prop_time;
   double pos[3];
@@ -26,7 +33,17 @@ struct Pkt {
   int type;
   int cellindex;
   Rng rng;
+  // A macro-atom activation is recorded here and run by the caller right after the activating step
+  // (do_macroatom runs to deactivation, so this never outlives the step: reference packet.h:52-54, TYPE_MA).
+  // Deferring it lets the propagation kernel run all of a warp's macro-atom walks together, converged.
+  MacroAtomState ma;
+  int ma_pending;
 };
+
+AHD void activate_macroatom(Pkt& p, const MacroAtomState& state) {
+  p.ma = state;
+  p.ma_pending = 1;
+}
 
 // continuum opacity of the current r-packet (reference rpkt.h:68-99 ContinuumOpacity). The per-ground-continuum
 // contributions live in the per-thread scratch column (Tables::scratch_groundcont).
@@ -37,13 +54,6 @@ struct ChiCont {
   double chi_boundfree;
   int nonemptymgi;
   AHD double total() const { return chi_escatter + chi_boundfree + chi_freefree_heat; }
-};
-
-struct MacroAtomState {  // packet.h:96-105
-  int element;
-  int ion;
-  int level;
-  int activatingline;
 };
 
 // per-thread context: tables, this packet's SoA index, thread-private accumulators
@@ -79,6 +89,8 @@ AHD void load_pkt(Pkt& p, const Tables& T, const long long ip) {
   p.next_trans = s.next_trans[ip];
   p.type = s.type[ip];
   p.cellindex = s.cellindex[ip];
+  p.ma_pending = 0;
+  p.rng.have_block = 0;
   p.rng.mode = T.rng_mode;
   p.rng.s0 = s.rng0[ip];
   p.rng.s1 = s.rng1[ip];

@@ -197,22 +197,36 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   }
 }
 
-// Advance one packet: up to `max_steps` do_packet calls (<= 0: until the end of the timestep).
-// Returns true if the packet still needs propagating this timestep.
-AHD bool propagate_packet(Pkt& p, const Ctx& c, const long long max_steps) {
-  const double ts_end = c.T.ts_end;
-  ChiCont chi;
+// run a macro-atom activation recorded by the step that has just been taken (macroatom.cc:360-596)
+AHD void finish_macroatom(Pkt& p, const Ctx& c) {
+  if (p.ma_pending != 0) {
+    p.ma_pending = 0;
+    do_macroatom(p, c, p.ma);
+  }
+}
+
+AHD void init_chicont(ChiCont& chi) {
   chi.nu = -1.;
   chi.chi_escatter = 0.;
   chi.chi_freefree_heat = 0.;
   chi.chi_boundfree = 0.;
   chi.nonemptymgi = -1;
+}
+
+// Advance one packet: up to `max_steps` do_packet calls (<= 0: until the end of the timestep).
+// Returns true if the packet still needs propagating this timestep. (Serial form, used by the host test build;
+// the CUDA kernel runs the same two calls per iteration with warp convergence points in between.)
+AHD bool propagate_packet(Pkt& p, const Ctx& c, const long long max_steps) {
+  const double ts_end = c.T.ts_end;
+  ChiCont chi;
+  init_chicont(chi);
   long long steps = 0;
   while (packetprop_update_required(p, ts_end)) {
     if (max_steps > 0 && steps >= max_steps) {
       return true;
     }
     do_packet(p, c, ts_end, chi);
+    finish_macroatom(p, c);
     steps++;
   }
   return false;

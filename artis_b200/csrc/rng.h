@@ -34,22 +34,12 @@ struct Rng {
   unsigned int key0;  // philox key word 0 (seed)
   unsigned int ctr1;  // philox counter word 1 (timestep)
   unsigned int ctr2;  // philox counter word 2 (rank)
+  unsigned int b0, b1, b2, b3;  // philox: the four outputs of block (s0 >> 2); valid when have_block != 0
+  int have_block;
 
-  AHD unsigned int next_u32() {
-    if (mode == RNG_XOSHIRO) {
-      // Xoshiro128++ (Blackman & Vigna), same output function as reference random.h:124-135
-      const unsigned int result = rotl32(s0 + s3, 7U) + s0;
-      const unsigned int t = s1 << 9U;
-      s2 ^= s0;
-      s3 ^= s1;
-      s1 ^= s2;
-      s0 ^= s3;
-      s2 ^= t;
-      s3 = rotl32(s3, 11U);
-      return result;
-    }
-    // Philox4x32-10
-    unsigned int c0 = s0;
+  AHD void philox_block(const unsigned int blockindex) {
+    // Philox4x32-10 (Salmon et al. 2011): counter (block, timestep, rank, 0), key (seed, packet number)
+    unsigned int c0 = blockindex;
     unsigned int c1 = ctr1;
     unsigned int c2 = ctr2;
     unsigned int c3 = 0U;
@@ -68,8 +58,34 @@ struct Rng {
       k0 += 0x9E3779B9U;
       k1 += 0xBB67AE85U;
     }
+    b0 = c0;
+    b1 = c1;
+    b2 = c2;
+    b3 = c3;
+    have_block = 1;
+  }
+
+  AHD unsigned int next_u32() {
+    if (mode == RNG_XOSHIRO) {
+      // Xoshiro128++ (Blackman & Vigna), same output function as reference random.h:124-135
+      const unsigned int result = rotl32(s0 + s3, 7U) + s0;
+      const unsigned int t = s1 << 9U;
+      s2 ^= s0;
+      s3 ^= s1;
+      s1 ^= s2;
+      s0 ^= s3;
+      s2 ^= t;
+      s3 = rotl32(s3, 11U);
+      return result;
+    }
+    // draw number s0 is word (s0 & 3) of Philox block (s0 >> 2): one 10-round evaluation serves four draws, and
+    // the value of a draw depends only on its index, not on where a history was split across kernel launches
+    const unsigned int word = s0 & 3U;
+    if (word == 0U || have_block == 0) {
+      philox_block(s0 >> 2U);
+    }
     s0 += 1U;
-    return c0;
+    return (word == 0U) ? b0 : ((word == 1U) ? b1 : ((word == 2U) ? b2 : b3));
   }
 
   // U[0,1) float with 24 random bits (random.h:140-166); never returns 1

@@ -323,7 +323,7 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
     const int phixstargetindex = T.cont_phixstargetindex[allcontindex];
     if (p.rng.uniform() < nu_edge / nu) {
       c.count(CNT_MA_STAT_ACTIVATION_BF);
-      do_macroatom(p, c, {element, ion + 1, phixsupperlevel(T, uniquelevel(T, element, ion, level), phixstargetindex), -99});
+      activate_macroatom(p, {element, ion + 1, phixsupperlevel(T, uniquelevel(T, element, ion, level), phixstargetindex), -99});
     } else {
       c.count(CNT_K_STAT_FROM_BF);
       p.type = TYPE_KPKT;
@@ -392,7 +392,7 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
       c.count(CNT_MA_STAT_ACTIVATION_BB);
       T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
       T.pkt.absorptionfreq[c.ip] = p.nu_rf;
-      do_macroatom(p, c, pktmastate);
+      activate_macroatom(p, pktmastate);
     }
     return (p.type == TYPE_RPKT);
   }

@@ -182,6 +182,10 @@ def run_ours(args):
     before = snap.read_snapshot(before_path)
     n = int(before["packets.count"][0])
     stride = int(before["packets.stride"][0])
+    n_sub = int(os.environ.get("ARTISB200_BENCH_NPACKETS", "0"))  # profiling aid only: propagate a packet subset
+    if 0 < n_sub < n:
+        before["packets.aos"] = before["packets.aos"][: n_sub * stride].copy()
+        n = n_sub
 
     eng = ablib.ArtisB200(preset=PRESET, device=local_rank)
     eng.set_option("rng_mode", 0)
