@@ -38,7 +38,10 @@ struct Pkt {
   // Deferring it lets the propagation kernel run all of a warp's macro-atom walks together, converged.
   MacroAtomState ma;
   int ma_pending;
+  int ev_pending;  // EV_NONE, or an r-packet event whose handling was deferred by do_rpkt_step<true>
 };
+
+enum : int { EV_NONE = 0, EV_EMIT = 1, EV_CONTINUUM = 2 };
 
 AHD void activate_macroatom(Pkt& p, const MacroAtomState& state) {
   p.ma = state;
@@ -90,6 +93,7 @@ AHD void load_pkt(Pkt& p, const Tables& T, const long long ip) {
   p.type = s.type[ip];
   p.cellindex = s.cellindex[ip];
   p.ma_pending = 0;
+  p.ev_pending = EV_NONE;
   p.rng.have_block = 0;
   p.rng.mode = T.rng_mode;
   p.rng.s0 = s.rng0[ip];

@@ -167,7 +167,7 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
       do_gamma(p, c, t2);
       break;
     case TYPE_RPKT:
-      do_rpkt_step(p, c, t2, chi);
+      do_rpkt_step<false>(p, c, t2, chi);
       break;
     case TYPE_NONTHERMAL_PREDEPOSIT_ALPHA:
     case TYPE_NONTHERMAL_PREDEPOSIT_BETAMINUS:

@@ -334,6 +334,10 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
 // One r-packet step (rpkt.cc:542-693). Returns true if the packet can keep going in this call: still an
 // r-packet and not at the end of the timestep. (The reference additionally returns to its scheduler on a
 // change of model cell, a CPU cell-cache artefact that the all-cells-resident device tables do not need.)
+// With DEFER_EVENTS the handling of a thick-cell scattering (emit_rpkt) and of a continuum event
+// (rpkt_event_continuum) is only recorded in p.ev_pending for the caller to run next; the packet's own random
+// number sequence is unchanged by this.
+template <bool DEFER_EVENTS = false>
 AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   const Tables& T = c.T;
   const int cell = T.propcell_nonemptymgi[p.cellindex];
@@ -385,9 +389,17 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
     if (thickcell) {
       T.pkt.nscatterings[c.ip]++;
       c.count(CNT_ELECTRON_SCATTERINGS);
-      emit_rpkt(p, c);
+      if constexpr (DEFER_EVENTS) {
+        p.ev_pending = EV_EMIT;
+      } else {
+        emit_rpkt(p, c);
+      }
     } else if (!event_is_boundbound) {
-      rpkt_event_continuum(p, c, chi);
+      if constexpr (DEFER_EVENTS) {
+        p.ev_pending = EV_CONTINUUM;
+      } else {
+        rpkt_event_continuum(p, c, chi);
+      }
     } else {
       c.count(CNT_MA_STAT_ACTIVATION_BB);
       T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
