@@ -39,13 +39,6 @@ __global__ void k_soa_to_aos(const __grid_constant__ Tables T, unsigned char* ao
   }
 }
 
-__global__ void k_reset_philox(const __grid_constant__ Tables T, const long long n) {
-  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  if (i < n) {
-    ab::reset_philox_one(T, i);
-  }
-}
-
 __global__ void k_build_levelpops(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(T.ncells) * T.nlevels;
@@ -91,25 +84,24 @@ __global__ void k_build_cooling(const __grid_constant__ Tables T) {
   }
 }
 
-// ---- cell-sorted packet queue: counting sort of the active packets by (packet class, model cell) -------------
-// The propagation kernel hands packets out in this order, so that the lanes of a warp start in the same cell and
-// on the same kind of packet (coalesced/broadcast table loads, same thick/thin branch); it mirrors the reference's
-// own sort of the packets by cell before each pass (update_packets.cc:363-394, 570-572) without moving the packets.
-__device__ __forceinline__ int sort_bucket_of(const Tables& T, const long long i, const int nbuckets_per_class) {
-  const int type = T.pkt.type[i];
-  if (type == ab::TYPE_ESCAPE || !(T.pkt.prop_time[i] < T.ts_end)) {
+// ---- cell-sorted packet queues: counting sort of the active packets by (stage, model cell) -------------------
+// Packets are handed to the kernels in this order, so that the lanes of a warp start in the same cell and on the
+// same kind of packet (coalesced/broadcast table loads, same branch); it mirrors the reference's own sort of the
+// packets by cell before each pass (update_packets.cc:363-394, 570-572) without moving the packets.
+__device__ __forceinline__ int sort_bucket_of(const Tables& T, const long long i, const int nbuckets_per_stage) {
+  const int stage = ab::stored_stage(T.pkt.hc[i]);
+  if (stage < 0) {
     return -1;  // nothing to do this timestep
   }
-  const int cls = (type == ab::TYPE_RPKT) ? 0 : ((type == ab::TYPE_KPKT) ? 1 : 2);
-  const int cell = T.propcell_nonemptymgi[T.pkt.cellindex[i]];
-  return (cls * nbuckets_per_class) + cell + 1;  // empty cells (-1) -> 0
+  const int cell = T.propcell_nonemptymgi[T.pkt.hc[i].cellindex];
+  return (stage * nbuckets_per_stage) + cell + 1;  // empty cells (-1) -> 0
 }
 
-__global__ void k_sort_count(const __grid_constant__ Tables T, const long long n, const int nbuckets_per_class, int* keys,
+__global__ void k_sort_count(const __grid_constant__ Tables T, const long long n, const int nbuckets_per_stage, int* keys,
                              unsigned int* bucket_count) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   if (i < n) {
-    const int b = sort_bucket_of(T, i, nbuckets_per_class);
+    const int b = sort_bucket_of(T, i, nbuckets_per_stage);
     keys[i] = b;
     if (b >= 0) {
       atomicAdd(&bucket_count[b], 1U);
@@ -117,8 +109,10 @@ __global__ void k_sort_count(const __grid_constant__ Tables T, const long long n
   }
 }
 
-// exclusive scan of the bucket counts (a few thousand entries): one block, each thread scans a contiguous chunk
-__global__ void k_sort_scan(unsigned int* bucket_count, unsigned int* bucket_start, const int nbuckets, unsigned long long* queue) {
+// exclusive scan of the bucket counts (a few thousand entries): one block, each thread scans a contiguous chunk.
+// Also writes the number of active packets (queue[2]) and the per-stage list lengths (stage_count[0..NSTAGES)).
+__global__ void k_sort_scan(unsigned int* bucket_count, unsigned int* bucket_start, const int nbuckets,
+                            const int nbuckets_per_stage, unsigned long long* queue, unsigned int* stage_count) {
   __shared__ unsigned int chunk_total[1024];
   const int nthreads = blockDim.x;
   const int chunk = (nbuckets + nthreads - 1) / nthreads;
@@ -146,6 +140,13 @@ __global__ void k_sort_scan(unsigned int* bucket_count, unsigned int* bucket_sta
     running += bucket_count[b];
     bucket_count[b] = 0U;  // reused as the scatter cursor
   }
+  __syncthreads();
+  if (threadIdx.x < ab::NSTAGES) {
+    const int first = threadIdx.x * nbuckets_per_stage;
+    const int next = first + nbuckets_per_stage;
+    const unsigned int stop = (next < nbuckets) ? bucket_start[next] : static_cast<unsigned int>(queue[2]);
+    stage_count[threadIdx.x] = stop - bucket_start[first];
+  }
 }
 
 __global__ void k_sort_scatter(const long long n, const int* keys, const unsigned int* bucket_start, unsigned int* bucket_cursor,
@@ -159,65 +160,207 @@ __global__ void k_sort_scatter(const long long n, const int* keys, const unsigne
   }
 }
 
-__global__ void k_test_kernel(const __grid_constant__ Tables T, const int which, const long long n, const double* in_f64,
-                              const int* in_i32, double* out_f64, int* out_i32) {
-  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  if (i < n) {
-    ab::test_kernel_item(T, which, i, i, in_f64, in_i32, out_f64, out_i32);
+// ---- block-local accumulators ----------------------------------------------------------------------------------
+__device__ __forceinline__ void accum_zero(ab::Accum& acc) {
+  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
+    acc.cnt[k] = 0U;
+  }
+  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
+    acc.diag[k] = 0U;
+  }
+  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
+    acc.tss[k] = 0.;
+  }
+  if (threadIdx.x == 0) {
+    acc.pellet_decays = 0U;
+  }
+  __syncthreads();
+}
+
+// one global atomic per block and non-zero entry
+__device__ __forceinline__ void accum_flush(const ab::Accum& acc, const Tables& T) {
+  __syncthreads();
+  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
+    if (acc.cnt[k] != 0U) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&T.counters[k]), static_cast<unsigned long long>(acc.cnt[k]));
+    }
+  }
+  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
+    if (acc.diag[k] != 0U) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&T.diag[k]), static_cast<unsigned long long>(acc.diag[k]));
+    }
+  }
+  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
+    if (acc.tss[k] != 0.) {
+      atomicAdd(&T.ts_scalars[k], acc.tss[k]);
+    }
+  }
+  if (threadIdx.x == 0 && acc.pellet_decays != 0U) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(T.ts_pellet_decays), static_cast<unsigned long long>(acc.pellet_decays));
   }
 }
 
+__global__ void k_test_kernel(const __grid_constant__ Tables T, const int which, const long long n, const double* in_f64,
+                              const int* in_i32, double* out_f64, int* out_i32) {
+  __shared__ ab::Accum acc;  // work counters of the tested functions (discarded)
+  accum_zero(acc);
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::test_kernel_item(T, acc, which, i, i, in_f64, in_i32, out_f64, out_i32);
+  }
+}
+
+// ---- wavefront schedule ---------------------------------------------------------------------------------------
+// Every active packet waits in one stage list (packet.h ST_*). One iteration runs one kernel per stage over the
+// stage's list: each thread loads a packet, runs that stage's physics once, stores the packet and appends its
+// index to the list of the stage it waits in next (warp-aggregated: one atomic per warp and destination).
+// All lanes of a warp therefore execute the same stage, and each kernel carries only its own stage's code
+// (the first, one-kernel version of this path ran 4-5 of 32 lanes per issued instruction and spent 72 % of its
+// stall samples waiting for instructions: profiles/r1_k_propagate_v1.md).
+struct WfQueues {
+  int* list[2][ab::NSTAGES];  // double-buffered index lists
+  unsigned int* count;        // [2][NSTAGES] list lengths
+  unsigned int* cursor;       // [NSTAGES] next 32-packet chunk of the running iteration's lists
+  unsigned long long* status; // [0] packets waiting after the last completed iteration, [1] iterations run
+};
+
+// threads per block / minimum resident blocks per SM of the stage kernels (the register budget follows from it)
+#ifndef ARTISB200_WF_BLOCK
+#define ARTISB200_WF_BLOCK 128
+#endif
+#ifndef ARTISB200_WF_MINBLOCKS
+#define ARTISB200_WF_MINBLOCKS 4
+#endif
+constexpr int WF_BLOCK = ARTISB200_WF_BLOCK;
+
+template <int STAGE>
+__global__ void __launch_bounds__(WF_BLOCK, ARTISB200_WF_MINBLOCKS)
+    k_wf_stage(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int max_steps) {
+  __shared__ ab::Accum acc;
+  accum_zero(acc);
+  constexpr unsigned FULL = 0xffffffffU;
+  const unsigned int n = q.count[(cur * ab::NSTAGES) + STAGE];
+  const int* __restrict__ in = q.list[cur][STAGE];
+  const unsigned int lane = threadIdx.x & 31U;
+  unsigned int hot[ab::Ctx::NHOT] = {};
+  while (true) {
+    // warps fetch 32-packet chunks dynamically: the work per packet varies (line walks, continuum sums, walks)
+    unsigned int base = 0U;
+    if (lane == 0U) {
+      base = atomicAdd(&q.cursor[STAGE], 32U);
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= n) {
+      break;
+    }
+    const unsigned int k = base + lane;
+    int dest = ab::ST_DONE;
+    int ip = 0;
+    if (k < n) {
+      ip = in[k];
+      ab::Pkt p;
+      ab::ChiCont chi;
+      ab::load_pkt<STAGE>(p, chi, T, ip);
+      const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+      ab::run_stage<STAGE>(p, c, chi, max_steps);
+      dest = ab::stage_of(p, T);
+      ab::store_pkt<STAGE>(p, chi, T, ip, dest);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < ab::NSTAGES; s++) {
+      const unsigned m = __ballot_sync(FULL, dest == s);
+      if (m != 0U) {
+        // macro-atom activations recorded by the other stages are run in the same iteration (the macro-atom kernel
+        // is launched last); walks it leaves unfinished continue in the next one
+        const int buf = (s == ab::ST_MA && STAGE != ab::ST_MA) ? cur : (cur ^ 1);
+        const int leader = __ffs(m) - 1;
+        unsigned int pos = 0U;
+        if (lane == static_cast<unsigned int>(leader)) {
+          pos = atomicAdd(&q.count[(buf * ab::NSTAGES) + s], static_cast<unsigned int>(__popc(m)));
+        }
+        pos = __shfl_sync(FULL, pos, leader);
+        if (dest == s) {
+          q.list[buf][s][pos + __popc(m & ((1U << lane) - 1U))] = ip;
+        }
+      }
+    }
+  }
+  ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
+  accum_flush(acc, T);
+}
+
+// initial lists = the stage ranges of the cell-sorted order
+__global__ void k_wf_seed(const WfQueues q, const int* __restrict__ order, const unsigned int* __restrict__ stage_count) {
+  unsigned int offset[ab::NSTAGES + 1];
+  offset[0] = 0U;
+  for (int s = 0; s < ab::NSTAGES; s++) {
+    offset[s + 1] = offset[s] + stage_count[s];
+  }
+  const long long total = offset[ab::NSTAGES];
+  for (long long k = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x; k < total;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int s = 0;
+    while (k >= offset[s + 1]) {
+      s++;
+    }
+    q.list[0][s][k - offset[s]] = order[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2 * ab::NSTAGES) {
+    q.count[threadIdx.x] = (threadIdx.x < ab::NSTAGES) ? stage_count[threadIdx.x] : 0U;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ab::NSTAGES) {
+    q.cursor[threadIdx.x] = 0U;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q.status[0] = static_cast<unsigned long long>(total);
+    q.status[1] = 0ULL;
+  }
+}
+
+// end of an iteration: the consumed lists become the (empty) output lists of the next iteration
+__global__ void k_wf_advance(const WfQueues q, const int cur) {
+  if (threadIdx.x == 0) {
+    unsigned long long waiting = 0ULL;
+    for (int s = 0; s < ab::NSTAGES; s++) {
+      q.count[(cur * ab::NSTAGES) + s] = 0U;
+      q.cursor[s] = 0U;
+      waiting += q.count[((cur ^ 1) * ab::NSTAGES) + s];
+    }
+    q.status[0] = waiting;
+    q.status[1] += 1ULL;
+  }
+}
+
+__global__ void k_reset_work(const __grid_constant__ Tables T, const long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    ab::reset_work_one(T, i);
+  }
+}
+
+// ---- whole-history kernel -------------------------------------------------------------------------------------
+// One thread per packet history with a per-thread dynamic work fetch. It finishes the thin tail of the wavefront
+// (a few thousand packets with long histories, where one launch per step would be launch-bound) and is the
+// "history" schedule that the wavefront is measured against.
 // queue[0]: next queue position to hand out; queue[1]: packets that still need work after this launch;
 // queue[2]: number of active packets in `order`
 __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const int* __restrict__ order,
                                                           unsigned long long* queue) {
-  __shared__ unsigned long long s_cnt[ab::CNT_COUNT];
-  __shared__ unsigned long long s_diag[ab::NDIAG];
-  __shared__ double s_tss[ab::NTSSCALARS];
-  __shared__ unsigned long long s_misc[2];  // pellet decays, still-active packets
-  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
-    s_cnt[k] = 0ULL;
+  __shared__ ab::Accum acc;
+  __shared__ unsigned int s_still_active;
+  if (threadIdx.x == 0) {
+    s_still_active = 0U;
   }
-  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
-    s_diag[k] = 0ULL;
-  }
-  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
-    s_tss[k] = 0.;
-  }
-  if (threadIdx.x < 2) {
-    s_misc[threadIdx.x] = 0ULL;
-  }
-  __syncthreads();
+  accum_zero(acc);
 
-  int cnt[ab::CNT_COUNT];
-  long long diag[ab::NDIAG];
-  double tss[ab::NTSSCALARS];
-  long long pellet_decays = 0;
-  long long still_active = 0;
-#pragma unroll
-  for (int k = 0; k < ab::CNT_COUNT; k++) {
-    cnt[k] = 0;
-  }
-#pragma unroll
-  for (int k = 0; k < ab::NDIAG; k++) {
-    diag[k] = 0;
-  }
-#pragma unroll
-  for (int k = 0; k < ab::NTSSCALARS; k++) {
-    tss[k] = 0.;
-  }
-
-  const long long tid = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   const double ts_end = T.ts_end;
-  // Warp-synchronous phase machine. Every lane owns one packet at a time; each iteration of the loop takes the
-  // warp through the same sequence of phases with a convergence point (__syncwarp) before each, so that lanes
-  // in the same phase execute it together instead of being scattered over unrelated points of a long history
-  // (measured on the first version of this kernel, which ran each history straight through: 4.1 of 32 lanes
-  // active per issued instruction, profiles/r1_k_propagate_v1.md):
+  // Warp-synchronous phase machine: every lane owns one packet at a time; each iteration takes the warp through
   //   refill   lanes whose packet is finished fetch the next active packet from the global queue
   //   phase A  one step of the rare packet types (pellet, gamma, k-packet, non-thermal)
   //   phase B  one r-packet transport step (boundary / line walk / continuum / event selection)
   //   phase C  macro-atom walks activated in phases A/B, run to deactivation
+  // with a convergence point (__syncwarp) before each.
   constexpr unsigned FULL = 0xffffffffU;
   const long long max_steps = T.max_steps_per_launch;
   const unsigned long long nactive = queue[2];
@@ -228,102 +371,57 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
   p.ma_pending = 0;
   long long ip = 0;
   long long steps = 0;
+  unsigned int hot[ab::Ctx::NHOT] = {};
   bool have = false;
   bool exhausted = false;
   while (true) {
     __syncwarp();
     if (!have && !exhausted) {
-      while (true) {
-        const unsigned long long q = atomicAdd(&queue[0], 1ULL);
-        if (q >= nactive) {
-          exhausted = true;
-          break;
-        }
-        const long long i = order[q];
-        ip = i;
-        ab::load_pkt(p, T, ip);
-        ab::init_chicont(chi);
+      const unsigned long long qpos = atomicAdd(&queue[0], 1ULL);
+      if (qpos >= nactive) {
+        exhausted = true;
+      } else {
+        ip = order[qpos];
+        ab::load_pkt(p, chi, T, ip);
         steps = 0;
         have = true;
-        diag[ab::DIAG_PACKET_SEGMENTS]++;
-        break;
+        atomicAdd(&acc.diag[ab::DIAG_PACKET_SEGMENTS], 1U);
       }
     }
     if (__all_sync(FULL, !have)) {
       break;
     }
-    const ab::Ctx c{T, ip, tid, cnt, diag, tss, &pellet_decays};
-    if (have && p.type != ab::TYPE_RPKT) {  // phase A
+    const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+    if (have && p.ma_pending == 0 && p.ev_pending == ab::EV_NONE && p.type != ab::TYPE_RPKT) {  // phase A
       ab::do_packet(p, c, ts_end, chi);
       steps++;
     }
     __syncwarp();
-    if (have && p.type == ab::TYPE_RPKT && p.ma_pending == 0 && ab::packetprop_update_required(p, ts_end)) {  // phase B
+    if (have && p.type == ab::TYPE_RPKT && p.ma_pending == 0 && p.ev_pending == ab::EV_NONE &&
+        ab::packetprop_update_required(p, ts_end)) {  // phase B
       ab::do_rpkt_step(p, c, ts_end, chi);
       steps++;
     }
     __syncwarp();
-    if (have && p.ma_pending != 0) {  // phase C
+    if (have && (p.ma_pending != 0 || p.ev_pending != ab::EV_NONE)) {  // phase C (+ the re-emission it leaves pending)
       ab::finish_macroatom(p, c);
     }
     if (have) {
       const bool more = ab::packetprop_update_required(p, ts_end);
       const bool yield = more && max_steps > 0 && steps >= max_steps;
       if (!more || yield) {
-        ab::store_pkt(p, T, ip);
+        ab::store_pkt(p, chi, T, ip, ab::stage_of(p, T));
         have = false;
         if (yield) {
-          still_active++;
+          atomicAdd(&s_still_active, 1U);
         }
       }
     }
   }
-
-  // block-level reduction in shared memory, then one global atomic per block and counter
-  for (int k = 0; k < ab::CNT_COUNT; k++) {
-    if (cnt[k] != 0) {
-      atomicAdd(&s_cnt[k], static_cast<unsigned long long>(cnt[k]));
-    }
-  }
-  for (int k = 0; k < ab::NDIAG; k++) {
-    if (diag[k] != 0) {
-      atomicAdd(&s_diag[k], static_cast<unsigned long long>(diag[k]));
-    }
-  }
-  for (int k = 0; k < ab::NTSSCALARS; k++) {
-    if (tss[k] != 0.) {
-      atomicAdd(&s_tss[k], tss[k]);
-    }
-  }
-  if (pellet_decays != 0) {
-    atomicAdd(&s_misc[0], static_cast<unsigned long long>(pellet_decays));
-  }
-  if (still_active != 0) {
-    atomicAdd(&s_misc[1], static_cast<unsigned long long>(still_active));
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
-    if (s_cnt[k] != 0ULL) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(&T.counters[k]), s_cnt[k]);
-    }
-  }
-  for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
-    if (s_diag[k] != 0ULL) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(&T.diag[k]), s_diag[k]);
-    }
-  }
-  for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
-    if (s_tss[k] != 0.) {
-      atomicAdd(&T.ts_scalars[k], s_tss[k]);
-    }
-  }
-  if (threadIdx.x == 0) {
-    if (s_misc[0] != 0ULL) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(T.ts_pellet_decays), s_misc[0]);
-    }
-    if (s_misc[1] != 0ULL) {
-      atomicAdd(&queue[1], s_misc[1]);
-    }
+  ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
+  accum_flush(acc, T);
+  if (threadIdx.x == 0 && s_still_active != 0U) {
+    atomicAdd(&queue[1], static_cast<unsigned long long>(s_still_active));
   }
 }
 
@@ -337,14 +435,21 @@ struct CudaBackend {
   cudaEvent_t ev_sched0{nullptr};
   cudaEvent_t ev_sched1{nullptr};
   unsigned long long* d_queue{nullptr};
-  double* d_scratch{nullptr};
-  long long scratch_elems{0};
   int* d_keys{nullptr};
   int* d_order{nullptr};
   long long sort_capacity{0};
   unsigned int* d_bucket_count{nullptr};
   unsigned int* d_bucket_start{nullptr};
   int bucket_capacity{0};
+  unsigned int* d_stage_count{nullptr};  // [NSTAGES] list lengths of the cell-sorted order
+  unsigned int* d_wf_count{nullptr};     // [2][NSTAGES] list lengths + [NSTAGES] chunk cursors
+  int* d_wf_lists{nullptr};              // [2][NSTAGES][wf_capacity]
+  long long wf_capacity{0};
+  int history_blocks_per_sm{0};
+  int stage_blocks_per_sm[ab::NSTAGES]{};
+  std::vector<cudaEvent_t> stage_events;
+  cudaEvent_t ev_tail0{nullptr};
+  cudaEvent_t ev_tail1{nullptr};
 
   bool ok(const cudaError_t e, const char* what) {
     if (e != cudaSuccess) {
@@ -382,7 +487,12 @@ struct CudaBackend {
         !ok(cudaEventCreate(&ev_sched0), "cudaEventCreate") || !ok(cudaEventCreate(&ev_sched1), "cudaEventCreate")) {
       return false;
     }
-    if (!ok(cudaMalloc(&d_queue, 4 * sizeof(unsigned long long)), "cudaMalloc(queue)")) {
+    if (!ok(cudaEventCreate(&ev_tail0), "cudaEventCreate") || !ok(cudaEventCreate(&ev_tail1), "cudaEventCreate")) {
+      return false;
+    }
+    if (!ok(cudaMalloc(&d_queue, 8 * sizeof(unsigned long long)), "cudaMalloc(queue)") ||
+        !ok(cudaMalloc(&d_stage_count, ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(stage counts)") ||
+        !ok(cudaMalloc(&d_wf_count, 3 * ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(list counts)")) {
       return false;
     }
     return true;
@@ -393,11 +503,20 @@ struct CudaBackend {
       cudaSetDevice(device);
       cudaStreamSynchronize(stream);
       cudaFree(d_queue);
-      cudaFree(d_scratch);
       cudaFree(d_keys);
       cudaFree(d_order);
       cudaFree(d_bucket_count);
       cudaFree(d_bucket_start);
+      cudaFree(d_stage_count);
+      cudaFree(d_wf_count);
+      cudaFree(d_wf_lists);
+      for (cudaEvent_t e : stage_events) {
+        cudaEventDestroy(e);
+      }
+      cudaEventDestroy(ev_tail0);
+      cudaEventDestroy(ev_tail1);
+      cudaEventDestroy(ev_sched0);
+      cudaEventDestroy(ev_sched1);
       cudaEventDestroy(ev_start);
       cudaEventDestroy(ev_stop);
       cudaStreamDestroy(stream);
@@ -474,12 +593,15 @@ struct CudaBackend {
     if (!ok(cudaMalloc(&scratch, static_cast<size_t>(n * ng) * sizeof(double)), "cudaMalloc(test scratch)")) {
       return false;
     }
+    double* const saved = T.scratch_groundcont;
+    const long long saved_stride = T.scratch_stride;
     T.scratch_groundcont = scratch;
     T.scratch_stride = n;
     k_test_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(T, which, n, in_f64, in_i32, out_f64, out_i32);
     const bool good = ok(cudaStreamSynchronize(stream), "k_test_kernel") && ok(cudaGetLastError(), "k_test_kernel");
     cudaFree(scratch);
-    T.scratch_groundcont = nullptr;
+    T.scratch_groundcont = saved;
+    T.scratch_stride = saved_stride;
     return good;
   }
 
@@ -499,97 +621,199 @@ struct CudaBackend {
     return ok(cudaGetLastError(), "k_soa_to_aos");
   }
 
-  bool propagate(Tables& T, const int64_t n, bool /*sort*/, double* total_ms, double* prop_ms, double* sched_ms) {
-    cudaSetDevice(device);
-    // persistent grid: a multiple of the SM count, sized for the resident blocks per SM of this kernel
-    int blocks_per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_propagate, PROP_BLOCK, 0);
-    if (blocks_per_sm < 1) {
-      blocks_per_sm = 1;
-    }
-    long long nblocks = static_cast<long long>(sm_count) * blocks_per_sm;
-    const long long needed = (n + PROP_BLOCK - 1) / PROP_BLOCK;
-    if (nblocks > needed) {
-      nblocks = needed;
-    }
-    const long long nthreads = nblocks * PROP_BLOCK;
-    const long long ng = T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1;
-    if (scratch_elems < nthreads * ng) {
-      cudaFree(d_scratch);
-      d_scratch = nullptr;
-      if (!ok(cudaMalloc(&d_scratch, static_cast<size_t>(nthreads * ng) * sizeof(double)), "cudaMalloc(scratch)")) {
-        return false;
-      }
-      scratch_elems = nthreads * ng;
-    }
-    T.scratch_groundcont = d_scratch;
-    T.scratch_stride = nthreads;
+  template <class Ptr>
+  bool grow(Ptr*& ptr, const size_t nbytes, const char* what) {
+    cudaFree(ptr);
+    ptr = nullptr;
+    return ok(cudaMalloc(&ptr, nbytes), what);
+  }
 
-    const int nbuckets_per_class = T.ncells + 1;
-    const int nbuckets = 3 * nbuckets_per_class;
+  bool ensure_schedule_buffers(const Tables& T, const int64_t n, const bool wavefront) {
+    const int nbuckets = ab::NSTAGES * (T.ncells + 1);
     if (sort_capacity < n) {
-      cudaFree(d_keys);
-      cudaFree(d_order);
-      d_keys = nullptr;
-      d_order = nullptr;
-      if (!ok(cudaMalloc(&d_keys, static_cast<size_t>(n) * sizeof(int)), "cudaMalloc(sort keys)") ||
-          !ok(cudaMalloc(&d_order, static_cast<size_t>(n) * sizeof(int)), "cudaMalloc(sort order)")) {
+      if (!grow(d_keys, static_cast<size_t>(n) * sizeof(int), "cudaMalloc(sort keys)") ||
+          !grow(d_order, static_cast<size_t>(n) * sizeof(int), "cudaMalloc(sort order)")) {
         return false;
       }
       sort_capacity = n;
     }
     if (bucket_capacity < nbuckets) {
-      cudaFree(d_bucket_count);
-      cudaFree(d_bucket_start);
-      d_bucket_count = nullptr;
-      d_bucket_start = nullptr;
-      if (!ok(cudaMalloc(&d_bucket_count, static_cast<size_t>(nbuckets) * sizeof(unsigned int)), "cudaMalloc(buckets)") ||
-          !ok(cudaMalloc(&d_bucket_start, static_cast<size_t>(nbuckets) * sizeof(unsigned int)), "cudaMalloc(buckets)")) {
+      if (!grow(d_bucket_count, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)") ||
+          !grow(d_bucket_start, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)")) {
         return false;
       }
       bucket_capacity = nbuckets;
     }
-
-    cudaEventRecord(ev_start, stream);
-    if (T.rng_mode == ab::RNG_PHILOX) {
-      k_reset_philox<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
+    if (wavefront && wf_capacity < n) {
+      if (!grow(d_wf_lists, static_cast<size_t>(2 * ab::NSTAGES) * static_cast<size_t>(n) * sizeof(int), "cudaMalloc(stage lists)")) {
+        return false;
+      }
+      wf_capacity = n;
     }
-    long long launches = 0;
-    float sched_total = 0.F;
+    return true;
+  }
+
+  void sort_active(const Tables& T, const int64_t n) {
+    const int nbuckets_per_stage = T.ncells + 1;
+    const int nbuckets = ab::NSTAGES * nbuckets_per_stage;
+    cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
+    k_sort_count<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, nbuckets_per_stage, d_keys, d_bucket_count);
+    k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, nbuckets_per_stage, d_queue, d_stage_count);
+    k_sort_scatter<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_keys, d_bucket_start, d_bucket_count, d_order);
+  }
+
+  // whole-history kernel over every packet that still needs work, relaunched while max_steps_per_launch leaves any
+  bool run_history(const Tables& T, const int64_t n, ab::PropagateTimings* tm) {
+    if (history_blocks_per_sm == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&history_blocks_per_sm, k_propagate, PROP_BLOCK, 0);
+      history_blocks_per_sm = (history_blocks_per_sm < 1) ? 1 : history_blocks_per_sm;
+    }
+    long long nblocks = static_cast<long long>(sm_count) * history_blocks_per_sm;
+    const long long needed = (n + PROP_BLOCK - 1) / PROP_BLOCK;
+    nblocks = (nblocks > needed) ? needed : nblocks;
     unsigned long long hq[4] = {0ULL, 1ULL, 0ULL, 0ULL};
     while (hq[1] > 0ULL) {
-      // (re)build the cell-sorted queue of the packets that still need work
       cudaEventRecord(ev_sched0, stream);
-      cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
-      cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
-      k_sort_count<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, nbuckets_per_class, d_keys, d_bucket_count);
-      k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, d_queue);
-      k_sort_scatter<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_keys, d_bucket_start, d_bucket_count, d_order);
+      sort_active(T, n);
       cudaEventRecord(ev_sched1, stream);
       k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, d_order, d_queue);
-      launches++;
+      tm->launches += 4;
       if (!ok(cudaMemcpyAsync(hq, d_queue, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
           !ok(cudaStreamSynchronize(stream), "k_propagate")) {
         return false;
       }
       float sms = 0.F;
       cudaEventElapsedTime(&sms, ev_sched0, ev_sched1);
-      sched_total += sms;
+      tm->schedule_ms += sms;
       if (T.max_steps_per_launch <= 0 && hq[1] > 0ULL) {
         error = "k_propagate left active packets in whole-history mode";
         return false;
       }
     }
-    cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    return true;
+  }
+
+  template <int STAGE>
+  void launch_stage(const Tables& T, const WfQueues& q, const int cur, const int max_steps, const unsigned int grid_limit) {
+    if (stage_blocks_per_sm[STAGE] == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stage_blocks_per_sm[STAGE], k_wf_stage<STAGE>, WF_BLOCK, 0);
+      stage_blocks_per_sm[STAGE] = (stage_blocks_per_sm[STAGE] < 1) ? 1 : stage_blocks_per_sm[STAGE];
+    }
+    // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
+    unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
+    grid = (grid > grid_limit) ? grid_limit : grid;
+    k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, stream>>>(T, q, cur, max_steps);
+  }
+
+  bool run_wavefront(const Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
+    WfQueues q{};
+    for (int b = 0; b < 2; b++) {
+      for (int s = 0; s < ab::NSTAGES; s++) {
+        q.list[b][s] = d_wf_lists + (static_cast<size_t>((b * ab::NSTAGES) + s) * static_cast<size_t>(wf_capacity));
+      }
+    }
+    q.count = d_wf_count;
+    q.cursor = d_wf_count + (2 * ab::NSTAGES);
+    q.status = d_queue + 4;
+    cudaEventRecord(ev_sched0, stream);
+    sort_active(T, n);
+    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, stream>>>(q, d_order, d_stage_count);
+    cudaEventRecord(ev_sched1, stream);
+    tm->launches += 4;
+
+    const bool timing = (o.stage_timing != 0);
+    const int sync_every = (o.sync_every < 1) ? 1 : o.sync_every;
+    if (timing && stage_events.size() < static_cast<size_t>(sync_every) * (ab::NSTAGES + 1)) {
+      const size_t want = static_cast<size_t>(sync_every) * (ab::NSTAGES + 1);
+      while (stage_events.size() < want) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        stage_events.push_back(e);
+      }
+    }
+    unsigned long long status[2] = {static_cast<unsigned long long>(n), 0ULL};
+    int cur = 0;
+    while (true) {
+      // every list of the coming iterations is at most as long as the number of packets waiting now
+      const unsigned long long bound = (status[0] + WF_BLOCK - 1ULL) / WF_BLOCK;
+      const unsigned int grid_limit = static_cast<unsigned int>((bound < 1ULL) ? 1ULL : ((bound > 1048576ULL) ? 1048576ULL : bound));
+      for (int it = 0; it < sync_every; it++) {
+        cudaEvent_t* ev = timing ? &stage_events[static_cast<size_t>(it) * (ab::NSTAGES + 1)] : nullptr;
+        if (timing) { cudaEventRecord(ev[0], stream); }
+        launch_stage<ab::ST_OTHER>(T, q, cur, 1, grid_limit);
+        if (timing) { cudaEventRecord(ev[1], stream); }
+        launch_stage<ab::ST_RTHIN>(T, q, cur, o.rsteps_thin, grid_limit);
+        if (timing) { cudaEventRecord(ev[2], stream); }
+        launch_stage<ab::ST_RTHICK>(T, q, cur, o.rsteps_thick, grid_limit);
+        if (timing) { cudaEventRecord(ev[3], stream); }
+        launch_stage<ab::ST_MA>(T, q, cur, o.masteps, grid_limit);
+        if (timing) { cudaEventRecord(ev[4], stream); }
+        k_wf_advance<<<1, 32, 0, stream>>>(q, cur);
+        cur ^= 1;
+      }
+      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + 1);
+      tm->iterations += sync_every;
+      if (!ok(cudaMemcpyAsync(status, q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "status readback") ||
+          !ok(cudaStreamSynchronize(stream), "wavefront iteration")) {
+        return false;
+      }
+      if (timing) {
+        for (int it = 0; it < sync_every; it++) {
+          for (int s = 0; s < ab::NSTAGES; s++) {
+            float ms = 0.F;
+            cudaEventElapsedTime(&ms, stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s],
+                                 stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s + 1]);
+            tm->stage_ms[s] += ms;
+          }
+        }
+      }
+      if (status[0] == 0ULL) {
+        break;
+      }
+      if (static_cast<long long>(status[0]) <= o.tail_threshold) {
+        // thin tail: few packets with long histories; finish them with the whole-history kernel
+        cudaEventRecord(ev_tail0, stream);
+        tm->tail_packets = static_cast<long long>(status[0]);
+        if (!run_history(T, n, tm)) {
+          return false;
+        }
+        cudaEventRecord(ev_tail1, stream);
+        cudaEventSynchronize(ev_tail1);
+        float ms = 0.F;
+        cudaEventElapsedTime(&ms, ev_tail0, ev_tail1);
+        tm->tail_ms = ms;
+        break;
+      }
+    }
+    float sms = 0.F;
+    cudaEventElapsedTime(&sms, ev_sched0, ev_sched1);
+    tm->schedule_ms += sms;
+    return true;
+  }
+
+  bool propagate(Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
+    cudaSetDevice(device);
+    *tm = ab::PropagateTimings{};
+    if (!ensure_schedule_buffers(T, n, o.schedule == 1)) {
+      return false;
+    }
+    cudaEventRecord(ev_start, stream);
+    k_reset_work<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
+    tm->launches += 1;
+    const bool good = (o.schedule == 1) ? run_wavefront(T, n, o, tm) : run_history(T, n, tm);
+    if (!good) {
+      return false;
+    }
+    cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &tm->launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
     cudaEventRecord(ev_stop, stream);
     if (!ok(cudaEventSynchronize(ev_stop), "cudaEventSynchronize")) {
       return false;
     }
     float ms = 0.F;
     cudaEventElapsedTime(&ms, ev_start, ev_stop);
-    *total_ms = ms;
-    *prop_ms = ms - sched_total;
-    *sched_ms = sched_total;
+    tm->total_ms = ms;
+    tm->propagate_ms = ms - tm->schedule_ms;
     return ok(cudaGetLastError(), "propagate");
   }
 };

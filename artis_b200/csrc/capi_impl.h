@@ -114,9 +114,21 @@ int artisb200_estimator_device_buffer(artisb200_ctx* ctx, void** device_ptr, int
 }
 
 int artisb200_last_timing_ms(artisb200_ctx* ctx, double* total_ms, double* propagate_ms, double* schedule_ms) {
-  *total_ms = ctx->eng.last_total_ms;
-  *propagate_ms = ctx->eng.last_propagate_ms;
-  *schedule_ms = ctx->eng.last_schedule_ms;
+  *total_ms = ctx->eng.last.total_ms;
+  *propagate_ms = ctx->eng.last.propagate_ms;
+  *schedule_ms = ctx->eng.last.schedule_ms;
+  return 0;
+}
+
+int artisb200_last_schedule_stats(artisb200_ctx* ctx, double* stage_ms, double* tail_ms, int64_t* tail_packets, int64_t* iterations,
+                                  int64_t* launches) {
+  for (int s = 0; s < ab::NSTAGES; s++) {
+    stage_ms[s] = ctx->eng.last.stage_ms[s];
+  }
+  *tail_ms = ctx->eng.last.tail_ms;
+  *tail_packets = ctx->eng.last.tail_packets;
+  *iterations = ctx->eng.last.iterations;
+  *launches = ctx->eng.last.launches;
   return 0;
 }
 

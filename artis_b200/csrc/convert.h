@@ -23,41 +23,58 @@ AHD void wr(unsigned char* base, const int off, const U v) {
   memcpy(base + off, &v, sizeof(U));
 }
 
+// reference Packet (240 B, or 256 B with the GPU_ON rngstate prefix) -> device records
 AHD void aos_to_soa_one(const Tables& T, const unsigned char* aos, const int stride, const long long i) {
   const unsigned char* rec = aos + (i * stride);
   const int b = stride - AosLayout::size;  // 0 or 16
   const unsigned char* q = rec + b;
-  const PacketSoA& s = T.pkt;
+  const PacketStore& s = T.pkt;
   using L = AosLayout;
-  s.prop_time[i] = rd<double>(q, L::prop_time);
-  s.pos_x[i] = rd<double>(q, L::pos);
-  s.pos_y[i] = rd<double>(q, L::pos + 8);
-  s.pos_z[i] = rd<double>(q, L::pos + 16);
-  s.dir_x[i] = rd<double>(q, L::dir);
-  s.dir_y[i] = rd<double>(q, L::dir + 8);
-  s.dir_z[i] = rd<double>(q, L::dir + 16);
-  s.nu_cmf[i] = rd<double>(q, L::nu_cmf);
-  s.e_cmf[i] = rd<double>(q, L::e_cmf);
-  s.nu_rf[i] = rd<double>(q, L::nu_rf);
-  s.e_rf[i] = rd<double>(q, L::e_rf);
-  s.next_trans[i] = rd<int>(q, L::next_trans);
-  s.nscatterings[i] = rd<int>(q, L::nscatterings);
-  s.emissiontype[i] = rd<int>(q, L::emissiontype);
-  s.em_pos_x[i] = rd<double>(q, L::em_pos);
-  s.em_pos_y[i] = rd<double>(q, L::em_pos + 8);
-  s.em_pos_z[i] = rd<double>(q, L::em_pos + 16);
-  s.em_time[i] = rd<float>(q, L::em_time);
+  HotA ha;
+  ha.prop_time = rd<double>(q, L::prop_time);
+  HotB hb;
+  for (int d = 0; d < 3; d++) {
+    ha.pos[d] = rd<double>(q, L::pos + (8 * d));
+    ha.dir[d] = rd<double>(q, L::dir + (8 * d));
+  }
+  ha.nu_cmf = rd<double>(q, L::nu_cmf);
+  hb.e_cmf = rd<double>(q, L::e_cmf);
+  hb.nu_rf = rd<double>(q, L::nu_rf);
+  hb.e_rf = rd<double>(q, L::e_rf);
+  hb.stokes_q = rd<double>(q, L::stokes_q);
+  hb.stokes_u = rd<double>(q, L::stokes_u);
+  hb.chi_nu = -1.;
+  hb.chi_escatter = 0.;
+  hb.chi_ff = 0.;
+  HotC hc;
+  hc.chi_bf = 0.;
+  hc.next_trans = rd<int>(q, L::next_trans);
+  hc.type = rd<int>(q, L::type);
+  hc.cellindex = rd<int>(q, L::cellindex);
+  hc.stage = pack_stage(ST_DONE, EV_NONE);
+  for (int k = 0; k < 4; k++) {
+    hc.rng[k] = (b == 16) ? rd<unsigned int>(rec, 4 * k) : 0U;
+    hc.ma[k] = -1;
+  }
+  hc.chi_mgi = -1;
+  hc.nscatterings = rd<int>(q, L::nscatterings);
+  EmRec em;
+  EmRec trueem;
+  for (int d = 0; d < 3; d++) {
+    em.pos[d] = rd<double>(q, L::em_pos + (8 * d));
+    trueem.pos[d] = rd<double>(q, L::trueem_pos + (8 * d));
+  }
+  em.time = rd<float>(q, L::em_time);
+  em.type = rd<int>(q, L::emissiontype);
+  trueem.time = rd<float>(q, L::trueem_time);
+  trueem.type = rd<int>(q, L::trueemissiontype);
+  s.ha[i] = ha;
+  s.hb[i] = hb;
+  s.hc[i] = hc;
+  s.em[i] = em;
+  s.trueem[i] = trueem;
   s.absorptiontype[i] = rd<int>(q, L::absorptiontype);
   s.absorptionfreq[i] = rd<double>(q, L::absorptionfreq);
-  s.stokes_q[i] = rd<double>(q, L::stokes_q);
-  s.stokes_u[i] = rd<double>(q, L::stokes_u);
-  s.trueemissiontype[i] = rd<int>(q, L::trueemissiontype);
-  s.trueem_pos_x[i] = rd<double>(q, L::trueem_pos);
-  s.trueem_pos_y[i] = rd<double>(q, L::trueem_pos + 8);
-  s.trueem_pos_z[i] = rd<double>(q, L::trueem_pos + 16);
-  s.trueem_time[i] = rd<float>(q, L::trueem_time);
-  s.type[i] = rd<int>(q, L::type);
-  s.cellindex[i] = rd<int>(q, L::cellindex);
   s.escape_type[i] = rd<int>(q, L::escape_type);
   s.escape_time[i] = rd<float>(q, L::escape_time);
   s.tdecay[i] = rd<double>(q, L::tdecay);
@@ -65,54 +82,42 @@ AHD void aos_to_soa_one(const Tables& T, const unsigned char* aos, const int str
   s.originated_from_particlenotgamma[i] = static_cast<int>(rd<unsigned char>(q, L::originated_from_particlenotgamma));
   s.pellet_decaytype[i] = rd<int>(q, L::pellet_decaytype);
   s.pellet_nucindex[i] = rd<int>(q, L::pellet_nucindex);
-  if (b == 16) {
-    s.rng0[i] = rd<unsigned int>(rec, 0);
-    s.rng1[i] = rd<unsigned int>(rec, 4);
-    s.rng2[i] = rd<unsigned int>(rec, 8);
-    s.rng3[i] = rd<unsigned int>(rec, 12);
-  } else {
-    s.rng0[i] = 0U;
-    s.rng1[i] = 0U;
-    s.rng2[i] = 0U;
-    s.rng3[i] = 0U;
-  }
 }
 
 AHD void soa_to_aos_one(const Tables& T, unsigned char* aos, const int stride, const long long i) {
   unsigned char* rec = aos + (i * stride);
   const int b = stride - AosLayout::size;
   unsigned char* q = rec + b;
-  const PacketSoA& s = T.pkt;
+  const PacketStore& s = T.pkt;
   using L = AosLayout;
-  wr<double>(q, L::prop_time, s.prop_time[i]);
-  wr<double>(q, L::pos, s.pos_x[i]);
-  wr<double>(q, L::pos + 8, s.pos_y[i]);
-  wr<double>(q, L::pos + 16, s.pos_z[i]);
-  wr<double>(q, L::dir, s.dir_x[i]);
-  wr<double>(q, L::dir + 8, s.dir_y[i]);
-  wr<double>(q, L::dir + 16, s.dir_z[i]);
-  wr<double>(q, L::nu_cmf, s.nu_cmf[i]);
-  wr<double>(q, L::e_cmf, s.e_cmf[i]);
-  wr<double>(q, L::nu_rf, s.nu_rf[i]);
-  wr<double>(q, L::e_rf, s.e_rf[i]);
-  wr<int>(q, L::next_trans, s.next_trans[i]);
-  wr<int>(q, L::nscatterings, s.nscatterings[i]);
-  wr<int>(q, L::emissiontype, s.emissiontype[i]);
-  wr<double>(q, L::em_pos, s.em_pos_x[i]);
-  wr<double>(q, L::em_pos + 8, s.em_pos_y[i]);
-  wr<double>(q, L::em_pos + 16, s.em_pos_z[i]);
-  wr<float>(q, L::em_time, s.em_time[i]);
+  const HotA ha = s.ha[i];
+  const HotB hb = s.hb[i];
+  const HotC hc = s.hc[i];
+  const EmRec em = s.em[i];
+  const EmRec trueem = s.trueem[i];
+  wr<double>(q, L::prop_time, ha.prop_time);
+  for (int d = 0; d < 3; d++) {
+    wr<double>(q, L::pos + (8 * d), ha.pos[d]);
+    wr<double>(q, L::dir + (8 * d), ha.dir[d]);
+    wr<double>(q, L::em_pos + (8 * d), em.pos[d]);
+    wr<double>(q, L::trueem_pos + (8 * d), trueem.pos[d]);
+  }
+  wr<double>(q, L::nu_cmf, ha.nu_cmf);
+  wr<double>(q, L::e_cmf, hb.e_cmf);
+  wr<double>(q, L::nu_rf, hb.nu_rf);
+  wr<double>(q, L::e_rf, hb.e_rf);
+  wr<int>(q, L::next_trans, hc.next_trans);
+  wr<int>(q, L::nscatterings, hc.nscatterings);
+  wr<int>(q, L::emissiontype, em.type);
+  wr<float>(q, L::em_time, em.time);
   wr<int>(q, L::absorptiontype, s.absorptiontype[i]);
   wr<double>(q, L::absorptionfreq, s.absorptionfreq[i]);
-  wr<double>(q, L::stokes_q, s.stokes_q[i]);
-  wr<double>(q, L::stokes_u, s.stokes_u[i]);
-  wr<int>(q, L::trueemissiontype, s.trueemissiontype[i]);
-  wr<double>(q, L::trueem_pos, s.trueem_pos_x[i]);
-  wr<double>(q, L::trueem_pos + 8, s.trueem_pos_y[i]);
-  wr<double>(q, L::trueem_pos + 16, s.trueem_pos_z[i]);
-  wr<float>(q, L::trueem_time, s.trueem_time[i]);
-  wr<int>(q, L::type, s.type[i]);
-  wr<int>(q, L::cellindex, s.cellindex[i]);
+  wr<double>(q, L::stokes_q, hb.stokes_q);
+  wr<double>(q, L::stokes_u, hb.stokes_u);
+  wr<int>(q, L::trueemissiontype, trueem.type);
+  wr<float>(q, L::trueem_time, trueem.time);
+  wr<int>(q, L::type, hc.type);
+  wr<int>(q, L::cellindex, hc.cellindex);
   wr<int>(q, L::escape_type, s.escape_type[i]);
   wr<float>(q, L::escape_time, s.escape_time[i]);
   wr<double>(q, L::tdecay, s.tdecay[i]);
@@ -122,19 +127,10 @@ AHD void soa_to_aos_one(const Tables& T, unsigned char* aos, const int stride, c
   wr<int>(q, L::pellet_decaytype, s.pellet_decaytype[i]);
   wr<int>(q, L::pellet_nucindex, s.pellet_nucindex[i]);
   if (b == 16 && T.rng_mode == RNG_XOSHIRO) {
-    wr<unsigned int>(rec, 0, s.rng0[i]);
-    wr<unsigned int>(rec, 4, s.rng1[i]);
-    wr<unsigned int>(rec, 8, s.rng2[i]);
-    wr<unsigned int>(rec, 12, s.rng3[i]);
+    for (int k = 0; k < 4; k++) {
+      wr<unsigned int>(rec, 4 * k, hc.rng[k]);
+    }
   }
-}
-
-// Philox streams restart every timestep: counter word 0 = draw index (reset to 0), key word 1 = packet number
-AHD void reset_philox_one(const Tables& T, const long long i) {
-  T.pkt.rng0[i] = 0U;
-  T.pkt.rng1[i] = static_cast<unsigned int>(T.pkt.number[i]);
-  T.pkt.rng2[i] = 0U;
-  T.pkt.rng3[i] = 0U;
 }
 
 // ---- per-cell table build steps, one work item each (see rates.h) ------------------------------------
@@ -148,19 +144,10 @@ namespace ab {
 enum : int { TESTK_BOUNDARY_DISTANCE = 0, TESTK_CLOSEST_TRANSITION = 1, TESTK_CHI_RPKT_CONT = 2 };
 
 // one element of artisb200_test_kernel()
-AHD void test_kernel_item(const Tables& T, const int which, const long long i, const long long tid, const double* in_f64,
-                          const int* in_i32, double* out_f64, int* out_i32) {
-  int cnt[CNT_COUNT];
-  long long diag[NDIAG];
-  double tss[NTSSCALARS];
-  long long pellet_decays = 0;
-  for (int k = 0; k < CNT_COUNT; k++) {
-    cnt[k] = 0;
-  }
-  for (int k = 0; k < NDIAG; k++) {
-    diag[k] = 0;
-  }
-  const Ctx c{T, 0, tid, cnt, diag, tss, &pellet_decays};
+AHD void test_kernel_item(const Tables& T, Accum& acc, const int which, const long long i, const long long tid,
+                          const double* in_f64, const int* in_i32, double* out_f64, int* out_i32) {
+  unsigned int hot[Ctx::NHOT] = {};
+  const Ctx c{T, tid, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};  // `tid` selects the scratch column
   if (which == TESTK_BOUNDARY_DISTANCE) {
     const double* rec = in_f64 + (i * 7);
     const BoundaryHit hit = boundary_distance(T, rec + 3, rec, rec[6], in_i32[i]);

@@ -99,6 +99,28 @@ inline uint64_t options_hash_value() {
   return h;
 }
 
+// how update_packets schedules the packets onto kernels (artisb200_set_option names in brackets)
+struct PropagateOptions {
+  int schedule{1};                 // [schedule] 0 = one whole-history kernel, 1 = wavefront of per-stage kernels
+  int rsteps_thin{1};              // [wf_rsteps_thin]  r-packet steps per visit to ST_RTHIN
+  int rsteps_thick{8};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
+  int masteps{1};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
+  long long tail_threshold{4096};  // [wf_tail] hand the last packets to the whole-history kernel below this many
+  int sync_every{8};               // [wf_sync_every] wavefront iterations enqueued between host checks
+  int stage_timing{0};             // [wf_stage_timing] bracket every stage kernel with CUDA events (profiling aid)
+};
+
+struct PropagateTimings {
+  double total_ms{0.};
+  double propagate_ms{0.};
+  double schedule_ms{0.};
+  double stage_ms[NSTAGES]{};  // only with stage_timing
+  double tail_ms{0.};
+  long long tail_packets{0};
+  long long iterations{0};
+  long long launches{0};
+};
+
 struct ArrayRec {
   void* dptr{nullptr};
   char dtype{0};
@@ -133,11 +155,9 @@ class Engine {
   // options
   int rank{0};
   int nranks{1};
-  long long sort_packets{0};
-
-  double last_total_ms{0.};
-  double last_propagate_ms{0.};
-  double last_schedule_ms{0.};
+  PropagateOptions popt;
+  PropagateTimings last;
+  int64_t scratch_capacity{0};
 
   int fail(const std::string& msg) {
     err = msg;
@@ -252,8 +272,23 @@ class Engine {
       T.seed = static_cast<unsigned long long>(value);
     } else if (name == "max_steps_per_launch") {
       T.max_steps_per_launch = value;
-    } else if (name == "sort_packets") {
-      sort_packets = value;
+    } else if (name == "schedule") {
+      if (value != 0 && value != 1) {
+        return fail("option schedule: 0 (whole-history kernel) or 1 (wavefront)");
+      }
+      popt.schedule = static_cast<int>(value);
+    } else if (name == "wf_rsteps_thin") {
+      popt.rsteps_thin = static_cast<int>(value < 1 ? 1 : value);
+    } else if (name == "wf_rsteps_thick") {
+      popt.rsteps_thick = static_cast<int>(value < 1 ? 1 : value);
+    } else if (name == "wf_masteps") {
+      popt.masteps = static_cast<int>(value < 0 ? 0 : value);
+    } else if (name == "wf_tail") {
+      popt.tail_threshold = value;
+    } else if (name == "wf_sync_every") {
+      popt.sync_every = static_cast<int>(value < 1 ? 1 : value);
+    } else if (name == "wf_stage_timing") {
+      popt.stage_timing = static_cast<int>(value);
     } else if (name == "rank") {
       rank = static_cast<int>(value);
     } else if (name == "nranks") {
@@ -496,19 +531,32 @@ class Engine {
 
   int ensure_packet_capacity(const int64_t n, const int stride) {
     if (n > packet_capacity) {
-      PacketSoA& s = T.pkt;
+      PacketStore& s = T.pkt;
 #define X(type, name)                                                 \
   if (s.name != nullptr) {                                            \
     be.free(s.name);                                                  \
   }                                                                   \
   s.name = static_cast<type*>(be.alloc(n * static_cast<int64_t>(sizeof(type)))); \
   if (s.name == nullptr) {                                            \
-    return fail("packet SoA allocation failed: " + be.last_error());  \
+    return fail("packet storage allocation failed: " + be.last_error());  \
   }
-      AB_PACKET_FIELDS(X)
+      AB_PACKET_ARRAYS(X)
 #undef X
       packet_capacity = n;
     }
+    // the per-packet, per-ground-continuum part of the continuum-opacity cache
+    const int64_t ng = T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1;
+    if (scratch_capacity < packet_capacity * ng) {
+      if (T.scratch_groundcont != nullptr) {
+        be.free(T.scratch_groundcont);
+      }
+      T.scratch_groundcont = static_cast<double*>(be.alloc(packet_capacity * ng * 8));
+      if (T.scratch_groundcont == nullptr) {
+        return fail("continuum-opacity cache allocation failed: " + be.last_error());
+      }
+      scratch_capacity = packet_capacity * ng;
+    }
+    T.scratch_stride = packet_capacity;
     const int64_t need = n * stride;
     if (need > aos_staging_bytes) {
       if (aos_staging != nullptr) {
@@ -565,7 +613,7 @@ class Engine {
     if (npackets <= 0) {
       return fail("update_packets: no packets uploaded");
     }
-    if (!be.propagate(T, npackets, sort_packets != 0, &last_total_ms, &last_propagate_ms, &last_schedule_ms)) {
+    if (!be.propagate(T, npackets, popt, &last)) {
       return fail("update_packets: propagation failed: " + be.last_error());
     }
     return 0;
@@ -627,13 +675,13 @@ class Engine {
       }
       soa_save.clear();
 #define X(type, name) soa_save.push_back(be.alloc(npackets * static_cast<int64_t>(sizeof(type))));
-      AB_PACKET_FIELDS(X)
+      AB_PACKET_ARRAYS(X)
 #undef X
       soa_save_count = npackets;
     }
     size_t k = 0;
 #define X(type, name) be.d2d(soa_save[k++], T.pkt.name, npackets * static_cast<int64_t>(sizeof(type)));
-    AB_PACKET_FIELDS(X)
+    AB_PACKET_ARRAYS(X)
 #undef X
     return 0;
   }
@@ -644,7 +692,7 @@ class Engine {
     }
     size_t k = 0;
 #define X(type, name) be.d2d(T.pkt.name, soa_save[k++], npackets * static_cast<int64_t>(sizeof(type)));
-    AB_PACKET_FIELDS(X)
+    AB_PACKET_ARRAYS(X)
 #undef X
     return 0;
   }

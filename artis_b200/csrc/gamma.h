@@ -144,7 +144,7 @@ AHD void update_gamma_dep(const Pkt& p, const Ctx& c, const int cell, const doub
   const double doppler_sq = pow2(doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time));
   const double heating_cont = get_chi_cmf_loss_weighted(c.T, cell, p.nu_cmf) * p.e_rf * dist * doppler_sq;
   atomic_add(&c.T.est_dep_gamma[cell], heating_cont);
-  c.work(DIAG_ESTIMATOR_ADDS);
+  c.work<DIAG_ESTIMATOR_ADDS>();
 }
 
 AHD double thomson_angle(Rng& rng) {  // gammapkt.cc:284-294
@@ -215,7 +215,7 @@ AHD void compton_scatter(Pkt& p, const Ctx& c) {  // gammapkt.cc:346-413
       p.type = TYPE_NTLEPTON_DEPOSITED;
     }
     c.T.pkt.absorptiontype[c.ip] = ABSTYPE_GAMMA_COMPTON;
-    c.count(CNT_NT_STAT_FROM_GAMMA);
+    c.count<CNT_NT_STAT_FROM_GAMMA>();
   }
 }
 
@@ -242,7 +242,7 @@ AHD void pair_production(Pkt& p, const Ctx& c) {  // gammapkt.cc:618-652
       p.type = TYPE_NTLEPTON_DEPOSITED;
     }
     c.T.pkt.absorptiontype[c.ip] = ABSTYPE_GAMMA_PAIRPRODUCTION;
-    c.count(CNT_NT_STAT_FROM_GAMMA);
+    c.count<CNT_NT_STAT_FROM_GAMMA>();
   } else {
     p.nu_cmf = 0.511 * MEV / H;
     emit_gamma_isotropic(p);
@@ -252,7 +252,7 @@ AHD void pair_production(Pkt& p, const Ctx& c) {  // gammapkt.cc:618-652
 // one gamma-packet step (gammapkt.cc:655-751)
 AHD void transport_gamma(Pkt& p, const Ctx& c, const double t2) {
   const Tables& T = c.T;
-  c.work(DIAG_GAMMA_STEPS);
+  c.work<DIAG_GAMMA_STEPS>();
   const double tau_next = -log(static_cast<double>(p.rng.uniform_pos()));
   const BoundaryHit hit = boundary_distance(T, p.dir, p.pos, p.prop_time, p.cellindex);
   const double boundarydist = hit.distance;
@@ -291,7 +291,7 @@ AHD void transport_gamma(Pkt& p, const Ctx& c, const double t2) {
       update_gamma_dep(p, c, cell, edist);
     }
     move_pkt_withtime(p, edist / 2.);
-    c.work(DIAG_GAMMA_EVENTS);
+    c.work<DIAG_GAMMA_EVENTS>();
     const double chi_rnd = p.rng.uniform() * chi_tot;
     if (chi_compton > chi_rnd) {
       compton_scatter(p, c);
@@ -302,7 +302,7 @@ AHD void transport_gamma(Pkt& p, const Ctx& c, const double t2) {
         p.type = TYPE_NTLEPTON_DEPOSITED;
       }
       T.pkt.absorptiontype[c.ip] = ABSTYPE_GAMMA_PHOTOELECTRIC;
-      c.count(CNT_NT_STAT_FROM_GAMMA);
+      c.count<CNT_NT_STAT_FROM_GAMMA>();
     } else {
       pair_production(p, c);
     }
@@ -316,7 +316,7 @@ AHD void do_gamma(Pkt& p, const Ctx& c, const double t2) {
   transport_gamma(p, c, t2);
   if (p.type != TYPE_GAMMA && p.type != TYPE_ESCAPE) {
     if constexpr (opt::PARTICLE_THERMALISATION_SCHEME != opt::PTS_TIMEDEPENDENTWITHGAMMAPRODUCTS) {
-      c.tss[TS_GAMMA_DEP_DISCRETE] += p.e_cmf;
+      c.add_ts(TS_GAMMA_DEP_DISCRETE, p.e_cmf);
     }
   }
 }

@@ -345,12 +345,12 @@ AHD void change_cell_or_escape(Pkt& p, const Ctx& c, const int next_cellindex) {
       snap_pos_to_cell(c.T, p.pos, p.prop_time, next_cellindex);
     }
     p.cellindex = next_cellindex;
-    c.count(CNT_CELLCROSSINGS);
+    c.count<CNT_CELLCROSSINGS>();
   } else {
     c.T.pkt.escape_type[c.ip] = p.type;
     c.T.pkt.escape_time[c.ip] = static_cast<float>(p.prop_time);
     p.type = TYPE_ESCAPE;
-    c.count(CNT_PKTESCAPES);
+    c.count<CNT_PKTESCAPES>();
   }
 }
 

@@ -15,12 +15,12 @@ constexpr float kpktdiffusion_timestep_fraction = 0.001F;  // kpkt.cc:51
 
 // thermal emission bookkeeping shared by the k-packet emission channels (kpkt.cc:412-421, 504-513, 532-538)
 AHD void mark_thermal_emission(Pkt& p, const Ctx& c, const int emissiontype) {
-  const PacketSoA& s = c.T.pkt;
+  const PacketStore& s = c.T.pkt;
   p.next_trans = -1;
-  s.emissiontype[c.ip] = emissiontype;
-  s.trueemissiontype[c.ip] = emissiontype;
+  s.em[c.ip].type = emissiontype;
+  s.trueem[c.ip].type = emissiontype;
   set_trueem_here(p, c);
-  s.nscatterings[c.ip] = 0;
+  p.nscatterings = 0;
 }
 
 // kpkt.cc:399-422 (thick cells: Planck re-emission)
@@ -29,8 +29,8 @@ AHD void do_kpkt_blackbody(Pkt& p, const Ctx& c) {
   const int cell = T.propcell_nonemptymgi[p.cellindex];
   p.nu_cmf = sample_planck_montecarlo(T.Te[cell], p.rng);
   emit_rpkt(p, c);
-  c.count(CNT_K_STAT_TO_R_BB);
-  c.count(CNT_INTERACTIONS);
+  c.count<CNT_K_STAT_TO_R_BB>();
+  c.count<CNT_INTERACTIONS>();
   mark_thermal_emission(p, c, EMTYPE_FREEFREE);
 }
 
@@ -51,8 +51,8 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
     return;
   }
 
-  c.count(CNT_INTERACTIONS);
-  c.work(DIAG_K_STEPS);
+  c.count<CNT_INTERACTIONS>();
+  c.work<DIAG_K_STEPS>();
 
   const int cell = T.propcell_nonemptymgi[p.cellindex];
   const double* ion_cooling = T.ion_cooling_contribs + (static_cast<long long>(cell) * T.nions);
@@ -77,7 +77,7 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
   if (rndcoolingtype == COOLING_FREEFREE) {
     p.nu_cmf = -KB * T_e / H * log(static_cast<double>(p.rng.uniform_pos()));
     emit_rpkt(p, c);
-    c.count(CNT_K_STAT_TO_R_FF);
+    c.count<CNT_K_STAT_TO_R_FF>();
     mark_thermal_emission(p, c, EMTYPE_FREEFREE);
   } else if (rndcoolingtype == COOLING_FREEBOUND) {
     const int lowerion = ion;
@@ -85,7 +85,7 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
     const int phixstargetindex = T.cooling_phixstargetindex[i];
     p.nu_cmf = select_continuum_nu(T, element, lowerion, lowerlevel, phixstargetindex, T_e, p.rng);
     emit_rpkt(p, c);
-    c.count(CNT_K_STAT_TO_R_FB);
+    c.count<CNT_K_STAT_TO_R_FB>();
     mark_thermal_emission(p, c, emtype_continuum(T, uniquelevel(T, element, lowerion, lowerlevel), phixstargetindex));
   } else if (rndcoolingtype == COOLING_COLLEXC) {
     const float clumpednne_ = T.clumpfactor[cell] * T.nne[cell];
@@ -113,17 +113,17 @@ AHD void do_kpkt(Pkt& p, const Ctx& c, const double t2) {
         break;
       }
     }
-    c.count(CNT_MA_STAT_ACTIVATION_COLLEXC);
-    c.count(CNT_K_STAT_TO_MA_COLLEXC);
-    T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
+    c.count<CNT_MA_STAT_ACTIVATION_COLLEXC>();
+    c.count<CNT_K_STAT_TO_MA_COLLEXC>();
+    T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;
     set_trueem_pos_nan(c);
     activate_macroatom(p, {element, ion, upper, -99});
   } else {  // COOLING_COLLION
     const int upperion = ion + 1;
     const int upper = phixsupperlevel(T, uniquelevel(T, element, ion, T.cooling_level[i]), T.cooling_phixstargetindex[i]);
-    c.count(CNT_MA_STAT_ACTIVATION_COLLION);
-    c.count(CNT_K_STAT_TO_MA_COLLION);
-    T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
+    c.count<CNT_MA_STAT_ACTIVATION_COLLION>();
+    c.count<CNT_K_STAT_TO_MA_COLLION>();
+    T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;
     set_trueem_pos_nan(c);
     activate_macroatom(p, {element, upperion, upper, -99});
   }

@@ -11,27 +11,53 @@
 
 namespace ab {
 
-// first index in [0, n) whose value is > target (std::upper_bound); counts probe loads for the roofline
+// First index in [0, n) whose value is > target (std::upper_bound over a non-decreasing array; sn3d.h:85-92).
+// The tables searched here are the per-cell cumulative transition rates: gigabytes in HBM, visited at random, so
+// every probe of a binary search is a dependent DRAM access. This search issues 7 independent probes per round
+// (8-way split) and finishes with one round over the last <= 8 elements: 2 rounds instead of 7 dependent loads
+// for a 70-entry row, and the same index as the binary search for any sorted input. The work counter keeps counting
+// the probes of the binary search (the compulsory traffic of the roofline model).
 AHD int index_upperbound(const double* a, const int n, const double target, const Ctx& c) {
   int lo = 0;
   int len = n;
   int probes = 0;
-  while (len > 0) {
-    const int half = len >> 1;
+  for (int m = n; m > 0; m >>= 1) {
     probes++;
-    if (!(target < a[lo + half])) {
-      lo += half + 1;
-      len -= half + 1;
-    } else {
-      len = half;
+  }
+  c.work<DIAG_BINSEARCH_STEPS>(probes);
+  while (len > 8) {
+    const int step = (len + 7) >> 3;
+    int npassed = 0;  // pivots that are <= target (the pivots are sorted, so these are the first npassed)
+    int nvalid = 0;
+#pragma unroll
+    for (int k = 1; k <= 7; k++) {
+      const int pos = (k * step) - 1;
+      if (pos < len) {
+        nvalid++;
+        npassed += (!(target < a[lo + pos])) ? 1 : 0;
+      }
+    }
+    lo += npassed * step;
+    // the answer is after the last passed pivot and not after the first failed one
+    len = (npassed < nvalid) ? (step - 1) : (len - (npassed * step));
+  }
+  int count = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (k < len) {
+      count += (!(target < a[lo + k])) ? 1 : 0;
     }
   }
-  c.work(DIAG_BINSEARCH_STEPS, probes);
-  return lo;
+  return lo + count;
 }
 
-AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
+// Take up to `max_steps` transitions (<= 0: walk to deactivation) of the activation recorded in p.ma.
+// The walk ends with p.ma_pending == 0 and either a k-packet, or an r-packet whose re-emission is left pending
+// (EV_EMIT_MA, run by finish_ma_emission); otherwise p.ma holds the level reached and the walk continues in the
+// packet's next visit to the macro-atom stage.
+AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
   const Tables& T = c.T;
+  const MacroAtomState mastate = p.ma;
   const int cell = T.propcell_nonemptymgi[p.cellindex];
   const auto T_e = T.Te[cell];
   const auto clumpednne_ = T.clumpfactor[cell] * T.nne[cell];
@@ -45,7 +71,13 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
   const double* cellmatrans = T.cell_matrans + (static_cast<long long>(cell) * T.matrans_total);
 
   bool end_packet = false;
+  int nsteps = 0;
   while (!end_packet) {
+    if (max_steps > 0 && nsteps >= max_steps) {
+      p.ma = {element, ion, level, activatingline};
+      return;
+    }
+    nsteps++;
     const int ustart = levelstart(T, element, ion);
     const int ulev = ustart + level;
     const double epsilon_current = epsilon(T, ulev);
@@ -68,8 +100,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
     }
     selected_action = (selected_action < MA_ACTION_COUNT - 1) ? selected_action : MA_ACTION_COUNT - 1;
 
-    c.count(CNT_INTERACTIONS);
-    c.work(DIAG_MA_STEPS);
+    c.count<CNT_INTERACTIONS>();
+    c.work<DIAG_MA_STEPS>();
 
     const int ndowntrans = T.level_ndowntrans[ulev];
     const double* transblock = cellmatrans + T.level_matransblock_start[ulev];
@@ -82,31 +114,36 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
         const int alltrans_startdown = T.level_alltrans_startdown[ulev];
         const int lineindex = T.trans_lineindex[alltrans_startdown + downtransindex];
         if (lineindex == activatingline) {
-          c.count(CNT_RESONANCESCATTERINGS);
+          c.count<CNT_RESONANCESCATTERINGS>();
         }
         const int ulevlower = ustart + T.trans_targetlevelindex[alltrans_startdown + downtransindex];
         const double epsilon_trans = epsilon_current - epsilon(T, ulevlower);
         const double oldnucmf = p.nu_cmf;
         p.nu_cmf = epsilon_trans / H;
         if (activatingline >= 0) {
-          c.count((oldnucmf < p.nu_cmf) ? CNT_UPSCATTER : CNT_DOWNSCATTER);
+          if (oldnucmf < p.nu_cmf) {
+            c.count<CNT_UPSCATTER>();
+          } else {
+            c.count<CNT_DOWNSCATTER>();
+          }
         }
-        c.count(CNT_MA_STAT_DEACTIVATION_BB);
-        emit_rpkt(p, c);
+        c.count<CNT_MA_STAT_DEACTIVATION_BB>();
+        p.type = TYPE_RPKT;
+        p.ev_pending = EV_EMIT_MA;
         p.next_trans = lineindex + 1;
-        T.pkt.emissiontype[c.ip] = lineindex;
-        T.pkt.nscatterings[c.ip] = 0;
+        T.pkt.em[c.ip].type = lineindex;
+        p.nscatterings = 0;
         end_packet = true;
         break;
       }
 
       case MA_ACTION_COLDEEXC: {
-        c.count(CNT_MA_STAT_DEACTIVATION_COLLDEEXC);
+        c.count<CNT_MA_STAT_DEACTIVATION_COLLDEEXC>();
         p.type = TYPE_KPKT;
         end_packet = true;
         if constexpr (!opt::DIRECT_COL_HEAT) {
           atomic_add(&T.est_colheating[cell], p.e_cmf);
-          c.work(DIAG_ESTIMATOR_ADDS);
+          c.work<DIAG_ESTIMATOR_ADDS>();
         }
         break;
       }
@@ -153,11 +190,12 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
         }
         const int lowerion = ion - 1;
         p.nu_cmf = select_continuum_nu(T, element, lowerion, lowerionlevel, selected_phixstargetindex, T_e, p.rng);
-        c.count(CNT_MA_STAT_DEACTIVATION_FB);
-        emit_rpkt(p, c);
+        c.count<CNT_MA_STAT_DEACTIVATION_FB>();
+        p.type = TYPE_RPKT;
+        p.ev_pending = EV_EMIT_MA;
         p.next_trans = -1;
-        T.pkt.emissiontype[c.ip] = emtype_continuum(T, lowerionstart + lowerionlevel, selected_phixstargetindex);
-        T.pkt.nscatterings[c.ip] = 0;
+        T.pkt.em[c.ip].type = emtype_continuum(T, lowerionstart + lowerionlevel, selected_phixstargetindex);
+        p.nscatterings = 0;
         level = lowerionlevel;
         ion -= 1;
         end_packet = true;
@@ -165,18 +203,18 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
       }
 
       case MA_ACTION_COLRECOMB: {
-        c.count(CNT_MA_STAT_DEACTIVATION_COLLRECOMB);
+        c.count<CNT_MA_STAT_DEACTIVATION_COLLRECOMB>();
         p.type = TYPE_KPKT;
         end_packet = true;
         if constexpr (!opt::DIRECT_COL_HEAT) {
           atomic_add(&T.est_colheating[cell], p.e_cmf);
-          c.work(DIAG_ESTIMATOR_ADDS);
+          c.work<DIAG_ESTIMATOR_ADDS>();
         }
         break;
       }
 
       case MA_ACTION_INTERNALDOWNLOWER: {
-        c.count(CNT_MA_STAT_INTERNALDOWNLOWER);
+        c.count<CNT_MA_STAT_INTERNALDOWNLOWER>();
         const double targetrate = p.rng.uniform() * levelrates[MA_ACTION_INTERNALDOWNLOWER];
         double rate = 0.;
         const int nlevels = nlevels_ionising(T, element, ion - 1);
@@ -215,7 +253,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
 
       case MA_ACTION_INTERNALUPHIGHER: {
         // macroatom.cc:298-322
-        c.count(CNT_MA_STAT_INTERNALUPHIGHER);
+        c.count<CNT_MA_STAT_INTERNALUPHIGHER>();
         const double targetrate = p.rng.uniform() * levelrates[MA_ACTION_INTERNALUPHIGHER];
         double rate = 0.;
         const int nphixstargets = T.level_nphixstargets[ulev];
@@ -241,20 +279,27 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const MacroAtomState& mastate) {
       default: {  // MA_ACTION_INTERNALUPHIGHERNT: nt_random_upperion without Spencer-Fano gives ion + 1
         ion = ion + 1;
         level = 0;
-        c.count(CNT_MA_STAT_INTERNALUPHIGHERNT);
+        c.count<CNT_MA_STAT_INTERNALUPHIGHERNT>();
         break;
       }
     }
   }
 
-  if (p.type == TYPE_RPKT) {
-    // macroatom.cc:579-590
-    if (T.pkt.trueemissiontype[c.ip] == EMTYPE_NOTSET) {
-      T.pkt.trueemissiontype[c.ip] = T.pkt.emissiontype[c.ip];
-      set_trueem_here(p, c);
-    }
-  } else {
-    T.pkt.trueemissiontype[c.ip] = EMTYPE_NOTSET;
+  p.ma_pending = 0;
+  if (p.type != TYPE_RPKT) {
+    T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;  // macroatom.cc:588-590
+  }
+}
+
+// the r-packet emission a radiative deactivation left pending: emit_rpkt (macroatom.cc:237, 282) and the
+// true-emission bookkeeping that follows the walk (macroatom.cc:579-587)
+AHD void finish_ma_emission(Pkt& p, const Ctx& c) {
+  const Tables& T = c.T;
+  p.ev_pending = EV_NONE;
+  emit_rpkt(p, c);
+  if (T.pkt.trueem[c.ip].type == EMTYPE_NOTSET) {
+    T.pkt.trueem[c.ip].type = T.pkt.em[c.ip].type;
+    set_trueem_here(p, c);
   }
 }
 

@@ -32,16 +32,21 @@ struct Pkt {
   int next_trans;
   int type;
   int cellindex;
+  int nscatterings;
   Rng rng;
   // A macro-atom activation is recorded here and run by the caller right after the activating step
   // (do_macroatom runs to deactivation, so this never outlives the step: reference packet.h:52-54, TYPE_MA).
   // Deferring it lets the propagation kernel run all of a warp's macro-atom walks together, converged.
   MacroAtomState ma;
   int ma_pending;
-  int ev_pending;  // EV_NONE, or an r-packet event whose handling was deferred by do_rpkt_step<true>
+  // A radiative macro-atom deactivation leaves the re-emission of the r-packet (new direction, rest-frame
+  // quantities, emission bookkeeping: emit_rpkt + macroatom.cc:579-590) pending here; it is run at the start of
+  // the packet's next r-packet visit, where whole warps have one to do, instead of by the few lanes of the
+  // macro-atom kernel whose walk has just ended. The packet's random numbers are drawn in the same order either way.
+  int ev_pending;
 };
 
-enum : int { EV_NONE = 0, EV_EMIT = 1, EV_CONTINUUM = 2 };
+enum : int { EV_NONE = 0, EV_EMIT_MA = 1 };
 
 AHD void activate_macroatom(Pkt& p, const MacroAtomState& state) {
   p.ma = state;
@@ -49,7 +54,7 @@ AHD void activate_macroatom(Pkt& p, const MacroAtomState& state) {
 }
 
 // continuum opacity of the current r-packet (reference rpkt.h:68-99 ContinuumOpacity). The per-ground-continuum
-// contributions live in the per-thread scratch column (Tables::scratch_groundcont).
+// contributions live in the packet's scratch column (Tables::scratch_groundcont).
 struct ChiCont {
   double nu;
   double chi_escatter;
@@ -59,100 +64,215 @@ struct ChiCont {
   AHD double total() const { return chi_escatter + chi_boundfree + chi_freefree_heat; }
 };
 
-// per-thread context: tables, this packet's SoA index, thread-private accumulators
+// per-thread context: tables, this packet's SoA index, and the accumulators of the running kernel.
+// On the device cnt/diag/tss/pellet_decays point into the thread block's SHARED memory and are updated with
+// shared-memory atomics (a few per step); each block flushes them with one global atomic per non-zero entry
+// when the kernel ends. Keeping them out of registers matters: 34 + 16 + 10 thread-private accumulators cost the
+// first version of the propagation kernel a 408-byte stack frame and ~60 registers.
 struct Ctx {
   const Tables& T;
-  long long ip;        // packet index in the SoA arrays
-  long long tid;       // thread slot (selects the scratch column)
-  int* cnt;            // [CNT_COUNT] thread-private event counters, flushed once per launch
-  long long* diag;     // [NDIAG] thread-private work counters
-  double* tss;         // [NTSSCALARS] thread-private timestep scalars
-  long long* pellet_decays;
+  long long ip;        // packet index in the SoA arrays (also selects the packet's ground-continuum scratch column)
+  unsigned int* cnt;   // [CNT_COUNT] event counters
+  unsigned int* diag;  // [NDIAG] work counters
+  double* tss;         // [NTSSCALARS] timestep scalars
+  unsigned int* pellet_decays;
+  unsigned int* hot;   // [NHOT] thread-private copies of the counters that are bumped every step (registers)
 
-  AHD void count(const int which) const { cnt[which]++; }
-  AHD void work(const int which, const long long n = 1) const { diag[which] += n; }
-  AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(i * T.scratch_stride) + tid]; }
+  // The counters bumped on every step live in the thread's registers (all indices are compile-time constants)
+  // and are added to the block's accumulators once, when the kernel ends; the rare ones go straight to the block's
+  // accumulators. A stage kernel only pays for the counters its own code touches.
+  static constexpr int NHOT = 11;
+  AHD static constexpr int hot_slot_cnt(const int which) {
+    return (which == CNT_INTERACTIONS) ? 7 : (which == CNT_ELECTRON_SCATTERINGS) ? 8 : (which == CNT_MA_STAT_ACTIVATION_BB) ? 9
+         : (which == CNT_CELLCROSSINGS) ? 10 : -1;
+  }
+  AHD static constexpr int hot_slot_diag(const int which) { return (which <= DIAG_MA_STEPS) ? which : -1; }
+
+  template <int WHICH>
+  AHD void count() const {
+    if constexpr (hot_slot_cnt(WHICH) >= 0) {
+      hot[hot_slot_cnt(WHICH)] += 1U;
+    } else {
+      bump(&cnt[WHICH], 1U);
+    }
+  }
+  template <int WHICH>
+  AHD void work(const long long n = 1) const {
+    if constexpr (hot_slot_diag(WHICH) >= 0) {
+      hot[hot_slot_diag(WHICH)] += static_cast<unsigned int>(n);
+    } else {
+      bump(&diag[WHICH], static_cast<unsigned int>(n));
+    }
+  }
+  AHD void add_ts(const int which, const double v) const {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&tss[which], v);
+#else
+    tss[which] += v;
+#endif
+  }
+  AHD void pellet_decay() const { bump(pellet_decays, 1U); }
+  AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(i * T.scratch_stride) + ip]; }
+
+  // add the thread-private counters to the block's accumulators (end of kernel) and clear them
+  AHD void flush_hot() const {
+#pragma unroll
+    for (int k = 0; k < NHOT; k++) {
+      if (hot[k] != 0U) {
+        unsigned int* dst = (k <= DIAG_MA_STEPS) ? &diag[k] : &cnt[(k == 7) ? CNT_INTERACTIONS : (k == 8) ? CNT_ELECTRON_SCATTERINGS
+                                                                : (k == 9) ? CNT_MA_STAT_ACTIVATION_BB : CNT_CELLCROSSINGS];
+        bump(dst, hot[k]);
+        hot[k] = 0U;
+      }
+    }
+  }
+
+ private:
+  AHD static void bump(unsigned int* addr, const unsigned int n) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(addr, n);
+#else
+    *addr += n;
+#endif
+  }
 };
 
-AHD void load_pkt(Pkt& p, const Tables& T, const long long ip) {
-  const PacketSoA& s = T.pkt;
-  p.prop_time = s.prop_time[ip];
-  p.pos[0] = s.pos_x[ip];
-  p.pos[1] = s.pos_y[ip];
-  p.pos[2] = s.pos_z[ip];
-  p.dir[0] = s.dir_x[ip];
-  p.dir[1] = s.dir_y[ip];
-  p.dir[2] = s.dir_z[ip];
-  p.nu_cmf = s.nu_cmf[ip];
-  p.e_cmf = s.e_cmf[ip];
-  p.nu_rf = s.nu_rf[ip];
-  p.e_rf = s.e_rf[ip];
-  p.stokes_q = s.stokes_q[ip];
-  p.stokes_u = s.stokes_u[ip];
-  p.next_trans = s.next_trans[ip];
-  p.type = s.type[ip];
-  p.cellindex = s.cellindex[ip];
-  p.ma_pending = 0;
-  p.ev_pending = EV_NONE;
+// block-local accumulators behind a Ctx (shared memory in kernels, a plain struct in the host test build)
+struct Accum {
+  unsigned int cnt[CNT_COUNT];
+  unsigned int diag[NDIAG];
+  double tss[NTSSCALARS];
+  unsigned int pellet_decays;
+};
+
+// stages a packet can wait in between kernels (HotC::stage)
+enum : int { ST_DONE = -1, ST_OTHER = 0, ST_RTHIN = 1, ST_RTHICK = 2, ST_MA = 3, NSTAGES = 4, ST_ANY = 99 };
+
+AHD int pack_stage(const int stage, const int ev_pending) { return (stage & 0xff) | (ev_pending << 8); }
+AHD int stored_stage(const HotC& hc) { return static_cast<int>(static_cast<signed char>(hc.stage & 0xff)); }
+
+// Bring a packet into registers. STAGE names what the caller is going to do with it: the macro-atom stage moves
+// one 64-byte record (plus nu_cmf and e_cmf, which a deactivation reads), everything else moves all three.
+template <int STAGE = ST_ANY>
+AHD void load_pkt(Pkt& p, ChiCont& chi, const Tables& T, const long long ip) {
+  const HotC hc = T.pkt.hc[ip];
+  p.next_trans = hc.next_trans;
+  p.type = hc.type;
+  p.cellindex = hc.cellindex;
+  p.nscatterings = hc.nscatterings;
+  const int stage = static_cast<int>(static_cast<signed char>(hc.stage & 0xff));  // low byte: ST_* (ST_DONE = -1)
+  p.ev_pending = hc.stage >> 8;
+  p.ma_pending = (stage == ST_MA) ? 1 : 0;
+  p.ma = {hc.ma[0], hc.ma[1], hc.ma[2], hc.ma[3]};
   p.rng.have_block = 0;
   p.rng.mode = T.rng_mode;
-  p.rng.s0 = s.rng0[ip];
-  p.rng.s1 = s.rng1[ip];
-  p.rng.s2 = s.rng2[ip];
-  p.rng.s3 = s.rng3[ip];
+  p.rng.s0 = hc.rng[0];
+  p.rng.s1 = hc.rng[1];
+  p.rng.s2 = hc.rng[2];
+  p.rng.s3 = hc.rng[3];
   p.rng.key0 = static_cast<unsigned int>(T.seed);
   p.rng.ctr1 = static_cast<unsigned int>(T.nts);
   p.rng.ctr2 = static_cast<unsigned int>(T.seed >> 32U);
+  chi.chi_boundfree = hc.chi_bf;
+  chi.nonemptymgi = hc.chi_mgi;
+  if constexpr (STAGE == ST_MA) {
+    p.prop_time = T.pkt.ha[ip].prop_time;  // stage_of() asks whether a k-packet left by the walk still has time
+    p.nu_cmf = T.pkt.ha[ip].nu_cmf;
+    p.e_cmf = T.pkt.hb[ip].e_cmf;
+  } else {
+    const HotA ha = T.pkt.ha[ip];
+    const HotB hb = T.pkt.hb[ip];
+    p.prop_time = ha.prop_time;
+    p.pos[0] = ha.pos[0];
+    p.pos[1] = ha.pos[1];
+    p.pos[2] = ha.pos[2];
+    p.dir[0] = ha.dir[0];
+    p.dir[1] = ha.dir[1];
+    p.dir[2] = ha.dir[2];
+    p.nu_cmf = ha.nu_cmf;
+    p.e_cmf = hb.e_cmf;
+    p.nu_rf = hb.nu_rf;
+    p.e_rf = hb.e_rf;
+    p.stokes_q = hb.stokes_q;
+    p.stokes_u = hb.stokes_u;
+    chi.nu = hb.chi_nu;
+    chi.chi_escatter = hb.chi_escatter;
+    chi.chi_freefree_heat = hb.chi_ff;
+  }
 }
 
-AHD void store_pkt(const Pkt& p, const Tables& T, const long long ip) {
-  const PacketSoA& s = T.pkt;
-  s.prop_time[ip] = p.prop_time;
-  s.pos_x[ip] = p.pos[0];
-  s.pos_y[ip] = p.pos[1];
-  s.pos_z[ip] = p.pos[2];
-  s.dir_x[ip] = p.dir[0];
-  s.dir_y[ip] = p.dir[1];
-  s.dir_z[ip] = p.dir[2];
-  s.nu_cmf[ip] = p.nu_cmf;
-  s.e_cmf[ip] = p.e_cmf;
-  s.nu_rf[ip] = p.nu_rf;
-  s.e_rf[ip] = p.e_rf;
-  s.stokes_q[ip] = p.stokes_q;
-  s.stokes_u[ip] = p.stokes_u;
-  s.next_trans[ip] = p.next_trans;
-  s.type[ip] = p.type;
-  s.cellindex[ip] = p.cellindex;
-  s.rng0[ip] = p.rng.s0;
-  s.rng1[ip] = p.rng.s1;
-  s.rng2[ip] = p.rng.s2;
-  s.rng3[ip] = p.rng.s3;
+// `stage`: where the packet waits next (ST_*); a recorded macro-atom activation is saved with ST_MA
+template <int STAGE = ST_ANY>
+AHD void store_pkt(const Pkt& p, const ChiCont& chi, const Tables& T, const long long ip, const int stage) {
+  HotC hc;
+  hc.next_trans = p.next_trans;
+  hc.type = p.type;
+  hc.cellindex = p.cellindex;
+  hc.stage = pack_stage(stage, p.ev_pending);
+  hc.nscatterings = p.nscatterings;
+  hc.rng[0] = p.rng.s0;
+  hc.rng[1] = p.rng.s1;
+  hc.rng[2] = p.rng.s2;
+  hc.rng[3] = p.rng.s3;
+  hc.ma[0] = p.ma.element;
+  hc.ma[1] = p.ma.ion;
+  hc.ma[2] = p.ma.level;
+  hc.ma[3] = p.ma.activatingline;
+  hc.chi_bf = chi.chi_boundfree;
+  hc.chi_mgi = chi.nonemptymgi;
+  T.pkt.hc[ip] = hc;
+  if constexpr (STAGE == ST_MA) {
+    if (p.ev_pending != EV_NONE) {
+      T.pkt.ha[ip].nu_cmf = p.nu_cmf;  // frequency of the r-packet a radiative deactivation emits
+    }
+  } else {
+    HotA ha;
+    ha.prop_time = p.prop_time;
+    ha.pos[0] = p.pos[0];
+    ha.pos[1] = p.pos[1];
+    ha.pos[2] = p.pos[2];
+    ha.dir[0] = p.dir[0];
+    ha.dir[1] = p.dir[1];
+    ha.dir[2] = p.dir[2];
+    ha.nu_cmf = p.nu_cmf;
+    T.pkt.ha[ip] = ha;
+    HotB hb;
+    hb.e_cmf = p.e_cmf;
+    hb.nu_rf = p.nu_rf;
+    hb.e_rf = p.e_rf;
+    hb.stokes_q = p.stokes_q;
+    hb.stokes_u = p.stokes_u;
+    hb.chi_nu = chi.nu;
+    hb.chi_escatter = chi.chi_escatter;
+    hb.chi_ff = chi.chi_freefree_heat;
+    T.pkt.hb[ip] = hb;
+  }
 }
 
 // cold-field writes (straight to global memory)
 AHD void set_em_here(const Pkt& p, const Ctx& c) {
-  const PacketSoA& s = c.T.pkt;
-  s.em_pos_x[c.ip] = p.pos[0];
-  s.em_pos_y[c.ip] = p.pos[1];
-  s.em_pos_z[c.ip] = p.pos[2];
-  s.em_time[c.ip] = static_cast<float>(p.prop_time);
+  EmRec& e = c.T.pkt.em[c.ip];
+  e.pos[0] = p.pos[0];
+  e.pos[1] = p.pos[1];
+  e.pos[2] = p.pos[2];
+  e.time = static_cast<float>(p.prop_time);
 }
 
 // trueem_* = em_* (which set_em_here has just set to the current position and time)
 AHD void set_trueem_here(const Pkt& p, const Ctx& c) {
-  const PacketSoA& s = c.T.pkt;
-  s.trueem_pos_x[c.ip] = p.pos[0];
-  s.trueem_pos_y[c.ip] = p.pos[1];
-  s.trueem_pos_z[c.ip] = p.pos[2];
-  s.trueem_time[c.ip] = static_cast<float>(p.prop_time);
+  EmRec& e = c.T.pkt.trueem[c.ip];
+  e.pos[0] = p.pos[0];
+  e.pos[1] = p.pos[1];
+  e.pos[2] = p.pos[2];
+  e.time = static_cast<float>(p.prop_time);
 }
 
 AHD void set_trueem_pos_nan(const Ctx& c) {
-  const PacketSoA& s = c.T.pkt;
+  EmRec& e = c.T.pkt.trueem[c.ip];
   const double nan = NAN;
-  s.trueem_pos_x[c.ip] = nan;
-  s.trueem_pos_y[c.ip] = nan;
-  s.trueem_pos_z[c.ip] = nan;
+  e.pos[0] = nan;
+  e.pos[1] = nan;
+  e.pos[2] = nan;
 }
 
 // Byte offsets of the reference's AoS Packet (measured with the reference headers).

@@ -31,7 +31,7 @@ AHD void update_pellet(Pkt& p, const Ctx& c, const double t2) {
     p.pos[2] = p.pos[2] * f;
     p.prop_time = t2;
   } else if (tdecay > ts) {
-    (*c.pellet_decays)++;
+    c.pellet_decay();
     p.prop_time = tdecay;
     const double f = tdecay / ts;
     p.pos[0] = p.pos[0] * f;
@@ -41,21 +41,21 @@ AHD void update_pellet(Pkt& p, const Ctx& c, const double t2) {
       const int decaytype = T.pkt.pellet_decaytype[c.ip];
       if (decaytype == DECAYTYPE_BETAPLUS) {
         p.type = TYPE_NONTHERMAL_PREDEPOSIT_BETAPLUS;
-        c.tss[TS_POSITRON_EMISSION] += p.e_cmf;
+        c.add_ts(TS_POSITRON_EMISSION, p.e_cmf);
       } else if (decaytype == DECAYTYPE_BETAMINUS) {
         p.type = TYPE_NONTHERMAL_PREDEPOSIT_BETAMINUS;
-        c.tss[TS_ELECTRON_EMISSION] += p.e_cmf;
+        c.add_ts(TS_ELECTRON_EMISSION, p.e_cmf);
       } else if (decaytype == DECAYTYPE_ALPHA) {
-        c.tss[TS_ALPHA_EMISSION] += p.e_cmf;
+        c.add_ts(TS_ALPHA_EMISSION, p.e_cmf);
         p.type = TYPE_NONTHERMAL_PREDEPOSIT_ALPHA;
       } else {  // DECAYTYPE_SPONTFISSION
-        c.tss[TS_SPFISSION_DEP_DISCRETE] += p.e_cmf;
+        c.add_ts(TS_SPFISSION_DEP_DISCRETE, p.e_cmf);
         p.type = TYPE_NTALPHA_FISPROD_DEPOSITED;
       }
-      T.pkt.em_time[c.ip] = static_cast<float>(p.prop_time);
+      T.pkt.em[c.ip].time = static_cast<float>(p.prop_time);
       T.pkt.absorptiontype[c.ip] = ABSTYPE_PELLET_PARTICLEDECAY;
     } else {
-      c.tss[TS_GAMMA_EMISSION] += p.e_cmf;
+      c.add_ts(TS_GAMMA_EMISSION, p.e_cmf);
       pellet_gamma_decay(p, c);
     }
   } else if ((tdecay > 0) && (T.nts == 0)) {
@@ -63,7 +63,7 @@ AHD void update_pellet(Pkt& p, const Ctx& c, const double t2) {
     p.e_cmf *= tdecay / T.tmin;
     p.type = TYPE_PRE_KPKT;
     T.pkt.absorptiontype[c.ip] = ABSTYPE_PELLET_BEFORESIMSTART;
-    c.count(CNT_K_STAT_FROM_EARLIERDECAY);
+    c.count<CNT_K_STAT_FROM_EARLIERDECAY>();
     p.prop_time = T.tmin;
   } else {
     // unreachable for valid input (reference: __builtin_unreachable); park the packet so the loop terminates
@@ -127,34 +127,34 @@ AHD void do_nonthermal_predeposit(Pkt& p, const Ctx& c, const double ts_end) {
     if (priortype == TYPE_NONTHERMAL_PREDEPOSIT_BETAMINUS) {
       atomic_add(&T.est_dep_electron[cell], e_cmf_deposited);
       if (p.type == deposit_type) {
-        c.tss[TS_ELECTRON_DEP_DISCRETE] += p.e_cmf;
+        c.add_ts(TS_ELECTRON_DEP_DISCRETE, p.e_cmf);
       }
     } else if (priortype == TYPE_NONTHERMAL_PREDEPOSIT_BETAPLUS) {
       atomic_add(&T.est_dep_positron[cell], e_cmf_deposited);
       if (p.type == deposit_type) {
-        c.tss[TS_POSITRON_DEP_DISCRETE] += p.e_cmf;
+        c.add_ts(TS_POSITRON_DEP_DISCRETE, p.e_cmf);
       }
     } else if (priortype == TYPE_NONTHERMAL_PREDEPOSIT_ALPHA) {
       atomic_add(&T.est_dep_alpha[cell], e_cmf_deposited);
       if (p.type == deposit_type) {
-        c.tss[TS_ALPHA_DEP_DISCRETE] += p.e_cmf;
+        c.add_ts(TS_ALPHA_DEP_DISCRETE, p.e_cmf);
       }
     }
-    c.work(DIAG_ESTIMATOR_ADDS);
+    c.work<DIAG_ESTIMATOR_ADDS>();
   } else if constexpr (scheme == opt::PTS_TIMEDEPENDENTWITHGAMMAPRODUCTS) {
     atomic_add(&T.est_dep_gamma[cell], e_cmf_deposited);
     if (p.type == TYPE_NTLEPTON_DEPOSITED) {
-      c.tss[TS_GAMMA_DEP_DISCRETE] += p.e_cmf;
+      c.add_ts(TS_GAMMA_DEP_DISCRETE, p.e_cmf);
     }
-    c.work(DIAG_ESTIMATOR_ADDS);
+    c.work<DIAG_ESTIMATOR_ADDS>();
   }
 }
 
 // nonthermal.cc:2520-2613 without the Spencer-Fano channels (NT_SOLVE_SPENCERFANO == false): all to heating
 AHD void do_nt_deposit(Pkt& p, const Ctx& c) {
-  c.tss[TS_NT_ENERGY_DEPOSITED] += p.e_cmf;
+  c.add_ts(TS_NT_ENERGY_DEPOSITED, p.e_cmf);
   p.type = TYPE_KPKT;
-  c.count(CNT_NT_STAT_TO_KPKT);
+  c.count<CNT_NT_STAT_TO_KPKT>();
 }
 
 // update_packets.cc:257-317
@@ -167,7 +167,7 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
       do_gamma(p, c, t2);
       break;
     case TYPE_RPKT:
-      do_rpkt_step<false>(p, c, t2, chi);
+      do_rpkt_step<0>(p, c, t2, chi);
       break;
     case TYPE_NONTHERMAL_PREDEPOSIT_ALPHA:
     case TYPE_NONTHERMAL_PREDEPOSIT_BETAMINUS:
@@ -197,11 +197,13 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   }
 }
 
-// run a macro-atom activation recorded by the step that has just been taken (macroatom.cc:360-596)
+// run a macro-atom activation recorded by the step that has just been taken to its end (macroatom.cc:360-596)
 AHD void finish_macroatom(Pkt& p, const Ctx& c) {
   if (p.ma_pending != 0) {
-    p.ma_pending = 0;
-    do_macroatom(p, c, p.ma);
+    do_macroatom(p, c, 0);
+  }
+  if (p.ev_pending == EV_EMIT_MA) {
+    finish_ma_emission(p, c);
   }
 }
 
@@ -213,14 +215,85 @@ AHD void init_chicont(ChiCont& chi) {
   chi.nonemptymgi = -1;
 }
 
-// Advance one packet: up to `max_steps` do_packet calls (<= 0: until the end of the timestep).
-// Returns true if the packet still needs propagating this timestep. (Serial form, used by the host test build;
-// the CUDA kernel runs the same two calls per iteration with warp convergence points in between.)
-AHD bool propagate_packet(Pkt& p, const Ctx& c, const long long max_steps) {
+// ---- stages ---------------------------------------------------------------------------------------------------
+// Between kernels every active packet waits in exactly one stage (packet.h ST_*):
+//   ST_OTHER   pellets, gamma packets, k-packets, non-thermal particles: one do_packet call
+//   ST_RTHIN   r-packet in a cell with the detailed treatment: continuum opacity + Sobolev line walk
+//   ST_RTHICK  r-packet in a grey (thick) or empty cell: boundary distance + grey scattering only
+//   ST_MA      r-packet with a recorded macro-atom activation: walk to deactivation
+AHD int stage_of(const Pkt& p, const Tables& T) {
+  if (p.ma_pending != 0) {
+    return ST_MA;
+  }
+  if (p.ev_pending == EV_NONE && !packetprop_update_required(p, T.ts_end)) {
+    return ST_DONE;
+  }
+  if (p.type != TYPE_RPKT) {
+    return ST_OTHER;
+  }
+  const int cell = T.propcell_nonemptymgi[p.cellindex];
+  return (cell >= 0 && T.thick[cell] != CELL_THICK) ? ST_RTHIN : ST_RTHICK;
+}
+
+// start of update_packets: the stage each stored packet starts in (no activation or emission pending: none
+// survives a timestep), continuum-opacity cache invalid (it is valid for one timestep, reference rpkt.cc:1023)
+AHD void reset_work_one(const Tables& T, const long long i) {
+  HotC hc = T.pkt.hc[i];
+  int stage = ST_DONE;
+  if (hc.type != TYPE_ESCAPE && T.pkt.ha[i].prop_time < T.ts_end) {
+    if (hc.type != TYPE_RPKT) {
+      stage = ST_OTHER;
+    } else {
+      const int cell = T.propcell_nonemptymgi[hc.cellindex];
+      stage = (cell >= 0 && T.thick[cell] != CELL_THICK) ? ST_RTHIN : ST_RTHICK;
+    }
+  }
+  hc.stage = pack_stage(stage, EV_NONE);
+  hc.chi_bf = 0.;
+  hc.chi_mgi = -1;
+  if (T.rng_mode == RNG_PHILOX) {
+    // Philox streams restart every timestep: counter word 0 = draw index (reset to 0), key word 1 = packet number
+    hc.rng[0] = 0U;
+    hc.rng[1] = static_cast<unsigned int>(T.pkt.number[i]);
+    hc.rng[2] = 0U;
+    hc.rng[3] = 0U;
+  }
+  T.pkt.hc[i] = hc;
+  T.pkt.hb[i].chi_nu = -1.;
+  T.pkt.hb[i].chi_escatter = 0.;
+  T.pkt.hb[i].chi_ff = 0.;
+}
+
+// Run one visit of the packet to `stage`. r-packet stages take up to `max_steps` transport steps while the
+// packet stays in the same stage (thick-cell random walks are many cheap steps); the macro-atom stage takes up to
+// `max_steps` transitions.
+template <int STAGE>
+AHD void run_stage(Pkt& p, const Ctx& c, ChiCont& chi, const int max_steps) {
   const double ts_end = c.T.ts_end;
-  ChiCont chi;
-  init_chicont(chi);
+  if constexpr (STAGE == ST_OTHER) {
+    do_packet(p, c, ts_end, chi);
+  } else if constexpr (STAGE == ST_MA) {
+    do_macroatom(p, c, max_steps);
+  } else {
+    if (p.ev_pending == EV_EMIT_MA) {
+      finish_ma_emission(p, c);
+    }
+    for (int k = 0; k < max_steps && packetprop_update_required(p, ts_end); k++) {
+      do_rpkt_step<(STAGE == ST_RTHIN) ? 1 : 2>(p, c, ts_end, chi);
+      if (stage_of(p, c.T) != STAGE) {
+        break;
+      }
+    }
+  }
+}
+
+// Advance one packet serially (host test build; the tail of the CUDA wavefront uses the same order of calls):
+// up to `max_steps` do_packet calls (<= 0: until the end of the timestep). Returns true if the packet still needs
+// propagating this timestep.
+AHD bool propagate_packet(Pkt& p, const Ctx& c, ChiCont& chi, const long long max_steps) {
+  const double ts_end = c.T.ts_end;
   long long steps = 0;
+  finish_macroatom(p, c);  // an activation recorded by an earlier kernel
   while (packetprop_update_required(p, ts_end)) {
     if (max_steps > 0 && steps >= max_steps) {
       return true;

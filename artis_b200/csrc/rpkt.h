@@ -44,7 +44,7 @@ AHD int closest_transition(const Tables& T, const double nu_cmf, const int next_
       len = half;
     }
   }
-  c.work(DIAG_BINSEARCH_STEPS, probes);
+  c.work<DIAG_BINSEARCH_STEPS>(probes);
   return lo;
 }
 
@@ -113,7 +113,7 @@ AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const doubl
   const double* nu_edge_arr = T.cont_nu_edge;
   const int allcontend = upper_bound_idx(nu_edge_arr, T.nbfcontinua, nu);
   const int allcontbegin = lower_bound_idx(nu_edge_arr, allcontend, nu / T.last_phixs_nuovernuedge);
-  c.work(DIAG_BINSEARCH_STEPS, 2 * T.log2_nbf);
+  c.work<DIAG_BINSEARCH_STEPS>(2 * T.log2_nbf);
 
   const long long base = static_cast<long long>(cell) * T.nbfcontinua;
   const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
@@ -164,7 +164,7 @@ AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const doubl
   if constexpr (SELECT) {
     return static_cast<double>(allcontend - 1);
   }
-  c.work(DIAG_CONT_TERMS, nterms);
+  c.work<DIAG_CONT_TERMS>(nterms);
   return chi_bf_sum;
 }
 
@@ -181,7 +181,7 @@ AHD void calculate_chi_rpkt_cont(const Ctx& c, const double nu_cmf, ChiCont& chi
   chi.chi_boundfree = calculate_chi_bf_gammacontr<false>(c, cell, nu_cmf, 0.);
   chi.nonemptymgi = cell;
   chi.nu = nu_cmf;
-  c.work(DIAG_CONT_EVALS);
+  c.work<DIAG_CONT_EVALS>();
 }
 
 struct PossibleEvent {
@@ -209,7 +209,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
   while (true) {
     const int lineindex = closest_transition(T, nu_cmf, next_trans, c);
     if (lineindex < 0) {
-      c.work(DIAG_LINES_VISITED, nvisited);
+      c.work<DIAG_LINES_VISITED>(nvisited);
       const double tau_cont = chi_cont * (abort_dist - dist);
       if (tau_rnd - tau > tau_cont) {
         return {DBL_MAX_, next_trans, false};
@@ -224,7 +224,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
 
     if (tau_rnd - tau > tau_cont) {
       if (nu_trans < nu_cmf_abort) {
-        c.work(DIAG_LINES_VISITED, nvisited);
+        c.work<DIAG_LINES_VISITED>(nvisited);
         return {DBL_MAX_, next_trans - 1, false};
       }
       const double tau_line = get_tau_sobolev(T, cellpops, lineindex, prop_time);
@@ -233,7 +233,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
         const int ion = T.line_ionindex[lineindex];
         const int upper = T.line_upper[lineindex] - levelstart(T, element, ion);
         mastate = {element, ion, upper, lineindex};
-        c.work(DIAG_LINES_VISITED, nvisited);
+        c.work<DIAG_LINES_VISITED>(nvisited);
         return {dist + ldist, next_trans, true};
       }
       dist += ldist;
@@ -248,7 +248,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
         nu_cmf = p.nu_cmf + (dnu_on_dl * dist);
       }
     } else {
-      c.work(DIAG_LINES_VISITED, nvisited);
+      c.work<DIAG_LINES_VISITED>(nvisited);
       return {dist + ((tau_rnd - tau) / chi_cont), next_trans - 1, false};
     }
   }
@@ -262,13 +262,13 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
   if (distance_e_cmf != 0) {
     atomic_add(&T.est_J[cell], distance_e_cmf);
     atomic_add(&T.est_nuJ[cell], distance_e_cmf * nu_cmf);
-    c.work(DIAG_ESTIMATOR_ADDS, 2);
+    c.work<DIAG_ESTIMATOR_ADDS>(2);
   }
   if (thickcell) {
     return;
   }
   atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
-  c.work(DIAG_ESTIMATOR_ADDS, 1);
+  c.work<DIAG_ESTIMATOR_ADDS>(1);
 
   if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
     const int ng = T.nbfcontinua_ground;
@@ -285,7 +285,7 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
       if constexpr (opt::USE_ION_BFHEATING_ESTIMATORS) {
         atomic_add(&T.est_bfheating[ionestimindex], contr * distance_e_cmf * (1. - (nu_edge / nu_cmf)));
       }
-      c.work(DIAG_ESTIMATOR_ADDS, 2);
+      c.work<DIAG_ESTIMATOR_ADDS>(2);
     }
   }
 }
@@ -302,12 +302,12 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
 
   const double chi_rnd = p.rng.uniform() * chi_cont;
   if (chi_rnd < chi_escatter) {
-    T.pkt.nscatterings[c.ip]++;
-    c.count(CNT_ELECTRON_SCATTERINGS);
+    p.nscatterings++;
+    c.count<CNT_ELECTRON_SCATTERINGS>();
     electron_scatter_rpkt(p);
     set_em_here(p, c);
   } else if (chi_rnd < chi_escatter + chi_ff) {
-    c.count(CNT_K_STAT_FROM_FF);
+    c.count<CNT_K_STAT_FROM_FF>();
     p.type = TYPE_KPKT;
     T.pkt.absorptiontype[c.ip] = ABSTYPE_FREEFREE;
   } else {
@@ -322,10 +322,10 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
     const int level = T.cont_level[allcontindex];
     const int phixstargetindex = T.cont_phixstargetindex[allcontindex];
     if (p.rng.uniform() < nu_edge / nu) {
-      c.count(CNT_MA_STAT_ACTIVATION_BF);
+      c.count<CNT_MA_STAT_ACTIVATION_BF>();
       activate_macroatom(p, {element, ion + 1, phixsupperlevel(T, uniquelevel(T, element, ion, level), phixstargetindex), -99});
     } else {
-      c.count(CNT_K_STAT_FROM_BF);
+      c.count<CNT_K_STAT_FROM_BF>();
       p.type = TYPE_KPKT;
     }
   }
@@ -334,15 +334,14 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
 // One r-packet step (rpkt.cc:542-693). Returns true if the packet can keep going in this call: still an
 // r-packet and not at the end of the timestep. (The reference additionally returns to its scheduler on a
 // change of model cell, a CPU cell-cache artefact that the all-cells-resident device tables do not need.)
-// With DEFER_EVENTS the handling of a thick-cell scattering (emit_rpkt) and of a continuum event
-// (rpkt_event_continuum) is only recorded in p.ev_pending for the caller to run next; the packet's own random
-// number sequence is unchanged by this.
-template <bool DEFER_EVENTS = false>
+// CELLKIND tells the compiler what the caller already knows about the packet's cell, so that a stage kernel carries
+// only its own half of the code: 0 = anything, 1 = detailed treatment (ST_RTHIN), 2 = grey or empty (ST_RTHICK).
+template <int CELLKIND = 0>
 AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   const Tables& T = c.T;
   const int cell = T.propcell_nonemptymgi[p.cellindex];
   MacroAtomState pktmastate = {-1, -1, -1, -99};
-  c.work(DIAG_RPKT_STEPS);
+  c.work<DIAG_RPKT_STEPS>();
 
   const double tau_rnd = -log(static_cast<double>(p.rng.uniform_pos()));
 
@@ -360,11 +359,12 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
 
   double edist = -1;
   bool event_is_boundbound = true;
-  const bool thickcell = (cell >= 0) && (T.thick[cell] == CELL_THICK);
-  if (cell < 0) {
+  const bool thickcell = (CELLKIND != 1) && (cell >= 0) && (T.thick[cell] == CELL_THICK);
+  const bool greycell = (CELLKIND == 2) || thickcell;  // only used where cell >= 0
+  if ((CELLKIND != 1) && cell < 0) {
     edist = DBL_MAX_;
     p.next_trans = -1;
-  } else if (thickcell) {
+  } else if (greycell) {
     const double chi_grey = T.kappagrey[cell] * T.rho[cell] * doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
     edist = tau_rnd / chi_grey;
     p.next_trans = -1;
@@ -382,26 +382,18 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
 
   if ((edist < boundarydist) && (edist <= tdist)) {
     move_pkt_withtime(p, edist / 2.);
-    update_estimators(c, p.e_cmf, p.nu_cmf, edist, cell, chi, thickcell);
+    update_estimators(c, p.e_cmf, p.nu_cmf, edist, cell, chi, greycell);
     move_pkt_withtime(p, edist / 2.);
 
-    c.count(CNT_INTERACTIONS);
-    if (thickcell) {
-      T.pkt.nscatterings[c.ip]++;
-      c.count(CNT_ELECTRON_SCATTERINGS);
-      if constexpr (DEFER_EVENTS) {
-        p.ev_pending = EV_EMIT;
-      } else {
-        emit_rpkt(p, c);
-      }
+    c.count<CNT_INTERACTIONS>();
+    if (greycell) {
+      p.nscatterings++;
+      c.count<CNT_ELECTRON_SCATTERINGS>();
+      emit_rpkt(p, c);
     } else if (!event_is_boundbound) {
-      if constexpr (DEFER_EVENTS) {
-        p.ev_pending = EV_CONTINUUM;
-      } else {
-        rpkt_event_continuum(p, c, chi);
-      }
+      rpkt_event_continuum(p, c, chi);
     } else {
-      c.count(CNT_MA_STAT_ACTIVATION_BB);
+      c.count<CNT_MA_STAT_ACTIVATION_BB>();
       T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
       T.pkt.absorptionfreq[c.ip] = p.nu_rf;
       activate_macroatom(p, pktmastate);
@@ -412,7 +404,7 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   if ((boundarydist <= tdist) && (boundarydist <= edist)) {
     move_pkt_withtime(p, boundarydist / 2.);
     if (cell >= 0) {
-      update_estimators(c, p.e_cmf, p.nu_cmf, boundarydist, cell, chi, thickcell);
+      update_estimators(c, p.e_cmf, p.nu_cmf, boundarydist, cell, chi, greycell);
     }
     move_pkt_withtime(p, boundarydist / 2.);
     if (next_cellindex != p.cellindex) {
@@ -427,7 +419,7 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
   // end of timestep reached before a boundary or an interaction
   move_pkt_withtime(p, tdist / 2.);
   if (cell >= 0) {
-    update_estimators(c, p.e_cmf, p.nu_cmf, tdist, cell, chi, thickcell);
+    update_estimators(c, p.e_cmf, p.nu_cmf, tdist, cell, chi, greycell);
   }
   move_pkt_withtime(p, tdist / 2.);
   p.prop_time = t2;

@@ -168,52 +168,82 @@ enum : int {
   DIAG_PACKET_SEGMENTS = 11,
 };
 
-// SoA packet state (device resident across timesteps). Field set = reference Packet (packet.h:109-156).
+// Packet state in HBM (device resident across timesteps). Field set = reference Packet (packet.h:109-156) plus the
+// work state that has to survive between the kernels of one timestep.
+//
+// The fields every transport step reads and writes are packed into three 64-byte records per packet, one array
+// per record, so that a thread moves its packet with full-width 128-bit accesses to lines it owns instead of
+// gathering ~25 separate 8-byte values from as many 32-byte sectors (measured on the first wavefront version:
+// 2.2 kB of DRAM reads per 0.2 kB packet visit), and so that a stage touches only the lines it needs:
+//   HotA  kinematics                                   (r-packet, gamma, pellet stages)
+//   HotB  energies, rest-frame frequency, Stokes parameters and the cached continuum opacity
+//   HotC  type, cell, line-list position, stage, RNG state, pending macro-atom activation   (all stages; the
+//         macro-atom stage needs nothing else to take a step)
+// Emission bookkeeping (written at every emission) is one 32-byte record per packet for the last emission and one
+// for the true emission; the remaining cold fields are plain arrays indexed by packet.
+struct alignas(64) HotA {
+  double prop_time;
+  double pos[3];
+  double dir[3];
+  double nu_cmf;
+};
+
+struct alignas(64) HotB {
+  double e_cmf;
+  double nu_rf;
+  double e_rf;
+  double stokes_q;
+  double stokes_u;
+  // cached continuum opacity (reference rpkt.h:68-99 ContinuumOpacity; valid for one timestep, rpkt.cc:1023); its
+  // per-ground-continuum part is Tables::scratch_groundcont
+  double chi_nu;
+  double chi_escatter;
+  double chi_ff;
+};
+
+struct alignas(64) HotC {
+  double chi_bf;
+  int next_trans;
+  int type;
+  int cellindex;
+  int stage;            // ST_* the packet waits in between kernels, + 256 * (pending event EV_*)
+  unsigned int rng[4];  // xoshiro state, or philox (draw counter, packet number, -, -)
+  int ma[4];            // recorded macro-atom activation: element, ion, level, activating line (packet.h:96-105)
+  int chi_mgi;
+  int nscatterings;
+};
+
+struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_time/trueemissiontype
+  double pos[3];
+  float time;
+  int type;
+};
+
+static_assert(sizeof(HotA) == 64 && sizeof(HotB) == 64 && sizeof(HotC) == 64 && sizeof(EmRec) == 32, "record sizes");
+
+#define AB_PACKET_RECORDS(X) \
+  X(HotA, ha)                \
+  X(HotB, hb)                \
+  X(HotC, hc)                \
+  X(EmRec, em)               \
+  X(EmRec, trueem)
+
 #define AB_PACKET_FIELDS(X)   \
-  X(double, prop_time)        \
-  X(double, pos_x)            \
-  X(double, pos_y)            \
-  X(double, pos_z)            \
-  X(double, dir_x)            \
-  X(double, dir_y)            \
-  X(double, dir_z)            \
-  X(double, nu_cmf)           \
-  X(double, e_cmf)            \
-  X(double, nu_rf)            \
-  X(double, e_rf)             \
-  X(int, next_trans)          \
-  X(int, nscatterings)        \
-  X(int, emissiontype)        \
-  X(double, em_pos_x)         \
-  X(double, em_pos_y)         \
-  X(double, em_pos_z)         \
-  X(float, em_time)           \
   X(int, absorptiontype)      \
   X(double, absorptionfreq)   \
-  X(double, stokes_q)         \
-  X(double, stokes_u)         \
-  X(int, trueemissiontype)    \
-  X(double, trueem_pos_x)     \
-  X(double, trueem_pos_y)     \
-  X(double, trueem_pos_z)     \
-  X(float, trueem_time)       \
-  X(int, type)                \
-  X(int, cellindex)           \
   X(int, escape_type)         \
   X(float, escape_time)       \
   X(double, tdecay)           \
   X(int, number)              \
   X(int, originated_from_particlenotgamma) \
   X(int, pellet_decaytype)    \
-  X(int, pellet_nucindex)     \
-  X(unsigned int, rng0)       \
-  X(unsigned int, rng1)       \
-  X(unsigned int, rng2)       \
-  X(unsigned int, rng3)
+  X(int, pellet_nucindex)
 
-struct PacketSoA {
+#define AB_PACKET_ARRAYS(X) AB_PACKET_RECORDS(X) AB_PACKET_FIELDS(X)
+
+struct PacketStore {
 #define X(type, name) type* name;
-  AB_PACKET_FIELDS(X)
+  AB_PACKET_ARRAYS(X)
 #undef X
 };
 
@@ -227,7 +257,7 @@ struct Tables {
 #define X(type, name, pub) type* name;
   AB_OUTPUT_ARRAYS(X)
 #undef X
-  PacketSoA pkt;
+  PacketStore pkt;
 
   // sizes
   int ncoord[3];
@@ -266,7 +296,7 @@ struct Tables {
   unsigned long long seed;
   long long max_steps_per_launch;
 
-  // per-launch scratch: per-thread ground-continuum contributions [nbfcontinua_ground][nthreads]
+  // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
   double* scratch_groundcont;
   long long scratch_stride;
 };

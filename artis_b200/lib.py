@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path(preset):
-    return os.path.join(_HERE, "_build", f"libartis_b200_{preset}.so")
+    # ARTISB200_LIB_SUFFIX selects a side-by-side tuning build (see __graft_entry__.build_cuda); default: the product
+    return os.path.join(_HERE, "_build", f"libartis_b200_{preset}{os.environ.get('ARTISB200_LIB_SUFFIX', '')}.so")
 
 
 class ArtisB200Error(RuntimeError):
@@ -40,6 +41,9 @@ _SIGNATURES = {
     "artisb200_restore_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_estimator_device_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "artisb200_last_timing_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "artisb200_last_schedule_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                                      ctypes.POINTER(ctypes.c_int64)]),
     "artisb200_test_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
     "artisb200_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
@@ -161,6 +165,15 @@ class ArtisB200:
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         self.lib.artisb200_last_timing_ms(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         return a.value, b.value, c.value
+
+    def last_schedule_stats(self):
+        stage = (ctypes.c_double * 4)()
+        tail_ms = ctypes.c_double()
+        tail_n, iters, launches = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self.lib.artisb200_last_schedule_stats(self.ctx, stage, ctypes.byref(tail_ms), ctypes.byref(tail_n), ctypes.byref(iters),
+                                               ctypes.byref(launches))
+        return {"stage_ms": dict(zip(("other", "rpkt_thin", "rpkt_thick", "macroatom"), list(stage))), "tail_ms": tail_ms.value,
+                "tail_packets": tail_n.value, "iterations": iters.value, "launches": launches.value}
 
     def stream(self):
         return self.lib.artisb200_stream(self.ctx)

@@ -193,6 +193,10 @@ def run_ours(args):
     eng.set_option("rank", rank)
     eng.set_option("nranks", world)
     eng.set_option("max_steps_per_launch", int(os.environ.get("ARTISB200_MAXSTEPS", "0")))
+    # tuning aid: ARTISB200_OPTS="schedule=0,wf_tail=4096,..." (artisb200_set_option names)
+    user_opts = dict(kv.split("=") for kv in os.environ.get("ARTISB200_OPTS", "").split(",") if "=" in kv)
+    for name, value in user_opts.items():
+        eng.set_option(name, int(value))
     eng.set_arrays(static)
     eng.commit_static()
     eng.set_arrays(before)
@@ -255,6 +259,14 @@ def run_ours(args):
             diag_sum = est["diag"] if diag_sum is None else diag_sum + est["diag"]
             counters = est["counters"]
     clock_summary = clocks.summary()
+    sched_stats = eng.last_schedule_stats()
+
+    # one extra, untimed pass with every stage kernel bracketed by CUDA events: how the step splits over the kernels
+    eng.set_option("wf_stage_timing", 1)
+    device_step_timed()
+    stage_stats = eng.last_schedule_stats()
+    stage_total_ms = eng.last_timing_ms()[0]
+    eng.set_option("wf_stage_timing", 0)
 
     # end-to-end through the host-buffer call (the drop-in signature): H2D packets, propagate, D2H packets + estimators
     e2e_ms = []
@@ -302,10 +314,21 @@ def run_ours(args):
                        "interactions_per_step_per_gpu": n_int, "l2_policy": "inputs larger than L2 (packet SoA + per-cell tables > 126 MB)"},
             "e2e": {"value": n_int_total / (t_e2e * 1e-3), "unit": "interactions/s", "h2d_bytes_per_step": int(n * stride),
                     "d2h_bytes_per_step": int(n * stride + est_count * 8), "ms_per_step": t_e2e},
-            # per step: k_propagate launches + k_reset_philox + the 5 per-cell table-build kernels of begin_timestep
-            "gpu_launches": int(launches + 1 + 5),
+            # per step: the propagation launches (stage kernels, sort, resets) + the 5 per-cell table-build kernels
+            "gpu_launches": int(launches + 5),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_kind, "kernel": "k_propagate", "kernel_ms": t_prop, "algorithmic_bytes": int(b_alg)},
+                         "peak_source": peak_kind,
+                         "kernel": ("k_wf_stage<other|rpkt_thin|rpkt_thick|macroatom> (all propagation kernels of the step)"
+                                    if sched_stats["iterations"] > 0 else "k_propagate"),
+                         "kernel_ms": t_prop, "algorithmic_bytes": int(b_alg)},
+            "schedule": {"options": user_opts, "iterations": sched_stats["iterations"], "launches": sched_stats["launches"],
+                         "tail_packets": sched_stats["tail_packets"], "tail_ms": sched_stats["tail_ms"],
+                         "stage_timing_pass": {"total_ms": stage_total_ms, "stage_ms": stage_stats["stage_ms"],
+                                               "tail_ms": stage_stats["tail_ms"]}},
+            "event_counters": {k: int(counters[i]) for k, i in (("interactions", 26), ("electron_scatterings", 27), ("ma_activation_bb", 4),
+                                                                 ("ma_activation_bf", 5), ("ma_deactivation_bb", 9), ("k_from_ff", 19),
+                                                                 ("k_from_bf", 20), ("cellcrossings", 29), ("escapes", 33),
+                                                                 ("resonance_scatterings", 28))},
             "clocks": clock_summary,
             "work_counters": {k: int(diag_mean[i]) for i, k in enumerate(
                 ["rpkt_steps", "lines_visited", "cont_evals", "cont_terms", "binsearch_probes", "estimator_adds", "ma_steps",

@@ -118,8 +118,14 @@ int artisb200_set_array(artisb200_ctx* ctx, const char* name, char dtype, const 
 int artisb200_get_array(artisb200_ctx* ctx, const char* name, char dtype, void* host_out, int64_t count);
 int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name); /* -1 if unknown / unset */
 
-/* Runtime options: "rng_mode" (ARTISB200_RNG_*), "seed", "max_steps_per_launch" (0 = whole history in one
- * launch, the order-independent parity mode), "sort_packets" (0/1), "rank", "nranks". */
+/* Runtime options: "rng_mode" (ARTISB200_RNG_*), "seed", "rank", "nranks";
+ * "schedule": 1 (default) = wavefront: one kernel per packet stage (other | r-packet detailed | r-packet grey |
+ *   macro-atom) over cell-sorted index lists per iteration, 0 = one whole-history kernel (thread per packet);
+ *   packet results do not depend on the schedule (per-packet random number streams, per-packet opacity cache);
+ * "wf_rsteps_thin", "wf_rsteps_thick": r-packet steps per visit to the two r-packet stages;
+ * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
+ * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
+ * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep. */
 int artisb200_set_option(artisb200_ctx* ctx, const char* name, int64_t value);
 
 /* Validate that all required static tables are present and build derived static tables.
@@ -156,6 +162,12 @@ int artisb200_estimator_device_buffer(artisb200_ctx* ctx, void** device_ptr, int
 /* Device time [ms] of the last artisb200_update_packets measured with CUDA events on the library's stream,
  * split as total / propagation kernels / scheduling (sort, compaction). */
 int artisb200_last_timing_ms(artisb200_ctx* ctx, double* total_ms, double* propagate_ms, double* schedule_ms);
+/* Schedule statistics of the last artisb200_update_packets: device time per stage kernel family
+ * [other, r-packet detailed, r-packet grey, macro-atom] (only with option wf_stage_timing), the time and packet
+ * count of the whole-history tail, wavefront iterations and kernel launches. */
+#define ARTISB200_NSTAGES 4
+int artisb200_last_schedule_stats(artisb200_ctx* ctx, double stage_ms[ARTISB200_NSTAGES], double* tail_ms, int64_t* tail_packets,
+                                  int64_t* iterations, int64_t* launches);
 
 /* Element-wise evaluation of the deterministic device functions on caller-supplied inputs, used by the
  * parity tests (north_star: "boundary_distance, closest_transition indices, cell opacities ... must match

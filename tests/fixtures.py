@@ -39,10 +39,12 @@ def hostsim_library(preset):
     return out
 
 
-def make_engine(libpath, fx, rng="xoshiro", max_steps=0, device=0, seed=None):
+def make_engine(libpath, fx, rng="xoshiro", max_steps=0, device=0, seed=None, options=None):
     eng = ablib.ArtisB200(libpath=libpath, device=device)
     eng.set_option("rng_mode", 1 if rng == "xoshiro" else 0)
     eng.set_option("max_steps_per_launch", max_steps)
+    for name, value in (options or {}).items():
+        eng.set_option(name, value)
     if seed is not None:
         eng.set_option("seed", seed)
     eng.set_arrays(fx["static"])
@@ -52,9 +54,9 @@ def make_engine(libpath, fx, rng="xoshiro", max_steps=0, device=0, seed=None):
     return eng
 
 
-def run_fixture(libpath, fx, rng="xoshiro", max_steps=0, device=0, seed=None):
+def run_fixture(libpath, fx, rng="xoshiro", max_steps=0, device=0, seed=None, options=None):
     """replay the fixture's timestep through the C ABI -> (packets structured array, estimators, built tables, timing)"""
-    eng = make_engine(libpath, fx, rng, max_steps, device, seed)
+    eng = make_engine(libpath, fx, rng, max_steps, device, seed, options)
     before = fx["before"]
     n = int(before["packets.count"][0])
     stride = int(before["packets.stride"][0])

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "convert.h"
 #include "engine.h"
@@ -61,12 +62,16 @@ struct HostBackend {
   bool run_test_kernel(ab::Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,
                        double* out_f64, int* out_i32) {
     std::vector<double> scratch(static_cast<size_t>(T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1));
+    double* const saved = T.scratch_groundcont;
+    const long long saved_stride = T.scratch_stride;
     T.scratch_groundcont = scratch.data();
     T.scratch_stride = 1;
+    ab::Accum acc{};
     for (int64_t i = 0; i < n; i++) {
-      ab::test_kernel_item(T, which, i, 0, in_f64, in_i32, out_f64, out_i32);
+      ab::test_kernel_item(T, acc, which, i, 0, in_f64, in_i32, out_f64, out_i32);
     }
-    T.scratch_groundcont = nullptr;
+    T.scratch_groundcont = saved;
+    T.scratch_stride = saved_stride;
     return true;
   }
 
@@ -83,53 +88,119 @@ struct HostBackend {
     return true;
   }
 
-  bool propagate(ab::Tables& T, const int64_t n, bool /*sort*/, double* total_ms, double* prop_ms, double* sched_ms) {
+  // one visit of a packet to a stage, exactly as the stage kernels do it (stage-specific load/store included)
+  template <int STAGE>
+  static int visit(const ab::Tables& T, const ab::Ctx& c, const long long ip, const int max_steps) {
+    ab::Pkt p;
+    ab::ChiCont chi;
+    ab::load_pkt<STAGE>(p, chi, T, ip);
+    ab::run_stage<STAGE>(p, c, chi, max_steps);
+    const int dest = ab::stage_of(p, T);
+    ab::store_pkt<STAGE>(p, chi, T, ip, dest);
+    return dest;
+  }
+
+  // serial emulation of the two schedules of the CUDA backend (same stage functions, same order of calls)
+  unsigned int hot[ab::Ctx::NHOT] = {};
+
+  bool propagate(ab::Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<double> scratch(static_cast<size_t>(T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1));
-    T.scratch_groundcont = scratch.data();
-    T.scratch_stride = 1;
-    int cnt[ab::CNT_COUNT] = {};
-    long long diag[ab::NDIAG] = {};
-    double tss[ab::NTSSCALARS] = {};
-    long long pellet_decays = 0;
-    if (T.rng_mode == ab::RNG_PHILOX) {
-      for (int64_t i = 0; i < n; i++) {
-        ab::reset_philox_one(T, i);
-      }
+    *tm = ab::PropagateTimings{};
+    ab::Accum acc{};
+    for (int64_t i = 0; i < n; i++) {
+      ab::reset_work_one(T, i);
     }
+    if (o.schedule == 1) {
+      std::vector<int> lists[2][ab::NSTAGES];
+      for (int64_t i = 0; i < n; i++) {
+        const int st = ab::stored_stage(T.pkt.hc[i]);
+        if (st >= 0) {
+          lists[0][st].push_back(static_cast<int>(i));
+        }
+      }
+      int cur = 0;
+      auto run_list = [&](const int stage) {
+        // index loop: a stage may append to the macro-atom list of the running iteration
+        for (size_t k = 0; k < lists[cur][stage].size(); k++) {
+          const long long ip = lists[cur][stage][k];
+          const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+          int dest = ab::ST_DONE;
+          switch (stage) {
+            case ab::ST_OTHER: dest = visit<ab::ST_OTHER>(T, c, ip, 1); break;
+            case ab::ST_RTHIN: dest = visit<ab::ST_RTHIN>(T, c, ip, o.rsteps_thin); break;
+            case ab::ST_RTHICK: dest = visit<ab::ST_RTHICK>(T, c, ip, o.rsteps_thick); break;
+            default: dest = visit<ab::ST_MA>(T, c, ip, o.masteps); break;
+          }
+          c.flush_hot();
+          if (dest >= 0) {
+            lists[(dest == ab::ST_MA && stage != ab::ST_MA) ? cur : (cur ^ 1)][dest].push_back(static_cast<int>(ip));
+          }
+        }
+      };
+      while (true) {
+        size_t waiting = 0;
+        for (int s = 0; s < ab::NSTAGES; s++) {
+          waiting += lists[cur][s].size();
+        }
+        if (waiting == 0) {
+          break;
+        }
+        if (static_cast<long long>(waiting) <= o.tail_threshold && tm->iterations > 0) {
+          tm->tail_packets = static_cast<long long>(waiting);
+          run_history(T, n, acc, tm);
+          break;
+        }
+        run_list(ab::ST_OTHER);
+        run_list(ab::ST_RTHIN);
+        run_list(ab::ST_RTHICK);
+        run_list(ab::ST_MA);
+        for (int s = 0; s < ab::NSTAGES; s++) {
+          lists[cur][s].clear();
+        }
+        cur ^= 1;
+        tm->iterations++;
+        tm->launches += ab::NSTAGES + 1;
+      }
+    } else {
+      run_history(T, n, acc, tm);
+    }
+    for (int k = 0; k < ab::CNT_COUNT; k++) {
+      T.counters[k] += acc.cnt[k];
+    }
+    for (int k = 0; k < ab::NDIAG; k++) {
+      T.diag[k] += acc.diag[k];
+    }
+    T.diag[ab::DIAG_KERNEL_LAUNCHES] = tm->launches;
+    for (int k = 0; k < ab::NTSSCALARS; k++) {
+      T.ts_scalars[k] += acc.tss[k];
+    }
+    T.ts_pellet_decays[0] += acc.pellet_decays;
+    tm->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    tm->propagate_ms = tm->total_ms;
+    return true;
+  }
+
+  void run_history(ab::Tables& T, const int64_t n, ab::Accum& acc, ab::PropagateTimings* tm) {
     long long remaining = 1;
     while (remaining > 0) {
       remaining = 0;
-      diag[ab::DIAG_KERNEL_LAUNCHES]++;
+      tm->launches++;
       for (int64_t i = 0; i < n; i++) {
-        if (T.pkt.type[i] == ab::TYPE_ESCAPE || !(T.pkt.prop_time[i] < T.ts_end)) {
+        if (ab::stored_stage(T.pkt.hc[i]) < 0) {
           continue;
         }
         ab::Pkt p;
-        ab::load_pkt(p, T, i);
-        const ab::Ctx c{T, i, 0, cnt, diag, tss, &pellet_decays};
-        diag[ab::DIAG_PACKET_SEGMENTS]++;
-        if (ab::propagate_packet(p, c, T.max_steps_per_launch)) {
+        ab::ChiCont chi;
+        ab::load_pkt(p, chi, T, i);
+        const ab::Ctx c{T, i, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+        acc.diag[ab::DIAG_PACKET_SEGMENTS]++;
+        if (ab::propagate_packet(p, c, chi, T.max_steps_per_launch)) {
           remaining++;
         }
-        ab::store_pkt(p, T, i);
+        c.flush_hot();
+        ab::store_pkt(p, chi, T, i, ab::stage_of(p, T));
       }
     }
-    for (int k = 0; k < ab::CNT_COUNT; k++) {
-      T.counters[k] += cnt[k];
-    }
-    for (int k = 0; k < ab::NDIAG; k++) {
-      T.diag[k] += diag[k];
-    }
-    for (int k = 0; k < ab::NTSSCALARS; k++) {
-      T.ts_scalars[k] += tss[k];
-    }
-    T.ts_pellet_decays[0] += pellet_decays;
-    T.scratch_groundcont = nullptr;
-    *total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    *prop_ms = *total_ms;
-    *sched_ms = 0.;
-    return true;
   }
 };
 

@@ -52,10 +52,10 @@ def check_cell_tables(built, after):
     assert np.array_equal(built["built.cont_keepbits"], after["ref.cont_keepbits"]), "continuum keep-bitmaps differ"
 
 
-def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction=1.0, tol=1e-9, est_tol=1e-9):
+def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction=1.0, tol=1e-9, est_tol=1e-9, options=None):
     """replay the timestep with every packet continuing its own reference RNG stream: histories must coincide"""
     fx = fixtures.load_golden(config, nts)
-    pk, est, built, _ = fixtures.run_fixture(libpath, fx, rng="xoshiro", max_steps=max_steps)
+    pk, est, built, _ = fixtures.run_fixture(libpath, fx, rng="xoshiro", max_steps=max_steps, options=options)
     after = fx["after"]
     ref = fixtures.snap.packets_view(after)
     # Free-bound emissions sample their frequency from select_continuum_nu, which the reference integrates
@@ -71,7 +71,7 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
     fb = np.zeros(len(ref), dtype=bool)
     fb[:n_fb_events] = True
     n_fb = int(np.count_nonzero(fb))
-    if max_steps == 0:
+    if min_exact_fraction == 1.0:
         check_cell_tables(built, after)
         if n_fb == 0:
             assert int(est["counters"][fixtures.INTERACTIONS]) == int(after["counters"][fixtures.INTERACTIONS])

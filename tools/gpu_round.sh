@@ -1,0 +1,40 @@
+#!/bin/bash
+# One gpurun session: GPU parity tests, bench of the schedules, launch list and one full ncu capture.
+# usage (from the repo root on the GPU box): bash tools/gpu_round.sh <tag> [steps...]
+set -u
+TAG=${1:-r1}
+shift || true
+STEPS=${*:-"tests bench history launches full"}
+export ARTISB200_BENCH_CACHE=/tmp/bench_cache
+mkdir -p gpurun_out
+for step in $STEPS; do
+  case $step in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" ;;
+    bench)
+      timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" ;;
+    history)
+      ARTISB200_OPTS="schedule=0" timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_history.json 2> gpurun_out/${TAG}_bench_history.err; echo "history rc=$?" ;;
+    variants)
+      for v in "wf_tail=0" "wf_tail=65536" "wf_rsteps_thin=2" "wf_rsteps_thick=1" "wf_rsteps_thick=32"; do
+        ARTISB200_OPTS="$v" timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_${v}.json 2> gpurun_out/${TAG}_bench_${v}.err; echo "$v rc=$?"
+      done ;;
+    tune)
+      # TUNE="<lib suffix>:<options>;..." e.g. TUNE=":wf_masteps=1;_b6:wf_masteps=2"
+      IFS=';' read -ra CASES <<< "${TUNE:-:}"
+      for cs in "${CASES[@]}"; do
+        suf="${cs%%:*}"; opts="${cs#*:}"
+        name="${TAG}_tune${suf}_$(echo "$opts" | tr ',=' '__')"
+        ARTISB200_LIB_SUFFIX="$suf" ARTISB200_OPTS="$opts" timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${name}.json 2> gpurun_out/${name}.err; echo "tune [$suf] [$opts] rc=$?"
+      done ;;
+    launches)
+      ARTISB200_BENCH_NPACKETS=2000000 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv -c 600 \
+        --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu.json 2> gpurun_out/${TAG}_launches.err; echo "launches rc=$?" ;;
+    full)
+      # one early (large) launch of each stage kernel of a 1e6-packet step
+      ARTISB200_BENCH_NPACKETS=${FULL_NPACKETS:-2000000} ARTISB200_OPTS="${FULL_OPTS:-}" timeout 1500 ncu --set full --clock-control none --import-source on \
+        -k regex:k_wf_stage --launch-skip ${FULL_SKIP:-8} --launch-count ${FULL_COUNT:-4} -o gpurun_out/${TAG}_full -f \
+        python bench.py --steps 1 --warmup 0 --no-cpu-baseline > /dev/null 2> gpurun_out/${TAG}_full.err; echo "full rc=$?" ;;
+  esac
+done
+ls -la gpurun_out | tail -20
