@@ -235,7 +235,8 @@ constexpr int WF_BLOCK = ARTISB200_WF_BLOCK;
 
 template <int STAGE>
 __global__ void __launch_bounds__(WF_BLOCK, ARTISB200_WF_MINBLOCKS)
-    k_wf_stage(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int max_steps) {
+    k_wf_stage(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int next, const int next_ma,
+               const int max_steps) {
   __shared__ ab::Accum acc;
   accum_zero(acc);
   constexpr unsigned FULL = 0xffffffffU;
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(WF_BLOCK, ARTISB200_WF_MINBLOCKS)
     for (int s = 0; s < ab::NSTAGES; s++) {
       const unsigned m = __ballot_sync(FULL, dest == s);
       if (m != 0U) {
-        // macro-atom activations recorded by the other stages are run in the same iteration (the macro-atom kernel
-        // is launched last); walks it leaves unfinished continue in the next one
-        const int buf = (s == ab::ST_MA && STAGE != ab::ST_MA) ? cur : (cur ^ 1);
+        // `next`: lists of the next iteration. `next_ma`: where macro-atom work goes. Activations recorded by the
+        // other stages are run in the same iteration (the macro-atom kernels are launched last); a macro-atom
+        // kernel hands unfinished walks to the macro-atom kernel that follows it.
+        const int buf = (s == ab::ST_MA) ? next_ma : next;
         const int leader = __ffs(m) - 1;
         unsigned int pos = 0U;
         if (lane == static_cast<unsigned int>(leader)) {
@@ -315,6 +317,14 @@ __global__ void k_wf_seed(const WfQueues q, const int* __restrict__ order, const
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     q.status[0] = static_cast<unsigned long long>(total);
     q.status[1] = 0ULL;
+  }
+}
+
+// between two macro-atom kernels of one iteration: the consumed list becomes the (empty) output list of the next
+__global__ void k_wf_ma_swap(const WfQueues q, const int consumed) {
+  if (threadIdx.x == 0) {
+    q.count[(consumed * ab::NSTAGES) + ab::ST_MA] = 0U;
+    q.cursor[ab::ST_MA] = 0U;
   }
 }
 
@@ -695,7 +705,8 @@ struct CudaBackend {
   }
 
   template <int STAGE>
-  void launch_stage(const Tables& T, const WfQueues& q, const int cur, const int max_steps, const unsigned int grid_limit) {
+  void launch_stage(const Tables& T, const WfQueues& q, const int cur, const int next, const int next_ma, const int max_steps,
+                    const unsigned int grid_limit) {
     if (stage_blocks_per_sm[STAGE] == 0) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stage_blocks_per_sm[STAGE], k_wf_stage<STAGE>, WF_BLOCK, 0);
       stage_blocks_per_sm[STAGE] = (stage_blocks_per_sm[STAGE] < 1) ? 1 : stage_blocks_per_sm[STAGE];
@@ -703,7 +714,7 @@ struct CudaBackend {
     // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
     unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
     grid = (grid > grid_limit) ? grid_limit : grid;
-    k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, stream>>>(T, q, cur, max_steps);
+    k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, stream>>>(T, q, cur, next, next_ma, max_steps);
   }
 
   bool run_wavefront(const Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
@@ -723,6 +734,7 @@ struct CudaBackend {
     tm->launches += 4;
 
     const bool timing = (o.stage_timing != 0);
+    const int ma_rounds = (o.ma_rounds < 1) ? 1 : (o.ma_rounds | 1);  // odd: the last round writes to the next iteration's list
     const int sync_every = (o.sync_every < 1) ? 1 : o.sync_every;
     if (timing && stage_events.size() < static_cast<size_t>(sync_every) * (ab::NSTAGES + 1)) {
       const size_t want = static_cast<size_t>(sync_every) * (ab::NSTAGES + 1);
@@ -740,19 +752,30 @@ struct CudaBackend {
       const unsigned int grid_limit = static_cast<unsigned int>((bound < 1ULL) ? 1ULL : ((bound > 1048576ULL) ? 1048576ULL : bound));
       for (int it = 0; it < sync_every; it++) {
         cudaEvent_t* ev = timing ? &stage_events[static_cast<size_t>(it) * (ab::NSTAGES + 1)] : nullptr;
+        const int next = cur ^ 1;
         if (timing) { cudaEventRecord(ev[0], stream); }
-        launch_stage<ab::ST_OTHER>(T, q, cur, 1, grid_limit);
+        launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit);
         if (timing) { cudaEventRecord(ev[1], stream); }
-        launch_stage<ab::ST_RTHIN>(T, q, cur, o.rsteps_thin, grid_limit);
+        launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit);
         if (timing) { cudaEventRecord(ev[2], stream); }
-        launch_stage<ab::ST_RTHICK>(T, q, cur, o.rsteps_thick, grid_limit);
+        launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit);
         if (timing) { cudaEventRecord(ev[3], stream); }
-        launch_stage<ab::ST_MA>(T, q, cur, o.masteps, grid_limit);
+        // macro-atom walks: `ma_rounds` kernels of at most `masteps` transitions each, ping-ponging between the two
+        // macro-atom lists; what is still walking after the last round continues in the next iteration
+        int ma_in = cur;
+        for (int r = 0; r < ma_rounds; r++) {
+          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, (r + 1 < ma_rounds || o.masteps_last < 0) ? o.masteps : o.masteps_last,
+                                  grid_limit);
+          if (r + 1 < ma_rounds) {
+            k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
+            ma_in ^= 1;
+          }
+        }
         if (timing) { cudaEventRecord(ev[4], stream); }
         k_wf_advance<<<1, 32, 0, stream>>>(q, cur);
         cur ^= 1;
       }
-      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + 1);
+      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + (2 * ma_rounds) - 1);
       tm->iterations += sync_every;
       if (!ok(cudaMemcpyAsync(status, q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "status readback") ||
           !ok(cudaStreamSynchronize(stream), "wavefront iteration")) {

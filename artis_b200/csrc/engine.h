@@ -103,9 +103,12 @@ inline uint64_t options_hash_value() {
 struct PropagateOptions {
   int schedule{1};                 // [schedule] 0 = one whole-history kernel, 1 = wavefront of per-stage kernels
   int rsteps_thin{1};              // [wf_rsteps_thin]  r-packet steps per visit to ST_RTHIN
-  int rsteps_thick{8};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
-  int masteps{1};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
-  long long tail_threshold{4096};  // [wf_tail] hand the last packets to the whole-history kernel below this many
+  // defaults: tuned on B200 with the kilonova 2D workload (profiles/r1_tuning.md)
+  int rsteps_thick{2};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
+  int masteps{2};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
+  int ma_rounds{5};                // [wf_ma_rounds] macro-atom kernels per iteration (odd)
+  int masteps_last{0};             // [wf_masteps_last] transitions per visit in the last round (-1 = as wf_masteps)
+  long long tail_threshold{65536}; // [wf_tail] hand the last packets to the whole-history kernel below this many
   int sync_every{8};               // [wf_sync_every] wavefront iterations enqueued between host checks
   int stage_timing{0};             // [wf_stage_timing] bracket every stage kernel with CUDA events (profiling aid)
 };
@@ -283,6 +286,10 @@ class Engine {
       popt.rsteps_thick = static_cast<int>(value < 1 ? 1 : value);
     } else if (name == "wf_masteps") {
       popt.masteps = static_cast<int>(value < 0 ? 0 : value);
+    } else if (name == "wf_ma_rounds") {
+      popt.ma_rounds = static_cast<int>(value < 1 ? 1 : (value | 1));
+    } else if (name == "wf_masteps_last") {
+      popt.masteps_last = static_cast<int>(value);
     } else if (name == "wf_tail") {
       popt.tail_threshold = value;
     } else if (name == "wf_sync_every") {

@@ -159,6 +159,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    from artis_b200 import distributed as abdist
     from artis_b200 import lib as ablib
     from artis_b200 import snapshot as snap
 
@@ -189,7 +190,7 @@ def run_ours(args):
 
     eng = ablib.ArtisB200(preset=PRESET, device=local_rank)
     eng.set_option("rng_mode", 0)
-    eng.set_option("seed", 20260101 + (rank << 32))
+    eng.set_option("seed", abdist.rank_seed(20260101, rank))
     eng.set_option("rank", rank)
     eng.set_option("nranks", world)
     eng.set_option("max_steps_per_launch", int(os.environ.get("ARTISB200_MAXSTEPS", "0")))
@@ -213,8 +214,7 @@ def run_ours(args):
     def reduce_estimators():
         if world > 1:
             # one packed all-reduce replaces the per-array MPI_Allreduce calls of sn3d.cc:565-625 / radfield.cc:988-1030
-            t = _as_tensor(est_ptr, est_count, local_rank)
-            dist.all_reduce(t)
+            abdist.allreduce_estimators_device(eng, local_rank)
 
     def step_device():
         eng.restore_packets_device()
@@ -343,16 +343,6 @@ def run_ours(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def _as_tensor(ptr, count, device_index):
-    """wrap the library's packed estimator buffer (device pointer) as a torch tensor without copying"""
-    import torch
-
-    class _Holder:
-        def __init__(self, p, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 3}
-    return torch.as_tensor(_Holder(ptr, count), device=torch.device("cuda", device_index))
 
 
 # ------------------------------------------------------------------------------------------------------------

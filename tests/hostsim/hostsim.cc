@@ -119,24 +119,26 @@ struct HostBackend {
         }
       }
       int cur = 0;
-      auto run_list = [&](const int stage) {
-        // index loop: a stage may append to the macro-atom list of the running iteration
-        for (size_t k = 0; k < lists[cur][stage].size(); k++) {
-          const long long ip = lists[cur][stage][k];
+      // one stage kernel: visit every packet of lists[in][stage]; packets go on to lists[next][.], macro-atom work to
+      // lists[next_ma][ST_MA] (index loop: a stage may append to the macro-atom list of the running iteration)
+      auto run_list = [&](const int stage, const int in, const int next, const int next_ma, const int max_steps) {
+        for (size_t k = 0; k < lists[in][stage].size(); k++) {
+          const long long ip = lists[in][stage][k];
           const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
           int dest = ab::ST_DONE;
           switch (stage) {
-            case ab::ST_OTHER: dest = visit<ab::ST_OTHER>(T, c, ip, 1); break;
-            case ab::ST_RTHIN: dest = visit<ab::ST_RTHIN>(T, c, ip, o.rsteps_thin); break;
-            case ab::ST_RTHICK: dest = visit<ab::ST_RTHICK>(T, c, ip, o.rsteps_thick); break;
-            default: dest = visit<ab::ST_MA>(T, c, ip, o.masteps); break;
+            case ab::ST_OTHER: dest = visit<ab::ST_OTHER>(T, c, ip, max_steps); break;
+            case ab::ST_RTHIN: dest = visit<ab::ST_RTHIN>(T, c, ip, max_steps); break;
+            case ab::ST_RTHICK: dest = visit<ab::ST_RTHICK>(T, c, ip, max_steps); break;
+            default: dest = visit<ab::ST_MA>(T, c, ip, max_steps); break;
           }
           c.flush_hot();
           if (dest >= 0) {
-            lists[(dest == ab::ST_MA && stage != ab::ST_MA) ? cur : (cur ^ 1)][dest].push_back(static_cast<int>(ip));
+            lists[(dest == ab::ST_MA) ? next_ma : next][dest].push_back(static_cast<int>(ip));
           }
         }
       };
+      const int ma_rounds = (o.ma_rounds < 1) ? 1 : (o.ma_rounds | 1);
       while (true) {
         size_t waiting = 0;
         for (int s = 0; s < ab::NSTAGES; s++) {
@@ -150,16 +152,24 @@ struct HostBackend {
           run_history(T, n, acc, tm);
           break;
         }
-        run_list(ab::ST_OTHER);
-        run_list(ab::ST_RTHIN);
-        run_list(ab::ST_RTHICK);
-        run_list(ab::ST_MA);
+        const int next = cur ^ 1;
+        run_list(ab::ST_OTHER, cur, next, cur, 1);
+        run_list(ab::ST_RTHIN, cur, next, cur, o.rsteps_thin);
+        run_list(ab::ST_RTHICK, cur, next, cur, o.rsteps_thick);
+        int ma_in = cur;
+        for (int r = 0; r < ma_rounds; r++) {
+          run_list(ab::ST_MA, ma_in, next, ma_in ^ 1, (r + 1 < ma_rounds || o.masteps_last < 0) ? o.masteps : o.masteps_last);
+          if (r + 1 < ma_rounds) {
+            lists[ma_in][ab::ST_MA].clear();
+            ma_in ^= 1;
+          }
+        }
         for (int s = 0; s < ab::NSTAGES; s++) {
           lists[cur][s].clear();
         }
         cur ^= 1;
         tm->iterations++;
-        tm->launches += ab::NSTAGES + 1;
+        tm->launches += ab::NSTAGES + (2 * ma_rounds) - 1;
       }
     } else {
       run_history(T, n, acc, tm);

@@ -22,10 +22,12 @@ def _lib(config):
 
 # how the packets are scheduled onto kernels must not change any packet's result (include/artis_b200.h, options)
 SCHEDULES = {
-    "wavefront": {"schedule": 1},                                       # default
+    "wavefront": {"schedule": 1},                                       # default (toy sizes: mostly the tail kernel)
     "history": {"schedule": 0},                                         # one whole-history kernel
-    "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1},
+    "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1, "wf_masteps": 1, "wf_ma_rounds": 1,
+                         "wf_masteps_last": -1},
     "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0},   # whole macro-atom walk per visit
+    "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2},
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
 }
 
