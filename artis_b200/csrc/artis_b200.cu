@@ -228,13 +228,30 @@ struct WfQueues {
 #ifndef ARTISB200_WF_BLOCK
 #define ARTISB200_WF_BLOCK 128
 #endif
-#ifndef ARTISB200_WF_MINBLOCKS
-#define ARTISB200_WF_MINBLOCKS 4
+// The stages are latency-bound (dependent table gathers, FP64 dependency chains), so resident warps matter more
+// than a spill-free register allocation: measured on B200 (profiles/r1_tuning.md), per stage.
+#ifndef ARTISB200_WF_MINBLOCKS_OTHER
+#define ARTISB200_WF_MINBLOCKS_OTHER 4
+#endif
+#ifndef ARTISB200_WF_MINBLOCKS_RTHIN
+#define ARTISB200_WF_MINBLOCKS_RTHIN 8
+#endif
+#ifndef ARTISB200_WF_MINBLOCKS_RTHICK
+#define ARTISB200_WF_MINBLOCKS_RTHICK 8
+#endif
+#ifndef ARTISB200_WF_MINBLOCKS_MA
+#define ARTISB200_WF_MINBLOCKS_MA 6
 #endif
 constexpr int WF_BLOCK = ARTISB200_WF_BLOCK;
+constexpr int wf_minblocks(const int stage) {
+  return (stage == ab::ST_RTHIN)    ? ARTISB200_WF_MINBLOCKS_RTHIN
+         : (stage == ab::ST_RTHICK) ? ARTISB200_WF_MINBLOCKS_RTHICK
+         : (stage == ab::ST_MA)     ? ARTISB200_WF_MINBLOCKS_MA
+                                    : ARTISB200_WF_MINBLOCKS_OTHER;
+}
 
 template <int STAGE>
-__global__ void __launch_bounds__(WF_BLOCK, ARTISB200_WF_MINBLOCKS)
+__global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
     k_wf_stage(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int next, const int next_ma,
                const int max_steps) {
   __shared__ ab::Accum acc;

@@ -91,61 +91,86 @@ AHD double calculate_chi_ffheating(const Tables& T, const int cell, const double
   return chi_ff_nnionpart / pow3(nu) * clumpednne_ * (1 - exp(-HOVERKB * nu / T_e));
 }
 
-// Sum the bound-free opacity at nu over the window of continua with nu_edge <= nu <= nu_edge * last_phixs_nuovernuedge,
-// walking the cell's keep-bitmap a 64-bit word at a time (rpkt.cc:721-928).
-//   SELECT == false: returns chi_bf and records the per-ground-continuum sigma contributions in the thread's scratch
+// One kept continuum of the bound-free sum (rpkt.cc:840-905): sigma_contr = sigma_bf * probability * (1 - stimulated
+// correction); its opacity contribution is nnlevel * sigma_contr.
+struct BfEval {  // per-evaluation constants
+  double nu;
+  double T_e;
+  double exp_minus_hnu_over_kte;
+  bool stimfactor_split_usable;
+  long long base;  // cell * nbfcontinua
+};
+
+AHD BfEval bf_eval_begin(const Tables& T, const int cell, const double nu) {
+  BfEval e;
+  e.nu = nu;
+  e.T_e = T.Te[cell];
+  e.exp_minus_hnu_over_kte = exp(-HOVERKB * nu / e.T_e);
+  e.stimfactor_split_usable = (e.exp_minus_hnu_over_kte >= DBL_MIN_);
+  e.base = static_cast<long long>(cell) * T.nbfcontinua;
+  return e;
+}
+
+AHD double bf_term_sigma_contr(const Tables& T, const BfEval& e, const int i) {
+  const double nu_edge = T.cont_nu_edge[i];
+  const double sigma_bf = photoionisation_crosssection_fromtable(T, phixs_table(T, T.cont_uniquelevelindex[i]), nu_edge, e.nu);
+  const double stimfactor_edgepart = T.cell_cont_edgepart[e.base + i];
+  double stimfactor;
+  if (stimfactor_edgepart >= 0. && e.stimfactor_split_usable) {
+    stimfactor = stimfactor_edgepart * e.exp_minus_hnu_over_kte;
+  } else {
+    stimfactor = T.cell_cont_departure[e.base + i] * exp(-HOVERKB * (e.nu - nu_edge) / e.T_e);
+  }
+  const double corrfactor = dmax(0., 1 - stimfactor);
+  return sigma_bf * T.cont_probability[i] * corrfactor;
+}
+
+// the window [begin, end) of continua with nu_edge <= nu <= nu_edge * last_phixs_nuovernuedge (rpkt.cc:800-812)
+AHD void bf_window(const Tables& T, const double nu, int& allcontbegin, int& allcontend) {
+  allcontend = upper_bound_idx(T.cont_nu_edge, T.nbfcontinua, nu);
+  allcontbegin = lower_bound_idx(T.cont_nu_edge, allcontend, nu / T.last_phixs_nuovernuedge);
+}
+
+// keep-bitmap word `word` of the cell restricted to the window
+AHD unsigned long long bf_window_bits(const unsigned long long* keepbits, const int word, const int allcontbegin,
+                                      const int allcontend) {
+  unsigned long long bits = keepbits[word];
+  if (word == (allcontbegin / 64)) {
+    bits &= ~0ULL << static_cast<unsigned>(allcontbegin % 64);
+  }
+  if (((word + 1) * 64) > allcontend) {
+    bits &= ~0ULL >> static_cast<unsigned>(64 - (allcontend % 64));
+  }
+  return bits;
+}
+
+// Sum the bound-free opacity at nu over the window of continua, walking the cell's keep-bitmap a 64-bit word at a
+// time (rpkt.cc:721-928).
+//   SELECT == false: returns chi_bf and records the per-ground-continuum sigma contributions in the packet's scratch
 //   SELECT == true : returns (as a double) the index of the continuum at which the running sum first exceeds
 //                    `threshold` (or the last continuum of the window), writes nothing
+// the sum over the kept continua of the window [allcontbegin, allcontend), in ascending order
 template <bool SELECT>
-AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const double nu, const double threshold) {
+AHD double bf_sum_window(const Ctx& c, const int cell, const BfEval& e, const int allcontbegin, const int allcontend,
+                         const double threshold, int& nterms) {
   const Tables& T = c.T;
   double chi_bf_sum = 0.;
-  const int ng = T.nbfcontinua_ground;
   if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
+    const int ng = T.nbfcontinua_ground;
     for (int i = 0; i < ng; i++) {
       *c.groundcont_contr(i) = 0.;
     }
   }
-  const auto T_e = T.Te[cell];
-  const double exp_minus_hnu_over_kte = exp(-HOVERKB * nu / T_e);
-  const bool stimfactor_split_usable = (exp_minus_hnu_over_kte >= DBL_MIN_);
-
-  const double* nu_edge_arr = T.cont_nu_edge;
-  const int allcontend = upper_bound_idx(nu_edge_arr, T.nbfcontinua, nu);
-  const int allcontbegin = lower_bound_idx(nu_edge_arr, allcontend, nu / T.last_phixs_nuovernuedge);
-  c.work<DIAG_BINSEARCH_STEPS>(2 * T.log2_nbf);
-
-  const long long base = static_cast<long long>(cell) * T.nbfcontinua;
   const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
-  int nterms = 0;
-
   for (int word = allcontbegin / 64; word * 64 < allcontend; word++) {
-    unsigned long long bits = keepbits[word];
-    if (word == (allcontbegin / 64)) {
-      bits &= ~0ULL << static_cast<unsigned>(allcontbegin % 64);
-    }
-    if (((word + 1) * 64) > allcontend) {
-      bits &= ~0ULL >> static_cast<unsigned>(64 - (allcontend % 64));
-    }
+    unsigned long long bits = bf_window_bits(keepbits, word, allcontbegin, allcontend);
     while (bits != 0) {
       const int i = (word * 64) + lowest_set_bit(bits);
       bits &= bits - 1;
       nterms++;
 
-      const double nnlevel = T.cell_cont_nnlevel[base + i];
-      const double nu_edge = nu_edge_arr[i];
-      const double sigma_bf =
-          photoionisation_crosssection_fromtable(T, phixs_table(T, T.cont_uniquelevelindex[i]), nu_edge, nu);
-
-      const double stimfactor_edgepart = T.cell_cont_edgepart[base + i];
-      double stimfactor;
-      if (stimfactor_edgepart >= 0. && stimfactor_split_usable) {
-        stimfactor = stimfactor_edgepart * exp_minus_hnu_over_kte;
-      } else {
-        stimfactor = T.cell_cont_departure[base + i] * exp(-HOVERKB * (nu - nu_edge) / T_e);
-      }
-      const double corrfactor = dmax(0., 1 - stimfactor);
-      const double sigma_contr = sigma_bf * T.cont_probability[i] * corrfactor;
+      const double nnlevel = T.cell_cont_nnlevel[e.base + i];
+      const double sigma_contr = bf_term_sigma_contr(T, e, i);
 
       if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
         const int g = T.cont_groundcontestimindex[i];
@@ -164,14 +189,33 @@ AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const doubl
   if constexpr (SELECT) {
     return static_cast<double>(allcontend - 1);
   }
-  c.work<DIAG_CONT_TERMS>(nterms);
   return chi_bf_sum;
+}
+
+template <bool SELECT>
+AHD double calculate_chi_bf_gammacontr(const Ctx& c, const int cell, const double nu, const double threshold) {
+  const Tables& T = c.T;
+  const BfEval e = bf_eval_begin(T, cell, nu);
+  int allcontbegin = 0;
+  int allcontend = 0;
+  bf_window(T, nu, allcontbegin, allcontend);
+  c.work<DIAG_BINSEARCH_STEPS>(2 * T.log2_nbf);
+  int nterms = 0;
+  const double result = bf_sum_window<SELECT>(c, cell, e, allcontbegin, allcontend, threshold, nterms);
+  if constexpr (!SELECT) {
+    c.work<DIAG_CONT_TERMS>(nterms);
+  }
+  return result;
+}
+
+AHD bool chi_cache_valid(const ChiCont& chi, const double nu_cmf, const int cell) {  // rpkt.cc:1023-1027
+  return (cell == chi.nonemptymgi) && (fabs((chi.nu / nu_cmf) - 1.0) < 1e-4);
 }
 
 // rpkt.cc:1020-1044: (re)evaluate the continuum opacity unless the cached value is for the same cell and a
 // frequency within 1e-4 (the cache lives for one packet within one timestep)
 AHD void calculate_chi_rpkt_cont(const Ctx& c, const double nu_cmf, ChiCont& chi, const int cell) {
-  if ((cell == chi.nonemptymgi) && (fabs((chi.nu / nu_cmf) - 1.0) < 1e-4)) {
+  if (chi_cache_valid(chi, nu_cmf, cell)) {
     return;
   }
   const Tables& T = c.T;
@@ -336,23 +380,51 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
 // change of model cell, a CPU cell-cache artefact that the all-cells-resident device tables do not need.)
 // CELLKIND tells the compiler what the caller already knows about the packet's cell, so that a stage kernel carries
 // only its own half of the code: 0 = anything, 1 = detailed treatment (ST_RTHIN), 2 = grey or empty (ST_RTHICK).
+// The step in two halves: rstep_begin draws tau_rnd and finds the cell boundary (and finishes the step itself when
+// the packet sits exactly on a boundary), rstep_finish does the rest.
+struct RStepPre {
+  double tau_rnd;
+  double boundarydist;
+  int next_cellindex;
+  int cell;
+};
+
+// returns false when the step is already over (boundarydist == 0: the packet changed cell or escaped)
+AHD bool rstep_begin(Pkt& p, const Ctx& c, RStepPre& pre) {
+  const Tables& T = c.T;
+  pre.cell = T.propcell_nonemptymgi[p.cellindex];
+  c.work<DIAG_RPKT_STEPS>();
+  pre.tau_rnd = -log(static_cast<double>(p.rng.uniform_pos()));
+  const BoundaryHit hit = boundary_distance(T, p.dir, p.pos, p.prop_time, p.cellindex);
+  pre.boundarydist = hit.distance;
+  pre.next_cellindex = hit.next_cellindex;
+  if (pre.boundarydist == 0) {
+    change_cell_or_escape(p, c, pre.next_cellindex);
+    return false;
+  }
+  return true;
+}
+
+template <int CELLKIND = 0>
+AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const RStepPre& pre);
+
 template <int CELLKIND = 0>
 AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
-  const Tables& T = c.T;
-  const int cell = T.propcell_nonemptymgi[p.cellindex];
-  MacroAtomState pktmastate = {-1, -1, -1, -99};
-  c.work<DIAG_RPKT_STEPS>();
-
-  const double tau_rnd = -log(static_cast<double>(p.rng.uniform_pos()));
-
-  const BoundaryHit hit = boundary_distance(T, p.dir, p.pos, p.prop_time, p.cellindex);
-  const double boundarydist = hit.distance;
-  const int next_cellindex = hit.next_cellindex;
-
-  if (boundarydist == 0) {
-    change_cell_or_escape(p, c, next_cellindex);
+  RStepPre pre;
+  if (!rstep_begin(p, c, pre)) {
     return (p.type == TYPE_RPKT);
   }
+  return rstep_finish<CELLKIND>(p, c, t2, chi, pre);
+}
+
+template <int CELLKIND>
+AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const RStepPre& pre) {
+  const Tables& T = c.T;
+  const int cell = pre.cell;
+  MacroAtomState pktmastate = {-1, -1, -1, -99};
+  const double tau_rnd = pre.tau_rnd;
+  const double boundarydist = pre.boundarydist;
+  const int next_cellindex = pre.next_cellindex;
 
   const double tdist = (t2 - p.prop_time) * CLIGHT_PROP;
   const double abort_dist = dmin(tdist, boundarydist);
@@ -380,11 +452,18 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
     event_is_boundbound = ev.is_boundbound;
   }
 
-  if ((edist < boundarydist) && (edist <= tdist)) {
-    move_pkt_withtime(p, edist / 2.);
-    update_estimators(c, p.e_cmf, p.nu_cmf, edist, cell, chi, greycell);
-    move_pkt_withtime(p, edist / 2.);
+  // Which of the three outcomes (rpkt.cc:604-690): 0 = event, 1 = cell boundary, 2 = end of the timestep. All three
+  // move the packet in two halves with the estimator update in between (at the midpoint), so that part is written
+  // once here and the outcome-specific work follows.
+  const int outcome = ((edist < boundarydist) && (edist <= tdist)) ? 0 : (((boundarydist <= tdist) && (boundarydist <= edist)) ? 1 : 2);
+  const double movedist = (outcome == 0) ? edist : ((outcome == 1) ? boundarydist : tdist);
+  move_pkt_withtime(p, movedist / 2.);
+  if (cell >= 0) {  // an event only happens in a non-empty cell
+    update_estimators(c, p.e_cmf, p.nu_cmf, movedist, cell, chi, greycell);
+  }
+  move_pkt_withtime(p, movedist / 2.);
 
+  if (outcome == 0) {
     c.count<CNT_INTERACTIONS>();
     if (greycell) {
       p.nscatterings++;
@@ -400,13 +479,7 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
     }
     return (p.type == TYPE_RPKT);
   }
-
-  if ((boundarydist <= tdist) && (boundarydist <= edist)) {
-    move_pkt_withtime(p, boundarydist / 2.);
-    if (cell >= 0) {
-      update_estimators(c, p.e_cmf, p.nu_cmf, boundarydist, cell, chi, greycell);
-    }
-    move_pkt_withtime(p, boundarydist / 2.);
+  if (outcome == 1) {
     if (next_cellindex != p.cellindex) {
       change_cell_or_escape(p, c, next_cellindex);
       if (next_cellindex < 0) {
@@ -415,14 +488,7 @@ AHD bool do_rpkt_step(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
     }
     return true;
   }
-
-  // end of timestep reached before a boundary or an interaction
-  move_pkt_withtime(p, tdist / 2.);
-  if (cell >= 0) {
-    update_estimators(c, p.e_cmf, p.nu_cmf, tdist, cell, chi, greycell);
-  }
-  move_pkt_withtime(p, tdist / 2.);
-  p.prop_time = t2;
+  p.prop_time = t2;  // end of timestep reached before a boundary or an interaction
   return false;
 }
 
