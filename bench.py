@@ -337,6 +337,9 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline(cores=1)
+                # same model, same timestep, independent random numbers: the two codes must agree within Monte Carlo noise
+                out["crosscheck"] = {"interactions_per_packet_gpu": n_int / n,
+                                     "interactions_per_packet_cpu_reference": out["cpu_baseline"].pop("interactions_per_packet")}
             except Exception as e:  # the baseline must never take the bench line down
                 out["cpu_baseline"] = {"value": None, "unit": "interactions/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(out), flush=True)
@@ -392,7 +395,7 @@ def cpu_baseline(cores=1):
     return {"value": total_int / wall, "unit": "interactions/s", "cores": cores, "kind": "reference",
             "sample": f"{CPU_SAMPLE_CONFIG}: {npk} packets per process of the same model and atomic data, timestep {BENCH_TS} "
                       f"after evolving timesteps 0..{BENCH_TS - 1} on the CPU; update_packets wall {wall:.2f} s, "
-                      f"{total_int} interactions", "wall_s": wall}
+                      f"{total_int} interactions", "wall_s": wall, "interactions_per_packet": total_int / (npk * len(res))}
 
 
 def run_reference(args):

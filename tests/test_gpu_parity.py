@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from artis_b200 import lib as ablib
-from tests import fixtures, parity_checks
+from tests import fixtures, parity_checks, stochastic_checks
 
 pytestmark = pytest.mark.gpu
 CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
@@ -129,6 +129,13 @@ def test_philox_statistics_agree_with_reference_rng():
         assert abs(x_ref - mean) <= 4.0 * std * np.sqrt(1 + 1 / K) + 1e-12 * abs(mean), (name, x_ref, mean, std)
     # pellets that do not decay in this timestep are untouched by the random numbers: exact agreement
     assert np.isclose(runs[0]["pellet_fraction"], ref["pellet_fraction"], atol=4 * np.sqrt(0.25 * 2 / len(ref_pk)))
+
+
+@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy", 3)])
+def test_stochastic_parity_ks_and_estimators(config, nts):
+    """Philox (production) random numbers against the reference's own run: KS test on the r-packet frequencies, energy
+    budget per packet type, per-cell estimator z-scores (tests/stochastic_checks.py states the tests)."""
+    stochastic_checks.check_stochastic_parity(_lib(config), config, nts, K=8)
 
 
 def test_energy_bookkeeping():

@@ -6,7 +6,7 @@ and deterministic helper is checked against the compiled reference before GPU ti
 assertions run against the real CUDA library on the B200 in tests/test_gpu_parity.py."""
 import pytest
 
-from tests import fixtures, parity_checks
+from tests import fixtures, parity_checks, stochastic_checks
 
 CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
 
@@ -40,3 +40,11 @@ def test_bounded_launches_keep_histories():
     # (rpkt.cc:1023-1027) and pending macro-atom activations are part of the stored packet work state
     lib = fixtures.hostsim_library("kilonova_lte")
     parity_checks.check_packet_histories(lib, "kilonova_toy", 4, max_steps=7, options={"schedule": 0})
+
+
+@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4)])
+def test_stochastic_parity_ks_and_estimators(config, nts):
+    # the same stated tests as on the GPU (tests/stochastic_checks.py), fewer seeds to keep the CPU suite short
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
+    report = stochastic_checks.check_stochastic_parity(lib, config, nts, K=5)
+    assert report["n_rpkt_ref"] > 0
