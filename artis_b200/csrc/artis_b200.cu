@@ -104,7 +104,11 @@ __global__ void k_sort_count(const __grid_constant__ Tables T, const long long n
     const int b = sort_bucket_of(T, i, nbuckets_per_stage);
     keys[i] = b;
     if (b >= 0) {
-      atomicAdd(&bucket_count[b], 1U);
+      // one atomic per group of equal keys in the warp (packets that arrive already sorted would otherwise serialise)
+      const unsigned peers = __match_any_sync(__activemask(), b);
+      if ((threadIdx.x & 31U) == static_cast<unsigned>(__ffs(peers) - 1)) {
+        atomicAdd(&bucket_count[b], static_cast<unsigned int>(__popc(peers)));
+      }
     }
   }
 }
@@ -155,7 +159,15 @@ __global__ void k_sort_scatter(const long long n, const int* keys, const unsigne
   if (i < n) {
     const int b = keys[i];
     if (b >= 0) {
-      order[bucket_start[b] + atomicAdd(&bucket_cursor[b], 1U)] = static_cast<int>(i);
+      const unsigned peers = __match_any_sync(__activemask(), b);
+      const unsigned lane = threadIdx.x & 31U;
+      const int leader = __ffs(peers) - 1;
+      unsigned int base = 0U;
+      if (lane == static_cast<unsigned>(leader)) {
+        base = atomicAdd(&bucket_cursor[b], static_cast<unsigned int>(__popc(peers)));
+      }
+      base = __shfl_sync(peers, base, leader);
+      order[bucket_start[b] + base + __popc(peers & ((1U << lane) - 1U))] = static_cast<int>(i);
     }
   }
 }
@@ -307,6 +319,64 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
   }
   ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
   accum_flush(acc, T);
+}
+
+// Re-sort of the running lists by (stage, model cell): the appends keep them only roughly in cell order, and the
+// stages gather from per-cell tables (level populations, bound-free tables, gigabytes of cumulative macro-atom rates),
+// so warps whose lanes share a cell hit L1/L2 instead of HBM. Counting sort over the list entries only.
+__device__ __forceinline__ bool list_entry(const WfQueues& q, const int cur, const long long f, int& stage, int& ip) {
+  long long offset = 0;
+  for (int s = 0; s < ab::NSTAGES; s++) {
+    const long long cnt = q.count[(cur * ab::NSTAGES) + s];
+    if (f < offset + cnt) {
+      stage = s;
+      ip = q.list[cur][s][f - offset];
+      return true;
+    }
+    offset += cnt;
+  }
+  return false;
+}
+
+__global__ void k_list_count(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int nbuckets_per_stage, int* keys,
+                             unsigned int* bucket_count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long f = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;; f += stride) {
+    int stage = 0;
+    int ip = 0;
+    if (!list_entry(q, cur, f, stage, ip)) {
+      break;
+    }
+    const int b = (stage * nbuckets_per_stage) + T.propcell_nonemptymgi[T.pkt.hc[ip].cellindex] + 1;
+    keys[f] = b;
+    // neighbouring entries are mostly in the same cell already: one atomic per group of equal keys
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    if ((threadIdx.x & 31U) == static_cast<unsigned>(__ffs(peers) - 1)) {
+      atomicAdd(&bucket_count[b], static_cast<unsigned int>(__popc(peers)));
+    }
+  }
+}
+
+__global__ void k_list_scatter(const WfQueues q, const int cur, const int* keys, const unsigned int* bucket_start,
+                               unsigned int* bucket_cursor, int* order) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long f = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;; f += stride) {
+    int stage = 0;
+    int ip = 0;
+    if (!list_entry(q, cur, f, stage, ip)) {
+      break;
+    }
+    const int b = keys[f];
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    const unsigned lane = threadIdx.x & 31U;
+    const int leader = __ffs(peers) - 1;
+    unsigned int base = 0U;
+    if (lane == static_cast<unsigned>(leader)) {
+      base = atomicAdd(&bucket_cursor[b], static_cast<unsigned int>(__popc(peers)));
+    }
+    base = __shfl_sync(peers, base, leader);
+    order[bucket_start[b] + base + __popc(peers & ((1U << lane) - 1U))] = ip;
+  }
 }
 
 // initial lists = the stage ranges of the cell-sorted order
@@ -690,6 +760,20 @@ struct CudaBackend {
     k_sort_scatter<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_keys, d_bucket_start, d_bucket_count, d_order);
   }
 
+  // lists of buffer `cur` -> sorted by (stage, cell) into buffer 0
+  void resort_lists(const Tables& T, const WfQueues& q, const int cur, const unsigned long long waiting) {
+    const int nbuckets_per_stage = T.ncells + 1;
+    const int nbuckets = ab::NSTAGES * nbuckets_per_stage;
+    unsigned int grid = static_cast<unsigned int>((waiting + 255ULL) / 256ULL);
+    grid = (grid < 1U) ? 1U : ((grid > static_cast<unsigned int>(sm_count * 8)) ? static_cast<unsigned int>(sm_count * 8) : grid);
+    cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
+    k_list_count<<<grid, 256, 0, stream>>>(T, q, cur, nbuckets_per_stage, d_keys, d_bucket_count);
+    k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, nbuckets_per_stage, d_queue, d_stage_count);
+    k_list_scatter<<<grid, 256, 0, stream>>>(q, cur, d_keys, d_bucket_start, d_bucket_count, d_order);
+    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, stream>>>(q, d_order, d_stage_count);
+  }
+
   // whole-history kernel over every packet that still needs work, relaunched while max_steps_per_launch leaves any
   bool run_history(const Tables& T, const int64_t n, ab::PropagateTimings* tm) {
     if (history_blocks_per_sm == 0) {
@@ -763,6 +847,7 @@ struct CudaBackend {
     }
     unsigned long long status[2] = {static_cast<unsigned long long>(n), 0ULL};
     int cur = 0;
+    long long iteration = 0;
     while (true) {
       // every list of the coming iterations is at most as long as the number of packets waiting now
       const unsigned long long bound = (status[0] + WF_BLOCK - 1ULL) / WF_BLOCK;
@@ -781,8 +866,7 @@ struct CudaBackend {
         // macro-atom lists; what is still walking after the last round continues in the next iteration
         int ma_in = cur;
         for (int r = 0; r < ma_rounds; r++) {
-          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, (r + 1 < ma_rounds || o.masteps_last < 0) ? o.masteps : o.masteps_last,
-                                  grid_limit);
+          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit);
           if (r + 1 < ma_rounds) {
             k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
             ma_in ^= 1;
@@ -791,6 +875,13 @@ struct CudaBackend {
         if (timing) { cudaEventRecord(ev[4], stream); }
         k_wf_advance<<<1, 32, 0, stream>>>(q, cur);
         cur ^= 1;
+        iteration++;
+        if (o.resort_every > 0 && (iteration % o.resort_every) == 0 && static_cast<long long>(status[0]) >= o.resort_min_packets) {
+          // no host involvement: the lists of buffer `cur` are sorted into buffer 0 on the device
+          resort_lists(T, q, cur, status[0]);
+          tm->launches += 4;
+          cur = 0;
+        }
       }
       tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + (2 * ma_rounds) - 1);
       tm->iterations += sync_every;

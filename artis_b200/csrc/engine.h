@@ -107,11 +107,26 @@ struct PropagateOptions {
   int rsteps_thick{2};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
   int masteps{2};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
   int ma_rounds{5};                // [wf_ma_rounds] macro-atom kernels per iteration (odd)
-  int masteps_last{0};             // [wf_masteps_last] transitions per visit in the last round (-1 = as wf_masteps)
+  int masteps_last{0};             // [wf_masteps_last] transitions per visit in the last round (-1 = as the others)
+  int ma_growth{0};                // [wf_ma_growth] 1 = double the transitions per visit every second round
+  int resort_every{1};             // [wf_resort_every] re-sort the lists by cell every this many iterations (0 = never)
+  long long resort_min_packets{0}; // [wf_resort_min] ... while at least this many packets are waiting
   long long tail_threshold{65536}; // [wf_tail] hand the last packets to the whole-history kernel below this many
   int sync_every{8};               // [wf_sync_every] wavefront iterations enqueued between host checks
   int stage_timing{0};             // [wf_stage_timing] bracket every stage kernel with CUDA events (profiling aid)
 };
+
+// macro-atom transitions per visit in round r of an iteration
+inline int ma_round_steps(const PropagateOptions& o, const int r, const int rounds) {
+  if (r + 1 == rounds && o.masteps_last >= 0) {
+    return o.masteps_last;
+  }
+  if (o.masteps <= 0) {
+    return 0;
+  }
+  const int shift = (o.ma_growth != 0) ? ((r / 2 < 20) ? r / 2 : 20) : 0;
+  return o.masteps << shift;
+}
 
 struct PropagateTimings {
   double total_ms{0.};
@@ -288,6 +303,12 @@ class Engine {
       popt.masteps = static_cast<int>(value < 0 ? 0 : value);
     } else if (name == "wf_ma_rounds") {
       popt.ma_rounds = static_cast<int>(value < 1 ? 1 : (value | 1));
+    } else if (name == "wf_resort_every") {
+      popt.resort_every = static_cast<int>(value < 0 ? 0 : value);
+    } else if (name == "wf_resort_min") {
+      popt.resort_min_packets = value;
+    } else if (name == "wf_ma_growth") {
+      popt.ma_growth = static_cast<int>(value);
     } else if (name == "wf_masteps_last") {
       popt.masteps_last = static_cast<int>(value);
     } else if (name == "wf_tail") {
@@ -620,6 +641,8 @@ class Engine {
     if (npackets <= 0) {
       return fail("update_packets: no packets uploaded");
     }
+    T.rng_setup = {T.rng_mode, static_cast<unsigned int>(T.seed), static_cast<unsigned int>(T.nts),
+                   static_cast<unsigned int>(T.seed >> 32U)};
     if (!be.propagate(T, npackets, popt, &last)) {
       return fail("update_packets: propagation failed: " + be.last_error());
     }

@@ -28,6 +28,43 @@ AHD void atomic_add(double* addr, const double val) {
 #endif
 }
 
+// Estimator accumulation from converged code (all lanes of a warp add to J[cell], nuJ[cell], ... at the same time):
+// warp-aggregated. Lanes that add to the same address are found with match.any, their values are summed with
+// shuffles, and one lane issues the atomic. With cell-sorted packet lists most lanes of a warp are in the same cell:
+// one RED per warp instead of a 32-way same-address conflict (measured: the grey r-packet stage doubled its time on
+// freshly sorted lists before this, profiles/r1_tuning.md).
+AHD void est_atomic_add(double* addr, const double val) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const unsigned lane = threadIdx.x & 31U;
+  const unsigned peers = __match_any_sync(active, reinterpret_cast<unsigned long long>(addr));
+  if (peers == 0xffffffffU) {
+    // the whole warp adds to one address: butterfly
+    double sum = val;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffU, sum, d);
+    }
+    if (lane == 0U) {
+      atomicAdd(addr, sum);
+    }
+    return;
+  }
+  double sum = 0.;
+  unsigned m = peers;
+  while (m != 0U) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1U;
+    sum += __shfl_sync(peers, val, src);
+  }
+  if (lane == static_cast<unsigned>(__ffs(peers) - 1)) {
+    atomicAdd(addr, sum);
+  }
+#else
+  *addr += val;
+#endif
+}
+
 AHD void atomic_add(long long* addr, const long long val) {
 #if defined(__CUDA_ARCH__)
   atomicAdd(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(val));

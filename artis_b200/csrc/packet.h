@@ -6,7 +6,10 @@
 // register footprint at ~14 doubles instead of the ~33 doubles of the reference's 240-byte Packet
 // (packet.h:109-156).
 #pragma once
+#include <cstring>
+
 #include "hd.h"
+#include "options.h"
 #include "rng.h"
 #include "tables.h"
 
@@ -151,37 +154,67 @@ enum : int { ST_DONE = -1, ST_OTHER = 0, ST_RTHIN = 1, ST_RTHICK = 2, ST_MA = 3,
 AHD int pack_stage(const int stage, const int ev_pending) { return (stage & 0xff) | (ev_pending << 8); }
 AHD int stored_stage(const HotC& hc) { return static_cast<int>(static_cast<signed char>(hc.stage & 0xff)); }
 
-// Bring a packet into registers. STAGE names what the caller is going to do with it: the macro-atom stage moves
-// one 64-byte record (plus nu_cmf and e_cmf, which a deactivation reads), everything else moves all three.
+// 16-byte group of a record
+struct alignas(16) Q4 {
+  int a, b, c, d;
+};
+AHD Q4 load_q4(const void* src) {
+  Q4 v;
+#if defined(__CUDA_ARCH__)
+  v = *static_cast<const Q4*>(src);
+#else
+  memcpy(&v, src, sizeof(Q4));
+#endif
+  return v;
+}
+AHD void store_q4(void* dst, const Q4& v) {
+#if defined(__CUDA_ARCH__)
+  *static_cast<Q4*>(dst) = v;
+#else
+  memcpy(dst, &v, sizeof(Q4));
+#endif
+}
+
+// What a stage moves (everything else stays in HBM untouched; fewer live registers = more resident warps):
+//   kinematics + energies   every stage but the macro-atom stage (which reads prop_time, nu_cmf, e_cmf only)
+//   Stokes parameters       only with POL_ON
+//   opacity cache           only where r-packet steps in cells with the detailed treatment can happen
+//   macro-atom activation   read by the macro-atom stage; written by whichever stage records or continues one
+template <int STAGE>
+struct StageIO {
+  static constexpr bool kinematics = (STAGE != ST_MA);
+  static constexpr bool chi = (STAGE == ST_RTHIN) || (STAGE == ST_ANY);
+  static constexpr bool ma_in = (STAGE == ST_MA) || (STAGE == ST_ANY);
+};
+
+// Bring a packet into registers. STAGE names what the caller is going to do with it.
 template <int STAGE = ST_ANY>
 AHD void load_pkt(Pkt& p, ChiCont& chi, const Tables& T, const long long ip) {
-  const HotC hc = T.pkt.hc[ip];
-  p.next_trans = hc.next_trans;
-  p.type = hc.type;
-  p.cellindex = hc.cellindex;
-  p.nscatterings = hc.nscatterings;
-  const int stage = static_cast<int>(static_cast<signed char>(hc.stage & 0xff));  // low byte: ST_* (ST_DONE = -1)
-  p.ev_pending = hc.stage >> 8;
+  const HotC* hc = &T.pkt.hc[ip];
+  const Q4 head = load_q4(&hc->next_trans);
+  const Q4 rng = load_q4(hc->rng);
+  p.next_trans = head.a;
+  p.type = head.b;
+  p.cellindex = head.c;
+  const int stage = static_cast<int>(static_cast<signed char>(head.d & 0xff));  // low byte: ST_* (ST_DONE = -1)
+  p.ev_pending = head.d >> 8;
   p.ma_pending = (stage == ST_MA) ? 1 : 0;
-  p.ma = {hc.ma[0], hc.ma[1], hc.ma[2], hc.ma[3]};
+  p.nscatterings = hc->nscatterings;
   p.rng.have_block = 0;
-  p.rng.mode = T.rng_mode;
-  p.rng.s0 = hc.rng[0];
-  p.rng.s1 = hc.rng[1];
-  p.rng.s2 = hc.rng[2];
-  p.rng.s3 = hc.rng[3];
-  p.rng.key0 = static_cast<unsigned int>(T.seed);
-  p.rng.ctr1 = static_cast<unsigned int>(T.nts);
-  p.rng.ctr2 = static_cast<unsigned int>(T.seed >> 32U);
-  chi.chi_boundfree = hc.chi_bf;
-  chi.nonemptymgi = hc.chi_mgi;
-  if constexpr (STAGE == ST_MA) {
-    p.prop_time = T.pkt.ha[ip].prop_time;  // stage_of() asks whether a k-packet left by the walk still has time
-    p.nu_cmf = T.pkt.ha[ip].nu_cmf;
-    p.e_cmf = T.pkt.hb[ip].e_cmf;
+  p.rng.setup = &T.rng_setup;
+  p.rng.s0 = static_cast<unsigned int>(rng.a);
+  p.rng.s1 = static_cast<unsigned int>(rng.b);
+  p.rng.s2 = static_cast<unsigned int>(rng.c);
+  p.rng.s3 = static_cast<unsigned int>(rng.d);
+  if constexpr (StageIO<STAGE>::ma_in) {
+    const Q4 ma = load_q4(hc->ma);
+    p.ma = {ma.a, ma.b, ma.c, ma.d};
   } else {
+    p.ma = {-1, -1, -1, -99};
+  }
+  if constexpr (StageIO<STAGE>::kinematics) {
     const HotA ha = T.pkt.ha[ip];
-    const HotB hb = T.pkt.hb[ip];
+    const HotB* hb = &T.pkt.hb[ip];
     p.prop_time = ha.prop_time;
     p.pos[0] = ha.pos[0];
     p.pos[1] = ha.pos[1];
@@ -190,42 +223,47 @@ AHD void load_pkt(Pkt& p, ChiCont& chi, const Tables& T, const long long ip) {
     p.dir[1] = ha.dir[1];
     p.dir[2] = ha.dir[2];
     p.nu_cmf = ha.nu_cmf;
-    p.e_cmf = hb.e_cmf;
-    p.nu_rf = hb.nu_rf;
-    p.e_rf = hb.e_rf;
-    p.stokes_q = hb.stokes_q;
-    p.stokes_u = hb.stokes_u;
-    chi.nu = hb.chi_nu;
-    chi.chi_escatter = hb.chi_escatter;
-    chi.chi_freefree_heat = hb.chi_ff;
+    p.e_cmf = hb->e_cmf;
+    p.nu_rf = hb->nu_rf;
+    p.e_rf = hb->e_rf;
+    if constexpr (opt::POL_ON) {
+      p.stokes_q = hb->stokes_q;
+      p.stokes_u = hb->stokes_u;
+    } else {
+      p.stokes_q = 0.;
+      p.stokes_u = 0.;
+    }
+    if constexpr (StageIO<STAGE>::chi) {
+      chi.nu = hb->chi_nu;
+      chi.chi_escatter = hb->chi_escatter;
+      chi.chi_freefree_heat = hb->chi_ff;
+    }
+  } else {
+    p.prop_time = T.pkt.ha[ip].prop_time;  // stage_of() asks whether a k-packet left by the walk still has time
+    p.nu_cmf = T.pkt.ha[ip].nu_cmf;
+    p.e_cmf = T.pkt.hb[ip].e_cmf;
+  }
+  if constexpr (StageIO<STAGE>::chi) {
+    chi.chi_boundfree = hc->chi_bf;
+    chi.nonemptymgi = hc->chi_mgi;
   }
 }
 
 // `stage`: where the packet waits next (ST_*); a recorded macro-atom activation is saved with ST_MA
 template <int STAGE = ST_ANY>
 AHD void store_pkt(const Pkt& p, const ChiCont& chi, const Tables& T, const long long ip, const int stage) {
-  HotC hc;
-  hc.next_trans = p.next_trans;
-  hc.type = p.type;
-  hc.cellindex = p.cellindex;
-  hc.stage = pack_stage(stage, p.ev_pending);
-  hc.nscatterings = p.nscatterings;
-  hc.rng[0] = p.rng.s0;
-  hc.rng[1] = p.rng.s1;
-  hc.rng[2] = p.rng.s2;
-  hc.rng[3] = p.rng.s3;
-  hc.ma[0] = p.ma.element;
-  hc.ma[1] = p.ma.ion;
-  hc.ma[2] = p.ma.level;
-  hc.ma[3] = p.ma.activatingline;
-  hc.chi_bf = chi.chi_boundfree;
-  hc.chi_mgi = chi.nonemptymgi;
-  T.pkt.hc[ip] = hc;
-  if constexpr (STAGE == ST_MA) {
-    if (p.ev_pending != EV_NONE) {
-      T.pkt.ha[ip].nu_cmf = p.nu_cmf;  // frequency of the r-packet a radiative deactivation emits
-    }
-  } else {
+  HotC* hc = &T.pkt.hc[ip];
+  store_q4(&hc->next_trans, {p.next_trans, p.type, p.cellindex, pack_stage(stage, p.ev_pending)});
+  store_q4(hc->rng, {static_cast<int>(p.rng.s0), static_cast<int>(p.rng.s1), static_cast<int>(p.rng.s2), static_cast<int>(p.rng.s3)});
+  hc->nscatterings = p.nscatterings;
+  if (stage == ST_MA) {
+    store_q4(hc->ma, {p.ma.element, p.ma.ion, p.ma.level, p.ma.activatingline});
+  }
+  if constexpr (StageIO<STAGE>::chi) {
+    hc->chi_mgi = chi.nonemptymgi;
+    hc->chi_bf = chi.chi_boundfree;
+  }
+  if constexpr (StageIO<STAGE>::kinematics) {
     HotA ha;
     ha.prop_time = p.prop_time;
     ha.pos[0] = p.pos[0];
@@ -236,16 +274,23 @@ AHD void store_pkt(const Pkt& p, const ChiCont& chi, const Tables& T, const long
     ha.dir[2] = p.dir[2];
     ha.nu_cmf = p.nu_cmf;
     T.pkt.ha[ip] = ha;
-    HotB hb;
-    hb.e_cmf = p.e_cmf;
-    hb.nu_rf = p.nu_rf;
-    hb.e_rf = p.e_rf;
-    hb.stokes_q = p.stokes_q;
-    hb.stokes_u = p.stokes_u;
-    hb.chi_nu = chi.nu;
-    hb.chi_escatter = chi.chi_escatter;
-    hb.chi_ff = chi.chi_freefree_heat;
-    T.pkt.hb[ip] = hb;
+    HotB* hb = &T.pkt.hb[ip];
+    hb->e_cmf = p.e_cmf;
+    hb->nu_rf = p.nu_rf;
+    hb->e_rf = p.e_rf;
+    if constexpr (opt::POL_ON) {
+      hb->stokes_q = p.stokes_q;
+      hb->stokes_u = p.stokes_u;
+    }
+    if constexpr (StageIO<STAGE>::chi) {
+      hb->chi_nu = chi.nu;
+      hb->chi_escatter = chi.chi_escatter;
+      hb->chi_ff = chi.chi_freefree_heat;
+    }
+  } else {
+    if (p.ev_pending != EV_NONE) {
+      T.pkt.ha[ip].nu_cmf = p.nu_cmf;  // frequency of the r-packet a radiative deactivation emits
+    }
   }
 }
 

@@ -28,22 +28,27 @@ AHD unsigned int mulhi32(const unsigned int a, const unsigned int b) {
 #endif
 }
 
-struct Rng {
-  unsigned int s0, s1, s2, s3;  // xoshiro state, or philox (draw counter, packet number, -, -)
+struct RngSetup {
   int mode;
   unsigned int key0;  // philox key word 0 (seed)
   unsigned int ctr1;  // philox counter word 1 (timestep)
   unsigned int ctr2;  // philox counter word 2 (rank)
+};
+
+struct Rng {
+  unsigned int s0, s1, s2, s3;  // xoshiro state, or philox (draw counter, packet number, -, -)
+  // run-wide settings are read where they are needed (kernel parameter space) instead of living in registers
+  const RngSetup* setup;
   unsigned int b0, b1, b2, b3;  // philox: the four outputs of block (s0 >> 2); valid when have_block != 0
   int have_block;
 
   AHD void philox_block(const unsigned int blockindex) {
     // Philox4x32-10 (Salmon et al. 2011): counter (block, timestep, rank, 0), key (seed, packet number)
     unsigned int c0 = blockindex;
-    unsigned int c1 = ctr1;
-    unsigned int c2 = ctr2;
+    unsigned int c1 = setup->ctr1;
+    unsigned int c2 = setup->ctr2;
     unsigned int c3 = 0U;
-    unsigned int k0 = key0;
+    unsigned int k0 = setup->key0;
     unsigned int k1 = s1;
 #pragma unroll
     for (int round = 0; round < 10; round++) {
@@ -66,7 +71,7 @@ struct Rng {
   }
 
   AHD unsigned int next_u32() {
-    if (mode == RNG_XOSHIRO) {
+    if (setup->mode == RNG_XOSHIRO) {
       // Xoshiro128++ (Blackman & Vigna), same output function as reference random.h:124-135
       const unsigned int result = rotl32(s0 + s3, 7U) + s0;
       const unsigned int t = s1 << 9U;

@@ -162,27 +162,37 @@ AHD double bf_sum_window(const Ctx& c, const int cell, const BfEval& e, const in
     }
   }
   const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
-  for (int word = allcontbegin / 64; word * 64 < allcontend; word++) {
-    unsigned long long bits = bf_window_bits(keepbits, word, allcontbegin, allcontend);
-    while (bits != 0) {
-      const int i = (word * 64) + lowest_set_bit(bits);
-      bits &= bits - 1;
-      nterms++;
-
-      const double nnlevel = T.cell_cont_nnlevel[e.base + i];
-      const double sigma_contr = bf_term_sigma_contr(T, e, i);
-
-      if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
-        const int g = T.cont_groundcontestimindex[i];
-        if (g >= 0) {
-          *c.groundcont_contr(g) = sigma_contr;
-        }
+  // ONE loop over "fetch the next bitmap word" / "evaluate the next kept continuum": with a loop over words around a
+  // loop over bits the lanes of a warp drift apart (each is in a different word) and the term code ran with 2.4 of 32
+  // lanes active (ncu, profiles/r1_tuning.md); here all lanes that still have terms execute the term code together.
+  int word = (allcontbegin / 64) - 1;
+  unsigned long long bits = 0ULL;
+  while (true) {
+    if (bits == 0ULL) {
+      word++;
+      if (word * 64 >= allcontend) {
+        break;
       }
-      chi_bf_sum += nnlevel * sigma_contr;
-      if constexpr (SELECT) {
-        if (chi_bf_sum > threshold) {
-          return static_cast<double>(i);
-        }
+      bits = bf_window_bits(keepbits, word, allcontbegin, allcontend);
+      continue;
+    }
+    const int i = (word * 64) + lowest_set_bit(bits);
+    bits &= bits - 1;
+    nterms++;
+
+    const double nnlevel = T.cell_cont_nnlevel[e.base + i];
+    const double sigma_contr = bf_term_sigma_contr(T, e, i);
+
+    if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
+      const int g = T.cont_groundcontestimindex[i];
+      if (g >= 0) {
+        *c.groundcont_contr(g) = sigma_contr;
+      }
+    }
+    chi_bf_sum += nnlevel * sigma_contr;
+    if constexpr (SELECT) {
+      if (chi_bf_sum > threshold) {
+        return static_cast<double>(i);
       }
     }
   }
@@ -304,14 +314,14 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
   const Tables& T = c.T;
   const double distance_e_cmf = distance * e_cmf;
   if (distance_e_cmf != 0) {
-    atomic_add(&T.est_J[cell], distance_e_cmf);
-    atomic_add(&T.est_nuJ[cell], distance_e_cmf * nu_cmf);
+    est_atomic_add(&T.est_J[cell], distance_e_cmf);
+    est_atomic_add(&T.est_nuJ[cell], distance_e_cmf * nu_cmf);
     c.work<DIAG_ESTIMATOR_ADDS>(2);
   }
   if (thickcell) {
     return;
   }
-  atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
+  est_atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
   c.work<DIAG_ESTIMATOR_ADDS>(1);
 
   if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
@@ -324,10 +334,10 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
       const long long ionestimindex = (static_cast<long long>(cell) * ng) + i;
       const double contr = *c.groundcont_contr(i);
       if constexpr (opt::USE_LUT_PHOTOION) {
-        atomic_add(&T.est_gamma[ionestimindex], contr * (distance_e_cmf / nu_cmf));
+        est_atomic_add(&T.est_gamma[ionestimindex], contr * (distance_e_cmf / nu_cmf));
       }
       if constexpr (opt::USE_ION_BFHEATING_ESTIMATORS) {
-        atomic_add(&T.est_bfheating[ionestimindex], contr * distance_e_cmf * (1. - (nu_edge / nu_cmf)));
+        est_atomic_add(&T.est_bfheating[ionestimindex], contr * distance_e_cmf * (1. - (nu_edge / nu_cmf)));
       }
       c.work<DIAG_ESTIMATOR_ADDS>(2);
     }

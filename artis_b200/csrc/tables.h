@@ -9,6 +9,7 @@
 #include <cstdint>
 
 #include "hd.h"
+#include "rng.h"
 
 namespace ab {
 
@@ -202,15 +203,16 @@ struct alignas(64) HotB {
 };
 
 struct alignas(64) HotC {
-  double chi_bf;
+  // 16-byte groups, so that a stage moves exactly the groups it needs with 128-bit accesses
   int next_trans;
   int type;
   int cellindex;
   int stage;            // ST_* the packet waits in between kernels, + 256 * (pending event EV_*)
   unsigned int rng[4];  // xoshiro state, or philox (draw counter, packet number, -, -)
   int ma[4];            // recorded macro-atom activation: element, ion, level, activating line (packet.h:96-105)
-  int chi_mgi;
   int nscatterings;
+  int chi_mgi;          // cached continuum opacity: cell ...
+  double chi_bf;        // ... and bound-free part (the rest is in HotB)
 };
 
 struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_time/trueemissiontype
@@ -294,6 +296,7 @@ struct Tables {
   // run options
   int rng_mode;
   unsigned long long seed;
+  RngSetup rng_setup;  // (rng_mode, seed, timestep) in the form the generators read; refreshed before every propagation
   long long max_steps_per_launch;
 
   // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]

@@ -158,7 +158,7 @@ struct HostBackend {
         run_list(ab::ST_RTHICK, cur, next, cur, o.rsteps_thick);
         int ma_in = cur;
         for (int r = 0; r < ma_rounds; r++) {
-          run_list(ab::ST_MA, ma_in, next, ma_in ^ 1, (r + 1 < ma_rounds || o.masteps_last < 0) ? o.masteps : o.masteps_last);
+          run_list(ab::ST_MA, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds));
           if (r + 1 < ma_rounds) {
             lists[ma_in][ab::ST_MA].clear();
             ma_in ^= 1;

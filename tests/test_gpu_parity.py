@@ -27,6 +27,7 @@ SCHEDULES = {
     "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1, "wf_masteps": 1, "wf_ma_rounds": 1,
                          "wf_masteps_last": -1},
     "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0},   # whole macro-atom walk per visit
+    "wavefront-resort": {"schedule": 1, "wf_tail": 0, "wf_resort_every": 1, "wf_sync_every": 2},  # lists re-sorted by cell
     "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2},
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
 }
