@@ -527,6 +527,10 @@ struct CudaBackend {
   int device{-1};
   int sm_count{0};
   cudaStream_t stream{nullptr};
+  cudaStream_t copy_stream{nullptr};
+  cudaEvent_t ev_upload{nullptr};
+  cudaEvent_t ev_pre_build{nullptr};
+  bool tables_building{false};
   cudaEvent_t ev_start{nullptr};
   cudaEvent_t ev_stop{nullptr};
   cudaEvent_t ev_sched0{nullptr};
@@ -577,7 +581,10 @@ struct CudaBackend {
       return false;
     }
     sm_count = prop.multiProcessorCount;
-    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ok(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ok(cudaEventCreateWithFlags(&ev_upload, cudaEventDisableTiming), "cudaEventCreate") ||
+        !ok(cudaEventCreateWithFlags(&ev_pre_build, cudaEventDisableTiming), "cudaEventCreate")) {
       return false;
     }
     if (!ok(cudaEventCreate(&ev_start), "cudaEventCreate") || !ok(cudaEventCreate(&ev_stop), "cudaEventCreate") ||
@@ -614,6 +621,9 @@ struct CudaBackend {
       cudaEventDestroy(ev_tail1);
       cudaEventDestroy(ev_sched0);
       cudaEventDestroy(ev_sched1);
+      cudaEventDestroy(ev_upload);
+      cudaEventDestroy(ev_pre_build);
+      cudaStreamDestroy(copy_stream);
       cudaEventDestroy(ev_start);
       cudaEventDestroy(ev_stop);
       cudaStreamDestroy(stream);
@@ -659,6 +669,8 @@ struct CudaBackend {
 
   bool build_cell_tables(const Tables& T) {
     cudaSetDevice(device);
+    cudaEventRecord(ev_pre_build, stream);  // an upload may start once everything enqueued before the build is done
+    tables_building = true;
     constexpr int B = 128;
     const long long ncl = static_cast<long long>(T.ncells) * T.nlevels;
     if (ncl > 0) {
@@ -679,7 +691,9 @@ struct CudaBackend {
     // stats::Counter::UPDATECELL counts one cell-cache fill per cell (update_packets.cc:399)
     const long long ncells = T.ncells;
     cudaMemcpyAsync(&T.counters[ab::CNT_UPDATECELL], &ncells, sizeof(long long), cudaMemcpyHostToDevice, stream);
-    return ok(cudaStreamSynchronize(stream), "build_cell_tables") && ok(cudaGetLastError(), "build_cell_tables");
+    // not synchronised: the caller's next step is usually the packet upload, which runs on the copy stream while
+    // these kernels build the tables (execution errors surface at the next synchronisation of this stream)
+    return ok(cudaGetLastError(), "build_cell_tables");
   }
 
   bool run_test_kernel(Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,
@@ -702,12 +716,27 @@ struct CudaBackend {
     return good;
   }
 
-  bool aos_to_soa(const Tables& T, const void* aos, const int64_t n, const int stride) {
+  // Host AoS packets -> device records, on the COPY stream: overlaps with whatever the main stream is still doing
+  // (the per-cell table build of begin_timestep). Returns when the host buffer may be reused; the main stream is made
+  // to wait for the converted records.
+  bool upload_packets(const Tables& T, void* staging, const void* host_aos, const int64_t n, const int stride) {
     cudaSetDevice(device);
-    if (n > 0) {
-      k_aos_to_soa<<<blocks_for(n, 256), 256, 0, stream>>>(T, static_cast<const unsigned char*>(aos), n, stride);
+    // order the upload after the work already enqueued on the main stream, except a table build in flight (it does
+    // not touch the packet records): that one is what the copy overlaps with
+    if (!tables_building) {
+      cudaEventRecord(ev_pre_build, stream);
     }
-    return ok(cudaGetLastError(), "k_aos_to_soa");
+    cudaStreamWaitEvent(copy_stream, ev_pre_build, 0);
+    if (n > 0) {
+      if (!ok(cudaMemcpyAsync(staging, host_aos, static_cast<size_t>(n) * static_cast<size_t>(stride), cudaMemcpyHostToDevice, copy_stream),
+              "cudaMemcpy H2D (packets)")) {
+        return false;
+      }
+      k_aos_to_soa<<<blocks_for(n, 256), 256, 0, copy_stream>>>(T, static_cast<const unsigned char*>(staging), n, stride);
+    }
+    cudaEventRecord(ev_upload, copy_stream);
+    cudaStreamWaitEvent(stream, ev_upload, 0);
+    return ok(cudaStreamSynchronize(copy_stream), "packet upload") && ok(cudaGetLastError(), "k_aos_to_soa");
   }
 
   bool soa_to_aos(const Tables& T, void* aos, const int64_t n, const int stride) {
@@ -941,6 +970,7 @@ struct CudaBackend {
     if (!ok(cudaEventSynchronize(ev_stop), "cudaEventSynchronize")) {
       return false;
     }
+    tables_building = false;  // the stream has been synchronised
     float ms = 0.F;
     cudaEventElapsedTime(&ms, ev_start, ev_stop);
     tm->total_ms = ms;

@@ -104,8 +104,8 @@ struct PropagateOptions {
   int schedule{1};                 // [schedule] 0 = one whole-history kernel, 1 = wavefront of per-stage kernels
   int rsteps_thin{1};              // [wf_rsteps_thin]  r-packet steps per visit to ST_RTHIN
   // defaults: tuned on B200 with the kilonova 2D workload (profiles/r1_tuning.md)
-  int rsteps_thick{2};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
-  int masteps{2};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
+  int rsteps_thick{4};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
+  int masteps{3};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
   int ma_rounds{5};                // [wf_ma_rounds] macro-atom kernels per iteration (odd)
   int masteps_last{0};             // [wf_masteps_last] transitions per visit in the last round (-1 = as the others)
   int ma_growth{0};                // [wf_ma_growth] 1 = double the transitions per visit every second round
@@ -610,13 +610,10 @@ class Engine {
     if (rc != 0) {
       return rc;
     }
-    if (n > 0 && !be.h2d(aos_staging, aos, n * stride)) {
-      return fail("upload_packets: host-to-device copy failed: " + be.last_error());
-    }
     npackets = n;
     aos_stride = stride;
-    if (!be.aos_to_soa(T, aos_staging, n, stride)) {
-      return fail("upload_packets: conversion kernel failed: " + be.last_error());
+    if (!be.upload_packets(T, aos_staging, aos, n, stride)) {
+      return fail("upload_packets: copy or conversion failed: " + be.last_error());
     }
     return 0;
   }

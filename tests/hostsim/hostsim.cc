@@ -75,9 +75,10 @@ struct HostBackend {
     return true;
   }
 
-  bool aos_to_soa(const ab::Tables& T, const void* aos, const int64_t n, const int stride) {
+  bool upload_packets(const ab::Tables& T, void* staging, const void* host_aos, const int64_t n, const int stride) {
+    std::memcpy(staging, host_aos, static_cast<size_t>(n) * static_cast<size_t>(stride));
     for (int64_t i = 0; i < n; i++) {
-      ab::aos_to_soa_one(T, static_cast<const unsigned char*>(aos), stride, i);
+      ab::aos_to_soa_one(T, static_cast<const unsigned char*>(staging), stride, i);
     }
     return true;
   }

@@ -4,11 +4,15 @@
 set -u
 TAG=${1:-r1}
 shift || true
-STEPS=${*:-"tests bench history launches full"}
+STEPS=${*:-"smoke tests bench history reference launches full"}
 export ARTISB200_BENCH_CACHE=/tmp/bench_cache
 mkdir -p gpurun_out
 for step in $STEPS; do
   case $step in
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log ;;
+    reference)
+      timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "reference rc=$?" ;;
     tests)
       timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" ;;
     bench)
