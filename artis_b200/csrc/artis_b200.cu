@@ -529,6 +529,9 @@ struct CudaBackend {
   cudaStream_t stream{nullptr};
   cudaStream_t copy_stream{nullptr};
   cudaEvent_t ev_upload{nullptr};
+  cudaStream_t side_stream[2]{nullptr, nullptr};
+  cudaEvent_t ev_fork{nullptr};
+  cudaEvent_t ev_join[2]{nullptr, nullptr};
   cudaEvent_t ev_pre_build{nullptr};
   bool tables_building{false};
   cudaEvent_t ev_start{nullptr};
@@ -584,7 +587,12 @@ struct CudaBackend {
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !ok(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !ok(cudaEventCreateWithFlags(&ev_upload, cudaEventDisableTiming), "cudaEventCreate") ||
-        !ok(cudaEventCreateWithFlags(&ev_pre_build, cudaEventDisableTiming), "cudaEventCreate")) {
+        !ok(cudaEventCreateWithFlags(&ev_pre_build, cudaEventDisableTiming), "cudaEventCreate") ||
+        !ok(cudaStreamCreateWithFlags(&side_stream[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ok(cudaStreamCreateWithFlags(&side_stream[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !ok(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate") ||
+        !ok(cudaEventCreateWithFlags(&ev_join[0], cudaEventDisableTiming), "cudaEventCreate") ||
+        !ok(cudaEventCreateWithFlags(&ev_join[1], cudaEventDisableTiming), "cudaEventCreate")) {
       return false;
     }
     if (!ok(cudaEventCreate(&ev_start), "cudaEventCreate") || !ok(cudaEventCreate(&ev_stop), "cudaEventCreate") ||
@@ -623,6 +631,11 @@ struct CudaBackend {
       cudaEventDestroy(ev_sched1);
       cudaEventDestroy(ev_upload);
       cudaEventDestroy(ev_pre_build);
+      cudaEventDestroy(ev_fork);
+      cudaEventDestroy(ev_join[0]);
+      cudaEventDestroy(ev_join[1]);
+      cudaStreamDestroy(side_stream[0]);
+      cudaStreamDestroy(side_stream[1]);
       cudaStreamDestroy(copy_stream);
       cudaEventDestroy(ev_start);
       cudaEventDestroy(ev_stop);
@@ -836,7 +849,7 @@ struct CudaBackend {
 
   template <int STAGE>
   void launch_stage(const Tables& T, const WfQueues& q, const int cur, const int next, const int next_ma, const int max_steps,
-                    const unsigned int grid_limit) {
+                    const unsigned int grid_limit, cudaStream_t on) {
     if (stage_blocks_per_sm[STAGE] == 0) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stage_blocks_per_sm[STAGE], k_wf_stage<STAGE>, WF_BLOCK, 0);
       stage_blocks_per_sm[STAGE] = (stage_blocks_per_sm[STAGE] < 1) ? 1 : stage_blocks_per_sm[STAGE];
@@ -844,7 +857,7 @@ struct CudaBackend {
     // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
     unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
     grid = (grid > grid_limit) ? grid_limit : grid;
-    k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, stream>>>(T, q, cur, next, next_ma, max_steps);
+    k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, on>>>(T, q, cur, next, next_ma, max_steps);
   }
 
   bool run_wavefront(const Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
@@ -884,18 +897,33 @@ struct CudaBackend {
       for (int it = 0; it < sync_every; it++) {
         cudaEvent_t* ev = timing ? &stage_events[static_cast<size_t>(it) * (ab::NSTAGES + 1)] : nullptr;
         const int next = cur ^ 1;
-        if (timing) { cudaEventRecord(ev[0], stream); }
-        launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit);
-        if (timing) { cudaEventRecord(ev[1], stream); }
-        launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit);
-        if (timing) { cudaEventRecord(ev[2], stream); }
-        launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit);
-        if (timing) { cudaEventRecord(ev[3], stream); }
+        if (timing || o.concurrent == 0) {
+          if (timing) { cudaEventRecord(ev[0], stream); }
+          launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, stream);
+          if (timing) { cudaEventRecord(ev[1], stream); }
+          launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
+          if (timing) { cudaEventRecord(ev[2], stream); }
+          launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit, stream);
+          if (timing) { cudaEventRecord(ev[3], stream); }
+        } else {
+          // the three stages read and append to different lists: run them side by side, so that the drain of one
+          // (its last, slowest chunks) overlaps with the bulk of the others; the macro-atom kernels wait for all three
+          cudaEventRecord(ev_fork, stream);
+          cudaStreamWaitEvent(side_stream[0], ev_fork, 0);
+          cudaStreamWaitEvent(side_stream[1], ev_fork, 0);
+          launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
+          launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit, side_stream[0]);
+          launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, side_stream[1]);
+          cudaEventRecord(ev_join[0], side_stream[0]);
+          cudaEventRecord(ev_join[1], side_stream[1]);
+          cudaStreamWaitEvent(stream, ev_join[0], 0);
+          cudaStreamWaitEvent(stream, ev_join[1], 0);
+        }
         // macro-atom walks: `ma_rounds` kernels of at most `masteps` transitions each, ping-ponging between the two
         // macro-atom lists; what is still walking after the last round continues in the next iteration
         int ma_in = cur;
         for (int r = 0; r < ma_rounds; r++) {
-          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit);
+          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit, stream);
           if (r + 1 < ma_rounds) {
             k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
             ma_in ^= 1;

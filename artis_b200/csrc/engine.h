@@ -113,6 +113,7 @@ struct PropagateOptions {
   long long resort_min_packets{0}; // [wf_resort_min] ... while at least this many packets are waiting
   long long tail_threshold{65536}; // [wf_tail] hand the last packets to the whole-history kernel below this many
   int sync_every{8};               // [wf_sync_every] wavefront iterations enqueued between host checks
+  int concurrent{1};               // [wf_concurrent] run the three independent stage kernels of an iteration side by side
   int stage_timing{0};             // [wf_stage_timing] bracket every stage kernel with CUDA events (profiling aid)
 };
 
@@ -315,6 +316,8 @@ class Engine {
       popt.tail_threshold = value;
     } else if (name == "wf_sync_every") {
       popt.sync_every = static_cast<int>(value < 1 ? 1 : value);
+    } else if (name == "wf_concurrent") {
+      popt.concurrent = static_cast<int>(value);
     } else if (name == "wf_stage_timing") {
       popt.stage_timing = static_cast<int>(value);
     } else if (name == "rank") {

@@ -127,6 +127,7 @@ int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name); /* -1 if un
  *   kernels per iteration, transitions per visit in the last of them (0 = finish the walk), doubling every 2nd round;
  * "wf_resort_every", "wf_resort_min": re-sort the stage lists by model cell every this many iterations while at least
  *   that many packets are waiting (table locality; the appends keep the lists only roughly sorted);
+ * "wf_concurrent": 1 (default) = the three independent stage kernels of an iteration run on separate streams;
  * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
  * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
  * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep. */
