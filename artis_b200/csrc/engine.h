@@ -105,9 +105,10 @@ struct PropagateOptions {
   int rsteps_thin{1};              // [wf_rsteps_thin]  r-packet steps per visit to ST_RTHIN
   // defaults: tuned on B200 with the kilonova 2D workload (profiles/r1_tuning.md)
   int rsteps_thick{4};             // [wf_rsteps_thick] r-packet steps per visit to ST_RTHICK
-  int masteps{3};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
-  int ma_rounds{5};                // [wf_ma_rounds] macro-atom kernels per iteration (odd)
-  int masteps_last{0};             // [wf_masteps_last] transitions per visit in the last round (-1 = as the others)
+  int masteps{4};                  // [wf_masteps] macro-atom transitions per visit to ST_MA (0 = whole walk)
+  int ma_rounds{3};                // [wf_ma_rounds] macro-atom kernels per iteration (odd)
+  int masteps_last{8};             // [wf_masteps_last] transitions per visit in the last round (-1 = as the others,
+                                   //   0 = finish the walk); walks still unfinished continue in the next iteration
   int ma_growth{0};                // [wf_ma_growth] 1 = double the transitions per visit every second round
   int resort_every{1};             // [wf_resort_every] re-sort the lists by cell every this many iterations (0 = never)
   long long resort_min_packets{0}; // [wf_resort_min] ... while at least this many packets are waiting
