@@ -185,7 +185,7 @@ class Engine {
   }
 
   static bool keep_hostcopy(const std::string& name) {
-    return name.rfind("elem.", 0) == 0 || name.rfind("ion.", 0) == 0 || name.rfind("level.", 0) == 0 ||
+    return name.rfind("elem.", 0) == 0 || name.rfind("ion.", 0) == 0 || name.rfind("level.", 0) == 0 || name.rfind("cont.", 0) == 0 ||
            name.rfind("timesteps.", 0) == 0 || name == "lut.temperature_grid";
   }
 
@@ -436,6 +436,35 @@ class Engine {
       matrans_total += (2LL * l_ndown[l]) + l_nup[l];
     }
     T.matrans_total = static_cast<int>(matrans_total);
+    // static half of the bound-free terms (tables.h ContStatic)
+    {
+      const auto* c_nu_edge = host<double>("cont.nu_edge");
+      const auto* c_prob = host<double>("cont.probability");
+      const auto* c_ulev = host<int>("cont.uniquelevelindex");
+      const auto* c_ground = host<int>("cont.groundcontestimindex");
+      const auto* l_phixsstart = host<int>("level.phixsstart");
+      std::vector<ContStatic> cs(static_cast<size_t>(T.nbfcontinua));
+      for (int i = 0; i < T.nbfcontinua; i++) {
+        const long long offset = static_cast<long long>(l_phixsstart[c_ulev[i]]) * T.nphixspoints;
+        if (offset > 2147483647LL) {
+          return fail("commit_static: photoionisation table larger than 2^31 entries");
+        }
+        cs[static_cast<size_t>(i)] = {c_nu_edge[i], c_prob[i], static_cast<int>(offset), c_ground[i], {0, 0}};
+      }
+      ArrayRec& rec = arrays["derived.cont_static"];
+      if (rec.dptr != nullptr) {
+        be.free(rec.dptr);
+      }
+      const int64_t nbytes = static_cast<int64_t>(cs.size() * sizeof(ContStatic));
+      rec.dptr = be.alloc(nbytes > 0 ? nbytes : 32);
+      if (rec.dptr == nullptr || (nbytes > 0 && !be.h2d(rec.dptr, cs.data(), nbytes))) {
+        return fail("commit_static: device allocation of the continuum records failed: " + be.last_error());
+      }
+      rec.dtype = 'B';
+      rec.count = nbytes;
+      rec.capacity_bytes = nbytes;
+      T.cont_static = static_cast<const ContStatic*>(rec.dptr);
+    }
     if (!make_derived("derived.ion_element", ion_element, &T.ion_element) ||
         !make_derived("derived.ion_index", ion_index, &T.ion_index) ||
         !make_derived("derived.level_uniqueion", level_uniqueion, &T.level_uniqueion)) {
@@ -509,6 +538,7 @@ class Engine {
     ok = ok && alloc_output("built.cont_keepbits", 'Q', nc * T.keepwords, &T.cell_cont_keepbits);
     ok = ok && alloc_output("built.cont_departure", 'd', nc * T.nbfcontinua, &T.cell_cont_departure);
     ok = ok && alloc_output("built.cont_edgepart", 'd', nc * T.nbfcontinua, &T.cell_cont_edgepart);
+    ok = ok && alloc_output("built.cont_pack", 'd', 2 * nc * T.nbfcontinua, &T.cell_cont_pack);
     ok = ok && alloc_output("built.chi_ff_nnionpart", 'd', nc, &T.cell_chi_ff_nnionpart);
     ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nc * static_cast<int64_t>(T.nphixstargets_total),
                             &T.cell_corrphotoioncoeff);

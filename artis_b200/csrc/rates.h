@@ -181,6 +181,7 @@ AHD bool build_cell_continuum(const Tables& T, const int cell, const int i) {
   }
   T.cell_cont_departure[base + i] = departure;
   T.cell_cont_edgepart[base + i] = edgepart;
+  T.cell_cont_pack[base + i] = {nnlevel, edgepart};
   return keep;
 }
 

@@ -111,18 +111,21 @@ AHD BfEval bf_eval_begin(const Tables& T, const int cell, const double nu) {
   return e;
 }
 
-AHD double bf_term_sigma_contr(const Tables& T, const BfEval& e, const int i) {
-  const double nu_edge = T.cont_nu_edge[i];
-  const double sigma_bf = photoionisation_crosssection_fromtable(T, phixs_table(T, T.cont_uniquelevelindex[i]), nu_edge, e.nu);
-  const double stimfactor_edgepart = T.cell_cont_edgepart[e.base + i];
+// returns sigma_contr; `nnlevel` is the population the caller multiplies it with
+AHD double bf_term_sigma_contr(const Tables& T, const BfEval& e, const int i, double& nnlevel, int& groundcontestimindex) {
+  const ContStatic cs = T.cont_static[i];
+  const CellCont cc = T.cell_cont_pack[e.base + i];
+  nnlevel = cc.nnlevel;
+  groundcontestimindex = cs.groundcontestimindex;
+  const double sigma_bf = photoionisation_crosssection_fromtable(T, T.phixs_table + cs.phixs_offset, cs.nu_edge, e.nu);
   double stimfactor;
-  if (stimfactor_edgepart >= 0. && e.stimfactor_split_usable) {
-    stimfactor = stimfactor_edgepart * e.exp_minus_hnu_over_kte;
+  if (cc.edgepart >= 0. && e.stimfactor_split_usable) {
+    stimfactor = cc.edgepart * e.exp_minus_hnu_over_kte;
   } else {
-    stimfactor = T.cell_cont_departure[e.base + i] * exp(-HOVERKB * (e.nu - nu_edge) / e.T_e);
+    stimfactor = T.cell_cont_departure[e.base + i] * exp(-HOVERKB * (e.nu - cs.nu_edge) / e.T_e);
   }
   const double corrfactor = dmax(0., 1 - stimfactor);
-  return sigma_bf * T.cont_probability[i] * corrfactor;
+  return sigma_bf * cs.probability * corrfactor;
 }
 
 // the window [begin, end) of continua with nu_edge <= nu <= nu_edge * last_phixs_nuovernuedge (rpkt.cc:800-812)
@@ -180,11 +183,11 @@ AHD double bf_sum_window(const Ctx& c, const int cell, const BfEval& e, const in
     bits &= bits - 1;
     nterms++;
 
-    const double nnlevel = T.cell_cont_nnlevel[e.base + i];
-    const double sigma_contr = bf_term_sigma_contr(T, e, i);
+    double nnlevel = 0.;
+    int g = -1;
+    const double sigma_contr = bf_term_sigma_contr(T, e, i, nnlevel, g);
 
     if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
-      const int g = T.cont_groundcontestimindex[i];
       if (g >= 0) {
         *c.groundcont_contr(g) = sigma_contr;
       }

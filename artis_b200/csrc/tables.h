@@ -215,6 +215,22 @@ struct alignas(64) HotC {
   double chi_bf;        // ... and bound-free part (the rest is in HotB)
 };
 
+// What one term of the bound-free opacity sum needs, packed so that it costs two independent loads instead of a
+// chain of dependent gathers through five arrays: the static half per continuum (one 32-byte sector), the per-cell
+// half per (cell, continuum) (one 16-byte load).
+struct alignas(32) ContStatic {
+  double nu_edge;
+  double probability;
+  int phixs_offset;          // index of the continuum's photoionisation table in phixs.table
+  int groundcontestimindex;
+  int pad[2];
+};
+
+struct alignas(16) CellCont {
+  double nnlevel;
+  double edgepart;  // departure * exp(h nu_edge / kT), or < 0: use the slow form (rpkt.cc:873-889)
+};
+
 struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_time/trueemissiontype
   double pos[3];
   float time;
@@ -291,7 +307,8 @@ struct Tables {
   const int* level_uniqueion;   // [nlevels] unique ion index of each level
   const int* ion_element;       // [nions]
   const int* ion_index;         // [nions] ion index within its element
-  const int* cont_bflistindex;  // unused placeholder for future lookups
+  const ContStatic* cont_static;  // [nbfcontinua]
+  CellCont* cell_cont_pack;       // [ncells][nbfcontinua], written by the per-cell table build
 
   // run options
   int rng_mode;
