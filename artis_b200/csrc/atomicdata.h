@@ -207,8 +207,45 @@ AHD double planck(const double nu, const double temperature) {
   return 2 * H * pow3(nu) / pow2(CLIGHT) / expm1(HOVERKB * nu / temperature);
 }
 
-// mean intensity model J_nu: single dilute blackbody (radfield.cc:786-801 without the multibin branch)
+// frequency bin of the multi-bin radiation field model (radfield.cc:118-161; sn3d.h:115-122 get_linearbinindex):
+// -2 below the lowest bin, -1 at or above the top of the T_e superbin
+AHD int radfield_select_bin(const double nu) {
+  constexpr double delta_nu = (opt::RADFIELDBINS_NU_MAX - opt::RADFIELDBINS_NU_MIN) / (opt::RADFIELDBINCOUNT - 1);
+  if (nu < opt::RADFIELDBINS_NU_MIN) {
+    return -2;
+  }
+  if (nu >= opt::RADFIELDBINS_T_E_SUPERBIN_NU_MAX) {
+    return -1;
+  }
+  if (nu >= opt::RADFIELDBINS_NU_MAX) {
+    return opt::RADFIELDBINCOUNT - 1;
+  }
+  const double fracindex = (nu - opt::RADFIELDBINS_NU_MIN) / delta_nu;
+  const long long truncated = static_cast<long long>(fracindex);
+  const int binindex = static_cast<int>((fracindex < static_cast<double>(truncated)) ? truncated - 1 : truncated);
+  const double nu_upper = (binindex == opt::RADFIELDBINCOUNT - 1) ? opt::RADFIELDBINS_T_E_SUPERBIN_NU_MAX
+                                                                   : opt::RADFIELDBINS_NU_MIN + ((binindex + 1) * delta_nu);
+  if (nu == nu_upper) {
+    return binindex + 1;  // exactly on the upper boundary: bins are left-closed
+  }
+  return binindex;
+}
+
+// mean intensity model J_nu (radfield.cc:786-801): the fitted dilute blackbody of the frequency bin once the
+// multi-bin model is active, else a single dilute blackbody
 AHD double radfield_J(const Tables& T, const double nu, const int cell) {
+  if constexpr (opt::MULTIBIN_RADFIELD_MODEL_ON) {
+    if (T.globals_timestep >= opt::FIRST_NLTE_RADFIELD_TIMESTEP) {
+      const int binindex = radfield_select_bin(nu);
+      if (binindex >= 0) {
+        const float W = T.radfield_bin_W[(static_cast<long long>(cell) * opt::RADFIELDBINCOUNT) + binindex];
+        if (W >= 0.) {
+          return W * planck(nu, T.radfield_bin_T_R[(static_cast<long long>(cell) * opt::RADFIELDBINCOUNT) + binindex]);
+        }
+      }
+      return 0.;
+    }
+  }
   return T.W[cell] * planck(nu, T.TR[cell]);
 }
 

@@ -78,11 +78,12 @@ inline std::string options_summary_string() {
   char buf[1024];
   std::snprintf(buf, sizeof(buf),
                 "preset=%s;POL_ON=%d;DIPOLE=%d;RELDOPPLER=%d;PHIXS_CLASSIC=%d;LUT_PHOTOION=%d;ION_BFHEAT=%d;"
-                "DETAILED_BF=%d;MULTIBIN=%d;DIRECT_COL_HEAT=%d;NT_ON=%d;TJ_EXC=%d;BFCOOL_LEVELPOP=%d;"
+                "DETAILED_BF=%d;MULTIBIN=%d(%d bins from ts %d);DIRECT_COL_HEAT=%d;NT_ON=%d;TJ_EXC=%d;BFCOOL_LEVELPOP=%d;"
                 "PARTICLE_SCHEME=%d;GAMMA_SCHEME=%d;MINPOP=%g;NU_MIN_R=%g;NU_MAX_R=%g",
                 ARTISB200_PRESET_NAME, opt::POL_ON, opt::DIPOLE, opt::USE_RELATIVISTIC_DOPPLER_SHIFT,
                 opt::PHIXS_CLASSIC_NO_INTERPOLATION, opt::USE_LUT_PHOTOION, opt::USE_ION_BFHEATING_ESTIMATORS,
-                opt::DETAILED_BF_ESTIMATORS_ON, opt::MULTIBIN_RADFIELD_MODEL_ON, opt::DIRECT_COL_HEAT, opt::NT_ON,
+                opt::DETAILED_BF_ESTIMATORS_ON, opt::MULTIBIN_RADFIELD_MODEL_ON, opt::RADFIELDBINCOUNT,
+                opt::FIRST_NLTE_RADFIELD_TIMESTEP, opt::DIRECT_COL_HEAT, opt::NT_ON,
                 opt::LTEPOP_EXCITATION_USE_TJ, opt::BFCOOLING_USELEVELPOPNOTIONPOP, opt::PARTICLE_THERMALISATION_SCHEME,
                 opt::GAMMA_THERMALISATION_SCHEME, opt::MINPOP, opt::NU_MIN_R, opt::NU_MAX_R);
   return buf;
@@ -498,11 +499,16 @@ class Engine {
     const int64_t nc = T.ncells;
     const int64_t ng = T.nbfcontinua_ground;
     // one packed f64 buffer for everything that is summed over ranks (see artisb200_estimator_device_buffer)
-    const int64_t sizes[11] = {nc, nc, nc, nc, nc * ng, nc * ng, nc, nc, nc, nc, NTSSCALARS};
-    const char* names[11] = {"est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating",
-                             "est.dep_gamma", "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars"};
-    double** slots[11] = {&T.est_J, &T.est_nuJ, &T.est_ffheating, &T.est_colheating, &T.est_gamma, &T.est_bfheating,
-                          &T.est_dep_gamma, &T.est_dep_positron, &T.est_dep_electron, &T.est_dep_alpha, &T.ts_scalars};
+    // the multi-bin radiation field estimators (radfield.cc:63-70) exist only with MULTIBIN_RADFIELD_MODEL_ON
+    const int64_t nbins = opt::MULTIBIN_RADFIELD_MODEL_ON ? nc * opt::RADFIELDBINCOUNT : 0;
+    constexpr int NPACK = 13;
+    const int64_t sizes[NPACK] = {nc, nc, nc, nc, nc * ng, nc * ng, nc, nc, nc, nc, NTSSCALARS, nbins, nbins};
+    const char* names[NPACK] = {"est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating",
+                                "est.dep_gamma", "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars",
+                                "est.bins_J_raw", "est.bins_nuJ_raw"};
+    double** slots[NPACK] = {&T.est_J, &T.est_nuJ, &T.est_ffheating, &T.est_colheating, &T.est_gamma, &T.est_bfheating,
+                             &T.est_dep_gamma, &T.est_dep_positron, &T.est_dep_electron, &T.est_dep_alpha, &T.ts_scalars,
+                             &T.est_bins_J_raw, &T.est_bins_nuJ_raw};
     int64_t total = 0;
     for (const auto s : sizes) {
       total += s;
@@ -516,7 +522,10 @@ class Engine {
     }
     estimator_pack_count = total;
     int64_t off = 0;
-    for (int k = 0; k < 11; k++) {
+    for (int k = 0; k < NPACK; k++) {
+      if (sizes[k] == 0 && k >= 11) {
+        continue;  // optional estimators that this preset does not have stay unregistered
+      }
       ArrayRec& rec = arrays[names[k]];
       rec.dptr = static_cast<double*>(estimator_pack) + off;
       rec.dtype = 'd';
@@ -561,6 +570,13 @@ class Engine {
     for (const char* name : required) {
       if (count_of(name) < 0) {
         return fail(std::string("begin_timestep: per-timestep array '") + name + "' has not been set");
+      }
+    }
+    if constexpr (opt::MULTIBIN_RADFIELD_MODEL_ON) {
+      const int64_t want = static_cast<int64_t>(T.ncells) * opt::RADFIELDBINCOUNT;
+      if (count_of("radfield.bin_W") != want || count_of("radfield.bin_T_R") != want) {
+        return fail("begin_timestep: radfield.bin_W / radfield.bin_T_R must hold ncells x RADFIELDBINCOUNT entries "
+                    "(MULTIBIN_RADFIELD_MODEL_ON)");
       }
     }
     if (count_of("cell.rho") != T.ncells || count_of("cell.ion_groundlevelpops") != static_cast<int64_t>(T.ncells) * T.nions) {

@@ -16,6 +16,11 @@ constexpr bool USE_LUT_PHOTOION = ::USE_LUT_PHOTOION;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = ::USE_ION_BFHEATING_ESTIMATORS;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = ::DETAILED_BF_ESTIMATORS_ON;
 constexpr bool MULTIBIN_RADFIELD_MODEL_ON = ::MULTIBIN_RADFIELD_MODEL_ON;
+constexpr int RADFIELDBINCOUNT = ::RADFIELDBINCOUNT;
+constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = ::FIRST_NLTE_RADFIELD_TIMESTEP;
+constexpr double RADFIELDBINS_NU_MIN = ::RADFIELDBINS_NU_MIN;
+constexpr double RADFIELDBINS_NU_MAX = ::RADFIELDBINS_NU_MAX;
+constexpr double RADFIELDBINS_T_E_SUPERBIN_NU_MAX = ::RADFIELDBINS_T_E_SUPERBIN_NU_MAX;
 constexpr bool DIRECT_COL_HEAT = ::DIRECT_COL_HEAT;
 constexpr bool NT_ON = ::NT_ON;
 constexpr bool NT_SOLVE_SPENCERFANO = ::NT_SOLVE_SPENCERFANO;
@@ -58,7 +63,6 @@ constexpr int GTS_GUTTMAN = 3;
 
 // modes of the reference that this library does not implement yet fail at compile time rather than silently
 static_assert(!DETAILED_BF_ESTIMATORS_ON, "DETAILED_BF_ESTIMATORS_ON (NLTE presets) is not implemented yet");
-static_assert(!MULTIBIN_RADFIELD_MODEL_ON, "MULTIBIN_RADFIELD_MODEL_ON (NLTE presets) is not implemented yet");
 static_assert(!NT_SOLVE_SPENCERFANO, "Spencer-Fano non-thermal routing is not implemented yet");
 static_assert(!HAS_NLTE_LEVELS, "NLTE level populations are not implemented yet");
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,

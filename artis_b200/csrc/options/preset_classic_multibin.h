@@ -1,6 +1,7 @@
-// Hot-path subset of the reference preset artisoptions_classic.h (values restated).
+// artisoptions_classic.h with the multi-bin radiation field model switched on from timestep 1 (the radiation-field
+// part of the NLTE presets: radfield.cc:138-161, 745-771, 786-801), used by the classic_multibin_toy parity case.
 #pragma once
-#define ARTISB200_PRESET_NAME "classic"
+#define ARTISB200_PRESET_NAME "classic_multibin"
 namespace opt {
 constexpr bool POL_ON = true;
 constexpr bool DIPOLE = true;
@@ -9,9 +10,9 @@ constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = true;
 constexpr bool USE_LUT_PHOTOION = true;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = true;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = false;
-constexpr bool MULTIBIN_RADFIELD_MODEL_ON = false;
+constexpr bool MULTIBIN_RADFIELD_MODEL_ON = true;
 constexpr int RADFIELDBINCOUNT = 256;
-constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = 12;
+constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = 1;
 constexpr double RADFIELDBINS_NU_MIN = 2.99792458e+10 / 40000e-8;
 constexpr double RADFIELDBINS_NU_MAX = 2.99792458e+10 / 1085e-8;
 constexpr double RADFIELDBINS_T_E_SUPERBIN_NU_MAX = 2.99792458e+10 / 10e-8;

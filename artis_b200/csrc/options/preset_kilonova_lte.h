@@ -10,6 +10,11 @@ constexpr bool USE_LUT_PHOTOION = true;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = true;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = false;
 constexpr bool MULTIBIN_RADFIELD_MODEL_ON = false;
+constexpr int RADFIELDBINCOUNT = 256;
+constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = 12;
+constexpr double RADFIELDBINS_NU_MIN = 2.99792458e+10 / 40000e-8;
+constexpr double RADFIELDBINS_NU_MAX = 2.99792458e+10 / 1085e-8;
+constexpr double RADFIELDBINS_T_E_SUPERBIN_NU_MAX = 2.99792458e+10 / 10e-8;
 constexpr bool DIRECT_COL_HEAT = true;
 constexpr bool NT_ON = false;
 constexpr bool NT_SOLVE_SPENCERFANO = false;

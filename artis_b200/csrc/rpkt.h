@@ -324,6 +324,17 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
   if (thickcell) {
     return;
   }
+  if constexpr (opt::MULTIBIN_RADFIELD_MODEL_ON) {  // radfield.cc:762-770
+    if (distance_e_cmf != 0) {
+      const int binindex = radfield_select_bin(nu_cmf);
+      if (binindex >= 0) {
+        const long long mgibinindex = (static_cast<long long>(cell) * opt::RADFIELDBINCOUNT) + binindex;
+        est_atomic_add(&T.est_bins_J_raw[mgibinindex], distance_e_cmf);
+        est_atomic_add(&T.est_bins_nuJ_raw[mgibinindex], distance_e_cmf * nu_cmf);
+        c.work<DIAG_ESTIMATOR_ADDS>(2);
+      }
+    }
+  }
   est_atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
   c.work<DIAG_ESTIMATOR_ADDS>(1);
 

@@ -97,7 +97,9 @@ namespace ab {
   X(float, ion_groundlevelpops, "cell.ion_groundlevelpops")           \
   X(float, ion_partfuncts, "cell.ion_partfuncts")                     \
   X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
-  X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")
+  X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
+  X(float, radfield_bin_W, "radfield.bin_W")                        \
+  X(float, radfield_bin_T_R, "radfield.bin_T_R")
 
 // X(type, member, "public name")   — scalars
 #define AB_INPUT_SCALARS(X)                                  \
@@ -125,6 +127,8 @@ namespace ab {
   X(double, est_dep_positron, "est.dep_positron") \
   X(double, est_dep_electron, "est.dep_electron") \
   X(double, est_dep_alpha, "est.dep_alpha")       \
+  X(double, est_bins_J_raw, "est.bins_J_raw")     \
+  X(double, est_bins_nuJ_raw, "est.bins_nuJ_raw") \
   X(double, ts_scalars, "ts.scalars")             \
   X(long long, ts_pellet_decays, "ts.pellet_decays") \
   X(long long, counters, "counters")              \

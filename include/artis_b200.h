@@ -47,9 +47,11 @@
  *   cell.rho/Te/TJ/TR/W/nne/nnetot/kappagrey/clumpfactor 'f'[Nc], cell.thick 'i'[Nc]        grid.h:19-36
  *   cell.elem_massfracs 'f'[Nc*nelements] grid.h:45   cell.ion_groundlevelpops/ion_partfuncts 'f'[Nc*Nion] grid.h:47-48
  *   cell.ion_cooling_contribs 'd'[Nc*Nion] kpkt.h:18  cell.corrphotoionrenorm 'd'[Nc*Ng] globals.h:124
+ *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132
  *   est.gamma/bfheating 'd'[Nc*Ng] globals.h:126-129   est.dep_gamma/dep_positron/dep_electron/dep_alpha 'd'[Nc] globals.h:118-121
+ *   est.bins_J_raw/bins_nuJ_raw 'd'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:63-70, 762-770
  *   ts.scalars 'd'[ARTISB200_NTSSCALARS] (order below; globals.h:73-113 and nonthermal.cc:200)   ts.pellet_decays 'q'
  *   counters 'q'[34]  (stats.h:14-50; INTERACTIONS is index 26)      diag 'q'[ARTISB200_NDIAG]
  */
@@ -159,7 +161,7 @@ int artisb200_update_packets_host(artisb200_ctx* ctx, int nts, void* packets_aos
 int artisb200_save_packets_device(artisb200_ctx* ctx);
 int artisb200_restore_packets_device(artisb200_ctx* ctx);
 
-/* One packed device buffer [J|nuJ|ffheating|colheating|gamma|bfheating|dep_*|ts.scalars] of f64 for the
+/* One packed device buffer [J|nuJ|ffheating|colheating|gamma|bfheating|dep_*|ts.scalars|bins_J_raw|bins_nuJ_raw] of f64 for the
  * per-timestep all-reduce (replaces the MPI_Allreduce calls at sn3d.cc:565-625 and radfield.cc:988-1030).
  * The caller (torch.distributed / NCCL) reduces it in place. */
 int artisb200_estimator_device_buffer(artisb200_ctx* ctx, void** device_ptr, int64_t* count_f64);

@@ -272,6 +272,13 @@ void emit_timestep_state(Sink& s, const int nts) {
         static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
   s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
         static_cast<int64_t>(globals::corrphotoionrenorm.size()));
+  if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
+    // fitted (W, T_R) of every frequency bin: radfield::radfield(nu, cell) reads them (radfield.cc:786-797)
+    const auto w = radfield::b200_bin_solutions_W();
+    const auto tr = radfield::b200_bin_solutions_T_R();
+    s.arr("radfield.bin_W", w.data(), static_cast<int64_t>(w.size()));
+    s.arr("radfield.bin_T_R", tr.data(), static_cast<int64_t>(tr.size()));
+  }
 }
 
 void fill_ts_scalars(const int nts, double* out) {
@@ -302,6 +309,12 @@ void emit_estimators(Sink& s, const int nts) {
   s.arr("est.dep_positron", globals::dep_estimator_positron.data(), static_cast<int64_t>(globals::dep_estimator_positron.size()));
   s.arr("est.dep_electron", globals::dep_estimator_electron.data(), static_cast<int64_t>(globals::dep_estimator_electron.size()));
   s.arr("est.dep_alpha", globals::dep_estimator_alpha.data(), static_cast<int64_t>(globals::dep_estimator_alpha.size()));
+  if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
+    const auto jraw = radfield::b200_bins_J_raw();
+    const auto nujraw = radfield::b200_bins_nuJ_raw();
+    s.arr("est.bins_J_raw", jraw.data(), static_cast<int64_t>(jraw.size()));
+    s.arr("est.bins_nuJ_raw", nujraw.data(), static_cast<int64_t>(nujraw.size()));
+  }
   double tss[ARTISB200_NTSSCALARS];
   fill_ts_scalars(nts, tss);
   s.arr("ts.scalars", tss, ARTISB200_NTSSCALARS);
@@ -462,6 +475,10 @@ void update_packets_gpu(const int nts, std::span<Packet> packets) {
   fetch_add<double>("est.dep_positron", globals::dep_estimator_positron);
   fetch_add<double>("est.dep_electron", globals::dep_estimator_electron);
   fetch_add<double>("est.dep_alpha", globals::dep_estimator_alpha);
+  if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
+    fetch_add<double>("est.bins_J_raw", radfield::b200_bins_J_raw());
+    fetch_add<double>("est.bins_nuJ_raw", radfield::b200_bins_nuJ_raw());
+  }
   double tss[ARTISB200_NTSSCALARS];
   check(lib.get_array(lib.ctx, "ts.scalars", 'd', tss, ARTISB200_NTSSCALARS), "ts.scalars");
   auto& ts = globals::timesteps[nts];

@@ -12,8 +12,10 @@ from artis_b200 import lib as ablib  # noqa: E402
 from artis_b200 import snapshot as snap  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-PRESET_OF = {"classic_toy": "classic", "classic_toy_1d": "classic", "classic3d_toy": "classic", "kilonova_toy": "kilonova_lte"}
-GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_toy": [0, 2], "kilonova_toy": [1, 4]}
+PRESET_OF = {"classic_toy": "classic", "classic_toy_1d": "classic", "classic3d_toy": "classic", "kilonova_toy": "kilonova_lte",
+             "classic_multibin_toy": "classic_multibin"}
+GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_toy": [0, 2], "kilonova_toy": [1, 4],
+                    "classic_multibin_toy": [2, 4]}
 INTERACTIONS = 26  # stats::Counter::INTERACTIONS (reference stats.h:41)
 
 

@@ -8,7 +8,7 @@ order-independent per-packet schedule (every packet driven through the reference
 RNG stream). The inputs of update_packets() (static tables, cell state, packets) and its outputs (packets,
 estimators, counters) are stored as
     tests/golden/<config>_static.npz, tests/golden/<config>_ts<N>.npz  (keys "before/<name>", "after/<name>")
-Usage: python tests/golden/make_golden.py   (needs `python __graft_entry__.py build` to have built oracle/_ref)
+Usage: python tests/golden/make_golden.py [config ...]   (needs `python __graft_entry__.py build` to have built oracle/_ref)
 """
 import os
 import sys
@@ -26,12 +26,16 @@ GOLDEN = {
     "classic_toy_1d": [0, 3],
     "classic3d_toy": [0, 2],
     "kilonova_toy": [1, 4],
+    "classic_multibin_toy": [2, 4],
 }
 
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]  # optional: regenerate just these configs
     for config, timesteps in GOLDEN.items():
+        if only and config not in only:
+            continue
         rundir = run_oracle.run(config, "parity", "ref_perpacket", ",".join(str(t) for t in timesteps))
         dump = os.path.join(rundir, "dump")
         static = snap.read_snapshot(os.path.join(dump, "static.abt"))

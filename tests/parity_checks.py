@@ -76,8 +76,12 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
         if n_fb == 0:
             assert int(est["counters"][fixtures.INTERACTIONS]) == int(after["counters"][fixtures.INTERACTIONS])
             assert np.array_equal(est["counters"], after["counters"]), "event counters differ from the reference"
-            for name in ("est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
-                         "est.dep_positron", "est.dep_electron", "est.dep_alpha"):
+            names = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
+                     "est.dep_positron", "est.dep_electron", "est.dep_alpha"]
+            if "est.bins_J_raw" in after:  # MULTIBIN_RADFIELD_MODEL_ON fixtures
+                assert "est.bins_J_raw" in est and after["est.bins_J_raw"].sum() > 0
+                names += ["est.bins_J_raw", "est.bins_nuJ_raw"]
+            for name in names:
                 assert est_err.get(name, 0.0) <= est_tol, f"{name}: {est_err[name]:.3e}"
             m = 9  # ts.scalars[9] (nt_energy_deposited) is file-static in the reference and not dumped
             scale = np.abs(after["ts.scalars"][:m]).max()
