@@ -113,19 +113,57 @@ AHD double nnion(const Tables& T, const int cell, const int element, const int i
          statw(T, T.ion_levelstart[u]);
 }
 
-// LTE (Boltzmann) level population with the MINPOP floor (ltepop.cc:395-423; NLTE populations not implemented)
+// Boltzmann factor of a level inside the superlevel of an ion with NLTE levels (nltepop.cc:1794-1806)
+AHD double superlevel_boltzmann(const Tables& T, const int cell, const int element, const int ion, const int level) {
+  const int uion = uniqueion(T, element, ion);
+  const int ustart = T.ion_levelstart[uion];
+  const int level_superlevel_start = T.ion_nlevels_excited_nlte[uion] + 1;
+  const double T_exc = opt::LTEPOP_EXCITATION_USE_TJ ? T.TJ[cell] : T.Te[cell];
+  const double E_level = epsilon(T, ustart + level);
+  const double E_superlevel = epsilon(T, ustart + level_superlevel_start);
+  return statw(T, ustart + level) / statw(T, ustart + level_superlevel_start) * exp(-(E_level - E_superlevel) / KB / T_exc);
+}
+
+// Level population with the MINPOP floor (ltepop.cc:168-199 calculate_levelpop_nominpop, 395-423): the NLTE solver's
+// population where the host has one (cell.nltepops: per-level slots and the superlevel slot of each NLTE ion,
+// nltepop.cc:1955-1968), else Boltzmann excitation from the ground level population.
 AHD double calculate_levelpop(const Tables& T, const int cell, const int element, const int ion, const int level) {
-  double nn;
+  double nn = 0.;
+  bool skipminpop = false;
+  bool have = false;
   const double nnground = groundlevelpop(T, cell, element, ion);
   if (level == 0) {
     nn = nnground;
-  } else {
+    have = true;
+  } else if constexpr (opt::HAS_NLTE_LEVELS) {
+    if (T.elem_has_nlte_levels[element] != 0) {
+      const int uion = uniqueion(T, element, ion);
+      const int nexc = T.ion_nlevels_excited_nlte[uion];
+      const long long base = (static_cast<long long>(cell) * T.total_nlte_levels) + T.ion_allnltelevelsindexstart[uion];
+      if (level <= nexc) {  // is_nlte (atomic.h:304)
+        const double nltepop_over_rho = T.nltepops[base + level - 1];
+        if (nltepop_over_rho >= 0.) {
+          nn = nltepop_over_rho * T.rho[cell];
+          skipminpop = true;
+          have = true;
+        }
+      } else if (T.ion_nlevels[uion] > (nexc + T.ion_nlevels_autoion[uion] + 1)) {  // ion_has_superlevel (atomic.h:448)
+        const double superlevelpop_over_rho = T.nltepops[base + nexc];
+        if (superlevelpop_over_rho >= 0.) {
+          nn = superlevelpop_over_rho * T.rho[cell] * superlevel_boltzmann(T, cell, element, ion, level);
+          skipminpop = true;
+          have = true;
+        }
+      }
+    }
+  }
+  if (!have) {
     const auto T_exc = opt::LTEPOP_EXCITATION_USE_TJ ? T.TJ[cell] : T.Te[cell];
     const int ustart = levelstart(T, element, ion);
     const double E_aboveground = epsilon(T, ustart + level) - epsilon(T, ustart);
     nn = (nnground * statw(T, ustart + level) / statw(T, ustart) * exp(-E_aboveground / KB / T_exc));
   }
-  if (nn < opt::MINPOP) {
+  if (!skipminpop && nn < opt::MINPOP) {
     if (elem_massfrac(T, cell, element) > 0) {
       return opt::MINPOP;
     }

@@ -424,6 +424,21 @@ class Engine {
         ion_index[e_start[e] + i] = i;
       }
     }
+    std::vector<int> elem_has_nlte(T.nelements, 0);
+    if (const auto* i_nexc = host<int>("ion.nlevels_excited_nlte"); i_nexc != nullptr) {
+      for (int u = 0; u < T.nions; u++) {
+        if (i_nexc[u] > 0) {
+          elem_has_nlte[ion_element[u]] = 1;
+        }
+      }
+    }
+    if constexpr (opt::HAS_NLTE_LEVELS) {
+      if (count_of("ion.nlevels_excited_nlte") != T.nions || count_of("ion.allnltelevelsindexstart") != T.nions ||
+          count_of("ion.nlevels_autoion") != T.nions) {
+        return fail("commit_static: ion.nlevels_excited_nlte / allnltelevelsindexstart / nlevels_autoion are required "
+                    "by a preset with NLTE levels");
+      }
+    }
     std::vector<int> level_uniqueion(T.nlevels, -1);
     for (int u = 0; u < T.nions; u++) {
       for (int l = 0; l < i_nlevels[u]; l++) {
@@ -468,6 +483,7 @@ class Engine {
     }
     if (!make_derived("derived.ion_element", ion_element, &T.ion_element) ||
         !make_derived("derived.ion_index", ion_index, &T.ion_index) ||
+        !make_derived("derived.elem_has_nlte_levels", elem_has_nlte, &T.elem_has_nlte_levels) ||
         !make_derived("derived.level_uniqueion", level_uniqueion, &T.level_uniqueion)) {
       return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
     }
@@ -571,6 +587,13 @@ class Engine {
       if (count_of(name) < 0) {
         return fail(std::string("begin_timestep: per-timestep array '") + name + "' has not been set");
       }
+    }
+    if constexpr (opt::HAS_NLTE_LEVELS) {
+      const int64_t n = count_of("cell.nltepops");
+      if (n <= 0 || (n % T.ncells) != 0) {
+        return fail("begin_timestep: cell.nltepops must hold ncells x total_nlte_levels entries (preset with NLTE levels)");
+      }
+      T.total_nlte_levels = static_cast<int>(n / T.ncells);
     }
     if constexpr (opt::MULTIBIN_RADFIELD_MODEL_ON) {
       const int64_t want = static_cast<int64_t>(T.ncells) * opt::RADFIELDBINCOUNT;

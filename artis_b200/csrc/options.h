@@ -64,7 +64,6 @@ constexpr int GTS_GUTTMAN = 3;
 // modes of the reference that this library does not implement yet fail at compile time rather than silently
 static_assert(!DETAILED_BF_ESTIMATORS_ON, "DETAILED_BF_ESTIMATORS_ON (NLTE presets) is not implemented yet");
 static_assert(!NT_SOLVE_SPENCERFANO, "Spencer-Fano non-thermal routing is not implemented yet");
-static_assert(!HAS_NLTE_LEVELS, "NLTE level populations are not implemented yet");
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,
               "expansion-opacity r-packet modes are not implemented yet");
 static_assert(!USE_XCOM_GAMMAPHOTOION, "XCOM gamma photoionisation tables are not implemented yet");

@@ -33,6 +33,7 @@ namespace ab {
   X(int, ion_groundcontindex, "ion.groundcontindex")                  \
   X(int, ion_nlevels_excited_nlte, "ion.nlevels_excited_nlte")        \
   X(int, ion_allnltelevelsindexstart, "ion.allnltelevelsindexstart")  \
+  X(int, ion_nlevels_autoion, "ion.nlevels_autoion")                  \
   X(double, ion_ionpot, "ion.ionpot")                                 \
   X(double, level_epsilon, "level.epsilon")                           \
   X(float, level_statweight, "level.statweight")                      \
@@ -98,6 +99,7 @@ namespace ab {
   X(float, ion_partfuncts, "cell.ion_partfuncts")                     \
   X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
   X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
+  X(double, nltepops, "cell.nltepops")                              \
   X(float, radfield_bin_W, "radfield.bin_W")                        \
   X(float, radfield_bin_T_R, "radfield.bin_T_R")
 
@@ -295,6 +297,7 @@ struct Tables {
   int nphixstargets_total;
   int ncoolingterms;
   int ntimesteps;
+  int total_nlte_levels;  // NLTE level slots per cell in cell.nltepops (globals.h:356)
   int matrans_total;   // sum over levels of (2*ndown + nup)
   int keepwords;       // ceil(nbfcontinua / 64)
   int log2_nbf;        // probes of one binary search over the continuum list
@@ -311,6 +314,7 @@ struct Tables {
   const int* level_uniqueion;   // [nlevels] unique ion index of each level
   const int* ion_element;       // [nions]
   const int* ion_index;         // [nions] ion index within its element
+  const int* elem_has_nlte_levels;  // [nelements]
   const ContStatic* cont_static;  // [nbfcontinua]
   CellCont* cell_cont_pack;       // [ncells][nbfcontinua], written by the per-cell table build
 

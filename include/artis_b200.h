@@ -31,7 +31,7 @@
  *   cell.ffegrp 'f'[Nc]                  grid.cc:110 via get_ffegrp(mgi)
  *   elem.anumber/nions/lowest_ionstage/uniqueionindexstart 'i'[nelements]            globals.h:59-66
  *   ion.nlevels/nlevels_ionising/maxrecombininglevel/coolingoffset/ncoolingterms/uniquelevelindexstart/
- *       groundcontindex/nlevels_excited_nlte/allnltelevelsindexstart 'i'[Nion], ion.ionpot 'd'  globals.h:44-57
+ *       groundcontindex/nlevels_excited_nlte/allnltelevelsindexstart/nlevels_autoion 'i'[Nion], ion.ionpot 'd'  globals.h:44-57
  *   level.epsilon 'd', level.statweight 'f', level.alltrans_startdown/ndowntrans/nuptrans/closestgroundlevelcont/
  *       phixsstart/nphixstargets/phixstargetstart/bflist_start/matransblock_start 'i'[Nlev]      globals.h:173-216
  *   trans.lineindex/targetlevelindex 'i', trans.einstein_A/coll_str/osc_strength 'f', trans.forbidden 'B'  globals.h:148-155
@@ -47,6 +47,8 @@
  *   cell.rho/Te/TJ/TR/W/nne/nnetot/kappagrey/clumpfactor 'f'[Nc], cell.thick 'i'[Nc]        grid.h:19-36
  *   cell.elem_massfracs 'f'[Nc*nelements] grid.h:45   cell.ion_groundlevelpops/ion_partfuncts 'f'[Nc*Nion] grid.h:47-48
  *   cell.ion_cooling_contribs 'd'[Nc*Nion] kpkt.h:18  cell.corrphotoionrenorm 'd'[Nc*Ng] globals.h:124
+ *   cell.nltepops 'd'[Nc*total_nlte_levels]  (presets with ION_NLEVELS_EXCITED_NLTE > 0 only) nltepop.h:15, read by
+ *       calculate_levelpop (ltepop.cc:168-199) through nltepop.cc:1955-1968
  *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132

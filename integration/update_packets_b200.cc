@@ -52,6 +52,7 @@
 #include "grid.h"
 #include "kpkt.h"
 #include "mpi_logging.h"
+#include "nltepop.h"
 #include "nonthermal.h"
 #include "packet.h"
 #include "radfield.h"
@@ -110,6 +111,7 @@ void emit_static(Sink& s) {
   std::vector<int> i_groundcontindex(nions);
   std::vector<int> i_nlevels_nlte(nions);
   std::vector<int> i_nltestart(nions);
+  std::vector<int> i_nlevels_autoion(nions);
   std::vector<double> i_ionpot(nions);
   for (int element = 0; element < nelements; element++) {
     const auto& el = globals::elements[element];
@@ -129,6 +131,7 @@ void emit_static(Sink& s) {
       i_groundcontindex[u] = io.groundcontindex;
       i_nlevels_nlte[u] = io.nlevels_excited_nlte;
       i_nltestart[u] = io.allnltelevelsindexstart;
+      i_nlevels_autoion[u] = io.nlevels_autoion;
       i_ionpot[u] = io.ionpot;
     }
   }
@@ -145,6 +148,7 @@ void emit_static(Sink& s) {
   s.arr("ion.groundcontindex", i_groundcontindex.data(), nions);
   s.arr("ion.nlevels_excited_nlte", i_nlevels_nlte.data(), nions);
   s.arr("ion.allnltelevelsindexstart", i_nltestart.data(), nions);
+  s.arr("ion.nlevels_autoion", i_nlevels_autoion.data(), nions);
   s.arr("ion.ionpot", i_ionpot.data(), nions);
 
   // levels
@@ -272,6 +276,10 @@ void emit_timestep_state(Sink& s, const int nts) {
         static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
   s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
         static_cast<int64_t>(globals::corrphotoionrenorm.size()));
+  if (globals::total_nlte_levels > 0) {
+    // NLTE solver populations over rho, one slot per NLTE level and superlevel (nltepop.h:15, nltepop.cc:1955-1968)
+    s.arr("cell.nltepops", nltepops_allcells.data(), static_cast<int64_t>(nltepops_allcells.size()));
+  }
   if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
     // fitted (W, T_R) of every frequency bin: radfield::radfield(nu, cell) reads them (radfield.cc:786-797)
     const auto w = radfield::b200_bin_solutions_W();

@@ -27,6 +27,7 @@ GOLDEN = {
     "classic3d_toy": [0, 2],
     "kilonova_toy": [1, 4],
     "classic_multibin_toy": [2, 4],
+    "classic_nlte_toy": [2, 4],
 }
 
 

@@ -66,6 +66,17 @@ CONFIGS = {
         model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
         run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=5, thick=8.0, ngrey=2, nlte_ts=1),
     ),
+    # classic_toy_1d with three NLTE excited levels (+ superlevel) in Fe II: the hot path reads the NLTE solver's populations
+    "classic_nlte_toy": dict(
+        preset="classic",
+        opts=_opts(1500, None, None, {
+            "constexpr int ION_NLEVELS_EXCITED_NLTE": "constexpr int ION_NLEVELS_EXCITED_NLTE(int element_z, int ionstage) "
+                                                      "{ return (element_z == 26 && ionstage == 2) ? 3 : 0; }",
+        }),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=5, thick=8.0, ngrey=2, nlte_ts=1),
+    ),
     "kilonova_toy": dict(
         preset="kilonova_lte",
         opts=_opts(1000, None, None, {
