@@ -1,13 +1,19 @@
 // CUDA backend (sm_100a) and C ABI of the B200 packet-propagation library.
 //
-// Kernels
-//   k_propagate        one thread per packet history, persistent grid (a multiple of the SM count) with a
-//                      per-thread dynamic work fetch so that lanes whose packet finishes early pick up the next
-//                      one; event counters / timestep scalars are accumulated thread-privately, reduced per block
-//                      in shared memory and flushed with one global atomic per block and counter.
-//   k_build_*          the per-cell tables (level populations, continuum keep-bitmaps, macro-atom cumulative
+// Kernels (DESIGN.md section 4)
+//   k_wf_stage<STAGE>  the wavefront schedule: one persistent-grid kernel per packet stage (other | r-packet detailed |
+//                      r-packet grey | macro-atom) and iteration; warps fetch 32-packet chunks of the stage's index
+//                      list, each thread runs the stage once for its packet and appends it to the list of the stage it
+//                      waits in next. k_wf_seed / k_wf_advance / k_wf_ma_swap keep the double-buffered lists.
+//   k_sort_* / k_list_*  counting sort of the packets (or of the running lists) by (stage, model cell), with
+//                      warp-aggregated bucket atomics.
+//   k_propagate        one thread per packet history (warp phase machine): finishes the thin tail of the wavefront and
+//                      is the schedule=0 comparison point.
+//   k_build_*          the per-cell tables (level populations, continuum keep-bitmaps and records, macro-atom cumulative
 //                      rates, cooling contributions): one work item per (cell, level | ion | 64 continua).
-//   k_aos_to_soa / k_soa_to_aos   the reference's 240/256-byte Packet <-> SoA.
+//   k_aos_to_soa / k_soa_to_aos   the reference's 240/256-byte Packet <-> device records.
+// Event counters are kept in registers (hot ones) and block-shared accumulators, flushed with one global atomic per
+// block and non-zero entry; estimator adds are warp-aggregated (hd.h est_atomic_add).
 // There is no host execution path in this library: artisb200_create() fails without a CUDA device.
 #include <cuda_runtime.h>
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from artis_b200 import lib as ablib
-from tests import fixtures, parity_checks, stochastic_checks
+from tests import abi_checks, fixtures, parity_checks, stochastic_checks
 
 pytestmark = pytest.mark.gpu
 CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
@@ -151,6 +151,10 @@ def test_energy_bookkeeping():
     emitted = est["ts.scalars"][[2, 4, 6, 7, 8]].sum()  # positron, electron, alpha emission, spfission, gamma emission
     assert abs(emitted - before["e_cmf"][decayed].sum()) / max(emitted, 1e-300) < 1e-12
     assert int(est["ts.pellet_decays"][0]) == int(np.count_nonzero(decayed))
+
+
+def test_abi_reports_misuse():
+    abi_checks.check_abi_errors(_lib("classic_toy_1d"))
 
 
 def test_errors_are_reported_not_swallowed():

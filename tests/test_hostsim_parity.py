@@ -6,7 +6,7 @@ and deterministic helper is checked against the compiled reference before GPU ti
 assertions run against the real CUDA library on the B200 in tests/test_gpu_parity.py."""
 import pytest
 
-from tests import fixtures, parity_checks, stochastic_checks
+from tests import abi_checks, fixtures, parity_checks, stochastic_checks
 
 CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
 
@@ -49,3 +49,12 @@ def test_stochastic_parity_ks_and_estimators(config, nts):
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
     report = stochastic_checks.check_stochastic_parity(lib, config, nts, K=5)
     assert report["n_rpkt_ref"] > 0
+
+
+def test_abi_reports_misuse():
+    abi_checks.check_abi_errors(fixtures.hostsim_library("classic"))
+
+
+@pytest.mark.parametrize("preset", ["classic", "kilonova_lte", "classic_multibin", "classic_nlte"])
+def test_options_summary_names_the_preset(preset):
+    abi_checks.check_options_summary(fixtures.hostsim_library(preset), preset)
