@@ -23,6 +23,7 @@ import os
 import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,7 +37,8 @@ BENCH_TS = int(os.environ.get("ARTISB200_BENCH_TS", "2"))
 CPU_SAMPLE_CONFIG = os.environ.get("ARTISB200_BENCH_CPU_CONFIG", "kilonova_2d_cpu")
 FLAVOR = os.environ.get("ARTISB200_BENCH_FLAVOR", "fast")
 CPU_FLAVOR = os.environ.get("ARTISB200_BENCH_CPU_FLAVOR", "fast")
-CACHE = os.environ.get("ARTISB200_BENCH_CACHE", os.path.join(ROOT, "gpurun_out", "bench_cache"))
+# several GB of snapshots and run folders: outside the repository tree
+CACHE = os.environ.get("ARTISB200_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "artis_b200_bench_cache"))
 INTERACTIONS = 26
 
 
