@@ -42,6 +42,7 @@ int artisb200_create(artisb200_ctx** out, const int device_ordinal) {
 
 void artisb200_destroy(artisb200_ctx* ctx) {
   if (ctx != nullptr) {
+    ctx->eng.release();
     ctx->eng.be.shutdown();
     delete ctx;
   }

@@ -185,6 +185,47 @@ class Engine {
     return 1;
   }
 
+  // release every device allocation this context owns (artisb200_destroy)
+  void release() {
+    for (auto& [name, rec] : arrays) {
+      if (rec.dptr != nullptr && rec.owned) {
+        be.free(rec.dptr);
+      }
+      rec.dptr = nullptr;
+    }
+    arrays.clear();
+    if (estimator_pack != nullptr) {
+      be.free(estimator_pack);
+      estimator_pack = nullptr;
+    }
+#define X(type, name)          \
+  if (T.pkt.name != nullptr) { \
+    be.free(T.pkt.name);       \
+    T.pkt.name = nullptr;      \
+  }
+    AB_PACKET_ARRAYS(X)
+#undef X
+    if (T.scratch_groundcont != nullptr) {
+      be.free(T.scratch_groundcont);
+      T.scratch_groundcont = nullptr;
+    }
+    if (aos_staging != nullptr) {
+      be.free(aos_staging);
+      aos_staging = nullptr;
+    }
+    for (void* ptr : soa_save) {
+      be.free(ptr);
+    }
+    soa_save.clear();
+    packet_capacity = 0;
+    scratch_capacity = 0;
+    aos_staging_bytes = 0;
+    soa_save_count = 0;
+    outputs_allocated = false;
+    static_committed = false;
+    timestep_begun = false;
+  }
+
   static bool keep_hostcopy(const std::string& name) {
     return name.rfind("elem.", 0) == 0 || name.rfind("ion.", 0) == 0 || name.rfind("level.", 0) == 0 || name.rfind("cont.", 0) == 0 ||
            name.rfind("timesteps.", 0) == 0 || name == "lut.temperature_grid";
