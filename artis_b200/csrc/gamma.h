@@ -310,13 +310,95 @@ AHD void transport_gamma(Pkt& p, const Ctx& c, const double t2) {
 }
 
 // gammapkt.cc:911-938 (FREQUENCYDEPENDENT scheme)
+// ---- parameterised gamma-ray thermalisation schemes (gammapkt.cc:752-858): no transport, the packet is absorbed
+// on the spot with probability f_gamma or escapes -------------------------------------------------------------------
+AHD void absorb_or_escape_gamma(Pkt& p, const Ctx& c, const double f_gamma) {  // gammapkt.cc:754-771
+  if (p.rng.uniform() < f_gamma) {
+    p.type = TYPE_NTLEPTON_DEPOSITED;
+    c.T.pkt.absorptiontype[c.ip] = ABSTYPE_GAMMA_PHOTOELECTRIC;
+  } else {
+    change_cell_or_escape(p, c, -99);
+  }
+}
+
+// optical depth mean_gamma_opac * int rho dl along a ray from the packet to the edge of the grid, with the density of
+// each cell taken at the time the ray reaches it (gammapkt.cc:794-826, 838-853); the ray is a copy of the packet
+AHD double gamma_ray_tau_to_edge(const Tables& T, const Pkt& p, const double* raydir, const double mean_gamma_opac) {
+  Pkt ray = p;
+  ray.dir[0] = raydir[0];
+  ray.dir[1] = raydir[1];
+  ray.dir[2] = raydir[2];
+  double tau = 0.;
+  while (ray.type != TYPE_ESCAPE) {
+    const BoundaryHit hit = boundary_distance(T, ray.dir, ray.pos, ray.prop_time, ray.cellindex);
+    const int cell = T.propcell_nonemptymgi[ray.cellindex];
+    if (cell >= 0) {
+      const double rho = T.rho_tmin[cell] * pow3(T.tmin / ray.prop_time);
+      tau += mean_gamma_opac * rho * hit.distance;
+    }
+    move_pkt_withtime(ray, hit.distance);
+    // grid.h:114-137 with tally_stats = false: no counters, nothing recorded for the copy
+    if (hit.next_cellindex >= 0) {
+      if (hit.next_cellindex != ray.cellindex) {
+        snap_pos_to_cell(T, ray.pos, ray.prop_time, hit.next_cellindex);
+      }
+      ray.cellindex = hit.next_cellindex;
+    } else {
+      ray.type = TYPE_ESCAPE;
+    }
+  }
+  return tau;
+}
+
+AHD void barnes_thermalisation(Pkt& p, const Ctx& c) {  // gammapkt.cc:777-792
+  const Tables& T = c.T;
+  const double v_ej = sqrt(T.ejecta_kinetic_energy * 2 / T.mtot_input);
+  const double t_ineff = 1.4 * DAY * sqrt(T.mtot_input / (5.e-3 * MSUN)) * ((0.2 * CLIGHT) / v_ej);
+  const double tau = pow2(t_ineff / p.prop_time);
+  absorb_or_escape_gamma(p, c, 1. - exp(-tau));
+}
+
+AHD void wollaeger_thermalisation(Pkt& p, const Ctx& c) {  // gammapkt.cc:794-826
+  double radial[3];
+  vec_norm3(p.pos, radial);
+  const double tau = gamma_ray_tau_to_edge(c.T, p, radial, 0.1);
+  absorb_or_escape_gamma(p, c, 1. - exp(-tau));
+}
+
+AHD void guttman_thermalisation(Pkt& p, const Ctx& c) {  // gammapkt.cc:828-858
+  constexpr int num_directions = 100;
+  double deposition_probability_sum = 0.;
+  for (int i = 0; i < num_directions; i++) {
+    double raydir[3];
+    rand_isotropic_unitvec(p.rng, raydir);
+    const double tau = gamma_ray_tau_to_edge(c.T, p, raydir, 0.03);
+    deposition_probability_sum -= expm1(-tau);
+  }
+  absorb_or_escape_gamma(p, c, deposition_probability_sum / num_directions);
+}
+
+// gammapkt.cc:911-938
 AHD void do_gamma(Pkt& p, const Ctx& c, const double t2) {
-  static_assert(opt::GAMMA_THERMALISATION_SCHEME == opt::GTS_FREQUENCYDEPENDENT,
-                "only the FREQUENCYDEPENDENT gamma-ray scheme is implemented");
-  transport_gamma(p, c, t2);
+  if constexpr (opt::GAMMA_THERMALISATION_SCHEME == opt::GTS_FREQUENCYDEPENDENT) {
+    transport_gamma(p, c, t2);
+  } else if constexpr (opt::GAMMA_THERMALISATION_SCHEME == opt::GTS_BARNES) {
+    barnes_thermalisation(p, c);
+  } else if constexpr (opt::GAMMA_THERMALISATION_SCHEME == opt::GTS_WOLLAEGER) {
+    wollaeger_thermalisation(p, c);
+  } else {
+    guttman_thermalisation(p, c);
+  }
   if (p.type != TYPE_GAMMA && p.type != TYPE_ESCAPE) {
     if constexpr (opt::PARTICLE_THERMALISATION_SCHEME != opt::PTS_TIMEDEPENDENTWITHGAMMAPRODUCTS) {
       c.add_ts(TS_GAMMA_DEP_DISCRETE, p.e_cmf);
+    }
+    if constexpr (opt::GAMMA_THERMALISATION_SCHEME != opt::GTS_FREQUENCYDEPENDENT) {
+      // no transport, so the path-based deposition estimator is fed here (empty cells have none)
+      const int cell = c.T.propcell_nonemptymgi[p.cellindex];
+      if (cell >= 0) {
+        atomic_add(&c.T.est_dep_gamma[cell], p.e_cmf);
+        c.work<DIAG_ESTIMATOR_ADDS>();
+      }
     }
   }
 }

@@ -67,8 +67,7 @@ static_assert(!NT_SOLVE_SPENCERFANO, "Spencer-Fano non-thermal routing is not im
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,
               "expansion-opacity r-packet modes are not implemented yet");
 static_assert(!USE_XCOM_GAMMAPHOTOION, "XCOM gamma photoionisation tables are not implemented yet");
-static_assert(GAMMA_THERMALISATION_SCHEME == GTS_FREQUENCYDEPENDENT,
-              "only the FREQUENCYDEPENDENT gamma-ray scheme is implemented");
-static_assert(PARTICLE_THERMALISATION_SCHEME != PTS_BARNES, "the BARNES particle scheme is not implemented");
+static_assert(GAMMA_THERMALISATION_SCHEME >= GTS_FREQUENCYDEPENDENT && GAMMA_THERMALISATION_SCHEME <= GTS_GUTTMAN,
+              "unknown gamma-ray thermalisation scheme");
 static_assert(!NT_ON, "NT_ON presets are not implemented yet");
 }  // namespace opt

@@ -80,10 +80,21 @@ AHD void do_nonthermal_predeposit(Pkt& p, const Ctx& c, const double ts_end) {
   const double ts = p.prop_time;
   const int deposit_type = (p.type == TYPE_NONTHERMAL_PREDEPOSIT_ALPHA) ? TYPE_NTALPHA_FISPROD_DEPOSITED : TYPE_NTLEPTON_DEPOSITED;
   constexpr int scheme = opt::PARTICLE_THERMALISATION_SCHEME;
-  static_assert(scheme != opt::PTS_BARNES, "the BARNES particle thermalisation scheme is not implemented");
 
   if constexpr (scheme == opt::PTS_INSTANTFULLDEPOSITION) {
     p.type = deposit_type;
+  } else if constexpr (scheme == opt::PTS_BARNES) {
+    // update_packets.cc:68-76
+    const double v_ej = sqrt(T.ejecta_kinetic_energy * 2 / T.mtot_input);
+    const double prefactor = (p.type == TYPE_NONTHERMAL_PREDEPOSIT_ALPHA) ? 7.74 : 7.4;
+    const double tau_ineff = prefactor * DAY * sqrt(T.mtot_input / (5.e-3 * MSUN)) * pow((0.2 * CLIGHT) / v_ej, 3. / 2.);
+    const double f_p = log1p(2. * ts * ts / tau_ineff / tau_ineff) / (2. * ts * ts / tau_ineff / tau_ineff);
+    if (p.rng.uniform() < f_p) {
+      p.type = deposit_type;
+    } else {
+      e_cmf_deposited = 0.;
+      change_cell_or_escape(p, c, -99);
+    }
   } else if constexpr (scheme == opt::PTS_WOLLAEGER) {
     const double A = (p.type == TYPE_NONTHERMAL_PREDEPOSIT_ALPHA) ? 1.2 * 1.e-11 : 1.3 * 1.e-11;
     const double aux_term = 2 * A / (ts * T.rho[cell]);

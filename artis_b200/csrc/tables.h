@@ -20,6 +20,7 @@ namespace ab {
   X(double, coord2, "grid.coord_pos_min_tmin2")                       \
   X(int, propcell_nonemptymgi, "grid.propcell_nonemptymgi")           \
   X(float, ffegrp, "cell.ffegrp")                                     \
+  X(float, rho_tmin, "cell.rho_tmin")                                 \
   X(int, elem_anumber, "elem.anumber")                                \
   X(int, elem_nions, "elem.nions")                                    \
   X(int, elem_lowest_ionstage, "elem.lowest_ionstage")                \
@@ -115,7 +116,9 @@ namespace ab {
   X(long long, tablesize, "scalar.tablesize")                \
   X(long long, nts_host, "scalar.nts")                       \
   X(long long, globals_timestep, "scalar.globals_timestep")  \
-  X(double, max_path_step, "scalar.max_path_step")
+  X(double, max_path_step, "scalar.max_path_step")          \
+  X(double, ejecta_kinetic_energy, "scalar.ejecta_kinetic_energy") \
+  X(double, mtot_input, "scalar.mtot_input")
 
 // device-side output / work arrays that can be read back with artisb200_get_array()
 #define AB_OUTPUT_ARRAYS(X)                       \

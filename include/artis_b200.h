@@ -29,6 +29,8 @@
  *  static tables
  *   grid.coord_pos_min_tmin{0,1,2} 'd'   grid.cc:82        grid.propcell_nonemptymgi 'i'[ngrid] grid.cc:87
  *   cell.ffegrp 'f'[Nc]                  grid.cc:110 via get_ffegrp(mgi)
+ *   cell.rho_tmin 'f'[Nc] grid.h:57, scalar.ejecta_kinetic_energy 'd' grid.h:139, scalar.mtot_input 'd' grid.h:40
+ *       (only read by the BARNES / WOLLAEGER / GUTTMAN thermalisation schemes)
  *   elem.anumber/nions/lowest_ionstage/uniqueionindexstart 'i'[nelements]            globals.h:59-66
  *   ion.nlevels/nlevels_ionising/maxrecombininglevel/coolingoffset/ncoolingterms/uniquelevelindexstart/
  *       groundcontindex/nlevels_excited_nlte/allnltelevelsindexstart/nlevels_autoion 'i'[Nion], ion.ionpot 'd'  globals.h:44-57

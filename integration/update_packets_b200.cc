@@ -94,6 +94,14 @@ void emit_static(Sink& s) {
     ffegrp[nonemptymgi] = grid::get_ffegrp(grid::get_mgi_of_nonemptymgi(nonemptymgi));
   }
   s.arr("cell.ffegrp", ffegrp.data(), nc);
+  // inputs of the parameterised thermalisation schemes (gammapkt.cc:777-858, update_packets.cc:68-76)
+  std::vector<float> rho_tmin(nc);
+  for (int nonemptymgi = 0; nonemptymgi < nc; nonemptymgi++) {
+    rho_tmin[nonemptymgi] = grid::get_rho_tmin(grid::get_mgi_of_nonemptymgi(nonemptymgi));
+  }
+  s.arr("cell.rho_tmin", rho_tmin.data(), nc);
+  s.f64("scalar.ejecta_kinetic_energy", grid::get_ejecta_kinetic_energy());
+  s.f64("scalar.mtot_input", grid::mtot_input);
 
   // elements and ions
   const int nelements = get_nelements();

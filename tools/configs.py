@@ -88,6 +88,21 @@ CONFIGS = {
         model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
         run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
     ),
+    # kilonova_toy with the parameterised thermalisation schemes (gammapkt.cc:752-858, update_packets.cc:57-84)
+    **{f"kilonova_{tag}_toy": dict(
+        preset="kilonova_lte",
+        opts=_opts(1000, None, None, {
+            "constexpr int TABLESIZE": "constexpr int TABLESIZE = 20;",
+            "constexpr double MINTEMP": "constexpr double MINTEMP = 1000.;",
+            "constexpr double MAXTEMP": "constexpr double MAXTEMP = 20000.;",
+            "constexpr auto GAMMA_THERMALISATION_SCHEME": f"constexpr auto GAMMA_THERMALISATION_SCHEME = GammaThermalisationScheme::{gam};",
+            "constexpr auto PARTICLE_THERMALISATION_SCHEME": f"constexpr auto PARTICLE_THERMALISATION_SCHEME = ParticleThermalisationScheme::{par};",
+        }),
+        atomic=dict(elements=_KN_ELEMS, nions=3, nlevels=8, trans_frac=0.6, seed=2),
+        model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
+        run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
+    ) for tag, gam, par in (("guttman", "GUTTMAN", "BARNES"), ("wollaeger", "WOLLAEGER", "WOLLAEGER"),
+                            ("barnes", "BARNES", "INSTANTFULLDEPOSITION"))},
     "classic3d_toy": dict(
         preset="classic",
         opts=_opts(1500),
