@@ -172,6 +172,85 @@ AHD double calculate_levelpop(const Tables& T, const int cell, const int element
   return nn;
 }
 
+// ---- non-thermal ionisation channels (nonthermal.cc:2398-2474) on the per-cell state handed over by the host ----
+AHD int nt_ionisation_maxupperion(const Tables& T, const int element, const int lowerion) {
+  int maxupper = lowerion + 1;
+  if constexpr (opt::NT_SOLVE_SPENCERFANO) {
+    maxupper += opt::NT_MAX_AUGER_ELECTRONS;
+  }
+  const int top = nions_of(T, element) - 1;
+  return (top < maxupper) ? top : maxupper;
+}
+
+AHD double nt_ionisation_upperion_probability(const Tables& T, const int cell, const int element, const int lowerion,
+                                              const int upperion, const bool energyweighted) {
+  if constexpr (opt::NT_SOLVE_SPENCERFANO && opt::NT_MAX_AUGER_ELECTRONS > 0) {
+    constexpr int NA = opt::NT_MAX_AUGER_ELECTRONS + 1;
+    const int numaugerelec = upperion - lowerion - 1;
+    const float* probs = (energyweighted ? T.nt_ionenfrac_num_auger : T.nt_prob_num_auger) +
+                         (((static_cast<long long>(cell) * T.nions) + uniqueion(T, element, lowerion)) * NA);
+    if (numaugerelec < opt::NT_MAX_AUGER_ELECTRONS) {
+      return probs[numaugerelec];
+    }
+    if (numaugerelec == opt::NT_MAX_AUGER_ELECTRONS) {
+      double prob_remaining = 1.;
+      for (int a = 0; a < opt::NT_MAX_AUGER_ELECTRONS; a++) {
+        prob_remaining -= probs[a];
+      }
+      return prob_remaining;
+    }
+    return 0.;
+  }
+  return (upperion == lowerion + 1) ? 1.0 : 0.;
+}
+
+AHD int nt_random_upperion(const Tables& T, const int cell, const int element, const int lowerion, const bool energyweighted,
+                           Rng& rng) {
+  if constexpr (opt::NT_SOLVE_SPENCERFANO && opt::NT_MAX_AUGER_ELECTRONS > 0) {
+    const double zrand = rng.uniform();
+    double prob_sum = 0.;
+    const int maxupper = nt_ionisation_maxupperion(T, element, lowerion);
+    for (int upperion = lowerion + 1; upperion <= maxupper; upperion++) {
+      prob_sum += nt_ionisation_upperion_probability(T, cell, element, lowerion, upperion, energyweighted);
+      if (zrand < prob_sum) {
+        return upperion;
+      }
+    }
+    return maxupper;
+  }
+  return lowerion + 1;
+}
+
+// ion to ionise, weighted by each ion's non-thermal ionisation energy rate; element = -1 if none (nonthermal.cc:1537-1566)
+AHD void select_nt_ionisation(const Tables& T, const int cell, Rng& rng, int& element_out, int& lowerion_out) {
+  element_out = -1;
+  lowerion_out = -1;
+  const double* energyrate = T.nt_ion_energyrate + (static_cast<long long>(cell) * T.nions);
+  double ratetotal = 0.;
+  for (int element = 0; element < T.nelements; element++) {
+    const int nions = nions_of(T, element);
+    for (int lowerion = 0; lowerion < nions - 1; lowerion++) {
+      ratetotal += energyrate[uniqueion(T, element, lowerion)];
+    }
+  }
+  if (!(ratetotal > 0.)) {
+    return;
+  }
+  const double zrand = rng.uniform();
+  double ratesum = 0.;
+  for (int element = 0; element < T.nelements; element++) {
+    const int nions = nions_of(T, element);
+    for (int lowerion = 0; lowerion < nions - 1; lowerion++) {
+      ratesum += energyrate[uniqueion(T, element, lowerion)];
+      if (ratesum > zrand * ratetotal) {
+        element_out = element;
+        lowerion_out = lowerion;
+        return;
+      }
+    }
+  }
+}
+
 AHD double cell_levelpop(const Tables& T, const int cell, const int ulev) {  // ltepop.h:58-65
   return T.cell_levelpops[(static_cast<long long>(cell) * T.nlevels) + ulev];
 }

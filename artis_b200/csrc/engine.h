@@ -78,12 +78,12 @@ inline std::string options_summary_string() {
   char buf[1024];
   std::snprintf(buf, sizeof(buf),
                 "preset=%s;POL_ON=%d;DIPOLE=%d;RELDOPPLER=%d;PHIXS_CLASSIC=%d;LUT_PHOTOION=%d;ION_BFHEAT=%d;"
-                "DETAILED_BF=%d;MULTIBIN=%d(%d bins from ts %d);DIRECT_COL_HEAT=%d;NT_ON=%d;TJ_EXC=%d;BFCOOL_LEVELPOP=%d;"
+                "DETAILED_BF=%d;MULTIBIN=%d(%d bins from ts %d);DIRECT_COL_HEAT=%d;NT_ON=%d(SF=%d);TJ_EXC=%d;BFCOOL_LEVELPOP=%d;"
                 "PARTICLE_SCHEME=%d;GAMMA_SCHEME=%d;MINPOP=%g;NU_MIN_R=%g;NU_MAX_R=%g",
                 ARTISB200_PRESET_NAME, opt::POL_ON, opt::DIPOLE, opt::USE_RELATIVISTIC_DOPPLER_SHIFT,
                 opt::PHIXS_CLASSIC_NO_INTERPOLATION, opt::USE_LUT_PHOTOION, opt::USE_ION_BFHEATING_ESTIMATORS,
                 opt::DETAILED_BF_ESTIMATORS_ON, opt::MULTIBIN_RADFIELD_MODEL_ON, opt::RADFIELDBINCOUNT,
-                opt::FIRST_NLTE_RADFIELD_TIMESTEP, opt::DIRECT_COL_HEAT, opt::NT_ON,
+                opt::FIRST_NLTE_RADFIELD_TIMESTEP, opt::DIRECT_COL_HEAT, opt::NT_ON, opt::NT_SOLVE_SPENCERFANO,
                 opt::LTEPOP_EXCITATION_USE_TJ, opt::BFCOOLING_USELEVELPOPNOTIONPOP, opt::PARTICLE_THERMALISATION_SCHEME,
                 opt::GAMMA_THERMALISATION_SCHEME, opt::MINPOP, opt::NU_MIN_R, opt::NU_MAX_R);
   return buf;
@@ -627,6 +627,15 @@ class Engine {
     for (const char* name : required) {
       if (count_of(name) < 0) {
         return fail(std::string("begin_timestep: per-timestep array '") + name + "' has not been set");
+      }
+    }
+    if constexpr (opt::NT_ON) {
+      constexpr int NA = opt::NT_MAX_AUGER_ELECTRONS + 1;
+      const int64_t ni = static_cast<int64_t>(T.ncells) * T.nions;
+      if (count_of("cell.nt_ionisation_ratecoeff") != ni || count_of("cell.nt_ion_energyrate") != ni ||
+          count_of("cell.nt_prob_num_auger") != ni * NA || count_of("cell.nt_ionenfrac_num_auger") != ni * NA ||
+          count_of("cell.nt_frac_ionisation") != T.ncells) {
+        return fail("begin_timestep: the cell.nt_* arrays (non-thermal routing state, NT_ON) are missing or have the wrong length");
       }
     }
     if constexpr (opt::HAS_NLTE_LEVELS) {

@@ -276,8 +276,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
         break;
       }
 
-      default: {  // MA_ACTION_INTERNALUPHIGHERNT: nt_random_upperion without Spencer-Fano gives ion + 1
-        ion = ion + 1;
+      default: {  // MA_ACTION_INTERNALUPHIGHERNT (macroatom.cc:562-568)
+        ion = nt_random_upperion(T, cell, element, ion, false, p.rng);
         level = 0;
         c.count<CNT_MA_STAT_INTERNALUPHIGHERNT>();
         break;

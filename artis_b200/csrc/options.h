@@ -25,6 +25,7 @@ constexpr bool DIRECT_COL_HEAT = ::DIRECT_COL_HEAT;
 constexpr bool NT_ON = ::NT_ON;
 constexpr bool NT_SOLVE_SPENCERFANO = ::NT_SOLVE_SPENCERFANO;
 constexpr bool NT_EXCITATION_ON = ::NT_EXCITATION_ON;
+constexpr int NT_MAX_AUGER_ELECTRONS = ::NT_MAX_AUGER_ELECTRONS;
 constexpr bool LTEPOP_EXCITATION_USE_TJ = ::LTEPOP_EXCITATION_USE_TJ;
 constexpr bool BFCOOLING_USELEVELPOPNOTIONPOP = ::BFCOOLING_USELEVELPOPNOTIONPOP;
 constexpr bool RPKT_USE_EXPANSION_OPACITIES = ::RPKT_USE_EXPANSION_OPACITIES;
@@ -63,11 +64,11 @@ constexpr int GTS_GUTTMAN = 3;
 
 // modes of the reference that this library does not implement yet fail at compile time rather than silently
 static_assert(!DETAILED_BF_ESTIMATORS_ON, "DETAILED_BF_ESTIMATORS_ON (NLTE presets) is not implemented yet");
-static_assert(!NT_SOLVE_SPENCERFANO, "Spencer-Fano non-thermal routing is not implemented yet");
+static_assert(!NT_EXCITATION_ON, "non-thermal excitation (NT_EXCITATION_ON) is not implemented yet");
+static_assert(!NT_SOLVE_SPENCERFANO || NT_ON, "NT_SOLVE_SPENCERFANO needs NT_ON");
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,
               "expansion-opacity r-packet modes are not implemented yet");
 static_assert(!USE_XCOM_GAMMAPHOTOION, "XCOM gamma photoionisation tables are not implemented yet");
 static_assert(GAMMA_THERMALISATION_SCHEME >= GTS_FREQUENCYDEPENDENT && GAMMA_THERMALISATION_SCHEME <= GTS_GUTTMAN,
               "unknown gamma-ray thermalisation scheme");
-static_assert(!NT_ON, "NT_ON presets are not implemented yet");
 }  // namespace opt

@@ -1,6 +1,7 @@
-// Hot-path subset of the reference preset artisoptions_classic.h (values restated).
+// artisoptions_classic.h with non-thermal deposition solved by Spencer-Fano (NT_ON, NT_SOLVE_SPENCERFANO): deposited
+// leptons are routed to non-thermal ionisation (nonthermal.cc:2529-2613), used by the classic_nt_toy parity case.
 #pragma once
-#define ARTISB200_PRESET_NAME "classic"
+#define ARTISB200_PRESET_NAME "classic_nt"
 namespace opt {
 constexpr bool POL_ON = true;
 constexpr bool DIPOLE = true;
@@ -16,8 +17,8 @@ constexpr double RADFIELDBINS_NU_MIN = 2.99792458e+10 / 40000e-8;
 constexpr double RADFIELDBINS_NU_MAX = 2.99792458e+10 / 1085e-8;
 constexpr double RADFIELDBINS_T_E_SUPERBIN_NU_MAX = 2.99792458e+10 / 10e-8;
 constexpr bool DIRECT_COL_HEAT = false;
-constexpr bool NT_ON = false;
-constexpr bool NT_SOLVE_SPENCERFANO = false;
+constexpr bool NT_ON = true;
+constexpr bool NT_SOLVE_SPENCERFANO = true;
 constexpr bool NT_EXCITATION_ON = false;
 constexpr int NT_MAX_AUGER_ELECTRONS = 2;
 constexpr bool LTEPOP_EXCITATION_USE_TJ = true;

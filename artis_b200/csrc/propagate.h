@@ -161,9 +161,44 @@ AHD void do_nonthermal_predeposit(Pkt& p, const Ctx& c, const double ts_end) {
   }
 }
 
-// nonthermal.cc:2520-2613 without the Spencer-Fano channels (NT_SOLVE_SPENCERFANO == false): all to heating
-AHD void do_nt_deposit(Pkt& p, const Ctx& c) {
+// nonthermal.cc:2520-2527: deposition by alpha particles and fission products is heating
+AHD void do_ntalpha_fisprod_deposit(Pkt& p, const Ctx& c) {
   c.add_ts(TS_NT_ENERGY_DEPOSITED, p.e_cmf);
+  p.type = TYPE_KPKT;
+  c.count<CNT_NT_STAT_TO_KPKT>();
+}
+
+// nonthermal.cc:2529-2613: a deposited lepton heats, or - with a Spencer-Fano solution, outside grey cells - ionises
+// an ion chosen by its share of the ionisation energy rate and activates a macro-atom in the ground level of the
+// resulting ion. (The excitation channel needs NT_EXCITATION_ON, which is a compile-time error here.)
+AHD void do_ntlepton_deposit(Pkt& p, const Ctx& c) {
+  const Tables& T = c.T;
+  c.add_ts(TS_NT_ENERGY_DEPOSITED, p.e_cmf);
+  if constexpr (opt::NT_ON && opt::NT_SOLVE_SPENCERFANO) {
+    const int cell = T.propcell_nonemptymgi[p.cellindex];
+    if (cell >= 0 && T.thick[cell] != CELL_THICK) {
+      const double zrand = p.rng.uniform();
+      const double frac_ionisation = T.nt_frac_ionisation[cell];
+      if (zrand < frac_ionisation) {
+        int element = -1;
+        int lowerion = -1;
+        select_nt_ionisation(T, cell, p.rng, element, lowerion);
+        if (lowerion >= 0) {
+          const int upperion = nt_random_upperion(T, cell, element, lowerion, true, p.rng);
+          c.count<CNT_MA_STAT_ACTIVATION_NTCOLLION>();
+          c.count<CNT_INTERACTIONS>();
+          T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;
+          set_trueem_pos_nan(c);
+          c.count<CNT_NT_STAT_TO_IONISATION>();
+          activate_macroatom(p, {element, upperion, 0, -99});
+          return;
+        }
+        p.type = TYPE_KPKT;  // no ion can be selected (zero deposition rate density): heat
+        c.count<CNT_NT_STAT_TO_KPKT>();
+        return;
+      }
+    }
+  }
   p.type = TYPE_KPKT;
   c.count<CNT_NT_STAT_TO_KPKT>();
 }
@@ -186,8 +221,10 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
       do_nonthermal_predeposit(p, c, t2);
       break;
     case TYPE_NTLEPTON_DEPOSITED:
+      do_ntlepton_deposit(p, c);
+      break;
     case TYPE_NTALPHA_FISPROD_DEPOSITED:
-      do_nt_deposit(p, c);
+      do_ntalpha_fisprod_deposit(p, c);
       break;
     case TYPE_PRE_KPKT:
       do_kpkt_blackbody(p, c);

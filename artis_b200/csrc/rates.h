@@ -187,7 +187,6 @@ AHD bool build_cell_continuum(const Tables& T, const int cell, const int i) {
 
 // macroatom.cc:64-200 for one (cell, level). NT_ON == false in the implemented presets: the non-thermal terms are 0.
 AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) {
-  static_assert(!opt::NT_ON, "macro-atom non-thermal rates need NT_ON support");
   const int uion = T.level_uniqueion[ulev];
   const int element = T.ion_element[uion];
   const int ion = T.ion_index[uion];
@@ -275,8 +274,12 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
   levelrates[MA_ACTION_COLRECOMB] = sum_colrecomb;
 
   double sum_up_higher = 0.;
+  double sum_up_highernt = 0.;
   const int ionisinglevels = nlevels_ionising(T, element, ion);
   if (ion < nions_of(T, element) - 1 && level < ionisinglevels) {
+    if constexpr (opt::NT_ON) {  // macroatom.cc:180-182; the rate coefficient is per-timestep cell state from the host
+      sum_up_highernt = T.nt_ionisation_ratecoeff[(static_cast<long long>(cell) * T.nions) + uion] * epsilon_current;
+    }
     const int nphixstargets = T.level_nphixstargets[ulev];
     for (int phixstargetindex = 0; phixstargetindex < nphixstargets; phixstargetindex++) {
       const double epsilon_trans = phixs_threshold(T, element, ion, level, phixstargetindex);
@@ -285,7 +288,7 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
       sum_up_higher += (R + C) * epsilon_current;
     }
   }
-  levelrates[MA_ACTION_INTERNALUPHIGHERNT] = 0.;
+  levelrates[MA_ACTION_INTERNALUPHIGHERNT] = sum_up_highernt;
   levelrates[MA_ACTION_INTERNALUPHIGHER] = sum_up_higher;
 }
 

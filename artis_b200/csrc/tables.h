@@ -101,6 +101,11 @@ namespace ab {
   X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
   X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
   X(double, nltepops, "cell.nltepops")                              \
+  X(double, nt_ionisation_ratecoeff, "cell.nt_ionisation_ratecoeff") \
+  X(double, nt_ion_energyrate, "cell.nt_ion_energyrate")            \
+  X(float, nt_prob_num_auger, "cell.nt_prob_num_auger")             \
+  X(float, nt_ionenfrac_num_auger, "cell.nt_ionenfrac_num_auger")   \
+  X(float, nt_frac_ionisation, "cell.nt_frac_ionisation")           \
   X(float, radfield_bin_W, "radfield.bin_W")                        \
   X(float, radfield_bin_T_R, "radfield.bin_T_R")
 

@@ -51,6 +51,9 @@
  *   cell.ion_cooling_contribs 'd'[Nc*Nion] kpkt.h:18  cell.corrphotoionrenorm 'd'[Nc*Ng] globals.h:124
  *   cell.nltepops 'd'[Nc*total_nlte_levels]  (presets with ION_NLEVELS_EXCITED_NLTE > 0 only) nltepop.h:15, read by
  *       calculate_levelpop (ltepop.cc:168-199) through nltepop.cc:1955-1968
+ *   cell.nt_ionisation_ratecoeff/nt_ion_energyrate 'd'[Nc*Nion], cell.nt_prob_num_auger/nt_ionenfrac_num_auger
+ *       'f'[Nc*Nion*(NT_MAX_AUGER_ELECTRONS+1)], cell.nt_frac_ionisation 'f'[Nc]  (NT_ON only): nonthermal.cc:1172-1183,
+ *       1509-1522, 2398-2492 evaluated by the host for the timestep (integration/ref_access/ref_nonthermal.cc)
  *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132

@@ -3,6 +3,7 @@
 #include <array>
 #include <cstddef>
 #include <span>
+#include <vector>
 
 #include "constants.h"
 
@@ -33,6 +34,11 @@ auto b200_bfrate_raw() -> std::span<double>;
 auto b200_bin_solutions_W() -> std::span<const float>;
 auto b200_bin_solutions_T_R() -> std::span<const float>;
 }  // namespace radfield
+
+namespace nonthermal {
+void b200_nt_cell_state(std::vector<double>& ion_ratecoeff, std::vector<double>& ion_energyrate, std::vector<float>& prob_num_auger,
+                        std::vector<float>& ionenfrac_num_auger, std::vector<float>& frac_ionisation);
+}  // namespace nonthermal
 
 namespace stats {
 void b200_add_counter(int i, std::ptrdiff_t n);

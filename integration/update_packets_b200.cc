@@ -284,6 +284,20 @@ void emit_timestep_state(Sink& s, const int nts) {
         static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
   s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
         static_cast<int64_t>(globals::corrphotoionrenorm.size()));
+  if constexpr (NT_ON) {
+    // non-thermal routing state (ref_access/ref_nonthermal.cc): rate coefficients and channel probabilities per ion
+    std::vector<double> ratecoeff;
+    std::vector<double> energyrate;
+    std::vector<float> prob;
+    std::vector<float> enfrac;
+    std::vector<float> fracion;
+    nonthermal::b200_nt_cell_state(ratecoeff, energyrate, prob, enfrac, fracion);
+    s.arr("cell.nt_ionisation_ratecoeff", ratecoeff.data(), static_cast<int64_t>(ratecoeff.size()));
+    s.arr("cell.nt_ion_energyrate", energyrate.data(), static_cast<int64_t>(energyrate.size()));
+    s.arr("cell.nt_prob_num_auger", prob.data(), static_cast<int64_t>(prob.size()));
+    s.arr("cell.nt_ionenfrac_num_auger", enfrac.data(), static_cast<int64_t>(enfrac.size()));
+    s.arr("cell.nt_frac_ionisation", fracion.data(), static_cast<int64_t>(fracion.size()));
+  }
   if (globals::total_nlte_levels > 0) {
     // NLTE solver populations over rho, one slot per NLTE level and superlevel (nltepop.h:15, nltepop.cc:1955-1968)
     s.arr("cell.nltepops", nltepops_allcells.data(), static_cast<int64_t>(nltepops_allcells.size()));
