@@ -251,6 +251,35 @@ AHD void select_nt_ionisation(const Tables& T, const int cell, Rng& rng, int& el
   }
 }
 
+// non-thermal excitation rate coefficient of a transition (nonthermal.cc:2494-2518): the cell's excitation list is
+// sorted by alltransindex
+AHD double nt_excitation_ratecoeff(const Tables& T, const int cell, const int lowerlevel, const int upperlevel,
+                                   const int alltransindex) {
+  if constexpr (!opt::NT_EXCITATION_ON) {
+    return 0.;
+  }
+  if (lowerlevel >= opt::NTEXCITATION_MAXNLEVELS_LOWER || upperlevel >= opt::NTEXCITATION_MAXNLEVELS_UPPER) {
+    return 0.;
+  }
+  const long long base = static_cast<long long>(cell) * T.nt_excitations_stored;
+  const int n = T.nt_exc_count[cell];
+  int lo = 0;
+  int len = n;
+  while (len > 0) {  // lower_bound on alltransindex
+    const int half = len >> 1;
+    if (T.nt_exc_alltransindex[base + lo + half] < alltransindex) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  if (lo >= n || T.nt_exc_alltransindex[base + lo] != alltransindex) {
+    return 0.;
+  }
+  return T.nt_exc_ratecoeffperdeposition[base + lo] * T.nt_deposition_rate_density[cell];
+}
+
 AHD double cell_levelpop(const Tables& T, const int cell, const int ulev) {  // ltepop.h:58-65
   return T.cell_levelpops[(static_cast<long long>(cell) * T.nlevels) + ulev];
 }

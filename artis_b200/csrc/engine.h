@@ -638,6 +638,15 @@ class Engine {
         return fail("begin_timestep: the cell.nt_* arrays (non-thermal routing state, NT_ON) are missing or have the wrong length");
       }
     }
+    if constexpr (opt::NT_EXCITATION_ON) {
+      const int64_t want = static_cast<int64_t>(T.ncells) * T.nt_excitations_stored;
+      if (count_of("cell.nt_exc_count") != T.ncells || count_of("cell.nt_exc_alltransindex") != want ||
+          count_of("cell.nt_exc_frac_deposition") != want || count_of("cell.nt_exc_ratecoeffperdeposition") != want ||
+          count_of("cell.nt_deposition_rate_density") != T.ncells || count_of("cell.nt_frac_excitation") != T.ncells) {
+        return fail("begin_timestep: the cell.nt_exc_* arrays (non-thermal excitation lists, NT_EXCITATION_ON) are missing or "
+                    "do not match scalar.nt_excitations_stored");
+      }
+    }
     if constexpr (opt::HAS_NLTE_LEVELS) {
       const int64_t n = count_of("cell.nltepops");
       if (n <= 0 || (n % T.ncells) != 0) {

@@ -26,6 +26,8 @@ constexpr bool NT_ON = ::NT_ON;
 constexpr bool NT_SOLVE_SPENCERFANO = ::NT_SOLVE_SPENCERFANO;
 constexpr bool NT_EXCITATION_ON = ::NT_EXCITATION_ON;
 constexpr int NT_MAX_AUGER_ELECTRONS = ::NT_MAX_AUGER_ELECTRONS;
+constexpr int NTEXCITATION_MAXNLEVELS_LOWER = ::NTEXCITATION_MAXNLEVELS_LOWER;
+constexpr int NTEXCITATION_MAXNLEVELS_UPPER = ::NTEXCITATION_MAXNLEVELS_UPPER;
 constexpr bool LTEPOP_EXCITATION_USE_TJ = ::LTEPOP_EXCITATION_USE_TJ;
 constexpr bool BFCOOLING_USELEVELPOPNOTIONPOP = ::BFCOOLING_USELEVELPOPNOTIONPOP;
 constexpr bool RPKT_USE_EXPANSION_OPACITIES = ::RPKT_USE_EXPANSION_OPACITIES;
@@ -64,7 +66,7 @@ constexpr int GTS_GUTTMAN = 3;
 
 // modes of the reference that this library does not implement yet fail at compile time rather than silently
 static_assert(!DETAILED_BF_ESTIMATORS_ON, "DETAILED_BF_ESTIMATORS_ON (NLTE presets) is not implemented yet");
-static_assert(!NT_EXCITATION_ON, "non-thermal excitation (NT_EXCITATION_ON) is not implemented yet");
+static_assert(!NT_EXCITATION_ON || (NT_ON && NT_SOLVE_SPENCERFANO), "NT_EXCITATION_ON needs NT_ON and NT_SOLVE_SPENCERFANO");
 static_assert(!NT_SOLVE_SPENCERFANO || NT_ON, "NT_SOLVE_SPENCERFANO needs NT_ON");
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,
               "expansion-opacity r-packet modes are not implemented yet");

@@ -21,6 +21,8 @@ constexpr bool NT_ON = false;
 constexpr bool NT_SOLVE_SPENCERFANO = false;
 constexpr bool NT_EXCITATION_ON = false;
 constexpr int NT_MAX_AUGER_ELECTRONS = 2;
+constexpr int NTEXCITATION_MAXNLEVELS_LOWER = 5;
+constexpr int NTEXCITATION_MAXNLEVELS_UPPER = 250;
 constexpr bool LTEPOP_EXCITATION_USE_TJ = true;
 constexpr bool BFCOOLING_USELEVELPOPNOTIONPOP = false;
 constexpr bool RPKT_USE_EXPANSION_OPACITIES = false;

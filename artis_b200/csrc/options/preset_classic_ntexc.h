@@ -1,11 +1,12 @@
-// artisoptions_kilonova_lte.h with the GUTTMAN gamma-ray and BARNES particle thermalisation schemes (parity cases of the parameterised thermalisation schemes).
+// artisoptions_classic.h with non-thermal deposition solved by Spencer-Fano (NT_ON, NT_SOLVE_SPENCERFANO): deposited
+// leptons are routed to non-thermal ionisation (nonthermal.cc:2529-2613), and excitation (NT_EXCITATION_ON), used by the classic_ntexc_toy parity case.
 #pragma once
-#define ARTISB200_PRESET_NAME "kilonova_guttman"
+#define ARTISB200_PRESET_NAME "classic_ntexc"
 namespace opt {
-constexpr bool POL_ON = false;
-constexpr bool DIPOLE = false;
-constexpr bool USE_RELATIVISTIC_DOPPLER_SHIFT = true;
-constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = false;
+constexpr bool POL_ON = true;
+constexpr bool DIPOLE = true;
+constexpr bool USE_RELATIVISTIC_DOPPLER_SHIFT = false;
+constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = true;
 constexpr bool USE_LUT_PHOTOION = true;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = true;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = false;
@@ -15,10 +16,10 @@ constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = 12;
 constexpr double RADFIELDBINS_NU_MIN = 2.99792458e+10 / 40000e-8;
 constexpr double RADFIELDBINS_NU_MAX = 2.99792458e+10 / 1085e-8;
 constexpr double RADFIELDBINS_T_E_SUPERBIN_NU_MAX = 2.99792458e+10 / 10e-8;
-constexpr bool DIRECT_COL_HEAT = true;
-constexpr bool NT_ON = false;
-constexpr bool NT_SOLVE_SPENCERFANO = false;
-constexpr bool NT_EXCITATION_ON = false;
+constexpr bool DIRECT_COL_HEAT = false;
+constexpr bool NT_ON = true;
+constexpr bool NT_SOLVE_SPENCERFANO = true;
+constexpr bool NT_EXCITATION_ON = true;
 constexpr int NT_MAX_AUGER_ELECTRONS = 2;
 constexpr int NTEXCITATION_MAXNLEVELS_LOWER = 5;
 constexpr int NTEXCITATION_MAXNLEVELS_UPPER = 250;
@@ -31,10 +32,10 @@ constexpr bool USE_XCOM_GAMMAPHOTOION = false;
 constexpr bool HAS_GAMMA_KAPPA_GREY = false;
 constexpr double GAMMA_KAPPA_GREY = 0.;
 constexpr bool FORCE_SPHERICAL_ESCAPE_SURFACE = false;
-constexpr int PARTICLE_THERMALISATION_SCHEME = 4;  // BARNES
-constexpr int GAMMA_THERMALISATION_SCHEME = 3;     // GUTTMAN
-constexpr double MINPOP = 1e-40;
-constexpr double NU_MIN_R = 1e13;
-constexpr double NU_MAX_R = 5e16;
+constexpr int PARTICLE_THERMALISATION_SCHEME = 0;  // INSTANTFULLDEPOSITION
+constexpr int GAMMA_THERMALISATION_SCHEME = 0;     // FREQUENCYDEPENDENT
+constexpr double MINPOP = 1e-30;
+constexpr double NU_MIN_R = 1e14;
+constexpr double NU_MAX_R = 5e15;
 constexpr bool HAS_NLTE_LEVELS = false;
 }  // namespace opt

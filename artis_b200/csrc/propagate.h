@@ -170,7 +170,7 @@ AHD void do_ntalpha_fisprod_deposit(Pkt& p, const Ctx& c) {
 
 // nonthermal.cc:2529-2613: a deposited lepton heats, or - with a Spencer-Fano solution, outside grey cells - ionises
 // an ion chosen by its share of the ionisation energy rate and activates a macro-atom in the ground level of the
-// resulting ion. (The excitation channel needs NT_EXCITATION_ON, which is a compile-time error here.)
+// resulting ion, or excites a transition of the cell's non-thermal excitation list.
 AHD void do_ntlepton_deposit(Pkt& p, const Ctx& c) {
   const Tables& T = c.T;
   c.add_ts(TS_NT_ENERGY_DEPOSITED, p.e_cmf);
@@ -196,6 +196,32 @@ AHD void do_ntlepton_deposit(Pkt& p, const Ctx& c) {
         p.type = TYPE_KPKT;  // no ion can be selected (zero deposition rate density): heat
         c.count<CNT_NT_STAT_TO_KPKT>();
         return;
+      }
+      if constexpr (opt::NT_EXCITATION_ON) {
+        // the excitation share goes to macro-atoms in the upper level of the chosen transition; what the stored
+        // (truncated) list does not cover falls through to heating (nonthermal.cc:2578-2607)
+        const double frac_excitation = T.nt_frac_excitation[cell];
+        if (zrand < (frac_ionisation + frac_excitation)) {
+          double z = zrand - frac_ionisation;
+          const long long base = static_cast<long long>(cell) * T.nt_excitations_stored;
+          const int n = T.nt_exc_count[cell];
+          for (int k = 0; k < n; k++) {
+            const double frac_deposition_exc = T.nt_exc_frac_deposition[base + k];
+            if (z < frac_deposition_exc) {
+              const int lineindex = T.trans_lineindex[T.nt_exc_alltransindex[base + k]];
+              const int upper_ulev = T.line_upper[lineindex];
+              const int uion = T.level_uniqueion[upper_ulev];
+              c.count<CNT_MA_STAT_ACTIVATION_NTCOLLEXC>();
+              c.count<CNT_INTERACTIONS>();
+              T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;
+              set_trueem_pos_nan(c);
+              c.count<CNT_NT_STAT_TO_EXCITATION>();
+              activate_macroatom(p, {T.ion_element[uion], T.ion_index[uion], upper_ulev - T.ion_levelstart[uion], -99});
+              return;
+            }
+            z -= frac_deposition_exc;
+          }
+        }
       }
     }
   }

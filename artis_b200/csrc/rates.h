@@ -243,7 +243,7 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
     const double R = rad_excitation_ratecoeff(T, cell, upper_statweight, T.trans_einstein_A[alltransindex], epsilon_trans,
                                               nnlevel, cell_levelpop(T, cell, upper_ulev), statweight, t_mid);
     const double C = col_excitation_ratecoeff(T, T_e, clumpednne_, epsilon_trans, upper_statweight, statweight, alltransindex);
-    const double NT = 0.;
+    const double NT = nt_excitation_ratecoeff(T, cell, level, upper, alltransindex);  // macroatom.cc:133
     sum_internal_up_same += (R + C + NT) * epsilon_current;
     arr_sum_internal_up_same[ii] = sum_internal_up_same;
   }

@@ -106,6 +106,12 @@ namespace ab {
   X(float, nt_prob_num_auger, "cell.nt_prob_num_auger")             \
   X(float, nt_ionenfrac_num_auger, "cell.nt_ionenfrac_num_auger")   \
   X(float, nt_frac_ionisation, "cell.nt_frac_ionisation")           \
+  X(int, nt_exc_count, "cell.nt_exc_count")                         \
+  X(int, nt_exc_alltransindex, "cell.nt_exc_alltransindex")         \
+  X(double, nt_exc_frac_deposition, "cell.nt_exc_frac_deposition")  \
+  X(double, nt_exc_ratecoeffperdeposition, "cell.nt_exc_ratecoeffperdeposition") \
+  X(double, nt_deposition_rate_density, "cell.nt_deposition_rate_density") \
+  X(float, nt_frac_excitation, "cell.nt_frac_excitation")           \
   X(float, radfield_bin_W, "radfield.bin_W")                        \
   X(float, radfield_bin_T_R, "radfield.bin_T_R")
 
@@ -123,7 +129,8 @@ namespace ab {
   X(long long, globals_timestep, "scalar.globals_timestep")  \
   X(double, max_path_step, "scalar.max_path_step")          \
   X(double, ejecta_kinetic_energy, "scalar.ejecta_kinetic_energy") \
-  X(double, mtot_input, "scalar.mtot_input")
+  X(double, mtot_input, "scalar.mtot_input")                \
+  X(long long, nt_excitations_stored, "scalar.nt_excitations_stored")
 
 // device-side output / work arrays that can be read back with artisb200_get_array()
 #define AB_OUTPUT_ARRAYS(X)                       \

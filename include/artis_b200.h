@@ -54,6 +54,9 @@
  *   cell.nt_ionisation_ratecoeff/nt_ion_energyrate 'd'[Nc*Nion], cell.nt_prob_num_auger/nt_ionenfrac_num_auger
  *       'f'[Nc*Nion*(NT_MAX_AUGER_ELECTRONS+1)], cell.nt_frac_ionisation 'f'[Nc]  (NT_ON only): nonthermal.cc:1172-1183,
  *       1509-1522, 2398-2492 evaluated by the host for the timestep (integration/ref_access/ref_nonthermal.cc)
+ *   scalar.nt_excitations_stored 'q', cell.nt_exc_count 'i'[Nc], cell.nt_exc_alltransindex 'i' / nt_exc_frac_deposition 'd' /
+ *       nt_exc_ratecoeffperdeposition 'd' [Nc*stored], cell.nt_deposition_rate_density 'd'[Nc], cell.nt_frac_excitation 'f'[Nc]
+ *       (NT_EXCITATION_ON only): nonthermal.cc:202-212, 364-367, 2382-2385, 1186-1195
  *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132

@@ -38,6 +38,9 @@ auto b200_bin_solutions_T_R() -> std::span<const float>;
 namespace nonthermal {
 void b200_nt_cell_state(std::vector<double>& ion_ratecoeff, std::vector<double>& ion_energyrate, std::vector<float>& prob_num_auger,
                         std::vector<float>& ionenfrac_num_auger, std::vector<float>& frac_ionisation);
+void b200_nt_excitations(int& stride, std::vector<int>& count, std::vector<int>& alltransindex, std::vector<double>& frac_deposition,
+                         std::vector<double>& ratecoeffperdeposition, std::vector<double>& deposition_rate_density,
+                         std::vector<float>& frac_excitation);
 }  // namespace nonthermal
 
 namespace stats {

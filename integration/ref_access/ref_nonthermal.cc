@@ -41,4 +41,35 @@ void b200_nt_cell_state(std::vector<double>& ion_ratecoeff, std::vector<double>&
     }
   }
 }
+
+// the per-cell lists of non-thermal excitation transitions (nonthermal.cc:202-212, 364-367), flattened with the
+// reference's own stride, and what nt_excitation_ratecoeff() multiplies them with (nonthermal.cc:2494-2518)
+void b200_nt_excitations(int& stride, std::vector<int>& count, std::vector<int>& alltransindex, std::vector<double>& frac_deposition,
+                         std::vector<double>& ratecoeffperdeposition, std::vector<double>& deposition_rate_density,
+                         std::vector<float>& frac_excitation) {
+  const ptrdiff_t nc = grid::get_nonempty_npts_model();
+  stride = (NT_ON && NT_SOLVE_SPENCERFANO && NT_EXCITATION_ON) ? nt_excitations_stored : 0;
+  count.assign(nc, 0);
+  deposition_rate_density.assign(nc, 0.);
+  frac_excitation.assign(nc, 0.F);
+  alltransindex.assign(nc * stride, -1);
+  frac_deposition.assign(nc * stride, 0.);
+  ratecoeffperdeposition.assign(nc * stride, 0.);
+  if constexpr (!NT_ON) {
+    return;
+  }
+  for (ptrdiff_t nonemptymgi = 0; nonemptymgi < nc; nonemptymgi++) {
+    deposition_rate_density[nonemptymgi] = ntlepton_deposition_rate_density_all_cells[nonemptymgi];
+    frac_excitation[nonemptymgi] = get_nt_frac_excitation(static_cast<int>(nonemptymgi));
+    if (stride > 0) {
+      const auto list = get_cell_ntexcitations(nonemptymgi);
+      count[nonemptymgi] = static_cast<int>(list.size());
+      for (size_t k = 0; k < list.size(); k++) {
+        alltransindex[(nonemptymgi * stride) + k] = list[k].alltransindex;
+        frac_deposition[(nonemptymgi * stride) + k] = list[k].frac_deposition;
+        ratecoeffperdeposition[(nonemptymgi * stride) + k] = list[k].ratecoeffperdeposition;
+      }
+    }
+  }
+}
 }  // namespace nonthermal

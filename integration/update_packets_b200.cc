@@ -297,6 +297,23 @@ void emit_timestep_state(Sink& s, const int nts) {
     s.arr("cell.nt_prob_num_auger", prob.data(), static_cast<int64_t>(prob.size()));
     s.arr("cell.nt_ionenfrac_num_auger", enfrac.data(), static_cast<int64_t>(enfrac.size()));
     s.arr("cell.nt_frac_ionisation", fracion.data(), static_cast<int64_t>(fracion.size()));
+    if constexpr (NT_EXCITATION_ON) {
+      int stride = 0;
+      std::vector<int> count;
+      std::vector<int> alltransindex;
+      std::vector<double> fracdep;
+      std::vector<double> rateperdep;
+      std::vector<double> deprate;
+      std::vector<float> fracexc;
+      nonthermal::b200_nt_excitations(stride, count, alltransindex, fracdep, rateperdep, deprate, fracexc);
+      s.i64("scalar.nt_excitations_stored", stride);
+      s.arr("cell.nt_exc_count", count.data(), static_cast<int64_t>(count.size()));
+      s.arr("cell.nt_exc_alltransindex", alltransindex.data(), static_cast<int64_t>(alltransindex.size()));
+      s.arr("cell.nt_exc_frac_deposition", fracdep.data(), static_cast<int64_t>(fracdep.size()));
+      s.arr("cell.nt_exc_ratecoeffperdeposition", rateperdep.data(), static_cast<int64_t>(rateperdep.size()));
+      s.arr("cell.nt_deposition_rate_density", deprate.data(), static_cast<int64_t>(deprate.size()));
+      s.arr("cell.nt_frac_excitation", fracexc.data(), static_cast<int64_t>(fracexc.size()));
+    }
   }
   if (globals::total_nlte_levels > 0) {
     // NLTE solver populations over rho, one slot per NLTE level and superlevel (nltepop.h:15, nltepop.cc:1955-1968)
