@@ -727,11 +727,33 @@ struct CudaBackend {
     const long long saved_stride = T.scratch_stride;
     T.scratch_groundcont = scratch;
     T.scratch_stride = n;
+    // the same for the detailed bound-free estimator scratch (one column per tested element)
+    double* const saved_bfcontr = T.scratch_bfcontr;
+    int* const saved_begin = T.scratch_bfestimbegin;
+    int* const saved_end = T.scratch_bfestimend;
+    double* bfcontr = nullptr;
+    int* bfwindow = nullptr;
+    if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+      const long long nb = T.nbfestim > 0 ? T.nbfestim : 1;
+      if (!ok(cudaMalloc(&bfcontr, static_cast<size_t>(n * nb) * sizeof(double)), "cudaMalloc(test scratch)") ||
+          !ok(cudaMalloc(&bfwindow, static_cast<size_t>(2 * n) * sizeof(int)), "cudaMalloc(test scratch)")) {
+        cudaFree(scratch);
+        return false;
+      }
+      T.scratch_bfcontr = bfcontr;
+      T.scratch_bfestimbegin = bfwindow;
+      T.scratch_bfestimend = bfwindow + n;
+    }
     k_test_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(T, which, n, in_f64, in_i32, out_f64, out_i32);
     const bool good = ok(cudaStreamSynchronize(stream), "k_test_kernel") && ok(cudaGetLastError(), "k_test_kernel");
     cudaFree(scratch);
+    cudaFree(bfcontr);
+    cudaFree(bfwindow);
     T.scratch_groundcont = saved;
     T.scratch_stride = saved_stride;
+    T.scratch_bfcontr = saved_bfcontr;
+    T.scratch_bfestimbegin = saved_begin;
+    T.scratch_bfestimend = saved_end;
     return good;
   }
 

@@ -331,7 +331,13 @@ AHD double bfcoolingcoeff(const Tables& T, const int ulev, const int phixstarget
 
 // stimulated-recombination-corrected photoionisation rate coefficient, LUT branch (ratecoeff.cc:840-875)
 AHD double calc_corrphotoioncoeff(const Tables& T, const int cell, const int ulev, const int phixstargetindex) {
-  static_assert(opt::USE_LUT_PHOTOION, "only the USE_LUT_PHOTOION branch of get_corrphotoioncoeff is implemented");
+  if constexpr (!opt::USE_LUT_PHOTOION) {
+    // ratecoeff.cc:848-857: the bound-free rate estimator of the previous timestep or, without one, an integral of the
+    // cross-section over the radiation field model. Both belong to the host's solver state; the binding evaluates
+    // get_corrphotoioncoeff() per (cell, level, target) for the timestep and hands the table over.
+    return T.corrphotoioncoeff_host[(static_cast<long long>(cell) * T.nphixstargets_total) + T.level_phixstargetstart[ulev] +
+                                    phixstargetindex];
+  }
   const double W = T.W[cell];
   const double T_R = T.TR[cell];
   double gammacorr = W * lerp_or_last(T, T.lut_corrphotoion, ulev, phixstargetindex, T_R);

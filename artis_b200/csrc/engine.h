@@ -179,6 +179,7 @@ class Engine {
   PropagateOptions popt;
   PropagateTimings last;
   int64_t scratch_capacity{0};
+  int64_t bfscratch_capacity{0};
 
   int fail(const std::string& msg) {
     err = msg;
@@ -212,6 +213,15 @@ class Engine {
     if (aos_staging != nullptr) {
       be.free(aos_staging);
       aos_staging = nullptr;
+    }
+    if (T.scratch_bfcontr != nullptr) {
+      be.free(T.scratch_bfcontr);
+      be.free(T.scratch_bfestimbegin);
+      be.free(T.scratch_bfestimend);
+      T.scratch_bfcontr = nullptr;
+      T.scratch_bfestimbegin = nullptr;
+      T.scratch_bfestimend = nullptr;
+      bfscratch_capacity = 0;
     }
     for (void* ptr : soa_save) {
       be.free(ptr);
@@ -420,6 +430,12 @@ class Engine {
     T.ntrans = static_cast<int>(count_of("trans.lineindex"));
     T.nbfcontinua = static_cast<int>(count_of("cont.nu_edge"));
     T.nbfcontinua_ground = static_cast<int>(count_of("groundcont.nu_edge"));
+    T.nbfestim = (count_of("bfestim.nu_edge") > 0) ? static_cast<int>(count_of("bfestim.nu_edge")) : 0;
+    if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+      if (count_of("bfestim.nu_edge") < 0 || count_of("cont.bfestimindex") != count_of("cont.nu_edge")) {
+        return fail("commit_static: bfestim.nu_edge and cont.bfestimindex are required with DETAILED_BF_ESTIMATORS_ON");
+      }
+    }
     T.nphixstargets_total = static_cast<int>(count_of("phixstarget.levelindex"));
     T.ncoolingterms = static_cast<int>(count_of("cooling.type"));
     T.ntimesteps = static_cast<int>(count_of("timesteps.start"));
@@ -506,7 +522,9 @@ class Engine {
         if (offset > 2147483647LL) {
           return fail("commit_static: photoionisation table larger than 2^31 entries");
         }
-        cs[static_cast<size_t>(i)] = {c_nu_edge[i], c_prob[i], static_cast<int>(offset), c_ground[i], {0, 0}};
+        const auto* c_bfestim = host<int>("cont.bfestimindex");
+        cs[static_cast<size_t>(i)] = {c_nu_edge[i], c_prob[i], static_cast<int>(offset), c_ground[i],
+                                      (c_bfestim != nullptr) ? c_bfestim[i] : -1, 0};
       }
       ArrayRec& rec = arrays["derived.cont_static"];
       if (rec.dptr != nullptr) {
@@ -558,14 +576,16 @@ class Engine {
     // one packed f64 buffer for everything that is summed over ranks (see artisb200_estimator_device_buffer)
     // the multi-bin radiation field estimators (radfield.cc:63-70) exist only with MULTIBIN_RADFIELD_MODEL_ON
     const int64_t nbins = opt::MULTIBIN_RADFIELD_MODEL_ON ? nc * opt::RADFIELDBINCOUNT : 0;
-    constexpr int NPACK = 13;
-    const int64_t sizes[NPACK] = {nc, nc, nc, nc, nc * ng, nc * ng, nc, nc, nc, nc, NTSSCALARS, nbins, nbins};
+    // ... and the detailed bound-free rate estimators (radfield.cc:96-111) only with DETAILED_BF_ESTIMATORS_ON
+    const int64_t nbfrate = opt::DETAILED_BF_ESTIMATORS_ON ? nc * T.nbfestim : 0;
+    constexpr int NPACK = 14;
+    const int64_t sizes[NPACK] = {nc, nc, nc, nc, nc * ng, nc * ng, nc, nc, nc, nc, NTSSCALARS, nbins, nbins, nbfrate};
     const char* names[NPACK] = {"est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating",
                                 "est.dep_gamma", "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars",
-                                "est.bins_J_raw", "est.bins_nuJ_raw"};
+                                "est.bins_J_raw", "est.bins_nuJ_raw", "est.bfrate_raw"};
     double** slots[NPACK] = {&T.est_J, &T.est_nuJ, &T.est_ffheating, &T.est_colheating, &T.est_gamma, &T.est_bfheating,
                              &T.est_dep_gamma, &T.est_dep_positron, &T.est_dep_electron, &T.est_dep_alpha, &T.ts_scalars,
-                             &T.est_bins_J_raw, &T.est_bins_nuJ_raw};
+                             &T.est_bins_J_raw, &T.est_bins_nuJ_raw, &T.est_bfrate_raw};
     int64_t total = 0;
     for (const auto s : sizes) {
       total += s;
@@ -636,6 +656,12 @@ class Engine {
           count_of("cell.nt_prob_num_auger") != ni * NA || count_of("cell.nt_ionenfrac_num_auger") != ni * NA ||
           count_of("cell.nt_frac_ionisation") != T.ncells) {
         return fail("begin_timestep: the cell.nt_* arrays (non-thermal routing state, NT_ON) are missing or have the wrong length");
+      }
+    }
+    if constexpr (!opt::USE_LUT_PHOTOION) {
+      if (count_of("cell.corrphotoioncoeff") != static_cast<int64_t>(T.ncells) * T.nphixstargets_total) {
+        return fail("begin_timestep: cell.corrphotoioncoeff must hold ncells x (photoionisation targets) entries "
+                    "(USE_LUT_PHOTOION = false: evaluated by the host)");
       }
     }
     if constexpr (opt::NT_EXCITATION_ON) {
@@ -717,6 +743,26 @@ class Engine {
       scratch_capacity = packet_capacity * ng;
     }
     T.scratch_stride = packet_capacity;
+    if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+      const int64_t need = packet_capacity * static_cast<int64_t>(T.nbfestim > 0 ? T.nbfestim : 1);
+      if (bfscratch_capacity < need) {
+        if (T.scratch_bfcontr != nullptr) {
+          be.free(T.scratch_bfcontr);
+          be.free(T.scratch_bfestimbegin);
+          be.free(T.scratch_bfestimend);
+        }
+        T.scratch_bfcontr = static_cast<double*>(be.alloc(need * 8));
+        T.scratch_bfestimbegin = static_cast<int*>(be.alloc(packet_capacity * 4));
+        T.scratch_bfestimend = static_cast<int*>(be.alloc(packet_capacity * 4));
+        if (T.scratch_bfcontr == nullptr || T.scratch_bfestimbegin == nullptr || T.scratch_bfestimend == nullptr) {
+          return fail("detailed bound-free estimator scratch allocation failed: " + be.last_error());
+        }
+        be.zero(T.scratch_bfcontr, need * 8);
+        be.zero(T.scratch_bfestimbegin, packet_capacity * 4);
+        be.zero(T.scratch_bfestimend, packet_capacity * 4);
+        bfscratch_capacity = need;
+      }
+    }
     const int64_t need = n * stride;
     if (need > aos_staging_bytes) {
       if (aos_staging != nullptr) {

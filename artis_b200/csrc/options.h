@@ -65,7 +65,7 @@ constexpr int GTS_WOLLAEGER = 2;
 constexpr int GTS_GUTTMAN = 3;
 
 // modes of the reference that this library does not implement yet fail at compile time rather than silently
-static_assert(!DETAILED_BF_ESTIMATORS_ON, "DETAILED_BF_ESTIMATORS_ON (NLTE presets) is not implemented yet");
+static_assert(!DETAILED_BF_ESTIMATORS_ON || !USE_LUT_PHOTOION, "DETAILED_BF_ESTIMATORS_ON needs USE_LUT_PHOTOION = false");
 static_assert(!NT_EXCITATION_ON || (NT_ON && NT_SOLVE_SPENCERFANO), "NT_EXCITATION_ON needs NT_ON and NT_SOLVE_SPENCERFANO");
 static_assert(!NT_SOLVE_SPENCERFANO || NT_ON, "NT_SOLVE_SPENCERFANO needs NT_ON");
 static_assert(!RPKT_USE_EXPANSION_OPACITIES && !HAS_BB_THERMALISATION_PROBABILITY,

@@ -116,6 +116,7 @@ struct Ctx {
   }
   AHD void pellet_decay() const { bump(pellet_decays, 1U); }
   AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(i * T.scratch_stride) + ip]; }
+  AHD double* bfestim_contr(const int i) const { return &T.scratch_bfcontr[(i * T.scratch_stride) + ip]; }
 
   // add the thread-private counters to the block's accumulators (end of kernel) and clear them
   AHD void flush_hot() const {

@@ -144,9 +144,12 @@ AHD double calculate_chi_ffheat_nnionpart(const Tables& T, const int cell) {
   return sum * 3.69255e8 / sqrt(static_cast<double>(T_e));  // unqualified sqrt(float) is the double overload in rpkt.cc
 }
 
-// rpkt.h:191-197 (the !DETAILED_BF_ESTIMATORS_ON branch)
+// rpkt.h:191-197
 AHD bool keep_this_cont(const Tables& T, const int element, const int ion, const int level, const int cell,
                         const float nnetot) {
+  if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+    return elem_massfrac(T, cell, element) > 0;
+  }
   return ((nnion(T, cell, element, ion) / nnetot > 1.e-6) || (level == 0));
 }
 

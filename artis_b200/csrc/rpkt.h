@@ -112,11 +112,13 @@ AHD BfEval bf_eval_begin(const Tables& T, const int cell, const double nu) {
 }
 
 // returns sigma_contr; `nnlevel` is the population the caller multiplies it with
-AHD double bf_term_sigma_contr(const Tables& T, const BfEval& e, const int i, double& nnlevel, int& groundcontestimindex) {
+AHD double bf_term_sigma_contr(const Tables& T, const BfEval& e, const int i, double& nnlevel, int& groundcontestimindex,
+                               int& bfestimindex) {
   const ContStatic cs = T.cont_static[i];
   const CellCont cc = T.cell_cont_pack[e.base + i];
   nnlevel = cc.nnlevel;
   groundcontestimindex = cs.groundcontestimindex;
+  bfestimindex = cs.bfestimindex;
   const double sigma_bf = photoionisation_crosssection_fromtable(T, T.phixs_table + cs.phixs_offset, cs.nu_edge, e.nu);
   double stimfactor;
   if (cc.edgepart >= 0. && e.stimfactor_split_usable) {
@@ -164,6 +166,16 @@ AHD double bf_sum_window(const Ctx& c, const int cell, const BfEval& e, const in
       *c.groundcont_contr(i) = 0.;
     }
   }
+  if constexpr (!SELECT && opt::DETAILED_BF_ESTIMATORS_ON) {
+    // rpkt.cc:764-776: the window of estimator slots of this evaluation, cleared before the contributing continua write
+    const int bfestimend = upper_bound_idx(T.bfestim_nu_edge, T.nbfestim, e.nu);
+    const int bfestimbegin = lower_bound_idx(T.bfestim_nu_edge, bfestimend, e.nu / T.last_phixs_nuovernuedge);
+    T.scratch_bfestimbegin[c.ip] = bfestimbegin;
+    T.scratch_bfestimend[c.ip] = bfestimend;
+    for (int k = bfestimbegin; k < bfestimend; k++) {
+      *c.bfestim_contr(k) = 0.;
+    }
+  }
   const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
   // ONE loop over "fetch the next bitmap word" / "evaluate the next kept continuum": with a loop over words around a
   // loop over bits the lanes of a warp drift apart (each is in a different word) and the term code ran with 2.4 of 32
@@ -185,7 +197,13 @@ AHD double bf_sum_window(const Ctx& c, const int cell, const BfEval& e, const in
 
     double nnlevel = 0.;
     int g = -1;
-    const double sigma_contr = bf_term_sigma_contr(T, e, i, nnlevel, g);
+    int bfestimindex = -1;
+    const double sigma_contr = bf_term_sigma_contr(T, e, i, nnlevel, g, bfestimindex);
+    if constexpr (!SELECT && opt::DETAILED_BF_ESTIMATORS_ON) {
+      if (bfestimindex >= 0) {
+        *c.bfestim_contr(bfestimindex) = sigma_contr;  // rpkt.cc:903-907
+      }
+    }
 
     if constexpr (!SELECT && (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS)) {
       if (g >= 0) {
@@ -323,6 +341,22 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
   }
   if (thickcell) {
     return;
+  }
+  if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {  // radfield.cc:215-248 update_bfestimators
+    if (distance_e_cmf != 0) {
+      const double distance_e_cmf_over_nu = distance_e_cmf / nu_cmf;
+      const int stored_end = T.scratch_bfestimend[c.ip];
+      const int stored_begin = T.scratch_bfestimbegin[c.ip];
+      // nu_cmf has drifted down since the window was stored: re-derive it, never wider than the stored one
+      const int bfestimend = upper_bound_idx(T.bfestim_nu_edge, stored_end, nu_cmf);
+      const int begin_clamped = (stored_begin < bfestimend) ? stored_begin : bfestimend;
+      const int bfestimbegin = begin_clamped + lower_bound_idx(T.bfestim_nu_edge + begin_clamped, bfestimend - begin_clamped,
+                                                               nu_cmf / T.last_phixs_nuovernuedge);
+      for (int k = bfestimbegin; k < bfestimend; k++) {
+        est_atomic_add(&T.est_bfrate_raw[(static_cast<long long>(cell) * T.nbfestim) + k], *c.bfestim_contr(k) * distance_e_cmf_over_nu);
+      }
+      c.work<DIAG_ESTIMATOR_ADDS>(bfestimend - bfestimbegin);
+    }
   }
   if constexpr (opt::MULTIBIN_RADFIELD_MODEL_ON) {  // radfield.cc:762-770
     if (distance_e_cmf != 0) {

@@ -100,6 +100,7 @@ namespace ab {
   X(float, ion_partfuncts, "cell.ion_partfuncts")                     \
   X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
   X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
+  X(double, corrphotoioncoeff_host, "cell.corrphotoioncoeff")       \
   X(double, nltepops, "cell.nltepops")                              \
   X(double, nt_ionisation_ratecoeff, "cell.nt_ionisation_ratecoeff") \
   X(double, nt_ion_energyrate, "cell.nt_ion_energyrate")            \
@@ -146,6 +147,7 @@ namespace ab {
   X(double, est_dep_alpha, "est.dep_alpha")       \
   X(double, est_bins_J_raw, "est.bins_J_raw")     \
   X(double, est_bins_nuJ_raw, "est.bins_nuJ_raw") \
+  X(double, est_bfrate_raw, "est.bfrate_raw")     \
   X(double, ts_scalars, "ts.scalars")             \
   X(long long, ts_pellet_decays, "ts.pellet_decays") \
   X(long long, counters, "counters")              \
@@ -244,7 +246,8 @@ struct alignas(32) ContStatic {
   double probability;
   int phixs_offset;          // index of the continuum's photoionisation table in phixs.table
   int groundcontestimindex;
-  int pad[2];
+  int bfestimindex;  // slot of the detailed bound-free estimators (DETAILED_BF_ESTIMATORS_ON), or -1
+  int pad;
 };
 
 struct alignas(16) CellCont {
@@ -339,6 +342,12 @@ struct Tables {
   RngSetup rng_setup;  // (rng_mode, seed, timestep) in the form the generators read; refreshed before every propagation
   long long max_steps_per_launch;
 
+  // DETAILED_BF_ESTIMATORS_ON: per-packet sigma contributions of every estimator slot [nbfestim][scratch_stride] and the
+  // estimator window of the cached opacity (reference rpkt.h:49-66 Phixslist gamma_contr, bfestimbegin, bfestimend)
+  double* scratch_bfcontr;
+  int* scratch_bfestimbegin;
+  int* scratch_bfestimend;
+  int nbfestim;
   // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
   double* scratch_groundcont;
   long long scratch_stride;

@@ -8,7 +8,7 @@ torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo in the CPU te
 import numpy as np
 
 ESTIMATOR_ORDER = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
-                   "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "est.bins_J_raw", "est.bins_nuJ_raw"]
+                   "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "est.bins_J_raw", "est.bins_nuJ_raw", "est.bfrate_raw"]
 
 
 def rank_seed(base_seed, rank):

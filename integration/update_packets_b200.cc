@@ -56,6 +56,7 @@
 #include "nonthermal.h"
 #include "packet.h"
 #include "radfield.h"
+#include "ratecoeff.h"
 #include "rpkt.h"
 #include "stats.h"
 #include "update_packets.h"
@@ -284,6 +285,27 @@ void emit_timestep_state(Sink& s, const int nts) {
         static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
   s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
         static_cast<int64_t>(globals::corrphotoionrenorm.size()));
+  if constexpr (!USE_LUT_PHOTOION) {
+    // corrected photoionisation rate coefficients without the LUT (ratecoeff.cc:840-875): the previous timestep's
+    // bound-free rate estimators or an integral over the radiation field model, i.e. solver state of the host
+    const int nlevels_total = get_includedlevels();
+    std::vector<double> gammacorr;
+    gammacorr.reserve(static_cast<size_t>(nc) * static_cast<size_t>(nlevels_total));
+    for (int64_t cell = 0; cell < nc; cell++) {
+      for (int element = 0; element < get_nelements(); element++) {
+        for (int ion = 0; ion < get_nions(element); ion++) {
+          for (int level = 0; level < get_nlevels(element, ion); level++) {
+            const int ntargets = get_nphixstargets(element, ion, level);
+            const bool ionises = (ion < get_nions(element) - 1) && (level < get_nlevels_ionising(element, ion));
+            for (int k = 0; k < ntargets; k++) {
+              gammacorr.push_back(ionises ? get_corrphotoioncoeff(element, ion, level, k, static_cast<int>(cell), false) : 0.);
+            }
+          }
+        }
+      }
+    }
+    s.arr("cell.corrphotoioncoeff", gammacorr.data(), static_cast<int64_t>(gammacorr.size()));
+  }
   if constexpr (NT_ON) {
     // non-thermal routing state (ref_access/ref_nonthermal.cc): rate coefficients and channel probabilities per ion
     std::vector<double> ratecoeff;
@@ -356,6 +378,10 @@ void emit_estimators(Sink& s, const int nts) {
   s.arr("est.dep_positron", globals::dep_estimator_positron.data(), static_cast<int64_t>(globals::dep_estimator_positron.size()));
   s.arr("est.dep_electron", globals::dep_estimator_electron.data(), static_cast<int64_t>(globals::dep_estimator_electron.size()));
   s.arr("est.dep_alpha", globals::dep_estimator_alpha.data(), static_cast<int64_t>(globals::dep_estimator_alpha.size()));
+  if constexpr (DETAILED_BF_ESTIMATORS_ON) {
+    const auto bfrate = radfield::b200_bfrate_raw();
+    s.arr("est.bfrate_raw", bfrate.data(), static_cast<int64_t>(bfrate.size()));
+  }
   if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
     const auto jraw = radfield::b200_bins_J_raw();
     const auto nujraw = radfield::b200_bins_nuJ_raw();
@@ -522,6 +548,9 @@ void update_packets_gpu(const int nts, std::span<Packet> packets) {
   fetch_add<double>("est.dep_positron", globals::dep_estimator_positron);
   fetch_add<double>("est.dep_electron", globals::dep_estimator_electron);
   fetch_add<double>("est.dep_alpha", globals::dep_estimator_alpha);
+  if constexpr (DETAILED_BF_ESTIMATORS_ON) {
+    fetch_add<double>("est.bfrate_raw", radfield::b200_bfrate_raw());
+  }
   if constexpr (MULTIBIN_RADFIELD_MODEL_ON) {
     fetch_add<double>("est.bins_J_raw", radfield::b200_bins_J_raw());
     fetch_add<double>("est.bins_nuJ_raw", radfield::b200_bins_nuJ_raw());

@@ -30,6 +30,7 @@ GOLDEN = {
     "classic_nlte_toy": [2, 4],
     "classic_nt_toy": [2, 3],
     "classic_ntexc_toy": [2, 3],
+    "classic_detailedbf_toy": [1, 3],
     "kilonova_guttman_toy": [1],
     "kilonova_wollaeger_toy": [1],
     "kilonova_barnes_toy": [1],

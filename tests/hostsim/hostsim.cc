@@ -66,12 +66,23 @@ struct HostBackend {
     const long long saved_stride = T.scratch_stride;
     T.scratch_groundcont = scratch.data();
     T.scratch_stride = 1;
+    std::vector<double> bfcontr(static_cast<size_t>(T.nbfestim > 0 ? T.nbfestim : 1));
+    int bfwindow[2] = {0, 0};
+    double* const saved_bfcontr = T.scratch_bfcontr;
+    int* const saved_begin = T.scratch_bfestimbegin;
+    int* const saved_end = T.scratch_bfestimend;
+    T.scratch_bfcontr = bfcontr.data();
+    T.scratch_bfestimbegin = &bfwindow[0];
+    T.scratch_bfestimend = &bfwindow[1];
     ab::Accum acc{};
     for (int64_t i = 0; i < n; i++) {
       ab::test_kernel_item(T, acc, which, i, 0, in_f64, in_i32, out_f64, out_i32);
     }
     T.scratch_groundcont = saved;
     T.scratch_stride = saved_stride;
+    T.scratch_bfcontr = saved_bfcontr;
+    T.scratch_bfestimbegin = saved_begin;
+    T.scratch_bfestimend = saved_end;
     return true;
   }
 

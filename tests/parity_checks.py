@@ -81,6 +81,9 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
             if "est.bins_J_raw" in after:  # MULTIBIN_RADFIELD_MODEL_ON fixtures
                 assert "est.bins_J_raw" in est and after["est.bins_J_raw"].sum() > 0
                 names += ["est.bins_J_raw", "est.bins_nuJ_raw"]
+            if "est.bfrate_raw" in after:  # DETAILED_BF_ESTIMATORS_ON fixtures
+                assert "est.bfrate_raw" in est and after["est.bfrate_raw"].sum() > 0
+                names += ["est.bfrate_raw"]
             for name in names:
                 assert est_err.get(name, 0.0) <= est_tol, f"{name}: {est_err[name]:.3e}"
             m = 9  # ts.scalars[9] (nt_energy_deposited) is file-static in the reference and not dumped

@@ -99,6 +99,19 @@ CONFIGS = {
         model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
         run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=4, thick=8.0, ngrey=2, nlte_ts=1),
     ),
+    # classic_toy_1d with the detailed bound-free estimators of the NLTE presets (no photoionisation LUT)
+    "classic_detailedbf_toy": dict(
+        preset="classic",
+        opts=_opts(1500, None, None, {
+            "constexpr bool DETAILED_BF_ESTIMATORS_ON": "constexpr bool DETAILED_BF_ESTIMATORS_ON = true;",
+            "constexpr bool USE_LUT_PHOTOION": "constexpr bool USE_LUT_PHOTOION = false;",
+            "constexpr int DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP": "constexpr int DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP = 1;",
+            "constexpr bool LEVEL_HAS_BFEST": "constexpr bool LEVEL_HAS_BFEST(int element_z, int ionstage, int level) { return level <= 2; }",
+        }),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=4, thick=8.0, ngrey=2, nlte_ts=1),
+    ),
     "kilonova_toy": dict(
         preset="kilonova_lte",
         opts=_opts(1000, None, None, {
