@@ -16,12 +16,13 @@ PRESET_OF = {"classic_toy": "classic", "classic_toy_1d": "classic", "classic3d_t
              "classic_multibin_toy": "classic_multibin", "classic_nlte_toy": "classic_nlte",
              "kilonova_guttman_toy": "kilonova_guttman", "kilonova_wollaeger_toy": "kilonova_wollaeger",
              "kilonova_barnes_toy": "kilonova_barnes", "classic_nt_toy": "classic_nt",
-             "classic_ntexc_toy": "classic_ntexc", "classic_detailedbf_toy": "classic_detailedbf"}
+             "classic_ntexc_toy": "classic_ntexc", "classic_detailedbf_toy": "classic_detailedbf",
+             "nltephot_toy": "nltephotospheric"}
 GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_toy": [0, 2], "kilonova_toy": [1, 4],
                     "classic_multibin_toy": [2, 4], "classic_nlte_toy": [2, 4],
                     "kilonova_guttman_toy": [1], "kilonova_wollaeger_toy": [1], "kilonova_barnes_toy": [1],
                     "classic_nt_toy": [2, 3], "classic_ntexc_toy": [2, 3],
-                    "classic_detailedbf_toy": [1, 3]}
+                    "classic_detailedbf_toy": [1, 3], "nltephot_toy": [1, 3]}
 INTERACTIONS = 26  # stats::Counter::INTERACTIONS (reference stats.h:41)
 
 

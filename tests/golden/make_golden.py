@@ -31,6 +31,7 @@ GOLDEN = {
     "classic_nt_toy": [2, 3],
     "classic_ntexc_toy": [2, 3],
     "classic_detailedbf_toy": [1, 3],
+    "nltephot_toy": [1, 3],
     "kilonova_guttman_toy": [1],
     "kilonova_wollaeger_toy": [1],
     "kilonova_barnes_toy": [1],

@@ -112,6 +112,15 @@ CONFIGS = {
         model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
         run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=4, thick=8.0, ngrey=2, nlte_ts=1),
     ),
+    # BASELINE configs[4] in miniature: the reference's NLTE photospheric preset unchanged (NLTE levels, multi-bin radiation
+    # field, detailed bound-free estimators, Spencer-Fano non-thermal deposition with excitation) on the 1D toy model
+    "nltephot_toy": dict(
+        preset="nltephotospheric_dynamic_ion_range",
+        opts=_opts(1500),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="1d", ncell=20, vmax_kmps=20000.0, t_model_days=2.0, rho0=2e-11, v_e_kmps=3000.0, seed=1),
+        run=dict(seed=8, ntimesteps=8, tmin=4.0, tmax=40.0, nts_run=4, thick=8.0, ngrey=2, nlte_ts=1),
+    ),
     "kilonova_toy": dict(
         preset="kilonova_lte",
         opts=_opts(1000, None, None, {
