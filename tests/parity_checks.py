@@ -75,7 +75,16 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
         check_cell_tables(built, after)
         if n_fb == 0:
             assert int(est["counters"][fixtures.INTERACTIONS]) == int(after["counters"][fixtures.INTERACTIONS])
-            assert np.array_equal(est["counters"], after["counters"]), "event counters differ from the reference"
+            # UPSCATTER / DOWNSCATTER classify a macro-atom emission by comparing the new comoving frequency with the one
+            # the packet had when it was absorbed (macroatom.cc:227-232). After a resonance scattering the two agree to
+            # the last bit or two, so the classification follows the rounding of the Doppler factor (device libm vs
+            # glibc); every other counter, and the sum of the two, must be equal.
+            UP, DOWN = 30, 31
+            mine, ref_c = est["counters"].copy(), after["counters"].copy()
+            assert int(mine[UP] + mine[DOWN]) == int(ref_c[UP] + ref_c[DOWN]), "up- plus down-scatterings differ from the reference"
+            mine[[UP, DOWN]] = 0
+            ref_c[[UP, DOWN]] = 0
+            assert np.array_equal(mine, ref_c), f"event counters differ from the reference: {np.nonzero(mine != ref_c)[0]}"
             names = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
                      "est.dep_positron", "est.dep_electron", "est.dep_alpha"]
             if "est.bins_J_raw" in after:  # MULTIBIN_RADFIELD_MODEL_ON fixtures

@@ -13,7 +13,8 @@ from artis_b200 import lib as ablib
 from tests import abi_checks, fixtures, parity_checks, stochastic_checks
 
 pytestmark = pytest.mark.gpu
-CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
+# the NLTE photospheric case has its own file (test_gpu_zz_nltephot.py), which pytest collects after this one
+CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts if c != "nltephot_toy"]
 
 
 def _lib(config):
