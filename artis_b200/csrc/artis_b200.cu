@@ -297,7 +297,11 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
       ab::Pkt p;
       ab::ChiCont chi;
       ab::load_pkt<STAGE>(p, chi, T, ip);
+#if ARTISB200_CHI_PREPASS
+      const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot, STAGE == ab::ST_RTHIN};
+#else
       const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+#endif
       ab::run_stage<STAGE>(p, c, chi, max_steps);
       dest = ab::stage_of(p, T);
       ab::store_pkt<STAGE>(p, chi, T, ip, dest);
@@ -326,6 +330,63 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
   ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
   accum_flush(acc, T);
 }
+
+#if ARTISB200_CHI_PREPASS
+// Pre-pass of the detailed r-packet stage (rpkt.h chiterm_*): every packet of the stage's list says how many
+// bound-free terms its coming step needs; a warp reserves the room for its 32 requests with one atomic and writes
+// the (packet, continuum) descriptors; k_chi_terms then evaluates one term per thread.
+__global__ void __launch_bounds__(256) k_chi_prepass(const __grid_constant__ Tables T, const WfQueues q, const int cur) {
+  constexpr unsigned FULL = 0xffffffffU;
+  const unsigned int n = q.count[(cur * ab::NSTAGES) + ab::ST_RTHIN];
+  const int* __restrict__ in = q.list[cur][ab::ST_RTHIN];
+  const unsigned int lane = threadIdx.x & 31U;
+  const unsigned int stride = gridDim.x * blockDim.x;
+  const unsigned int n_warps = (n + 31U) & ~31U;
+  for (unsigned int k = (blockIdx.x * blockDim.x) + threadIdx.x; k < n_warps; k += stride) {
+    ab::ChiTermRequest r{-1, 0, 0, -1, 0.};
+    int ip = -1;
+    if (k < n) {
+      ip = in[k];
+      r = ab::chiterm_request(T, ip);
+    }
+    const unsigned int mine = (r.count > 0) ? static_cast<unsigned int>(r.count) : 0U;
+    unsigned int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int up = __shfl_up_sync(FULL, incl, d);
+      if (lane >= static_cast<unsigned int>(d)) {
+        incl += up;
+      }
+    }
+    const unsigned int total = __shfl_sync(FULL, incl, 31);
+    unsigned long long base = 0ULL;
+    if (lane == 0U && total != 0U) {
+      base = atomicAdd(T.chiterm_cursor, static_cast<unsigned long long>(total));
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (ip >= 0) {
+      const long long off = static_cast<long long>(base) + (incl - mine);
+      const bool fits = (off + mine) <= T.chiterm_capacity;
+      ab::chiterm_emit(T, ip, r, fits ? off : -1);
+      if (!fits) {
+        // the slots of this request below the capacity stay unused: mark them for the term kernel
+        for (long long j = off; j < off + mine && j < T.chiterm_capacity; j++) {
+          T.chiterm_desc[j] = {-1, 0};
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_chi_terms(const __grid_constant__ Tables T) {
+  const unsigned long long requested = *T.chiterm_cursor;
+  const long long n = (requested < static_cast<unsigned long long>(T.chiterm_capacity)) ? static_cast<long long>(requested) : T.chiterm_capacity;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x; idx < n; idx += stride) {
+    ab::chiterm_eval(T, idx);
+  }
+}
+#endif  // ARTISB200_CHI_PREPASS
 
 // Re-sort of the running lists by (stage, model cell): the appends keep them only roughly in cell order, and the
 // stages gather from per-cell tables (level populations, bound-free tables, gigabytes of cumulative macro-atom rates),
@@ -885,6 +946,14 @@ struct CudaBackend {
     // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
     unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
     grid = (grid > grid_limit) ? grid_limit : grid;
+#if ARTISB200_CHI_PREPASS
+    if constexpr (STAGE == ab::ST_RTHIN) {
+      const unsigned int pre_grid = static_cast<unsigned int>(sm_count * 8);
+      cudaMemsetAsync(T.chiterm_cursor, 0, sizeof(unsigned long long), on);
+      k_chi_prepass<<<(pre_grid > grid_limit) ? grid_limit : pre_grid, 256, 0, on>>>(T, q, cur);
+      k_chi_terms<<<pre_grid, 256, 0, on>>>(T);
+    }
+#endif
     k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, on>>>(T, q, cur, next, next_ma, max_steps);
   }
 
@@ -968,7 +1037,7 @@ struct CudaBackend {
           cur = 0;
         }
       }
-      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + (2 * ma_rounds) - 1);
+      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + (2 * ma_rounds) - 1 + (2 * ARTISB200_CHI_PREPASS));
       tm->iterations += sync_every;
       if (!ok(cudaMemcpyAsync(status, q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "status readback") ||
           !ok(cudaStreamSynchronize(stream), "wavefront iteration")) {

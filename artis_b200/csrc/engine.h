@@ -180,6 +180,29 @@ class Engine {
   PropagateTimings last;
   int64_t scratch_capacity{0};
   int64_t bfscratch_capacity{0};
+#if ARTISB200_CHI_PREPASS
+  int64_t chiterm_packets{0};  // packet capacity the per-packet term arrays were allocated for
+
+  void free_chiterms() {
+    void* ptrs[] = {T.chiterm_desc, T.chiterm_val, T.chiterm_cursor, T.chiterm_nu, T.chiterm_exp,
+                    T.chiterm_cell, T.chiterm_off, T.chiterm_cnt};
+    for (void* ptr : ptrs) {
+      if (ptr != nullptr) {
+        be.free(ptr);
+      }
+    }
+    T.chiterm_desc = nullptr;
+    T.chiterm_val = nullptr;
+    T.chiterm_cursor = nullptr;
+    T.chiterm_nu = nullptr;
+    T.chiterm_exp = nullptr;
+    T.chiterm_cell = nullptr;
+    T.chiterm_off = nullptr;
+    T.chiterm_cnt = nullptr;
+    T.chiterm_capacity = 0;
+    chiterm_packets = 0;
+  }
+#endif
 
   int fail(const std::string& msg) {
     err = msg;
@@ -223,6 +246,9 @@ class Engine {
       T.scratch_bfestimend = nullptr;
       bfscratch_capacity = 0;
     }
+#if ARTISB200_CHI_PREPASS
+    free_chiterms();
+#endif
     for (void* ptr : soa_save) {
       be.free(ptr);
     }
@@ -763,6 +789,37 @@ class Engine {
         bfscratch_capacity = need;
       }
     }
+#if ARTISB200_CHI_PREPASS
+    if (chiterm_packets < packet_capacity) {
+      free_chiterms();
+      int64_t terms = packet_capacity * static_cast<int64_t>(ARTISB200_CHITERMS_PER_PACKET);
+      if (ARTISB200_CHITERMS_CAP > 0 && terms > ARTISB200_CHITERMS_CAP) {
+        terms = ARTISB200_CHITERMS_CAP;
+      }
+      if (terms >= (1LL << 31)) {
+        return fail("bound-free term buffer: more than 2^31 terms");
+      }
+      T.chiterm_desc = static_cast<ChiTermDesc*>(be.alloc(terms * static_cast<int64_t>(sizeof(ChiTermDesc))));
+      T.chiterm_val = static_cast<ChiTermVal*>(be.alloc(terms * static_cast<int64_t>(sizeof(ChiTermVal))));
+      T.chiterm_cursor = static_cast<unsigned long long*>(be.alloc(8));
+      T.chiterm_nu = static_cast<double*>(be.alloc(packet_capacity * 8));
+      T.chiterm_exp = static_cast<double*>(be.alloc(packet_capacity * 8));
+      T.chiterm_cell = static_cast<int*>(be.alloc(packet_capacity * 4));
+      T.chiterm_off = static_cast<int*>(be.alloc(packet_capacity * 4));
+      T.chiterm_cnt = static_cast<int*>(be.alloc(packet_capacity * 4));
+      if (T.chiterm_desc == nullptr || T.chiterm_val == nullptr || T.chiterm_cursor == nullptr || T.chiterm_nu == nullptr ||
+          T.chiterm_exp == nullptr || T.chiterm_cell == nullptr || T.chiterm_off == nullptr || T.chiterm_cnt == nullptr) {
+        return fail("bound-free term buffer allocation failed: " + be.last_error());
+      }
+      be.zero(T.chiterm_cursor, 8);
+      be.zero(T.chiterm_nu, packet_capacity * 8);
+      be.zero(T.chiterm_cell, packet_capacity * 4);
+      be.zero(T.chiterm_off, packet_capacity * 4);
+      be.zero(T.chiterm_cnt, packet_capacity * 4);  // 0 terms for nu == 0: never matches a packet
+      T.chiterm_capacity = terms;
+      chiterm_packets = packet_capacity;
+    }
+#endif
     const int64_t need = n * stride;
     if (need > aos_staging_bytes) {
       if (aos_staging != nullptr) {

@@ -96,6 +96,14 @@ AHD int lowest_set_bit(const unsigned long long bits) {
 #endif
 }
 
+AHD int popcount64(const unsigned long long bits) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(bits);
+#else
+  return __builtin_popcountll(bits);
+#endif
+}
+
 // physical constants [cgs] (values as in the reference's constants.h:21-70 so that results agree)
 constexpr double CLIGHT = 2.99792458e+10;
 constexpr double CLIGHT_PROP = CLIGHT;

@@ -190,6 +190,7 @@ enum : int {
   DIAG_GAMMA_EVENTS = 9,
   DIAG_KERNEL_LAUNCHES = 10,
   DIAG_PACKET_SEGMENTS = 11,
+  DIAG_CONT_TERMS_PREPASS = 12,  // of DIAG_CONT_TERMS: taken from the term kernel's buffer (ARTISB200_CHI_PREPASS builds)
 };
 
 // Packet state in HBM (device resident across timesteps). Field set = reference Packet (packet.h:109-156) plus the
@@ -253,6 +254,27 @@ struct alignas(32) ContStatic {
 struct alignas(16) CellCont {
   double nnlevel;
   double edgepart;  // departure * exp(h nu_edge / kT), or < 0: use the slow form (rpkt.cc:873-889)
+};
+
+// ARTISB200_CHI_PREPASS=1 (experimental, off in the shipped libraries): the terms of the bound-free opacity sums an
+// iteration's detailed r-packet steps will need are evaluated by a kernel of their own, one thread per (packet,
+// continuum) term, and the r-packet stage only adds them up in order (rpkt.h chiterm_*). See DESIGN.md section 9.
+#ifndef ARTISB200_CHI_PREPASS
+#define ARTISB200_CHI_PREPASS 0
+#endif
+#ifndef ARTISB200_CHITERMS_PER_PACKET
+#define ARTISB200_CHITERMS_PER_PACKET 16  // capacity of the term buffer per packet of capacity (overflow: inline sum)
+#endif
+#ifndef ARTISB200_CHITERMS_CAP
+#define ARTISB200_CHITERMS_CAP 0  // > 0: absolute upper limit of the term buffer (tests of the overflow path)
+#endif
+struct ChiTermDesc {
+  int ip;    // packet, or -1: slot of a request that did not fit
+  int cont;  // continuum index
+};
+struct alignas(16) ChiTermVal {
+  double chi_contr;    // nnlevel * sigma_contr
+  double sigma_contr;
 };
 
 struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_time/trueemissiontype
@@ -351,6 +373,18 @@ struct Tables {
   // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
   double* scratch_groundcont;
   long long scratch_stride;
+#if ARTISB200_CHI_PREPASS
+  ChiTermDesc* chiterm_desc;           // [chiterm_capacity]
+  ChiTermVal* chiterm_val;             // [chiterm_capacity]
+  long long chiterm_capacity;
+  unsigned long long* chiterm_cursor;  // terms requested in the running iteration
+  // per packet: the evaluation the terms were requested for, and where they are
+  double* chiterm_nu;
+  double* chiterm_exp;  // exp(-h nu / k T_e)
+  int* chiterm_cell;
+  int* chiterm_off;
+  int* chiterm_cnt;     // -1: nothing requested (or already consumed)
+#endif
 };
 
 }  // namespace ab

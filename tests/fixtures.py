@@ -34,15 +34,16 @@ def load_golden(config, nts):
     return {"config": config, "nts": nts, "static": static, "before": before, "after": after}
 
 
-def hostsim_library(preset):
-    """test-only single-threaded host build of the device headers (tests/hostsim/hostsim.cc); built on demand"""
-    out = os.path.join(ROOT, "tests", "_build", f"libartis_b200_hostsim_{preset}.so")
+def hostsim_library(preset, defines=(), tag=""):
+    """test-only single-threaded host build of the device headers (tests/hostsim/hostsim.cc); built on demand.
+    `defines` / `tag`: a variant with extra -D flags (compile-time experiments such as ARTISB200_CHI_PREPASS)"""
+    out = os.path.join(ROOT, "tests", "_build", f"libartis_b200_hostsim_{preset}{tag}.so")
     csrc = os.path.join(ROOT, "artis_b200", "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")] + [os.path.join(ROOT, "tests", "hostsim", "hostsim.cc")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                        "-Wno-subobject-linkage", "-I" + csrc, f"-DARTISB200_PRESET_HEADER=\"options/preset_{preset}.h\"",
+                        "-Wno-subobject-linkage", "-I" + csrc, *[f"-D{d}" for d in defines], f"-DARTISB200_PRESET_HEADER=\"options/preset_{preset}.h\"",
                         os.path.join(ROOT, "tests", "hostsim", "hostsim.cc"), "-o", out], check=True)
     os.environ["ARTISB200_ALLOW_HOSTSIM"] = "1"
     return out

@@ -58,3 +58,27 @@ def test_abi_reports_misuse():
 @pytest.mark.parametrize("preset", ["classic", "kilonova_lte", "classic_multibin", "classic_nlte"])
 def test_options_summary_names_the_preset(preset):
     abi_checks.check_options_summary(fixtures.hostsim_library(preset), preset)
+
+
+# ARTISB200_CHI_PREPASS (experimental compile-time variant): bound-free terms evaluated by a
+# kernel of their own ahead of the detailed r-packet stage. Same packets, estimators and counters; the second variant
+# has a term buffer of 8 terms, so that most requests do not fit and fall back to the inline sum.
+PREPASS_CASES = [("classic_toy", 3), ("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_detailedbf_toy", 3), ("nltephot_toy", 3)]
+PREPASS_SCHEDULES = ["wavefront-notail", "wavefront-resort", "wavefront-tail"]
+
+
+@pytest.mark.parametrize("tag,defines", [("_prepass", ("ARTISB200_CHI_PREPASS=1",)),
+                                         ("_prepass_tiny", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_CHITERMS_CAP=8"))])
+@pytest.mark.parametrize("schedule", PREPASS_SCHEDULES)
+@pytest.mark.parametrize("config,nts", PREPASS_CASES)
+def test_chi_prepass_variant_keeps_histories(config, nts, schedule, tag, defines):
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=defines, tag=tag)
+    _, _, est = parity_checks.check_packet_histories(lib, config, nts, options=SCHEDULES[schedule])
+    terms, from_buffer = int(est["diag"][3]), int(est["diag"][12])
+    assert 0 <= from_buffer <= terms
+    if tag == "_prepass":
+        assert from_buffer > 0
+    if tag == "_prepass" and schedule != "wavefront-tail":  # (the tail kernel and steps 2.. of a visit sum inline)
+        assert from_buffer > 0.9 * terms
+    if tag == "_prepass_tiny":
+        assert from_buffer < terms  # some requests did not fit and were summed inline
