@@ -11,6 +11,43 @@
 #include <string>
 #include <vector>
 
+#ifdef ARTISB200_HOSTSIM_FUZZ_LIBM
+// Emulation of "another libm" (the device's exp/log/sin/cos/pow are correct to 1-2 ulp, not bit-equal to glibc's):
+// every transcendental result is moved by -1, 0 or +1 ulp, chosen by a hash of its bits. The parity tests run with this
+// build at the GPU tolerance show which assertions depend on the last bit of a libm result. sqrt and the four
+// arithmetic operations are IEEE-exact on both sides and are left alone.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <unordered_map>
+inline double abfz(const double v) {
+  if (!std::isfinite(v) || v == 0.) {
+    return v;
+  }
+  std::uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(bits));
+  const std::uint64_t h = (bits * 0x9E3779B97F4A7C15ULL) >> 40;
+  const int pick = static_cast<int>(h % 3ULL);
+  return (pick == 0) ? v : std::nextafter(v, (pick == 1) ? std::numeric_limits<double>::infinity() : -std::numeric_limits<double>::infinity());
+}
+namespace std {
+using ::abfz;
+}
+#define exp(x) abfz(::exp(x))
+#define expm1(x) abfz(::expm1(x))
+#define log(x) abfz(::log(x))
+#define sin(x) abfz(::sin(x))
+#define cos(x) abfz(::cos(x))
+#define acos(x) abfz(::acos(x))
+#define atan2(y, x) abfz(::atan2(y, x))
+#define cbrt(x) abfz(::cbrt(x))
+#define pow(x, y) abfz(::pow(x, y))
+#endif
+
 #include "convert.h"
 #include "engine.h"
 #include "propagate.h"
