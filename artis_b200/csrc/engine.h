@@ -535,6 +535,20 @@ class Engine {
       matrans_total += (2LL * l_ndown[l]) + l_nup[l];
     }
     T.matrans_total = static_cast<int>(matrans_total);
+#if ARTISB200_MA_SUMMARY
+    {
+      std::vector<int> masum_start(static_cast<size_t>(T.nlevels));
+      long long masum_total = 0;
+      for (int l = 0; l < T.nlevels; l++) {
+        masum_start[static_cast<size_t>(l)] = static_cast<int>(masum_total);
+        masum_total += (2LL * (l_ndown[l] / 8)) + (l_nup[l] / 8);
+      }
+      T.masum_total = static_cast<int>(masum_total);
+      if (!make_derived("derived.level_masum_start", masum_start, &T.level_masum_start)) {
+        return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
+      }
+    }
+#endif
     // static half of the bound-free terms (tables.h ContStatic)
     {
       const auto* c_nu_edge = host<double>("cont.nu_edge");
@@ -645,6 +659,9 @@ class Engine {
     ok = ok && alloc_output("built.levelpops", 'd', nc * T.nlevels, &T.cell_levelpops);
     ok = ok && alloc_output("built.maprocessrates", 'd', nc * T.nlevels * MA_ACTION_COUNT, &T.cell_maprocessrates);
     ok = ok && alloc_output("built.matrans", 'd', nc * static_cast<int64_t>(T.matrans_total), &T.cell_matrans);
+#if ARTISB200_MA_SUMMARY
+    ok = ok && alloc_output("built.masum", 'd', nc * static_cast<int64_t>(T.masum_total), &T.cell_masum);
+#endif
     ok = ok && alloc_output("built.cooling_contrib", 'd', nc * T.ncoolingterms, &T.cell_cooling_contrib);
     ok = ok && alloc_output("built.cont_nnlevel", 'd', nc * T.nbfcontinua, &T.cell_cont_nnlevel);
     ok = ok && alloc_output("built.cont_keepbits", 'Q', nc * T.keepwords, &T.cell_cont_keepbits);

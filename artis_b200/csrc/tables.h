@@ -268,6 +268,12 @@ struct alignas(16) CellCont {
 #ifndef ARTISB200_CHITERMS_CAP
 #define ARTISB200_CHITERMS_CAP 0  // > 0: absolute upper limit of the term buffer (tests of the overflow path)
 #endif
+// ARTISB200_MA_SUMMARY=1 (experimental, off in the shipped libraries): every 8th value of each cumulative macro-atom
+// rate array is also kept in a summary table an eighth of the size, so that a search reads one or two sectors of the
+// summary and one 64-byte window of the array instead of a sector per probe (macroatom.h index_upperbound_summary).
+#ifndef ARTISB200_MA_SUMMARY
+#define ARTISB200_MA_SUMMARY 0
+#endif
 struct ChiTermDesc {
   int ip;    // packet, or -1: slot of a request that did not fit
   int cont;  // continuum index
@@ -373,6 +379,11 @@ struct Tables {
   // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
   double* scratch_groundcont;
   long long scratch_stride;
+#if ARTISB200_MA_SUMMARY
+  double* cell_masum;                // [ncells][masum_total]: per level a[8j+7] of the three cumulative arrays
+  const int* level_masum_start;      // [nlevels]
+  int masum_total;                   // sum over levels of 2*(ndown/8) + nup/8
+#endif
 #if ARTISB200_CHI_PREPASS
   ChiTermDesc* chiterm_desc;           // [chiterm_capacity]
   ChiTermVal* chiterm_val;             // [chiterm_capacity]

@@ -68,7 +68,8 @@ PREPASS_SCHEDULES = ["wavefront-notail", "wavefront-resort", "wavefront-tail"]
 
 
 @pytest.mark.parametrize("tag,defines", [("_prepass", ("ARTISB200_CHI_PREPASS=1",)),
-                                         ("_prepass_tiny", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_CHITERMS_CAP=8"))])
+                                         ("_prepass_tiny", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_CHITERMS_CAP=8")),
+                                         ("_prepass_masum", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_MA_SUMMARY=1"))])
 @pytest.mark.parametrize("schedule", PREPASS_SCHEDULES)
 @pytest.mark.parametrize("config,nts", PREPASS_CASES)
 def test_chi_prepass_variant_keeps_histories(config, nts, schedule, tag, defines):
@@ -76,7 +77,7 @@ def test_chi_prepass_variant_keeps_histories(config, nts, schedule, tag, defines
     _, _, est = parity_checks.check_packet_histories(lib, config, nts, options=SCHEDULES[schedule])
     terms, from_buffer = int(est["diag"][3]), int(est["diag"][12])
     assert 0 <= from_buffer <= terms
-    if tag == "_prepass":
+    if tag != "_prepass_tiny":
         assert from_buffer > 0
     if tag == "_prepass" and schedule != "wavefront-tail":  # (the tail kernel and steps 2.. of a visit sum inline)
         assert from_buffer > 0.9 * terms
@@ -94,3 +95,29 @@ def test_parity_assertions_do_not_depend_on_libm_rounding(config, nts):
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=("ARTISB200_HOSTSIM_FUZZ_LIBM",), tag="_fuzz")
     parity_checks.check_packet_histories(lib, config, nts, tol=1e-9, est_tol=1e-9, options={"schedule": 0})
     parity_checks.check_packet_histories(lib, config, nts, tol=1e-9, est_tol=1e-9, options=SCHEDULES["wavefront-resort"])
+
+
+# ARTISB200_MA_SUMMARY (experimental compile-time variant): macro-atom searches through a summary of
+# every 8th cumulative rate. Same transitions selected, hence the same packets, estimators and counters.
+@pytest.mark.parametrize("schedule", ["history", "wavefront-rounds", "wavefront-walk"])
+@pytest.mark.parametrize("config,nts", PREPASS_CASES + [("classic_nt_toy", 3), ("classic_nlte_toy", 4)])
+def test_ma_summary_variant_keeps_histories(config, nts, schedule):
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=("ARTISB200_MA_SUMMARY=1",), tag="_masum")
+    plain = fixtures.hostsim_library(fixtures.PRESET_OF[config])
+    _, _, est = parity_checks.check_packet_histories(lib, config, nts, options=SCHEDULES[schedule])
+    _, _, est_plain = parity_checks.check_packet_histories(plain, config, nts, options=SCHEDULES[schedule])
+    assert int(est["diag"][6]) == int(est_plain["diag"][6]) > 0     # macro-atom transitions taken
+    assert int(est["diag"][4]) == int(est_plain["diag"][4])         # the work counter of the searches is kept
+
+
+def test_macroatom_searches_equal_upper_bound(tmp_path):
+    # tests/hostsim/search_check.cc: the 8-way search and the summary search against std::upper_bound (lengths 0..700)
+    import os
+    import subprocess
+    csrc = os.path.join(fixtures.ROOT, "artis_b200", "csrc")
+    exe = str(tmp_path / "search_check")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-subobject-linkage", "-I" + csrc,
+                    "-DARTISB200_MA_SUMMARY=1", "-DARTISB200_PRESET_HEADER=\"options/preset_kilonova_lte.h\"",
+                    os.path.join(fixtures.ROOT, "tests", "hostsim", "search_check.cc"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("ok "), out
