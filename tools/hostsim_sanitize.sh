@@ -1,12 +1,12 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE: compile the physics headers for the host (tests/hostsim) with AddressSanitizer + UBSan and replay
-# oracle fixtures through every schedule. usage: bash tools/hostsim_sanitize.sh [preset config nts]
+# oracle fixtures through every schedule. usage: [EXTRA_DEFS="-DARTISB200_CHI_PREPASS=1 ..."] bash tools/hostsim_sanitize.sh [preset config nts]
 set -eu
 cd "$(dirname "$0")/.."
 PRESET=${1:-kilonova_lte}; CONFIG=${2:-kilonova_toy}; NTS=${3:-4}
 OUT=/tmp/artis_b200_asan; mkdir -p $OUT
 g++ -std=c++20 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -ffp-contract=off -fPIC -shared -Wno-unknown-pragmas \
-    -Wno-subobject-linkage -Iartis_b200/csrc "-DARTISB200_PRESET_HEADER=\"options/preset_${PRESET}.h\"" tests/hostsim/hostsim.cc \
+    -Wno-subobject-linkage -Iartis_b200/csrc ${EXTRA_DEFS:-} "-DARTISB200_PRESET_HEADER=\"options/preset_${PRESET}.h\"" tests/hostsim/hostsim.cc \
     -o $OUT/libhostsim_${PRESET}.so
 cat > $OUT/run.py <<PY
 import os, sys
