@@ -101,3 +101,27 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
                 assert np.abs(est["ts.scalars"][:m] - after["ts.scalars"][:m]).max() / scale <= est_tol
             assert int(est["ts.pellet_decays"][0]) == int(after["ts.pellet_decays"][0])
     return frac_ok, n_fb, est
+
+
+def check_idempotence(libpath, config, nts, options=None):
+    """update_packets on packets that have already been propagated to the end of the timestep changes nothing: not a
+    byte of a packet (no step, no random number drawn), no estimator, no event counter (update_packets.cc:321-326: a
+    packet is only processed while prop_time < ts_end and it has not escaped)"""
+    fx = fixtures.load_golden(config, nts)
+    eng = fixtures.make_engine(libpath, fx, rng="xoshiro", options=options)
+    before = fx["before"]
+    n = int(before["packets.count"][0])
+    stride = int(before["packets.stride"][0])
+    aos = before["packets.aos"].copy()
+    eng.update_packets_host(nts, aos, n, stride)
+    est1 = eng.estimators()
+    again = aos.copy()
+    eng.update_packets_host(nts, again, n, stride)
+    est2 = eng.estimators()
+    eng.close()
+    assert np.array_equal(again, aos), "a second update_packets of the same timestep moved packets"
+    for name, value in est1.items():
+        if name == "diag":  # work counters: the second call still launches (empty) kernels
+            continue
+        assert np.array_equal(value, est2[name], equal_nan=True), f"{name} changed in a second update_packets of the same timestep"
+    return n

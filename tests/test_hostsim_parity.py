@@ -121,3 +121,10 @@ def test_macroatom_searches_equal_upper_bound(tmp_path):
                     os.path.join(fixtures.ROOT, "tests", "hostsim", "search_check.cc"), "-o", exe], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.startswith("ok "), out
+
+
+@pytest.mark.parametrize("schedule", ["history", "wavefront-notail", "wavefront-resort"])
+@pytest.mark.parametrize("config,nts", [("kilonova_toy", 1), ("classic3d_toy", 0), ("classic_nt_toy", 3)])
+def test_update_packets_is_idempotent_within_a_timestep(config, nts, schedule):
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
+    assert parity_checks.check_idempotence(lib, config, nts, options=SCHEDULES[schedule]) > 0
