@@ -74,11 +74,22 @@ __global__ void k_build_keepwords(const __grid_constant__ Tables T) {
   }
 }
 
+// ARTISB200_BUILD_CELL_LANES=1 (experimental, off in the shipped libraries): the lanes of a warp
+// build the same level in 32 consecutive cells instead of 32 consecutive levels of one cell - equal trip counts and
+// branches across the warp, and the atomic-data loads (transition targets, A values, collision strengths, level
+// energies) become one broadcast transaction instead of 32 gathers. Same function per (cell, level), same tables.
+#ifndef ARTISB200_BUILD_CELL_LANES
+#define ARTISB200_BUILD_CELL_LANES 0
+#endif
 __global__ void k_build_macroatom(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(T.ncells) * T.nlevels;
   if (idx < total) {
+#if ARTISB200_BUILD_CELL_LANES
+    ab::build_macroatom_level(T, static_cast<int>(idx % T.ncells), static_cast<int>(idx / T.ncells));
+#else
     ab::build_macroatom_level(T, static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+#endif
   }
 }
 
