@@ -1,7 +1,7 @@
 """GPU parity of the reference's NLTE photospheric preset, unmodified (BASELINE configs[4] in miniature: NLTE level
 populations, multi-bin radiation field, detailed bound-free estimators without the photoionisation LUT, Spencer-Fano
 non-thermal deposition with excitation), against the oracle fixture nltephot_toy. Same assertions as
-tests/test_gpu_parity.py; kept in its own file, collected last, because it is the newest preset."""
+tests/test_gpu_parity.py, in a file of its own (the newest preset; DESIGN.md section 8 has its GPU history)."""
 import pytest
 
 from artis_b200 import lib as ablib
