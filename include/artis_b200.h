@@ -58,9 +58,10 @@
  *       nt_exc_ratecoeffperdeposition 'd' [Nc*stored], cell.nt_deposition_rate_density 'd'[Nc], cell.nt_frac_excitation 'f'[Nc]
  *       (NT_EXCITATION_ON only): nonthermal.cc:202-212, 364-367, 2382-2385, 1186-1195
  *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
- *   cell.corrphotoioncoeff 'd'[Nc*Nbf]  (USE_LUT_PHOTOION == false only): the corrected photoionisation coefficient of every
- *       continuum in the cell's radiation field, ratecoeff.cc:840 get_corrphotoioncoeff (the integral the reference keeps in its
- *       cell cache), evaluated by the host for the timestep (integration/update_packets_b200.cc)
+ *   cell.corrphotoioncoeff 'd'[Nc*(total photoionisation targets)], indexed by level.phixstargetstart + target
+ *       (USE_LUT_PHOTOION == false only): the corrected photoionisation coefficient of every continuum in the cell's
+ *       radiation field, ratecoeff.cc:840 get_corrphotoioncoeff (the integral the reference keeps in its cell cache),
+ *       evaluated by the host for the timestep (integration/update_packets_b200.cc)
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132
  *   est.gamma/bfheating 'd'[Nc*Ng] globals.h:126-129   est.dep_gamma/dep_positron/dep_electron/dep_alpha 'd'[Nc] globals.h:118-121
