@@ -141,7 +141,7 @@ AHD void soa_to_aos_one(const Tables& T, unsigned char* aos, const int stride, c
 
 namespace ab {
 
-enum : int { TESTK_BOUNDARY_DISTANCE = 0, TESTK_CLOSEST_TRANSITION = 1, TESTK_CHI_RPKT_CONT = 2 };
+enum : int { TESTK_BOUNDARY_DISTANCE = 0, TESTK_CLOSEST_TRANSITION = 1, TESTK_CHI_RPKT_CONT = 2, TESTK_SELECT_CONTINUUM_NU = 3 };
 
 // one element of artisb200_test_kernel()
 AHD void test_kernel_item(const Tables& T, Accum& acc, const int which, const long long i, const long long tid,
@@ -155,6 +155,11 @@ AHD void test_kernel_item(const Tables& T, Accum& acc, const int which, const lo
     out_i32[i] = hit.next_cellindex;
   } else if (which == TESTK_CLOSEST_TRANSITION) {
     out_i32[i] = closest_transition(T, in_f64[i], in_i32[i], c);
+  } else if (which == TESTK_SELECT_CONTINUUM_NU) {
+    // in: (T_e, zrand) per item and the continuum (index into the allcont list); out: the sampled frequency
+    const int ci = in_i32[i];
+    out_f64[i] = select_continuum_nu_z(T, T.cont_element[ci], T.cont_ion[ci], T.cont_level[ci], T.cont_phixstargetindex[ci],
+                                       static_cast<float>(in_f64[(i * 2) + 0]), in_f64[(i * 2) + 1]);
   } else {
     ChiCont chi;
     chi.nu = -1.;

@@ -4,6 +4,7 @@
 // (select_continuum_nu); kpkt.cc:266-276 (sample_planck_montecarlo).
 #pragma once
 #include "atomicdata.h"
+#include "gk.h"
 #include "hd.h"
 #include "options.h"
 #include "packet.h"
@@ -120,45 +121,17 @@ AHD double alpha_sp_E_integrand(const Tables& T, const double nu_minus_nu_edge, 
   return (2 / CLIGHTSQUARED) * sigma_bf * pow3(nu) / nu_edge * exp(-HOVERKB * nu_minus_nu_edge / T_e);
 }
 
-// integral of the emissivity over [a, b], split at the knots of the cross-section table (where the tabulated
-// cross section has kinks, or steps with PHIXS_CLASSIC_NO_INTERPOLATION) with 5-point Gauss-Legendre on each part
-AHD double emissivity_piece_integral(const Tables& T, const double a, const double b, const double nu_edge,
-                                     const float T_e, const float* photoion_xs) {
-  constexpr double gl_x[5] = {-0.9061798459386640, -0.5384693101056831, 0.0, 0.5384693101056831, 0.9061798459386640};
-  constexpr double gl_w[5] = {0.2369268850561891, 0.4786286704993665, 0.5688888888888889, 0.4786286704993665,
-                              0.2369268850561891};
-  const double knotspacing = T.nphixsnuincrement * nu_edge;
-  double total = 0.;
-  double lo = a;
-  long long k = static_cast<long long>(floor(a / knotspacing)) + 1;
-  while (lo < b) {
-    double hi = static_cast<double>(k) * knotspacing;
-    if (!(hi < b)) {
-      hi = b;
-    }
-    if (hi > lo) {
-      const double half = 0.5 * (hi - lo);
-      const double mid = 0.5 * (hi + lo);
-      double s = 0.;
-#pragma unroll
-      for (int q = 0; q < 5; q++) {
-        s += gl_w[q] * alpha_sp_E_integrand(T, mid + (half * gl_x[q]), nu_edge, T_e, photoion_xs);
-      }
-      total += s * half;
-    }
-    lo = hi;
-    k++;
-  }
-  return total;
-}
-
 // Sample the frequency of a free-bound emission into (element, lowerion, lower) from the target
-// phixstargetindex (ratecoeff.cc:563-638). The reference evaluates up to NPHIXSPOINTS adaptive 31-point
-// Gauss-Kronrod tail integrals per call (relative accuracy 1e-3); here the same tail integrals at the same
-// piece boundaries come from one pass of fixed-order quadrature over the pieces, and the selection and the
-// in-piece linear interpolation follow the reference exactly. One draw.
-AHD double select_continuum_nu(const Tables& T, const int element, const int lowerion, const int lower,
-                               const int phixstargetindex, const float T_e, Rng& rng) {
+// phixstargetindex (ratecoeff.cc:563-638): the normalisation integral of the energy-weighted emissivity over the
+// whole continuum, then the tail integrals above the boundaries of the NPHIXSPOINTS pieces until the drawn fraction is
+// bracketed, and a linear interpolation inside that piece. Every integral is the reference's adaptive 31-point
+// Gauss-Kronrod rule at its relative accuracy (ratecoeff.cc:37), evaluated in the reference's order (gk.h), so the
+// sampled frequency agrees with the reference's to rounding and the packet's history continues identically. One draw.
+constexpr double RATECOEFF_INTEGRAL_ACCURACY = 1e-3;  // ratecoeff.cc:37
+
+// `zrand` = 1 - (the packet's draw), 0 < zrand <= 1
+AHD double select_continuum_nu_z(const Tables& T, const int element, const int lowerion, const int lower,
+                                 const int phixstargetindex, const float T_e, const double zrand) {
   const int lower_ulev = uniquelevel(T, element, lowerion, lower);
   const double E_threshold = phixs_threshold(T, element, lowerion, lower, phixstargetindex);
   const double nu_threshold = (1. / H) * E_threshold;
@@ -166,28 +139,24 @@ AHD double select_continuum_nu(const Tables& T, const int element, const int low
   const int npieces = static_cast<int>(T.nphixspoints);
   const float* photoion_xs = phixs_table(T, lower_ulev);
 
-  const double zrand = 1. - rng.uniform();  // 0 < zrand <= 1
-
   const double nu_range = nu_max_phixs - nu_threshold;
   const double deltanu = nu_range / npieces;
+  const auto integrand = [&](const double nu_minus_nu_edge) {
+    return alpha_sp_E_integrand(T, nu_minus_nu_edge, nu_threshold, T_e, photoion_xs);
+  };
 
-  double emissivity_integral_total = 0.;
-  for (int j = 0; j < npieces; j++) {
-    emissivity_integral_total +=
-        emissivity_piece_integral(T, j * deltanu, (j + 1) * deltanu, nu_threshold, T_e, photoion_xs);
-  }
+  const double emissivity_integral_total = gk_integrate<31>(integrand, 0., nu_range, RATECOEFF_INTEGRAL_ACCURACY);
   if (!(emissivity_integral_total > 0.) || !is_finite(emissivity_integral_total)) {
     return nu_threshold;
   }
 
   double emissivity_tailintegral_prev = emissivity_integral_total;
   double emissivity_tailintegral = emissivity_integral_total;
-  double prefix = 0.;
   int i = 1;
   for (; i < npieces; i++) {
     emissivity_tailintegral_prev = emissivity_tailintegral;
-    prefix += emissivity_piece_integral(T, (i - 1) * deltanu, i * deltanu, nu_threshold, T_e, photoion_xs);
-    emissivity_tailintegral = dmax(emissivity_integral_total - prefix, 0.);
+    const double nu_minus_nu_edge_low = i * deltanu;
+    emissivity_tailintegral = gk_integrate<31>(integrand, nu_minus_nu_edge_low, nu_range, RATECOEFF_INTEGRAL_ACCURACY);
     if (zrand >= emissivity_tailintegral / emissivity_integral_total) {
       break;
     }
@@ -203,6 +172,12 @@ AHD double select_continuum_nu(const Tables& T, const int element, const int low
     nuoffset = (emissivity_tailintegral - (emissivity_integral_total * zrand)) / emissivity_tailintegral * deltanu;
   }
   return nu_threshold + ((i - 1) * deltanu) + nuoffset;
+}
+
+AHD double select_continuum_nu(const Tables& T, const int element, const int lowerion, const int lower,
+                               const int phixstargetindex, const float T_e, Rng& rng) {
+  const double zrand = 1. - rng.uniform();  // 0 < zrand <= 1 (ratecoeff.cc:575)
+  return select_continuum_nu_z(T, element, lowerion, lower, phixstargetindex, T_e, zrand);
 }
 
 }  // namespace ab

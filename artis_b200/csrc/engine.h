@@ -73,7 +73,7 @@ inline const FieldDesc* find_field(const std::string& name) {
   return nullptr;
 }
 
-// FNV-1a over the canonical option string; the reference-side binding builds the same string from artisoptions.h
+// human-readable summary of the compiled-in options (the guard itself is the hash of include/artis_b200_options.h)
 inline std::string options_summary_string() {
   char buf[1024];
   std::snprintf(buf, sizeof(buf),
@@ -86,19 +86,18 @@ inline std::string options_summary_string() {
                 opt::FIRST_NLTE_RADFIELD_TIMESTEP, opt::DIRECT_COL_HEAT, opt::NT_ON, opt::NT_SOLVE_SPENCERFANO,
                 opt::LTEPOP_EXCITATION_USE_TJ, opt::BFCOOLING_USELEVELPOPNOTIONPOP, opt::PARTICLE_THERMALISATION_SCHEME,
                 opt::GAMMA_THERMALISATION_SCHEME, opt::MINPOP, opt::NU_MIN_R, opt::NU_MAX_R);
-  return buf;
+  std::string out(buf);
+  // ... and every hashed value by name (include/artis_b200_options.h)
+  out += ";all:";
+#define X(name)                                                                  \
+  std::snprintf(buf, sizeof(buf), " " #name "=%g", static_cast<double>(opt::name)); \
+  out += buf;
+  ARTISB200_OPTION_VALUE_LIST(X)
+#undef X
+  return out;
 }
 
-inline uint64_t options_hash_value() {
-  const std::string s = options_summary_string();
-  const auto start = s.find(';');  // the preset NAME is not part of the hash, only the values
-  uint64_t h = 1469598103934665603ULL;
-  for (size_t i = start; i < s.size(); i++) {
-    h ^= static_cast<unsigned char>(s[i]);
-    h *= 1099511628211ULL;
-  }
-  return h;
-}
+inline uint64_t options_hash_value() { return artisb200_options_hash_here(); }
 
 // how update_packets schedules the packets onto kernels (artisb200_set_option names in brackets)
 struct PropagateOptions {
@@ -337,6 +336,14 @@ class Engine {
 
   int get_array(const char* name_c, const char dtype, void* out, const int64_t count) {
     const std::string name(name_c);
+    if (name == "scalar.options_hash") {
+      if (dtype != 'q' || count != 1) {
+        return fail("scalar.options_hash is 'q'[1]");
+      }
+      const uint64_t h = options_hash_value();
+      std::memcpy(out, &h, sizeof(h));
+      return 0;
+    }
     const FieldDesc* f = find_field(name);
     if (f == nullptr) {
       return fail("unknown array name '" + name + "'");
@@ -515,6 +522,14 @@ class Engine {
         }
       }
     }
+    if constexpr (!opt::HAS_NLTE_LEVELS) {
+      for (int e = 0; e < T.nelements; e++) {
+        if (elem_has_nlte[e] != 0) {
+          return fail("commit_static: ion.nlevels_excited_nlte names NLTE levels, but this library was compiled without "
+                      "them (HAS_NLTE_LEVELS = false): the level populations would silently be Boltzmann");
+        }
+      }
+    }
     if constexpr (opt::HAS_NLTE_LEVELS) {
       if (count_of("ion.nlevels_excited_nlte") != T.nions || count_of("ion.allnltelevelsindexstart") != T.nions ||
           count_of("ion.nlevels_autoion") != T.nions) {
@@ -533,6 +548,9 @@ class Engine {
     long long matrans_total = 0;
     for (int l = 0; l < T.nlevels; l++) {
       matrans_total += (2LL * l_ndown[l]) + l_nup[l];
+    }
+    if (matrans_total > 2147483647LL) {
+      return fail("commit_static: macro-atom transition table of one cell has more than 2^31 entries");
     }
     T.matrans_total = static_cast<int>(matrans_total);
 #if ARTISB200_MA_SUMMARY
@@ -890,8 +908,11 @@ class Engine {
     if (npackets <= 0) {
       return fail("update_packets: no packets uploaded");
     }
+    // Philox: key (seed low word, packet number), counter (draw block, timestep, seed high word, rank). The rank is part of
+    // the counter, so that ranks propagating packets with the same numbers (every MPI rank of the reference numbers its
+    // own MPKTS packets from 0) draw from different streams even when the caller gives every rank the same seed.
     T.rng_setup = {T.rng_mode, static_cast<unsigned int>(T.seed), static_cast<unsigned int>(T.nts),
-                   static_cast<unsigned int>(T.seed >> 32U)};
+                   static_cast<unsigned int>(T.seed >> 32U), static_cast<unsigned int>(rank)};
     if (!be.propagate(T, npackets, popt, &last)) {
       return fail("update_packets: propagation failed: " + be.last_error());
     }
@@ -914,6 +935,8 @@ class Engine {
       if (!timestep_begun) {
         return fail("test_kernel(chi_rpkt_cont): begin_timestep must be called first");
       }
+    } else if (which == "select_continuum_nu") {
+      code = 3; nf_in = 2 * n; nf_out = n;
     } else {
       return fail("test_kernel: unknown kernel '" + which + "'");
     }

@@ -1,7 +1,7 @@
 // Per-packet random number streams.
 //
 //  * RNG_PHILOX (production): counter-based Philox4x32-10 (Salmon et al. 2011). key = (seed, packet number),
-//    counter = (draw index within the timestep, timestep, rank, 0). A packet's stream therefore depends on
+//    counter = (draw block within the timestep, timestep, high word of the seed, rank). A packet's stream therefore depends on
 //    nothing but its identity and the timestep: no generator state has to survive between timesteps, and
 //    the result is independent of how packets are scheduled onto threads, launches or GPUs.
 //  * RNG_XOSHIRO (parity): the reference's own per-packet generator in its GPU_ON build, Xoshiro128++ seeded
@@ -32,7 +32,8 @@ struct RngSetup {
   int mode;
   unsigned int key0;  // philox key word 0 (seed)
   unsigned int ctr1;  // philox counter word 1 (timestep)
-  unsigned int ctr2;  // philox counter word 2 (rank)
+  unsigned int ctr2;  // philox counter word 2 (high word of the seed)
+  unsigned int ctr3;  // philox counter word 3 (rank)
 };
 
 struct Rng {
@@ -43,11 +44,11 @@ struct Rng {
   int have_block;
 
   AHD void philox_block(const unsigned int blockindex) {
-    // Philox4x32-10 (Salmon et al. 2011): counter (block, timestep, rank, 0), key (seed, packet number)
+    // Philox4x32-10 (Salmon et al. 2011): counter (block, timestep, seed high word, rank), key (seed, packet number)
     unsigned int c0 = blockindex;
     unsigned int c1 = setup->ctr1;
     unsigned int c2 = setup->ctr2;
-    unsigned int c3 = 0U;
+    unsigned int c3 = setup->ctr3;
     unsigned int k0 = setup->key0;
     unsigned int k1 = s1;
 #pragma unroll

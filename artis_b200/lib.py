@@ -184,6 +184,9 @@ class ArtisB200:
         in_f64 = np.ascontiguousarray(in_f64, dtype=np.float64)
         in_i32 = np.ascontiguousarray(in_i32, dtype=np.int32)
         n = in_i32.size
+        expect = {"boundary_distance": 7 * n, "select_continuum_nu": 2 * n}.get(which, n)
+        if in_f64.size != expect:
+            raise ValueError(f"test_kernel({which}): {in_f64.size} f64 inputs for {n} items, expected {expect}")
         out_f64 = np.zeros(3 * n if which == "chi_rpkt_cont" else n, dtype=np.float64)
         out_i32 = np.zeros(n, dtype=np.int32)
         self._check(self.lib.artisb200_test_kernel(self.ctx, which.encode(), n, in_f64.ctypes.data_as(ctypes.c_void_p),

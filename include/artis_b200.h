@@ -199,6 +199,8 @@ int artisb200_last_schedule_stats(artisb200_ctx* ctx, double stage_ms[ARTISB200_
  *   which = "closest_transition": in_f64[n] = nu_cmf; in_i32[n] = next_trans; out_i32[n] = line index   (rpkt.h:144)
  *   which = "chi_rpkt_cont"     : in_f64[n] = nu_cmf; in_i32[n] = nonemptymgi; out_f64[n*3] = chi_escatter,
  *                                 chi_freefree_heat, chi_boundfree (needs begin_timestep)               (rpkt.cc:1020)
+ *   which = "select_continuum_nu": in_f64[n*2] = T_e, zrand (= 1 - the packet's draw, 0 < zrand <= 1); in_i32[n] = index
+ *                                 into the continuum list (cont.*); out_f64[n] = sampled frequency (ratecoeff.cc:563-638)
  * Unused output pointers may be NULL. */
 int artisb200_test_kernel(artisb200_ctx* ctx, const char* which, int64_t n, const double* in_f64, const int32_t* in_i32,
                           double* out_f64, int32_t* out_i32);

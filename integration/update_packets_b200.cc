@@ -35,6 +35,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <array>
+#include <bit>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -43,6 +44,8 @@
 #include <vector>
 
 #include "artis_b200.h"
+#define ARTISB200_REFERENCE_OPTIONS 1
+#include "artis_b200_options.h"
 #include "artisoptions.h"
 #include "atomic.h"
 #include "b200_access.h"
@@ -424,6 +427,7 @@ struct Lib {
   decltype(&artisb200_update_packets_host) update_packets_host{};
   decltype(&artisb200_last_timing_ms) last_timing_ms{};
   decltype(&artisb200_options_summary) options_summary{};
+  decltype(&artisb200_options_hash) options_hash{};
   artisb200_ctx* ctx{nullptr};
 };
 
@@ -461,6 +465,23 @@ auto env_or(const char* name, const char* fallback) -> std::string {
   return (v != nullptr) ? std::string(v) : std::string(fallback);
 }
 
+// the run's random number seed: the first line of input.txt (input.cc:1883-1900: a positive value is used as it is,
+// anything else asks for a random seed, chosen by rank 0 and broadcast). The library adds the rank itself.
+auto read_pre_zseed() -> long long {
+  std::int64_t pre_zseed = -1;
+  if (FILE* f = std::fopen("input.txt", "r"); f != nullptr) {
+    if (std::fscanf(f, "%ld", &pre_zseed) != 1) {
+      pre_zseed = -1;
+    }
+    std::fclose(f);
+  }
+  if (pre_zseed <= 0) {
+    pre_zseed = get_rng_random_seed();
+    MPI_Bcast(&pre_zseed, 1, MPI_INT64_T, 0, MPI_COMM_WORLD);
+  }
+  return pre_zseed;
+}
+
 void lib_init() {
   const auto path = env_or("ARTISB200_LIB", "libartis_b200.so");
   lib.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -480,6 +501,7 @@ void lib_init() {
   load_symbol(lib.update_packets_host, "artisb200_update_packets_host");
   load_symbol(lib.last_timing_ms, "artisb200_last_timing_ms");
   load_symbol(lib.options_summary, "artisb200_options_summary");
+  load_symbol(lib.options_hash, "artisb200_options_hash");
 
   const int device = std::atoi(env_or("ARTISB200_DEVICE", env_or("LOCAL_RANK", "0").c_str()).c_str());
   if (lib.create(&lib.ctx, device) != 0) {
@@ -488,6 +510,13 @@ void lib_init() {
     std::abort();
   }
   printlnlog("artis_b200: library {} on device {} options [{}]", path, device, lib.options_summary());
+  // the library is compiled for one set of artisoptions.h values: it must be THIS program's set (include/artis_b200_options.h)
+  if (lib.options_hash() != artisb200_options_hash_here() && env_or("ARTISB200_IGNORE_OPTIONS_HASH", "0") != "1") {
+    printlnlog("[fatal] artis_b200: {} was compiled for other artisoptions.h values than this program (hash {:x} vs {:x})", path,
+               lib.options_hash(), artisb200_options_hash_here());
+    std::fprintf(stderr, "[fatal] artis_b200: %s was compiled for other artisoptions.h values than this program\n", path.c_str());
+    std::abort();
+  }
   const bool xoshiro = env_or("ARTISB200_RNG", "philox") == "xoshiro";
 #ifndef GPU_ON
   if (xoshiro) {
@@ -496,6 +525,7 @@ void lib_init() {
   }
 #endif
   check(lib.set_option(lib.ctx, "rng_mode", xoshiro ? ARTISB200_RNG_XOSHIRO : ARTISB200_RNG_PHILOX), "rng_mode");
+  check(lib.set_option(lib.ctx, "seed", read_pre_zseed()), "seed");
   check(lib.set_option(lib.ctx, "rank", globals::my_rank), "rank");
   check(lib.set_option(lib.ctx, "nranks", globals::nprocs), "nranks");
   check(lib.set_option(lib.ctx, "max_steps_per_launch", std::atoll(env_or("ARTISB200_MAXSTEPS", "-1").c_str())),
@@ -767,6 +797,55 @@ void emit_reference_kats(Sink& s, const int nts) {
   s.arr("kat.chi.nu", chi_nu.data(), static_cast<int64_t>(chi_nu.size()));
   s.arr("kat.chi.cell", chi_cell.data(), static_cast<int64_t>(chi_cell.size()));
   s.arr("kat.chi.out", chi_out.data(), static_cast<int64_t>(chi_out.size()));
+
+  // ---- select_continuum_nu (ratecoeff.cc:563-638): free-bound emission frequencies ----
+  // random continuum of the allcont list, T_e log-uniform over the LUT's temperature range, the draw taken from a
+  // seeded generator exactly as a packet would take it (zrand = 1 - rng_uniform)
+  constexpr int NSC = 600;
+  std::vector<double> sc_in(static_cast<size_t>(NSC) * 2);
+  std::vector<int> sc_cont(NSC);
+  std::vector<double> sc_out(NSC);
+  for (int k = 0; k < NSC; k++) {
+    const int ci = static_cast<int>(rng.next() * globals::nbfcontinua) % globals::nbfcontinua;
+    const auto T_e = static_cast<float>(std::exp(std::log(MINTEMP) + ((std::log(MAXTEMP) - std::log(MINTEMP)) * rng.next())));
+    rngstate_type state(static_cast<std::uint32_t>(rng.next() * 4294967295.));
+    if (k % 50 == 49) {
+      // the extremes of the draw: uniform = 0 -> zrand = 1 (first piece) and uniform = 1 - 2^-24 -> zrand = 2^-24
+      // (topmost piece, ratecoeff.cc:624-631); xoshiro128++ returns rotl(s0 + s3, 7) + s0
+      const std::uint32_t extreme[2][4] = {{0U, 1U, 1U, 0U}, {0U, 1U, 1U, std::rotr(0xFFFFFF00U, 7)}};
+      std::memcpy(&state, extreme[(k / 50) % 2], sizeof(state));
+    }
+    static_assert(sizeof(rngstate_type) == 16);
+    rngstate_type peek = state;
+    const double zrand = 1. - rng_uniform(peek);
+    sc_in[(static_cast<size_t>(k) * 2) + 0] = T_e;
+    sc_in[(static_cast<size_t>(k) * 2) + 1] = zrand;
+    sc_cont[k] = ci;
+    sc_out[k] = select_continuum_nu(globals::allcont.element[ci], globals::allcont.ion[ci], globals::allcont.level[ci],
+                                    globals::allcont.phixstargetindex[ci], T_e, state);
+  }
+  // ... and the sampled DISTRIBUTION for two fixed (continuum, T_e) pairs: NKS reference draws each, for a two-sample
+  // Kolmogorov-Smirnov test against draws made by the device function with independent random numbers
+  constexpr int NKS = 5000;
+  std::vector<double> ks_setup(4);
+  std::vector<double> ks_out(static_cast<size_t>(2) * NKS);
+  for (int c = 0; c < 2; c++) {
+    const int ci = (c == 0) ? 0 : globals::nbfcontinua / 2;
+    const auto T_e = static_cast<float>((c == 0) ? 8000. : 25000.);
+    ks_setup[(c * 2) + 0] = ci;
+    ks_setup[(c * 2) + 1] = T_e;
+    rngstate_type state(static_cast<std::uint32_t>(1234567U + c));
+    for (int k = 0; k < NKS; k++) {
+      ks_out[(static_cast<size_t>(c) * NKS) + k] =
+          select_continuum_nu(globals::allcont.element[ci], globals::allcont.ion[ci], globals::allcont.level[ci],
+                              globals::allcont.phixstargetindex[ci], T_e, state);
+    }
+  }
+  s.arr("kat.scks.setup", ks_setup.data(), 4);
+  s.arr("kat.scks.out", ks_out.data(), static_cast<int64_t>(ks_out.size()));
+  s.arr("kat.sc.in", sc_in.data(), static_cast<int64_t>(sc_in.size()));
+  s.arr("kat.sc.cont", sc_cont.data(), NSC);
+  s.arr("kat.sc.out", sc_out.data(), NSC);
 }
 
 // the reference's own per-cell cache tables (GPU_ON: one slot per cell, all filled up front)

@@ -23,6 +23,8 @@ GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_
                     "kilonova_guttman_toy": [1], "kilonova_wollaeger_toy": [1], "kilonova_barnes_toy": [1],
                     "classic_nt_toy": [2, 3], "classic_ntexc_toy": [2, 3],
                     "classic_detailedbf_toy": [1, 3], "nltephot_toy": [1, 3]}
+# presets compiled with USE_LUT_PHOTOION = false (csrc/options/preset_*.h)
+PRESETS_WITHOUT_LUT_PHOTOION = {"classic_detailedbf", "nltephotospheric"}
 INTERACTIONS = 26  # stats::Counter::INTERACTIONS (reference stats.h:41)
 
 

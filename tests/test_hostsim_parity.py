@@ -26,7 +26,7 @@ SCHEDULES = {
 @pytest.mark.parametrize("config,nts", CASES)
 def test_deterministic_kernels(config, nts):
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
-    parity_checks.check_deterministic_kernels(lib, config, nts)
+    parity_checks.check_deterministic_kernels(lib, config, nts, ks_draws=500)
 
 
 @pytest.mark.parametrize("schedule", sorted(SCHEDULES))
@@ -45,9 +45,9 @@ def test_bounded_launches_keep_histories():
 
 @pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4)])
 def test_stochastic_parity_ks_and_estimators(config, nts):
-    # the same stated tests as on the GPU (tests/stochastic_checks.py), fewer seeds to keep the CPU suite short
+    # the same stated tests as on the GPU (tests/stochastic_checks.py)
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
-    report = stochastic_checks.check_stochastic_parity(lib, config, nts, K=5)
+    report = stochastic_checks.check_stochastic_parity(lib, config, nts, K=8)
     assert report["n_rpkt_ref"] > 0
 
 

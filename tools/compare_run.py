@@ -85,15 +85,20 @@ def compare(pk, est, after, tol=1e-9, verbose=True):
             if np.issubdtype(r.dtype, np.integer):
                 est_err[name] = int(np.abs(r.astype(np.int64) - val.astype(np.int64)).max())
             else:
+                # per-element relative error: every entry (cell, ion, bin) is held to the tolerance on its own, so a
+                # low-signal cell cannot hide behind the array's largest entry; the absolute floor (1e-20 of the
+                # largest reference entry) only keeps 0 against 0 and denormal dust from dividing by nothing
                 scale = np.abs(r).max()
-                est_err[name] = float(np.abs(r - val).max() / scale) if scale > 0 else float(np.abs(val).max())
+                floor = 1e-20 * scale if scale > 0 else 1e-300
+                denom = np.maximum(np.maximum(np.abs(r), np.abs(val)), floor)
+                est_err[name] = float((np.abs(r - val) / denom).max())
     if verbose:
         print(f"packets: {n}  matching within {tol:g}: {frac_ok * 100:.4f}%  ({int(bad.sum())} differ)")
         print("  per-field worst (int: mismatches, float: max rel err):")
         for k, v in worst.items():
             if v:
                 print(f"    {k:34s} {v}")
-        print("  estimators (max abs err / max |ref|; counters: max abs diff):")
+        print("  estimators (max per-element relative error; counters: max abs diff):")
         for k, v in est_err.items():
             print(f"    {k:20s} {v}")
         if bad.any():
