@@ -24,6 +24,7 @@
 #include "convert.h"
 #include "engine.h"
 #include "propagate.h"
+#include "warp_chi.h"
 
 namespace {
 
@@ -74,12 +75,19 @@ __global__ void k_build_keepwords(const __grid_constant__ Tables T) {
   }
 }
 
+__global__ void k_build_keptlist(const __grid_constant__ Tables T) {
+  const int cell = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x);
+  if (cell < T.ncells) {
+    ab::build_keptlist_cell(T, cell);
+  }
+}
+
 // ARTISB200_BUILD_CELL_LANES=1 (experimental, off in the shipped libraries): the lanes of a warp
 // build the same level in 32 consecutive cells instead of 32 consecutive levels of one cell - equal trip counts and
 // branches across the warp, and the atomic-data loads (transition targets, A values, collision strengths, level
 // energies) become one broadcast transaction instead of 32 gathers. Same function per (cell, level), same tables.
 #ifndef ARTISB200_BUILD_CELL_LANES
-#define ARTISB200_BUILD_CELL_LANES 0
+#define ARTISB200_BUILD_CELL_LANES 1
 #endif
 __global__ void k_build_macroatom(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
@@ -207,7 +215,8 @@ __device__ __forceinline__ void accum_zero(ab::Accum& acc) {
 }
 
 // one global atomic per block and non-zero entry
-__device__ __forceinline__ void accum_flush(const ab::Accum& acc, const Tables& T) {
+// (`family`: row of diag_stage the work counters are also added to - the stage, or NSTAGES for the whole-history kernel)
+__device__ __forceinline__ void accum_flush(const ab::Accum& acc, const Tables& T, const int family) {
   __syncthreads();
   for (int k = threadIdx.x; k < ab::CNT_COUNT; k += blockDim.x) {
     if (acc.cnt[k] != 0U) {
@@ -217,6 +226,7 @@ __device__ __forceinline__ void accum_flush(const ab::Accum& acc, const Tables& 
   for (int k = threadIdx.x; k < ab::NDIAG; k += blockDim.x) {
     if (acc.diag[k] != 0U) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&T.diag[k]), static_cast<unsigned long long>(acc.diag[k]));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&T.diag_stage[(family * ab::NDIAG) + k]), static_cast<unsigned long long>(acc.diag[k]));
     }
   }
   for (int k = threadIdx.x; k < ab::NTSSCALARS; k += blockDim.x) {
@@ -272,6 +282,14 @@ struct WfQueues {
 #define ARTISB200_WF_MINBLOCKS_MA 6
 #endif
 constexpr int WF_BLOCK = ARTISB200_WF_BLOCK;
+// warp-cooperative continuum opacity in the detailed r-packet stage (warp_chi.h): terms per round of the flat list
+#ifndef ARTISB200_WARP_CHI
+#define ARTISB200_WARP_CHI 1
+#endif
+#ifndef ARTISB200_WARP_CHI_CAP
+#define ARTISB200_WARP_CHI_CAP 128
+#endif
+constexpr int WARP_CHI_CAP = ARTISB200_WARP_CHI_CAP;
 constexpr int wf_minblocks(const int stage) {
   return (stage == ab::ST_RTHIN)    ? ARTISB200_WF_MINBLOCKS_RTHIN
          : (stage == ab::ST_RTHICK) ? ARTISB200_WF_MINBLOCKS_RTHICK
@@ -284,6 +302,12 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
     k_wf_stage(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int next, const int next_ma,
                const int max_steps) {
   __shared__ ab::Accum acc;
+  // flat term list of the warp-cooperative continuum opacity (detailed r-packet stage only)
+  __shared__ ab::WarpChiScratch<(STAGE == ab::ST_RTHIN && ARTISB200_WARP_CHI) ? WARP_CHI_CAP : 1> chi_scratch[(STAGE == ab::ST_RTHIN && ARTISB200_WARP_CHI) ? (WF_BLOCK / 32) : 1];
+  __shared__ ab::EdgeCoarseT<(STAGE == ab::ST_RTHIN && ARTISB200_WARP_CHI) ? ab::EDGE_COARSE_MAX : 1> edge_coarse;
+  if constexpr (STAGE == ab::ST_RTHIN && ARTISB200_WARP_CHI) {
+    ab::edge_coarse_fill(edge_coarse, T);
+  }
   accum_zero(acc);
   constexpr unsigned FULL = 0xffffffffU;
   const unsigned int n = q.count[(cur * ab::NSTAGES) + STAGE];
@@ -303,16 +327,47 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
     const unsigned int k = base + lane;
     int dest = ab::ST_DONE;
     int ip = 0;
-    if (k < n) {
+    if constexpr (STAGE == ab::ST_RTHIN && ARTISB200_WARP_CHI) {
+      // The detailed r-packet step taken by the whole warp together: step begin (tau_rnd, cell boundary), the
+      // continuum opacities of all lanes evaluated cooperatively (warp_chi.h), then the rest of the step (line walk,
+      // move, estimators, event). Same calls in the same order per packet as run_stage<ST_RTHIN>.
+      const bool active = k < n;
+      ab::Pkt p;
+      ab::ChiCont chi;
+      if (active) {
+        ip = in[k];
+        ab::load_pkt<STAGE>(p, chi, T, ip);
+      }
+      const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+      if (active && p.ev_pending == ab::EV_EMIT_MA) {
+        ab::finish_ma_emission(p, c);
+      }
+      for (int step = 0; step < max_steps; step++) {
+        const bool doing = active && ab::packetprop_update_required(p, T.ts_end) && (step == 0 || ab::stage_of(p, T) == STAGE);
+        if (!__any_sync(FULL, doing)) {
+          break;
+        }
+        ab::RStepPre pre{};
+        bool unfinished = false;
+        if (doing) {
+          unfinished = ab::rstep_begin(p, c, pre);
+        }
+        const bool need = unfinished && !ab::chi_cache_valid(chi, p.nu_cmf, pre.cell);
+        ab::warp_chi_rpkt_cont<WARP_CHI_CAP>(need, c, p.nu_cmf, chi, pre.cell, chi_scratch[threadIdx.x >> 5], edge_coarse);
+        if (unfinished) {
+          ab::rstep_finish<1>(p, c, T.ts_end, chi, pre);
+        }
+      }
+      if (active) {
+        dest = ab::stage_of(p, T);
+        ab::store_pkt<STAGE>(p, chi, T, ip, dest);
+      }
+    } else if (k < n) {
       ip = in[k];
       ab::Pkt p;
       ab::ChiCont chi;
       ab::load_pkt<STAGE>(p, chi, T, ip);
-#if ARTISB200_CHI_PREPASS
-      const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot, STAGE == ab::ST_RTHIN};
-#else
       const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
-#endif
       ab::run_stage<STAGE>(p, c, chi, max_steps);
       dest = ab::stage_of(p, T);
       ab::store_pkt<STAGE>(p, chi, T, ip, dest);
@@ -339,65 +394,103 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
     }
   }
   ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
-  accum_flush(acc, T);
+  accum_flush(acc, T, STAGE);
 }
 
-#if ARTISB200_CHI_PREPASS
-// Pre-pass of the detailed r-packet stage (rpkt.h chiterm_*): every packet of the stage's list says how many
-// bound-free terms its coming step needs; a warp reserves the room for its 32 requests with one atomic and writes
-// the (packet, continuum) descriptors; k_chi_terms then evaluates one term per thread.
-__global__ void __launch_bounds__(256) k_chi_prepass(const __grid_constant__ Tables T, const WfQueues q, const int cur) {
+// The same stage with lane refill: a lane keeps its packet in registers for up to `max_steps` steps of the stage
+// (macro-atom transitions, grey scatterings) and, as soon as the packet leaves the stage, stores it and takes the next
+// packet of the list - instead of idling until the slowest lane of its 32-packet chunk is done. Walk lengths are
+// geometric (5.4 transitions on average with a long tail): in chunks, a visit of <= 4 transitions ran with 8-10 of 32
+// lanes per issued instruction (ncu, profiles/r1_tuning.md). Indices are fetched 2 x 32 at a time per warp.
+template <int STAGE>
+__global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
+    k_wf_refill(const __grid_constant__ Tables T, const WfQueues q, const int cur, const int next, const int next_ma,
+                const int max_steps) {
+  __shared__ ab::Accum acc;
+  accum_zero(acc);
   constexpr unsigned FULL = 0xffffffffU;
-  const unsigned int n = q.count[(cur * ab::NSTAGES) + ab::ST_RTHIN];
-  const int* __restrict__ in = q.list[cur][ab::ST_RTHIN];
+  constexpr unsigned int FETCH = 64U;
+  const unsigned int n = q.count[(cur * ab::NSTAGES) + STAGE];
+  const int* __restrict__ in = q.list[cur][STAGE];
   const unsigned int lane = threadIdx.x & 31U;
-  const unsigned int stride = gridDim.x * blockDim.x;
-  const unsigned int n_warps = (n + 31U) & ~31U;
-  for (unsigned int k = (blockIdx.x * blockDim.x) + threadIdx.x; k < n_warps; k += stride) {
-    ab::ChiTermRequest r{-1, 0, 0, -1, 0.};
-    int ip = -1;
-    if (k < n) {
-      ip = in[k];
-      r = ab::chiterm_request(T, ip);
+  const unsigned int lanes_below = (1U << lane) - 1U;
+  unsigned int hot[ab::Ctx::NHOT] = {};
+  unsigned int chunk_pos = 0U;  // warp-uniform: the indices [chunk_pos, chunk_end) of the list belong to this warp
+  unsigned int chunk_end = 0U;
+  bool exhausted = false;       // warp-uniform: the list has no more chunks
+  bool have = false;
+  int ip = 0;
+  int steps = 0;
+  ab::Pkt p;
+  ab::ChiCont chi;
+  ab::init_chicont(chi);
+  while (true) {
+    // refill the idle lanes
+    unsigned int idle = __ballot_sync(FULL, !have);
+    while (idle != 0U && !(exhausted && chunk_pos >= chunk_end)) {
+      if (chunk_pos >= chunk_end) {
+        unsigned int base = 0U;
+        if (lane == 0U) {
+          base = atomicAdd(&q.cursor[STAGE], FETCH);
+        }
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) {
+          exhausted = true;
+          break;
+        }
+        chunk_pos = base;
+        chunk_end = (base + FETCH < n) ? base + FETCH : n;
+      }
+      const unsigned int avail = chunk_end - chunk_pos;
+      const unsigned int rank = __popc(idle & lanes_below);
+      const bool take = !have && rank < avail;
+      if (take) {
+        ip = in[chunk_pos + rank];
+        ab::load_pkt<STAGE>(p, chi, T, ip);
+        have = true;
+        steps = 0;
+      }
+      const unsigned int taken = __popc(__ballot_sync(FULL, take));
+      chunk_pos += taken;
+      idle = __ballot_sync(FULL, !have);
     }
-    const unsigned int mine = (r.count > 0) ? static_cast<unsigned int>(r.count) : 0U;
-    unsigned int incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned int up = __shfl_up_sync(FULL, incl, d);
-      if (lane >= static_cast<unsigned int>(d)) {
-        incl += up;
+    if (!__any_sync(FULL, have)) {
+      break;
+    }
+    int dest = -2;  // -2: the lane keeps its packet
+    if (have) {
+      const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
+      ab::run_stage<STAGE>(p, c, chi, 1);
+      steps++;
+      const int now = ab::stage_of(p, T);
+      if (now != STAGE || steps >= max_steps) {
+        dest = now;
+        ab::store_pkt<STAGE>(p, chi, T, ip, dest);
+        have = false;
       }
     }
-    const unsigned int total = __shfl_sync(FULL, incl, 31);
-    unsigned long long base = 0ULL;
-    if (lane == 0U && total != 0U) {
-      base = atomicAdd(T.chiterm_cursor, static_cast<unsigned long long>(total));
-    }
-    base = __shfl_sync(FULL, base, 0);
-    if (ip >= 0) {
-      const long long off = static_cast<long long>(base) + (incl - mine);
-      const bool fits = (off + mine) <= T.chiterm_capacity;
-      ab::chiterm_emit(T, ip, r, fits ? off : -1);
-      if (!fits) {
-        // the slots of this request below the capacity stay unused: mark them for the term kernel
-        for (long long j = off; j < off + mine && j < T.chiterm_capacity; j++) {
-          T.chiterm_desc[j] = {-1, 0};
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < ab::NSTAGES; s++) {
+      const unsigned m = __ballot_sync(FULL, dest == s);
+      if (m != 0U) {
+        const int buf = (s == ab::ST_MA) ? next_ma : next;
+        const int leader = __ffs(m) - 1;
+        unsigned int pos = 0U;
+        if (lane == static_cast<unsigned int>(leader)) {
+          pos = atomicAdd(&q.count[(buf * ab::NSTAGES) + s], static_cast<unsigned int>(__popc(m)));
+        }
+        pos = __shfl_sync(FULL, pos, leader);
+        if (dest == s) {
+          q.list[buf][s][pos + __popc(m & lanes_below)] = ip;
         }
       }
     }
   }
+  ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
+  accum_flush(acc, T, STAGE);
 }
 
-__global__ void __launch_bounds__(256) k_chi_terms(const __grid_constant__ Tables T) {
-  const unsigned long long requested = *T.chiterm_cursor;
-  const long long n = (requested < static_cast<unsigned long long>(T.chiterm_capacity)) ? static_cast<long long>(requested) : T.chiterm_capacity;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x; idx < n; idx += stride) {
-    ab::chiterm_eval(T, idx);
-  }
-}
-#endif  // ARTISB200_CHI_PREPASS
 
 // Re-sort of the running lists by (stage, model cell): the appends keep them only roughly in cell order, and the
 // stages gather from per-cell tables (level populations, bound-free tables, gigabytes of cumulative macro-atom rates),
@@ -594,7 +687,7 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
     }
   }
   ab::Ctx{T, 0, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot}.flush_hot();
-  accum_flush(acc, T);
+  accum_flush(acc, T, ab::NSTAGES);
   if (threadIdx.x == 0 && s_still_active != 0U) {
     atomicAdd(&queue[1], static_cast<unsigned long long>(s_still_active));
   }
@@ -771,6 +864,7 @@ struct CudaBackend {
     const long long nkw = static_cast<long long>(T.ncells) * T.keepwords;
     if (nkw > 0) {
       k_build_keepwords<<<blocks_for(nkw, B), B, 0, stream>>>(T);
+      k_build_keptlist<<<blocks_for(T.ncells, 64), 64, 0, stream>>>(T);
     }
     if (ncl > 0) {
       k_build_macroatom<<<blocks_for(ncl, B), B, 0, stream>>>(T);
@@ -957,15 +1051,29 @@ struct CudaBackend {
     // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
     unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
     grid = (grid > grid_limit) ? grid_limit : grid;
-#if ARTISB200_CHI_PREPASS
-    if constexpr (STAGE == ab::ST_RTHIN) {
-      const unsigned int pre_grid = static_cast<unsigned int>(sm_count * 8);
-      cudaMemsetAsync(T.chiterm_cursor, 0, sizeof(unsigned long long), on);
-      k_chi_prepass<<<(pre_grid > grid_limit) ? grid_limit : pre_grid, 256, 0, on>>>(T, q, cur);
-      k_chi_terms<<<pre_grid, 256, 0, on>>>(T);
-    }
-#endif
     k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, on>>>(T, q, cur, next, next_ma, max_steps);
+  }
+
+  int refill_blocks_per_sm[ab::NSTAGES]{};
+  template <int STAGE>
+  void launch_refill(const Tables& T, const WfQueues& q, const int cur, const int next, const int next_ma, const int max_steps,
+                     const unsigned int grid_limit, cudaStream_t on) {
+    if (refill_blocks_per_sm[STAGE] == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refill_blocks_per_sm[STAGE], k_wf_refill<STAGE>, WF_BLOCK, 0);
+      refill_blocks_per_sm[STAGE] = (refill_blocks_per_sm[STAGE] < 1) ? 1 : refill_blocks_per_sm[STAGE];
+    }
+    unsigned int grid = static_cast<unsigned int>(sm_count * refill_blocks_per_sm[STAGE]);
+    grid = (grid > grid_limit) ? grid_limit : grid;
+    k_wf_refill<STAGE><<<grid, WF_BLOCK, 0, on>>>(T, q, cur, next, next_ma, max_steps);
+  }
+
+  void launch_thick(const Tables& T, const WfQueues& q, const int cur, const int next, const ab::PropagateOptions& o,
+                    const unsigned int grid_limit, cudaStream_t on) {
+    if (o.refill_thicksteps > 0) {
+      launch_refill<ab::ST_RTHICK>(T, q, cur, next, cur, o.refill_thicksteps, grid_limit, on);
+    } else {
+      launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit, on);
+    }
   }
 
   bool run_wavefront(const Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
@@ -1011,7 +1119,7 @@ struct CudaBackend {
           if (timing) { cudaEventRecord(ev[1], stream); }
           launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
           if (timing) { cudaEventRecord(ev[2], stream); }
-          launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit, stream);
+          launch_thick(T, q, cur, next, o, grid_limit, stream);
           if (timing) { cudaEventRecord(ev[3], stream); }
         } else {
           // the three stages read and append to different lists: run them side by side, so that the drain of one
@@ -1020,7 +1128,7 @@ struct CudaBackend {
           cudaStreamWaitEvent(side_stream[0], ev_fork, 0);
           cudaStreamWaitEvent(side_stream[1], ev_fork, 0);
           launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
-          launch_stage<ab::ST_RTHICK>(T, q, cur, next, cur, o.rsteps_thick, grid_limit, side_stream[0]);
+          launch_thick(T, q, cur, next, o, grid_limit, side_stream[0]);
           launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, side_stream[1]);
           cudaEventRecord(ev_join[0], side_stream[0]);
           cudaEventRecord(ev_join[1], side_stream[1]);
@@ -1029,12 +1137,17 @@ struct CudaBackend {
         }
         // macro-atom walks: `ma_rounds` kernels of at most `masteps` transitions each, ping-ponging between the two
         // macro-atom lists; what is still walking after the last round continues in the next iteration
-        int ma_in = cur;
-        for (int r = 0; r < ma_rounds; r++) {
-          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit, stream);
-          if (r + 1 < ma_rounds) {
-            k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
-            ma_in ^= 1;
+        if (o.refill_masteps > 0) {
+          // one kernel with lane refill; walks longer than the limit continue in the next iteration
+          launch_refill<ab::ST_MA>(T, q, cur, next, next, o.refill_masteps, grid_limit, stream);
+        } else {
+          int ma_in = cur;
+          for (int r = 0; r < ma_rounds; r++) {
+            launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit, stream);
+            if (r + 1 < ma_rounds) {
+              k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
+              ma_in ^= 1;
+            }
           }
         }
         if (timing) { cudaEventRecord(ev[4], stream); }
@@ -1048,7 +1161,7 @@ struct CudaBackend {
           cur = 0;
         }
       }
-      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + (2 * ma_rounds) - 1 + (2 * ARTISB200_CHI_PREPASS));
+      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + ((o.refill_masteps > 0) ? 1 : (2 * ma_rounds) - 1));
       tm->iterations += sync_every;
       if (!ok(cudaMemcpyAsync(status, q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "status readback") ||
           !ok(cudaStreamSynchronize(stream), "wavefront iteration")) {

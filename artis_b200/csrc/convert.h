@@ -200,4 +200,21 @@ AHD void build_keepword_item(const Tables& T, const int cell, const int word) {
   T.cell_cont_keepbits[(static_cast<long long>(cell) * T.keepwords) + word] = bits;
 }
 
+// list and per-word ranks of the kept continua of one cell (see Tables::cell_cont_keptlist)
+AHD void build_keptlist_cell(const Tables& T, const int cell) {
+  const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(cell) * T.keepwords);
+  int* list = T.cell_cont_keptlist + (static_cast<long long>(cell) * T.nbfcontinua);
+  int* rank = T.cell_cont_keptrank + (static_cast<long long>(cell) * (T.keepwords + 1));
+  int n = 0;
+  for (int word = 0; word < T.keepwords; word++) {
+    rank[word] = n;
+    unsigned long long bits = keepbits[word];
+    while (bits != 0ULL) {
+      list[n++] = (word * 64) + lowest_set_bit(bits);
+      bits &= bits - 1;
+    }
+  }
+  rank[T.keepwords] = n;
+}
+
 }  // namespace ab

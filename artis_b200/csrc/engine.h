@@ -116,6 +116,10 @@ struct PropagateOptions {
   int sync_every{8};               // [wf_sync_every] wavefront iterations enqueued between host checks
   int concurrent{1};               // [wf_concurrent] run the three independent stage kernels of an iteration side by side
   int stage_timing{0};             // [wf_stage_timing] bracket every stage kernel with CUDA events (profiling aid)
+  // lane refill (artis_b200.cu k_wf_refill): a lane keeps its packet for up to this many steps of the stage and takes
+  // the next packet of the list as soon as its own leaves the stage; 0 = the chunked stage kernel above
+  int refill_masteps{0};           // [wf_refill_masteps] macro-atom stage: one kernel per iteration instead of the rounds
+  int refill_thicksteps{0};        // [wf_refill_thicksteps] grey r-packet stage
 };
 
 // macro-atom transitions per visit in round r of an iteration
@@ -179,29 +183,6 @@ class Engine {
   PropagateTimings last;
   int64_t scratch_capacity{0};
   int64_t bfscratch_capacity{0};
-#if ARTISB200_CHI_PREPASS
-  int64_t chiterm_packets{0};  // packet capacity the per-packet term arrays were allocated for
-
-  void free_chiterms() {
-    void* ptrs[] = {T.chiterm_desc, T.chiterm_val, T.chiterm_cursor, T.chiterm_nu, T.chiterm_exp,
-                    T.chiterm_cell, T.chiterm_off, T.chiterm_cnt};
-    for (void* ptr : ptrs) {
-      if (ptr != nullptr) {
-        be.free(ptr);
-      }
-    }
-    T.chiterm_desc = nullptr;
-    T.chiterm_val = nullptr;
-    T.chiterm_cursor = nullptr;
-    T.chiterm_nu = nullptr;
-    T.chiterm_exp = nullptr;
-    T.chiterm_cell = nullptr;
-    T.chiterm_off = nullptr;
-    T.chiterm_cnt = nullptr;
-    T.chiterm_capacity = 0;
-    chiterm_packets = 0;
-  }
-#endif
 
   int fail(const std::string& msg) {
     err = msg;
@@ -245,9 +226,6 @@ class Engine {
       T.scratch_bfestimend = nullptr;
       bfscratch_capacity = 0;
     }
-#if ARTISB200_CHI_PREPASS
-    free_chiterms();
-#endif
     for (void* ptr : soa_save) {
       be.free(ptr);
     }
@@ -404,6 +382,10 @@ class Engine {
       popt.sync_every = static_cast<int>(value < 1 ? 1 : value);
     } else if (name == "wf_concurrent") {
       popt.concurrent = static_cast<int>(value);
+    } else if (name == "wf_refill_masteps") {
+      popt.refill_masteps = static_cast<int>(value < 0 ? 0 : value);
+    } else if (name == "wf_refill_thicksteps") {
+      popt.refill_thicksteps = static_cast<int>(value < 0 ? 0 : value);
     } else if (name == "wf_stage_timing") {
       popt.stage_timing = static_cast<int>(value);
     } else if (name == "rank") {
@@ -553,20 +535,6 @@ class Engine {
       return fail("commit_static: macro-atom transition table of one cell has more than 2^31 entries");
     }
     T.matrans_total = static_cast<int>(matrans_total);
-#if ARTISB200_MA_SUMMARY
-    {
-      std::vector<int> masum_start(static_cast<size_t>(T.nlevels));
-      long long masum_total = 0;
-      for (int l = 0; l < T.nlevels; l++) {
-        masum_start[static_cast<size_t>(l)] = static_cast<int>(masum_total);
-        masum_total += (2LL * (l_ndown[l] / 8)) + (l_nup[l] / 8);
-      }
-      T.masum_total = static_cast<int>(masum_total);
-      if (!make_derived("derived.level_masum_start", masum_start, &T.level_masum_start)) {
-        return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
-      }
-    }
-#endif
     // static half of the bound-free terms (tables.h ContStatic)
     {
       const auto* c_nu_edge = host<double>("cont.nu_edge");
@@ -674,18 +642,19 @@ class Engine {
     ok = ok && alloc_output("ts.pellet_decays", 'q', 1, &T.ts_pellet_decays);
     ok = ok && alloc_output("counters", 'q', CNT_COUNT, &T.counters);
     ok = ok && alloc_output("diag", 'q', NDIAG, &T.diag);
+    // the same work counters per kernel family: rows ST_OTHER, ST_RTHIN, ST_RTHICK, ST_MA, and the whole-history kernel
+    ok = ok && alloc_output("diag_stage", 'q', (NSTAGES + 1) * NDIAG, &T.diag_stage);
     ok = ok && alloc_output("built.levelpops", 'd', nc * T.nlevels, &T.cell_levelpops);
     ok = ok && alloc_output("built.maprocessrates", 'd', nc * T.nlevels * MA_ACTION_COUNT, &T.cell_maprocessrates);
     ok = ok && alloc_output("built.matrans", 'd', nc * static_cast<int64_t>(T.matrans_total), &T.cell_matrans);
-#if ARTISB200_MA_SUMMARY
-    ok = ok && alloc_output("built.masum", 'd', nc * static_cast<int64_t>(T.masum_total), &T.cell_masum);
-#endif
     ok = ok && alloc_output("built.cooling_contrib", 'd', nc * T.ncoolingterms, &T.cell_cooling_contrib);
     ok = ok && alloc_output("built.cont_nnlevel", 'd', nc * T.nbfcontinua, &T.cell_cont_nnlevel);
     ok = ok && alloc_output("built.cont_keepbits", 'Q', nc * T.keepwords, &T.cell_cont_keepbits);
     ok = ok && alloc_output("built.cont_departure", 'd', nc * T.nbfcontinua, &T.cell_cont_departure);
     ok = ok && alloc_output("built.cont_edgepart", 'd', nc * T.nbfcontinua, &T.cell_cont_edgepart);
     ok = ok && alloc_output("built.cont_pack", 'd', 2 * nc * T.nbfcontinua, &T.cell_cont_pack);
+    ok = ok && alloc_output("built.cont_keptlist", 'i', nc * T.nbfcontinua, &T.cell_cont_keptlist);
+    ok = ok && alloc_output("built.cont_keptrank", 'i', nc * (T.keepwords + 1), &T.cell_cont_keptrank);
     ok = ok && alloc_output("built.chi_ff_nnionpart", 'd', nc, &T.cell_chi_ff_nnionpart);
     ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nc * static_cast<int64_t>(T.nphixstargets_total),
                             &T.cell_corrphotoioncoeff);
@@ -769,6 +738,7 @@ class Engine {
     be.zero(T.ts_pellet_decays, 8);
     be.zero(T.counters, CNT_COUNT * 8);
     be.zero(T.diag, NDIAG * 8);
+    be.zero(T.diag_stage, (NSTAGES + 1) * NDIAG * 8);
     if (!be.build_cell_tables(T)) {
       return fail("begin_timestep: building the per-cell tables failed: " + be.last_error());
     }
@@ -824,37 +794,6 @@ class Engine {
         bfscratch_capacity = need;
       }
     }
-#if ARTISB200_CHI_PREPASS
-    if (chiterm_packets < packet_capacity) {
-      free_chiterms();
-      int64_t terms = packet_capacity * static_cast<int64_t>(ARTISB200_CHITERMS_PER_PACKET);
-      if (ARTISB200_CHITERMS_CAP > 0 && terms > ARTISB200_CHITERMS_CAP) {
-        terms = ARTISB200_CHITERMS_CAP;
-      }
-      if (terms >= (1LL << 31)) {
-        return fail("bound-free term buffer: more than 2^31 terms");
-      }
-      T.chiterm_desc = static_cast<ChiTermDesc*>(be.alloc(terms * static_cast<int64_t>(sizeof(ChiTermDesc))));
-      T.chiterm_val = static_cast<ChiTermVal*>(be.alloc(terms * static_cast<int64_t>(sizeof(ChiTermVal))));
-      T.chiterm_cursor = static_cast<unsigned long long*>(be.alloc(8));
-      T.chiterm_nu = static_cast<double*>(be.alloc(packet_capacity * 8));
-      T.chiterm_exp = static_cast<double*>(be.alloc(packet_capacity * 8));
-      T.chiterm_cell = static_cast<int*>(be.alloc(packet_capacity * 4));
-      T.chiterm_off = static_cast<int*>(be.alloc(packet_capacity * 4));
-      T.chiterm_cnt = static_cast<int*>(be.alloc(packet_capacity * 4));
-      if (T.chiterm_desc == nullptr || T.chiterm_val == nullptr || T.chiterm_cursor == nullptr || T.chiterm_nu == nullptr ||
-          T.chiterm_exp == nullptr || T.chiterm_cell == nullptr || T.chiterm_off == nullptr || T.chiterm_cnt == nullptr) {
-        return fail("bound-free term buffer allocation failed: " + be.last_error());
-      }
-      be.zero(T.chiterm_cursor, 8);
-      be.zero(T.chiterm_nu, packet_capacity * 8);
-      be.zero(T.chiterm_cell, packet_capacity * 4);
-      be.zero(T.chiterm_off, packet_capacity * 4);
-      be.zero(T.chiterm_cnt, packet_capacity * 4);  // 0 terms for nu == 0: never matches a packet
-      T.chiterm_capacity = terms;
-      chiterm_packets = packet_capacity;
-    }
-#endif
     const int64_t need = n * stride;
     if (need > aos_staging_bytes) {
       if (aos_staging != nullptr) {

@@ -51,38 +51,6 @@ AHD int index_upperbound(const double* a, const int n, const double target, cons
   return lo + count;
 }
 
-#if ARTISB200_MA_SUMMARY
-// The same index from the summary S[j] = a[8j+7]: j = number of summary keys <= target, then the answer is in the
-// eight consecutive entries a[8j .. 8j+7] (one 64-byte window) or in the array's last n % 8 entries.
-AHD int index_upperbound_summary(const double* a, const double* S, const int n, const double target, const Ctx& c) {
-  int probes = 0;
-  for (int m = n; m > 0; m >>= 1) {
-    probes++;
-  }
-  c.work<DIAG_BINSEARCH_STEPS>(probes);
-  const int m = n >> 3;
-  // (the work counter of the inner search is the thread-private one as well; take its probes back out)
-  int j = 0;
-  if (m > 0) {
-    int inner = 0;
-    for (int k = m; k > 0; k >>= 1) {
-      inner++;
-    }
-    j = index_upperbound(S, m, target, c);
-    c.work<DIAG_BINSEARCH_STEPS>(-inner);
-  }
-  const int lo = j << 3;
-  const int len = n - lo;
-  int count = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    if (k < len) {
-      count += (!(target < a[lo + k])) ? 1 : 0;
-    }
-  }
-  return lo + count;
-}
-#endif
 
 // Take up to `max_steps` transitions (<= 0: walk to deactivation) of the activation recorded in p.ma.
 // The walk ends with p.ma_pending == 0 and either a k-packet, or an r-packet whose re-emission is left pending
@@ -138,19 +106,12 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
 
     const int ndowntrans = T.level_ndowntrans[ulev];
     const double* transblock = cellmatrans + T.level_matransblock_start[ulev];
-#if ARTISB200_MA_SUMMARY
-    const double* sumblock = T.cell_masum + (static_cast<long long>(cell) * T.masum_total) + T.level_masum_start[ulev];
-#endif
 
     switch (selected_action) {
       case MA_ACTION_RADDEEXC: {
         // macroatom.cc:204-244
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_RADDEEXC];
-#if ARTISB200_MA_SUMMARY
-        const int downtransindex = index_upperbound_summary(transblock, sumblock, ndowntrans - 1, targetval, c);
-#else
         const int downtransindex = index_upperbound(transblock, ndowntrans - 1, targetval, c);
-#endif
         const int alltrans_startdown = T.level_alltrans_startdown[ulev];
         const int lineindex = T.trans_lineindex[alltrans_startdown + downtransindex];
         if (lineindex == activatingline) {
@@ -190,12 +151,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
 
       case MA_ACTION_INTERNALDOWNSAME: {
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALDOWNSAME];
-#if ARTISB200_MA_SUMMARY
-        const int downtransindex =
-            index_upperbound_summary(transblock + ndowntrans, sumblock + (ndowntrans >> 3), ndowntrans - 1, targetval, c);
-#else
         const int downtransindex = index_upperbound(transblock + ndowntrans, ndowntrans - 1, targetval, c);
-#endif
         level = T.trans_targetlevelindex[T.level_alltrans_startdown[ulev] + downtransindex];
         break;
       }
@@ -291,12 +247,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
       case MA_ACTION_INTERNALUPSAME: {
         const int nuptrans = T.level_nuptrans[ulev];
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALUPSAME];
-#if ARTISB200_MA_SUMMARY
-        const int uptransindex = index_upperbound_summary(transblock + (2 * ndowntrans), sumblock + (2 * (ndowntrans >> 3)),
-                                                          nuptrans - 1, targetval, c);
-#else
         const int uptransindex = index_upperbound(transblock + (2 * ndowntrans), nuptrans - 1, targetval, c);
-#endif
         level = T.trans_targetlevelindex[alltrans_startup(T, ulev) + uptransindex];
         break;
       }

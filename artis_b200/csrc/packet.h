@@ -80,9 +80,6 @@ struct Ctx {
   double* tss;         // [NTSSCALARS] timestep scalars
   unsigned int* pellet_decays;
   unsigned int* hot;   // [NHOT] thread-private copies of the counters that are bumped every step (registers)
-#if ARTISB200_CHI_PREPASS
-  bool use_chiterms = false;  // the caller is the detailed r-packet stage of a wavefront iteration whose pre-pass has run
-#endif
 
   // The counters bumped on every step live in the thread's registers (all indices are compile-time constants)
   // and are added to the block's accumulators once, when the kernel ends; the rare ones go straight to the block's

@@ -212,9 +212,6 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
   const int ndowntrans = T.level_ndowntrans[ulev];
   double* arr_sum_epstrans_rad_deexc = transblock;
   double* arr_sum_internal_down_same = transblock + ndowntrans;
-#if ARTISB200_MA_SUMMARY
-  double* sumblock = T.cell_masum + (static_cast<long long>(cell) * T.masum_total) + T.level_masum_start[ulev];
-#endif
   for (int i = 0; i < ndowntrans; i++) {
     const int alltransindex = alltrans_startdown + i;
     const int lower = T.trans_targetlevelindex[alltransindex];
@@ -231,12 +228,6 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
     sum_internal_down_same += (R + C) * epsilon_target;
     arr_sum_epstrans_rad_deexc[i] = sum_raddeexc;
     arr_sum_internal_down_same[i] = sum_internal_down_same;
-#if ARTISB200_MA_SUMMARY
-    if ((i & 7) == 7) {
-      sumblock[i >> 3] = sum_raddeexc;
-      sumblock[(ndowntrans >> 3) + (i >> 3)] = sum_internal_down_same;
-    }
-#endif
   }
   levelrates[MA_ACTION_RADDEEXC] = sum_raddeexc;
   levelrates[MA_ACTION_COLDEEXC] = sum_coldeexc;
@@ -258,11 +249,6 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
     const double NT = nt_excitation_ratecoeff(T, cell, level, upper, alltransindex);  // macroatom.cc:133
     sum_internal_up_same += (R + C + NT) * epsilon_current;
     arr_sum_internal_up_same[ii] = sum_internal_up_same;
-#if ARTISB200_MA_SUMMARY
-    if ((ii & 7) == 7) {
-      sumblock[(2 * (ndowntrans >> 3)) + (ii >> 3)] = sum_internal_up_same;
-    }
-#endif
   }
   levelrates[MA_ACTION_INTERNALUPSAME] = sum_internal_up_same;
 

@@ -243,142 +243,6 @@ AHD bool chi_cache_valid(const ChiCont& chi, const double nu_cmf, const int cell
   return (cell == chi.nonemptymgi) && (fabs((chi.nu / nu_cmf) - 1.0) < 1e-4);
 }
 
-#if ARTISB200_CHI_PREPASS
-// ---- bound-free terms evaluated ahead of the r-packet stage (ARTISB200_CHI_PREPASS) -----------------------------
-// In the r-packet stage the bound-free sum runs at 3 of 32 lanes (the windows differ in length, and only some lanes
-// need an evaluation at all); as a kernel over the TERMS it runs at 32 of 32. Three parts:
-//   chiterm_request  (pre-pass, per packet of the detailed r-packet list): does the coming step need a new opacity
-//                    (same test as calculate_chi_rpkt_cont), and if so how many kept continua are in its window
-//   chiterm_emit     (pre-pass): the (packet, continuum) descriptors, in ascending continuum order
-//   chiterm_eval     (term kernel, per term): bf_term_sigma_contr, exactly as the inline sum evaluates it
-//   chiterm_consume  (r-packet stage): the ordered sum of the packet's terms and the per-ground-continuum / estimator
-//                    slots, bit-identical to bf_sum_window<false>; false = no (matching) terms, sum inline
-struct ChiTermRequest {
-  int cell;
-  int allcontbegin;
-  int allcontend;
-  int count;  // -1: no evaluation needed
-  double nu;
-};
-
-AHD ChiTermRequest chiterm_request(const Tables& T, const long long ip) {
-  ChiTermRequest r{-1, 0, 0, -1, 0.};
-  const HotC* hc = &T.pkt.hc[ip];
-  const Q4 head = load_q4(&hc->next_trans);
-  if (head.b != TYPE_RPKT || !(T.pkt.ha[ip].prop_time < T.ts_end)) {
-    return r;
-  }
-  r.cell = T.propcell_nonemptymgi[head.c];
-  if (r.cell < 0 || T.thick[r.cell] == CELL_THICK) {
-    return r;
-  }
-  r.nu = T.pkt.ha[ip].nu_cmf;
-  ChiCont cached;
-  cached.nu = T.pkt.hb[ip].chi_nu;
-  cached.nonemptymgi = hc->chi_mgi;
-  if (chi_cache_valid(cached, r.nu, r.cell)) {
-    return r;
-  }
-  bf_window(T, r.nu, r.allcontbegin, r.allcontend);
-  const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(r.cell) * T.keepwords);
-  int count = 0;
-  for (int word = r.allcontbegin / 64; word * 64 < r.allcontend; word++) {
-    count += popcount64(bf_window_bits(keepbits, word, r.allcontbegin, r.allcontend));
-  }
-  r.count = count;
-  return r;
-}
-
-// `off` < 0: the request did not fit into the term buffer
-AHD void chiterm_emit(const Tables& T, const long long ip, const ChiTermRequest& r, const long long off) {
-  if (r.count < 0 || off < 0) {
-    T.chiterm_cnt[ip] = -1;
-    return;
-  }
-  T.chiterm_cnt[ip] = r.count;
-  T.chiterm_off[ip] = static_cast<int>(off);
-  T.chiterm_cell[ip] = r.cell;
-  T.chiterm_nu[ip] = r.nu;
-  T.chiterm_exp[ip] = exp(-HOVERKB * r.nu / T.Te[r.cell]);
-  const unsigned long long* keepbits = T.cell_cont_keepbits + (static_cast<long long>(r.cell) * T.keepwords);
-  long long k = off;
-  for (int word = r.allcontbegin / 64; word * 64 < r.allcontend; word++) {
-    unsigned long long bits = bf_window_bits(keepbits, word, r.allcontbegin, r.allcontend);
-    while (bits != 0ULL) {
-      T.chiterm_desc[k++] = {static_cast<int>(ip), (word * 64) + lowest_set_bit(bits)};
-      bits &= bits - 1;
-    }
-  }
-}
-
-AHD void chiterm_eval(const Tables& T, const long long idx) {
-  const ChiTermDesc d = T.chiterm_desc[idx];
-  if (d.ip < 0) {
-    return;
-  }
-  const int cell = T.chiterm_cell[d.ip];
-  BfEval e;
-  e.nu = T.chiterm_nu[d.ip];
-  e.T_e = T.Te[cell];
-  e.exp_minus_hnu_over_kte = T.chiterm_exp[d.ip];
-  e.stimfactor_split_usable = (e.exp_minus_hnu_over_kte >= DBL_MIN_);
-  e.base = static_cast<long long>(cell) * T.nbfcontinua;
-  double nnlevel = 0.;
-  int g = -1;
-  int bfestimindex = -1;
-  const double sigma_contr = bf_term_sigma_contr(T, e, d.cont, nnlevel, g, bfestimindex);
-  T.chiterm_val[idx] = {nnlevel * sigma_contr, sigma_contr};
-}
-
-AHD bool chiterm_consume(const Ctx& c, const int cell, const double nu, double& chi_bf) {
-  const Tables& T = c.T;
-  if (!c.use_chiterms) {
-    return false;
-  }
-  const int count = T.chiterm_cnt[c.ip];
-  if (count < 0 || T.chiterm_cell[c.ip] != cell || T.chiterm_nu[c.ip] != nu) {
-    return false;
-  }
-  T.chiterm_cnt[c.ip] = -1;  // the buffer is rewritten by the next iteration's pre-pass
-  if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
-    const int ng = T.nbfcontinua_ground;
-    for (int i = 0; i < ng; i++) {
-      *c.groundcont_contr(i) = 0.;
-    }
-  }
-  if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
-    const int bfestimend = upper_bound_idx(T.bfestim_nu_edge, T.nbfestim, nu);
-    const int bfestimbegin = lower_bound_idx(T.bfestim_nu_edge, bfestimend, nu / T.last_phixs_nuovernuedge);
-    T.scratch_bfestimbegin[c.ip] = bfestimbegin;
-    T.scratch_bfestimend[c.ip] = bfestimend;
-    for (int k = bfestimbegin; k < bfestimend; k++) {
-      *c.bfestim_contr(k) = 0.;
-    }
-  }
-  const long long off = T.chiterm_off[c.ip];
-  double chi_bf_sum = 0.;
-  for (int j = 0; j < count; j++) {
-    const ChiTermVal v = T.chiterm_val[off + j];
-    const ContStatic cs = T.cont_static[T.chiterm_desc[off + j].cont];
-    if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
-      if (cs.bfestimindex >= 0) {
-        *c.bfestim_contr(cs.bfestimindex) = v.sigma_contr;
-      }
-    }
-    if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
-      if (cs.groundcontestimindex >= 0) {
-        *c.groundcont_contr(cs.groundcontestimindex) = v.sigma_contr;
-      }
-    }
-    chi_bf_sum += v.chi_contr;
-  }
-  c.work<DIAG_BINSEARCH_STEPS>(2 * T.log2_nbf);
-  c.work<DIAG_CONT_TERMS>(count);
-  c.work<DIAG_CONT_TERMS_PREPASS>(count);
-  chi_bf = chi_bf_sum;
-  return true;
-}
-#endif  // ARTISB200_CHI_PREPASS
 
 
 // rpkt.cc:1020-1044: (re)evaluate the continuum opacity unless the cached value is for the same cell and a
@@ -391,9 +255,6 @@ AHD void calculate_chi_rpkt_cont(const Ctx& c, const double nu_cmf, ChiCont& chi
   const auto nne = T.nne[cell];
   chi.chi_freefree_heat = calculate_chi_ffheating(T, cell, nu_cmf);
   chi.chi_escatter = SIGMA_T * nne;
-#if ARTISB200_CHI_PREPASS
-  if (!chiterm_consume(c, cell, nu_cmf, chi.chi_boundfree))
-#endif
   {
     chi.chi_boundfree = calculate_chi_bf_gammacontr<false>(c, cell, nu_cmf, 0.);
   }

@@ -152,6 +152,7 @@ namespace ab {
   X(long long, ts_pellet_decays, "ts.pellet_decays") \
   X(long long, counters, "counters")              \
   X(long long, diag, "diag")                      \
+  X(long long, diag_stage, "diag_stage")          \
   X(double, cell_levelpops, "built.levelpops")    \
   X(double, cell_maprocessrates, "built.maprocessrates") \
   X(double, cell_matrans, "built.matrans")        \
@@ -190,7 +191,6 @@ enum : int {
   DIAG_GAMMA_EVENTS = 9,
   DIAG_KERNEL_LAUNCHES = 10,
   DIAG_PACKET_SEGMENTS = 11,
-  DIAG_CONT_TERMS_PREPASS = 12,  // of DIAG_CONT_TERMS: taken from the term kernel's buffer (ARTISB200_CHI_PREPASS builds)
 };
 
 // Packet state in HBM (device resident across timesteps). Field set = reference Packet (packet.h:109-156) plus the
@@ -254,33 +254,6 @@ struct alignas(32) ContStatic {
 struct alignas(16) CellCont {
   double nnlevel;
   double edgepart;  // departure * exp(h nu_edge / kT), or < 0: use the slow form (rpkt.cc:873-889)
-};
-
-// ARTISB200_CHI_PREPASS=1 (experimental, off in the shipped libraries): the terms of the bound-free opacity sums an
-// iteration's detailed r-packet steps will need are evaluated by a kernel of their own, one thread per (packet,
-// continuum) term, and the r-packet stage only adds them up in order (rpkt.h chiterm_*). See DESIGN.md section 9.
-#ifndef ARTISB200_CHI_PREPASS
-#define ARTISB200_CHI_PREPASS 0
-#endif
-#ifndef ARTISB200_CHITERMS_PER_PACKET
-#define ARTISB200_CHITERMS_PER_PACKET 16  // capacity of the term buffer per packet of capacity (overflow: inline sum)
-#endif
-#ifndef ARTISB200_CHITERMS_CAP
-#define ARTISB200_CHITERMS_CAP 0  // > 0: absolute upper limit of the term buffer (tests of the overflow path)
-#endif
-// ARTISB200_MA_SUMMARY=1 (experimental, off in the shipped libraries): every 8th value of each cumulative macro-atom
-// rate array is also kept in a summary table an eighth of the size, so that a search reads one or two sectors of the
-// summary and one 64-byte window of the array instead of a sector per probe (macroatom.h index_upperbound_summary).
-#ifndef ARTISB200_MA_SUMMARY
-#define ARTISB200_MA_SUMMARY 0
-#endif
-struct ChiTermDesc {
-  int ip;    // packet, or -1: slot of a request that did not fit
-  int cont;  // continuum index
-};
-struct alignas(16) ChiTermVal {
-  double chi_contr;    // nnlevel * sigma_contr
-  double sigma_contr;
 };
 
 struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_time/trueemissiontype
@@ -363,6 +336,11 @@ struct Tables {
   const int* elem_has_nlte_levels;  // [nelements]
   const ContStatic* cont_static;  // [nbfcontinua]
   CellCont* cell_cont_pack;       // [ncells][nbfcontinua], written by the per-cell table build
+  // The kept continua of every cell as a list (ascending continuum index = ascending edge frequency), and the number of
+  // kept continua below each 64-continuum word of the keep-bitmap: the kept continua of a frequency window are then a
+  // contiguous range of the list (warp_chi.h). Built after the keep-bitmaps.
+  int* cell_cont_keptlist;        // [ncells][nbfcontinua]
+  int* cell_cont_keptrank;        // [ncells][keepwords + 1]
 
   // run options
   int rng_mode;
@@ -379,23 +357,6 @@ struct Tables {
   // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
   double* scratch_groundcont;
   long long scratch_stride;
-#if ARTISB200_MA_SUMMARY
-  double* cell_masum;                // [ncells][masum_total]: per level a[8j+7] of the three cumulative arrays
-  const int* level_masum_start;      // [nlevels]
-  int masum_total;                   // sum over levels of 2*(ndown/8) + nup/8
-#endif
-#if ARTISB200_CHI_PREPASS
-  ChiTermDesc* chiterm_desc;           // [chiterm_capacity]
-  ChiTermVal* chiterm_val;             // [chiterm_capacity]
-  long long chiterm_capacity;
-  unsigned long long* chiterm_cursor;  // terms requested in the running iteration
-  // per packet: the evaluation the terms were requested for, and where they are
-  double* chiterm_nu;
-  double* chiterm_exp;  // exp(-h nu / k T_e)
-  int* chiterm_cell;
-  int* chiterm_off;
-  int* chiterm_cnt;     // -1: nothing requested (or already consumed)
-#endif
 };
 
 }  // namespace ab

@@ -146,6 +146,28 @@ def algorithmic_bytes(diag, counters, log2_lines, nions, mean_ncoolingterms_log2
     return b
 
 
+def bench_config(npackets=10000000):
+    """the workload both arms are quoted on (BASELINE.json configs[1]); identical in the two arms' JSON lines"""
+    return {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}",
+            "packets_per_gpu": int(npackets), "timestep": BENCH_TS, "model_grid": "2D cylindrical 50 x 100",
+            "atomic_data": "synthetic, 5 elements x 4 ions x 120 levels (54 892 lines, 1 475 bound-free continua)",
+            "l2_policy": "inputs larger than L2 (packet records + per-cell tables > 126 MB)"}
+
+
+STAGE_NAMES = ["other", "rpkt_thin", "rpkt_thick", "macroatom", "history_tail"]
+STAGE_KERNELS = {"other": "k_wf_stage<other>", "rpkt_thin": "k_wf_stage<rpkt_thin>", "rpkt_thick": "k_wf_stage<rpkt_thick>",
+                 "macroatom": "k_wf_stage<macroatom>", "history_tail": "k_propagate"}
+
+
+def dram_traffic_profile():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per stage kernel and step, from the committed ncu pass over
+    every launch of one full-size step (profiles/r2_dram_traffic.json, written by tools/ncu_dram_traffic.py)"""
+    path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path))
+    return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -268,6 +290,11 @@ def run_ours(args):
     device_step_timed()
     stage_stats = eng.last_schedule_stats()
     stage_total_ms = eng.last_timing_ms()[0]
+    stage_diag = eng.get_array("diag_stage").reshape(len(STAGE_NAMES), -1)
+    iters = max(1, int(stage_stats["iterations"]))
+    ma_per_iter = 1 if int(user_opts.get("wf_refill_masteps", 0)) > 0 else int(user_opts.get("wf_ma_rounds", 3)) | 1
+    stage_launches = {"other": iters, "rpkt_thin": iters, "rpkt_thick": iters, "macroatom": iters * ma_per_iter,
+                      "history_tail": 1 if stage_stats["tail_ms"] > 0 else 0}
     eng.set_option("wf_stage_timing", 0)
 
     # end-to-end through the host-buffer call (the drop-in signature): H2D packets, propagate, D2H packets + estimators
@@ -306,23 +333,46 @@ def run_ours(args):
         achieved = b_alg / (t_prop * 1e-3) / 1e9
         launches = int(diag_mean[10])
         ncells = static["cell.ffegrp"].size
+        # per kernel family: algorithmic bytes of the family's own work counters / the family's CUDA-event time of the
+        # stage-timing pass (kernels run one after the other there), per launch; DRAM traffic from the committed ncu pass
+        traffic = dram_traffic_profile()
+        stage_rooflines = []
+        for si, sname in enumerate(STAGE_NAMES):
+            ms = stage_stats["stage_ms"].get(sname, 0.0) if sname != "history_tail" else stage_stats["tail_ms"]
+            b_stage = algorithmic_bytes(stage_diag[si], counters, 0, 0, 0, 0)
+            nlaunch = stage_launches.get(sname, 0)
+            if ms <= 0 or nlaunch <= 0:
+                continue
+            tr = traffic["kernels"].get(sname) if traffic else None
+            stage_rooflines.append({
+                "kernel": STAGE_KERNELS[sname], "bound": "hbm", "launches_per_step": nlaunch, "ms_per_step": ms,
+                "algorithmic_bytes_per_launch": b_stage / nlaunch, "avg_launch_ms": ms / nlaunch,
+                "achieved": b_stage / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": b_stage / (ms * 1e-3) / 1e9 / peak,
+                "traffic": (tr["dram_bytes_per_step"] / tr["launches_per_step"]) if tr else None,
+                "traffic_over_algorithmic": (tr["dram_bytes_per_step"] / b_stage) if (tr and b_stage > 0) else None})
+        dominant = max(stage_rooflines, key=lambda r: r["ms_per_step"]) if stage_rooflines else None
+        roofline = dict(dominant) if dominant else {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                                      "frac": achieved / peak, "traffic": None}
+        roofline.update({"peak_source": peak_kind, "algorithmic_bytes": roofline.get("algorithmic_bytes_per_launch"),
+                         "traffic_source": (traffic.get("source") if traffic else None),
+                         "note": "dominant kernel of the step (largest share of the stage-timing pass); per launch; the whole step is in roofline_step"})
         out = {
             "metric": "packet-interactions/sec per timestep", "value": n_int_total / (t_step * 1e-3), "unit": "interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}",
-                       "packets_per_gpu": n, "model_cells": int(ncells), "lines": int(nlines), "levels": int(static["level.epsilon"].size),
-                       "bf_continua": int(static["cont.nu_edge"].size), "rng": "philox4x32-10",
-                       "interactions_per_step_per_gpu": n_int, "l2_policy": "inputs larger than L2 (packet SoA + per-cell tables > 126 MB)"},
+            "config": bench_config(n),
+            "workload_details": {"model_cells": int(ncells), "lines": int(nlines), "levels": int(static["level.epsilon"].size),
+                                 "bf_continua": int(static["cont.nu_edge"].size), "rng": "philox4x32-10",
+                                 "interactions_per_step_per_gpu": n_int},
             "e2e": {"value": n_int_total / (t_e2e * 1e-3), "unit": "interactions/s", "h2d_bytes_per_step": int(n * stride),
                     "d2h_bytes_per_step": int(n * stride + est_count * 8), "ms_per_step": t_e2e},
             # per step: the propagation launches (stage kernels, sort, resets) + the 5 per-cell table-build kernels
             "gpu_launches": int(launches + 5),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_kind,
-                         "kernel": ("k_wf_stage<other|rpkt_thin|rpkt_thick|macroatom> (all propagation kernels of the step)"
-                                    if sched_stats["iterations"] > 0 else "k_propagate"),
-                         "kernel_ms": t_prop, "algorithmic_bytes": int(b_alg)},
+            "roofline": roofline,
+            "roofline_step": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "kernel": "all propagation kernels of the step", "kernel_ms": t_prop, "algorithmic_bytes": int(b_alg),
+                              "traffic": (sum(v["dram_bytes_per_step"] for v in traffic["kernels"].values()) if traffic else None)},
+            "roofline_stages": stage_rooflines,
             "schedule": {"options": user_opts, "iterations": sched_stats["iterations"], "launches": sched_stats["launches"],
                          "tail_packets": sched_stats["tail_packets"], "tail_ms": sched_stats["tail_ms"],
                          "stage_timing_pass": {"total_ms": stage_total_ms, "stage_ms": stage_stats["stage_ms"],
@@ -338,10 +388,8 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                out["cpu_baseline"] = cpu_baseline(cores=1)
                 # same model, same timestep, independent random numbers: the two codes must agree within Monte Carlo noise
-                out["crosscheck"] = {"interactions_per_packet_gpu": n_int / n,
-                                     "interactions_per_packet_cpu_reference": out["cpu_baseline"].pop("interactions_per_packet")}
+                out["cpu_baseline"], out["crosscheck"] = cpu_baseline(n_int / n)
             except Exception as e:  # the baseline must never take the bench line down
                 out["cpu_baseline"] = {"value": None, "unit": "interactions/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(out), flush=True)
@@ -354,26 +402,19 @@ def run_ours(args):
 # CPU baseline / reference arm: the compiled reference's own update_packets on this box
 # ------------------------------------------------------------------------------------------------------------
 
-def cpu_reference_run(nproc, rundir_root):
-    """nproc concurrent single-rank reference processes (the reference's production parallelism is one MPI rank per
-    core with no communication inside update_packets, update_packets.cc:561/631), each on its own packets"""
+def _set_input_line(path, index, text):
+    lines = open(path).read().split("\n")
+    lines[index] = text.ljust(24) + f" # {index:2d}"
+    open(path, "w").write("\n".join(lines))
+
+
+def _run_reference_processes(rundirs, binary):
+    """one single-rank reference process per run folder, all at once (the reference's production parallelism is one MPI
+    rank per core with no communication inside update_packets, update_packets.cc:561/631); returns the ARTISB200_TIMING
+    record of timestep BENCH_TS of every process"""
     import run_oracle
-    odir = run_oracle.oracle_dir(CPU_SAMPLE_CONFIG, CPU_FLAVOR)
-    binary = os.path.join(odir, "sn3d_ref")
-    if not os.path.exists(binary):
-        raise RuntimeError(f"{binary} missing")
     procs = []
-    for r in range(nproc):
-        rundir = os.path.join(rundir_root, f"cpu_rank{r}")
-        if os.path.isdir(rundir):
-            shutil.rmtree(rundir)
-        shutil.copytree(os.path.join(odir, "inputs"), rundir)
-        os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
-        inp = os.path.join(rundir, "input.txt")
-        lines = open(inp).read().split("\n")
-        lines[0] = f"{20260101 + 1000 * r}".ljust(24) + " #  0"
-        lines[2] = f"000 {BENCH_TS + 1:03d}".ljust(24) + " #  2"
-        open(inp, "w").write("\n".join(lines))
+    for rundir in rundirs:
         env = dict(os.environ, ARTISB200_MODE="ref")
         env.pop("ARTISB200_DUMP_DIR", None)
         out = open(os.path.join(rundir, "stdout.txt"), "w")
@@ -382,48 +423,155 @@ def cpu_reference_run(nproc, rundir_root):
     for rundir, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"reference process failed in {rundir}")
-        res.append([t for t in run_oracle.timing_lines(rundir) if t["nts"] == BENCH_TS][0])
+        res.append([t for t in run_oracle.timing_lines(rundir) if t["nts"] == BENCH_TS][-1])
     return res
 
 
-def cpu_baseline(cores=1):
-    import configs
+def cpu_reference_setup(nproc, rundir_root):
+    """fresh run folders of the bounded CPU sample (same model and atomic data, MPKTS = 1e5 packets per process, distinct
+    seeds)"""
+    import run_oracle
+    odir = run_oracle.oracle_dir(CPU_SAMPLE_CONFIG, CPU_FLAVOR)
+    binary = os.path.join(odir, "sn3d_ref")
+    if not os.path.exists(binary):
+        raise RuntimeError(f"{binary} missing")
+    rundirs = []
+    for r in range(nproc):
+        rundir = os.path.join(rundir_root, f"cpu_rank{r}")
+        if os.path.isdir(rundir):
+            shutil.rmtree(rundir)
+        shutil.copytree(os.path.join(odir, "inputs"), rundir)
+        os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
+        _set_input_line(os.path.join(rundir, "input.txt"), 0, f"{20260101 + 1000 * r}")
+        rundirs.append(rundir)
+    return rundirs, binary
+
+
+def cpu_reference_evolve(rundirs, binary):
+    """timesteps 0..BENCH_TS from scratch. Leaves gridsave_ts<BENCH_TS>.tmp / packets_0000_ts<BENCH_TS>.tmp and an
+    input.txt that resumes there (grid.cc:974, packet.cc:253-311, sn3d.cc:663-716), so that every further call of
+    cpu_reference_restart() times update_packets(BENCH_TS) alone"""
+    for rundir in rundirs:
+        _set_input_line(os.path.join(rundir, "input.txt"), 2, f"000 {BENCH_TS + 1:03d}")
+    res = _run_reference_processes(rundirs, binary)
+    for rundir in rundirs:
+        for f in (f"gridsave_ts{BENCH_TS}.tmp", f"packets_0000_ts{BENCH_TS}.tmp"):
+            if not os.path.exists(os.path.join(rundir, f)):
+                raise RuntimeError(f"{f} was not written in {rundir}")
+        _set_input_line(os.path.join(rundir, "input.txt"), 2, f"{BENCH_TS:03d} {BENCH_TS + 1:03d}")
+        _set_input_line(os.path.join(rundir, "input.txt"), 16, "1")
+    return res
+
+
+def cpu_reference_restart(rundirs, binary):
+    """resume at BENCH_TS from the saved grid and packets: one update_packets(BENCH_TS) per process"""
+    return _run_reference_processes(rundirs, binary)
+
+
+def cpu_restart_from_gpu_state(nproc, rundir_root, npackets_each):
+    """run folders that resume at BENCH_TS from the state the GPU workload run saved: its cell state
+    (gridsave_ts<BENCH_TS>.tmp, written by the reference's own driver in the drop-in binary) and disjoint slices of its
+    packets. The CPU reference then propagates a sample of exactly the packets, in exactly the cell state, of the GPU step."""
+    gpu_run = os.path.join(CACHE, f"{WORKLOAD}_run")
+    gridsave = os.path.join(gpu_run, f"gridsave_ts{BENCH_TS}.tmp")
+    pktfile = os.path.join(gpu_run, f"packets_0000_ts{BENCH_TS}.tmp")
+    if not (os.path.exists(gridsave) and os.path.exists(pktfile)):
+        return None
+    import struct
+    rundirs, binary = cpu_reference_setup(nproc, rundir_root)
+    with open(pktfile, "rb") as f:
+        total = struct.unpack("<q", f.read(8))[0]
+        stride = (os.path.getsize(pktfile) - 8) // total
+        for r, rundir in enumerate(rundirs):
+            f.seek(8 + r * npackets_each * stride)
+            chunk = f.read(npackets_each * stride)
+            with open(os.path.join(rundir, f"packets_0000_ts{BENCH_TS}.tmp"), "wb") as g:
+                g.write(struct.pack("<q", npackets_each))
+                g.write(chunk)
+            shutil.copy(gridsave, os.path.join(rundir, f"gridsave_ts{BENCH_TS}.tmp"))
+            _set_input_line(os.path.join(rundir, "input.txt"), 2, f"{BENCH_TS:03d} {BENCH_TS + 1:03d}")
+            _set_input_line(os.path.join(rundir, "input.txt"), 16, "1")
+    return rundirs, binary
+
+
+def cpu_baseline(gpu_interactions_per_packet=None):
+    """the compiled reference on the host cores of this box, K = min(8, cores) single-rank processes side by side: a bounded
+    sample (1e5 packets each) of the GPU step's own packets in the GPU step's own cell state when the workload run left
+    its restart files, else of an independent CPU evolution of the same model. Also the cross-check of the two codes:
+    interactions per packet of the GPU step against the K CPU samples (mean, standard error, z)."""
     root = os.path.join(CACHE, "cpu_baseline")
     os.makedirs(root, exist_ok=True)
-    res = cpu_reference_run(cores, root)
+    k = max(1, min(8, os.cpu_count() or 1))
+    npk = 100000
+    prepared = cpu_restart_from_gpu_state(k, root, npk)
+    if prepared is not None:
+        rundirs, binary = prepared
+        res = cpu_reference_restart(rundirs, binary)
+        how = (f"{k} processes x {npk} packets: disjoint slices of the GPU step's own packets, resumed by the reference from "
+               f"the cell state of the GPU workload run (gridsave_ts{BENCH_TS}.tmp)")
+    else:
+        rundirs, binary = cpu_reference_setup(k, root)
+        res = cpu_reference_evolve(rundirs, binary)
+        how = f"{k} processes x {npk} packets of an independent CPU evolution of timesteps 0..{BENCH_TS} of the same model"
     total_int = sum(r["interactions"] for r in res)
     wall = max(r["wall_s"] for r in res)
-    npk = res[0]["npackets"]
-    return {"value": total_int / wall, "unit": "interactions/s", "cores": cores, "kind": "reference",
-            "sample": f"{CPU_SAMPLE_CONFIG}: {npk} packets per process of the same model and atomic data, timestep {BENCH_TS} "
-                      f"after evolving timesteps 0..{BENCH_TS - 1} on the CPU; update_packets wall {wall:.2f} s, "
-                      f"{total_int} interactions", "wall_s": wall, "interactions_per_packet": total_int / (npk * len(res))}
+    per_packet = [r["interactions"] / r["npackets"] for r in res]
+    mean = sum(per_packet) / len(per_packet)
+    sd = (sum((x - mean) ** 2 for x in per_packet) / max(1, len(per_packet) - 1)) ** 0.5
+    out = {"value": total_int / wall, "unit": "interactions/s", "cores": k, "kind": "reference",
+           "sample": f"{CPU_SAMPLE_CONFIG}: {how}; update_packets({BENCH_TS}) wall {wall:.2f} s (slowest process), {total_int} interactions",
+           "wall_s": wall}
+    cross = {"interactions_per_packet_cpu_reference": mean, "cpu_seeds": len(per_packet), "cpu_std_between_seeds": sd,
+             "cpu_standard_error": sd / len(per_packet) ** 0.5 if len(per_packet) > 1 else None,
+             "same_cell_state_and_packets": prepared is not None}
+    if gpu_interactions_per_packet is not None:
+        cross["interactions_per_packet_gpu"] = gpu_interactions_per_packet
+        if len(per_packet) > 1 and sd > 0:
+            z = (gpu_interactions_per_packet - mean) / (sd / len(per_packet) ** 0.5)
+            cross.update(z=z, criterion="|z| < 4 (GPU mean of 1e7 packets against the mean of the CPU seeds, standard error from "
+                                        "the scatter between the seeds)", passed=bool(abs(z) < 4.0))
+    return out, cross
 
 
 def run_reference(args):
+    """the reference's own CPU update_packets on every host core: evolve timesteps 0..BENCH_TS-1 once (not timed), then
+    `warmup` + `steps` passes, each resuming from the saved grid and packets and running update_packets(BENCH_TS) alone"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    t_begin = time.time()
+    budget_s = float(os.environ.get("ARTISB200_REFERENCE_BUDGET_S", "270"))
     cores = os.cpu_count() or 1
     root = os.path.join(CACHE, "reference_arm")
     os.makedirs(root, exist_ok=True)
+    rundirs, binary = cpu_reference_setup(cores, root)
+    log(f"reference arm: evolving timesteps 0..{BENCH_TS} on {cores} cores (not timed) ...")
+    first = cpu_reference_evolve(rundirs, binary)
+    log(f"evolved in {time.time() - t_begin:.1f} s; update_packets({BENCH_TS}) took {max(r['wall_s'] for r in first):.2f} s")
     values, walls = [], []
-    for _ in range(args.warmup + args.steps):
-        res = cpu_reference_run(cores, root)
+    for it in range(args.warmup + args.steps):
+        t0 = time.time()
+        res = cpu_reference_restart(rundirs, binary)
         values.append(sum(r["interactions"] for r in res) / max(r["wall_s"] for r in res))
         walls.append(max(r["wall_s"] for r in res))
-        if len(values) >= 1 + args.steps or sum(walls) > 240:   # bounded: each pass re-evolves timesteps 0..k-1 as well
+        remaining_needed = (time.time() - t0) * (args.warmup + args.steps - it - 1)
+        if it + 1 >= args.steps and (time.time() - t_begin) + remaining_needed > budget_s:
+            log(f"reference arm: stopping after {it + 1} passes to stay within {budget_s:.0f} s")
             break
-    use = values[-args.steps:] if len(values) > args.steps else values
+    n_timed = min(args.steps, len(values))
+    use, use_walls = values[-n_timed:], walls[-n_timed:]
     v = sum(use) / len(use)
     npk = res[0]["npackets"]
-    sample = (f"{CPU_SAMPLE_CONFIG}: {cores} concurrent single-rank reference processes x {npk} packets, timestep {BENCH_TS}")
+    sample = (f"{CPU_SAMPLE_CONFIG}: {cores} concurrent single-rank reference processes x {npk} packets of the same model and "
+              f"atomic data (a bounded sample of the workload: {cores * npk} of the {bench_config()['packets_per_gpu']} packets), "
+              f"update_packets({BENCH_TS}) resumed from saved grid and packets each pass")
     out = {"impl": "reference", "metric": "packet-interactions/sec per timestep", "value": v, "unit": "interactions/s",
-           "n_gpus": args.gpus, "steps": len(use), "warmup": max(0, len(values) - len(use)), "ms_per_step": 1e3 * sum(walls[-len(use):]) / len(use),
+           "n_gpus": args.gpus, "steps": n_timed, "warmup": len(values) - n_timed, "ms_per_step": 1e3 * sum(use_walls) / len(use_walls),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}"},
+           "config": bench_config(),
            "cpu_baseline": {"value": v, "unit": "interactions/s", "cores": cores, "kind": "reference", "sample": sample},
-           "e2e": {"value": v, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "e2e": {"value": v, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "elapsed_s": time.time() - t_begin}
     print(json.dumps(out), flush=True)
 
 

@@ -142,6 +142,9 @@ int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name); /* -1 if un
  * "wf_rsteps_thin", "wf_rsteps_thick": r-packet steps per visit to the two r-packet stages;
  * "wf_masteps", "wf_ma_rounds", "wf_masteps_last", "wf_ma_growth": macro-atom transitions per visit, macro-atom
  *   kernels per iteration, transitions per visit in the last of them (0 = finish the walk), doubling every 2nd round;
+ * "wf_refill_masteps", "wf_refill_thicksteps": > 0 (default 0: measured no faster on B200, profiles/) = the macro-atom / grey r-packet stage runs as ONE kernel
+ *   per iteration in which a lane keeps its packet for up to this many transitions / steps and takes the next packet of
+ *   the list as soon as its own leaves the stage (lane refill); 0 = 32-packet chunks with the per-visit limits above;
  * "wf_resort_every", "wf_resort_min": re-sort the stage lists by model cell every this many iterations while at least
  *   that many packets are waiting (table locality; the appends keep the lists only roughly sorted);
  * "wf_concurrent": 1 (default) = the three independent stage kernels of an iteration run on separate streams;

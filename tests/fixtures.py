@@ -38,7 +38,7 @@ def load_golden(config, nts):
 
 def hostsim_library(preset, defines=(), tag=""):
     """test-only single-threaded host build of the device headers (tests/hostsim/hostsim.cc); built on demand.
-    `defines` / `tag`: a variant with extra -D flags (compile-time experiments such as ARTISB200_CHI_PREPASS)"""
+    `defines` / `tag`: a variant with extra -D flags (e.g. ARTISB200_HOSTSIM_FUZZ_LIBM)"""
     out = os.path.join(ROOT, "tests", "_build", f"libartis_b200_hostsim_{preset}{tag}.so")
     csrc = os.path.join(ROOT, "artis_b200", "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")] + [os.path.join(ROOT, "tests", "hostsim", "hostsim.cc")]

@@ -85,6 +85,7 @@ struct HostBackend {
       for (int w = 0; w < T.keepwords; w++) {
         ab::build_keepword_item(T, cell, w);
       }
+      ab::build_keptlist_cell(T, cell);
       for (int ulev = 0; ulev < T.nlevels; ulev++) {
         ab::build_macroatom_level(T, cell, ulev);
       }
@@ -173,11 +174,7 @@ struct HostBackend {
       auto run_list = [&](const int stage, const int in, const int next, const int next_ma, const int max_steps) {
         for (size_t k = 0; k < lists[in][stage].size(); k++) {
           const long long ip = lists[in][stage][k];
-#if ARTISB200_CHI_PREPASS
-          const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot, stage == ab::ST_RTHIN};
-#else
           const ab::Ctx c{T, ip, acc.cnt, acc.diag, acc.tss, &acc.pellet_decays, hot};
-#endif
           int dest = ab::ST_DONE;
           switch (stage) {
             case ab::ST_OTHER: dest = visit<ab::ST_OTHER>(T, c, ip, max_steps); break;
@@ -207,37 +204,19 @@ struct HostBackend {
         }
         const int next = cur ^ 1;
         run_list(ab::ST_OTHER, cur, next, cur, 1);
-#if ARTISB200_CHI_PREPASS
-        {  // k_chi_prepass + k_chi_terms of the CUDA backend, serially
-          long long cursor = 0;
-          for (const int ip : lists[cur][ab::ST_RTHIN]) {
-            const ab::ChiTermRequest r = ab::chiterm_request(T, ip);
-            const long long mine = (r.count > 0) ? r.count : 0;
-            const long long off = cursor;
-            cursor += mine;
-            const bool fits = (off + mine) <= T.chiterm_capacity;
-            ab::chiterm_emit(T, ip, r, fits ? off : -1);
-            if (!fits) {
-              for (long long j = off; j < off + mine && j < T.chiterm_capacity; j++) {
-                T.chiterm_desc[j] = {-1, 0};
-              }
-            }
-          }
-          const long long nterms = (cursor < T.chiterm_capacity) ? cursor : T.chiterm_capacity;
-          for (long long idx = 0; idx < nterms; idx++) {
-            ab::chiterm_eval(T, idx);
-          }
-          tm->launches += 2;
-        }
-#endif
         run_list(ab::ST_RTHIN, cur, next, cur, o.rsteps_thin);
-        run_list(ab::ST_RTHICK, cur, next, cur, o.rsteps_thick);
-        int ma_in = cur;
-        for (int r = 0; r < ma_rounds; r++) {
-          run_list(ab::ST_MA, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds));
-          if (r + 1 < ma_rounds) {
-            lists[ma_in][ab::ST_MA].clear();
-            ma_in ^= 1;
+        // (lane refill, k_wf_refill: per packet the same as one visit of up to the refill limit of single steps)
+        run_list(ab::ST_RTHICK, cur, next, cur, (o.refill_thicksteps > 0) ? o.refill_thicksteps : o.rsteps_thick);
+        if (o.refill_masteps > 0) {
+          run_list(ab::ST_MA, cur, next, next, o.refill_masteps);
+        } else {
+          int ma_in = cur;
+          for (int r = 0; r < ma_rounds; r++) {
+            run_list(ab::ST_MA, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds));
+            if (r + 1 < ma_rounds) {
+              lists[ma_in][ab::ST_MA].clear();
+              ma_in ^= 1;
+            }
           }
         }
         for (int s = 0; s < ab::NSTAGES; s++) {
@@ -245,7 +224,7 @@ struct HostBackend {
         }
         cur ^= 1;
         tm->iterations++;
-        tm->launches += ab::NSTAGES + (2 * ma_rounds) - 1;
+        tm->launches += ab::NSTAGES + ((o.refill_masteps > 0) ? 1 : (2 * ma_rounds) - 1);
       }
     } else {
       run_history(T, n, acc, tm);

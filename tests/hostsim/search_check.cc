@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY. The searches of the macro-atom stage (artis_b200/csrc/macroatom.h: the 8-way
-// index_upperbound and, with ARTISB200_MA_SUMMARY, index_upperbound_summary) against std::upper_bound on random
+// index_upperbound) against std::upper_bound on random
 // cumulative arrays of every length 0..700, with runs of equal values, targets on, between and outside the values.
 // Built and run by tests/test_hostsim_parity.py (the toy fixtures have at most 7 transitions per level, which never
 // reaches the multi-level part of either search). Prints "ok <cases>" or the first mismatch.
@@ -50,13 +50,6 @@ int main() {
           std::printf("index_upperbound: n=%d target=%.17g got %d want %d\n", n, t, got, want);
           return 1;
         }
-#if ARTISB200_MA_SUMMARY
-        const int got_s = ab::index_upperbound_summary(a.data(), S.data(), n, t, c);
-        if (got_s != want) {
-          std::printf("index_upperbound_summary: n=%d target=%.17g got %d want %d\n", n, t, got_s, want);
-          return 1;
-        }
-#endif
         cases++;
       }
     }

@@ -15,11 +15,13 @@ CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
 SCHEDULES = {
     "wavefront": {"schedule": 1},                                       # default (toy sizes: mostly the tail kernel)
     "history": {"schedule": 0},                                         # one whole-history kernel
+    # chunked stage kernels (no lane refill), one step / one transition per visit
     "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1, "wf_masteps": 1, "wf_ma_rounds": 1,
-                         "wf_masteps_last": -1},
-    "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0},   # whole macro-atom walk per visit
+                         "wf_masteps_last": -1, "wf_refill_masteps": 0, "wf_refill_thicksteps": 0},
+    "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0, "wf_refill_masteps": 0},   # whole macro-atom walk per visit
+    "wavefront-refill": {"schedule": 1, "wf_tail": 0, "wf_refill_masteps": 3, "wf_refill_thicksteps": 2},  # lane refill, short visits
     "wavefront-resort": {"schedule": 1, "wf_tail": 0, "wf_resort_every": 1, "wf_sync_every": 2},  # lists re-sorted by cell
-    "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2},
+    "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2, "wf_refill_masteps": 0},
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
 }
 
@@ -60,31 +62,6 @@ def test_options_summary_names_the_preset(preset):
     abi_checks.check_options_summary(fixtures.hostsim_library(preset), preset)
 
 
-# ARTISB200_CHI_PREPASS (experimental compile-time variant): bound-free terms evaluated by a
-# kernel of their own ahead of the detailed r-packet stage. Same packets, estimators and counters; the second variant
-# has a term buffer of 8 terms, so that most requests do not fit and fall back to the inline sum.
-PREPASS_CASES = [("classic_toy", 3), ("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_detailedbf_toy", 3), ("nltephot_toy", 3)]
-PREPASS_SCHEDULES = ["wavefront-notail", "wavefront-resort", "wavefront-tail"]
-
-
-@pytest.mark.parametrize("tag,defines", [("_prepass", ("ARTISB200_CHI_PREPASS=1",)),
-                                         ("_prepass_tiny", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_CHITERMS_CAP=8")),
-                                         ("_prepass_masum", ("ARTISB200_CHI_PREPASS=1", "ARTISB200_MA_SUMMARY=1"))])
-@pytest.mark.parametrize("schedule", PREPASS_SCHEDULES)
-@pytest.mark.parametrize("config,nts", PREPASS_CASES)
-def test_chi_prepass_variant_keeps_histories(config, nts, schedule, tag, defines):
-    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=defines, tag=tag)
-    _, _, est = parity_checks.check_packet_histories(lib, config, nts, options=SCHEDULES[schedule])
-    terms, from_buffer = int(est["diag"][3]), int(est["diag"][12])
-    assert 0 <= from_buffer <= terms
-    if tag != "_prepass_tiny":
-        assert from_buffer > 0
-    if tag == "_prepass" and schedule != "wavefront-tail":  # (the tail kernel and steps 2.. of a visit sum inline)
-        assert from_buffer > 0.9 * terms
-    if tag == "_prepass_tiny":
-        assert from_buffer < terms  # some requests did not fit and were summed inline
-
-
 # "Another libm": the device's exp/log/sin/cos/pow are correct to 1-2 ulp but not bit-equal to glibc's. This host build
 # moves every transcendental result by -1/0/+1 ulp (tests/hostsim/hostsim.cc, ARTISB200_HOSTSIM_FUZZ_LIBM); the parity
 # assertions, at the tolerances the GPU suite uses, must not depend on those bits. (It reproduces what the B200 showed:
@@ -97,27 +74,14 @@ def test_parity_assertions_do_not_depend_on_libm_rounding(config, nts):
     parity_checks.check_packet_histories(lib, config, nts, tol=1e-9, est_tol=1e-9, options=SCHEDULES["wavefront-resort"])
 
 
-# ARTISB200_MA_SUMMARY (experimental compile-time variant): macro-atom searches through a summary of
-# every 8th cumulative rate. Same transitions selected, hence the same packets, estimators and counters.
-@pytest.mark.parametrize("schedule", ["history", "wavefront-rounds", "wavefront-walk"])
-@pytest.mark.parametrize("config,nts", PREPASS_CASES + [("classic_nt_toy", 3), ("classic_nlte_toy", 4)])
-def test_ma_summary_variant_keeps_histories(config, nts, schedule):
-    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=("ARTISB200_MA_SUMMARY=1",), tag="_masum")
-    plain = fixtures.hostsim_library(fixtures.PRESET_OF[config])
-    _, _, est = parity_checks.check_packet_histories(lib, config, nts, options=SCHEDULES[schedule])
-    _, _, est_plain = parity_checks.check_packet_histories(plain, config, nts, options=SCHEDULES[schedule])
-    assert int(est["diag"][6]) == int(est_plain["diag"][6]) > 0     # macro-atom transitions taken
-    assert int(est["diag"][4]) == int(est_plain["diag"][4])         # the work counter of the searches is kept
-
-
 def test_macroatom_searches_equal_upper_bound(tmp_path):
-    # tests/hostsim/search_check.cc: the 8-way search and the summary search against std::upper_bound (lengths 0..700)
+    # tests/hostsim/search_check.cc: the 8-way search against std::upper_bound (lengths 0..700)
     import os
     import subprocess
     csrc = os.path.join(fixtures.ROOT, "artis_b200", "csrc")
     exe = str(tmp_path / "search_check")
     subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-subobject-linkage", "-I" + csrc,
-                    "-DARTISB200_MA_SUMMARY=1", "-DARTISB200_PRESET_HEADER=\"options/preset_kilonova_lte.h\"",
+                    "-DARTISB200_PRESET_HEADER=\"options/preset_kilonova_lte.h\"",
                     os.path.join(fixtures.ROOT, "tests", "hostsim", "search_check.cc"), "-o", exe], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.startswith("ok "), out

@@ -1,6 +1,6 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE: compile the physics headers for the host (tests/hostsim) with AddressSanitizer + UBSan and replay
-# oracle fixtures through every schedule. usage: [EXTRA_DEFS="-DARTISB200_CHI_PREPASS=1 ..."] bash tools/hostsim_sanitize.sh [preset config nts]
+# oracle fixtures through every schedule. usage: [EXTRA_DEFS="-DARTISB200_HOSTSIM_FUZZ_LIBM ..."] bash tools/hostsim_sanitize.sh [preset config nts]
 set -eu
 cd "$(dirname "$0")/.."
 PRESET=${1:-kilonova_lte}; CONFIG=${2:-kilonova_toy}; NTS=${3:-4}
