@@ -261,7 +261,47 @@ struct WfQueues {
   unsigned int* count;        // [2][NSTAGES] list lengths
   unsigned int* cursor;       // [NSTAGES] next 32-packet chunk of the running iteration's lists
   unsigned long long* status; // [0] packets waiting after the last completed iteration, [1] iterations run
+  // packets that need no further work this timestep, in the order they finished (streamed download: the host copy of
+  // a finished packet can leave while the others are still being propagated); null = not collected
+  int* done;
+  unsigned int* done_count;
 };
+
+// append the packets of the lanes with `finished` to the done list (all 32 lanes call)
+__device__ __forceinline__ void done_append(const WfQueues& q, const bool finished, const int ip) {
+  if (q.done == nullptr) {
+    return;
+  }
+  const unsigned m = __ballot_sync(0xffffffffU, finished);
+  if (m != 0U) {
+    const unsigned lane = threadIdx.x & 31U;
+    const int leader = __ffs(m) - 1;
+    unsigned int pos = 0U;
+    if (lane == static_cast<unsigned int>(leader)) {
+      pos = atomicAdd(q.done_count, static_cast<unsigned int>(__popc(m)));
+    }
+    pos = __shfl_sync(0xffffffffU, pos, leader);
+    if (finished) {
+      q.done[pos + __popc(m & ((1U << lane) - 1U))] = ip;
+    }
+  }
+}
+
+// packets that are inactive from the start of the timestep (escaped earlier, or already at the end of the timestep)
+__global__ void k_done_seed(const __grid_constant__ Tables T, const WfQueues q, const long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const bool finished = (i < n) && (ab::stored_stage(T.pkt.hc[(i < n) ? i : 0]) < 0);
+  done_append(q, finished, static_cast<int>(i));
+}
+
+// AoS records of the packets done[first, last) into staging slots [first, last): completion order
+__global__ void k_soa_to_aos_list(const __grid_constant__ Tables T, unsigned char* aos, const int* __restrict__ done, const long long first,
+                                  const long long last, const int stride) {
+  const long long k = first + (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (k < last) {
+    ab::soa_to_aos_rec(T, aos + (k * stride), stride, done[k]);
+  }
+}
 
 // threads per block / minimum resident blocks per SM of the stage kernels (the register budget follows from it)
 #ifndef ARTISB200_WF_BLOCK
@@ -373,6 +413,7 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
       ab::store_pkt<STAGE>(p, chi, T, ip, dest);
     }
     __syncwarp();
+    done_append(q, (k < n) && (dest == ab::ST_DONE), ip);
 #pragma unroll
     for (int s = 0; s < ab::NSTAGES; s++) {
       const unsigned m = __ballot_sync(FULL, dest == s);
@@ -470,6 +511,7 @@ __global__ void __launch_bounds__(WF_BLOCK, wf_minblocks(STAGE))
       }
     }
     __syncwarp();
+    done_append(q, dest == ab::ST_DONE, ip);
 #pragma unroll
     for (int s = 0; s < ab::NSTAGES; s++) {
       const unsigned m = __ballot_sync(FULL, dest == s);
@@ -614,7 +656,7 @@ __global__ void k_reset_work(const __grid_constant__ Tables T, const long long n
 // queue[0]: next queue position to hand out; queue[1]: packets that still need work after this launch;
 // queue[2]: number of active packets in `order`
 __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const int* __restrict__ order,
-                                                          unsigned long long* queue) {
+                                                          unsigned long long* queue, int* done, unsigned int* done_count) {
   __shared__ ab::Accum acc;
   __shared__ unsigned int s_still_active;
   if (threadIdx.x == 0) {
@@ -682,6 +724,8 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
         have = false;
         if (yield) {
           atomicAdd(&s_still_active, 1U);
+        } else if (done != nullptr) {
+          done[atomicAdd(done_count, 1U)] = static_cast<int>(ip);
         }
       }
     }
@@ -719,6 +763,21 @@ struct CudaBackend {
   unsigned int* d_stage_count{nullptr};  // [NSTAGES] list lengths of the cell-sorted order
   unsigned int* d_wf_count{nullptr};     // [2][NSTAGES] list lengths + [NSTAGES] chunk cursors
   int* d_wf_lists{nullptr};              // [2][NSTAGES][wf_capacity]
+  // streamed download (update_packets_host with option stream_download): packets that have finished are converted to
+  // the reference's Packet layout and copied to the host, in completion order, on the copy stream while the wavefront
+  // goes on with the others
+  struct StreamOut {
+    bool active{false};
+    unsigned char* host{nullptr};     // the caller's packet array
+    unsigned char* staging{nullptr};  // device AoS staging (the upload buffer)
+    int stride{0};
+    long long total{0};
+    long long flushed{0};             // done-list entries already on their way to the host
+    long long min_chunk{262144};
+  } stream_out;
+  int* d_done{nullptr};
+  unsigned int* d_done_count{nullptr};
+  long long done_capacity{0};
   long long wf_capacity{0};
   int history_blocks_per_sm{0};
   int stage_blocks_per_sm[ab::NSTAGES]{};
@@ -793,6 +852,8 @@ struct CudaBackend {
       cudaFree(d_stage_count);
       cudaFree(d_wf_count);
       cudaFree(d_wf_lists);
+      cudaFree(d_done);
+      cudaFree(d_done_count);
       for (cudaEvent_t e : stage_events) {
         cudaEventDestroy(e);
       }
@@ -986,6 +1047,70 @@ struct CudaBackend {
     return true;
   }
 
+  // copy what has finished since the last call (or, with `final`, whatever is left) to the host. Called at points where
+  // the main stream has been synchronised, so the done list up to `upto` and those packets' records are final.
+  bool flush_done(const Tables& T, const bool final) {
+    if (!stream_out.active) {
+      return true;
+    }
+    unsigned int upto_u = 0U;
+    if (!ok(cudaMemcpyAsync(&upto_u, d_done_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream), "done count readback") ||
+        !ok(cudaStreamSynchronize(stream), "done count readback")) {
+      return false;
+    }
+    const long long upto = upto_u;
+    if (final && upto != stream_out.total) {
+      error = "streamed download: " + std::to_string(upto) + " of " + std::to_string(stream_out.total) + " packets finished";
+      return false;
+    }
+    const long long count = upto - stream_out.flushed;
+    if (count > 0 && (final || count >= stream_out.min_chunk)) {
+      const long long first = stream_out.flushed;
+      k_soa_to_aos_list<<<blocks_for(count, 256), 256, 0, copy_stream>>>(T, stream_out.staging, d_done, first, upto, stream_out.stride);
+      if (!ok(cudaMemcpyAsync(stream_out.host + (first * stream_out.stride), stream_out.staging + (first * stream_out.stride),
+                              static_cast<size_t>(count) * static_cast<size_t>(stream_out.stride), cudaMemcpyDeviceToHost, copy_stream),
+              "cudaMemcpy D2H (finished packets)")) {
+        return false;
+      }
+      stream_out.flushed = upto;
+    }
+    if (final) {
+      return ok(cudaStreamSynchronize(copy_stream), "streamed download") && ok(cudaGetLastError(), "k_soa_to_aos_list");
+    }
+    return true;
+  }
+
+  // upload + propagate + download of update_packets_host in one go, the download streamed
+  bool begin_stream_out(void* host_aos, void* staging, const int64_t n, const int stride) {
+    cudaSetDevice(device);
+    if (done_capacity < n) {
+      if (!grow(d_done, static_cast<size_t>(n) * sizeof(int), "cudaMalloc(done list)")) {
+        return false;
+      }
+      done_capacity = n;
+    }
+    if (d_done_count == nullptr && !ok(cudaMalloc(&d_done_count, sizeof(unsigned int)), "cudaMalloc(done count)")) {
+      return false;
+    }
+    stream_out = StreamOut{};
+    stream_out.active = true;
+    stream_out.host = static_cast<unsigned char*>(host_aos);
+    stream_out.staging = static_cast<unsigned char*>(staging);
+    stream_out.stride = stride;
+    stream_out.total = n;
+    return true;
+  }
+  void end_stream_out() { stream_out.active = false; }
+
+  bool register_host(void* ptr, const int64_t nbytes) {
+    cudaSetDevice(device);
+    return ok(cudaHostRegister(ptr, static_cast<size_t>(nbytes), cudaHostRegisterDefault), "cudaHostRegister");
+  }
+  bool unregister_host(void* ptr) {
+    cudaSetDevice(device);
+    return ok(cudaHostUnregister(ptr), "cudaHostUnregister");
+  }
+
   void sort_active(const Tables& T, const int64_t n) {
     const int nbuckets_per_stage = T.ncells + 1;
     const int nbuckets = ab::NSTAGES * nbuckets_per_stage;
@@ -1024,7 +1149,8 @@ struct CudaBackend {
       cudaEventRecord(ev_sched0, stream);
       sort_active(T, n);
       cudaEventRecord(ev_sched1, stream);
-      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, d_order, d_queue);
+      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, d_order, d_queue, stream_out.active ? d_done : nullptr,
+                                                                                 d_done_count);
       tm->launches += 4;
       if (!ok(cudaMemcpyAsync(hq, d_queue, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
           !ok(cudaStreamSynchronize(stream), "k_propagate")) {
@@ -1086,6 +1212,8 @@ struct CudaBackend {
     q.count = d_wf_count;
     q.cursor = d_wf_count + (2 * ab::NSTAGES);
     q.status = d_queue + 4;
+    q.done = stream_out.active ? d_done : nullptr;
+    q.done_count = d_done_count;
     cudaEventRecord(ev_sched0, stream);
     sort_active(T, n);
     k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, stream>>>(q, d_order, d_stage_count);
@@ -1177,6 +1305,9 @@ struct CudaBackend {
           }
         }
       }
+      if (!flush_done(T, false)) {
+        return false;
+      }
       if (status[0] == 0ULL) {
         break;
       }
@@ -1210,6 +1341,14 @@ struct CudaBackend {
     cudaEventRecord(ev_start, stream);
     k_reset_work<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
     tm->launches += 1;
+    if (stream_out.active) {
+      WfQueues dq{};
+      dq.done = d_done;
+      dq.done_count = d_done_count;
+      cudaMemsetAsync(d_done_count, 0, sizeof(unsigned int), stream);
+      k_done_seed<<<blocks_for(n, 256), 256, 0, stream>>>(T, dq, n);
+      tm->launches += 1;
+    }
     const bool good = (o.schedule == 1) ? run_wavefront(T, n, o, tm) : run_history(T, n, tm);
     if (!good) {
       return false;
@@ -1220,6 +1359,9 @@ struct CudaBackend {
       return false;
     }
     tables_building = false;  // the stream has been synchronised
+    if (!flush_done(T, true)) {
+      return false;
+    }
     float ms = 0.F;
     cudaEventElapsedTime(&ms, ev_start, ev_stop);
     tm->total_ms = ms;

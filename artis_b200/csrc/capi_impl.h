@@ -65,6 +65,11 @@ int artisb200_get_array(artisb200_ctx* ctx, const char* name, const char dtype, 
   return ctx->eng.get_array(name, dtype, host_out, count);
 }
 
+int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, const char dtype, void* host_out, const int64_t offset,
+                              const int64_t count) {
+  return ctx->eng.get_array_range(name, dtype, host_out, offset, count);
+}
+
 int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name) {
   const ab::FieldDesc* f = ab::find_field(name);
   if (f != nullptr && f->kind == ab::FieldKind::SCALAR) {
@@ -91,6 +96,9 @@ int artisb200_update_packets(artisb200_ctx* ctx, const int nts) { return ctx->en
 
 int artisb200_update_packets_host(artisb200_ctx* ctx, const int nts, void* packets_aos, const int64_t npackets,
                                   const int stride_bytes) {
+  if (ctx->eng.stream_download) {
+    return ctx->eng.update_packets_host_streamed(nts, packets_aos, npackets, stride_bytes);
+  }
   int rc = ctx->eng.upload_packets(packets_aos, npackets, stride_bytes);
   if (rc != 0) {
     return rc;
@@ -101,6 +109,11 @@ int artisb200_update_packets_host(artisb200_ctx* ctx, const int nts, void* packe
   }
   return ctx->eng.download_packets(packets_aos, npackets, stride_bytes);
 }
+
+int artisb200_register_host_buffer(artisb200_ctx* ctx, void* ptr, const int64_t nbytes) {
+  return ctx->eng.register_host_buffer(ptr, nbytes, true);
+}
+int artisb200_unregister_host_buffer(artisb200_ctx* ctx, void* ptr) { return ctx->eng.register_host_buffer(ptr, 0, false); }
 
 int artisb200_save_packets_device(artisb200_ctx* ctx) { return ctx->eng.save_packets_device(); }
 int artisb200_restore_packets_device(artisb200_ctx* ctx) { return ctx->eng.restore_packets_device(); }

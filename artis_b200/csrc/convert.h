@@ -82,10 +82,24 @@ AHD void aos_to_soa_one(const Tables& T, const unsigned char* aos, const int str
   s.originated_from_particlenotgamma[i] = static_cast<int>(rd<unsigned char>(q, L::originated_from_particlenotgamma));
   s.pellet_decaytype[i] = rd<int>(q, L::pellet_decaytype);
   s.pellet_nucindex[i] = rd<int>(q, L::pellet_nucindex);
+  if (b == 16) {
+    // the host's generator state travels with the packet (with Philox the device neither uses nor changes it)
+    RngPrefix pre;
+    for (int k = 0; k < 4; k++) {
+      pre.w[k] = rd<unsigned int>(rec, 4 * k);
+    }
+    s.rngprefix[i] = pre;
+  }
 }
 
+// packet i of the device records as one reference Packet at `rec`
+AHD void soa_to_aos_rec(const Tables& T, unsigned char* rec, const int stride, const long long i);
+
 AHD void soa_to_aos_one(const Tables& T, unsigned char* aos, const int stride, const long long i) {
-  unsigned char* rec = aos + (i * stride);
+  soa_to_aos_rec(T, aos + (i * stride), stride, i);
+}
+
+AHD void soa_to_aos_rec(const Tables& T, unsigned char* rec, const int stride, const long long i) {
   const int b = stride - AosLayout::size;
   unsigned char* q = rec + b;
   const PacketStore& s = T.pkt;
@@ -126,9 +140,10 @@ AHD void soa_to_aos_one(const Tables& T, unsigned char* aos, const int stride, c
                     static_cast<unsigned char>(s.originated_from_particlenotgamma[i] != 0 ? 1 : 0));
   wr<int>(q, L::pellet_decaytype, s.pellet_decaytype[i]);
   wr<int>(q, L::pellet_nucindex, s.pellet_nucindex[i]);
-  if (b == 16 && T.rng_mode == RNG_XOSHIRO) {
+  if (b == 16) {
+    const RngPrefix pre = s.rngprefix[i];
     for (int k = 0; k < 4; k++) {
-      wr<unsigned int>(rec, 4 * k, hc.rng[k]);
+      wr<unsigned int>(rec, 4 * k, (T.rng_mode == RNG_XOSHIRO) ? hc.rng[k] : pre.w[k]);
     }
   }
 }

@@ -179,6 +179,7 @@ class Engine {
   // options
   int rank{0};
   int nranks{1};
+  bool stream_download{false};  // [stream_download] update_packets_host returns the packets in completion order
   PropagateOptions popt;
   PropagateTimings last;
   int64_t scratch_capacity{0};
@@ -347,6 +348,24 @@ class Engine {
     return 0;
   }
 
+  // a slice [offset, offset + count) of an array (the per-cell tables of a large model are gigabytes)
+  int get_array_range(const char* name_c, const char dtype, void* out, const int64_t offset, const int64_t count) {
+    const std::string name(name_c);
+    const auto it = arrays.find(name);
+    if (it == arrays.end() || it->second.dptr == nullptr) {
+      return fail("array '" + name + "' has not been set/allocated");
+    }
+    if (dtype != it->second.dtype || offset < 0 || count < 0 || offset + count > it->second.count) {
+      return fail("array '" + name + "': dtype mismatch or range outside the array (have '" + std::string(1, it->second.dtype) +
+                  "' x " + std::to_string(it->second.count) + ")");
+    }
+    const int64_t item = static_cast<int64_t>(dsize(dtype));
+    if (count > 0 && !be.d2h(out, static_cast<const unsigned char*>(it->second.dptr) + (offset * item), count * item)) {
+      return fail("device-to-host copy failed for '" + name + "': " + be.last_error());
+    }
+    return 0;
+  }
+
   int set_option(const char* name_c, const long long value) {
     const std::string name(name_c);
     if (name == "rng_mode") {
@@ -388,6 +407,8 @@ class Engine {
       popt.refill_thicksteps = static_cast<int>(value < 0 ? 0 : value);
     } else if (name == "wf_stage_timing") {
       popt.stage_timing = static_cast<int>(value);
+    } else if (name == "stream_download") {
+      stream_download = (value != 0);
     } else if (name == "rank") {
       rank = static_cast<int>(value);
     } else if (name == "nranks") {
@@ -836,6 +857,36 @@ class Engine {
     }
     if (n > 0 && !be.d2h(aos, aos_staging, n * stride)) {
       return fail("download_packets: device-to-host copy failed: " + be.last_error());
+    }
+    return 0;
+  }
+
+  // update_packets_host with the download streamed (option stream_download): finished packets leave for the host while the
+  // others are still being propagated; the array comes back PERMUTED (completion order), as the reference's own
+  // update_packets leaves it sorted differently from how it got it (update_packets.cc:570)
+  int update_packets_host_streamed(const int nts, void* aos, const int64_t n, const int stride) {
+    int rc = upload_packets(aos, n, stride);
+    if (rc != 0) {
+      return rc;
+    }
+    if constexpr (requires(Backend& b) { b.begin_stream_out(aos, aos_staging, n, stride); }) {
+      if (!be.begin_stream_out(aos, aos_staging, n, stride)) {
+        return fail("update_packets_host: streamed download setup failed: " + be.last_error());
+      }
+      rc = update_packets(nts);
+      be.end_stream_out();
+      return rc;
+    } else {
+      rc = update_packets(nts);
+      return (rc != 0) ? rc : download_packets(aos, n, stride);
+    }
+  }
+
+  int register_host_buffer(void* ptr, const int64_t nbytes, const bool on) {
+    if constexpr (requires(Backend& b) { b.register_host(ptr, nbytes); }) {
+      if (!(on ? be.register_host(ptr, nbytes) : be.unregister_host(ptr))) {
+        return fail(std::string("host buffer ") + (on ? "registration" : "release") + " failed: " + be.last_error());
+      }
     }
     return 0;
   }

@@ -262,6 +262,10 @@ struct alignas(32) EmRec {  // em_pos/em_time/emissiontype or trueem_pos/trueem_
   int type;
 };
 
+struct alignas(16) RngPrefix {  // the 16-byte rngstate a GPU_ON host build keeps in front of every Packet (packet.h:110-114)
+  unsigned int w[4];
+};
+
 static_assert(sizeof(HotA) == 64 && sizeof(HotB) == 64 && sizeof(HotC) == 64 && sizeof(EmRec) == 32, "record sizes");
 
 #define AB_PACKET_RECORDS(X) \
@@ -280,7 +284,8 @@ static_assert(sizeof(HotA) == 64 && sizeof(HotB) == 64 && sizeof(HotC) == 64 && 
   X(int, number)              \
   X(int, originated_from_particlenotgamma) \
   X(int, pellet_decaytype)    \
-  X(int, pellet_nucindex)
+  X(int, pellet_nucindex)     \
+  X(RngPrefix, rngprefix)
 
 #define AB_PACKET_ARRAYS(X) AB_PACKET_RECORDS(X) AB_PACKET_FIELDS(X)
 

@@ -30,6 +30,8 @@ _SIGNATURES = {
     "artisb200_set_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64]),
     "artisb200_get_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64]),
     "artisb200_array_count": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p]),
+    "artisb200_get_array_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64,
+                                                 ctypes.c_int64]),
     "artisb200_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "artisb200_commit_static": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_begin_timestep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -37,6 +39,8 @@ _SIGNATURES = {
     "artisb200_download_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "artisb200_update_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "artisb200_update_packets_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "artisb200_register_host_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "artisb200_unregister_host_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "artisb200_save_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_restore_packets_device": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_estimator_device_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
@@ -125,6 +129,14 @@ class ArtisB200:
         code = snap_mod.dtype_code(out).encode()
         self._check(self.lib.artisb200_get_array(self.ctx, name.encode(), code, out.ctypes.data_as(ctypes.c_void_p), n),
                     f"get_array({name})")
+        return out
+
+    def get_array_range(self, name, offset, count, dtype=None):
+        dt = np.dtype(dtype or _OUT_DTYPES.get(name, np.float64))
+        out = np.empty(int(count), dtype=dt)
+        code = snap_mod.dtype_code(out).encode()
+        self._check(self.lib.artisb200_get_array_range(self.ctx, name.encode(), code, out.ctypes.data_as(ctypes.c_void_p), int(offset),
+                                                       int(count)), f"get_array_range({name})")
         return out
 
     def commit_static(self):

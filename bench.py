@@ -268,6 +268,11 @@ def run_ours(args):
             reduce_estimators()
         return timed(body)
 
+    if args.one_step:
+        ms = device_step_timed()
+        log(f"one step: {ms:.1f} ms (under a profiler this is not a bench value)")
+        eng.close()
+        return
     log(f"rank {rank}: {n} packets, stride {stride}; warm-up {args.warmup} steps")
     for _ in range(args.warmup):
         device_step_timed()
@@ -298,6 +303,9 @@ def run_ours(args):
     eng.set_option("wf_stage_timing", 0)
 
     # end-to-end through the host-buffer call (the drop-in signature): H2D packets, propagate, D2H packets + estimators
+    # (as the drop-in binding calls it: finished packets are copied back while the wavefront drains, the array comes
+    # back in completion order - the reference's own update_packets permutes it too)
+    eng.set_option("stream_download", int(os.environ.get("ARTISB200_BENCH_STREAM_DOWNLOAD", "1")))
     e2e_ms = []
     for it in range(max(1, min(args.steps, 3))):
         work.copy_(host_packets)
@@ -582,6 +590,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-step", action="store_true", help="profiling aid: run exactly one device step and exit (no JSON line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

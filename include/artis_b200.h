@@ -134,8 +134,10 @@ int artisb200_set_array(artisb200_ctx* ctx, const char* name, char dtype, const 
  * `count` must equal the array's length (query with artisb200_array_count). */
 int artisb200_get_array(artisb200_ctx* ctx, const char* name, char dtype, void* host_out, int64_t count);
 int64_t artisb200_array_count(artisb200_ctx* ctx, const char* name); /* -1 if unknown / unset */
+/* elements [offset, offset + count) of an array (the per-cell tables of a large model are gigabytes) */
+int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, void* host_out, int64_t offset, int64_t count);
 
-/* Runtime options: "rng_mode" (ARTISB200_RNG_*), "seed", "rank", "nranks";
+/* Runtime options: "rng_mode" (ARTISB200_RNG_*), "seed", "rank", "nranks"; "stream_download" (see update_packets_host);
  * "schedule": 1 (default) = wavefront: one kernel per packet stage (other | r-packet detailed | r-packet grey |
  *   macro-atom) over cell-sorted index lists per iteration, 0 = one whole-history kernel (thread per packet);
  *   packet results do not depend on the schedule (per-packet random number streams, per-packet opacity cache);
@@ -172,8 +174,16 @@ int artisb200_download_packets(artisb200_ctx* ctx, void* packets_aos, int64_t np
 int artisb200_update_packets(artisb200_ctx* ctx, int nts);
 
 /* The drop-in call: upload + artisb200_update_packets + download, i.e. exactly what
- * update_packets(nts, packets) does to the caller's array (order of packets is preserved here). */
+ * update_packets(nts, packets) does to the caller's array. The order of the packets is preserved unless the option
+ * "stream_download" is 1: then every packet is copied back as soon as it needs no further work this timestep, while the
+ * others are still being propagated, and the array comes back PERMUTED (completion order) - which the caller of the
+ * reference must be prepared for anyway: update_packets sorts the span it is given (update_packets.cc:363-394, 570). */
 int artisb200_update_packets_host(artisb200_ctx* ctx, int nts, void* packets_aos, int64_t npackets, int stride_bytes);
+
+/* Page-lock the caller's packet array (cudaHostRegister) so that the transfers above run at full PCIe speed and
+ * asynchronously; sn3d.cc allocates its std::vector<Packet> once (sn3d.cc:1089), the binding registers it once. */
+int artisb200_register_host_buffer(artisb200_ctx* ctx, void* ptr, int64_t nbytes);
+int artisb200_unregister_host_buffer(artisb200_ctx* ctx, void* ptr);
 
 /* Device-resident snapshot/restore of the packet state, for benchmarks that replay one timestep. */
 int artisb200_save_packets_device(artisb200_ctx* ctx);

@@ -428,6 +428,9 @@ struct Lib {
   decltype(&artisb200_last_timing_ms) last_timing_ms{};
   decltype(&artisb200_options_summary) options_summary{};
   decltype(&artisb200_options_hash) options_hash{};
+  decltype(&artisb200_register_host_buffer) register_host_buffer{};
+  decltype(&artisb200_unregister_host_buffer) unregister_host_buffer{};
+  void* registered{nullptr};
   artisb200_ctx* ctx{nullptr};
 };
 
@@ -502,6 +505,8 @@ void lib_init() {
   load_symbol(lib.last_timing_ms, "artisb200_last_timing_ms");
   load_symbol(lib.options_summary, "artisb200_options_summary");
   load_symbol(lib.options_hash, "artisb200_options_hash");
+  load_symbol(lib.register_host_buffer, "artisb200_register_host_buffer");
+  load_symbol(lib.unregister_host_buffer, "artisb200_unregister_host_buffer");
 
   const int device = std::atoi(env_or("ARTISB200_DEVICE", env_or("LOCAL_RANK", "0").c_str()).c_str());
   if (lib.create(&lib.ctx, device) != 0) {
@@ -527,6 +532,9 @@ void lib_init() {
   check(lib.set_option(lib.ctx, "rng_mode", xoshiro ? ARTISB200_RNG_XOSHIRO : ARTISB200_RNG_PHILOX), "rng_mode");
   check(lib.set_option(lib.ctx, "seed", read_pre_zseed()), "seed");
   check(lib.set_option(lib.ctx, "rank", globals::my_rank), "rank");
+  // finished packets are copied back while the others are still propagated; the span comes back permuted, like the
+  // reference's own update_packets leaves it (ARTISB200_STREAM_DOWNLOAD=0: ordered download)
+  check(lib.set_option(lib.ctx, "stream_download", std::atoi(env_or("ARTISB200_STREAM_DOWNLOAD", "1").c_str())), "stream_download");
   check(lib.set_option(lib.ctx, "nranks", globals::nprocs), "nranks");
   check(lib.set_option(lib.ctx, "max_steps_per_launch", std::atoll(env_or("ARTISB200_MAXSTEPS", "-1").c_str())),
         "max_steps_per_launch");
@@ -563,6 +571,14 @@ void update_packets_gpu(const int nts, std::span<Packet> packets) {
   LibSink sink;
   emit_timestep_state(sink, nts);
   check(lib.begin_timestep(lib.ctx, nts), "begin_timestep");
+  if (lib.registered != packets.data()) {
+    // page-lock the packet array once (sn3d.cc keeps one std::vector<Packet> for the whole run): full-speed, asynchronous copies
+    if (lib.registered != nullptr) {
+      check(lib.unregister_host_buffer(lib.ctx, lib.registered), "unregister_host_buffer");
+    }
+    check(lib.register_host_buffer(lib.ctx, packets.data(), static_cast<int64_t>(packets.size_bytes())), "register_host_buffer");
+    lib.registered = packets.data();
+  }
   check(lib.update_packets_host(lib.ctx, nts, packets.data(), static_cast<int64_t>(packets.size()),
                                 static_cast<int>(sizeof(Packet))),
         "update_packets_host");
@@ -860,7 +876,20 @@ void emit_reference_cellcache(Sink& s) {
     std::vector<double> nnlevel;
     std::vector<std::uint64_t> keepbits;
     std::vector<double> chiff;
-    for (int cell = 0; cell < nc; cell++) {
+    // ARTISB200_DUMP_CELLS=<n>: only n evenly spaced cells (bench-scale fixtures: one cell's tables are megabytes)
+    const int ncells_wanted = std::atoi(env_or("ARTISB200_DUMP_CELLS", "0").c_str());
+    std::vector<int> cells;
+    if (ncells_wanted > 0 && ncells_wanted < nc) {
+      for (int k = 0; k < ncells_wanted; k++) {
+        cells.push_back(static_cast<int>((static_cast<long long>(k) * nc) / ncells_wanted) + (nc / (2 * ncells_wanted)));
+      }
+      s.arr("ref.cells", cells.data(), static_cast<int64_t>(cells.size()));
+    } else {
+      for (int cell = 0; cell < nc; cell++) {
+        cells.push_back(cell);
+      }
+    }
+    for (const int cell : cells) {
       const auto& slot = globals::cellcache.at(cell);
       pops.insert(pops.end(), slot.alllevels_pops.begin(), slot.alllevels_pops.end());
       marates.insert(marates.end(), slot.alllevels_maprocessrates.begin(), slot.alllevels_maprocessrates.end());

@@ -17,7 +17,7 @@ PRESET_OF = {"classic_toy": "classic", "classic_toy_1d": "classic", "classic3d_t
              "kilonova_guttman_toy": "kilonova_guttman", "kilonova_wollaeger_toy": "kilonova_wollaeger",
              "kilonova_barnes_toy": "kilonova_barnes", "classic_nt_toy": "classic_nt",
              "classic_ntexc_toy": "classic_ntexc", "classic_detailedbf_toy": "classic_detailedbf",
-             "nltephot_toy": "nltephotospheric"}
+             "nltephot_toy": "nltephotospheric", "kilonova_2d_kat": "kilonova_lte"}
 GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_toy": [0, 2], "kilonova_toy": [1, 4],
                     "classic_multibin_toy": [2, 4], "classic_nlte_toy": [2, 4],
                     "kilonova_guttman_toy": [1], "kilonova_wollaeger_toy": [1], "kilonova_barnes_toy": [1],

@@ -35,7 +35,11 @@ GOLDEN = {
     "kilonova_guttman_toy": [1],
     "kilonova_wollaeger_toy": [1],
     "kilonova_barnes_toy": [1],
+    # BASELINE configs[1] at full atomic-data and grid size, 2000 packets: bench-scale KATs, histories, sampled cell tables
+    "kilonova_2d_kat": [2],
 }
+# per config: extra environment of the oracle run
+EXTRA_ENV = {"kilonova_2d_kat": {"ARTISB200_DUMP_CELLS": "6"}}
 
 
 def main():
@@ -44,7 +48,8 @@ def main():
     for config, timesteps in GOLDEN.items():
         if only and config not in only:
             continue
-        rundir = run_oracle.run(config, "parity", "ref_perpacket", ",".join(str(t) for t in timesteps))
+        rundir = run_oracle.run(config, "parity", "ref_perpacket", ",".join(str(t) for t in timesteps),
+                                env_extra=EXTRA_ENV.get(config))
         dump = os.path.join(rundir, "dump")
         static = snap.read_snapshot(os.path.join(dump, "static.abt"))
         np.savez_compressed(os.path.join(here, f"{config}_static.npz"), **static)

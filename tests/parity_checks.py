@@ -76,6 +76,39 @@ def check_cell_tables(built, after):
     assert np.array_equal(built["built.cont_keepbits"], after["ref.cont_keepbits"]), "continuum keep-bitmaps differ"
 
 
+def assert_aggregates(config, est, after, est_err, est_tol):
+    """event counters, estimators, timestep scalars of a replayed timestep against the reference's"""
+    assert int(est["counters"][fixtures.INTERACTIONS]) == int(after["counters"][fixtures.INTERACTIONS])
+    # UPSCATTER / DOWNSCATTER classify a macro-atom emission by comparing the new comoving frequency with the one
+    # the packet had when it was absorbed (macroatom.cc:227-232). After a resonance scattering the two agree to
+    # the last bit or two, so the classification follows the rounding of the Doppler factor (device libm vs
+    # glibc); every other counter, and the sum of the two, must be equal.
+    UP, DOWN = 30, 31
+    mine, ref_c = est["counters"].copy(), after["counters"].copy()
+    assert int(mine[UP] + mine[DOWN]) == int(ref_c[UP] + ref_c[DOWN]), "up- plus down-scatterings differ from the reference"
+    mine[[UP, DOWN]] = 0
+    ref_c[[UP, DOWN]] = 0
+    assert np.array_equal(mine, ref_c), f"event counters differ from the reference: {np.nonzero(mine != ref_c)[0]}"
+    names = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.bfheating", "est.dep_gamma",
+             "est.dep_positron", "est.dep_electron", "est.dep_alpha"]
+    if "est.bfrate_raw" in after:  # DETAILED_BF_ESTIMATORS_ON fixtures
+        assert "est.bfrate_raw" in est and after["est.bfrate_raw"].sum() > 0
+        names += ["est.bfrate_raw"]
+    if fixtures.PRESET_OF[config] not in fixtures.PRESETS_WITHOUT_LUT_PHOTOION:
+        # (without the photoionisation LUT update_packets does not touch gammaestimator: the reference neither
+        # zeroes it, sn3d.cc:729-732, nor adds to it, rpkt.cc:526-530; update_grid.cc:398-409 parks other values there)
+        names += ["est.gamma"]
+    if "est.bins_J_raw" in after:  # MULTIBIN_RADFIELD_MODEL_ON fixtures
+        assert "est.bins_J_raw" in est and after["est.bins_J_raw"].sum() > 0
+        names += ["est.bins_J_raw", "est.bins_nuJ_raw"]
+    for name in names:
+        assert est_err.get(name, 0.0) <= est_tol, f"{name}: {est_err[name]:.3e}"
+    m = 9  # ts.scalars[9] (nt_energy_deposited) is file-static in the reference and not dumped
+    ts_err = _rel(est["ts.scalars"][:m], after["ts.scalars"][:m])
+    assert ts_err.max() <= est_tol, f"ts.scalars: {ts_err.max():.3e}"
+    assert int(est["ts.pellet_decays"][0]) == int(after["ts.pellet_decays"][0])
+
+
 def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction=1.0, tol=1e-9, est_tol=1e-9, options=None):
     """replay the timestep with every packet continuing its own reference RNG stream: histories must coincide"""
     fx = fixtures.load_golden(config, nts)
@@ -92,35 +125,7 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
     assert n_bad <= allowed, f"{n_bad} packets differ from the oracle ({n_fb_events} free-bound events) ({worst})"
     if min_exact_fraction == 1.0:
         check_cell_tables(built, after)
-        assert int(est["counters"][fixtures.INTERACTIONS]) == int(after["counters"][fixtures.INTERACTIONS])
-        # UPSCATTER / DOWNSCATTER classify a macro-atom emission by comparing the new comoving frequency with the one
-        # the packet had when it was absorbed (macroatom.cc:227-232). After a resonance scattering the two agree to
-        # the last bit or two, so the classification follows the rounding of the Doppler factor (device libm vs
-        # glibc); every other counter, and the sum of the two, must be equal.
-        UP, DOWN = 30, 31
-        mine, ref_c = est["counters"].copy(), after["counters"].copy()
-        assert int(mine[UP] + mine[DOWN]) == int(ref_c[UP] + ref_c[DOWN]), "up- plus down-scatterings differ from the reference"
-        mine[[UP, DOWN]] = 0
-        ref_c[[UP, DOWN]] = 0
-        assert np.array_equal(mine, ref_c), f"event counters differ from the reference: {np.nonzero(mine != ref_c)[0]}"
-        names = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.bfheating", "est.dep_gamma",
-                 "est.dep_positron", "est.dep_electron", "est.dep_alpha"]
-        if "est.bfrate_raw" in after:  # DETAILED_BF_ESTIMATORS_ON fixtures
-            assert "est.bfrate_raw" in est and after["est.bfrate_raw"].sum() > 0
-            names += ["est.bfrate_raw"]
-        if fixtures.PRESET_OF[config] not in fixtures.PRESETS_WITHOUT_LUT_PHOTOION:
-            # (without the photoionisation LUT update_packets does not touch gammaestimator: the reference neither
-            # zeroes it, sn3d.cc:729-732, nor adds to it, rpkt.cc:526-530; update_grid.cc:398-409 parks other values there)
-            names += ["est.gamma"]
-        if "est.bins_J_raw" in after:  # MULTIBIN_RADFIELD_MODEL_ON fixtures
-            assert "est.bins_J_raw" in est and after["est.bins_J_raw"].sum() > 0
-            names += ["est.bins_J_raw", "est.bins_nuJ_raw"]
-        for name in names:
-            assert est_err.get(name, 0.0) <= est_tol, f"{name}: {est_err[name]:.3e}"
-        m = 9  # ts.scalars[9] (nt_energy_deposited) is file-static in the reference and not dumped
-        ts_err = _rel(est["ts.scalars"][:m], after["ts.scalars"][:m])
-        assert ts_err.max() <= est_tol, f"ts.scalars: {ts_err.max():.3e}"
-        assert int(est["ts.pellet_decays"][0]) == int(after["ts.pellet_decays"][0])
+        assert_aggregates(config, est, after, est_err, est_tol)
     n_fb = n_fb_events
     return frac_ok, n_fb, est
 
@@ -147,3 +152,45 @@ def check_idempotence(libpath, config, nts, options=None):
             continue
         assert np.array_equal(value, est2[name], equal_nan=True), f"{name} changed in a second update_packets of the same timestep"
     return n
+
+
+def check_cell_tables_sampled(eng, static, after):
+    """the same comparison for a bench-scale fixture, where the reference dumped its cell cache for a few cells only
+    (after["ref.cells"]) and the device tables are read back cell by cell (artisb200_get_array_range)"""
+    cells = after["ref.cells"]
+    nlev = static["level.epsilon"].size
+    nbf = static["cont.nu_edge"].size
+    keepwords = (nbf + 63) // 64
+    per_cell = {"levelpops": nlev, "maprocessrates": nlev * 9, "matrans": after["ref.matrans"].size // cells.size,
+                "cooling_contrib": after["ref.cooling_contrib"].size // cells.size, "cont_nnlevel": nbf}
+    for k, cell in enumerate(cells):
+        for name, n in per_cell.items():
+            mine = eng.get_array_range("built." + name, int(cell) * n, n)
+            ref = after["ref." + name][k * n:(k + 1) * n]
+            err = _rel(mine, ref)
+            assert err.max() <= REL_TOL, f"built.{name} of cell {cell} differs from the reference cell cache by {err.max():.3e}"
+        bits = eng.get_array_range("built.cont_keepbits", int(cell) * keepwords, keepwords, dtype=np.uint64)
+        assert np.array_equal(bits, after["ref.cont_keepbits"][k * keepwords:(k + 1) * keepwords]), f"keep-bitmap of cell {cell} differs"
+        chiff = eng.get_array_range("built.chi_ff_nnionpart", int(cell), 1)
+        assert _rel(chiff, after["ref.chi_ff_nnionpart"][k:k + 1]).max() <= REL_TOL
+    return cells.size
+
+
+def check_bench_scale_histories(libpath, config, nts, options=None, tol=1e-9, est_tol=1e-9):
+    """a fixture at the bench model's full atomic-data and grid size (few packets): sampled cell tables, every packet
+    history, counters and estimators against the reference"""
+    fx = fixtures.load_golden(config, nts)
+    after, before = fx["after"], fx["before"]
+    eng = fixtures.make_engine(libpath, fx, rng="xoshiro", options=options)
+    n = int(before["packets.count"][0])
+    stride = int(before["packets.stride"][0])
+    aos = before["packets.aos"].copy()
+    eng.update_packets_host(nts, aos, n, stride)
+    est = eng.estimators()
+    ncells = check_cell_tables_sampled(eng, fx["static"], after)
+    eng.close()
+    pk = aos.view(fixtures.snap.packet_dtype(stride))
+    frac_ok, worst, est_err = compare_run.compare(pk, est, after, tol=tol, verbose=False)
+    assert frac_ok == 1.0, f"{int(round((1 - frac_ok) * n))} of {n} packets differ from the oracle ({worst})"
+    assert_aggregates(config, est, after, est_err, est_tol)
+    return n, ncells

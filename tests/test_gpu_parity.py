@@ -64,6 +64,22 @@ def test_schedules_give_identical_packets():
         assert np.array_equal(counters, first[1]), name
 
 
+@pytest.mark.parametrize("schedule", ["wavefront", "wavefront-notail", "wavefront-refill", "history"])
+def test_streamed_download_returns_the_same_packets(schedule):
+    """option stream_download: finished packets are copied back while the others are still being propagated, and the array
+    comes back in completion order; sorted by packet number it must be byte for byte what the ordered download returns"""
+    fx = fixtures.load_golden("kilonova_toy", 4)
+    ordered, est_o, _, _ = fixtures.run_fixture(_lib("kilonova_toy"), fx, rng="philox", seed=11, options=SCHEDULES[schedule])
+    opts = dict(SCHEDULES[schedule], stream_download=1)
+    streamed, est_s, _, _ = fixtures.run_fixture(_lib("kilonova_toy"), fx, rng="philox", seed=11, options=opts)
+    assert not np.array_equal(streamed["number"], ordered["number"]), "the streamed array is expected to be permuted"
+    a = ordered[np.argsort(ordered["number"], kind="stable")]
+    b = streamed[np.argsort(streamed["number"], kind="stable")]
+    for name in a.dtype.names:  # every field of the reference's Packet, bit for bit (NaN == NaN)
+        assert np.array_equal(np.ascontiguousarray(a[name]).view(np.uint8), np.ascontiguousarray(b[name]).view(np.uint8)), name
+    assert np.array_equal(est_o["counters"], est_s["counters"])
+
+
 @pytest.mark.parametrize("stride", [240, 256])
 def test_packet_roundtrip_is_identity(stride):
     fx = fixtures.load_golden("classic_toy", 3)

@@ -92,3 +92,25 @@ def test_macroatom_searches_equal_upper_bound(tmp_path):
 def test_update_packets_is_idempotent_within_a_timestep(config, nts, schedule):
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
     assert parity_checks.check_idempotence(lib, config, nts, options=SCHEDULES[schedule]) > 0
+
+
+def test_stream_download_option_is_accepted_by_a_backend_without_streams():
+    # the host test build has no copy stream: the option falls back to the ordered download (same packets)
+    lib = fixtures.hostsim_library("kilonova_lte")
+    fx = fixtures.load_golden("kilonova_toy", 4)
+    ordered, _, _, _ = fixtures.run_fixture(lib, fx, rng="philox", seed=11)
+    streamed, _, _, _ = fixtures.run_fixture(lib, fx, rng="philox", seed=11, options={"stream_download": 1})
+    assert ordered.tobytes() == streamed.tobytes()
+
+
+# BASELINE configs[1] at its full atomic-data and grid size (54 892 lines, 1 475 continua, 3 684 cells), 2000 packets of
+# the reference's parity build (tests/golden/kilonova_2d_kat_*): the same checks the B200 runs in test_gpu_bench_scale.py
+def test_bench_scale_known_answer_vectors():
+    lib = fixtures.hostsim_library("kilonova_lte")
+    assert parity_checks.check_deterministic_kernels(lib, "kilonova_2d_kat", 2, ks_draws=100) > 1000
+
+
+def test_bench_scale_histories_and_sampled_tables():
+    lib = fixtures.hostsim_library("kilonova_lte")
+    n, ncells = parity_checks.check_bench_scale_histories(lib, "kilonova_2d_kat", 2, options=SCHEDULES["wavefront-resort"])
+    assert n == 2000 and ncells == 6

@@ -171,6 +171,10 @@ CONFIGS = {
     # the bounded CPU sample of configs[1] timed by bench.py's cpu_baseline / reference arm
     "kilonova_2d_cpu": dict(preset="kilonova_lte", opts=_opts(100000, None, None, _KN_LUT), atomic=_KN2D_ATOMIC, model=_KN2D_MODEL,
                       run=_KN2D_RUN),
+    # configs[1] at full atomic-data and grid size with few packets: bench-scale known-answer vectors (54 892 lines, 1 475
+    # continua, 3 684 cells) and packet histories from the reference's parity build (tests/golden/kilonova_2d_kat_*)
+    "kilonova_2d_kat": dict(preset="kilonova_lte", opts=_opts(2000, None, None, _KN_LUT), atomic=_KN2D_ATOMIC, model=_KN2D_MODEL,
+                      run=_KN2D_RUN),
     # few-packet probe of configs[1] used while tuning the synthetic atomic data (interactions per packet per timestep)
     "kilonova_2d_probe": dict(preset="kilonova_lte", opts=_opts(2000, None, None, _KN_LUT), atomic=_KN2D_ATOMIC, model=_KN2D_MODEL,
                       run=_KN2D_RUN),

@@ -31,6 +31,16 @@ for step in $STEPS; do
         name="${TAG}_tune${suf}_$(echo "$opts" | tr ',=' '__')"
         ARTISB200_LIB_SUFFIX="$suf" ARTISB200_OPTS="$opts" timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${name}.json 2> gpurun_out/${name}.err; echo "tune [$suf] [$opts] rc=$?"
       done ;;
+    dram)
+      # DRAM bytes of every launch of ONE full-size step (three metrics = one replay pass per launch)
+      timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/${TAG}_dram.csv python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_dram.err; echo "dram rc=$?"
+      python tools/ncu_dram_traffic.py gpurun_out/${TAG}_dram.csv gpurun_out/${TAG}_dram_traffic.json | tee gpurun_out/${TAG}_dram_summary.txt ;;
+    thinfull)
+      # full ncu capture of two launches of the detailed r-packet stage kernel of a 2e6-packet step
+      ARTISB200_BENCH_NPACKETS=2000000 timeout 1500 ncu --set full --clock-control none --import-source on \
+        --kernel-name-base demangled -k 'regex:k_wf_stage<\(int\)1>' --launch-skip 2 --launch-count 2 -o gpurun_out/${TAG}_thinfull -f \
+        python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_thinfull.err; echo "thinfull rc=$?" ;;
     launches)
       ARTISB200_BENCH_NPACKETS=2000000 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv -c 600 \
         --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu.json 2> gpurun_out/${TAG}_launches.err; echo "launches rc=$?" ;;
