@@ -113,6 +113,40 @@ AHD double sample_planck_montecarlo(const double T, Rng& rng) {
   }
 }
 
+// ---- expansion-opacity wavelength grid (rpkt.h:23-44): bins of 20 Angstrom from 60 to 40000 Angstrom, ordered by
+// ascending wavelength = descending frequency
+// (the grid constants are in tables.h)
+
+AHD double expopac_bin_nu_upper(const int binindex) {
+  const double lambda_lower = expopac_lambdamin + (static_cast<double>(binindex) * expopac_deltalambda);
+  return 1e8 * CLIGHT / lambda_lower;
+}
+
+AHD double expopac_bin_nu_lower(const int binindex) {
+  const double lambda_upper = expopac_lambdamin + (static_cast<double>(binindex + 1) * expopac_deltalambda);
+  return 1e8 * CLIGHT / lambda_upper;
+}
+
+// sn3d.h:115-122: floor((value - minvalue) / binwidth) as an integer (negative below the grid)
+AHD long long linearbinindex(const double value, const double minvalue, const double binwidth) {
+  const double fracindex = (value - minvalue) / binwidth;
+  const auto truncated = static_cast<long long>(fracindex);
+  return (fracindex < static_cast<double>(truncated)) ? truncated - 1 : truncated;
+}
+
+// rpkt.cc:964-981: a frequency distributed as the Planck function times the expansion opacity of the cell (the
+// cumulative table is per-timestep cell state computed by calculate_expansion_opacities, rpkt.cc:1071-1123). Two draws.
+AHD double sample_planck_times_expansion_opacity(const Tables& T, const int cell, Rng& rng) {
+  const double* kappa_planck_bins = T.expopac_planck_cumulative + (static_cast<long long>(cell) * expopac_nbins);
+  const double rnd_integral = rng.uniform() * kappa_planck_bins[expopac_nbins - 1];
+  int binindex = upper_bound_idx(kappa_planck_bins, expopac_nbins, rnd_integral);  // sn3d.h:85-92 index_upperbound
+  binindex = (binindex < expopac_nbins - 1) ? binindex : expopac_nbins - 1;
+  const double bin_nu_lower = expopac_bin_nu_lower(binindex);
+  const double delta_nu = expopac_bin_nu_upper(binindex) - bin_nu_lower;
+  const double nuoffset = rng.uniform() * delta_nu;
+  return bin_nu_lower + nuoffset;
+}
+
 // energy-weighted free-bound emissivity integrand (ratecoeff.cc:84-90)
 AHD double alpha_sp_E_integrand(const Tables& T, const double nu_minus_nu_edge, const double nu_edge, const float T_e,
                                 const float* photoion_xs) {

@@ -662,6 +662,7 @@ class Engine {
     bool ok = true;
     ok = ok && alloc_output("ts.pellet_decays", 'q', 1, &T.ts_pellet_decays);
     ok = ok && alloc_output("counters", 'q', CNT_COUNT, &T.counters);
+    ok = ok && alloc_output("dev_error", 'q', NDEVERROR, &T.dev_error);
     ok = ok && alloc_output("diag", 'q', NDIAG, &T.diag);
     // the same work counters per kernel family: rows ST_OTHER, ST_RTHIN, ST_RTHICK, ST_MA, and the whole-history kernel
     ok = ok && alloc_output("diag_stage", 'q', (NSTAGES + 1) * NDIAG, &T.diag_stage);
@@ -715,6 +716,17 @@ class Engine {
                     "(USE_LUT_PHOTOION = false: evaluated by the host)");
       }
     }
+    if constexpr (opt::RPKT_USE_EXPANSION_OPACITIES) {
+      if (count_of("cell.expansionopacities") != static_cast<int64_t>(T.ncells) * expopac_nbins) {
+        return fail("begin_timestep: cell.expansionopacities must hold ncells x 1997 wavelength bins (RPKT_USE_EXPANSION_OPACITIES)");
+      }
+    }
+    if constexpr (opt::HAS_BB_THERMALISATION_PROBABILITY) {
+      if (count_of("cell.expopac_planck_cumulative") != static_cast<int64_t>(T.ncells) * expopac_nbins) {
+        return fail("begin_timestep: cell.expopac_planck_cumulative must hold ncells x 1997 wavelength bins "
+                    "(RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY)");
+      }
+    }
     if constexpr (opt::NT_EXCITATION_ON) {
       const int64_t want = static_cast<int64_t>(T.ncells) * T.nt_excitations_stored;
       if (count_of("cell.nt_exc_count") != T.ncells || count_of("cell.nt_exc_alltransindex") != want ||
@@ -759,6 +771,7 @@ class Engine {
     be.zero(T.ts_pellet_decays, 8);
     be.zero(T.counters, CNT_COUNT * 8);
     be.zero(T.diag, NDIAG * 8);
+    be.zero(T.dev_error, NDEVERROR * 8);
     be.zero(T.diag_stage, (NSTAGES + 1) * NDIAG * 8);
     if (!be.build_cell_tables(T)) {
       return fail("begin_timestep: building the per-cell tables failed: " + be.last_error());
@@ -905,6 +918,22 @@ class Engine {
                    static_cast<unsigned int>(T.seed >> 32U), static_cast<unsigned int>(rank)};
     if (!be.propagate(T, npackets, popt, &last)) {
       return fail("update_packets: propagation failed: " + be.last_error());
+    }
+    // the device-side stand-in for assert_always: the first failed assertion of the timestep fails the call
+    long long dev_error[NDEVERROR] = {0, 0, 0, 0};
+    if (!be.d2h(dev_error, T.dev_error, NDEVERROR * 8)) {
+      return fail("update_packets: reading the device error record failed: " + be.last_error());
+    }
+    if (dev_error[0] != 0) {
+      static const char* what[] = {"", "macro-atom radiative recombination found no lower level (macroatom.cc:290)",
+                                   "macro-atom internal transition to the lower ion found no level (macroatom.cc:502)",
+                                   "macro-atom ionisation found no target (macroatom.cc:320)",
+                                   "continuum event beyond the sum of the opacities (rpkt.cc:452)",
+                                   "pellet in an impossible state (update_packets.cc:251)", "unknown packet type (update_packets.cc:312)"};
+      const long long code = dev_error[0];
+      return fail("update_packets: device assertion failed: " + std::string((code > 0 && code <= 6) ? what[code] : "unknown code") +
+                  "; packet index " + std::to_string(dev_error[1]) + ", detail " + std::to_string(dev_error[2]) + ", " +
+                  std::to_string(dev_error[3]) + " failure(s) in this timestep");
     }
     return 0;
   }

@@ -27,7 +27,11 @@ AHD void mark_thermal_emission(Pkt& p, const Ctx& c, const int emissiontype) {
 AHD void do_kpkt_blackbody(Pkt& p, const Ctx& c) {
   const Tables& T = c.T;
   const int cell = T.propcell_nonemptymgi[p.cellindex];
-  p.nu_cmf = sample_planck_montecarlo(T.Te[cell], p.rng);
+  if (opt::HAS_BB_THERMALISATION_PROBABILITY && T.thick[cell] != CELL_THICK) {  // kpkt.cc:402-404
+    p.nu_cmf = sample_planck_times_expansion_opacity(T, cell, p.rng);
+  } else {
+    p.nu_cmf = sample_planck_montecarlo(T.Te[cell], p.rng);
+  }
   emit_rpkt(p, c);
   c.count<CNT_K_STAT_TO_R_BB>();
   c.count<CNT_INTERACTIONS>();

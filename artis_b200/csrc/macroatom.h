@@ -179,8 +179,9 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
           }
         }
         if (lowerionlevel < 0) {
-          // cannot happen for consistent tables (reference: assert_always). Deactivate to the last possible
-          // continuum rather than looping forever.
+          // cannot happen for consistent tables (reference: assert_always): reported through the device error record;
+          // deactivate to the last possible continuum rather than looping forever
+          c.fail(DEVERR_MA_RADRECOMB_NO_LEVEL, ulev);
           for (int tmp = nlevels - 1; tmp >= 0 && lowerionlevel < 0; tmp--) {
             const int phixstargetindex = find_phixstargetindex(T, lowerionstart + tmp, level);
             if (phixstargetindex >= 0) {
@@ -237,7 +238,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
           }
         }
         if (lower < 0) {
-          lower = 0;  // reference: assert_always(lower >= 0)
+          c.fail(DEVERR_MA_DOWNLOWER_NO_LEVEL, ulev);  // reference: assert_always(lower >= 0)
+          lower = 0;
         }
         ion--;
         level = lower;
@@ -270,7 +272,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
           }
         }
         if (newlevel < 0) {
-          newlevel = phixsupperlevel(T, ulev, nphixstargets - 1);  // reference: assert_always(false)
+          c.fail(DEVERR_MA_IONISATION_NO_TARGET, ulev);  // reference: assert_always(false)
+          newlevel = phixsupperlevel(T, ulev, nphixstargets - 1);
         }
         level = newlevel;
         ion += 1;

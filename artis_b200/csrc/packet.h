@@ -115,6 +115,23 @@ struct Ctx {
 #endif
   }
   AHD void pellet_decay() const { bump(pellet_decays, 1U); }
+  // record a failed device-side assertion (tables.h DEVERR_*); the first one of the timestep keeps its details
+  AHD void fail(const int code, const long long detail) const {
+#if defined(__CUDA_ARCH__)
+    if (atomicCAS(reinterpret_cast<unsigned long long*>(&T.dev_error[0]), 0ULL, static_cast<unsigned long long>(code)) == 0ULL) {
+      T.dev_error[1] = ip;
+      T.dev_error[2] = detail;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&T.dev_error[3]), 1ULL);
+#else
+    if (T.dev_error[0] == 0) {
+      T.dev_error[0] = code;
+      T.dev_error[1] = ip;
+      T.dev_error[2] = detail;
+    }
+    T.dev_error[3] += 1;
+#endif
+  }
   AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(i * T.scratch_stride) + ip]; }
   AHD double* bfestim_contr(const int i) const { return &T.scratch_bfcontr[(i * T.scratch_stride) + ip]; }
 

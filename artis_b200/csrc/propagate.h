@@ -66,7 +66,8 @@ AHD void update_pellet(Pkt& p, const Ctx& c, const double t2) {
     c.count<CNT_K_STAT_FROM_EARLIERDECAY>();
     p.prop_time = T.tmin;
   } else {
-    // unreachable for valid input (reference: __builtin_unreachable); park the packet so the loop terminates
+    // unreachable for valid input (reference: __builtin_unreachable): reported; park the packet so the loop terminates
+    c.fail(DEVERR_PELLET_STATE, T.nts);
     p.prop_time = t2;
   }
 }
@@ -265,7 +266,8 @@ AHD void do_packet(Pkt& p, const Ctx& c, const double t2, ChiCont& chi) {
       break;
     }
     default:
-      // unknown type: cannot happen for packets produced by this library or the reference; make it inert
+      // unknown type: cannot happen for packets produced by this library or the reference: reported; make it inert
+      c.fail(DEVERR_UNKNOWN_PACKET_TYPE, p.type);
       p.prop_time = t2;
       break;
   }

@@ -333,6 +333,78 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
   }
 }
 
+// rpkt.cc:221-320: the bound-bound opacity as an expansion opacity per wavelength bin instead of line by line. Walks the
+// bins red-ward; inside the bin where the event falls it either decides thermalisation/scattering against the bin's
+// opacity (bound-bound thermalisation probability set) or re-traces that bin line by line.
+struct ExpOpacEvent {
+  double edist;
+  bool is_boundbound;
+};
+
+AHD ExpOpacEvent get_possible_event_expansion_opacity(const Ctx& c, const int cell, Pkt& p, const ChiCont& chi,
+                                                      MacroAtomState& mastate, const double tau_rnd, const double nu_cmf_abort,
+                                                      const double dnu_on_dl, const double doppler) {
+  const Tables& T = c.T;
+  double pos[3] = {p.pos[0], p.pos[1], p.pos[2]};
+  double nu_cmf = p.nu_cmf;
+  double e_cmf = p.e_cmf;
+  double prop_time = p.prop_time;
+  double dist = 0.;
+  double tau = 0.;
+  // -1 means below the wavelength grid: continuum opacity only
+  long long binindex_start = linearbinindex(1e8 * CLIGHT / nu_cmf, expopac_lambdamin, expopac_deltalambda);
+  binindex_start = (binindex_start < -1) ? -1 : binindex_start;
+  for (long long binindex = binindex_start; binindex < expopac_nbins; binindex++) {
+    const double next_bin_edge_nu = (binindex < 0) ? expopac_bin_nu_upper(0) : expopac_bin_nu_lower(static_cast<int>(binindex));
+    const double binedgedist = get_linedistance(prop_time, nu_cmf, next_bin_edge_nu, dnu_on_dl);
+    const double chi_cont = chi.total() * doppler;
+    double chi_bb_expansionopac = 0.;
+    if (binindex >= 0) {
+      const auto kappa = T.expansionopacities[(static_cast<long long>(cell) * expopac_nbins) + binindex];  // [cm^2/g]
+      chi_bb_expansionopac = kappa * T.rho[cell];
+    }
+    const double chi_tot = chi_cont + chi_bb_expansionopac;
+    if (chi_tot * binedgedist > tau_rnd - tau) {
+      if constexpr (opt::HAS_BB_THERMALISATION_PROBABILITY) {
+        const double edist = dmax(dist + ((tau_rnd - tau) / chi_tot), 0.);
+        const bool event_is_boundbound = p.rng.uniform() < chi_bb_expansionopac / chi_tot;
+        return {edist, event_is_boundbound};
+      }
+      // re-trace this bin line by line (rpkt.cc:267-285); the expansion opacity was calculated at t_mid
+      Pkt bin_start = p;
+      bin_start.pos[0] = pos[0];
+      bin_start.pos[1] = pos[1];
+      bin_start.pos[2] = pos[2];
+      bin_start.nu_cmf = nu_cmf;
+      bin_start.e_cmf = e_cmf;
+      bin_start.prop_time = T.ts_mid[T.globals_timestep];
+      bin_start.next_trans = -1;
+      const PossibleEvent ev = get_possible_event(c, cell, bin_start, chi, mastate, tau_rnd - tau, DBL_MAX_, 0., dnu_on_dl, doppler);
+      return {dist + ev.edist, ev.is_boundbound};
+    }
+    tau += chi_tot * binedgedist;
+    dist += binedgedist;
+    if constexpr (!opt::USE_RELATIVISTIC_DOPPLER_SHIFT) {
+      move_withtime(pos, p.dir, prop_time, p.nu_rf, nu_cmf, p.e_rf, e_cmf, binedgedist);
+    } else {
+      pos[0] += (p.dir[0] * binedgedist);
+      pos[1] += (p.dir[1] * binedgedist);
+      pos[2] += (p.dir[2] * binedgedist);
+      prop_time += binedgedist / CLIGHT_PROP;
+      nu_cmf = p.nu_cmf + (dnu_on_dl * dist);
+    }
+    if (nu_cmf <= nu_cmf_abort) {
+      return {DBL_MAX_, false};  // edge of the cell or end of the timestep
+    }
+  }
+  // red-ward of the wavelength grid the continuum processes still provide opacity (rpkt.cc:313-319)
+  const double chi_cont = chi.total() * doppler;
+  if (chi_cont > 0.) {
+    return {dist + ((tau_rnd - tau) / chi_cont), false};
+  }
+  return {DBL_MAX_, false};
+}
+
 // radfield.cc:745-771 + rpkt.cc:502-538
 AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf, const double distance, const int cell,
                            const ChiCont& chi, const bool thickcell) {
@@ -417,8 +489,11 @@ AHD void rpkt_event_continuum(Pkt& p, const Ctx& c, const ChiCont& chi) {
     p.type = TYPE_KPKT;
     T.pkt.absorptiontype[c.ip] = ABSTYPE_FREEFREE;
   } else {
-    // reference asserts chi_rnd < chi_escatter + chi_ff + chi_bf; within rounding it always is
-    (void)chi_bf;
+    // rpkt.cc:452 assert_always(chi_rnd < chi_escatter + chi_ff + chi_bf): chi_rnd < chi_cont, and the two sums
+    // are the same three terms added in a different order - a failure beyond rounding goes to the device error record
+    if (!(chi_rnd < (chi_escatter + chi_ff + chi_bf) * (1. + 1e-12))) {
+      c.fail(DEVERR_RPKT_CONTINUUM_BEYOND_SUM, chi.nonemptymgi);
+    }
     T.pkt.absorptiontype[c.ip] = ABSTYPE_BOUNDFREE;
     const double chi_bf_rand = p.rng.uniform() * chi.chi_boundfree;
     const int allcontindex = static_cast<int>(calculate_chi_bf_gammacontr<true>(c, chi.nonemptymgi, chi.nu, chi_bf_rand));
@@ -483,7 +558,7 @@ template <int CELLKIND>
 AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const RStepPre& pre) {
   const Tables& T = c.T;
   const int cell = pre.cell;
-  MacroAtomState pktmastate = {-1, -1, -1, -99};
+  MacroAtomState pktmastate = {-1, -1, -1, -99};  // the default member initialisers of packet.h:96-104 (rpkt.cc:545)
   const double tau_rnd = pre.tau_rnd;
   const double boundarydist = pre.boundarydist;
   const int next_cellindex = pre.next_cellindex;
@@ -507,11 +582,18 @@ AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const
     const double nu_cmf_abort = get_nu_cmf_abort(p.pos, p.dir, p.prop_time, p.nu_rf, abort_dist);
     const double dnu_on_dl = (nu_cmf_abort - p.nu_cmf) / abort_dist;
     const double doppler = doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
-    const PossibleEvent ev =
-        get_possible_event(c, cell, p, chi, pktmastate, tau_rnd, abort_dist, nu_cmf_abort, dnu_on_dl, doppler);
-    edist = ev.edist;
-    p.next_trans = ev.next_trans;
-    event_is_boundbound = ev.is_boundbound;
+    if constexpr (opt::RPKT_USE_EXPANSION_OPACITIES) {
+      const ExpOpacEvent ev =
+          get_possible_event_expansion_opacity(c, cell, p, chi, pktmastate, tau_rnd, nu_cmf_abort, dnu_on_dl, doppler);
+      edist = ev.edist;
+      event_is_boundbound = ev.is_boundbound;
+    } else {
+      const PossibleEvent ev =
+          get_possible_event(c, cell, p, chi, pktmastate, tau_rnd, abort_dist, nu_cmf_abort, dnu_on_dl, doppler);
+      edist = ev.edist;
+      p.next_trans = ev.next_trans;
+      event_is_boundbound = ev.is_boundbound;
+    }
   }
 
   // Which of the three outcomes (rpkt.cc:604-690): 0 = event, 1 = cell boundary, 2 = end of the timestep. All three
@@ -533,11 +615,28 @@ AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const
       emit_rpkt(p, c);
     } else if (!event_is_boundbound) {
       rpkt_event_continuum(p, c, chi);
-    } else {
+    } else if constexpr (!opt::HAS_BB_THERMALISATION_PROBABILITY) {
       c.count<CNT_MA_STAT_ACTIVATION_BB>();
       T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
       T.pkt.absorptionfreq[c.ip] = p.nu_rf;
       activate_macroatom(p, pktmastate);
+    } else {
+      // rpkt.cc:628-651: thermal redistribution of the frequency with the given probability, else a pure scattering
+      if (opt::BB_THERMALISATION_PROBABILITY >= 1.F || p.rng.uniform() < opt::BB_THERMALISATION_PROBABILITY) {
+        T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
+        T.pkt.absorptionfreq[c.ip] = p.nu_rf;
+        p.nu_cmf = sample_planck_times_expansion_opacity(T, cell, p.rng);
+        p.next_trans = -1;
+        T.pkt.em[c.ip].type = EMTYPE_NOTSET;
+        T.pkt.trueem[c.ip].type = EMTYPE_NOTSET;
+        set_trueem_pos_nan(c);
+        T.pkt.trueem[c.ip].time = -1.F;
+        p.nscatterings = 0;
+      } else {
+        p.nscatterings++;
+        c.count<CNT_ELECTRON_SCATTERINGS>();
+      }
+      emit_rpkt(p, c);
     }
     return (p.type == TYPE_RPKT);
   }

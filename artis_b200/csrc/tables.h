@@ -113,6 +113,8 @@ namespace ab {
   X(double, nt_exc_ratecoeffperdeposition, "cell.nt_exc_ratecoeffperdeposition") \
   X(double, nt_deposition_rate_density, "cell.nt_deposition_rate_density") \
   X(float, nt_frac_excitation, "cell.nt_frac_excitation")           \
+  X(float, expansionopacities, "cell.expansionopacities")           \
+  X(double, expopac_planck_cumulative, "cell.expopac_planck_cumulative") \
   X(float, radfield_bin_W, "radfield.bin_W")                        \
   X(float, radfield_bin_T_R, "radfield.bin_T_R")
 
@@ -153,6 +155,7 @@ namespace ab {
   X(long long, counters, "counters")              \
   X(long long, diag, "diag")                      \
   X(long long, diag_stage, "diag_stage")          \
+  X(long long, dev_error, "dev_error")            \
   X(double, cell_levelpops, "built.levelpops")    \
   X(double, cell_maprocessrates, "built.maprocessrates") \
   X(double, cell_matrans, "built.matrans")        \
@@ -163,6 +166,27 @@ namespace ab {
   X(double, cell_cont_edgepart, "built.cont_edgepart") \
   X(double, cell_chi_ff_nnionpart, "built.chi_ff_nnionpart") \
   X(double, cell_corrphotoioncoeff, "built.corrphotoioncoeff")
+
+// Device-side failure record standing in for the reference's assert_always (mpi_logging.h:123-130: log, then abort):
+// dev_error[0] = code of the FIRST failed assertion of the timestep (0 = none), [1] = packet index, [2] = detail,
+// [3] = number of failures. The kernels carry on with a defined fallback so that they terminate; the host checks the
+// record after the propagation and fails the call, and the binding logs and aborts like the reference.
+enum : int {
+  DEVERR_NONE = 0,
+  DEVERR_MA_RADRECOMB_NO_LEVEL = 1,      // macroatom.cc:290 assert_always(lowerionlevel >= 0)
+  DEVERR_MA_DOWNLOWER_NO_LEVEL = 2,      // macroatom.cc:502 assert_always(lower >= 0)
+  DEVERR_MA_IONISATION_NO_TARGET = 3,    // macroatom.cc:320 assert_always(false)
+  DEVERR_RPKT_CONTINUUM_BEYOND_SUM = 4,  // rpkt.cc:452 assert_always(chi_rnd < chi_escatter + chi_ff + chi_bf)
+  DEVERR_PELLET_STATE = 5,               // update_packets.cc:251 unreachable pellet state
+  DEVERR_UNKNOWN_PACKET_TYPE = 6,        // update_packets.cc:312 default of do_packet's switch
+};
+constexpr int NDEVERROR = 4;
+
+// expansion-opacity wavelength grid (reference rpkt.h:23-26)
+constexpr double expopac_lambdamin = 60.;
+constexpr double expopac_lambdamax = 40000.;
+constexpr double expopac_deltalambda = 20.;
+constexpr int expopac_nbins = static_cast<int>((expopac_lambdamax - expopac_lambdamin) / expopac_deltalambda);
 
 constexpr int NTSSCALARS = 10;  // ARTISB200_NTSSCALARS
 constexpr int NDIAG = 16;       // ARTISB200_NDIAG

@@ -58,7 +58,7 @@ EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 ESTIMATOR_NAMES = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
                    "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "ts.pellet_decays", "counters", "diag"]
 OPTIONAL_ESTIMATOR_NAMES = ["est.bins_J_raw", "est.bins_nuJ_raw", "est.bfrate_raw"]  # MULTIBIN / DETAILED_BF presets only
-_OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "diag_stage": np.int64, "built.cont_keepbits": np.uint64}
+_OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "diag_stage": np.int64, "dev_error": np.int64, "built.cont_keepbits": np.uint64}
 
 
 def load_library(path):

@@ -62,6 +62,11 @@
  *       (USE_LUT_PHOTOION == false only): the corrected photoionisation coefficient of every continuum in the cell's
  *       radiation field, ratecoeff.cc:840 get_corrphotoioncoeff (the integral the reference keeps in its cell cache),
  *       evaluated by the host for the timestep (integration/update_packets_b200.cc)
+ *   cell.expansionopacities 'f'[Nc*1997]  (RPKT_USE_EXPANSION_OPACITIES only) rpkt.h:47: bound-bound opacity [cm^2/g] per
+ *       20-Angstrom wavelength bin from 60 to 40000 Angstrom (rpkt.h:23-44), written by calculate_expansion_opacities
+ *       (rpkt.cc:1071-1123) in update_grid; read by get_possible_event_expansion_opacity (rpkt.cc:221-320)
+ *   cell.expopac_planck_cumulative 'd'[Nc*1997]  (RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY set only) rpkt.cc:48: cumulative
+ *       Planck-weighted opacity over the same bins, sampled by sample_planck_times_expansion_opacity (rpkt.cc:964-981)
  *  estimators (read back with artisb200_get_array after artisb200_update_packets*)
  *   est.J/nuJ 'd'[Nc] radfield.cc:106-111   est.ffheating/colheating 'd'[Nc] globals.h:131-132
  *   est.gamma/bfheating 'd'[Nc*Ng] globals.h:126-129   est.dep_gamma/dep_positron/dep_electron/dep_alpha 'd'[Nc] globals.h:118-121
@@ -69,6 +74,13 @@
  *   est.bfrate_raw 'd'[Nc*bfestimcount]  (DETAILED_BF_ESTIMATORS_ON only) radfield.cc:96, accumulated by update_bfestimators 215-250
  *   ts.scalars 'd'[ARTISB200_NTSSCALARS] (order below; globals.h:73-113 and nonthermal.cc:200)   ts.pellet_decays 'q'
  *   counters 'q'[34]  (stats.h:14-50; INTERACTIONS is index 26)      diag 'q'[ARTISB200_NDIAG]
+ *   diag_stage 'q'[5*ARTISB200_NDIAG]: the work counters per kernel family (other, r-packet detailed, r-packet grey,
+ *     macro-atom, whole-history kernel)
+ *   dev_error 'q'[4]: device-side stand-in for the reference's assert_always (mpi_logging.h:123-130): code of the first
+ *     assertion that failed in the timestep (0 = none; 1-3 macro-atom selections without a target, macroatom.cc:290/502/320;
+ *     4 continuum event beyond the opacity sum, rpkt.cc:452; 5 impossible pellet state, update_packets.cc:251; 6 unknown
+ *     packet type, update_packets.cc:312), packet index, detail, number of failures. artisb200_update_packets[_host] returns
+ *     nonzero when it is set, and the binding logs and aborts like the reference.
  */
 #ifndef ARTIS_B200_H
 #define ARTIS_B200_H

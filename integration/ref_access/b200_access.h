@@ -19,6 +19,8 @@ auto b200_lut_corrphotoioncoeffs() -> std::span<const double>;
 auto b200_lut_bfcooling_coeffs() -> std::span<const double>;
 auto b200_lut_temperature_grid() -> std::span<const double>;
 
+auto b200_expansionopacity_planck_cumulative() -> std::span<const double>;
+
 namespace kpkt {
 auto b200_coolinglist_type(int i) -> int;
 auto b200_coolinglist_level(int i) -> int;

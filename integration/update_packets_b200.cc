@@ -340,6 +340,15 @@ void emit_timestep_state(Sink& s, const int nts) {
       s.arr("cell.nt_frac_excitation", fracexc.data(), static_cast<int64_t>(fracexc.size()));
     }
   }
+  if constexpr (RPKT_USE_EXPANSION_OPACITIES) {
+    // binned expansion opacities [cm^2/g] of this timestep (rpkt.h:47, written by calculate_expansion_opacities,
+    // rpkt.cc:1071-1123, from update_grid): per-timestep cell state like the temperatures
+    s.arr("cell.expansionopacities", expansionopacities.data(), static_cast<int64_t>(expansionopacities.size()));
+  }
+  if constexpr (RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY.has_value()) {
+    const auto cumulative = b200_expansionopacity_planck_cumulative();  // rpkt.cc:48 (ref_access/ref_rpkt.cc)
+    s.arr("cell.expopac_planck_cumulative", cumulative.data(), static_cast<int64_t>(cumulative.size()));
+  }
   if (globals::total_nlte_levels > 0) {
     // NLTE solver populations over rho, one slot per NLTE level and superlevel (nltepop.h:15, nltepop.cc:1955-1968)
     s.arr("cell.nltepops", nltepops_allcells.data(), static_cast<int64_t>(nltepops_allcells.size()));

@@ -68,6 +68,34 @@ def check_abi_errors(libpath):
     eng.close()
 
 
+def check_device_error_record(libpath):
+    """the device-side stand-in for the reference's assert_always: a packet of a type no code path knows
+    (update_packets.cc:312) is reported by update_packets with the failed assertion and the packet index, instead of
+    being coerced silently"""
+    fx = fixtures.load_golden("kilonova_toy", 4)
+    before = fx["before"]
+    n = int(before["packets.count"][0])
+    stride = int(before["packets.stride"][0])
+    for options in ({"schedule": 0}, {"schedule": 1, "wf_tail": 0}):
+        eng = fixtures.make_engine(libpath, fx, rng="philox", options=options)
+        aos = before["packets.aos"].copy()
+        pk = aos.view(fixtures.snap.packet_dtype(stride))
+        victim = int(np.nonzero(pk["type"] == 11)[0][3])
+        pk["type"][victim] = 77
+        with pytest.raises(ablib.ArtisB200Error, match="unknown packet type") as info:
+            eng.update_packets_host(fx["nts"], aos, n, stride)
+        assert f"packet index {victim}" in str(info.value)
+        record = eng.get_array("dev_error")
+        assert record[0] == 6 and record[1] == victim and record[2] == 77 and record[3] == 1
+        # the record is cleared when the next timestep begins, and a clean run passes again
+        eng.set_arrays(before)
+        eng.begin_timestep(fx["nts"])
+        good = before["packets.aos"].copy()
+        eng.update_packets_host(fx["nts"], good, n, stride)
+        assert eng.get_array("dev_error")[0] == 0
+        eng.close()
+
+
 def check_options_summary(libpath, preset):
     eng = ablib.ArtisB200(libpath=libpath)
     summary = eng.options_summary()

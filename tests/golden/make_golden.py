@@ -35,6 +35,10 @@ GOLDEN = {
     "kilonova_guttman_toy": [1],
     "kilonova_wollaeger_toy": [1],
     "kilonova_barnes_toy": [1],
+    # expansion-opacity / bound-bound thermalisation r-packet modes (rpkt.cc:221-320, 628-651, 964-981)
+    "kilonova_expansionopac_toy": [2, 4],
+    "kilonova_expopac_retrace_toy": [4],
+    "kilonova_bbtherm_toy": [4],
     # BASELINE configs[1] at full atomic-data and grid size, 2000 packets: bench-scale KATs, histories, sampled cell tables
     "kilonova_2d_kat": [2],
 }

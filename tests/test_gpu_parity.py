@@ -185,3 +185,7 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(ablib.ArtisB200Error):
         eng.begin_timestep(0)
     eng.close()
+
+
+def test_failed_device_assertions_are_reported():
+    abi_checks.check_device_error_record(_lib("kilonova_toy"))

@@ -114,3 +114,7 @@ def test_bench_scale_histories_and_sampled_tables():
     lib = fixtures.hostsim_library("kilonova_lte")
     n, ncells = parity_checks.check_bench_scale_histories(lib, "kilonova_2d_kat", 2, options=SCHEDULES["wavefront-resort"])
     assert n == 2000 and ncells == 6
+
+
+def test_failed_device_assertions_are_reported():
+    abi_checks.check_device_error_record(fixtures.hostsim_library("kilonova_lte"))

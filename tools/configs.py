@@ -147,6 +147,23 @@ CONFIGS = {
         run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
     ) for tag, gam, par in (("guttman", "GUTTMAN", "BARNES"), ("wollaeger", "WOLLAEGER", "WOLLAEGER"),
                             ("barnes", "BARNES", "INSTANTFULLDEPOSITION"))},
+    # kilonova_toy with the expansion-opacity / bound-bound thermalisation r-packet modes (rpkt.cc:221-320, 628-651,
+    # 964-981): the reference's CI variant (expansion opacities, every bound-bound event thermalises), expansion opacities
+    # with the line-by-line re-trace, and a thermalisation probability on the line-by-line opacity
+    **{f"kilonova_{tag}_toy": dict(
+        preset="kilonova_lte",
+        opts=_opts(1000, None, None, {
+            "constexpr int TABLESIZE": "constexpr int TABLESIZE = 20;",
+            "constexpr double MINTEMP": "constexpr double MINTEMP = 1000.;",
+            "constexpr double MAXTEMP": "constexpr double MAXTEMP = 20000.;",
+            "constexpr bool RPKT_USE_EXPANSION_OPACITIES": f"constexpr bool RPKT_USE_EXPANSION_OPACITIES = {expo};",
+            "constexpr std::optional<float> RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY":
+                f"constexpr std::optional<float> RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY{prob};",
+        }),
+        atomic=dict(elements=_KN_ELEMS, nions=3, nlevels=8, trans_frac=0.6, seed=2),
+        model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
+        run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
+    ) for tag, expo, prob in (("expansionopac", "true", " = 1."), ("expopac_retrace", "true", ""), ("bbtherm", "false", " = 0.5"))},
     "classic3d_toy": dict(
         preset="classic",
         opts=_opts(1500),
