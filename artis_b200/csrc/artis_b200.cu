@@ -48,17 +48,26 @@ __global__ void k_soa_to_aos(const __grid_constant__ Tables T, unsigned char* ao
 
 __global__ void k_build_levelpops(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * T.nlevels;
   if (idx < total) {
-    ab::build_levelpop_item(T, static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+    ab::build_levelpop_item(T, T.win_lo + static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+  }
+}
+
+// [cell][line] time-independent factors of the Sobolev optical depths, after the level populations
+__global__ void k_build_linetau(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * T.nlines;
+  if (idx < total) {
+    ab::build_linetau_item(T, T.win_lo + static_cast<int>(idx / T.nlines), static_cast<int>(idx % T.nlines));
   }
 }
 
 __global__ void k_build_percell_misc(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * T.nlevels;
   if (idx < total) {
-    const int cell = static_cast<int>(idx / T.nlevels);
+    const int cell = T.win_lo + static_cast<int>(idx / T.nlevels);
     const int ulev = static_cast<int>(idx % T.nlevels);
     ab::build_corrphotoion_item(T, cell, ulev);
     if (ulev == 0) {
@@ -69,15 +78,15 @@ __global__ void k_build_percell_misc(const __grid_constant__ Tables T) {
 
 __global__ void k_build_keepwords(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(T.ncells) * T.keepwords;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * T.keepwords;
   if (idx < total) {
-    ab::build_keepword_item(T, static_cast<int>(idx / T.keepwords), static_cast<int>(idx % T.keepwords));
+    ab::build_keepword_item(T, T.win_lo + static_cast<int>(idx / T.keepwords), static_cast<int>(idx % T.keepwords));
   }
 }
 
 __global__ void k_build_keptlist(const __grid_constant__ Tables T) {
-  const int cell = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x);
-  if (cell < T.ncells) {
+  const int cell = T.win_lo + static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x);
+  if (cell < T.win_hi) {
     ab::build_keptlist_cell(T, cell);
   }
 }
@@ -91,21 +100,22 @@ __global__ void k_build_keptlist(const __grid_constant__ Tables T) {
 #endif
 __global__ void k_build_macroatom(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(T.ncells) * T.nlevels;
+  const int nwin = T.win_hi - T.win_lo;
+  const long long total = static_cast<long long>(nwin) * T.nlevels;
   if (idx < total) {
 #if ARTISB200_BUILD_CELL_LANES
-    ab::build_macroatom_level(T, static_cast<int>(idx % T.ncells), static_cast<int>(idx / T.ncells));
+    ab::build_macroatom_level(T, T.win_lo + static_cast<int>(idx % nwin), static_cast<int>(idx / nwin));
 #else
-    ab::build_macroatom_level(T, static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
+    ab::build_macroatom_level(T, T.win_lo + static_cast<int>(idx / T.nlevels), static_cast<int>(idx % T.nlevels));
 #endif
   }
 }
 
 __global__ void k_build_cooling(const __grid_constant__ Tables T) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(T.ncells) * T.nions;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * T.nions;
   if (idx < total) {
-    ab::build_cooling_ion(T, static_cast<int>(idx / T.nions), static_cast<int>(idx % T.nions));
+    ab::build_cooling_ion(T, T.win_lo + static_cast<int>(idx / T.nions), static_cast<int>(idx % T.nions));
   }
 }
 
@@ -290,7 +300,7 @@ __device__ __forceinline__ void done_append(const WfQueues& q, const bool finish
 // packets that are inactive from the start of the timestep (escaped earlier, or already at the end of the timestep)
 __global__ void k_done_seed(const __grid_constant__ Tables T, const WfQueues q, const long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const bool finished = (i < n) && (ab::stored_stage(T.pkt.hc[(i < n) ? i : 0]) < 0);
+  const bool finished = (i < n) && (ab::stored_stage(T.pkt.hc[(i < n) ? i : 0]) == ab::ST_DONE);
   done_append(q, finished, static_cast<int>(i));
 }
 
@@ -649,6 +659,18 @@ __global__ void k_reset_work(const __grid_constant__ Tables T, const long long n
   }
 }
 
+// A new table window: parked packets whose cell is inside it join their stage; the others are counted per window
+// (census[w] = packets waiting for window w), so that the host can pick the next window that has work.
+__global__ void k_rewindow(const __grid_constant__ Tables T, const long long n, const int window_cells, unsigned int* census) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const int cell = ab::rewindow_one(T, i);
+    if (cell >= 0) {
+      atomicAdd(&census[cell / window_cells], 1U);
+    }
+  }
+}
+
 // ---- whole-history kernel -------------------------------------------------------------------------------------
 // One thread per packet history with a per-thread dynamic work fetch. It finishes the thin tail of the wavefront
 // (a few thousand packets with long histories, where one launch per step would be launch-bound) and is the
@@ -673,6 +695,7 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
   // with a convergence point (__syncwarp) before each.
   constexpr unsigned FULL = 0xffffffffU;
   const long long max_steps = T.max_steps_per_launch;
+  const bool windowed = (T.win_hi - T.win_lo) < T.ncells;
   const unsigned long long nactive = queue[2];
   ab::Pkt p;
   ab::ChiCont chi;
@@ -718,12 +741,16 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
     }
     if (have) {
       const bool more = ab::packetprop_update_required(p, ts_end);
-      const bool yield = more && max_steps > 0 && steps >= max_steps;
-      if (!more || yield) {
+      // moved into a cell whose tables are outside the window: the packet waits for that window's pass
+      const bool parked = more && windowed && ab::stage_of(p, T) == ab::ST_PARKED;
+      const bool yield = more && !parked && max_steps > 0 && steps >= max_steps;
+      if (!more || yield || parked) {
         ab::store_pkt(p, chi, T, ip, ab::stage_of(p, T));
         have = false;
         if (yield) {
           atomicAdd(&s_still_active, 1U);
+        } else if (parked) {
+          // nothing: counted by the census before the next window
         } else if (done != nullptr) {
           done[atomicAdd(done_count, 1U)] = static_cast<int>(ip);
         }
@@ -779,6 +806,8 @@ struct CudaBackend {
   unsigned int* d_done_count{nullptr};
   long long done_capacity{0};
   long long wf_capacity{0};
+  unsigned int* d_census{nullptr};  // [windows] packets waiting for each table window
+  int census_capacity{0};
   int history_blocks_per_sm{0};
   int stage_blocks_per_sm[ab::NSTAGES]{};
   std::vector<cudaEvent_t> stage_events;
@@ -854,6 +883,7 @@ struct CudaBackend {
       cudaFree(d_wf_lists);
       cudaFree(d_done);
       cudaFree(d_done_count);
+      cudaFree(d_census);
       for (cudaEvent_t e : stage_events) {
         cudaEventDestroy(e);
       }
@@ -877,6 +907,17 @@ struct CudaBackend {
 
   std::string last_error() const { return error; }
   void* stream_handle() { return stream; }
+
+  // device memory free right now (the engine sizes the window of the per-cell tables with it)
+  int64_t free_bytes() {
+    cudaSetDevice(device);
+    size_t free_b = 0;
+    size_t total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+      return -1;
+    }
+    return static_cast<int64_t>(free_b);
+  }
 
   void* alloc(const int64_t nbytes) {
     cudaSetDevice(device);
@@ -917,20 +958,25 @@ struct CudaBackend {
     cudaEventRecord(ev_pre_build, stream);  // an upload may start once everything enqueued before the build is done
     tables_building = true;
     constexpr int B = 128;
-    const long long ncl = static_cast<long long>(T.ncells) * T.nlevels;
+    const long long nwin = T.win_hi - T.win_lo;  // cells of the table window (all cells unless the tables are batched)
+    const long long ncl = nwin * T.nlevels;
     if (ncl > 0) {
       k_build_levelpops<<<blocks_for(ncl, B), B, 0, stream>>>(T);
       k_build_percell_misc<<<blocks_for(ncl, B), B, 0, stream>>>(T);
     }
-    const long long nkw = static_cast<long long>(T.ncells) * T.keepwords;
+    const long long nclines = nwin * T.nlines;
+    if (T.cell_linetau != nullptr && nclines > 0) {
+      k_build_linetau<<<blocks_for(nclines, 256), 256, 0, stream>>>(T);
+    }
+    const long long nkw = nwin * T.keepwords;
     if (nkw > 0) {
       k_build_keepwords<<<blocks_for(nkw, B), B, 0, stream>>>(T);
-      k_build_keptlist<<<blocks_for(T.ncells, 64), 64, 0, stream>>>(T);
+      k_build_keptlist<<<blocks_for(nwin, 64), 64, 0, stream>>>(T);
     }
     if (ncl > 0) {
       k_build_macroatom<<<blocks_for(ncl, B), B, 0, stream>>>(T);
     }
-    const long long nci = static_cast<long long>(T.ncells) * T.nions;
+    const long long nci = nwin * T.nions;
     if (nci > 0) {
       k_build_cooling<<<blocks_for(nci, B), B, 0, stream>>>(T);
     }
@@ -1349,11 +1395,60 @@ struct CudaBackend {
       k_done_seed<<<blocks_for(n, 256), 256, 0, stream>>>(T, dq, n);
       tm->launches += 1;
     }
-    const bool good = (o.schedule == 1) ? run_wavefront(T, n, o, tm) : run_history(T, n, tm);
-    if (!good) {
-      return false;
+    // Cell-batched per-cell tables: run the schedule on the packets whose cell is inside the table window, then move the
+    // window to the next group of cells that has packets waiting (parked), rebuild the tables there and go on, until no
+    // packet waits (the device form of the reference's passes over cell-cache groups, update_packets.cc:574-612).
+    const int window_cells = T.win_hi - T.win_lo;
+    const bool windowed = window_cells < T.ncells;
+    const int nwindows = windowed ? (T.ncells + window_cells - 1) / window_cells : 1;
+    std::vector<unsigned int> census(static_cast<size_t>(nwindows), 0U);
+    if (windowed && census_capacity < nwindows) {
+      if (!grow(d_census, static_cast<size_t>(nwindows) * sizeof(unsigned int), "cudaMalloc(window census)")) {
+        return false;
+      }
+      census_capacity = nwindows;
+    }
+    int window = T.win_lo / ((window_cells > 0) ? window_cells : 1);
+    while (true) {
+      tm->table_passes++;
+      const bool good = (o.schedule == 1) ? run_wavefront(T, n, o, tm) : run_history(T, n, tm);
+      if (!good) {
+        return false;
+      }
+      if (!windowed) {
+        break;
+      }
+      cudaMemsetAsync(d_census, 0, static_cast<size_t>(nwindows) * sizeof(unsigned int), stream);
+      k_rewindow<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, window_cells, d_census);
+      tm->launches += 1;
+      if (!ok(cudaMemcpyAsync(census.data(), d_census, static_cast<size_t>(nwindows) * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream),
+              "window census readback") ||
+          !ok(cudaStreamSynchronize(stream), "k_rewindow")) {
+        return false;
+      }
+      int next_window = -1;
+      for (int k = 1; k <= nwindows; k++) {
+        const int w = (window + k) % nwindows;
+        if (census[static_cast<size_t>(w)] > 0U) {
+          next_window = w;
+          break;
+        }
+      }
+      if (next_window < 0) {
+        break;  // nothing waits: every packet has reached the end of the timestep
+      }
+      window = next_window;
+      const int lo = window * window_cells;
+      const int hi = (lo + window_cells < T.ncells) ? lo + window_cells : T.ncells;
+      T = ab::window_view(T, lo, hi);
+      if (!build_cell_tables(T)) {
+        return false;
+      }
+      k_rewindow<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, window_cells, d_census);  // packets of this window join their stages
+      tm->launches += 8;
     }
     cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &tm->launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(&T.diag[ab::DIAG_TABLE_PASSES], &tm->table_passes, sizeof(long long), cudaMemcpyHostToDevice, stream);
     cudaEventRecord(ev_stop, stream);
     if (!ok(cudaEventSynchronize(ev_stop), "cudaEventSynchronize")) {
       return false;

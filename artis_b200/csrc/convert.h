@@ -195,6 +195,16 @@ AHD void build_levelpop_item(const Tables& T, const int cell, const int ulev) {
       calculate_levelpop(T, cell, T.ion_element[uion], T.ion_index[uion], ulev - T.ion_levelstart[uion]);
 }
 
+// the time-independent factor of the Sobolev optical depth of one line in one cell (rpkt.cc:75-100), for the line walk
+AHD void build_linetau_item(const Tables& T, const int cell, const int lineindex) {
+  const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
+  const double n_l = cellpops[T.line_lower[lineindex]];
+  const double n_u = cellpops[T.line_upper[lineindex]];
+  const double B_ul = T.line_B_ul[lineindex];
+  const double B_lu = T.line_B_lu[lineindex];
+  T.cell_linetau[(static_cast<long long>(cell) * T.nlines) + lineindex] = ((B_lu * n_l) - (B_ul * n_u)) * HCLIGHTOVERFOURPI;
+}
+
 AHD void build_corrphotoion_item(const Tables& T, const int cell, const int ulev) {
   const int n = T.level_nphixstargets[ulev];
   for (int k = 0; k < n; k++) {

@@ -143,6 +143,7 @@ struct PropagateTimings {
   long long tail_packets{0};
   long long iterations{0};
   long long launches{0};
+  long long table_passes{0};   // table windows run (cell-batched per-cell tables; 1 = all cells resident)
 };
 
 struct ArrayRec {
@@ -179,6 +180,12 @@ class Engine {
   // options
   int rank{0};
   int nranks{1};
+  // cell-batched per-cell tables (tables.h win_lo/win_hi): cells per window; 0 = chosen from table_budget_mb
+  long long table_window_cells{0};        // [table_window_cells]
+  long long table_budget_mb{0};           // [table_budget_mb] 0 = 60 % of the device memory free when the tables are allocated
+  int window_capacity{0};                 // cells the allocated tables hold
+  int line_tau_table{-1};               // [line_tau_table] per-cell line table of Sobolev optical depths: 0 off, 1 on, -1 if it fits
+  long long line_tau_table_max_mb{8192};  // [line_tau_table_max_mb]
   bool stream_download{false};  // [stream_download] update_packets_host returns the packets in completion order
   PropagateOptions popt;
   PropagateTimings last;
@@ -409,6 +416,22 @@ class Engine {
       popt.stage_timing = static_cast<int>(value);
     } else if (name == "stream_download") {
       stream_download = (value != 0);
+    } else if (name == "table_window_cells") {
+      // the per-cell tables hold this many cells at a time (0 = all cells if they fit into table_budget_mb, else as many
+      // as fit); packets whose cell is outside the window wait for its pass (update_packets.cc:468-524, 574-612)
+      table_window_cells = (value < 0) ? 0 : value;
+      outputs_allocated = false;
+    } else if (name == "table_budget_mb") {
+      table_budget_mb = (value < 0) ? 0 : value;
+      outputs_allocated = false;
+    } else if (name == "line_tau_table") {
+      // per-cell line table of the Sobolev optical depths (tables.h cell_linetau): 0 off, 1 on, -1 on when ncells x nlines
+      // doubles take at most line_tau_table_max_mb
+      line_tau_table = static_cast<int>(value);
+      outputs_allocated = false;
+    } else if (name == "line_tau_table_max_mb") {
+      line_tau_table_max_mb = value;
+      outputs_allocated = false;
     } else if (name == "rank") {
       rank = static_cast<int>(value);
     } else if (name == "nranks") {
@@ -659,6 +682,24 @@ class Engine {
       *slots[k] = static_cast<double*>(rec.dptr);
       off += sizes[k];
     }
+    // cells per table window: everything resident when it fits into the budget
+    const int64_t linetau_percell = static_cast<int64_t>(T.nlines) * 8;
+    const int64_t bytes_percell = 8 * (static_cast<int64_t>(T.nlevels) * (1 + MA_ACTION_COUNT) + T.matrans_total + T.ncoolingterms +
+                                       5 * static_cast<int64_t>(T.nbfcontinua) + 2 * static_cast<int64_t>(T.keepwords) + T.nphixstargets_total) +
+                                  4 * static_cast<int64_t>(T.nbfcontinua);
+    int64_t budget = table_budget_mb * 1048576LL;
+    if (budget <= 0) {
+      const int64_t free_now = be.free_bytes();
+      budget = (free_now > 0) ? (free_now / 10) * 6 : (1LL << 62);
+    }
+    int64_t nw = nc;
+    if (table_window_cells > 0) {
+      nw = (table_window_cells < nc) ? table_window_cells : nc;
+    } else if (bytes_percell > 0 && nc * bytes_percell > budget) {
+      nw = budget / bytes_percell;
+      nw = (nw < 1) ? 1 : nw;
+    }
+    window_capacity = static_cast<int>(nw);
     bool ok = true;
     ok = ok && alloc_output("ts.pellet_decays", 'q', 1, &T.ts_pellet_decays);
     ok = ok && alloc_output("counters", 'q', CNT_COUNT, &T.counters);
@@ -666,24 +707,34 @@ class Engine {
     ok = ok && alloc_output("diag", 'q', NDIAG, &T.diag);
     // the same work counters per kernel family: rows ST_OTHER, ST_RTHIN, ST_RTHICK, ST_MA, and the whole-history kernel
     ok = ok && alloc_output("diag_stage", 'q', (NSTAGES + 1) * NDIAG, &T.diag_stage);
-    ok = ok && alloc_output("built.levelpops", 'd', nc * T.nlevels, &T.cell_levelpops);
-    ok = ok && alloc_output("built.maprocessrates", 'd', nc * T.nlevels * MA_ACTION_COUNT, &T.cell_maprocessrates);
-    ok = ok && alloc_output("built.matrans", 'd', nc * static_cast<int64_t>(T.matrans_total), &T.cell_matrans);
-    ok = ok && alloc_output("built.cooling_contrib", 'd', nc * T.ncoolingterms, &T.cell_cooling_contrib);
-    ok = ok && alloc_output("built.cont_nnlevel", 'd', nc * T.nbfcontinua, &T.cell_cont_nnlevel);
-    ok = ok && alloc_output("built.cont_keepbits", 'Q', nc * T.keepwords, &T.cell_cont_keepbits);
-    ok = ok && alloc_output("built.cont_departure", 'd', nc * T.nbfcontinua, &T.cell_cont_departure);
-    ok = ok && alloc_output("built.cont_edgepart", 'd', nc * T.nbfcontinua, &T.cell_cont_edgepart);
-    ok = ok && alloc_output("built.cont_pack", 'd', 2 * nc * T.nbfcontinua, &T.cell_cont_pack);
-    ok = ok && alloc_output("built.cont_keptlist", 'i', nc * T.nbfcontinua, &T.cell_cont_keptlist);
-    ok = ok && alloc_output("built.cont_keptrank", 'i', nc * (T.keepwords + 1), &T.cell_cont_keptrank);
+    // (the windowed tables hold `nw` cells; with nw == nc every cell is resident)
+    ok = ok && alloc_output("built.levelpops", 'd', nw * T.nlevels, &T.cell_levelpops);
+    ok = ok && alloc_output("built.maprocessrates", 'd', nw * T.nlevels * MA_ACTION_COUNT, &T.cell_maprocessrates);
+    ok = ok && alloc_output("built.matrans", 'd', nw * static_cast<int64_t>(T.matrans_total), &T.cell_matrans);
+    ok = ok && alloc_output("built.cooling_contrib", 'd', nw * T.ncoolingterms, &T.cell_cooling_contrib);
+    ok = ok && alloc_output("built.cont_nnlevel", 'd', nw * T.nbfcontinua, &T.cell_cont_nnlevel);
+    ok = ok && alloc_output("built.cont_keepbits", 'Q', nw * T.keepwords, &T.cell_cont_keepbits);
+    ok = ok && alloc_output("built.cont_departure", 'd', nw * T.nbfcontinua, &T.cell_cont_departure);
+    ok = ok && alloc_output("built.cont_edgepart", 'd', nw * T.nbfcontinua, &T.cell_cont_edgepart);
+    ok = ok && alloc_output("built.cont_pack", 'd', 2 * nw * T.nbfcontinua, &T.cell_cont_pack);
+    ok = ok && alloc_output("built.cont_keptlist", 'i', nw * T.nbfcontinua, &T.cell_cont_keptlist);
+    ok = ok && alloc_output("built.cont_keptrank", 'i', nw * (T.keepwords + 1), &T.cell_cont_keptrank);
     ok = ok && alloc_output("built.chi_ff_nnionpart", 'd', nc, &T.cell_chi_ff_nnionpart);
-    ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nc * static_cast<int64_t>(T.nphixstargets_total),
+    ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nw * static_cast<int64_t>(T.nphixstargets_total),
                             &T.cell_corrphotoioncoeff);
+    const int64_t linetau_count = nw * static_cast<int64_t>(T.nlines);
+    const bool want_linetau = (line_tau_table > 0) || (line_tau_table < 0 && linetau_count * 8 <= line_tau_table_max_mb * 1048576LL &&
+                                                       (nw == nc ? nc * (bytes_percell + linetau_percell) <= budget : false));
+    T.cell_linetau = nullptr;
+    if (want_linetau && linetau_count > 0) {
+      ok = ok && alloc_output("built.line_taucoeff", 'd', linetau_count, &T.cell_linetau);
+    }
     if (!ok) {
       return fail("allocation of the per-cell tables failed (Nc x table sizes too large for this device?): " +
                   be.last_error());
     }
+    T.win_lo = 0;
+    T.win_hi = window_capacity;
     outputs_allocated = true;
     return 0;
   }
@@ -773,6 +824,8 @@ class Engine {
     be.zero(T.diag, NDIAG * 8);
     be.zero(T.dev_error, NDEVERROR * 8);
     be.zero(T.diag_stage, (NSTAGES + 1) * NDIAG * 8);
+    // the first table window (all cells unless the tables are batched); update_packets moves on from there
+    T = window_view(T, 0, window_capacity);
     if (!be.build_cell_tables(T)) {
       return fail("begin_timestep: building the per-cell tables failed: " + be.last_error());
     }

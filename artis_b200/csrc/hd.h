@@ -18,6 +18,15 @@
 
 namespace ab {
 
+// hint that a global-memory sector will be read soon (no register, no dependency); nothing on the host
+AHD void prefetch_global(const void* addr) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
+#else
+  (void)addr;
+#endif
+}
+
 // f64 / i64 accumulation into shared (global-memory) estimators: a relaxed atomic on the device
 // (the reference's atomicadd, constants.h:217-275), a plain add in the single-threaded host build
 AHD void atomic_add(double* addr, const double val) {

@@ -132,7 +132,9 @@ struct Ctx {
     T.dev_error[3] += 1;
 #endif
   }
-  AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(i * T.scratch_stride) + ip]; }
+  // packet-major: the Ng contributions of a packet are contiguous (zeroed, filled and read together: a few sectors
+  // instead of one per ground continuum; packets of a warp are not neighbours in memory after the sort by cell)
+  AHD double* groundcont_contr(const int i) const { return &T.scratch_groundcont[(ip * T.nbfcontinua_ground) + i]; }
   AHD double* bfestim_contr(const int i) const { return &T.scratch_bfcontr[(i * T.scratch_stride) + ip]; }
 
   // add the thread-private counters to the block's accumulators (end of kernel) and clear them
@@ -167,7 +169,8 @@ struct Accum {
 };
 
 // stages a packet can wait in between kernels (HotC::stage)
-enum : int { ST_DONE = -1, ST_OTHER = 0, ST_RTHIN = 1, ST_RTHICK = 2, ST_MA = 3, NSTAGES = 4, ST_ANY = 99 };
+// (ST_PARKED: active, but the per-cell tables of its cell are not in the current table window, tables.h win_lo/win_hi)
+enum : int { ST_PARKED = -2, ST_DONE = -1, ST_OTHER = 0, ST_RTHIN = 1, ST_RTHICK = 2, ST_MA = 3, NSTAGES = 4, ST_ANY = 99 };
 
 AHD int pack_stage(const int stage, const int ev_pending) { return (stage & 0xff) | (ev_pending << 8); }
 AHD int stored_stage(const HotC& hc) { return static_cast<int>(static_cast<signed char>(hc.stage & 0xff)); }

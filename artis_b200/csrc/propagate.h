@@ -297,6 +297,27 @@ AHD void init_chicont(ChiCont& chi) {
 //   ST_RTHIN   r-packet in a cell with the detailed treatment: continuum opacity + Sobolev line walk
 //   ST_RTHICK  r-packet in a grey (thick) or empty cell: boundary distance + grey scattering only
 //   ST_MA      r-packet with a recorded macro-atom activation: walk to deactivation
+//   ST_PARKED  any of these in a cell whose per-cell tables are outside the current table window (never when all cells
+//              are resident): waits for the pass that builds its cell's tables
+// Pellets, gamma packets and r-packets in grey or empty cells read no per-cell table and are never parked.
+AHD int stage_of_type_in_cell(const Tables& T, const int type, const int cellindex) {
+  const bool windowed = (T.win_hi - T.win_lo) < T.ncells;
+  if (type != TYPE_RPKT) {
+    if (windowed && type != TYPE_RADIOACTIVE_PELLET && type != TYPE_GAMMA) {
+      const int cell = T.propcell_nonemptymgi[cellindex];
+      if (cell >= 0 && (cell < T.win_lo || cell >= T.win_hi)) {
+        return ST_PARKED;
+      }
+    }
+    return ST_OTHER;
+  }
+  const int cell = T.propcell_nonemptymgi[cellindex];
+  if (cell < 0 || T.thick[cell] == CELL_THICK) {
+    return ST_RTHICK;
+  }
+  return (windowed && (cell < T.win_lo || cell >= T.win_hi)) ? ST_PARKED : ST_RTHIN;
+}
+
 AHD int stage_of(const Pkt& p, const Tables& T) {
   if (p.ma_pending != 0) {
     return ST_MA;
@@ -304,11 +325,7 @@ AHD int stage_of(const Pkt& p, const Tables& T) {
   if (p.ev_pending == EV_NONE && !packetprop_update_required(p, T.ts_end)) {
     return ST_DONE;
   }
-  if (p.type != TYPE_RPKT) {
-    return ST_OTHER;
-  }
-  const int cell = T.propcell_nonemptymgi[p.cellindex];
-  return (cell >= 0 && T.thick[cell] != CELL_THICK) ? ST_RTHIN : ST_RTHICK;
+  return stage_of_type_in_cell(T, p.type, p.cellindex);
 }
 
 // start of update_packets: the stage each stored packet starts in (no activation or emission pending: none
@@ -317,12 +334,7 @@ AHD void reset_work_one(const Tables& T, const long long i) {
   HotC hc = T.pkt.hc[i];
   int stage = ST_DONE;
   if (hc.type != TYPE_ESCAPE && T.pkt.ha[i].prop_time < T.ts_end) {
-    if (hc.type != TYPE_RPKT) {
-      stage = ST_OTHER;
-    } else {
-      const int cell = T.propcell_nonemptymgi[hc.cellindex];
-      stage = (cell >= 0 && T.thick[cell] != CELL_THICK) ? ST_RTHIN : ST_RTHICK;
-    }
+    stage = stage_of_type_in_cell(T, hc.type, hc.cellindex);
   }
   hc.stage = pack_stage(stage, EV_NONE);
   hc.chi_bf = 0.;
@@ -338,6 +350,22 @@ AHD void reset_work_one(const Tables& T, const long long i) {
   T.pkt.hb[i].chi_nu = -1.;
   T.pkt.hb[i].chi_escatter = 0.;
   T.pkt.hb[i].chi_ff = 0.;
+}
+
+// A new table window has been built: packets that waited for it join the stage they belong to. A parked packet has no
+// activation or emission pending (both are resolved in the cell they arose in, which was inside the window then).
+// Returns the window-independent cell of a packet that stays parked (for the census of waiting packets), or -1.
+AHD int rewindow_one(const Tables& T, const long long i) {
+  HotC* hc = &T.pkt.hc[i];
+  if (stored_stage(*hc) != ST_PARKED) {
+    return -1;
+  }
+  const int stage = stage_of_type_in_cell(T, hc->type, hc->cellindex);
+  if (stage != ST_PARKED) {
+    hc->stage = pack_stage(stage, hc->stage >> 8);
+    return -1;
+  }
+  return T.propcell_nonemptymgi[hc->cellindex];
 }
 
 // Run one visit of the packet to `stage`. r-packet stages take up to `max_steps` transport steps while the
@@ -377,6 +405,9 @@ AHD bool propagate_packet(Pkt& p, const Ctx& c, ChiCont& chi, const long long ma
     do_packet(p, c, ts_end, chi);
     finish_macroatom(p, c);
     steps++;
+    if ((c.T.win_hi - c.T.win_lo) < c.T.ncells && stage_of(p, c.T) == ST_PARKED) {
+      return false;  // waits for the pass that holds its cell's tables
+    }
   }
   return false;
 }

@@ -75,7 +75,13 @@ AHD double get_nu_cmf_abort(const double* pos, const double* dir, const double p
 }
 
 // rpkt.cc:75-100 with the cell's level-population table
-AHD double get_tau_sobolev(const Tables& T, const double* cellpops, const int lineindex, const double t_current) {
+AHD double get_tau_sobolev(const Tables& T, const double* cellpops, const double* celllinetau, const int lineindex,
+                           const double t_current) {
+  if (celllinetau != nullptr) {
+    // the time-independent factor from the per-cell line table (convert.h build_linetau_item): the same operations in
+    // the same order, one contiguous double per line instead of two gathered level populations
+    return dmax(celllinetau[lineindex] * t_current, 0.);
+  }
   const double n_l = cellpops[T.line_lower[lineindex]];
   const double n_u = cellpops[T.line_upper[lineindex]];
   const double B_ul = T.line_B_ul[lineindex];
@@ -280,6 +286,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
   double prop_time = p.prop_time;
   int next_trans = p.next_trans;
   const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
+  const double* celllinetau = (T.cell_linetau != nullptr) ? T.cell_linetau + (static_cast<long long>(cell) * T.nlines) : nullptr;
 
   const double chi_cont = chi.total() * doppler;
   double tau = 0.;
@@ -297,6 +304,12 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
     }
     nvisited++;
     const double nu_trans = T.line_nu[lineindex];
+    if (celllinetau != nullptr) {
+      // the walk reads the line frequencies and the cell's line table front to back: ask for the sectors one ahead
+      const int ahead = (lineindex + 4 < T.nlines) ? lineindex + 4 : T.nlines - 1;
+      prefetch_global(&T.line_nu[ahead]);
+      prefetch_global(&celllinetau[ahead]);
+    }
     next_trans = lineindex + 1;
     const double ldist = get_linedistance(prop_time, nu_cmf, nu_trans, dnu_on_dl);
     const double tau_cont = chi_cont * ldist;
@@ -306,7 +319,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
         c.work<DIAG_LINES_VISITED>(nvisited);
         return {DBL_MAX_, next_trans - 1, false};
       }
-      const double tau_line = get_tau_sobolev(T, cellpops, lineindex, prop_time);
+      const double tau_line = get_tau_sobolev(T, cellpops, celllinetau, lineindex, prop_time);
       if ((tau_rnd - tau) <= (tau_cont + tau_line)) {
         const int element = T.line_elementindex[lineindex];
         const int ion = T.line_ionindex[lineindex];

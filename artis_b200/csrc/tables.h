@@ -215,6 +215,7 @@ enum : int {
   DIAG_GAMMA_EVENTS = 9,
   DIAG_KERNEL_LAUNCHES = 10,
   DIAG_PACKET_SEGMENTS = 11,
+  DIAG_TABLE_PASSES = 12,  // table windows built and run in the last update_packets (1 = all cells resident)
 };
 
 // Packet state in HBM (device resident across timesteps). Field set = reference Packet (packet.h:109-156) plus the
@@ -351,6 +352,13 @@ struct Tables {
   int log2_nbf;        // probes of one binary search over the continuum list
 
   // current timestep
+  // Cell window of the per-cell tables: the built.* tables hold the cells [win_lo, win_hi) only (all cells when the tables
+  // fit into the device's memory). Their pointers are offset so that they are indexed with the cell number itself
+  // (window_view below); packets that need the tables of a cell outside the window wait (ST_PARKED) until a pass
+  // that holds their cell - the device form of the reference's per-group cell cache (update_packets.cc:468-524, 574-612).
+  int win_lo;
+  int win_hi;
+
   int nts;
   double ts_begin;
   double ts_end;
@@ -370,6 +378,10 @@ struct Tables {
   // contiguous range of the list (warp_chi.h). Built after the keep-bitmaps.
   int* cell_cont_keptlist;        // [ncells][nbfcontinua]
   int* cell_cont_keptrank;        // [ncells][keepwords + 1]
+  // Sobolev optical depth of every line in every cell without its time factor: ((B_lu n_l) - (B_ul n_u)) hc/4pi
+  // (rpkt.cc:75-100), [ncells][nlines], or null when the table is switched off / does not fit: the line walk then reads one
+  // contiguous double per visited line instead of gathering two level populations (option line_tau_table)
+  double* cell_linetau;
 
   // run options
   int rng_mode;
@@ -383,9 +395,37 @@ struct Tables {
   int* scratch_bfestimbegin;
   int* scratch_bfestimend;
   int nbfestim;
-  // per-packet ground-continuum contributions of the cached continuum opacity [nbfcontinua_ground][scratch_stride]
+  // per-packet ground-continuum contributions of the cached continuum opacity [packet][nbfcontinua_ground]
   double* scratch_groundcont;
   long long scratch_stride;
 };
+
+// The same tables seen with the per-cell table window [lo, hi): every windowed table is allocated for `capacity` cells and
+// holds cell `lo` first; the pointers are moved back by lo rows so that kernels keep indexing with the cell number.
+inline Tables window_view(const Tables& base, const int lo, const int hi) {
+  Tables W = base;
+  const long long shift = static_cast<long long>(lo) - base.win_lo;  // base may itself be a view
+  W.win_lo = lo;
+  W.win_hi = hi;
+  const auto move = [shift](auto*& ptr, const long long row) {
+    if (ptr != nullptr) {
+      ptr -= shift * row;
+    }
+  };
+  move(W.cell_levelpops, base.nlevels);
+  move(W.cell_maprocessrates, static_cast<long long>(base.nlevels) * MA_ACTION_COUNT);
+  move(W.cell_matrans, base.matrans_total);
+  move(W.cell_cooling_contrib, base.ncoolingterms);
+  move(W.cell_cont_nnlevel, base.nbfcontinua);
+  move(W.cell_cont_keepbits, base.keepwords);
+  move(W.cell_cont_departure, base.nbfcontinua);
+  move(W.cell_cont_edgepart, base.nbfcontinua);
+  move(W.cell_cont_pack, base.nbfcontinua);
+  move(W.cell_cont_keptlist, base.nbfcontinua);
+  move(W.cell_cont_keptrank, static_cast<long long>(base.keepwords) + 1);
+  move(W.cell_corrphotoioncoeff, base.nphixstargets_total);
+  move(W.cell_linetau, base.nlines);
+  return W;
+}
 
 }  // namespace ab

@@ -122,6 +122,7 @@ enum {
   ARTISB200_DIAG_GAMMA_EVENTS = 9,    /* physical gamma events (Compton/photoelectric/pair) */
   ARTISB200_DIAG_KERNEL_LAUNCHES = 10,/* propagation kernel launches in the last update_packets */
   ARTISB200_DIAG_PACKET_SEGMENTS = 11,/* packet (re)loads: one per packet per launch */
+  ARTISB200_DIAG_TABLE_PASSES = 12,   /* table windows built and run in the last update_packets (1 = all cells resident) */
   ARTISB200_NDIAG = 16
 };
 
@@ -164,7 +165,11 @@ int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, 
  * "wf_concurrent": 1 (default) = the three independent stage kernels of an iteration run on separate streams;
  * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
  * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
- * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep. */
+ * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep;
+ * "line_tau_table", "line_tau_table_max_mb": per-cell table [Nc][nlines] of the time-independent factor of every line's
+ *   Sobolev optical depth (rpkt.cc:75-100), built with the other per-cell tables: the line walk then reads one contiguous
+ *   double per visited line instead of gathering two level populations (bit-identical optical depths). 1 = on, 0 = off,
+ *   -1 (default) = on when the table takes at most line_tau_table_max_mb (default 8192). Read back as "built.line_taucoeff". */
 int artisb200_set_option(artisb200_ctx* ctx, const char* name, int64_t value);
 
 /* Validate that all required static tables are present and build derived static tables.

@@ -59,4 +59,8 @@ EXSPEC_OBJS := $(addprefix $(OUT)/,$(addsuffix .o,$(PLAIN) exspec $(addprefix re
 $(OUT)/exspec: $(EXSPEC_OBJS)
 	$(CXX) -o $@ $^ -ldl
 
+# object files are intermediates: a missing .o does not rebuild an up-to-date binary (they are deleted to keep the
+# snapshot that travels to the GPU box small)
+.SECONDARY: $(OBJS) $(EXSPEC_OBJS)
+
 .PHONY: all

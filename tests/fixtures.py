@@ -47,9 +47,11 @@ def hostsim_library(preset, defines=(), tag=""):
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")] + [os.path.join(ROOT, "tests", "hostsim", "hostsim.cc")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
+        tmp = f"{out}.{os.getpid()}.tmp"  # pytest-xdist workers may build the same library at the same time
         subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                         "-Wno-subobject-linkage", "-I" + csrc, *[f"-D{d}" for d in defines], f"-DARTISB200_PRESET_HEADER=\"options/preset_{preset}.h\"",
-                        os.path.join(ROOT, "tests", "hostsim", "hostsim.cc"), "-o", out], check=True)
+                        os.path.join(ROOT, "tests", "hostsim", "hostsim.cc"), "-o", tmp], check=True)
+        os.replace(tmp, out)
     os.environ["ARTISB200_ALLOW_HOSTSIM"] = "1"
     return out
 

@@ -73,10 +73,17 @@ struct HostBackend {
   void zero(void* d, const int64_t n) { std::memset(d, 0, static_cast<size_t>(n)); }
   void* stream_handle() { return nullptr; }
 
+  int64_t free_bytes() { return -1; }  // no budget of its own: the window comes from the options
+
   bool build_cell_tables(const ab::Tables& T) {
-    for (int cell = 0; cell < T.ncells; cell++) {
+    for (int cell = T.win_lo; cell < T.win_hi; cell++) {
       for (int ulev = 0; ulev < T.nlevels; ulev++) {
         ab::build_levelpop_item(T, cell, ulev);
+      }
+      if (T.cell_linetau != nullptr) {
+        for (int line = 0; line < T.nlines; line++) {
+          ab::build_linetau_item(T, cell, line);
+        }
       }
       T.cell_chi_ff_nnionpart[cell] = ab::calculate_chi_ffheat_nnionpart(T, cell);
       for (int ulev = 0; ulev < T.nlevels; ulev++) {
@@ -160,6 +167,13 @@ struct HostBackend {
     for (int64_t i = 0; i < n; i++) {
       ab::reset_work_one(T, i);
     }
+    // cell-batched per-cell tables: the same passes over table windows as the CUDA backend
+    const int window_cells = T.win_hi - T.win_lo;
+    const bool windowed = window_cells < T.ncells;
+    const int nwindows = windowed ? (T.ncells + window_cells - 1) / window_cells : 1;
+    int window = T.win_lo / ((window_cells > 0) ? window_cells : 1);
+    while (true) {
+    tm->table_passes++;
     if (o.schedule == 1) {
       std::vector<int> lists[2][ab::NSTAGES];
       for (int64_t i = 0; i < n; i++) {
@@ -229,6 +243,36 @@ struct HostBackend {
     } else {
       run_history(T, n, acc, tm);
     }
+    if (!windowed) {
+      break;
+    }
+    std::vector<unsigned int> census(static_cast<size_t>(nwindows), 0U);
+    for (int64_t i = 0; i < n; i++) {
+      const int cell = ab::rewindow_one(T, i);
+      if (cell >= 0) {
+        census[static_cast<size_t>(cell / window_cells)]++;
+      }
+    }
+    int next_window = -1;
+    for (int k = 1; k <= nwindows; k++) {
+      const int w = (window + k) % nwindows;
+      if (census[static_cast<size_t>(w)] > 0U) {
+        next_window = w;
+        break;
+      }
+    }
+    if (next_window < 0) {
+      break;
+    }
+    window = next_window;
+    const int lo = window * window_cells;
+    T = ab::window_view(T, lo, (lo + window_cells < T.ncells) ? lo + window_cells : T.ncells);
+    build_cell_tables(T);
+    for (int64_t i = 0; i < n; i++) {
+      ab::rewindow_one(T, i);
+    }
+    }
+    T.diag[ab::DIAG_TABLE_PASSES] = tm->table_passes;
     for (int k = 0; k < ab::CNT_COUNT; k++) {
       T.counters[k] += acc.cnt[k];
     }

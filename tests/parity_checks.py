@@ -109,7 +109,8 @@ def assert_aggregates(config, est, after, est_err, est_tol):
     assert int(est["ts.pellet_decays"][0]) == int(after["ts.pellet_decays"][0])
 
 
-def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction=1.0, tol=1e-9, est_tol=1e-9, options=None):
+def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction=1.0, tol=1e-9, est_tol=1e-9, options=None,
+                           check_tables=True):
     """replay the timestep with every packet continuing its own reference RNG stream: histories must coincide"""
     fx = fixtures.load_golden(config, nts)
     pk, est, built, _ = fixtures.run_fixture(libpath, fx, rng="xoshiro", max_steps=max_steps, options=options)
@@ -124,10 +125,23 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
     allowed = int(np.ceil((1.0 - min_exact_fraction) * len(ref)))
     assert n_bad <= allowed, f"{n_bad} packets differ from the oracle ({n_fb_events} free-bound events) ({worst})"
     if min_exact_fraction == 1.0:
-        check_cell_tables(built, after)
+        if check_tables and not (options or {}).get("table_window_cells"):  # (windowed tables hold one group of cells)
+            check_cell_tables(built, after)
         assert_aggregates(config, est, after, est_err, est_tol)
     n_fb = n_fb_events
     return frac_ok, n_fb, est
+
+
+def check_table_windows(libpath, config, nts, window_cells, options=None):
+    """cell-batched per-cell tables (the device form of the reference's cell-cache groups, update_packets.cc:468-524,
+    574-612): with the tables of only `window_cells` cells resident at a time, packets wait for the pass that holds their
+    cell - every packet history, counter and estimator must still coincide with the reference's"""
+    opts = dict(options or {})
+    opts["table_window_cells"] = window_cells
+    _, _, est = check_packet_histories(libpath, config, nts, options=opts, check_tables=False)
+    passes = int(est["diag"][12])  # ARTISB200_DIAG_TABLE_PASSES
+    assert passes > 1, f"the run used {passes} table window pass(es): the windows were not exercised"
+    return passes
 
 
 def check_idempotence(libpath, config, nts, options=None):

@@ -17,12 +17,14 @@ SCHEDULES = {
     "history": {"schedule": 0},                                         # one whole-history kernel
     # chunked stage kernels (no lane refill), one step / one transition per visit
     "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1, "wf_masteps": 1, "wf_ma_rounds": 1,
-                         "wf_masteps_last": -1, "wf_refill_masteps": 0, "wf_refill_thicksteps": 0},
+                         "wf_masteps_last": -1, "wf_refill_masteps": 0, "wf_refill_thicksteps": 0, "line_tau_table": 0},
     "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0, "wf_refill_masteps": 0},   # whole macro-atom walk per visit
     "wavefront-refill": {"schedule": 1, "wf_tail": 0, "wf_refill_masteps": 3, "wf_refill_thicksteps": 2},  # lane refill, short visits
     "wavefront-resort": {"schedule": 1, "wf_tail": 0, "wf_resort_every": 1, "wf_sync_every": 2},  # lists re-sorted by cell
     "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2, "wf_refill_masteps": 0},
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
+    # per-cell tables of 11 cells at a time: packets wait for the pass that holds their cell (cell-batched tables)
+    "wavefront-windows": {"schedule": 1, "wf_tail": 0, "table_window_cells": 11},
 }
 
 @pytest.mark.parametrize("config,nts", CASES)
@@ -114,6 +116,14 @@ def test_bench_scale_histories_and_sampled_tables():
     lib = fixtures.hostsim_library("kilonova_lte")
     n, ncells = parity_checks.check_bench_scale_histories(lib, "kilonova_2d_kat", 2, options=SCHEDULES["wavefront-resort"])
     assert n == 2000 and ncells == 6
+
+
+@pytest.mark.parametrize("schedule", ["history", "wavefront-notail", "wavefront-resort", "wavefront-tail"])
+@pytest.mark.parametrize("config,nts,window", [("classic3d_toy", 2, 37), ("kilonova_toy", 4, 9), ("classic_toy_1d", 3, 3),
+                                               ("nltephot_toy", 3, 1), ("classic_toy", 0, 5)])
+def test_cell_batched_tables_keep_histories(config, nts, window, schedule):
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[config])
+    parity_checks.check_table_windows(lib, config, nts, window, options=SCHEDULES[schedule])
 
 
 def test_failed_device_assertions_are_reported():
