@@ -2,6 +2,7 @@
 // rate-coefficient LUT interpolation. Mirrors reference atomic.h (accessors, phixs table lookup 202-252),
 // ltepop.h:56-113 / ltepop.cc:395-423 (populations), ratecoeff.cc:54-64, 523-539, 679-875 (LUTs).
 #pragma once
+#include "gk.h"
 #include "hd.h"
 #include "options.h"
 #include "tables.h"
@@ -329,14 +330,34 @@ AHD double bfcoolingcoeff(const Tables& T, const int ulev, const int phixstarget
   return lerp_or_last(T, T.lut_bfcooling, ulev, phixstargetindex, T_e);
 }
 
-// stimulated-recombination-corrected photoionisation rate coefficient, LUT branch (ratecoeff.cc:840-875)
+AHD double corrphotoioncoeff_integral(const Tables& T, int cell, int element, int ion, int level, int phixstargetindex);
+
+// stimulated-recombination-corrected photoionisation rate coefficient (ratecoeff.cc:840-875)
 AHD double calc_corrphotoioncoeff(const Tables& T, const int cell, const int ulev, const int phixstargetindex) {
   if constexpr (!opt::USE_LUT_PHOTOION) {
-    // ratecoeff.cc:848-857: the bound-free rate estimator of the previous timestep or, without one, an integral of the
-    // cross-section over the radiation field model. Both belong to the host's solver state; the binding evaluates
-    // get_corrphotoioncoeff() per (cell, level, target) for the timestep and hands the table over.
-    return T.corrphotoioncoeff_host[(static_cast<long long>(cell) * T.nphixstargets_total) + T.level_phixstargetstart[ulev] +
-                                    phixstargetindex];
+    // ratecoeff.cc:848-857: the normalised bound-free rate estimator of the previous timestep where the continuum has
+    // one, else the integral of the cross-section over the radiation field model (corrphotoioncoeff_integral below)
+    const int uion = T.level_uniqueion[ulev];
+    const int element = T.ion_element[uion];
+    const int ion = T.ion_index[uion];
+    const int level = ulev - T.ion_levelstart[uion];
+    if (ion >= nions_of(T, element) - 1 || level >= T.ion_nlevels_ionising[uion]) {
+      return 0.;  // the level does not photoionise
+    }
+    double gammacorr = -1.;
+    if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+      if (T.globals_timestep >= opt::DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP) {
+        // radfield.cc:932-946 get_bfrate_estimator
+        const int bfestimindex = T.phixstarget_bfestimindex[T.level_phixstargetstart[ulev] + phixstargetindex];
+        if (bfestimindex >= 0) {
+          gammacorr = T.prev_bfrate_normed[(static_cast<long long>(cell) * T.nbfestim) + bfestimindex];
+        }
+      }
+    }
+    if (!opt::DETAILED_BF_ESTIMATORS_ON || gammacorr < 0) {
+      gammacorr = corrphotoioncoeff_integral(T, cell, element, ion, level, phixstargetindex);
+    }
+    return gammacorr;
   }
   const double W = T.W[cell];
   const double T_R = T.TR[cell];
@@ -399,6 +420,41 @@ AHD double radfield_J(const Tables& T, const double nu, const int cell) {
     }
   }
   return T.W[cell] * planck(nu, T.TR[cell]);
+}
+
+// Photoionisation rate coefficient, corrected for stimulated recombination, as an integral of the cross-section over the
+// cell's radiation field model (ratecoeff.cc:460-520 calculate_corrphotoioncoeff_integral with its integrand 460-478): the
+// correction factor is built from the cell's own level populations and T_e; integrated with the reference's adaptive
+// 61-point Gauss-Kronrod rule to epsrel 1e-3 (integrator.h:48-64) in the reference's operation order.
+AHD double corrphotoioncoeff_integral(const Tables& T, const int cell, const int element, const int ion, const int level,
+                                      const int phixstargetindex) {
+  constexpr double epsrel = 1e-3;
+  const int ulev = uniquelevel(T, element, ion, level);
+  const double nu_threshold = (1. / H) * phixs_threshold(T, element, ion, level, phixstargetindex);
+  const double nu_max_phixs = nu_threshold * T.last_phixs_nuovernuedge;
+  const auto T_e = T.Te[cell];
+  const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
+  const double nnlevel = cellpops[ulev];
+  const auto clumpednne = T.nne[cell] * T.clumpfactor[cell];
+  const int upperionlevel = phixsupperlevel(T, ulev, phixstargetindex);
+  const int upperulev = uniquelevel(T, element, ion + 1, upperionlevel);
+  const double modified_sahafact = SAHACONST * statw(T, ulev) / statw(T, upperulev) * pow(static_cast<double>(T_e), -1.5);
+  const double nnupperionlevel = cellpops[upperulev];
+  double modified_departure_ratio = (nnlevel > 0.) ? nnupperionlevel / nnlevel * clumpednne * modified_sahafact : 1.;
+  if (!std::isfinite(modified_departure_ratio)) {
+    modified_departure_ratio = 0.;
+  }
+  const float* photoion_xs = phixs_table(T, ulev);
+  const auto integrand = [&](const double nu_minus_nu_edge) {
+    double corrfactor = 1. - (modified_departure_ratio * exp(-HOVERKB * nu_minus_nu_edge / T_e));
+    if (corrfactor < 0) {
+      corrfactor = 0.;
+    }
+    const float sigma_bf = photoionisation_crosssection_fromtable(T, photoion_xs, nu_threshold, nu_minus_nu_edge + nu_threshold);
+    const double Jnu = radfield_J(T, nu_minus_nu_edge + nu_threshold, cell);
+    return (1. / H) * sigma_bf / (nu_minus_nu_edge + nu_threshold) * Jnu * corrfactor;
+  };
+  return (4 * PI) * phixsprobability(T, ulev, phixstargetindex) * gk_integrate<61>(integrand, 0., nu_max_phixs - nu_threshold, epsrel);
 }
 
 // std::upper_bound / lower_bound index helpers over plain arrays (sn3d.h:85-101)

@@ -610,6 +610,25 @@ class Engine {
       rec.capacity_bytes = nbytes;
       T.cont_static = static_cast<const ContStatic*>(rec.dptr);
     }
+    // bound-free estimator slot of every (level, target): the inverse of the continuum list (radfield.cc:443-454, 628-640)
+    std::vector<int> phixstarget_bfestimindex(static_cast<size_t>(T.nphixstargets_total > 0 ? T.nphixstargets_total : 1), -1);
+    {
+      const auto* c_ulev = host<int>("cont.uniquelevelindex");
+      const auto* c_target = host<int>("cont.phixstargetindex");
+      const auto* c_bfestim = host<int>("cont.bfestimindex");
+      const auto* l_targetstart = host<int>("level.phixstargetstart");
+      if (c_bfestim != nullptr && c_target != nullptr && l_targetstart != nullptr) {
+        for (int i = 0; i < T.nbfcontinua; i++) {
+          const long long slot = static_cast<long long>(l_targetstart[c_ulev[i]]) + c_target[i];
+          if (slot >= 0 && slot < T.nphixstargets_total) {
+            phixstarget_bfestimindex[static_cast<size_t>(slot)] = c_bfestim[i];
+          }
+        }
+      }
+    }
+    if (!make_derived("derived.phixstarget_bfestimindex", phixstarget_bfestimindex, &T.phixstarget_bfestimindex)) {
+      return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
+    }
     if (!make_derived("derived.ion_element", ion_element, &T.ion_element) ||
         !make_derived("derived.ion_index", ion_index, &T.ion_index) ||
         !make_derived("derived.elem_has_nlte_levels", elem_has_nlte, &T.elem_has_nlte_levels) ||
@@ -761,10 +780,12 @@ class Engine {
         return fail("begin_timestep: the cell.nt_* arrays (non-thermal routing state, NT_ON) are missing or have the wrong length");
       }
     }
-    if constexpr (!opt::USE_LUT_PHOTOION) {
-      if (count_of("cell.corrphotoioncoeff") != static_cast<int64_t>(T.ncells) * T.nphixstargets_total) {
-        return fail("begin_timestep: cell.corrphotoioncoeff must hold ncells x (photoionisation targets) entries "
-                    "(USE_LUT_PHOTOION = false: evaluated by the host)");
+    if constexpr (!opt::USE_LUT_PHOTOION && opt::DETAILED_BF_ESTIMATORS_ON) {
+      // the normalised bound-free rate estimators of the previous timestep (radfield.cc:95, 923), read by the photoionisation
+      // coefficients from DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP on (ratecoeff.cc:848-851)
+      if (count_of("radfield.prev_bfrate_normed") != static_cast<int64_t>(T.ncells) * T.nbfestim) {
+        return fail("begin_timestep: radfield.prev_bfrate_normed must hold ncells x (bound-free estimators) entries "
+                    "(DETAILED_BF_ESTIMATORS_ON)");
       }
     }
     if constexpr (opt::RPKT_USE_EXPANSION_OPACITIES) {

@@ -9,6 +9,7 @@ constexpr bool USE_RELATIVISTIC_DOPPLER_SHIFT = false;
 constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = true;
 constexpr bool USE_LUT_PHOTOION = true;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = true;
+constexpr int DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP = 13;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = false;
 constexpr bool MULTIBIN_RADFIELD_MODEL_ON = false;
 constexpr int RADFIELDBINCOUNT = 256;

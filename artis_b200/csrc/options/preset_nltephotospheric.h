@@ -10,6 +10,7 @@ constexpr bool USE_RELATIVISTIC_DOPPLER_SHIFT = false;
 constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = false;
 constexpr bool USE_LUT_PHOTOION = false;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = false;
+constexpr int DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP = 13;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = true;
 constexpr bool MULTIBIN_RADFIELD_MODEL_ON = true;
 constexpr int RADFIELDBINCOUNT = 256;

@@ -101,6 +101,7 @@ namespace ab {
   X(double, ion_cooling_contribs, "cell.ion_cooling_contribs")        \
   X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
   X(double, corrphotoioncoeff_host, "cell.corrphotoioncoeff")       \
+  X(float, prev_bfrate_normed, "radfield.prev_bfrate_normed")       \
   X(double, nltepops, "cell.nltepops")                              \
   X(double, nt_ionisation_ratecoeff, "cell.nt_ionisation_ratecoeff") \
   X(double, nt_ion_energyrate, "cell.nt_ion_energyrate")            \
@@ -372,6 +373,9 @@ struct Tables {
   const int* ion_index;         // [nions] ion index within its element
   const int* elem_has_nlte_levels;  // [nelements]
   const ContStatic* cont_static;  // [nbfcontinua]
+  // bound-free estimator slot of every (level, photoionisation target), -1 = none (radfield.cc:443-454 get_allcontindex ->
+  // allcont.bfestimindex), indexed by level.phixstargetstart + target
+  const int* phixstarget_bfestimindex;  // [nphixstargets_total]
   CellCont* cell_cont_pack;       // [ncells][nbfcontinua], written by the per-cell table build
   // The kept continua of every cell as a list (ascending continuum index = ascending edge frequency), and the number of
   // kept continua below each 64-continuum word of the keep-bitmap: the kept continua of a frequency window are then a

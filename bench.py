@@ -31,10 +31,69 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
+# --workload: BASELINE.json configs. The bench line the driver reads is the default one (configs[1], the configuration the
+# metric is quoted on); the others are the same measurement on the other configurations (lines kept under profiles/).
+WORKLOADS = {
+    "kilonova_2d": dict(
+        preset="kilonova_lte", ts=2, cpu_config="kilonova_2d_cpu",
+        workload="kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1])", model_grid="2D cylindrical 50 x 100",
+        atomic_data="synthetic, 5 elements x 4 ions x 120 levels (54 892 lines, 1 475 bound-free continua)"),
+    "classic_1d3d": dict(
+        preset="classic", ts=4, cpu_config="classic_1d3d_cpu",
+        workload="classic LTE W7-like 1D model on a 3D Cartesian 100^3 grid, 1e5 packets (BASELINE configs[0])",
+        model_grid="1D model, 100 shells, on a 3D Cartesian 100^3 propagation grid",
+        atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
+    "asym3d": dict(
+        preset="classic", ts=4, cpu_config="asym3d_cpu",
+        workload="3D Cartesian asymmetric SN Ia model, classic macro-atom mode (BASELINE configs[2]; 1e6 packets per run, ~2.6e4 interactions per packet and timestep)",
+        model_grid="3D Cartesian 100^3 (ellipsoidal density with an off-centre Ni blob)",
+        atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
+    "gamma_3d50": dict(
+        preset="classic", ts=1, cpu_config="gamma_3d50_cpu",
+        workload="gamma-packet-only Ni56/Co56 deposition run (Compton/photoelectric/pair) on a 3D 50^3 grid, every cell grey "
+                 "for r-packets (BASELINE configs[3]; 1e7 packets per run)",
+        model_grid="3D Cartesian 50^3", atomic_data="synthetic, 3 elements x 3 ions x 6 levels (93 lines)"),
+}
 WORKLOAD = os.environ.get("ARTISB200_BENCH_CONFIG", "kilonova_2d")
 PRESET = "kilonova_lte"
 BENCH_TS = int(os.environ.get("ARTISB200_BENCH_TS", "2"))
 CPU_SAMPLE_CONFIG = os.environ.get("ARTISB200_BENCH_CPU_CONFIG", "kilonova_2d_cpu")
+
+
+def select_workload(name):
+    global WORKLOAD, PRESET, BENCH_TS, CPU_SAMPLE_CONFIG
+    if name not in WORKLOADS:
+        raise SystemExit(f"unknown workload {name!r}; known: {sorted(WORKLOADS)}")
+    w = WORKLOADS[name]
+    WORKLOAD = name
+    PRESET = w["preset"]
+    BENCH_TS = int(os.environ.get("ARTISB200_BENCH_TS", str(w["ts"])))
+    CPU_SAMPLE_CONFIG = os.environ.get("ARTISB200_BENCH_CPU_CONFIG", w["cpu_config"])
+
+
+def make_rundir(config, builddir, rundir):
+    """a fresh run folder of `config`: the input files written at build time (builddir/inputs) or, for the models too large
+    to keep in the tree, generated here once; large read-only files are linked, input.txt is copied (it gets edited)"""
+    import gen_inputs
+    inputs = os.path.join(builddir, "inputs")
+    if not os.path.isdir(inputs):
+        inputs = os.path.join(CACHE, f"inputs_{config}")
+        if not os.path.isdir(inputs):
+            log(f"writing the input files of {config} ...")
+            gen_inputs.generate(config, inputs + ".tmp")
+            os.replace(inputs + ".tmp", inputs)
+    if os.path.isdir(rundir):
+        shutil.rmtree(rundir)
+    os.makedirs(rundir)
+    for f in os.listdir(inputs):
+        src = os.path.join(inputs, f)
+        if f == "data":
+            continue
+        if f == "input.txt" or os.path.getsize(src) < (1 << 20):
+            shutil.copy(src, os.path.join(rundir, f))
+        else:
+            os.symlink(os.path.abspath(src), os.path.join(rundir, f))
+    os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
 FLAVOR = os.environ.get("ARTISB200_BENCH_FLAVOR", "fast")
 CPU_FLAVOR = os.environ.get("ARTISB200_BENCH_CPU_FLAVOR", "fast")
 # several GB of snapshots and run folders: outside the repository tree
@@ -62,10 +121,7 @@ def prepare_workload(device=0):
     if not os.path.exists(binary):
         raise RuntimeError(f"{binary} missing (python __graft_entry__.py build in the development container)")
     rundir = os.path.join(CACHE, f"{WORKLOAD}_run")
-    if os.path.isdir(rundir):
-        shutil.rmtree(rundir)
-    shutil.copytree(os.path.join(bdir, "inputs"), rundir)
-    os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
+    make_rundir(WORKLOAD, bdir, rundir)
     # run only timesteps 0..BENCH_TS
     inp = os.path.join(rundir, "input.txt")
     lines = open(inp).read().split("\n")
@@ -146,11 +202,15 @@ def algorithmic_bytes(diag, counters, log2_lines, nions, mean_ncoolingterms_log2
     return b
 
 
-def bench_config(npackets=10000000):
-    """the workload both arms are quoted on (BASELINE.json configs[1]); identical in the two arms' JSON lines"""
-    return {"workload": f"{WORKLOAD}: kilonova LTE 2D cylindrical r-process ejecta (BASELINE configs[1]), timestep {BENCH_TS}",
-            "packets_per_gpu": int(npackets), "timestep": BENCH_TS, "model_grid": "2D cylindrical 50 x 100",
-            "atomic_data": "synthetic, 5 elements x 4 ions x 120 levels (54 892 lines, 1 475 bound-free continua)",
+def bench_config(npackets=None):
+    """the workload both arms are quoted on; identical in the two arms' JSON lines"""
+    import configs as _configs
+    w = WORKLOADS[WORKLOAD]
+    if npackets is None:
+        npackets = int(_configs.get(WORKLOAD)["opts"]["constexpr int MPKTS"].split("=")[1].strip(" ;"))
+    return {"workload": f"{WORKLOAD}: {w['workload']}, timestep {BENCH_TS}",
+            "packets_per_gpu": int(npackets), "timestep": BENCH_TS, "model_grid": w["model_grid"],
+            "atomic_data": w["atomic_data"],
             "l2_policy": "inputs larger than L2 (packet records + per-cell tables > 126 MB)"}
 
 
@@ -163,6 +223,8 @@ def dram_traffic_profile():
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per stage kernel and step, from the committed ncu pass over
     every launch of one full-size step (profiles/r2_dram_traffic.json, written by tools/ncu_dram_traffic.py)"""
     path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if WORKLOAD != "kilonova_2d":
+        return None  # the committed ncu pass is of the default workload
     if os.path.exists(path):
         return json.load(open(path))
     return None
@@ -211,6 +273,12 @@ def run_ours(args):
     if 0 < n_sub < n:
         before["packets.aos"] = before["packets.aos"][: n_sub * stride].copy()
         n = n_sub
+    if args.scaling == "strong" and world > 1:
+        # strong scaling: the workload's packets are divided among the ranks (the reference divides MPKTS among its MPI ranks
+        # the same way when the total is fixed), tables replicated
+        per = n // world
+        before["packets.aos"] = before["packets.aos"][rank * per * stride:(rank + 1) * per * stride].copy()
+        n = per
 
     eng = ablib.ArtisB200(preset=PRESET, device=local_rank)
     eng.set_option("rng_mode", 0)
@@ -322,7 +390,8 @@ def run_ours(args):
     t_prop = sum(prop_ms) / len(prop_ms)
     t_e2e = sum(e2e_ms) / len(e2e_ms)
     n_int = sum(interactions) / len(interactions)
-    vals = torch.tensor([t_step, t_prop, t_e2e, n_int], dtype=torch.float64, device="cuda")
+    n_gamma = float(diag_sum[9]) / len(step_ms)
+    vals = torch.tensor([t_step, t_prop, t_e2e, n_int, n_gamma], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = vals.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -330,8 +399,10 @@ def run_ours(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         t_step, t_prop, t_e2e = (float(x) for x in tmax[:3])
         n_int_total = float(tsum[3])
+        n_gamma_total = float(tsum[4])
     else:
         n_int_total = n_int
+        n_gamma_total = n_gamma
 
     if rank == 0:
         nlines = static["line.nu"].size
@@ -367,7 +438,7 @@ def run_ours(args):
         out = {
             "metric": "packet-interactions/sec per timestep", "value": n_int_total / (t_step * 1e-3), "unit": "interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(n),
             "workload_details": {"model_cells": int(ncells), "lines": int(nlines), "levels": int(static["level.epsilon"].size),
                                  "bf_continua": int(static["cont.nu_edge"].size), "rng": "philox4x32-10",
@@ -392,8 +463,13 @@ def run_ours(args):
             "clocks": clock_summary,
             "work_counters": {k: int(diag_mean[i]) for i, k in enumerate(
                 ["rpkt_steps", "lines_visited", "cont_evals", "cont_terms", "binsearch_probes", "estimator_adds", "ma_steps",
-                 "k_steps", "gamma_steps", "gamma_events", "launches", "packet_segments"])},
+                 "k_steps", "gamma_steps", "gamma_events", "launches", "packet_segments", "table_passes"])},
         }
+        # gamma transport does not touch the reference's INTERACTIONS counter, so the gamma-only configuration
+        # is quoted in physical gamma events (Compton / photoelectric / pair, gammapkt.cc:720-747) per second as well
+        out["gamma_events_per_s"] = n_gamma_total / (t_step * 1e-3)
+        out["table_windows"] = {"passes_per_step": int(diag_mean[12]), "cells": int(ncells),
+                                "note": "1 = the per-cell tables of every cell are resident; > 1 = cell-batched tables"}
         if not args.no_cpu_baseline and world == 1:
             try:
                 # same model, same timestep, independent random numbers: the two codes must agree within Monte Carlo noise
@@ -446,10 +522,7 @@ def cpu_reference_setup(nproc, rundir_root):
     rundirs = []
     for r in range(nproc):
         rundir = os.path.join(rundir_root, f"cpu_rank{r}")
-        if os.path.isdir(rundir):
-            shutil.rmtree(rundir)
-        shutil.copytree(os.path.join(odir, "inputs"), rundir)
-        os.symlink(os.path.join(ROOT, "oracle", "_ref", "data"), os.path.join(rundir, "data"))
+        make_rundir(CPU_SAMPLE_CONFIG, odir, rundir)
         _set_input_line(os.path.join(rundir, "input.txt"), 0, f"{20260101 + 1000 * r}")
         rundirs.append(rundir)
     return rundirs, binary
@@ -509,8 +582,9 @@ def cpu_baseline(gpu_interactions_per_packet=None):
     interactions per packet of the GPU step against the K CPU samples (mean, standard error, z)."""
     root = os.path.join(CACHE, "cpu_baseline")
     os.makedirs(root, exist_ok=True)
+    import configs as _configs
     k = max(1, min(8, os.cpu_count() or 1))
-    npk = 100000
+    npk = int(_configs.get(CPU_SAMPLE_CONFIG)["opts"]["constexpr int MPKTS"].split("=")[1].strip(" ;"))
     prepared = cpu_restart_from_gpu_state(k, root, npk)
     if prepared is not None:
         rundirs, binary = prepared
@@ -536,7 +610,7 @@ def cpu_baseline(gpu_interactions_per_packet=None):
         cross["interactions_per_packet_gpu"] = gpu_interactions_per_packet
         if len(per_packet) > 1 and sd > 0:
             z = (gpu_interactions_per_packet - mean) / (sd / len(per_packet) ** 0.5)
-            cross.update(z=z, criterion="|z| < 4 (GPU mean of 1e7 packets against the mean of the CPU seeds, standard error from "
+            cross.update(z=z, criterion="|z| < 4 (GPU mean over all its packets against the mean of the CPU seeds, standard error from "
                                         "the scatter between the seeds)", passed=bool(abs(z) < 4.0))
     return out, cross
 
@@ -591,7 +665,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-step", action="store_true", help="profiling aid: run exactly one device step and exit (no JSON line)")
+    ap.add_argument("--workload", default=os.environ.get("ARTISB200_BENCH_CONFIG", "kilonova_2d"), choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU propagates the workload's packet count; strong: the packets are divided among the GPUs")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

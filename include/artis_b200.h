@@ -58,10 +58,15 @@
  *       nt_exc_ratecoeffperdeposition 'd' [Nc*stored], cell.nt_deposition_rate_density 'd'[Nc], cell.nt_frac_excitation 'f'[Nc]
  *       (NT_EXCITATION_ON only): nonthermal.cc:202-212, 364-367, 2382-2385, 1186-1195
  *   radfield.bin_W/bin_T_R 'f'[Nc*RADFIELDBINCOUNT]  (MULTIBIN_RADFIELD_MODEL_ON only) radfield.cc:78-79, read by radfield() 786-797
- *   cell.corrphotoioncoeff 'd'[Nc*(total photoionisation targets)], indexed by level.phixstargetstart + target
- *       (USE_LUT_PHOTOION == false only): the corrected photoionisation coefficient of every continuum in the cell's
- *       radiation field, ratecoeff.cc:840 get_corrphotoioncoeff (the integral the reference keeps in its cell cache),
- *       evaluated by the host for the timestep (integration/update_packets_b200.cc)
+ *   radfield.prev_bfrate_normed 'f'[Nc*bfestimcount]  (USE_LUT_PHOTOION == false with DETAILED_BF_ESTIMATORS_ON only)
+ *       radfield.cc:95, 923: the normalised bound-free rate estimators of the previous timestep. From
+ *       DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP on they are the corrected photoionisation coefficients of the continua that
+ *       have an estimator (ratecoeff.cc:848-851); every other coefficient of this mode is evaluated ON THE DEVICE as the
+ *       integral of the cross-section over the cell's radiation field model with the reference's adaptive 61-point
+ *       Gauss-Kronrod rule (ratecoeff.cc:460-520), read back as built.corrphotoioncoeff
+ *   cell.corrphotoioncoeff 'd'[Nc*(total photoionisation targets)]  optional, NOT read by the kernels: the same
+ *       coefficients as the reference's own get_corrphotoioncoeff evaluates them (ratecoeff.cc:840), written into the
+ *       oracle snapshots as known-answer vectors for built.corrphotoioncoeff
  *   cell.expansionopacities 'f'[Nc*1997]  (RPKT_USE_EXPANSION_OPACITIES only) rpkt.h:47: bound-bound opacity [cm^2/g] per
  *       20-Angstrom wavelength bin from 60 to 40000 Angstrom (rpkt.h:23-44), written by calculate_expansion_opacities
  *       (rpkt.cc:1071-1123) in update_grid; read by get_possible_event_expansion_opacity (rpkt.cc:221-320)

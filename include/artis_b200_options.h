@@ -24,6 +24,7 @@ constexpr bool PHIXS_CLASSIC_NO_INTERPOLATION = ::PHIXS_CLASSIC_NO_INTERPOLATION
 constexpr bool USE_LUT_PHOTOION = ::USE_LUT_PHOTOION;
 constexpr bool USE_ION_BFHEATING_ESTIMATORS = ::USE_ION_BFHEATING_ESTIMATORS;
 constexpr bool DETAILED_BF_ESTIMATORS_ON = ::DETAILED_BF_ESTIMATORS_ON;
+constexpr int DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP = ::DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP;
 constexpr bool MULTIBIN_RADFIELD_MODEL_ON = ::MULTIBIN_RADFIELD_MODEL_ON;
 constexpr int RADFIELDBINCOUNT = ::RADFIELDBINCOUNT;
 constexpr int FIRST_NLTE_RADFIELD_TIMESTEP = ::FIRST_NLTE_RADFIELD_TIMESTEP;
@@ -76,7 +77,7 @@ constexpr bool HAS_NLTE_LEVELS = any_ion_has_excited_nlte_levels();
   X(BFCOOLING_USELEVELPOPNOTIONPOP) X(RPKT_USE_EXPANSION_OPACITIES) X(HAS_BB_THERMALISATION_PROBABILITY)                 \
   X(BB_THERMALISATION_PROBABILITY) X(USE_XCOM_GAMMAPHOTOION) X(HAS_GAMMA_KAPPA_GREY) X(GAMMA_KAPPA_GREY)                 \
   X(FORCE_SPHERICAL_ESCAPE_SURFACE) X(PARTICLE_THERMALISATION_SCHEME) X(GAMMA_THERMALISATION_SCHEME) X(MINPOP)           \
-  X(NU_MIN_R) X(NU_MAX_R) X(HAS_NLTE_LEVELS)
+  X(NU_MIN_R) X(NU_MAX_R) X(HAS_NLTE_LEVELS) X(DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP)
 
 /* FNV-1a over the option values as IEEE doubles, in list order (the preset NAME is not part of it) */
 inline std::uint64_t artisb200_options_hash_here() {

@@ -33,6 +33,7 @@ auto b200_nuJ() -> std::span<double>;
 auto b200_bins_J_raw() -> std::span<double>;
 auto b200_bins_nuJ_raw() -> std::span<double>;
 auto b200_bfrate_raw() -> std::span<double>;
+auto b200_prev_bfrate_normed() -> std::span<const float>;
 auto b200_bin_solutions_W() -> std::span<const float>;
 auto b200_bin_solutions_T_R() -> std::span<const float>;
 }  // namespace radfield

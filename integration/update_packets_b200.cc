@@ -41,6 +41,7 @@
 #include <limits>
 #include <span>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "artis_b200.h"
@@ -288,9 +289,16 @@ void emit_timestep_state(Sink& s, const int nts) {
         static_cast<int64_t>(kpkt::ion_cooling_contribs_allcells.size()));
   s.arr("cell.corrphotoionrenorm", globals::corrphotoionrenorm.data(),
         static_cast<int64_t>(globals::corrphotoionrenorm.size()));
-  if constexpr (!USE_LUT_PHOTOION) {
-    // corrected photoionisation rate coefficients without the LUT (ratecoeff.cc:840-875): the previous timestep's
-    // bound-free rate estimators or an integral over the radiation field model, i.e. solver state of the host
+  if constexpr (!USE_LUT_PHOTOION && DETAILED_BF_ESTIMATORS_ON) {
+    // the previous timestep's normalised bound-free rate estimators (radfield.cc:95, 923): from
+    // DETAILED_BF_ESTIMATORS_USEFROMTIMESTEP on they are the photoionisation coefficients (ratecoeff.cc:848-851)
+    const auto prev = radfield::b200_prev_bfrate_normed();
+    s.arr("radfield.prev_bfrate_normed", prev.data(), static_cast<int64_t>(prev.size()));
+  }
+  if constexpr (!USE_LUT_PHOTOION && std::is_same_v<Sink, b200::SnapshotWriter>) {
+    // Oracle snapshots only (known-answer vectors; the library evaluates these itself on the device): the corrected
+    // photoionisation rate coefficients without the LUT as the reference's own get_corrphotoioncoeff gives them
+    // (ratecoeff.cc:840-875: the estimator above or an integral over the radiation field model)
     const int nlevels_total = get_includedlevels();
     std::vector<double> gammacorr;
     gammacorr.reserve(static_cast<size_t>(nc) * static_cast<size_t>(nlevels_total));

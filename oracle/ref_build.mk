@@ -48,7 +48,7 @@ $(OUT)/%.o: $(REF)/%.cc $(OUT)/artisoptions.h
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 $(OUT)/ref_%.o: $(ACCESS)/ref_%.cc $(OUT)/artisoptions.h
 	$(CXX) $(CXXFLAGS) -c $< -o $@
-$(OUT)/update_packets_b200.o: $(REPO)/integration/update_packets_b200.cc $(OUT)/artisoptions.h $(REPO)/include/artis_b200.h $(REPO)/integration/b200_snapshot.h
+$(OUT)/update_packets_b200.o: $(REPO)/integration/update_packets_b200.cc $(OUT)/artisoptions.h $(REPO)/include/artis_b200.h $(REPO)/include/artis_b200_options.h $(REPO)/integration/b200_snapshot.h $(ACCESS)/b200_access.h
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 $(OUT)/$(BIN): $(OBJS)

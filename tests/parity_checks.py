@@ -127,6 +127,14 @@ def check_packet_histories(libpath, config, nts, max_steps=0, min_exact_fraction
     if min_exact_fraction == 1.0:
         if check_tables and not (options or {}).get("table_window_cells"):  # (windowed tables hold one group of cells)
             check_cell_tables(built, after)
+            if "cell.corrphotoioncoeff" in fx["before"]:
+                # USE_LUT_PHOTOION = false: the photoionisation coefficients evaluated on the device (previous timestep's
+                # bound-free estimators / adaptive Gauss-Kronrod integral over the radiation field model) against the
+                # reference's own get_corrphotoioncoeff (ratecoeff.cc:840-875) for every (cell, level, target)
+                ref_gamma = fx["before"]["cell.corrphotoioncoeff"]
+                assert ref_gamma.size > 0 and np.count_nonzero(ref_gamma) > 0
+                err = _rel(built["built.corrphotoioncoeff"], ref_gamma)
+                assert err.max() <= 1e-10, f"built.corrphotoioncoeff differs from the reference's get_corrphotoioncoeff by {err.max():.3e}"
         assert_aggregates(config, est, after, est_err, est_tol)
     n_fb = n_fb_events
     return frac_ok, n_fb, est

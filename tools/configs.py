@@ -22,6 +22,9 @@ def _opts(mpkts, grid_override=None, cuboid=None, extra=None):
     return o
 
 
+import os
+
+_ASYM3D_N = int(os.environ.get("ARTISB200_ASYM3D_N", "100"))
 _FEGROUP = [(26, 55.845), (27, 58.9332), (28, 58.6934)]
 _CLASSIC_ELEMS = [(8, 15.999), (14, 28.085), (16, 32.06), (20, 40.078), (26, 55.845), (27, 58.9332), (28, 58.6934)]
 _KN_ELEMS = [(26, 55.845), (38, 87.62), (58, 140.116), (60, 144.242), (92, 238.029)]
@@ -176,7 +179,7 @@ CONFIGS = {
     "classic_1d3d": dict(
         preset="classic",
         opts=_opts(100000, "CARTESIAN3D", 100),
-        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, seed=20260101),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, seed=20260101),
         model=dict(kind="1d", ncell=100, vmax_kmps=25000.0, t_model_days=2.0, rho0=None, mass_msun=1.4,
                    v_e_kmps=2700.0, seed=20260101),
         run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=12, thick=8.0, ngrey=3, nlte_ts=5),
@@ -195,6 +198,69 @@ CONFIGS = {
     # few-packet probe of configs[1] used while tuning the synthetic atomic data (interactions per packet per timestep)
     "kilonova_2d_probe": dict(preset="kilonova_lte", opts=_opts(2000, None, None, _KN_LUT), atomic=_KN2D_ATOMIC, model=_KN2D_MODEL,
                       run=_KN2D_RUN),
+    # configs[2]: 3-D Cartesian 100^3 asymmetric SN Ia model (ellipsoidal density, off-centre Ni blob), classic macro-atom
+    # mode. 1e6 packets per run here (BASELINE: 4e7): in this optically thick phase an active packet takes ~2e5
+    # interactions per timestep (2.6e4 per packet averaged over all packets, most of which are still pellets), so 1e6 packets
+    # are 2.6e10 interactions per step - 25 times the kilonova step. Measured timestep 4: the last of the LTE start-up phase (the host's per-cell temperature solve from timestep 5 on costs ~1 ms per cell and timestep).
+    # ARTISB200_ASYM3D_N overrides the grid size (e.g. 40 for a quick look).
+    "asym3d": dict(
+        preset="classic",
+        opts=_opts(1000000),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, seed=20260101),
+        model=dict(kind="3d", n=_ASYM3D_N, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=12, thick=8.0, ngrey=3, nlte_ts=5),
+    ),
+    "asym3d_cpu": dict(
+        preset="classic",
+        opts=_opts(100000),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, seed=20260101),
+        model=dict(kind="3d", n=_ASYM3D_N, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=12, thick=8.0, ngrey=3, nlte_ts=5),
+    ),
+    # configs[3]: gamma-packet-only Ni56/Co56 deposition run on a 3-D 50^3 grid: early timesteps, in which the packets are
+    # pellets and gamma rays (Compton / photoelectric / pair transport and deposition); every cell grey for the r-packets
+    # (optical_depth_is_thick = 0, num_grey_timesteps = 999) so that they stay cheap, as SURVEY.md 8d prescribes
+    "gamma_3d50": dict(
+        preset="classic",
+        opts=_opts(10000000),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="3d", n=50, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=6, thick=0.0, ngrey=999, nlte_ts=999),
+    ),
+    "gamma_3d50_cpu": dict(
+        preset="classic",
+        opts=_opts(100000),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="3d", n=50, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=6, thick=0.0, ngrey=999, nlte_ts=999),
+    ),
+    # the stated stochastic test (tools/stochastic_ensemble.py): configs[0]'s model family and atomic data, 1e5 packets,
+    # twelve timesteps over the photospheric phase in which a large part of the packets escapes (spectrum, light curve)
+    "classic_spec": dict(
+        preset="classic",
+        opts=_opts(100000, "CARTESIAN3D", 40),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, A_perm_log10=(3.5, 7.0), seed=20260101),
+        model=dict(kind="1d", ncell=40, vmax_kmps=25000.0, t_model_days=2.0, rho0=None, mass_msun=0.3,
+                   v_e_kmps=3200.0, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=12, tmin=15.0, tmax=60.0, nts_run=12, thick=8.0, ngrey=2, nlte_ts=999),
+    ),
+    "classic_spec_probe": dict(
+        preset="classic",
+        opts=_opts(4000, "CARTESIAN3D", 40),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, A_perm_log10=(3.5, 7.0), seed=20260101),
+        model=dict(kind="1d", ncell=40, vmax_kmps=25000.0, t_model_days=2.0, rho0=None, mass_msun=0.3,
+                   v_e_kmps=3200.0, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=12, tmin=15.0, tmax=60.0, nts_run=12, thick=8.0, ngrey=2, nlte_ts=999),
+    ),
+    # configs[0] with the packet count of the CPU sample (the config itself is CPU-runnable: 1e5 packets)
+    "classic_1d3d_cpu": dict(
+        preset="classic",
+        opts=_opts(100000, "CARTESIAN3D", 100),
+        atomic=dict(elements=_CLASSIC_ELEMS, nions=4, nlevels=40, trans_frac=0.15, ionpot_dz=0.002, seed=20260101),
+        model=dict(kind="1d", ncell=100, vmax_kmps=25000.0, t_model_days=2.0, rho0=None, mass_msun=1.4,
+                   v_e_kmps=2700.0, seed=20260101),
+        run=dict(seed=20260101, ntimesteps=60, tmin=2.0, tmax=80.0, nts_run=12, thick=8.0, ngrey=3, nlte_ts=5),
+    ),
     "kilonova_2d_small": dict(preset="kilonova_lte", opts=_opts(200000, None, None, _KN_LUT), atomic=_KN2D_ATOMIC, model=_KN2D_MODEL,
                       run=_KN2D_RUN),
 }

@@ -28,9 +28,11 @@ NPHIXSPOINTS = 100
 NPHIXSNUINCREMENT = 0.1
 
 
-def ionpot_ev(Z, stage):
-    """smooth synthetic ionisation potential [eV] of ion `stage` (1 = neutral)"""
-    return 7.4 * stage**1.28 * (1.0 + 0.013 * (Z % 9))
+def ionpot_ev(Z, stage, dz=0.0):
+    """smooth synthetic ionisation potential [eV] of ion `stage` (1 = neutral). `dz` (config atomic.ionpot_dz) adds a term
+    that grows with Z: element sets in which two elements share Z % 9 (O and Fe) would otherwise get identical ionisation
+    edges, which the reference's ground-continuum search rejects (input.cc:703-747)"""
+    return 7.4 * stage**1.28 * (1.0 + 0.013 * (Z % 9) + dz * Z)
 
 
 def write_atomic(cfg, outdir):
@@ -51,7 +53,7 @@ def write_atomic(cfg, outdir):
     for Z, _amu in elements:
         for ion in range(nions):
             stage = ion + 1
-            ip = ionpot_ev(Z, stage)
+            ip = ionpot_ev(Z, stage, a.get("ionpot_dz", 0.0))
             # fewer levels in the higher ions, as in real data sets
             nlev = max(3, int(round(a["nlevels"] * (1.0 - 0.18 * ion))))
             en = [0.0] + sorted(rng.uniform(0.05, 0.82 * ip) for _ in range(nlev - 1))
@@ -279,8 +281,17 @@ def write_options(cfg, reference_dir, outpath):
         f.writelines(out)
 
 
-def generate(name, outdir, reference_dir=None, options_out=None, data_link=None):
+# configs whose model files are too large to keep in the tree (hundreds of MB for 1e6 cells): their run folders are
+# written where they are needed (bench.py on the GPU box, tools/run_oracle.py), not at build time
+LARGE_MODELS = {"asym3d", "asym3d_cpu", "gamma_3d50", "gamma_3d50_cpu"}
+
+
+def generate(name, outdir, reference_dir=None, options_out=None, data_link=None, options_only=False):
     cfg = configs.get(name)
+    if options_only:
+        os.makedirs(os.path.dirname(os.path.abspath(options_out)), exist_ok=True)
+        write_options(cfg, reference_dir, options_out)
+        return 0
     os.makedirs(outdir, exist_ok=True)
     nlines = write_atomic(cfg, outdir)
     {"1d": write_model_1d, "2d": write_model_2d, "3d": write_model_3d}[cfg["model"]["kind"]](cfg, outdir)
@@ -299,6 +310,8 @@ if __name__ == "__main__":
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--options-out", default=None)
     ap.add_argument("--data-link", default=None, help="directory to symlink as <outdir>/data (decay tables)")
+    ap.add_argument("--options-only", action="store_true", help="write artisoptions.h only (no run folder)")
     args = ap.parse_args()
-    n = generate(args.config, args.outdir, args.reference, args.options_out, args.data_link)
+    n = generate(args.config, args.outdir, args.reference, args.options_out, args.data_link,
+                 options_only=args.options_only or (args.config in LARGE_MODELS and args.options_out is not None))
     print(f"wrote {args.config} run folder to {args.outdir} ({n} lines in transitiondata)")
