@@ -123,6 +123,7 @@ __global__ void k_build_cooling(const __grid_constant__ Tables T) {
 // Packets are handed to the kernels in this order, so that the lanes of a warp start in the same cell and on the
 // same kind of packet (coalesced/broadcast table loads, same branch); it mirrors the reference's own sort of the
 // packets by cell before each pass (update_packets.cc:363-394, 570-572) without moving the packets.
+// (the sort kernels work on the packet range [first, first + n) of a wavefront instance; keys are indexed from 0)
 __device__ __forceinline__ int sort_bucket_of(const Tables& T, const long long i, const int nbuckets_per_stage) {
   const int stage = ab::stored_stage(T.pkt.hc[i]);
   if (stage < 0) {
@@ -132,11 +133,11 @@ __device__ __forceinline__ int sort_bucket_of(const Tables& T, const long long i
   return (stage * nbuckets_per_stage) + cell + 1;  // empty cells (-1) -> 0
 }
 
-__global__ void k_sort_count(const __grid_constant__ Tables T, const long long n, const int nbuckets_per_stage, int* keys,
-                             unsigned int* bucket_count) {
+__global__ void k_sort_count(const __grid_constant__ Tables T, const long long first, const long long n, const int nbuckets_per_stage,
+                             int* keys, unsigned int* bucket_count) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   if (i < n) {
-    const int b = sort_bucket_of(T, i, nbuckets_per_stage);
+    const int b = sort_bucket_of(T, first + i, nbuckets_per_stage);
     keys[i] = b;
     if (b >= 0) {
       // one atomic per group of equal keys in the warp (packets that arrive already sorted would otherwise serialise)
@@ -188,8 +189,8 @@ __global__ void k_sort_scan(unsigned int* bucket_count, unsigned int* bucket_sta
   }
 }
 
-__global__ void k_sort_scatter(const long long n, const int* keys, const unsigned int* bucket_start, unsigned int* bucket_cursor,
-                               int* order) {
+__global__ void k_sort_scatter(const long long first, const long long n, const int* keys, const unsigned int* bucket_start,
+                               unsigned int* bucket_cursor, int* order) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
   if (i < n) {
     const int b = keys[i];
@@ -202,7 +203,7 @@ __global__ void k_sort_scatter(const long long n, const int* keys, const unsigne
         base = atomicAdd(&bucket_cursor[b], static_cast<unsigned int>(__popc(peers)));
       }
       base = __shfl_sync(peers, base, leader);
-      order[bucket_start[b] + base + __popc(peers & ((1U << lane) - 1U))] = static_cast<int>(i);
+      order[bucket_start[b] + base + __popc(peers & ((1U << lane) - 1U))] = static_cast<int>(first + i);
     }
   }
 }
@@ -298,10 +299,10 @@ __device__ __forceinline__ void done_append(const WfQueues& q, const bool finish
 }
 
 // packets that are inactive from the start of the timestep (escaped earlier, or already at the end of the timestep)
-__global__ void k_done_seed(const __grid_constant__ Tables T, const WfQueues q, const long long n) {
+__global__ void k_done_seed(const __grid_constant__ Tables T, const WfQueues q, const long long first, const long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
-  const bool finished = (i < n) && (ab::stored_stage(T.pkt.hc[(i < n) ? i : 0]) == ab::ST_DONE);
-  done_append(q, finished, static_cast<int>(i));
+  const bool finished = (i < n) && (ab::stored_stage(T.pkt.hc[first + ((i < n) ? i : 0)]) == ab::ST_DONE);
+  done_append(q, finished, static_cast<int>(first + i));
 }
 
 // AoS records of the packets done[first, last) into staging slots [first, last): completion order
@@ -677,8 +678,13 @@ __global__ void k_rewindow(const __grid_constant__ Tables T, const long long n, 
 // "history" schedule that the wavefront is measured against.
 // queue[0]: next queue position to hand out; queue[1]: packets that still need work after this launch;
 // queue[2]: number of active packets in `order`
+// `lanes`: lanes per warp that take packets. With fewer active packets than the GPU has warp slots, the histories are
+// spread over the warps (one or a few lanes each) instead of being packed 32 to a warp: the lanes of a warp are in
+// different phases and branches of their histories, so a packed warp runs them largely one after the other, while
+// separate warps run side by side (classic 1D-on-3D model, 4025 active packets with ~3e5 interactions each: 14 s packed).
 __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant__ Tables T, const int* __restrict__ order,
-                                                          unsigned long long* queue, int* done, unsigned int* done_count) {
+                                                          unsigned long long* queue, int* done, unsigned int* done_count,
+                                                          const int lanes) {
   __shared__ ab::Accum acc;
   __shared__ unsigned int s_still_active;
   if (threadIdx.x == 0) {
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
   long long steps = 0;
   unsigned int hot[ab::Ctx::NHOT] = {};
   bool have = false;
-  bool exhausted = false;
+  bool exhausted = (static_cast<int>(threadIdx.x & 31U) >= lanes);
   while (true) {
     __syncwarp();
     if (!have && !exhausted) {
@@ -780,16 +786,11 @@ struct CudaBackend {
   cudaEvent_t ev_stop{nullptr};
   cudaEvent_t ev_sched0{nullptr};
   cudaEvent_t ev_sched1{nullptr};
-  unsigned long long* d_queue{nullptr};
+  // per-packet scratch shared by the wavefront instances (each works on its own slice, see WfInst)
   int* d_keys{nullptr};
   int* d_order{nullptr};
   long long sort_capacity{0};
-  unsigned int* d_bucket_count{nullptr};
-  unsigned int* d_bucket_start{nullptr};
-  int bucket_capacity{0};
-  unsigned int* d_stage_count{nullptr};  // [NSTAGES] list lengths of the cell-sorted order
-  unsigned int* d_wf_count{nullptr};     // [2][NSTAGES] list lengths + [NSTAGES] chunk cursors
-  int* d_wf_lists{nullptr};              // [2][NSTAGES][wf_capacity]
+  int* d_wf_lists{nullptr};              // per instance [2][NSTAGES][packets of the instance]
   // streamed download (update_packets_host with option stream_download): packets that have finished are converted to
   // the reference's Packet layout and copied to the host, in completion order, on the copy stream while the wavefront
   // goes on with the others
@@ -803,7 +804,6 @@ struct CudaBackend {
     long long min_chunk{262144};
   } stream_out;
   int* d_done{nullptr};
-  unsigned int* d_done_count{nullptr};
   long long done_capacity{0};
   long long wf_capacity{0};
   unsigned int* d_census{nullptr};  // [windows] packets waiting for each table window
@@ -861,28 +861,18 @@ struct CudaBackend {
     if (!ok(cudaEventCreate(&ev_tail0), "cudaEventCreate") || !ok(cudaEventCreate(&ev_tail1), "cudaEventCreate")) {
       return false;
     }
-    if (!ok(cudaMalloc(&d_queue, 8 * sizeof(unsigned long long)), "cudaMalloc(queue)") ||
-        !ok(cudaMalloc(&d_stage_count, ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(stage counts)") ||
-        !ok(cudaMalloc(&d_wf_count, 3 * ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(list counts)")) {
-      return false;
-    }
-    return true;
+    return init_instance(0);
   }
 
   void shutdown() {
     if (device >= 0) {
       cudaSetDevice(device);
       cudaStreamSynchronize(stream);
-      cudaFree(d_queue);
+      free_instances();
       cudaFree(d_keys);
       cudaFree(d_order);
-      cudaFree(d_bucket_count);
-      cudaFree(d_bucket_start);
-      cudaFree(d_stage_count);
-      cudaFree(d_wf_count);
       cudaFree(d_wf_lists);
       cudaFree(d_done);
-      cudaFree(d_done_count);
       cudaFree(d_census);
       for (cudaEvent_t e : stage_events) {
         cudaEventDestroy(e);
@@ -1069,20 +1059,13 @@ struct CudaBackend {
   }
 
   bool ensure_schedule_buffers(const Tables& T, const int64_t n, const bool wavefront) {
-    const int nbuckets = ab::NSTAGES * (T.ncells + 1);
+    (void)T;
     if (sort_capacity < n) {
       if (!grow(d_keys, static_cast<size_t>(n) * sizeof(int), "cudaMalloc(sort keys)") ||
           !grow(d_order, static_cast<size_t>(n) * sizeof(int), "cudaMalloc(sort order)")) {
         return false;
       }
       sort_capacity = n;
-    }
-    if (bucket_capacity < nbuckets) {
-      if (!grow(d_bucket_count, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)") ||
-          !grow(d_bucket_start, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)")) {
-        return false;
-      }
-      bucket_capacity = nbuckets;
     }
     if (wavefront && wf_capacity < n) {
       if (!grow(d_wf_lists, static_cast<size_t>(2 * ab::NSTAGES) * static_cast<size_t>(n) * sizeof(int), "cudaMalloc(stage lists)")) {
@@ -1093,32 +1076,170 @@ struct CudaBackend {
     return true;
   }
 
-  // copy what has finished since the last call (or, with `final`, whatever is left) to the host. Called at points where
-  // the main stream has been synchronised, so the done list up to `upto` and those packets' records are final.
-  bool flush_done(const Tables& T, const bool final) {
+  // ---- wavefront instances -------------------------------------------------------------------------------------
+  // The packets can be split into two halves that run the wavefront schedule side by side on their own streams, lists
+  // and counters (option wf_instances = 2). Every stage kernel ends with the latency of its slowest 32-packet chunk
+  // (0.1-0.3 ms of a 0.3-2 ms launch, ~500 launches per step); with two independent instances the drain of one
+  // instance's kernel is filled by the other instance's kernels instead of idling the GPU. Packet results do not
+  // depend on it (per-packet random number streams and caches).
+  struct WfInst {
+    cudaStream_t stream{nullptr};
+    cudaStream_t side[2]{nullptr, nullptr};
+    cudaEvent_t ev_fork{nullptr};
+    cudaEvent_t ev_join[2]{nullptr, nullptr};
+    cudaEvent_t ev_done{nullptr};
+    unsigned long long* d_queue{nullptr};      // [8]: sort/whole-history queue [0..3], wavefront status [4..5]
+    unsigned int* d_stage_count{nullptr};      // [NSTAGES]
+    unsigned int* d_wf_count{nullptr};         // [2][NSTAGES] list lengths + [NSTAGES] chunk cursors
+    unsigned int* d_bucket_count{nullptr};
+    unsigned int* d_bucket_start{nullptr};
+    int bucket_capacity{0};
+    unsigned int* d_done_count{nullptr};
+    unsigned long long* h_status{nullptr};     // pinned: [0..1] wavefront status, [2..5] whole-history queue
+    // views into the backend's per-packet scratch for the packet range [first, first + count)
+    long long first{0};
+    long long count{0};
+    int* keys{nullptr};
+    int* order{nullptr};
+    int* done{nullptr};
+    // run state
+    WfQueues q{};
+    int cur{0};
+    long long iteration{0};
+    unsigned long long waiting{0};
+    bool finished{false};
+    long long flushed{0};
+  };
+  WfInst inst[2];
+  bool inst_ready[2]{false, false};
+
+  bool init_instance(const int k) {
+    if (inst_ready[k]) {
+      return true;
+    }
+    WfInst& w = inst[k];
+    if (k == 0) {
+      w.stream = stream;
+      w.side[0] = side_stream[0];
+      w.side[1] = side_stream[1];
+      w.ev_fork = ev_fork;
+      w.ev_join[0] = ev_join[0];
+      w.ev_join[1] = ev_join[1];
+    } else if (!ok(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+               !ok(cudaStreamCreateWithFlags(&w.side[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
+               !ok(cudaStreamCreateWithFlags(&w.side[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
+               !ok(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming), "cudaEventCreate") ||
+               !ok(cudaEventCreateWithFlags(&w.ev_join[0], cudaEventDisableTiming), "cudaEventCreate") ||
+               !ok(cudaEventCreateWithFlags(&w.ev_join[1], cudaEventDisableTiming), "cudaEventCreate")) {
+      return false;
+    }
+    if (!ok(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming), "cudaEventCreate") ||
+        !ok(cudaMalloc(&w.d_queue, 8 * sizeof(unsigned long long)), "cudaMalloc(queue)") ||
+        !ok(cudaMalloc(&w.d_stage_count, ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(stage counts)") ||
+        !ok(cudaMalloc(&w.d_wf_count, 3 * ab::NSTAGES * sizeof(unsigned int)), "cudaMalloc(list counts)") ||
+        !ok(cudaMalloc(&w.d_done_count, sizeof(unsigned int)), "cudaMalloc(done count)") ||
+        !ok(cudaHostAlloc(&w.h_status, 8 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc(status)")) {
+      return false;
+    }
+    inst_ready[k] = true;
+    return true;
+  }
+
+  void free_instances() {
+    for (int k = 0; k < 2; k++) {
+      if (!inst_ready[k]) {
+        continue;
+      }
+      WfInst& w = inst[k];
+      cudaFree(w.d_queue);
+      cudaFree(w.d_stage_count);
+      cudaFree(w.d_wf_count);
+      cudaFree(w.d_bucket_count);
+      cudaFree(w.d_bucket_start);
+      cudaFree(w.d_done_count);
+      cudaFreeHost(w.h_status);
+      cudaEventDestroy(w.ev_done);
+      if (k > 0) {
+        cudaEventDestroy(w.ev_fork);
+        cudaEventDestroy(w.ev_join[0]);
+        cudaEventDestroy(w.ev_join[1]);
+        cudaStreamDestroy(w.side[0]);
+        cudaStreamDestroy(w.side[1]);
+        cudaStreamDestroy(w.stream);
+      }
+      inst_ready[k] = false;
+    }
+  }
+
+  // instance k propagates the packets [first, first + count); its lists and sort scratch are slices of the shared arrays
+  bool bind_instance(const int k, const Tables& T, const long long first, const long long count, const bool collect_done) {
+    if (!init_instance(k)) {
+      return false;
+    }
+    WfInst& w = inst[k];
+    const int nbuckets = ab::NSTAGES * (T.ncells + 1);
+    if (w.bucket_capacity < nbuckets) {
+      if (!grow(w.d_bucket_count, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)") ||
+          !grow(w.d_bucket_start, static_cast<size_t>(nbuckets) * sizeof(unsigned int), "cudaMalloc(buckets)")) {
+        return false;
+      }
+      w.bucket_capacity = nbuckets;
+    }
+    w.first = first;
+    w.count = count;
+    w.keys = d_keys + first;
+    w.order = d_order + first;
+    w.done = (d_done != nullptr) ? d_done + first : nullptr;
+    w.q = WfQueues{};
+    if (d_wf_lists != nullptr) {
+      int* base = d_wf_lists + (static_cast<size_t>(2 * ab::NSTAGES) * static_cast<size_t>(first));
+      for (int b = 0; b < 2; b++) {
+        for (int s = 0; s < ab::NSTAGES; s++) {
+          w.q.list[b][s] = base + (static_cast<size_t>((b * ab::NSTAGES) + s) * static_cast<size_t>(count));
+        }
+      }
+    }
+    w.q.count = w.d_wf_count;
+    w.q.cursor = w.d_wf_count + (2 * ab::NSTAGES);
+    w.q.status = w.d_queue + 4;
+    w.q.done = collect_done ? w.done : nullptr;
+    w.q.done_count = w.d_done_count;
+    w.cur = 0;
+    w.iteration = 0;
+    w.waiting = static_cast<unsigned long long>(count);
+    w.finished = false;
+    w.flushed = 0;
+    return true;
+  }
+
+  // copy what has finished in this instance since the last call (or, with `final`, whatever is left) to the host. Called
+  // at points where the instance's stream has been synchronised, so its done list up to `upto` and those packets' records
+  // are final.
+  bool flush_done(const Tables& T, WfInst& w, const bool final) {
     if (!stream_out.active) {
       return true;
     }
     unsigned int upto_u = 0U;
-    if (!ok(cudaMemcpyAsync(&upto_u, d_done_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream), "done count readback") ||
-        !ok(cudaStreamSynchronize(stream), "done count readback")) {
+    if (!ok(cudaMemcpyAsync(&upto_u, w.d_done_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, w.stream), "done count readback") ||
+        !ok(cudaStreamSynchronize(w.stream), "done count readback")) {
       return false;
     }
     const long long upto = upto_u;
-    if (final && upto != stream_out.total) {
-      error = "streamed download: " + std::to_string(upto) + " of " + std::to_string(stream_out.total) + " packets finished";
+    if (final && upto != w.count) {
+      error = "streamed download: " + std::to_string(upto) + " of " + std::to_string(w.count) + " packets finished";
       return false;
     }
-    const long long count = upto - stream_out.flushed;
+    const long long count = upto - w.flushed;
     if (count > 0 && (final || count >= stream_out.min_chunk)) {
-      const long long first = stream_out.flushed;
-      k_soa_to_aos_list<<<blocks_for(count, 256), 256, 0, copy_stream>>>(T, stream_out.staging, d_done, first, upto, stream_out.stride);
-      if (!ok(cudaMemcpyAsync(stream_out.host + (first * stream_out.stride), stream_out.staging + (first * stream_out.stride),
+      const long long lo = w.flushed;
+      unsigned char* staging = stream_out.staging + (w.first * stream_out.stride);
+      k_soa_to_aos_list<<<blocks_for(count, 256), 256, 0, copy_stream>>>(T, staging, w.done, lo, upto, stream_out.stride);
+      if (!ok(cudaMemcpyAsync(stream_out.host + ((w.first + lo) * stream_out.stride), staging + (lo * stream_out.stride),
                               static_cast<size_t>(count) * static_cast<size_t>(stream_out.stride), cudaMemcpyDeviceToHost, copy_stream),
               "cudaMemcpy D2H (finished packets)")) {
         return false;
       }
-      stream_out.flushed = upto;
+      w.flushed = upto;
     }
     if (final) {
       return ok(cudaStreamSynchronize(copy_stream), "streamed download") && ok(cudaGetLastError(), "k_soa_to_aos_list");
@@ -1134,9 +1255,6 @@ struct CudaBackend {
         return false;
       }
       done_capacity = n;
-    }
-    if (d_done_count == nullptr && !ok(cudaMalloc(&d_done_count, sizeof(unsigned int)), "cudaMalloc(done count)")) {
-      return false;
     }
     stream_out = StreamOut{};
     stream_out.active = true;
@@ -1157,54 +1275,68 @@ struct CudaBackend {
     return ok(cudaHostUnregister(ptr), "cudaHostUnregister");
   }
 
-  void sort_active(const Tables& T, const int64_t n) {
+  // counting sort of the instance's active packets by (stage, cell) into w.order
+  void sort_active(const Tables& T, WfInst& w) {
     const int nbuckets_per_stage = T.ncells + 1;
     const int nbuckets = ab::NSTAGES * nbuckets_per_stage;
-    cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
-    cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
-    k_sort_count<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, nbuckets_per_stage, d_keys, d_bucket_count);
-    k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, nbuckets_per_stage, d_queue, d_stage_count);
-    k_sort_scatter<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_keys, d_bucket_start, d_bucket_count, d_order);
+    cudaMemsetAsync(w.d_queue, 0, 4 * sizeof(unsigned long long), w.stream);
+    cudaMemsetAsync(w.d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), w.stream);
+    k_sort_count<<<blocks_for(w.count, 256), 256, 0, w.stream>>>(T, w.first, w.count, nbuckets_per_stage, w.keys, w.d_bucket_count);
+    k_sort_scan<<<1, 1024, 0, w.stream>>>(w.d_bucket_count, w.d_bucket_start, nbuckets, nbuckets_per_stage, w.d_queue, w.d_stage_count);
+    k_sort_scatter<<<blocks_for(w.count, 256), 256, 0, w.stream>>>(w.first, w.count, w.keys, w.d_bucket_start, w.d_bucket_count, w.order);
   }
 
   // lists of buffer `cur` -> sorted by (stage, cell) into buffer 0
-  void resort_lists(const Tables& T, const WfQueues& q, const int cur, const unsigned long long waiting) {
+  void resort_lists(const Tables& T, WfInst& w, const int cur) {
     const int nbuckets_per_stage = T.ncells + 1;
     const int nbuckets = ab::NSTAGES * nbuckets_per_stage;
-    unsigned int grid = static_cast<unsigned int>((waiting + 255ULL) / 256ULL);
+    unsigned int grid = static_cast<unsigned int>((w.waiting + 255ULL) / 256ULL);
     grid = (grid < 1U) ? 1U : ((grid > static_cast<unsigned int>(sm_count * 8)) ? static_cast<unsigned int>(sm_count * 8) : grid);
-    cudaMemsetAsync(d_queue, 0, 4 * sizeof(unsigned long long), stream);
-    cudaMemsetAsync(d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), stream);
-    k_list_count<<<grid, 256, 0, stream>>>(T, q, cur, nbuckets_per_stage, d_keys, d_bucket_count);
-    k_sort_scan<<<1, 1024, 0, stream>>>(d_bucket_count, d_bucket_start, nbuckets, nbuckets_per_stage, d_queue, d_stage_count);
-    k_list_scatter<<<grid, 256, 0, stream>>>(q, cur, d_keys, d_bucket_start, d_bucket_count, d_order);
-    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, stream>>>(q, d_order, d_stage_count);
+    cudaMemsetAsync(w.d_queue, 0, 4 * sizeof(unsigned long long), w.stream);
+    cudaMemsetAsync(w.d_bucket_count, 0, static_cast<size_t>(nbuckets) * sizeof(unsigned int), w.stream);
+    k_list_count<<<grid, 256, 0, w.stream>>>(T, w.q, cur, nbuckets_per_stage, w.keys, w.d_bucket_count);
+    k_sort_scan<<<1, 1024, 0, w.stream>>>(w.d_bucket_count, w.d_bucket_start, nbuckets, nbuckets_per_stage, w.d_queue, w.d_stage_count);
+    k_list_scatter<<<grid, 256, 0, w.stream>>>(w.q, cur, w.keys, w.d_bucket_start, w.d_bucket_count, w.order);
+    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, w.stream>>>(w.q, w.order, w.d_stage_count);
   }
 
-  // whole-history kernel over every packet that still needs work, relaunched while max_steps_per_launch leaves any
-  bool run_history(const Tables& T, const int64_t n, ab::PropagateTimings* tm) {
+  // whole-history kernel over every packet of the instance that still needs work, relaunched while
+  // max_steps_per_launch leaves any
+  bool run_history(const Tables& T, WfInst& w, ab::PropagateTimings* tm, const long long expected_active = -1) {
     if (history_blocks_per_sm == 0) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&history_blocks_per_sm, k_propagate, PROP_BLOCK, 0);
       history_blocks_per_sm = (history_blocks_per_sm < 1) ? 1 : history_blocks_per_sm;
     }
     long long nblocks = static_cast<long long>(sm_count) * history_blocks_per_sm;
-    const long long needed = (n + PROP_BLOCK - 1) / PROP_BLOCK;
+    // lanes per warp: all 32 when there are more active packets than lane slots, fewer (down to one) when the packets
+    // can be spread over the resident warps instead
+    const long long active = (expected_active >= 0) ? expected_active : w.count;
+    const long long warp_slots = nblocks * (PROP_BLOCK / 32);
+    int lanes = 32;
+    while (lanes > 1 && active <= warp_slots * (lanes / 2)) {
+      lanes /= 2;
+    }
+    const long long needed = ((active * (32 / lanes)) + PROP_BLOCK - 1) / PROP_BLOCK;
     nblocks = (nblocks > needed) ? needed : nblocks;
-    unsigned long long hq[4] = {0ULL, 1ULL, 0ULL, 0ULL};
+    nblocks = (nblocks < 1) ? 1 : nblocks;
+    unsigned long long* hq = w.h_status + 2;
+    hq[1] = 1ULL;
     while (hq[1] > 0ULL) {
-      cudaEventRecord(ev_sched0, stream);
-      sort_active(T, n);
-      cudaEventRecord(ev_sched1, stream);
-      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, stream>>>(T, d_order, d_queue, stream_out.active ? d_done : nullptr,
-                                                                                 d_done_count);
+      if (&w == &inst[0]) { cudaEventRecord(ev_sched0, w.stream); }
+      sort_active(T, w);
+      if (&w == &inst[0]) { cudaEventRecord(ev_sched1, w.stream); }
+      k_propagate<<<static_cast<unsigned int>(nblocks), PROP_BLOCK, 0, w.stream>>>(T, w.order, w.d_queue, stream_out.active ? w.done : nullptr,
+                                                                                   w.d_done_count, lanes);
       tm->launches += 4;
-      if (!ok(cudaMemcpyAsync(hq, d_queue, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "queue readback") ||
-          !ok(cudaStreamSynchronize(stream), "k_propagate")) {
+      if (!ok(cudaMemcpyAsync(hq, w.d_queue, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w.stream), "queue readback") ||
+          !ok(cudaStreamSynchronize(w.stream), "k_propagate")) {
         return false;
       }
-      float sms = 0.F;
-      cudaEventElapsedTime(&sms, ev_sched0, ev_sched1);
-      tm->schedule_ms += sms;
+      if (&w == &inst[0]) {
+        float sms = 0.F;
+        cudaEventElapsedTime(&sms, ev_sched0, ev_sched1);
+        tm->schedule_ms += sms;
+      }
       if (T.max_steps_per_launch <= 0 && hq[1] > 0ULL) {
         error = "k_propagate left active packets in whole-history mode";
         return false;
@@ -1212,6 +1344,8 @@ struct CudaBackend {
     }
     return true;
   }
+
+  int grid_div{1};  // two instances: each stage kernel may take a fraction of the resident blocks (wf_grid_div)
 
   template <int STAGE>
   void launch_stage(const Tables& T, const WfQueues& q, const int cur, const int next, const int next_ma, const int max_steps,
@@ -1221,7 +1355,8 @@ struct CudaBackend {
       stage_blocks_per_sm[STAGE] = (stage_blocks_per_sm[STAGE] < 1) ? 1 : stage_blocks_per_sm[STAGE];
     }
     // persistent grid: resident blocks per SM x SM count, fewer when the lists are short
-    unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]);
+    unsigned int grid = static_cast<unsigned int>(sm_count * stage_blocks_per_sm[STAGE]) / static_cast<unsigned int>(grid_div);
+    grid = (grid < static_cast<unsigned int>(sm_count)) ? static_cast<unsigned int>(sm_count) : grid;
     grid = (grid > grid_limit) ? grid_limit : grid;
     k_wf_stage<STAGE><<<grid, WF_BLOCK, 0, on>>>(T, q, cur, next, next_ma, max_steps);
   }
@@ -1248,26 +1383,126 @@ struct CudaBackend {
     }
   }
 
-  bool run_wavefront(const Tables& T, const int64_t n, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
-    WfQueues q{};
-    for (int b = 0; b < 2; b++) {
-      for (int s = 0; s < ab::NSTAGES; s++) {
-        q.list[b][s] = d_wf_lists + (static_cast<size_t>((b * ab::NSTAGES) + s) * static_cast<size_t>(wf_capacity));
+  // sort the instance's active packets and seed its stage lists
+  void wf_begin(const Tables& T, WfInst& w, ab::PropagateTimings* tm) {
+    if (&w == &inst[0]) { cudaEventRecord(ev_sched0, w.stream); }
+    sort_active(T, w);
+    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, w.stream>>>(w.q, w.order, w.d_stage_count);
+    if (&w == &inst[0]) { cudaEventRecord(ev_sched1, w.stream); }
+    tm->launches += 4;
+  }
+
+  // enqueue `sync_every` iterations of the instance and the read-back of its status (nothing blocks the host)
+  bool wf_enqueue(const Tables& T, WfInst& w, const ab::PropagateOptions& o, ab::PropagateTimings* tm, const bool timing) {
+    const int ma_rounds = (o.ma_rounds < 1) ? 1 : (o.ma_rounds | 1);  // odd: the last round writes to the next iteration's list
+    const int sync_every = (o.sync_every < 1) ? 1 : o.sync_every;
+    const WfQueues& q = w.q;
+    // every list of the coming iterations is at most as long as the number of packets waiting now
+    const unsigned long long bound = (w.waiting + WF_BLOCK - 1ULL) / WF_BLOCK;
+    const unsigned int grid_limit = static_cast<unsigned int>((bound < 1ULL) ? 1ULL : ((bound > 1048576ULL) ? 1048576ULL : bound));
+    for (int it = 0; it < sync_every; it++) {
+      cudaEvent_t* ev = timing ? &stage_events[static_cast<size_t>(it) * (ab::NSTAGES + 1)] : nullptr;
+      const int cur = w.cur;
+      const int next = cur ^ 1;
+      if (timing || o.concurrent == 0) {
+        if (timing) { cudaEventRecord(ev[0], w.stream); }
+        launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, w.stream);
+        if (timing) { cudaEventRecord(ev[1], w.stream); }
+        launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, w.stream);
+        if (timing) { cudaEventRecord(ev[2], w.stream); }
+        launch_thick(T, q, cur, next, o, grid_limit, w.stream);
+        if (timing) { cudaEventRecord(ev[3], w.stream); }
+      } else {
+        // the three stages read and append to different lists: run them side by side, so that the drain of one
+        // (its last, slowest chunks) overlaps with the bulk of the others; the macro-atom kernels wait for all three
+        cudaEventRecord(w.ev_fork, w.stream);
+        cudaStreamWaitEvent(w.side[0], w.ev_fork, 0);
+        cudaStreamWaitEvent(w.side[1], w.ev_fork, 0);
+        launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, w.stream);
+        launch_thick(T, q, cur, next, o, grid_limit, w.side[0]);
+        launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, w.side[1]);
+        cudaEventRecord(w.ev_join[0], w.side[0]);
+        cudaEventRecord(w.ev_join[1], w.side[1]);
+        cudaStreamWaitEvent(w.stream, w.ev_join[0], 0);
+        cudaStreamWaitEvent(w.stream, w.ev_join[1], 0);
+      }
+      // macro-atom walks: `ma_rounds` kernels of at most `masteps` transitions each, ping-ponging between the two
+      // macro-atom lists; what is still walking after the last round continues in the next iteration
+      if (o.refill_masteps > 0) {
+        // one kernel with lane refill; walks longer than the limit continue in the next iteration
+        launch_refill<ab::ST_MA>(T, q, cur, next, next, o.refill_masteps, grid_limit, w.stream);
+      } else {
+        int ma_in = cur;
+        for (int r = 0; r < ma_rounds; r++) {
+          launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit, w.stream);
+          if (r + 1 < ma_rounds) {
+            k_wf_ma_swap<<<1, 32, 0, w.stream>>>(q, ma_in);
+            ma_in ^= 1;
+          }
+        }
+      }
+      if (timing) { cudaEventRecord(ev[4], w.stream); }
+      k_wf_advance<<<1, 32, 0, w.stream>>>(q, cur);
+      w.cur ^= 1;
+      w.iteration++;
+      if (o.resort_every > 0 && (w.iteration % o.resort_every) == 0 && static_cast<long long>(w.waiting) >= o.resort_min_packets) {
+        // no host involvement: the lists of buffer `cur` are sorted into buffer 0 on the device
+        resort_lists(T, w, w.cur);
+        tm->launches += 4;
+        w.cur = 0;
       }
     }
-    q.count = d_wf_count;
-    q.cursor = d_wf_count + (2 * ab::NSTAGES);
-    q.status = d_queue + 4;
-    q.done = stream_out.active ? d_done : nullptr;
-    q.done_count = d_done_count;
-    cudaEventRecord(ev_sched0, stream);
-    sort_active(T, n);
-    k_wf_seed<<<static_cast<unsigned int>(sm_count * 4), 256, 0, stream>>>(q, d_order, d_stage_count);
-    cudaEventRecord(ev_sched1, stream);
-    tm->launches += 4;
+    tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + ((o.refill_masteps > 0) ? 1 : (2 * ma_rounds) - 1));
+    if (&w == &inst[0]) {
+      tm->iterations += sync_every;
+    }
+    return ok(cudaMemcpyAsync(w.h_status, w.q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w.stream), "status readback");
+  }
 
+  // wait for the instance's enqueued iterations; hands its last packets to the whole-history kernel
+  bool wf_collect(const Tables& T, WfInst& w, const ab::PropagateOptions& o, ab::PropagateTimings* tm, const bool timing,
+                  const long long tail_threshold) {
+    if (!ok(cudaStreamSynchronize(w.stream), "wavefront iteration")) {
+      return false;
+    }
+    w.waiting = w.h_status[0];
+    if (timing) {
+      const int sync_every = (o.sync_every < 1) ? 1 : o.sync_every;
+      for (int it = 0; it < sync_every; it++) {
+        for (int s = 0; s < ab::NSTAGES; s++) {
+          float ms = 0.F;
+          cudaEventElapsedTime(&ms, stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s],
+                               stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s + 1]);
+          tm->stage_ms[s] += ms;
+        }
+      }
+    }
+    if (!flush_done(T, w, false)) {
+      return false;
+    }
+    if (w.waiting == 0ULL) {
+      w.finished = true;
+      return true;
+    }
+    if (static_cast<long long>(w.waiting) <= tail_threshold) {
+      // thin tail: few packets with long histories; finish them with the whole-history kernel
+      cudaEventRecord(ev_tail0, w.stream);
+      tm->tail_packets += static_cast<long long>(w.waiting);
+      if (!run_history(T, w, tm, static_cast<long long>(w.waiting))) {
+        return false;
+      }
+      cudaEventRecord(ev_tail1, w.stream);
+      cudaEventSynchronize(ev_tail1);
+      float ms = 0.F;
+      cudaEventElapsedTime(&ms, ev_tail0, ev_tail1);
+      tm->tail_ms += ms;
+      w.finished = true;
+    }
+    return true;
+  }
+
+  bool run_wavefront(const Tables& T, const int ninst, const ab::PropagateOptions& o, ab::PropagateTimings* tm) {
     const bool timing = (o.stage_timing != 0);
-    const int ma_rounds = (o.ma_rounds < 1) ? 1 : (o.ma_rounds | 1);  // odd: the last round writes to the next iteration's list
     const int sync_every = (o.sync_every < 1) ? 1 : o.sync_every;
     if (timing && stage_events.size() < static_cast<size_t>(sync_every) * (ab::NSTAGES + 1)) {
       const size_t want = static_cast<size_t>(sync_every) * (ab::NSTAGES + 1);
@@ -1277,99 +1512,33 @@ struct CudaBackend {
         stage_events.push_back(e);
       }
     }
-    unsigned long long status[2] = {static_cast<unsigned long long>(n), 0ULL};
-    int cur = 0;
-    long long iteration = 0;
-    while (true) {
-      // every list of the coming iterations is at most as long as the number of packets waiting now
-      const unsigned long long bound = (status[0] + WF_BLOCK - 1ULL) / WF_BLOCK;
-      const unsigned int grid_limit = static_cast<unsigned int>((bound < 1ULL) ? 1ULL : ((bound > 1048576ULL) ? 1048576ULL : bound));
-      for (int it = 0; it < sync_every; it++) {
-        cudaEvent_t* ev = timing ? &stage_events[static_cast<size_t>(it) * (ab::NSTAGES + 1)] : nullptr;
-        const int next = cur ^ 1;
-        if (timing || o.concurrent == 0) {
-          if (timing) { cudaEventRecord(ev[0], stream); }
-          launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, stream);
-          if (timing) { cudaEventRecord(ev[1], stream); }
-          launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
-          if (timing) { cudaEventRecord(ev[2], stream); }
-          launch_thick(T, q, cur, next, o, grid_limit, stream);
-          if (timing) { cudaEventRecord(ev[3], stream); }
-        } else {
-          // the three stages read and append to different lists: run them side by side, so that the drain of one
-          // (its last, slowest chunks) overlaps with the bulk of the others; the macro-atom kernels wait for all three
-          cudaEventRecord(ev_fork, stream);
-          cudaStreamWaitEvent(side_stream[0], ev_fork, 0);
-          cudaStreamWaitEvent(side_stream[1], ev_fork, 0);
-          launch_stage<ab::ST_RTHIN>(T, q, cur, next, cur, o.rsteps_thin, grid_limit, stream);
-          launch_thick(T, q, cur, next, o, grid_limit, side_stream[0]);
-          launch_stage<ab::ST_OTHER>(T, q, cur, next, cur, 1, grid_limit, side_stream[1]);
-          cudaEventRecord(ev_join[0], side_stream[0]);
-          cudaEventRecord(ev_join[1], side_stream[1]);
-          cudaStreamWaitEvent(stream, ev_join[0], 0);
-          cudaStreamWaitEvent(stream, ev_join[1], 0);
-        }
-        // macro-atom walks: `ma_rounds` kernels of at most `masteps` transitions each, ping-ponging between the two
-        // macro-atom lists; what is still walking after the last round continues in the next iteration
-        if (o.refill_masteps > 0) {
-          // one kernel with lane refill; walks longer than the limit continue in the next iteration
-          launch_refill<ab::ST_MA>(T, q, cur, next, next, o.refill_masteps, grid_limit, stream);
-        } else {
-          int ma_in = cur;
-          for (int r = 0; r < ma_rounds; r++) {
-            launch_stage<ab::ST_MA>(T, q, ma_in, next, ma_in ^ 1, ab::ma_round_steps(o, r, ma_rounds), grid_limit, stream);
-            if (r + 1 < ma_rounds) {
-              k_wf_ma_swap<<<1, 32, 0, stream>>>(q, ma_in);
-              ma_in ^= 1;
-            }
-          }
-        }
-        if (timing) { cudaEventRecord(ev[4], stream); }
-        k_wf_advance<<<1, 32, 0, stream>>>(q, cur);
-        cur ^= 1;
-        iteration++;
-        if (o.resort_every > 0 && (iteration % o.resort_every) == 0 && static_cast<long long>(status[0]) >= o.resort_min_packets) {
-          // no host involvement: the lists of buffer `cur` are sorted into buffer 0 on the device
-          resort_lists(T, q, cur, status[0]);
-          tm->launches += 4;
-          cur = 0;
-        }
-      }
-      tm->launches += static_cast<long long>(sync_every) * (ab::NSTAGES + ((o.refill_masteps > 0) ? 1 : (2 * ma_rounds) - 1));
-      tm->iterations += sync_every;
-      if (!ok(cudaMemcpyAsync(status, q.status, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "status readback") ||
-          !ok(cudaStreamSynchronize(stream), "wavefront iteration")) {
+    const long long tail_threshold = o.tail_threshold / ninst;
+    for (int k = 0; k < ninst; k++) {
+      wf_begin(T, inst[k], tm);
+    }
+    for (int k = 0; k < ninst; k++) {
+      if (!wf_enqueue(T, inst[k], o, tm, timing)) {
         return false;
       }
-      if (timing) {
-        for (int it = 0; it < sync_every; it++) {
-          for (int s = 0; s < ab::NSTAGES; s++) {
-            float ms = 0.F;
-            cudaEventElapsedTime(&ms, stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s],
-                                 stage_events[(static_cast<size_t>(it) * (ab::NSTAGES + 1)) + s + 1]);
-            tm->stage_ms[s] += ms;
-          }
+    }
+    bool all_finished = false;
+    while (!all_finished) {
+      all_finished = true;
+      for (int k = 0; k < ninst; k++) {
+        WfInst& w = inst[k];
+        if (w.finished) {
+          continue;
         }
-      }
-      if (!flush_done(T, false)) {
-        return false;
-      }
-      if (status[0] == 0ULL) {
-        break;
-      }
-      if (static_cast<long long>(status[0]) <= o.tail_threshold) {
-        // thin tail: few packets with long histories; finish them with the whole-history kernel
-        cudaEventRecord(ev_tail0, stream);
-        tm->tail_packets = static_cast<long long>(status[0]);
-        if (!run_history(T, n, tm)) {
+        // (while the host waits here, the other instance still has its batch enqueued)
+        if (!wf_collect(T, w, o, tm, timing, tail_threshold)) {
           return false;
         }
-        cudaEventRecord(ev_tail1, stream);
-        cudaEventSynchronize(ev_tail1);
-        float ms = 0.F;
-        cudaEventElapsedTime(&ms, ev_tail0, ev_tail1);
-        tm->tail_ms = ms;
-        break;
+        if (!w.finished) {
+          if (!wf_enqueue(T, w, o, tm, timing)) {
+            return false;
+          }
+          all_finished = false;
+        }
       }
     }
     float sms = 0.F;
@@ -1384,16 +1553,30 @@ struct CudaBackend {
     if (!ensure_schedule_buffers(T, n, o.schedule == 1)) {
       return false;
     }
+    // two wavefront instances over the two halves of the packets (not while every stage kernel is being timed)
+    const int ninst = (o.schedule == 1 && o.instances >= 2 && o.stage_timing == 0 && n >= 64) ? 2 : 1;
+    grid_div = (ninst == 2 && o.grid_div >= 1) ? o.grid_div : 1;
+    const long long half = (ninst == 2) ? ((n / 2) / 32) * 32 : n;
+    if (!bind_instance(0, T, 0, half, stream_out.active) || (ninst == 2 && !bind_instance(1, T, half, n - half, stream_out.active))) {
+      return false;
+    }
     cudaEventRecord(ev_start, stream);
     k_reset_work<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
     tm->launches += 1;
+    if (ninst == 2) {
+      cudaEventRecord(inst[1].ev_done, stream);
+      cudaStreamWaitEvent(inst[1].stream, inst[1].ev_done, 0);
+    }
     if (stream_out.active) {
-      WfQueues dq{};
-      dq.done = d_done;
-      dq.done_count = d_done_count;
-      cudaMemsetAsync(d_done_count, 0, sizeof(unsigned int), stream);
-      k_done_seed<<<blocks_for(n, 256), 256, 0, stream>>>(T, dq, n);
-      tm->launches += 1;
+      for (int k = 0; k < ninst; k++) {
+        WfInst& w = inst[k];
+        WfQueues dq{};
+        dq.done = w.done;
+        dq.done_count = w.d_done_count;
+        cudaMemsetAsync(w.d_done_count, 0, sizeof(unsigned int), w.stream);
+        k_done_seed<<<blocks_for(w.count, 256), 256, 0, w.stream>>>(T, dq, w.first, w.count);
+        tm->launches += 1;
+      }
     }
     // Cell-batched per-cell tables: run the schedule on the packets whose cell is inside the table window, then move the
     // window to the next group of cells that has packets waiting (parked), rebuild the tables there and go on, until no
@@ -1411,7 +1594,17 @@ struct CudaBackend {
     int window = T.win_lo / ((window_cells > 0) ? window_cells : 1);
     while (true) {
       tm->table_passes++;
-      const bool good = (o.schedule == 1) ? run_wavefront(T, n, o, tm) : run_history(T, n, tm);
+      bool good = true;
+      if (o.schedule == 1) {
+        good = run_wavefront(T, ninst, o, tm);
+        if (good && ninst == 2) {
+          // the main stream carries on (window census, timing) after both instances
+          cudaEventRecord(inst[1].ev_done, inst[1].stream);
+          cudaStreamWaitEvent(stream, inst[1].ev_done, 0);
+        }
+      } else {
+        good = run_history(T, inst[0], tm);
+      }
       if (!good) {
         return false;
       }
@@ -1446,6 +1639,16 @@ struct CudaBackend {
       }
       k_rewindow<<<blocks_for(n, 256), 256, 0, stream>>>(T, n, window_cells, d_census);  // packets of this window join their stages
       tm->launches += 8;
+      for (int k = 0; k < ninst; k++) {
+        inst[k].finished = false;
+        inst[k].cur = 0;
+        inst[k].iteration = 0;
+        inst[k].waiting = static_cast<unsigned long long>(inst[k].count);
+      }
+      if (ninst == 2) {
+        cudaEventRecord(inst[1].ev_done, stream);
+        cudaStreamWaitEvent(inst[1].stream, inst[1].ev_done, 0);
+      }
     }
     cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &tm->launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(&T.diag[ab::DIAG_TABLE_PASSES], &tm->table_passes, sizeof(long long), cudaMemcpyHostToDevice, stream);
@@ -1454,8 +1657,10 @@ struct CudaBackend {
       return false;
     }
     tables_building = false;  // the stream has been synchronised
-    if (!flush_done(T, true)) {
-      return false;
+    for (int k = 0; k < ninst; k++) {
+      if (!flush_done(T, inst[k], true)) {
+        return false;
+      }
     }
     float ms = 0.F;
     cudaEventElapsedTime(&ms, ev_start, ev_stop);

@@ -120,6 +120,10 @@ struct PropagateOptions {
   // the next packet of the list as soon as its own leaves the stage; 0 = the chunked stage kernel above
   int refill_masteps{0};           // [wf_refill_masteps] macro-atom stage: one kernel per iteration instead of the rounds
   int refill_thicksteps{0};        // [wf_refill_thicksteps] grey r-packet stage
+  // two wavefront instances over the two halves of the packets, side by side on their own streams: the drain of one
+  // instance's stage kernel (its last, slowest chunks) is filled by the other instance's kernels
+  int instances{1};                // [wf_instances] 1 or 2
+  int grid_div{1};                 // [wf_grid_div] with two instances: every stage kernel takes 1/grid_div of the resident blocks
 };
 
 // macro-atom transitions per visit in round r of an iteration
@@ -412,6 +416,10 @@ class Engine {
       popt.refill_masteps = static_cast<int>(value < 0 ? 0 : value);
     } else if (name == "wf_refill_thicksteps") {
       popt.refill_thicksteps = static_cast<int>(value < 0 ? 0 : value);
+    } else if (name == "wf_instances") {
+      popt.instances = static_cast<int>((value >= 2) ? 2 : 1);
+    } else if (name == "wf_grid_div") {
+      popt.grid_div = static_cast<int>((value < 1) ? 1 : ((value > 4) ? 4 : value));
     } else if (name == "wf_stage_timing") {
       popt.stage_timing = static_cast<int>(value);
     } else if (name == "stream_download") {

@@ -133,6 +133,21 @@ constexpr double CLIGHTSQUARED = CLIGHT * CLIGHT;
 constexpr double CLIGHTSQUAREDOVERTWOH = (CLIGHT * CLIGHT) / (2 * H);
 constexpr double HOVERKB = H / KB;
 constexpr double HCLIGHTOVERFOURPI = H * CLIGHT / (4 * PI);
+// Reciprocals for the frame transforms and the line walk (vec.h, rpkt.h): a division by the speed of light, or several
+// divisions by the same value, are written as multiplications with the reciprocal. An FP64 division is a ~13-instruction
+// software sequence on the GPU and these stages are bound by instruction issue; the result differs from the reference's
+// division by at most one rounding (1e-16 relative, against the 1e-12 parity bar for doubles; cell indices and line
+// indices are never computed this way - geometry.h keeps the reference's divisions). ARTISB200_RECIP_DIV=0 restores them.
+#ifndef ARTISB200_RECIP_DIV
+#define ARTISB200_RECIP_DIV 1
+#endif
+constexpr bool RECIP_DIV = (ARTISB200_RECIP_DIV != 0);
+constexpr double INV_CLIGHT = 1. / CLIGHT;
+constexpr double INV_CLIGHT_PROP = 1. / CLIGHT_PROP;
+constexpr double INV_CLIGHTSQUARED = 1. / CLIGHTSQUARED;
+AHD double over_clight(const double x) { return RECIP_DIV ? x * INV_CLIGHT : x / CLIGHT; }
+AHD double over_clight_prop(const double x) { return RECIP_DIV ? x * INV_CLIGHT_PROP : x / CLIGHT_PROP; }
+AHD double over_clightsquared(const double x) { return RECIP_DIV ? x * INV_CLIGHTSQUARED : x / CLIGHTSQUARED; }
 constexpr double H_ionpot = 13.5979996 * EV;
 constexpr double C_0 = 5.465e-11;
 constexpr double DBL_MAX_ = 1.7976931348623157e308;

@@ -61,6 +61,14 @@ AHD double get_linedistance(const double prop_time, const double nu_cmf, const d
   return CLIGHT * prop_time * delta_nu / nu_trans;
 }
 
+// the same with the step's -1 / dnu_on_dl handed in (the line walk calls this once per line; hd.h RECIP_DIV)
+AHD double get_linedistance_recip(const double nu_cmf, const double nu_trans, const double minus_dl_on_dnu) {
+  if (nu_cmf <= nu_trans) {
+    return 0.;
+  }
+  return (nu_cmf - nu_trans) * minus_dl_on_dnu;
+}
+
 // rpkt.cc:54-68: comoving frequency at the abort distance, moved in two halves like do_rpkt_step
 AHD double get_nu_cmf_abort(const double* pos, const double* dir, const double prop_time, const double nu_rf,
                             const double abort_dist) {
@@ -289,6 +297,8 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
   const double* celllinetau = (T.cell_linetau != nullptr) ? T.cell_linetau + (static_cast<long long>(cell) * T.nlines) : nullptr;
 
   const double chi_cont = chi.total() * doppler;
+  constexpr bool recip_walk = RECIP_DIV && opt::USE_RELATIVISTIC_DOPPLER_SHIFT;
+  const double minus_dl_on_dnu = recip_walk ? (-1. / dnu_on_dl) : 0.;
   double tau = 0.;
   double dist = 0.;
   long long nvisited = 0;
@@ -311,7 +321,8 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
       prefetch_global(&celllinetau[ahead]);
     }
     next_trans = lineindex + 1;
-    const double ldist = get_linedistance(prop_time, nu_cmf, nu_trans, dnu_on_dl);
+    const double ldist = recip_walk ? get_linedistance_recip(nu_cmf, nu_trans, minus_dl_on_dnu)
+                                    : get_linedistance(prop_time, nu_cmf, nu_trans, dnu_on_dl);
     const double tau_cont = chi_cont * ldist;
 
     if (tau_rnd - tau > tau_cont) {
@@ -336,7 +347,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
         pos[0] += (p.dir[0] * ldist);
         pos[1] += (p.dir[1] * ldist);
         pos[2] += (p.dir[2] * ldist);
-        prop_time += ldist / CLIGHT_PROP;
+        prop_time += over_clight_prop(ldist);
         nu_cmf = p.nu_cmf + (dnu_on_dl * dist);
       }
     } else {

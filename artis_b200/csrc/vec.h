@@ -40,9 +40,16 @@ AHD double vec_len2(const double* v) {
 
 AHD void vec_norm3(const double* in, double* out) {  // vectors.h:31-36
   const double mag = vec_len3(in);
-  out[0] = in[0] / mag;
-  out[1] = in[1] / mag;
-  out[2] = in[2] / mag;
+  if constexpr (RECIP_DIV) {
+    const double inv = 1. / mag;
+    out[0] = in[0] * inv;
+    out[1] = in[1] * inv;
+    out[2] = in[2] * inv;
+  } else {
+    out[0] = in[0] / mag;
+    out[1] = in[1] / mag;
+    out[2] = in[2] / mag;
+  }
 }
 
 AHD void cross_prod(const double* a, const double* b, double* out) {  // vectors.h:54-60
@@ -53,24 +60,37 @@ AHD void cross_prod(const double* a, const double* b, double* out) {  // vectors
 
 // homologous flow velocity at position x and time t (vectors.h:50-52)
 AHD void get_velocity(const double* x, const double t, double* v) {
-  v[0] = x[0] / t;
-  v[1] = x[1] / t;
-  v[2] = x[2] / t;
+  if constexpr (RECIP_DIV) {
+    const double inv = 1. / t;
+    v[0] = x[0] * inv;
+    v[1] = x[1] * inv;
+    v[2] = x[2] * inv;
+  } else {
+    v[0] = x[0] / t;
+    v[1] = x[1] / t;
+    v[2] = x[2] / t;
+  }
 }
 
 // aberration of angles: direction dir1 in frame 1 -> direction in frame 2 moving with vel (vectors.h:70-83)
 AHD void angle_ab(const double* dir1, const double* vel, double* dir2) {
-  const double vsqr = dot3(vel, vel) / CLIGHTSQUARED;
+  const double vsqr = over_clightsquared(dot3(vel, vel));
   const double gamma_rel = 1. / sqrt(1 - vsqr);
   const double ndotv = dot3(dir1, vel);
-  const double fact1 = gamma_rel * (1 - (ndotv / CLIGHT));
-  const double fact2 = (gamma_rel - (pow2(gamma_rel) * ndotv / (gamma_rel + 1) / CLIGHT)) / CLIGHT;
-  const double tmp[3] = {
-      (dir1[0] - (vel[0] * fact2)) / fact1,
-      (dir1[1] - (vel[1] * fact2)) / fact1,
-      (dir1[2] - (vel[2] * fact2)) / fact1,
-  };
-  vec_norm3(tmp, dir2);
+  const double fact2 = over_clight(gamma_rel - over_clight(pow2(gamma_rel) * ndotv / (gamma_rel + 1)));
+  if constexpr (RECIP_DIV) {
+    // the result is normalised: the common factor 1 / fact1 (positive) drops out
+    const double tmp[3] = {dir1[0] - (vel[0] * fact2), dir1[1] - (vel[1] * fact2), dir1[2] - (vel[2] * fact2)};
+    vec_norm3(tmp, dir2);
+  } else {
+    const double fact1 = gamma_rel * (1 - over_clight(ndotv));
+    const double tmp[3] = {
+        (dir1[0] - (vel[0] * fact2)) / fact1,
+        (dir1[1] - (vel[1] * fact2)) / fact1,
+        (dir1[2] - (vel[2] * fact2)) / fact1,
+    };
+    vec_norm3(tmp, dir2);
+  }
 }
 
 // Doppler factor nu_cmf / nu_rf (vectors.h:91-113)
@@ -78,9 +98,9 @@ AHD double doppler_nucmf_on_nurf(const double* pos_rf, const double* dir_rf, con
   double vel_rf[3];
   get_velocity(pos_rf, prop_time, vel_rf);
   const double ndotv = dot3(dir_rf, vel_rf);
-  double dopplerfactor = 1. - (ndotv / CLIGHT);
+  double dopplerfactor = 1. - over_clight(ndotv);
   if constexpr (opt::USE_RELATIVISTIC_DOPPLER_SHIFT) {
-    const double betasq = dot3(vel_rf, vel_rf) / CLIGHTSQUARED;
+    const double betasq = over_clightsquared(dot3(vel_rf, vel_rf));
     dopplerfactor = dopplerfactor / sqrt(1 - betasq);
   }
   return dopplerfactor;
@@ -90,7 +110,7 @@ AHD double doppler_nucmf_on_nurf(const double* pos_rf, const double* dir_rf, con
 AHD void move_withtime(double* pos_rf, const double* dir_rf, double& prop_time, const double nu_rf, double& nu_cmf,
                        const double e_rf, double& e_cmf, const double distance) {
   const double nu_cmf_old = nu_cmf;
-  prop_time += distance / CLIGHT_PROP;
+  prop_time += over_clight_prop(distance);
   pos_rf[0] = pos_rf[0] + (dir_rf[0] * distance);
   pos_rf[1] = pos_rf[1] + (dir_rf[1] * distance);
   pos_rf[2] = pos_rf[2] + (dir_rf[2] * distance);
@@ -106,8 +126,14 @@ AHD void move_pkt_withtime(Pkt& p, const double distance) {  // vectors.h:135-13
 
 AHD void set_pkt_restframe_from_cmf(Pkt& p) {  // vectors.h:141-145
   const double dopplerfactor = doppler_nucmf_on_nurf(p.pos, p.dir, p.prop_time);
-  p.nu_rf = p.nu_cmf / dopplerfactor;
-  p.e_rf = p.e_cmf / dopplerfactor;
+  if constexpr (RECIP_DIV) {
+    const double inv = 1. / dopplerfactor;
+    p.nu_rf = p.nu_cmf * inv;
+    p.e_rf = p.e_cmf * inv;
+  } else {
+    p.nu_rf = p.nu_cmf / dopplerfactor;
+    p.e_rf = p.e_cmf / dopplerfactor;
+  }
 }
 
 // random isotropic unit vector (vectors.h:178-186): two draws

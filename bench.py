@@ -40,11 +40,15 @@ WORKLOADS = {
         atomic_data="synthetic, 5 elements x 4 ions x 120 levels (54 892 lines, 1 475 bound-free continua)"),
     "classic_1d3d": dict(
         preset="classic", ts=4, cpu_config="classic_1d3d_cpu",
+        # few active packets (~1e4) with ~3e5 interactions each in this optically thick phase: the whole-history kernel with
+        # the packets spread over the warps takes over early
+        options={"wf_tail": 16384},
         workload="classic LTE W7-like 1D model on a 3D Cartesian 100^3 grid, 1e5 packets (BASELINE configs[0])",
         model_grid="1D model, 100 shells, on a 3D Cartesian 100^3 propagation grid",
         atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
     "asym3d": dict(
         preset="classic", ts=4, cpu_config="asym3d_cpu",
+        options={"wf_tail": 8192},
         workload="3D Cartesian asymmetric SN Ia model, classic macro-atom mode (BASELINE configs[2]; 1e6 packets per run, ~2.6e4 interactions per packet and timestep)",
         model_grid="3D Cartesian 100^3 (ellipsoidal density with an off-centre Ni blob)",
         atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
@@ -287,7 +291,8 @@ def run_ours(args):
     eng.set_option("nranks", world)
     eng.set_option("max_steps_per_launch", int(os.environ.get("ARTISB200_MAXSTEPS", "0")))
     # tuning aid: ARTISB200_OPTS="schedule=0,wf_tail=4096,..." (artisb200_set_option names)
-    user_opts = dict(kv.split("=") for kv in os.environ.get("ARTISB200_OPTS", "").split(",") if "=" in kv)
+    user_opts = {k: str(v) for k, v in WORKLOADS[WORKLOAD].get("options", {}).items()}
+    user_opts.update(dict(kv.split("=") for kv in os.environ.get("ARTISB200_OPTS", "").split(",") if "=" in kv))
     for name, value in user_opts.items():
         eng.set_option(name, int(value))
     eng.set_arrays(static)
@@ -559,20 +564,27 @@ def cpu_restart_from_gpu_state(nproc, rundir_root, npackets_each):
     if not (os.path.exists(gridsave) and os.path.exists(pktfile)):
         return None
     import struct
+    import numpy as np
     rundirs, binary = cpu_reference_setup(nproc, rundir_root)
     with open(pktfile, "rb") as f:
         total = struct.unpack("<q", f.read(8))[0]
-        stride = (os.path.getsize(pktfile) - 8) // total
-        for r, rundir in enumerate(rundirs):
-            f.seek(8 + r * npackets_each * stride)
-            chunk = f.read(npackets_each * stride)
-            with open(os.path.join(rundir, f"packets_0000_ts{BENCH_TS}.tmp"), "wb") as g:
-                g.write(struct.pack("<q", npackets_each))
-                g.write(chunk)
-            shutil.copy(gridsave, os.path.join(rundir, f"gridsave_ts{BENCH_TS}.tmp"))
-            _set_input_line(os.path.join(rundir, "input.txt"), 2, f"{BENCH_TS:03d} {BENCH_TS + 1:03d}")
-            _set_input_line(os.path.join(rundir, "input.txt"), 16, "1")
-    return rundirs, binary
+    stride = (os.path.getsize(pktfile) - 8) // total
+    raw = np.memmap(pktfile, dtype=np.uint8, mode="r", offset=8, shape=(total, stride))
+    # an UNBIASED sample: the drop-in run returns the packets in completion order (streamed download), so the head of the
+    # file holds the packets that finished the previous timestep first (e.g. pellets that did not decay); every process
+    # takes every step-th packet, interleaved with the other processes
+    each = max(1, min(npackets_each, total // nproc))
+    step = max(1, total // (each * nproc))
+    for r, rundir in enumerate(rundirs):
+        idx = ((np.arange(each, dtype=np.int64) * nproc) + r) * step
+        chunk = np.ascontiguousarray(raw[idx])
+        with open(os.path.join(rundir, f"packets_0000_ts{BENCH_TS}.tmp"), "wb") as g:
+            g.write(struct.pack("<q", each))
+            g.write(chunk.tobytes())
+        shutil.copy(gridsave, os.path.join(rundir, f"gridsave_ts{BENCH_TS}.tmp"))
+        _set_input_line(os.path.join(rundir, "input.txt"), 2, f"{BENCH_TS:03d} {BENCH_TS + 1:03d}")
+        _set_input_line(os.path.join(rundir, "input.txt"), 16, "1")
+    return rundirs, binary, each
 
 
 def cpu_baseline(gpu_interactions_per_packet=None):
@@ -587,10 +599,10 @@ def cpu_baseline(gpu_interactions_per_packet=None):
     npk = int(_configs.get(CPU_SAMPLE_CONFIG)["opts"]["constexpr int MPKTS"].split("=")[1].strip(" ;"))
     prepared = cpu_restart_from_gpu_state(k, root, npk)
     if prepared is not None:
-        rundirs, binary = prepared
+        rundirs, binary, npk = prepared
         res = cpu_reference_restart(rundirs, binary)
-        how = (f"{k} processes x {npk} packets: disjoint slices of the GPU step's own packets, resumed by the reference from "
-               f"the cell state of the GPU workload run (gridsave_ts{BENCH_TS}.tmp)")
+        how = (f"{k} processes x {npk} packets: disjoint interleaved samples of the GPU step's own packets, resumed by the reference "
+               f"from the cell state of the GPU workload run (gridsave_ts{BENCH_TS}.tmp)")
     else:
         rundirs, binary = cpu_reference_setup(k, root)
         res = cpu_reference_evolve(rundirs, binary)

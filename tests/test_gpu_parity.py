@@ -35,6 +35,9 @@ SCHEDULES = {
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
     # per-cell tables of 11 cells at a time: packets wait for the pass that holds their cell (cell-batched tables)
     "wavefront-windows": {"schedule": 1, "wf_tail": 0, "table_window_cells": 11},
+    # two wavefront instances over the two halves of the packets, side by side (CUDA backend; also with table windows)
+    "wavefront-two": {"schedule": 1, "wf_tail": 300, "wf_instances": 2, "wf_sync_every": 2},
+    "wavefront-two-windows": {"schedule": 1, "wf_tail": 0, "wf_instances": 2, "wf_grid_div": 2, "table_window_cells": 13},
 }
 
 @pytest.mark.parametrize("config,nts", CASES)

@@ -21,10 +21,10 @@ for step in $STEPS; do
       # the other BASELINE configurations (bench.py --workload): one bench line each; asym3d a second time with the
       # per-cell tables forced into windows (cell-batched tables)
       for w in ${WORKLOADS:-classic_1d3d gamma_3d50 asym3d}; do
-        timeout 1500 python bench.py --workload $w --steps ${WL_STEPS:-2} --warmup ${WL_WARMUP:-1} > gpurun_out/${TAG}_bench_${w}.json 2> gpurun_out/${TAG}_bench_${w}.err; echo "workload $w rc=$?"
+        timeout ${WL_TIMEOUT:-900} python bench.py --workload $w --steps ${WL_STEPS:-2} --warmup ${WL_WARMUP:-1} > gpurun_out/${TAG}_bench_${w}.json 2> gpurun_out/${TAG}_bench_${w}.err; echo "workload $w rc=$?"
       done
       if [[ " ${WORKLOADS:-classic_1d3d gamma_3d50 asym3d} " == *" asym3d "* ]]; then
-        ARTISB200_OPTS="table_budget_mb=${WINDOW_BUDGET_MB:-8192}" timeout 1500 python bench.py --workload asym3d --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_asym3d_windows.json 2> gpurun_out/${TAG}_bench_asym3d_windows.err; echo "workload asym3d (windows) rc=$?"
+        ARTISB200_OPTS="table_budget_mb=${WINDOW_BUDGET_MB:-8192}" timeout ${WL_TIMEOUT:-900} python bench.py --workload asym3d --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_asym3d_windows.json 2> gpurun_out/${TAG}_bench_asym3d_windows.err; echo "workload asym3d (windows) rc=$?"
       fi ;;
     history)
       ARTISB200_OPTS="schedule=0" timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_history.json 2> gpurun_out/${TAG}_bench_history.err; echo "history rc=$?" ;;
