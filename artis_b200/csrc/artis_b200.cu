@@ -1110,8 +1110,9 @@ struct CudaBackend {
     bool finished{false};
     long long flushed{0};
   };
-  WfInst inst[2];
-  bool inst_ready[2]{false, false};
+  static constexpr int MAX_INSTANCES = 4;
+  WfInst inst[MAX_INSTANCES];
+  bool inst_ready[MAX_INSTANCES]{};
 
   bool init_instance(const int k) {
     if (inst_ready[k]) {
@@ -1146,7 +1147,7 @@ struct CudaBackend {
   }
 
   void free_instances() {
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < MAX_INSTANCES; k++) {
       if (!inst_ready[k]) {
         continue;
       }
@@ -1553,20 +1554,38 @@ struct CudaBackend {
     if (!ensure_schedule_buffers(T, n, o.schedule == 1)) {
       return false;
     }
-    // two wavefront instances over the two halves of the packets (not while every stage kernel is being timed)
-    const int ninst = (o.schedule == 1 && o.instances >= 2 && o.stage_timing == 0 && n >= 64) ? 2 : 1;
-    grid_div = (ninst == 2 && o.grid_div >= 1) ? o.grid_div : 1;
-    const long long half = (ninst == 2) ? ((n / 2) / 32) * 32 : n;
-    if (!bind_instance(0, T, 0, half, stream_out.active) || (ninst == 2 && !bind_instance(1, T, half, n - half, stream_out.active))) {
-      return false;
+    // several wavefront instances over equal parts of the packets (not while every stage kernel is being timed)
+    int ninst = (o.schedule == 1 && o.stage_timing == 0) ? o.instances : 1;
+    ninst = (ninst < 1) ? 1 : ((ninst > MAX_INSTANCES) ? MAX_INSTANCES : ninst);
+    while (ninst > 1 && n < 64LL * ninst) {
+      ninst--;
     }
+    grid_div = (ninst >= 2 && o.grid_div >= 1) ? o.grid_div : 1;
+    const long long part = (ninst >= 2) ? ((n / ninst) / 32) * 32 : n;
+    for (int k = 0; k < ninst; k++) {
+      const long long first = k * part;
+      if (!bind_instance(k, T, first, (k + 1 < ninst) ? part : n - first, stream_out.active)) {
+        return false;
+      }
+    }
+    // the other instances' streams start after what the main stream has enqueued so far, and the main stream carries on
+    // after them
+    const auto fork_instances = [&]() {
+      for (int k = 1; k < ninst; k++) {
+        cudaEventRecord(inst[k].ev_done, stream);
+        cudaStreamWaitEvent(inst[k].stream, inst[k].ev_done, 0);
+      }
+    };
+    const auto join_instances = [&]() {
+      for (int k = 1; k < ninst; k++) {
+        cudaEventRecord(inst[k].ev_done, inst[k].stream);
+        cudaStreamWaitEvent(stream, inst[k].ev_done, 0);
+      }
+    };
     cudaEventRecord(ev_start, stream);
     k_reset_work<<<blocks_for(n, 256), 256, 0, stream>>>(T, n);
     tm->launches += 1;
-    if (ninst == 2) {
-      cudaEventRecord(inst[1].ev_done, stream);
-      cudaStreamWaitEvent(inst[1].stream, inst[1].ev_done, 0);
-    }
+    fork_instances();
     if (stream_out.active) {
       for (int k = 0; k < ninst; k++) {
         WfInst& w = inst[k];
@@ -1597,10 +1616,8 @@ struct CudaBackend {
       bool good = true;
       if (o.schedule == 1) {
         good = run_wavefront(T, ninst, o, tm);
-        if (good && ninst == 2) {
-          // the main stream carries on (window census, timing) after both instances
-          cudaEventRecord(inst[1].ev_done, inst[1].stream);
-          cudaStreamWaitEvent(stream, inst[1].ev_done, 0);
+        if (good) {
+          join_instances();  // the main stream carries on (window census, timing) after all instances
         }
       } else {
         good = run_history(T, inst[0], tm);
@@ -1645,10 +1662,7 @@ struct CudaBackend {
         inst[k].iteration = 0;
         inst[k].waiting = static_cast<unsigned long long>(inst[k].count);
       }
-      if (ninst == 2) {
-        cudaEventRecord(inst[1].ev_done, stream);
-        cudaStreamWaitEvent(inst[1].stream, inst[1].ev_done, 0);
-      }
+      fork_instances();
     }
     cudaMemcpyAsync(&T.diag[ab::DIAG_KERNEL_LAUNCHES], &tm->launches, sizeof(long long), cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(&T.diag[ab::DIAG_TABLE_PASSES], &tm->table_passes, sizeof(long long), cudaMemcpyHostToDevice, stream);

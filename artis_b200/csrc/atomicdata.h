@@ -73,7 +73,8 @@ AHD float photoionisation_crosssection_fromtable(const Tables& T, const float* p
     }
     return sigma_bf;
   }
-  const double ireal = ((nu / nu_edge) - 1.0) / T.nphixsnuincrement;
+  // (hd.h RECIP_DIV: the table spacing is the same for every continuum; the interpolation is continuous in ireal)
+  const double ireal = RECIP_DIV ? ((nu / nu_edge) - 1.0) * (1. / T.nphixsnuincrement) : ((nu / nu_edge) - 1.0) / T.nphixsnuincrement;
   const int i = static_cast<int>(floor(ireal));
   if (i < 0) {
     sigma_bf = 0.;

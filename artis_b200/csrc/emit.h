@@ -67,8 +67,9 @@ AHD void electron_scatter_rpkt(Pkt& p) {
   if (fabs(old_dir_cmf[2]) < 0.99999) {
     const double sin_polar = sqrt(1. - pow2(old_dir_cmf[2]));
     const double common_factor = sin_tsc / sin_polar;
-    const double cos_phisc = cos(phisc);
-    const double sin_phisc = sin(phisc);
+    double cos_phisc;
+    double sin_phisc;
+    sin_cos(phisc, sin_phisc, cos_phisc);
     new_dir_cmf[0] = (common_factor * ((old_dir_cmf[1] * sin_phisc) - (old_dir_cmf[0] * old_dir_cmf[2] * cos_phisc))) +
                      (old_dir_cmf[0] * cos_tsc);
     new_dir_cmf[1] = (common_factor * ((-old_dir_cmf[0] * sin_phisc) - (old_dir_cmf[1] * old_dir_cmf[2] * cos_phisc))) +

@@ -122,7 +122,7 @@ struct PropagateOptions {
   int refill_thicksteps{0};        // [wf_refill_thicksteps] grey r-packet stage
   // two wavefront instances over the two halves of the packets, side by side on their own streams: the drain of one
   // instance's stage kernel (its last, slowest chunks) is filled by the other instance's kernels
-  int instances{1};                // [wf_instances] 1 or 2
+  int instances{1};                // [wf_instances] 1 .. 4
   int grid_div{1};                 // [wf_grid_div] with two instances: every stage kernel takes 1/grid_div of the resident blocks
 };
 
@@ -417,7 +417,7 @@ class Engine {
     } else if (name == "wf_refill_thicksteps") {
       popt.refill_thicksteps = static_cast<int>(value < 0 ? 0 : value);
     } else if (name == "wf_instances") {
-      popt.instances = static_cast<int>((value >= 2) ? 2 : 1);
+      popt.instances = static_cast<int>((value < 1) ? 1 : ((value > 4) ? 4 : value));
     } else if (name == "wf_grid_div") {
       popt.grid_div = static_cast<int>((value < 1) ? 1 : ((value > 4) ? 4 : value));
     } else if (name == "wf_stage_timing") {

@@ -145,6 +145,22 @@ constexpr bool RECIP_DIV = (ARTISB200_RECIP_DIV != 0);
 constexpr double INV_CLIGHT = 1. / CLIGHT;
 constexpr double INV_CLIGHT_PROP = 1. / CLIGHT_PROP;
 constexpr double INV_CLIGHTSQUARED = 1. / CLIGHTSQUARED;
+// 1 / sqrt(x) and (sin, cos) of one argument: one device sequence each instead of sqrt + division / two range reductions
+AHD double inv_sqrt(const double x) {
+#if defined(__CUDA_ARCH__)
+  return RECIP_DIV ? rsqrt(x) : 1. / sqrt(x);
+#else
+  return 1. / sqrt(x);
+#endif
+}
+AHD void sin_cos(const double x, double& s, double& c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, &s, &c);
+#else
+  s = sin(x);
+  c = cos(x);
+#endif
+}
 AHD double over_clight(const double x) { return RECIP_DIV ? x * INV_CLIGHT : x / CLIGHT; }
 AHD double over_clight_prop(const double x) { return RECIP_DIV ? x * INV_CLIGHT_PROP : x / CLIGHT_PROP; }
 AHD double over_clightsquared(const double x) { return RECIP_DIV ? x * INV_CLIGHTSQUARED : x / CLIGHTSQUARED; }

@@ -301,9 +301,13 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
   const double minus_dl_on_dnu = recip_walk ? (-1. / dnu_on_dl) : 0.;
   double tau = 0.;
   double dist = 0.;
-  long long nvisited = 0;
+  int nvisited = 0;
+  // closest_transition() for the first line; from then on next_trans > 0 and its answer is next_trans itself unless the
+  // list or the packet's frequency has run out (rpkt.h:144-156), with the reddest line's frequency read once
+  const int nlines = T.nlines;
+  const double nu_reddest_line = T.line_nu[nlines - 1];
+  int lineindex = closest_transition(T, nu_cmf, next_trans, c);
   while (true) {
-    const int lineindex = closest_transition(T, nu_cmf, next_trans, c);
     if (lineindex < 0) {
       c.work<DIAG_LINES_VISITED>(nvisited);
       const double tau_cont = chi_cont * (abort_dist - dist);
@@ -350,6 +354,7 @@ AHD PossibleEvent get_possible_event(const Ctx& c, const int cell, const Pkt& p,
         prop_time += over_clight_prop(ldist);
         nu_cmf = p.nu_cmf + (dnu_on_dl * dist);
       }
+      lineindex = (next_trans > (nlines - 1) || nu_cmf < nu_reddest_line) ? -1 : next_trans;
     } else {
       c.work<DIAG_LINES_VISITED>(nvisited);
       return {dist + ((tau_rnd - tau) / chi_cont), next_trans - 1, false};
@@ -474,6 +479,7 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
 
   if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
     const int ng = T.nbfcontinua_ground;
+    const double inv_nu_cmf = 1. / nu_cmf;  // (hd.h RECIP_DIV: one division for all ground continua)
     for (int i = 0; i < ng; i++) {
       const double nu_edge = T.groundcont_nu_edge[i];
       if (nu_cmf <= nu_edge) {
@@ -482,10 +488,11 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
       const long long ionestimindex = (static_cast<long long>(cell) * ng) + i;
       const double contr = *c.groundcont_contr(i);
       if constexpr (opt::USE_LUT_PHOTOION) {
-        est_atomic_add(&T.est_gamma[ionestimindex], contr * (distance_e_cmf / nu_cmf));
+        est_atomic_add(&T.est_gamma[ionestimindex], contr * (RECIP_DIV ? distance_e_cmf * inv_nu_cmf : distance_e_cmf / nu_cmf));
       }
       if constexpr (opt::USE_ION_BFHEATING_ESTIMATORS) {
-        est_atomic_add(&T.est_bfheating[ionestimindex], contr * distance_e_cmf * (1. - (nu_edge / nu_cmf)));
+        est_atomic_add(&T.est_bfheating[ionestimindex],
+                       contr * distance_e_cmf * (1. - (RECIP_DIV ? nu_edge * inv_nu_cmf : nu_edge / nu_cmf)));
       }
       c.work<DIAG_ESTIMATOR_ADDS>(2);
     }

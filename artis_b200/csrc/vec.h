@@ -39,13 +39,17 @@ AHD double vec_len2(const double* v) {
 }
 
 AHD void vec_norm3(const double* in, double* out) {  // vectors.h:31-36
-  const double mag = vec_len3(in);
   if constexpr (RECIP_DIV) {
-    const double inv = 1. / mag;
+    double sq = 0.;  // (the summation order of vec_len3)
+    sq += pow2(in[0]);
+    sq += pow2(in[1]);
+    sq += pow2(in[2]);
+    const double inv = inv_sqrt(sq);
     out[0] = in[0] * inv;
     out[1] = in[1] * inv;
     out[2] = in[2] * inv;
   } else {
+    const double mag = vec_len3(in);
     out[0] = in[0] / mag;
     out[1] = in[1] / mag;
     out[2] = in[2] / mag;
@@ -75,7 +79,7 @@ AHD void get_velocity(const double* x, const double t, double* v) {
 // aberration of angles: direction dir1 in frame 1 -> direction in frame 2 moving with vel (vectors.h:70-83)
 AHD void angle_ab(const double* dir1, const double* vel, double* dir2) {
   const double vsqr = over_clightsquared(dot3(vel, vel));
-  const double gamma_rel = 1. / sqrt(1 - vsqr);
+  const double gamma_rel = inv_sqrt(1 - vsqr);
   const double ndotv = dot3(dir1, vel);
   const double fact2 = over_clight(gamma_rel - over_clight(pow2(gamma_rel) * ndotv / (gamma_rel + 1)));
   if constexpr (RECIP_DIV) {
@@ -101,7 +105,7 @@ AHD double doppler_nucmf_on_nurf(const double* pos_rf, const double* dir_rf, con
   double dopplerfactor = 1. - over_clight(ndotv);
   if constexpr (opt::USE_RELATIVISTIC_DOPPLER_SHIFT) {
     const double betasq = over_clightsquared(dot3(vel_rf, vel_rf));
-    dopplerfactor = dopplerfactor / sqrt(1 - betasq);
+    dopplerfactor = RECIP_DIV ? dopplerfactor * inv_sqrt(1 - betasq) : dopplerfactor / sqrt(1 - betasq);
   }
   return dopplerfactor;
 }
@@ -142,8 +146,11 @@ AHD void rand_isotropic_unitvec(Rng& rng, double* out) {
   const double costheta = (2. * u) - 1.;
   const double sintheta = 2. * sqrt(u * (1. - u));
   const double phi = rng.uniform() * 2 * PI;
-  out[0] = sintheta * cos(phi);
-  out[1] = sintheta * sin(phi);
+  double sin_phi;
+  double cos_phi;
+  sin_cos(phi, sin_phi, cos_phi);
+  out[0] = sintheta * cos_phi;
+  out[1] = sintheta * sin_phi;
   out[2] = costheta;
 }
 

@@ -30,9 +30,6 @@ template <int CAP>
 struct WarpChiScratch {
   int offset[33];          // flat index of each lane's first term; [32] = number of terms
   double prod[CAP];        // nnlevel * sigma_contr
-  double sigma[CAP];       // sigma_contr
-  int slot_ground[CAP];    // the term's ground-continuum estimator slot, or -1
-  int slot_bfestim[CAP];   // the term's detailed bound-free estimator slot, or -1
 };
 
 // Coarse index of the frequency-sorted continuum edges for the two window searches (rpkt.cc:800-812), one per thread
@@ -193,6 +190,7 @@ __device__ __forceinline__ void warp_chi_rpkt_cont(const bool need, const Ctx& c
       eo.base = __shfl_sync(FULL, e.base, owner);
       const long long first_o = __shfl_sync(FULL, first, owner);
       const int begin_o = __shfl_sync(FULL, my_begin, owner);
+      const long long ip_o = __shfl_sync(FULL, static_cast<long long>(c.ip), owner);
       eo.stimfactor_split_usable = (eo.exp_minus_hnu_over_kte >= DBL_MIN_);
       if (have) {
         const int cont = T.cell_cont_keptlist[first_o + (t - begin_o)];
@@ -201,29 +199,24 @@ __device__ __forceinline__ void warp_chi_rpkt_cont(const bool need, const Ctx& c
         int bfestimindex = -1;
         const double sigma_contr = bf_term_sigma_contr(T, eo, cont, nnlevel, g, bfestimindex);
         sm.prod[t - base] = nnlevel * sigma_contr;
-        sm.sigma[t - base] = sigma_contr;
-        sm.slot_ground[t - base] = g;
-        sm.slot_bfestim[t - base] = bfestimindex;
+        // the owner's per-estimator slots are written by the lane that evaluated the term (every kept continuum has its
+        // own slot; the owner zeroed them before the __syncwarp above): rpkt.cc:903-907
+        if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
+          if (bfestimindex >= 0) {
+            T.scratch_bfcontr[(bfestimindex * T.scratch_stride) + ip_o] = sigma_contr;
+          }
+        }
+        if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
+          if (g >= 0) {
+            T.scratch_groundcont[(ip_o * T.nbfcontinua_ground) + g] = sigma_contr;
+          }
+        }
       }
     }
     __syncwarp();
     // 3b. every owner adds its terms of this round, in ascending continuum order
     while (summed < my_end && summed < stop) {
-      const int k = summed - base;
-      const double sigma_contr = sm.sigma[k];
-      if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
-        const int slot = sm.slot_bfestim[k];
-        if (slot >= 0) {
-          *c.bfestim_contr(slot) = sigma_contr;  // rpkt.cc:903-907
-        }
-      }
-      if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
-        const int slot = sm.slot_ground[k];
-        if (slot >= 0) {
-          *c.groundcont_contr(slot) = sigma_contr;
-        }
-      }
-      chi_bf_sum += sm.prod[k];
+      chi_bf_sum += sm.prod[summed - base];
       summed++;
     }
     __syncwarp();

@@ -54,8 +54,8 @@ WORKLOADS = {
         atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
     "gamma_3d50": dict(
         preset="classic", ts=1, cpu_config="gamma_3d50_cpu",
-        workload="gamma-packet-only Ni56/Co56 deposition run (Compton/photoelectric/pair) on a 3D 50^3 grid, every cell grey "
-                 "for r-packets (BASELINE configs[3]; 1e7 packets per run)",
+        workload="gamma-packet-only Ni56/Co56 deposition run (Compton/photoelectric/pair) on a 3D 50^3 grid from 20 d, every cell "
+                 "grey for r-packets (BASELINE configs[3]; 1e7 packets per run)",
         model_grid="3D Cartesian 50^3", atomic_data="synthetic, 3 elements x 3 ions x 6 levels (93 lines)"),
 }
 WORKLOAD = os.environ.get("ARTISB200_BENCH_CONFIG", "kilonova_2d")

@@ -168,9 +168,9 @@ int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, 
  * "wf_resort_every", "wf_resort_min": re-sort the stage lists by model cell every this many iterations while at least
  *   that many packets are waiting (table locality; the appends keep the lists only roughly sorted);
  * "wf_concurrent": 1 (default) = the three independent stage kernels of an iteration run on separate streams;
- * "wf_instances": 2 = the packets are split into two halves that run the wavefront side by side on their own streams, lists
- *   and counters, so that the drain of one half's stage kernel is filled by the other half's kernels; "wf_grid_div": with
- *   two instances every stage kernel takes 1/wf_grid_div of the resident blocks;
+ * "wf_instances": 2..4 = the packets are split into equal parts that run the wavefront side by side on their own streams,
+ *   lists and counters, so that the drain of one part's stage kernel is filled by the other parts' kernels; "wf_grid_div":
+ *   with several instances every stage kernel takes 1/wf_grid_div of the resident blocks;
  * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
  * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
  * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep;
