@@ -338,7 +338,7 @@ constexpr int WF_BLOCK = ARTISB200_WF_BLOCK;
 #define ARTISB200_WARP_CHI 1
 #endif
 #ifndef ARTISB200_WARP_CHI_CAP
-#define ARTISB200_WARP_CHI_CAP 128
+#define ARTISB200_WARP_CHI_CAP 256
 #endif
 constexpr int WARP_CHI_CAP = ARTISB200_WARP_CHI_CAP;
 constexpr int wf_minblocks(const int stage) {

@@ -27,6 +27,14 @@ AHD void prefetch_global(const void* addr) {
 #endif
 }
 
+AHD void prefetch_global_l2(const void* addr) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+#else
+  (void)addr;
+#endif
+}
+
 // f64 / i64 accumulation into shared (global-memory) estimators: a relaxed atomic on the device
 // (the reference's atomicadd, constants.h:217-275), a plain add in the single-threaded host build
 AHD void atomic_add(double* addr, const double val) {
@@ -223,6 +231,7 @@ enum : int {  // globals.h:22-42
   MA_ACTION_INTERNALUPHIGHER = 7,
   MA_ACTION_INTERNALUPHIGHERNT = 8,
   MA_ACTION_COUNT = 9,
+  MA_RECORD = 32,  // doubles per (cell, level) walk record: 9 rates + 3 x 7 search pivots, padded to 256 bytes
 };
 
 enum : int { COOLING_FREEFREE = 0, COOLING_FREEBOUND = 1, COOLING_COLLEXC = 2, COOLING_COLLION = 3 };  // kpkt.cc:42

@@ -17,7 +17,12 @@ namespace ab {
 // (8-way split) and finishes with one round over the last <= 8 elements: 2 rounds instead of 7 dependent loads
 // for a 70-entry row, and the same index as the binary search for any sorted input. The work counter keeps counting
 // the probes of the binary search (the compulsory traffic of the roofline model).
-AHD int index_upperbound(const double* a, const int n, const double target, const Ctx& c) {
+// positions of the (up to 7) first-round pivots of an array of length n: pos_k = k * ceil(n / 8) - 1, k = 1..7, while < n
+AHD int upperbound_pivot_pos(const int n, const int k) { return (k * ((n + 7) >> 3)) - 1; }
+
+// `pivots` (optional): the values a[pos_k] of the first round, read together with the process rates (tables.h
+// cell_marecord) - the first round then needs no access to the array itself
+AHD int index_upperbound(const double* a, const int n, const double target, const Ctx& c, const double* pivots = nullptr) {
   int lo = 0;
   int len = n;
   int probes = 0;
@@ -25,6 +30,21 @@ AHD int index_upperbound(const double* a, const int n, const double target, cons
     probes++;
   }
   c.work<DIAG_BINSEARCH_STEPS>(probes);
+  if (pivots != nullptr && len > 8) {
+    const int step = (len + 7) >> 3;
+    int npassed = 0;
+    int nvalid = 0;
+#pragma unroll
+    for (int k = 1; k <= 7; k++) {
+      const int pos = (k * step) - 1;
+      if (pos < len) {
+        nvalid++;
+        npassed += (!(target < pivots[k - 1])) ? 1 : 0;
+      }
+    }
+    lo += npassed * step;
+    len = (npassed < nvalid) ? (step - 1) : (len - (npassed * step));
+  }
   while (len > 8) {
     const int step = (len + 7) >> 3;
     int npassed = 0;  // pivots that are <= target (the pivots are sorted, so these are the first npassed)
@@ -70,6 +90,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
 
   const double* cellrates = T.cell_maprocessrates + (static_cast<long long>(cell) * T.nlevels * MA_ACTION_COUNT);
   const double* cellmatrans = T.cell_matrans + (static_cast<long long>(cell) * T.matrans_total);
+  const double* cellrecords =
+      (T.cell_marecord != nullptr) ? T.cell_marecord + (static_cast<long long>(cell) * T.nlevels * MA_RECORD) : nullptr;
 
   bool end_packet = false;
   int nsteps = 0;
@@ -82,7 +104,10 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
     const int ustart = levelstart(T, element, ion);
     const int ulev = ustart + level;
     const double epsilon_current = epsilon(T, ulev);
-    const double* levelrates = cellrates + (static_cast<long long>(ulev) * MA_ACTION_COUNT);
+    // the level's walk record: 9 process rates + the first-round pivots of its three cumulative arrays (tables.h)
+    const double* levelrates = (cellrecords != nullptr) ? cellrecords + (static_cast<long long>(ulev) * MA_RECORD)
+                                                        : cellrates + (static_cast<long long>(ulev) * MA_ACTION_COUNT);
+    const double* pivots = (cellrecords != nullptr) ? levelrates + MA_ACTION_COUNT : nullptr;
 
     // partial sums of the 9 process rates (macroatom.cc:424-425) and selection by upper_bound (433-437)
     double cumulative[MA_ACTION_COUNT];
@@ -111,7 +136,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
       case MA_ACTION_RADDEEXC: {
         // macroatom.cc:204-244
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_RADDEEXC];
-        const int downtransindex = index_upperbound(transblock, ndowntrans - 1, targetval, c);
+        const int downtransindex = index_upperbound(transblock, ndowntrans - 1, targetval, c, pivots);
         const int alltrans_startdown = T.level_alltrans_startdown[ulev];
         const int lineindex = T.trans_lineindex[alltrans_startdown + downtransindex];
         if (lineindex == activatingline) {
@@ -151,7 +176,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
 
       case MA_ACTION_INTERNALDOWNSAME: {
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALDOWNSAME];
-        const int downtransindex = index_upperbound(transblock + ndowntrans, ndowntrans - 1, targetval, c);
+        const int downtransindex =
+            index_upperbound(transblock + ndowntrans, ndowntrans - 1, targetval, c, (pivots != nullptr) ? pivots + 7 : nullptr);
         level = T.trans_targetlevelindex[T.level_alltrans_startdown[ulev] + downtransindex];
         break;
       }
@@ -249,7 +275,8 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
       case MA_ACTION_INTERNALUPSAME: {
         const int nuptrans = T.level_nuptrans[ulev];
         const double targetval = p.rng.uniform() * levelrates[MA_ACTION_INTERNALUPSAME];
-        const int uptransindex = index_upperbound(transblock + (2 * ndowntrans), nuptrans - 1, targetval, c);
+        const int uptransindex =
+            index_upperbound(transblock + (2 * ndowntrans), nuptrans - 1, targetval, c, (pivots != nullptr) ? pivots + 14 : nullptr);
         level = T.trans_targetlevelindex[alltrans_startup(T, ulev) + uptransindex];
         break;
       }

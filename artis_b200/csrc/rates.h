@@ -293,6 +293,27 @@ AHD void build_macroatom_level(const Tables& T, const int cell, const int ulev) 
   }
   levelrates[MA_ACTION_INTERNALUPHIGHERNT] = sum_up_highernt;
   levelrates[MA_ACTION_INTERNALUPHIGHER] = sum_up_higher;
+
+  if (T.cell_marecord != nullptr) {
+    // the walk record: the rates again, then the first-round pivots of the searches do_macroatom runs in the three
+    // cumulative arrays (macroatom.h index_upperbound: lengths ndown - 1, ndown - 1, nup - 1)
+    double* rec = T.cell_marecord + (((static_cast<long long>(cell) * T.nlevels) + ulev) * MA_RECORD);
+    for (int a = 0; a < MA_ACTION_COUNT; a++) {
+      rec[a] = levelrates[a];
+    }
+    const double* arrays[3] = {arr_sum_epstrans_rad_deexc, arr_sum_internal_down_same, arr_sum_internal_up_same};
+    const int lengths[3] = {ndowntrans - 1, ndowntrans - 1, nuptrans - 1};
+    for (int b = 0; b < 3; b++) {
+      const int n = lengths[b];
+      const int step = (n + 7) >> 3;
+      for (int k = 1; k <= 7; k++) {
+        const int pos = (k * step) - 1;
+        rec[MA_ACTION_COUNT + (7 * b) + (k - 1)] = (n > 8 && pos < n) ? arrays[b][pos] : 0.;
+      }
+    }
+    rec[30] = 0.;
+    rec[31] = 0.;
+  }
 }
 
 // kpkt.cc:57-229 with update_cellcache_contribs = true: cumulative cooling contributions of one ion

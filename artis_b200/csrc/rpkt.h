@@ -651,6 +651,13 @@ AHD bool rstep_finish(Pkt& p, const Ctx& c, const double t2, ChiCont& chi, const
       T.pkt.absorptiontype[c.ip] = pktmastate.activatingline;
       T.pkt.absorptionfreq[c.ip] = p.nu_rf;
       activate_macroatom(p, pktmastate);
+      if (T.cell_marecord != nullptr) {
+        // the macro-atom stage runs after this kernel: start moving the activated level's walk record towards L2
+        const double* rec = T.cell_marecord + (((static_cast<long long>(cell) * T.nlevels) + levelstart(T, pktmastate.element, pktmastate.ion) +
+                                                 pktmastate.level) * MA_RECORD);
+        prefetch_global_l2(rec);
+        prefetch_global_l2(rec + 16);
+      }
     } else {
       // rpkt.cc:628-651: thermal redistribution of the frequency with the given probability, else a pure scattering
       if (opt::BB_THERMALISATION_PROBABILITY >= 1.F || p.rng.uniform() < opt::BB_THERMALISATION_PROBABILITY) {

@@ -386,6 +386,11 @@ struct Tables {
   // (rpkt.cc:75-100), [ncells][nlines], or null when the table is switched off / does not fit: the line walk then reads one
   // contiguous double per visited line instead of gathering two level populations (option line_tau_table)
   double* cell_linetau;
+  // Macro-atom walk record of every (cell, level), MA_RECORD doubles = two 128-byte lines: the 9 process rates followed by
+  // the first-round pivots (7 each) of the 8-way searches in the level's three cumulative transition-rate arrays
+  // (radiative de-excitation, internal down, internal up). One contiguous read gives the action AND the first round of the
+  // search that follows it: a transition is two dependent DRAM accesses (record, final window of the array) instead of three.
+  double* cell_marecord;
 
   // run options
   int rng_mode;
@@ -429,6 +434,7 @@ inline Tables window_view(const Tables& base, const int lo, const int hi) {
   move(W.cell_cont_keptrank, static_cast<long long>(base.keepwords) + 1);
   move(W.cell_corrphotoioncoeff, base.nphixstargets_total);
   move(W.cell_linetau, base.nlines);
+  move(W.cell_marecord, static_cast<long long>(base.nlevels) * MA_RECORD);
   return W;
 }
 

@@ -574,9 +574,9 @@ def cpu_restart_from_gpu_state(nproc, rundir_root, npackets_each):
     # file holds the packets that finished the previous timestep first (e.g. pellets that did not decay); every process
     # takes every step-th packet, interleaved with the other processes
     each = max(1, min(npackets_each, total // nproc))
-    step = max(1, total // (each * nproc))
     for r, rundir in enumerate(rundirs):
-        idx = ((np.arange(each, dtype=np.int64) * nproc) + r) * step
+        # evenly spaced over the WHOLE file (its tail holds the packets that took longest in the previous timestep)
+        idx = (((np.arange(each, dtype=np.int64) * nproc) + r) * total) // (each * nproc)
         chunk = np.ascontiguousarray(raw[idx])
         with open(os.path.join(rundir, f"packets_0000_ts{BENCH_TS}.tmp"), "wb") as g:
             g.write(struct.pack("<q", each))

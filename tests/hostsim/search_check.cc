@@ -30,9 +30,11 @@ int main() {
         }
         a[static_cast<size_t>(i)] = running;
       }
-      std::vector<double> S(static_cast<size_t>(n / 8) + 1);
-      for (int j = 0; j < n / 8; j++) {
-        S[static_cast<size_t>(j)] = a[static_cast<size_t>((8 * j) + 7)];
+      // the first-round pivots as the table builder stores them in the walk record (rates.h build_macroatom_level)
+      double pivots[7] = {0., 0., 0., 0., 0., 0., 0.};
+      for (int k = 1; k <= 7; k++) {
+        const int pos = ab::upperbound_pivot_pos(n, k);
+        pivots[k - 1] = (n > 8 && pos < n) ? a[static_cast<size_t>(pos)] : 0.;
       }
       std::vector<double> targets = {-1., 0., running, running * 2. + 1.};
       for (int i = 0; i < n; i++) {
@@ -48,6 +50,11 @@ int main() {
         const int got = ab::index_upperbound(a.data(), n, t, c);
         if (got != want) {
           std::printf("index_upperbound: n=%d target=%.17g got %d want %d\n", n, t, got, want);
+          return 1;
+        }
+        const int got_piv = ab::index_upperbound(a.data(), n, t, c, pivots);
+        if (got_piv != want) {
+          std::printf("index_upperbound with record pivots: n=%d target=%.17g got %d want %d\n", n, t, got_piv, want);
           return 1;
         }
         cases++;

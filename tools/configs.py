@@ -167,6 +167,15 @@ CONFIGS = {
         model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
         run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
     ) for tag, expo, prob in (("expansionopac", "true", " = 1."), ("expopac_retrace", "true", ""), ("bbtherm", "false", " = 0.5"))},
+    # BASELINE configs[3] in miniature: 3-D model from 20 d with every cell grey for r-packets (optical_depth_is_thick = 0):
+    # pellets, gamma-ray transport and deposition, k-packets and grey random walks
+    "classic3d_grey_toy": dict(
+        preset="classic",
+        opts=_opts(1500),
+        atomic=dict(elements=_FEGROUP, nions=3, nlevels=6, trans_frac=1.0, seed=1),
+        model=dict(kind="3d", n=10, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=3),
+        run=dict(seed=10, ntimesteps=30, tmin=20.0, tmax=80.0, nts_run=3, thick=0.0, ngrey=999, nlte_ts=999),
+    ),
     "classic3d_toy": dict(
         preset="classic",
         opts=_opts(1500),
