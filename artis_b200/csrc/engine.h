@@ -188,7 +188,7 @@ class Engine {
   long long table_window_cells{0};        // [table_window_cells]
   long long table_budget_mb{0};           // [table_budget_mb] 0 = 60 % of the device memory free when the tables are allocated
   int window_capacity{0};                 // cells the allocated tables hold
-  int ma_record{1};                       // [ma_record]
+  int ma_record{-1};                      // [ma_record] -1 = on when the cumulative arrays are long enough to have pivots
   int line_tau_table{-1};               // [line_tau_table] per-cell line table of Sobolev optical depths: 0 off, 1 on, -1 if it fits
   long long line_tau_table_max_mb{8192};  // [line_tau_table_max_mb]
   bool stream_download{false};  // [stream_download] update_packets_host returns the packets in completion order
@@ -436,7 +436,7 @@ class Engine {
     } else if (name == "ma_record") {
       // 1 (default) = the macro-atom walk reads the level's process rates and the first-round pivots of its searches from
       // one 256-byte record per (cell, level) (tables.h cell_marecord); 0 = rates and arrays only
-      ma_record = static_cast<int>(value != 0);
+      ma_record = static_cast<int>((value < 0) ? -1 : ((value != 0) ? 1 : 0));
       outputs_allocated = false;
     } else if (name == "line_tau_table") {
       // per-cell line table of the Sobolev optical depths (tables.h cell_linetau): 0 off, 1 on, -1 on when ncells x nlines
@@ -717,7 +717,9 @@ class Engine {
     }
     // cells per table window: everything resident when it fits into the budget
     const int64_t linetau_percell = static_cast<int64_t>(T.nlines) * 8;
-    const int64_t bytes_percell = 8 * (static_cast<int64_t>(T.nlevels) * (1 + MA_ACTION_COUNT + ((ma_record != 0) ? MA_RECORD : 0)) + T.matrans_total + T.ncoolingterms +
+    // the walk record pays when the searches have a first round: arrays longer than 8 entries on average (a level has three)
+    const bool use_ma_record = (ma_record > 0) || (ma_record < 0 && static_cast<int64_t>(T.matrans_total) >= 24 * static_cast<int64_t>(T.nlevels));
+    const int64_t bytes_percell = 8 * (static_cast<int64_t>(T.nlevels) * (1 + MA_ACTION_COUNT + (use_ma_record ? MA_RECORD : 0)) + T.matrans_total + T.ncoolingterms +
                                        5 * static_cast<int64_t>(T.nbfcontinua) + 2 * static_cast<int64_t>(T.keepwords) + T.nphixstargets_total) +
                                   4 * static_cast<int64_t>(T.nbfcontinua);
     int64_t budget = table_budget_mb * 1048576LL;
@@ -756,7 +758,7 @@ class Engine {
     ok = ok && alloc_output("built.corrphotoioncoeff", 'd', nw * static_cast<int64_t>(T.nphixstargets_total),
                             &T.cell_corrphotoioncoeff);
     T.cell_marecord = nullptr;
-    if (ma_record != 0) {
+    if (use_ma_record) {
       ok = ok && alloc_output("built.marecord", 'd', nw * T.nlevels * MA_RECORD, &T.cell_marecord);
     }
     const int64_t linetau_count = nw * static_cast<int64_t>(T.nlines);

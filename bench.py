@@ -275,13 +275,17 @@ def run_ours(args):
     stride = int(before["packets.stride"][0])
     n_sub = int(os.environ.get("ARTISB200_BENCH_NPACKETS", "0"))  # profiling aid only: propagate a packet subset
     if 0 < n_sub < n:
-        before["packets.aos"] = before["packets.aos"][: n_sub * stride].copy()
+        # evenly spaced over the array: the workload run returns the packets in completion order, so its head holds the
+        # packets that had nothing to do in the previous timestep
+        pick = (np.arange(n_sub, dtype=np.int64) * n) // n_sub
+        before["packets.aos"] = np.ascontiguousarray(before["packets.aos"].reshape(n, stride)[pick]).reshape(-1)
         n = n_sub
     if args.scaling == "strong" and world > 1:
         # strong scaling: the workload's packets are divided among the ranks (the reference divides MPKTS among its MPI ranks
         # the same way when the total is fixed), tables replicated
         per = n // world
-        before["packets.aos"] = before["packets.aos"][rank * per * stride:(rank + 1) * per * stride].copy()
+        # interleaved, not contiguous: the snapshot holds the packets in completion order of the previous timestep
+        before["packets.aos"] = np.ascontiguousarray(before["packets.aos"].reshape(n, stride)[rank::world][:per]).reshape(-1)
         n = per
 
     eng = ablib.ArtisB200(preset=PRESET, device=local_rank)

@@ -174,7 +174,7 @@ int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, 
  * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
  * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
  * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep;
- * "ma_record": 1 (default) = per (cell, level) one 256-byte record with the 9 macro-atom process rates and the first-round
+ * "ma_record": 1 (default when the cumulative arrays average more than 8 entries, -1 = that rule) = per (cell, level) one 256-byte record with the 9 macro-atom process rates and the first-round
  *   pivots of the 8-way searches in the level's three cumulative transition-rate arrays ("built.marecord"): a transition is
  *   two dependent DRAM accesses instead of three; 0 = off (same transitions selected either way);
  * "line_tau_table", "line_tau_table_max_mb": per-cell table [Nc][nlines] of the time-independent factor of every line's

@@ -14,13 +14,13 @@ CASES = [(c, t) for c, ts in fixtures.GOLDEN_TIMESTEPS.items() for t in ts]
 # how the packets are scheduled onto kernels must not change any packet's result (include/artis_b200.h, options)
 SCHEDULES = {
     "wavefront": {"schedule": 1},                                       # default (toy sizes: mostly the tail kernel)
-    "history": {"schedule": 0},                                         # one whole-history kernel
+    "history": {"schedule": 0, "ma_record": 1},                                         # one whole-history kernel
     # chunked stage kernels (no lane refill), one step / one transition per visit
     "wavefront-notail": {"schedule": 1, "wf_tail": 0, "wf_sync_every": 3, "wf_rsteps_thick": 1, "wf_masteps": 1, "wf_ma_rounds": 1,
                          "wf_masteps_last": -1, "wf_refill_masteps": 0, "wf_refill_thicksteps": 0, "line_tau_table": 0, "ma_record": 0},
     "wavefront-walk": {"schedule": 1, "wf_tail": 0, "wf_masteps": 0, "wf_refill_masteps": 0},   # whole macro-atom walk per visit
     "wavefront-refill": {"schedule": 1, "wf_tail": 0, "wf_refill_masteps": 3, "wf_refill_thicksteps": 2},  # lane refill, short visits
-    "wavefront-resort": {"schedule": 1, "wf_tail": 0, "wf_resort_every": 1, "wf_sync_every": 2},  # lists re-sorted by cell
+    "wavefront-resort": {"schedule": 1, "wf_tail": 0, "wf_resort_every": 1, "wf_sync_every": 2, "ma_record": 1},  # lists re-sorted by cell
     "wavefront-rounds": {"schedule": 1, "wf_tail": 0, "wf_masteps": 1, "wf_ma_rounds": 3, "wf_masteps_last": 2, "wf_refill_masteps": 0},
     "wavefront-tail": {"schedule": 1, "wf_tail": 1000000, "wf_sync_every": 2, "wf_rsteps_thin": 3, "wf_masteps": 3},
     # per-cell tables of 11 cells at a time: packets wait for the pass that holds their cell (cell-batched tables)
