@@ -192,25 +192,33 @@ __device__ __forceinline__ void warp_chi_rpkt_cont(const bool need, const Ctx& c
       const int begin_o = __shfl_sync(FULL, my_begin, owner);
       const long long ip_o = __shfl_sync(FULL, static_cast<long long>(c.ip), owner);
       eo.stimfactor_split_usable = (eo.exp_minus_hnu_over_kte >= DBL_MIN_);
+      double sigma_contr = 0.;
+      int g = -1;
       if (have) {
         const int cont = T.cell_cont_keptlist[first_o + (t - begin_o)];
         double nnlevel = 0.;
-        int g = -1;
         int bfestimindex = -1;
-        const double sigma_contr = bf_term_sigma_contr(T, eo, cont, nnlevel, g, bfestimindex);
+        sigma_contr = bf_term_sigma_contr(T, eo, cont, nnlevel, g, bfestimindex);
         sm.prod[t - base] = nnlevel * sigma_contr;
-        // the owner's per-estimator slots are written by the lane that evaluated the term (every kept continuum has its
-        // own slot; the owner zeroed them before the __syncwarp above): rpkt.cc:903-907
+        // The owner's per-estimator slots are written by the lane that evaluated the term (the owner zeroed them before
+        // the __syncwarp above). A detailed bound-free estimator belongs to one continuum (rpkt.cc:903-907) ...
         if constexpr (opt::DETAILED_BF_ESTIMATORS_ON) {
           if (bfestimindex >= 0) {
             T.scratch_bfcontr[(bfestimindex * T.scratch_stride) + ip_o] = sigma_contr;
           }
         }
-        if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
-          if (g >= 0) {
-            T.scratch_groundcont[(ip_o * T.nbfcontinua_ground) + g] = sigma_contr;
-          }
+      }
+      if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
+        // ... but a ground-continuum slot is shared by the continua of all levels closest to that edge, and the serial sum
+        // leaves the LAST of them in it (ascending continuum order = ascending flat index): of the lanes of this pass with
+        // the same owner and slot only the highest stores, and a later pass overwrites an earlier one
+        const unsigned long long key =
+            (have && g >= 0) ? ((static_cast<unsigned long long>(owner) << 32U) | static_cast<unsigned long long>(g + 1)) : 0ULL;
+        const unsigned peers = __match_any_sync(FULL, key);
+        if (key != 0ULL && lane == static_cast<unsigned>(31 - __clz(peers))) {
+          T.scratch_groundcont[(ip_o * T.nbfcontinua_ground) + g] = sigma_contr;
         }
+        __syncwarp();  // orders this pass's stores before the next pass's
       }
     }
     __syncwarp();
