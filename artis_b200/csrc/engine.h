@@ -808,6 +808,13 @@ class Engine {
                     "(DETAILED_BF_ESTIMATORS_ON)");
       }
     }
+    if constexpr (opt::USE_XCOM_GAMMAPHOTOION) {
+      if (count_of("xcom.zstart") != 101 || count_of("xcom.energy") < 0 || count_of("xcom.energy") != count_of("xcom.sigma") ||
+          count_of("cell.elem_numberdens") != static_cast<int64_t>(T.ncells) * T.nelements) {
+        return fail("begin_timestep: xcom.zstart [101], xcom.energy / xcom.sigma and cell.elem_numberdens [ncells x nelements] "
+                    "are required (USE_XCOM_GAMMAPHOTOION)");
+      }
+    }
     if constexpr (opt::RPKT_USE_EXPANSION_OPACITIES) {
       if (count_of("cell.expansionopacities") != static_cast<int64_t>(T.ncells) * expopac_nbins) {
         return fail("begin_timestep: cell.expansionopacities must hold ncells x 1997 wavelength bins (RPKT_USE_EXPANSION_OPACITIES)");

@@ -85,6 +85,54 @@ AHD double get_chi_photo_electric_cmf(const Tables& T, const int cell, const dou
   if constexpr (opt::HAS_GAMMA_KAPPA_GREY) {
     return opt::GAMMA_KAPPA_GREY * rho;
   }
+  if constexpr (opt::USE_XCOM_GAMMAPHOTOION) {
+    // gammapkt.cc:444-497: per element the XCOM photoionisation cross-section (xcom_photoion_data.txt, Z = 1..100; energies
+    // in MeV, cross-sections in cm^2), interpolated linearly in log10-log10 and held constant outside the table
+    const double hnu_over_1MeV = nu_cmf / nu_1mev;
+    const double log10_hnu_over_1MeV = log10(hnu_over_1MeV);
+    double chi_cmf = 0.;
+    for (int i = 0; i < T.nelements; i++) {
+      const int Z = T.elem_anumber[i];
+      if (Z > 100) {
+        continue;
+      }
+      const int first = T.xcom_zstart[Z - 1];
+      const int numb_energies = T.xcom_zstart[Z] - first;
+      if (numb_energies == 0) {
+        continue;
+      }
+      const double n_i = T.elem_numberdens[(static_cast<long long>(cell) * T.nelements) + i];
+      if (n_i == 0) {
+        continue;
+      }
+      const double* energy = T.xcom_energy + first;
+      const double* sigma = T.xcom_sigma + first;
+      int idx_above = -1;
+      for (int j = 0; j < numb_energies; j++) {
+        if (energy[j] > hnu_over_1MeV) {
+          idx_above = j;
+          break;
+        }
+      }
+      if (idx_above == 0) {
+        chi_cmf += sigma[0] * n_i;
+        continue;
+      }
+      if (idx_above == -1) {
+        chi_cmf += sigma[numb_energies - 1] * n_i;
+        continue;
+      }
+      const int idx_below = idx_above - 1;
+      const double log10_E_above = log10(energy[idx_above]);
+      const double log10_E_below = log10(energy[idx_below]);
+      const double log10_sigma_below = log10(sigma[idx_below]);
+      const double log10_sigma_above = log10(sigma[idx_above]);
+      const double log10_sigma_interp =
+          log10_sigma_below + ((log10_sigma_above - log10_sigma_below) / (log10_E_above - log10_E_below) * (log10_hnu_over_1MeV - log10_E_below));
+      chi_cmf += pow(10., log10_sigma_interp) * n_i;
+    }
+    return chi_cmf;
+  }
   // Veigele (1973) fits via Ambwani & Sutherland (1988) eq. 2 (gammapkt.cc:424-442)
   const double hnu_over_100kev = nu_cmf / nu_100kev;
   const double sigma_cmf_si = 1.16e-24 * pow(hnu_over_100kev, -3.13);

@@ -31,7 +31,6 @@ constexpr int GTS_GUTTMAN = 3;
 static_assert(!DETAILED_BF_ESTIMATORS_ON || !USE_LUT_PHOTOION, "DETAILED_BF_ESTIMATORS_ON needs USE_LUT_PHOTOION = false");
 static_assert(!NT_EXCITATION_ON || (NT_ON && NT_SOLVE_SPENCERFANO), "NT_EXCITATION_ON needs NT_ON and NT_SOLVE_SPENCERFANO");
 static_assert(!NT_SOLVE_SPENCERFANO || NT_ON, "NT_SOLVE_SPENCERFANO needs NT_ON");
-static_assert(!USE_XCOM_GAMMAPHOTOION, "XCOM gamma photoionisation tables are not implemented yet");
 static_assert(GAMMA_THERMALISATION_SCHEME >= GTS_FREQUENCYDEPENDENT && GAMMA_THERMALISATION_SCHEME <= GTS_GUTTMAN,
               "unknown gamma-ray thermalisation scheme");
 }  // namespace opt

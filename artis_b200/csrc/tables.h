@@ -102,6 +102,10 @@ namespace ab {
   X(double, corrphotoionrenorm, "cell.corrphotoionrenorm")        \
   X(double, corrphotoioncoeff_host, "cell.corrphotoioncoeff")       \
   X(float, prev_bfrate_normed, "radfield.prev_bfrate_normed")       \
+  X(double, elem_numberdens, "cell.elem_numberdens")                \
+  X(int, xcom_zstart, "xcom.zstart")                                \
+  X(double, xcom_energy, "xcom.energy")                             \
+  X(double, xcom_sigma, "xcom.sigma")                               \
   X(double, nltepops, "cell.nltepops")                              \
   X(double, nt_ionisation_ratecoeff, "cell.nt_ionisation_ratecoeff") \
   X(double, nt_ion_energyrate, "cell.nt_ion_energyrate")            \

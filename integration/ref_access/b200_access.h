@@ -21,6 +21,11 @@ auto b200_lut_temperature_grid() -> std::span<const double>;
 
 auto b200_expansionopacity_planck_cumulative() -> std::span<const double>;
 
+namespace gammapkt {
+// XCOM photoionisation tables of Z = 1..100 flattened: rows [zstart[Z-1], zstart[Z]) of energy [MeV] / sigma [cm^2]
+void b200_xcom_tables(std::vector<int>& zstart, std::vector<double>& energy, std::vector<double>& sigma);
+}  // namespace gammapkt
+
 namespace kpkt {
 auto b200_coolinglist_type(int i) -> int;
 auto b200_coolinglist_level(int i) -> int;

@@ -52,6 +52,7 @@
 #include "b200_access.h"
 #include "b200_snapshot.h"
 #include "decay.h"
+#include "gammapkt.h"
 #include "globals.h"
 #include "grid.h"
 #include "kpkt.h"
@@ -230,6 +231,16 @@ void emit_static(Sink& s) {
   s.arr("lut.corrphotoion", lut_cp.data(), static_cast<int64_t>(lut_cp.size()));
   s.arr("lut.bfcooling", lut_bc.data(), static_cast<int64_t>(lut_bc.size()));
   s.arr("lut.temperature_grid", lut_tg.data(), static_cast<int64_t>(lut_tg.size()));
+  if constexpr (USE_XCOM_GAMMAPHOTOION) {
+    // XCOM photoionisation tables (gammapkt.cc:52-58, read by init_xcom_photoion_data 244-262): rows of Z = 1..100
+    std::vector<int> zstart;
+    std::vector<double> energy;
+    std::vector<double> sigma;
+    gammapkt::b200_xcom_tables(zstart, energy, sigma);
+    s.arr("xcom.zstart", zstart.data(), static_cast<int64_t>(zstart.size()));
+    s.arr("xcom.energy", energy.data(), static_cast<int64_t>(energy.size()));
+    s.arr("xcom.sigma", sigma.data(), static_cast<int64_t>(sigma.size()));
+  }
 
   const int ncool = kpkt::ncoolingterms;
   std::vector<unsigned char> c_type(ncool);
@@ -347,6 +358,17 @@ void emit_timestep_state(Sink& s, const int nts) {
       s.arr("cell.nt_deposition_rate_density", deprate.data(), static_cast<int64_t>(deprate.size()));
       s.arr("cell.nt_frac_excitation", fracexc.data(), static_cast<int64_t>(fracexc.size()));
     }
+  }
+  if constexpr (USE_XCOM_GAMMAPHOTOION) {
+    // element number densities of the timestep (grid.cc:1693-1697), read by the XCOM photoelectric opacity (gammapkt.cc:456)
+    const int nel = get_nelements();
+    std::vector<double> numberdens(static_cast<size_t>(nc) * static_cast<size_t>(nel));
+    for (int64_t cell = 0; cell < nc; cell++) {
+      for (int element = 0; element < nel; element++) {
+        numberdens[(static_cast<size_t>(cell) * static_cast<size_t>(nel)) + static_cast<size_t>(element)] = grid::get_elem_numberdens(cell, element);
+      }
+    }
+    s.arr("cell.elem_numberdens", numberdens.data(), static_cast<int64_t>(numberdens.size()));
   }
   if constexpr (RPKT_USE_EXPANSION_OPACITIES) {
     // binned expansion opacities [cm^2/g] of this timestep (rpkt.h:47, written by calculate_expansion_opacities,

@@ -19,14 +19,14 @@ PRESET_OF = {"classic_toy": "classic", "classic_toy_1d": "classic", "classic3d_t
              "classic_ntexc_toy": "classic_ntexc", "classic_detailedbf_toy": "classic_detailedbf",
              "nltephot_toy": "nltephotospheric", "kilonova_2d_kat": "kilonova_lte",
              "kilonova_expansionopac_toy": "kilonova_expansionopac", "kilonova_expopac_retrace_toy": "kilonova_expopac_retrace",
-             "kilonova_bbtherm_toy": "kilonova_bbtherm", "classic3d_grey_toy": "classic"}
+             "kilonova_bbtherm_toy": "kilonova_bbtherm", "classic3d_grey_toy": "classic", "kilonova_xcom_toy": "kilonova_xcom"}
 GOLDEN_TIMESTEPS = {"classic_toy": [0, 3], "classic_toy_1d": [0, 3], "classic3d_toy": [0, 2], "kilonova_toy": [1, 4],
                     "classic_multibin_toy": [2, 4], "classic_nlte_toy": [2, 4],
                     "kilonova_guttman_toy": [1], "kilonova_wollaeger_toy": [1], "kilonova_barnes_toy": [1],
                     "classic_nt_toy": [2, 3], "classic_ntexc_toy": [2, 3],
                     "classic_detailedbf_toy": [1, 3], "nltephot_toy": [1, 3],
                     "kilonova_expansionopac_toy": [2, 4], "kilonova_expopac_retrace_toy": [4], "kilonova_bbtherm_toy": [4],
-                    "classic3d_grey_toy": [0, 2]}
+                    "classic3d_grey_toy": [0, 2], "kilonova_xcom_toy": [1, 4]}
 # presets compiled with USE_LUT_PHOTOION = false (csrc/options/preset_*.h)
 PRESETS_WITHOUT_LUT_PHOTOION = {"classic_detailedbf", "nltephotospheric"}
 INTERACTIONS = 26  # stats::Counter::INTERACTIONS (reference stats.h:41)

@@ -36,6 +36,7 @@ GOLDEN = {
     "kilonova_wollaeger_toy": [1],
     "kilonova_barnes_toy": [1],
     "classic3d_grey_toy": [0, 2],
+    "kilonova_xcom_toy": [1, 4],
     # expansion-opacity / bound-bound thermalisation r-packet modes (rpkt.cc:221-320, 628-651, 964-981)
     "kilonova_expansionopac_toy": [2, 4],
     "kilonova_expopac_retrace_toy": [4],

@@ -176,6 +176,21 @@ CONFIGS = {
         model=dict(kind="3d", n=10, vmax_kmps=25000.0, t_model_days=2.0, mass_msun=1.4, seed=3),
         run=dict(seed=10, ntimesteps=30, tmin=20.0, tmax=80.0, nts_run=3, thick=0.0, ngrey=999, nlte_ts=999),
     ),
+    # kilonova_toy with the XCOM photoionisation tables for the gamma-ray photoelectric opacity (the reference's CI variant
+    # tests/setup_kilonova_2d_xcomgammaphotoion.sh)
+    "kilonova_xcom_toy": dict(
+        preset="kilonova_lte",
+        opts=_opts(1000, None, None, {
+            "constexpr int TABLESIZE": "constexpr int TABLESIZE = 20;",
+            "constexpr double MINTEMP": "constexpr double MINTEMP = 1000.;",
+            "constexpr double MAXTEMP": "constexpr double MAXTEMP = 20000.;",
+            "constexpr bool USE_XCOM_GAMMAPHOTOION": "constexpr bool USE_XCOM_GAMMAPHOTOION = true;",
+        }),
+        atomic=dict(elements=_KN_ELEMS, nions=3, nlevels=8, trans_frac=0.6, seed=2),
+        model=dict(kind="2d", nr=8, nz=16, vmax_c=0.3, t_model_days=0.1, mass_msun=0.01, seed=2),
+        run=dict(seed=9, ntimesteps=10, tmin=0.2, tmax=6.0, nts_run=5, thick=0.0, ngrey=2, nlte_ts=999),
+        extra_files=["xcom_photoion_data.txt"],
+    ),
     "classic3d_toy": dict(
         preset="classic",
         opts=_opts(1500),

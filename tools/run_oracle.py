@@ -28,6 +28,9 @@ def run(config, flavor="parity", mode="ref_perpacket", dump_ts="all", rundir=Non
     shutil.copytree(os.path.join(odir, "inputs"), rundir)
     datadir = os.path.join(ROOT, "oracle", "_ref", "data")
     os.symlink(datadir, os.path.join(rundir, "data"))
+    import configs as _configs
+    for extra in _configs.get(config).get("extra_files", []):  # e.g. xcom_photoion_data.txt, read from the run folder
+        shutil.copy(os.path.join(datadir, extra), os.path.join(rundir, extra))
     if seed is not None:
         path = os.path.join(rundir, "input.txt")
         lines = open(path).read().split("\n")
