@@ -188,7 +188,7 @@ class Engine {
   long long table_window_cells{0};        // [table_window_cells]
   long long table_budget_mb{0};           // [table_budget_mb] 0 = 60 % of the device memory free when the tables are allocated
   int window_capacity{0};                 // cells the allocated tables hold
-  int ma_record{-1};                      // [ma_record] -1 = on when the cumulative arrays are long enough to have pivots
+  int ma_record{0};                       // [ma_record] 1 = on, -1 = on when the cumulative arrays are long enough to have pivots
   int line_tau_table{-1};               // [line_tau_table] per-cell line table of Sobolev optical depths: 0 off, 1 on, -1 if it fits
   long long line_tau_table_max_mb{8192};  // [line_tau_table_max_mb]
   bool stream_download{false};  // [stream_download] update_packets_host returns the packets in completion order

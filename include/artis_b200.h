@@ -67,6 +67,9 @@
  *   cell.corrphotoioncoeff 'd'[Nc*(total photoionisation targets)]  optional, NOT read by the kernels: the same
  *       coefficients as the reference's own get_corrphotoioncoeff evaluates them (ratecoeff.cc:840), written into the
  *       oracle snapshots as known-answer vectors for built.corrphotoioncoeff
+ *   xcom.zstart 'i'[101], xcom.energy 'd'[rows] (MeV), xcom.sigma 'd'[rows] (cm^2)  (USE_XCOM_GAMMAPHOTOION only; static)
+ *       gammapkt.cc:52-58: the XCOM photoionisation table of element Z is rows [zstart[Z-1], zstart[Z]) (xcom_photoion_data.txt,
+ *       read by init_xcom_photoion_data 244-262); cell.elem_numberdens 'd'[Nc*nelements] (per timestep) grid.cc:1693-1697
  *   cell.expansionopacities 'f'[Nc*1997]  (RPKT_USE_EXPANSION_OPACITIES only) rpkt.h:47: bound-bound opacity [cm^2/g] per
  *       20-Angstrom wavelength bin from 60 to 40000 Angstrom (rpkt.h:23-44), written by calculate_expansion_opacities
  *       (rpkt.cc:1071-1123) in update_grid; read by get_possible_event_expansion_opacity (rpkt.cc:221-320)
@@ -174,7 +177,7 @@ int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, 
  * "wf_tail": finish with the whole-history kernel once at most this many packets remain;
  * "wf_sync_every": wavefront iterations enqueued between host checks; "wf_stage_timing": 1 = time each stage;
  * "max_steps_per_launch": whole-history kernel only, 0 = run every history to the end of the timestep;
- * "ma_record": 1 (default when the cumulative arrays average more than 8 entries, -1 = that rule) = per (cell, level) one 256-byte record with the 9 macro-atom process rates and the first-round
+ * "ma_record": 1 (-1 = when the cumulative arrays average more than 8 entries; default 0: measured neutral) = per (cell, level) one 256-byte record with the 9 macro-atom process rates and the first-round
  *   pivots of the 8-way searches in the level's three cumulative transition-rate arrays ("built.marecord"): a transition is
  *   two dependent DRAM accesses instead of three; 0 = off (same transitions selected either way);
  * "line_tau_table", "line_tau_table_max_mb": per-cell table [Nc][nlines] of the time-independent factor of every line's

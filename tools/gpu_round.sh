@@ -26,6 +26,18 @@ for step in $STEPS; do
       if [[ " ${WORKLOADS:-classic_1d3d gamma_3d50 asym3d} " == *" asym3d "* ]]; then
         ARTISB200_OPTS="table_budget_mb=${WINDOW_BUDGET_MB:-8192}" timeout ${WL_TIMEOUT:-900} python bench.py --workload asym3d --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_asym3d_windows.json 2> gpurun_out/${TAG}_bench_asym3d_windows.err; echo "workload asym3d (windows) rc=$?"
       fi ;;
+    final)
+      # the round's record: bench line, reference arm, DRAM traffic of every launch of one step, launch list, full captures
+      timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+      timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "reference rc=$?"
+      timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/${TAG}_dram.csv python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_dram.err; echo "dram rc=$?"
+      python tools/ncu_dram_traffic.py gpurun_out/${TAG}_dram.csv gpurun_out/${TAG}_dram_traffic.json | tee gpurun_out/${TAG}_dram_summary.txt
+      ARTISB200_BENCH_NPACKETS=2000000 timeout 600 ncu --set full --clock-control none --import-source on \
+        -k regex:k_wf_stage --launch-skip 18 --launch-count 6 -o gpurun_out/${TAG}_full -f \
+        python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_full.err; echo "full rc=$?"
+      ARTISB200_BENCH_NPACKETS=2000000 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv -c 600 \
+        --log-file gpurun_out/${TAG}_launches.csv python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_launches.err; echo "launches rc=$?" ;;
     history)
       ARTISB200_OPTS="schedule=0" timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_history.json 2> gpurun_out/${TAG}_bench_history.err; echo "history rc=$?" ;;
     variants)
