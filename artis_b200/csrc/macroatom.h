@@ -25,11 +25,7 @@ AHD int upperbound_pivot_pos(const int n, const int k) { return (k * ((n + 7) >>
 AHD int index_upperbound(const double* a, const int n, const double target, const Ctx& c, const double* pivots = nullptr) {
   int lo = 0;
   int len = n;
-  int probes = 0;
-  for (int m = n; m > 0; m >>= 1) {
-    probes++;
-  }
-  c.work<DIAG_BINSEARCH_STEPS>(probes);
+  c.work<DIAG_BINSEARCH_STEPS>(bit_length(n));  // probes of the binary search over n entries
   if (pivots != nullptr && len > 8) {
     const int step = (len + 7) >> 3;
     int npassed = 0;

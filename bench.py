@@ -52,9 +52,8 @@ WORKLOADS = {
         # per timestep one after the other (measured with the reference: 71 s per 1e5 packets and timestep on one core);
         # a step of that phase does not fit a bench run on any hardware
         preset="classic", ts=2, cpu_config="asym3d_cpu",
-        # the step ends with ~2e4 packets random-walking through very thick grey cells (1e4-1e5 scatterings each, one after
-        # the other): the wavefront keeps them longer before the whole-history kernel takes over
-        options={"wf_tail": 2048},
+        # (the step ends with ~2e4 packets random-walking through very thick grey cells, 1e4-1e5 scatterings each in sequence;
+        # keeping them in the wavefront down to 2048 packets was measured slower: 9.8 s against 4.5 s)
         workload="3D Cartesian asymmetric SN Ia model, classic macro-atom mode (BASELINE configs[2]; 1e6 packets per run)",
         model_grid="3D Cartesian 100^3 (ellipsoidal density with an off-centre Ni blob)",
         atomic_data="synthetic, 7 elements x 4 ions x <= 40 levels (2 002 lines)"),
