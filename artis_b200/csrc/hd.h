@@ -80,28 +80,9 @@ AHD void est_atomic_add(double* addr, const double val) {
     }
     return;
   }
-  // Several cells in the warp. With cell-sorted lists the lanes of one cell are neighbours: when every group is a dense
-  // run of lanes [lo, hi], a segmented shuffle-down reduction takes five steps whatever the number and size of the groups
-  // (the loop over the peers below took 8 instructions per peer: 23 % of the grey stage's instructions, ncu
-  // profiles/r2_final_source_summary.txt).
-  const int lo = __ffs(peers) - 1;
-  const int hi = 31 - __clz(peers);
-  const unsigned upto_hi = (hi == 31) ? 0xffffffffU : ((1U << (hi + 1)) - 1U);
-  const bool dense = (peers == (upto_hi & ~((1U << lo) - 1U)));
-  if (__all_sync(active, dense)) {
-    double sum = val;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const double other = __shfl_down_sync(active, sum, d);
-      if (static_cast<int>(lane) + d <= hi) {
-        sum += other;
-      }
-    }
-    if (static_cast<int>(lane) == lo) {
-      atomicAdd(addr, sum);
-    }
-    return;
-  }
+  // Several cells in the warp: every lane sums the values of its peers. (A segmented shuffle-down reduction over dense
+  // runs of lanes was tried - five steps whatever the number of groups - and measured no faster: lanes leave the step
+  // loops at different times, so the groups of the grey stage are rarely dense. profiles/r2_tuning.md)
   double sum = 0.;
   unsigned m = peers;
   while (m != 0U) {
