@@ -439,10 +439,20 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
                            const ChiCont& chi, const bool thickcell) {
   const Tables& T = c.T;
   const double distance_e_cmf = distance * e_cmf;
+  constexpr bool plain_cell_estimators = !opt::DETAILED_BF_ESTIMATORS_ON && !opt::MULTIBIN_RADFIELD_MODEL_ON;
   if (distance_e_cmf != 0) {
-    est_atomic_add(&T.est_J[cell], distance_e_cmf);
-    est_atomic_add(&T.est_nuJ[cell], distance_e_cmf * nu_cmf);
-    c.work<DIAG_ESTIMATOR_ADDS>(2);
+    if (plain_cell_estimators && !thickcell) {
+      // J, nuJ and the free-free heating of the cell in one aggregated add (same values, same cell as the three below)
+      double* const addr[3] = {&T.est_J[cell], &T.est_nuJ[cell], &T.est_ffheating[cell]};
+      const double val[3] = {distance_e_cmf, distance_e_cmf * nu_cmf, distance_e_cmf * chi.chi_freefree_heat};
+      est_atomic_add_n<3>(addr, val);
+      c.work<DIAG_ESTIMATOR_ADDS>(3);
+    } else {
+      double* const addr[2] = {&T.est_J[cell], &T.est_nuJ[cell]};
+      const double val[2] = {distance_e_cmf, distance_e_cmf * nu_cmf};
+      est_atomic_add_n<2>(addr, val);
+      c.work<DIAG_ESTIMATOR_ADDS>(2);
+    }
   }
   if (thickcell) {
     return;
@@ -474,8 +484,10 @@ AHD void update_estimators(const Ctx& c, const double e_cmf, const double nu_cmf
       }
     }
   }
-  est_atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
-  c.work<DIAG_ESTIMATOR_ADDS>(1);
+  if (!(plain_cell_estimators && distance_e_cmf != 0)) {  // (else added above, together with J and nuJ)
+    est_atomic_add(&T.est_ffheating[cell], distance_e_cmf * chi.chi_freefree_heat);
+    c.work<DIAG_ESTIMATOR_ADDS>(1);
+  }
 
   if constexpr (opt::USE_LUT_PHOTOION || opt::USE_ION_BFHEATING_ESTIMATORS) {
     const int ng = T.nbfcontinua_ground;
