@@ -147,7 +147,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
         }
         const int ulevlower = ustart + T.trans_targetlevelindex[alltrans_startdown + downtransindex];
         const double epsilon_trans = epsilon_current - epsilon(T, ulevlower);
-        const double oldnucmf = p.nu_cmf;
+        const double oldnucmf = (activatingline >= 0) ? (p.kin_in_memory ? T.pkt.ha[c.ip].nu_cmf : p.nu_cmf) : 0.;
         p.nu_cmf = epsilon_trans / H;
         if (activatingline >= 0) {
           if (oldnucmf < p.nu_cmf) {
@@ -171,7 +171,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
         p.type = TYPE_KPKT;
         end_packet = true;
         if constexpr (!opt::DIRECT_COL_HEAT) {
-          atomic_add(&T.est_colheating[cell], p.e_cmf);
+          atomic_add(&T.est_colheating[cell], p.kin_in_memory ? T.pkt.hb[c.ip].e_cmf : p.e_cmf);
           c.work<DIAG_ESTIMATOR_ADDS>();
         }
         break;
@@ -238,7 +238,7 @@ AHD void do_macroatom(Pkt& p, const Ctx& c, const int max_steps) {
         p.type = TYPE_KPKT;
         end_packet = true;
         if constexpr (!opt::DIRECT_COL_HEAT) {
-          atomic_add(&T.est_colheating[cell], p.e_cmf);
+          atomic_add(&T.est_colheating[cell], p.kin_in_memory ? T.pkt.hb[c.ip].e_cmf : p.e_cmf);
           c.work<DIAG_ESTIMATOR_ADDS>();
         }
         break;

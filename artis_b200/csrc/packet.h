@@ -47,6 +47,9 @@ struct Pkt {
   // the packet's next r-packet visit, where whole warps have one to do, instead of by the few lanes of the
   // macro-atom kernel whose walk has just ended. The packet's random numbers are drawn in the same order either way.
   int ev_pending;
+  // the macro-atom stage does not load the kinematics (prop_time, nu_cmf, e_cmf live in two other 64-byte records that a
+  // transition does not need): the few places of the walk that read nu_cmf or e_cmf fetch them from memory when this is set
+  bool kin_in_memory;
 };
 
 enum : int { EV_NONE = 0, EV_EMIT_MA = 1 };
@@ -260,10 +263,13 @@ AHD void load_pkt(Pkt& p, ChiCont& chi, const Tables& T, const long long ip) {
       chi.chi_freefree_heat = hb->chi_ff;
     }
   } else {
-    p.prop_time = T.pkt.ha[ip].prop_time;  // stage_of() asks whether a k-packet left by the walk still has time
-    p.nu_cmf = T.pkt.ha[ip].nu_cmf;
-    p.e_cmf = T.pkt.hb[ip].e_cmf;
+    // A packet in the macro-atom stage is in the middle of its timestep (the activating event happened before ts_end), which
+    // is all stage_of() asks of prop_time after the walk; nu_cmf and e_cmf are fetched by the walk where it needs them.
+    p.prop_time = T.ts_begin;
+    p.nu_cmf = 0.;
+    p.e_cmf = 0.;
   }
+  p.kin_in_memory = !StageIO<STAGE>::kinematics;
   if constexpr (StageIO<STAGE>::chi) {
     chi.chi_boundfree = hc->chi_bf;
     chi.nonemptymgi = hc->chi_mgi;
