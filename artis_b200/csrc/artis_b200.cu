@@ -770,6 +770,35 @@ __global__ void __launch_bounds__(PROP_BLOCK) k_propagate(const __grid_constant_
   }
 }
 
+// Spectra and light curves of the escaped packets (spectra.h): persistent grid (a multiple of the SM count), grid-stride
+// loop over the packets. The angle-averaged light curves would take every escaped packet's add on one of ntimesteps
+// addresses; they are accumulated per block in shared memory and flushed with one atomic per non-zero entry.
+__global__ void __launch_bounds__(256) k_bin_escaped(const __grid_constant__ ab::Tables T, const __grid_constant__ ab::SpectraView S,
+                                                     const long long n, const int use_local) {
+  extern __shared__ double lc_shared[];
+  ab::LcLocal local{lc_shared, lc_shared + S.ntimesteps, lc_shared + (2 * S.ntimesteps), lc_shared + (3 * S.ntimesteps)};
+  if (use_local != 0) {
+    for (int i = threadIdx.x; i < 4 * S.ntimesteps; i += blockDim.x) {
+      lc_shared[i] = 0.;
+    }
+    __syncthreads();
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long ip = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x; ip < n; ip += stride) {
+    ab::bin_escaped_packet(T, S, ip, (use_local != 0) ? &local : nullptr);
+  }
+  if (use_local != 0) {
+    __syncthreads();
+    double* const dst[4] = {S.lc_lum, S.lc_lumcmf, S.gamma_lc_lum, S.gamma_lc_lumcmf};
+    for (int i = threadIdx.x; i < 4 * S.ntimesteps; i += blockDim.x) {
+      const double v = lc_shared[i];
+      if (v != 0.) {
+        atomicAdd(&dst[i / S.ntimesteps][i % S.ntimesteps], v);
+      }
+    }
+  }
+}
+
 struct CudaBackend {
   std::string error;
   int device{-1};
@@ -976,6 +1005,25 @@ struct CudaBackend {
     // not synchronised: the caller's next step is usually the packet upload, which runs on the copy stream while
     // these kernels build the tables (execution errors surface at the next synchronisation of this stream)
     return ok(cudaGetLastError(), "build_cell_tables");
+  }
+
+  bool bin_escaped_packets(const ab::Tables& T, const ab::SpectraView& S, const long long n, double* ms) {
+    cudaSetDevice(device);
+    const size_t smem = static_cast<size_t>(4 * S.ntimesteps) * sizeof(double);
+    const int use_local = (smem <= 32768) ? 1 : 0;
+    const long long wanted = (n + 255) / 256;
+    const long long resident = static_cast<long long>(sm_count) * 8;  // 8 blocks of 256 threads per SM
+    const unsigned int blocks = static_cast<unsigned int>((wanted < resident) ? wanted : resident);
+    cudaEventRecord(ev_start, stream);
+    k_bin_escaped<<<blocks, 256, (use_local != 0) ? smem : 0, stream>>>(T, S, n, use_local);
+    cudaEventRecord(ev_stop, stream);
+    if (!ok(cudaStreamSynchronize(stream), "k_bin_escaped") || !ok(cudaGetLastError(), "k_bin_escaped")) {
+      return false;
+    }
+    float elapsed = 0.F;
+    cudaEventElapsedTime(&elapsed, ev_start, ev_stop);
+    *ms = static_cast<double>(elapsed);
+    return true;
   }
 
   bool run_test_kernel(Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,

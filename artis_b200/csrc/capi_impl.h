@@ -115,6 +115,14 @@ int artisb200_register_host_buffer(artisb200_ctx* ctx, void* ptr, const int64_t 
 }
 int artisb200_unregister_host_buffer(artisb200_ctx* ctx, void* ptr) { return ctx->eng.register_host_buffer(ptr, 0, false); }
 
+int artisb200_bin_escaped_packets(artisb200_ctx* ctx, int direction_bins, int emission_absorption, int nprocs_exspec) {
+  return ctx->eng.bin_escaped_packets(direction_bins, emission_absorption, nprocs_exspec);
+}
+int artisb200_last_binning_ms(artisb200_ctx* ctx, double* ms) {
+  *ms = ctx->eng.last_binning_ms;
+  return 0;
+}
+
 int artisb200_save_packets_device(artisb200_ctx* ctx) { return ctx->eng.save_packets_device(); }
 int artisb200_restore_packets_device(artisb200_ctx* ctx) { return ctx->eng.restore_packets_device(); }
 

@@ -17,6 +17,7 @@
 
 #include "options.h"
 #include "packet.h"
+#include "spectra.h"
 #include "tables.h"
 
 namespace ab {
@@ -196,6 +197,11 @@ class Engine {
   PropagateTimings last;
   int64_t scratch_capacity{0};
   int64_t bfscratch_capacity{0};
+  // spectra / light-curve binning (spectra.h)
+  SpectraView S{};
+  long long spec_nnubins{1000};    // [spec_nnubins] MNUBINS (exspec.h:8)
+  bool spec_record_dirbin{false};  // [spec_record_dirbin] keep every packet's direction bin ("spec.dirbin")
+  double last_binning_ms{0.};
 
   int fail(const std::string& msg) {
     err = msg;
@@ -336,10 +342,11 @@ class Engine {
       return 0;
     }
     const FieldDesc* f = find_field(name);
-    if (f == nullptr) {
+    const bool binned = (name.rfind("spec.", 0) == 0 || name.rfind("lc.", 0) == 0);  // outputs of bin_escaped_packets
+    if (f == nullptr && !binned) {
       return fail("unknown array name '" + name + "'");
     }
-    if (f->kind == FieldKind::SCALAR) {
+    if (f != nullptr && f->kind == FieldKind::SCALAR) {
       if (dtype != f->dtype || count != 1) {
         return fail("scalar '" + name + "': dtype/count mismatch");
       }
@@ -446,6 +453,13 @@ class Engine {
     } else if (name == "line_tau_table_max_mb") {
       line_tau_table_max_mb = value;
       outputs_allocated = false;
+    } else if (name == "spec_nnubins") {
+      if (value < 1) {
+        return fail("option spec_nnubins: at least one frequency bin");
+      }
+      spec_nnubins = value;
+    } else if (name == "spec_record_dirbin") {
+      spec_record_dirbin = (value != 0);
     } else if (name == "rank") {
       rank = static_cast<int>(value);
     } else if (name == "nranks") {
@@ -1085,6 +1099,137 @@ class Engine {
     be.free(d_outf);
     be.free(d_outi);
     return okay ? 0 : fail("test_kernel failed: " + be.last_error());
+  }
+
+  // Spectra and light curves of the device-resident packets in one pass (spectra.h): what the reference's
+  // write_partial_lightcurve_spectra (spectrum_lightcurve.cc:316-337) computes with 1 + MABINS passes over the host packets.
+  //   direction_bins: 0 = angle-averaged only, 1 = also the MABINS direction bins (sets 1..MABINS of every output)
+  //   emission_absorption: 0 = none, 1 = for the angle-averaged set, 2 = for every set
+  //   nprocs_exspec: globals::nprocs_exspec, the number of ranks whose packets make up the result
+  int bin_escaped_packets(const int direction_bins, const int emission_absorption, const int nprocs_exspec) {
+    if (!static_committed) {
+      return fail("bin_escaped_packets: commit_static must be called first");
+    }
+    if (npackets <= 0) {
+      return fail("bin_escaped_packets: no packets on the device");
+    }
+    if (emission_absorption < 0 || emission_absorption > 2 || nprocs_exspec < 1 || (emission_absorption == 2 && direction_bins == 0)) {
+      return fail("bin_escaped_packets: emission_absorption is 0, 1 or 2 (2 needs direction_bins), nprocs_exspec >= 1");
+    }
+    // timesteps.* hold the reference's ntimesteps + 1 entries: the last one is the end marker with start = tmax (input.cc:2292)
+    const auto* t_start = host<double>("timesteps.start");
+    if (T.ntimesteps < 2) {
+      return fail("bin_escaped_packets: timesteps.start needs the ntimesteps + 1 entries of globals::timesteps");
+    }
+    S.nnubins = static_cast<int>(spec_nnubins);
+    S.ntimesteps = T.ntimesteps - 1;
+    S.nsets = (direction_bins != 0) ? 1 + MABINS : 1;
+    S.nsets_emabs = (emission_absorption == 0) ? 0 : ((emission_absorption == 1) ? 1 : S.nsets);
+    const auto* e_nions = host<int>("elem.nions");
+    int max_nions = 0;
+    for (int e = 0; e < T.nelements; e++) {
+      max_nions = (e_nions[e] > max_nions) ? e_nions[e] : max_nions;
+    }
+    S.max_nions = max_nions;
+    S.ioncount = T.nelements * max_nions;
+    S.proccount = (2 * S.ioncount) + 1;
+    S.nu_min = opt::NU_MIN_R;
+    S.nu_max = opt::NU_MAX_R;
+    S.dlognu = (std::log(S.nu_max) - std::log(S.nu_min)) / static_cast<double>(S.nnubins);  // spectrum_lightcurve.cc:489
+    S.tmin = T.tmin;
+    S.tmax = t_start[T.ntimesteps - 1];
+    S.vmax = T.vmax;
+    S.nprocs_exspec = static_cast<double>(nprocs_exspec);
+    S.ts_start = T.ts_start;
+    S.ts_width = T.ts_width;
+    S.line_elementindex = T.line_elementindex;
+    S.line_ionindex = T.line_ionindex;
+    // frequency grid (spectrum_lightcurve.cc:500-504): float edges, evaluated with the host's libm like the reference
+    std::vector<float> lower_freq(static_cast<size_t>(S.nnubins));
+    std::vector<float> delta_freq(static_cast<size_t>(S.nnubins));
+    for (int nnu = 0; nnu < S.nnubins; nnu++) {
+      lower_freq[nnu] = static_cast<float>(std::exp(std::log(S.nu_min) + (static_cast<double>(nnu) * S.dlognu)));
+      delta_freq[nnu] = static_cast<float>(std::exp(std::log(S.nu_min) + (static_cast<double>(nnu + 1) * S.dlognu)) - lower_freq[nnu]);
+    }
+    // element / ion behind every bound-free emission type (globals::bflist in the order of input.cc:1765-1793)
+    const auto* i_nion = host<int>("ion.nlevels_ionising");
+    const auto* i_levelstart = host<int>("ion.uniquelevelindexstart");
+    const auto* e_start = host<int>("elem.uniqueionindexstart");
+    const auto* l_ntargets = host<int>("level.nphixstargets");
+    const auto* l_bfstart = host<int>("level.bflist_start");
+    S.nbflist = T.nbfcontinua;
+    std::vector<int> bf_element(static_cast<size_t>(S.nbflist > 0 ? S.nbflist : 1), 0);
+    std::vector<int> bf_ion(bf_element.size(), 0);
+    for (int e = 0; e < T.nelements; e++) {
+      for (int i = 0; i < e_nions[e]; i++) {
+        const int u = e_start[e] + i;
+        for (int l = 0; l < i_nion[u]; l++) {
+          const int ulev = i_levelstart[u] + l;
+          for (int t = 0; t < l_ntargets[ulev]; t++) {
+            const int b = l_bfstart[ulev] + t;
+            if (l_bfstart[ulev] >= 0 && b < S.nbflist) {
+              bf_element[b] = e;
+              bf_ion[b] = i;
+            }
+          }
+        }
+      }
+    }
+    const float* d_lower = nullptr;
+    if (!make_derived("spec.lower_freq", lower_freq, &d_lower) || !make_derived("spec.delta_freq", delta_freq, &S.delta_freq) ||
+        !make_derived("derived.bflist_element", bf_element, &S.bflist_element) ||
+        !make_derived("derived.bflist_ion", bf_ion, &S.bflist_ion)) {
+      return fail("bin_escaped_packets: allocation of the frequency grid failed: " + be.last_error());
+    }
+    const int64_t fluxsize = static_cast<int64_t>(S.nnubins) * S.ntimesteps;
+    const int64_t n_flux = S.nsets * fluxsize;
+    const int64_t n_em = S.nsets_emabs * fluxsize * S.proccount;
+    const int64_t n_abs = S.nsets_emabs * fluxsize * S.ioncount;
+    const int64_t n_lc = static_cast<int64_t>(S.nsets) * S.ntimesteps;
+    bool ok = true;
+    ok = ok && alloc_output("spec.flux", 'd', n_flux, &S.flux);
+    ok = ok && alloc_output("spec.emission", 'd', n_em, &S.emission);
+    ok = ok && alloc_output("spec.trueemission", 'd', n_em, &S.trueemission);
+    ok = ok && alloc_output("spec.absorption", 'd', n_abs, &S.absorption);
+    ok = ok && alloc_output("lc.lum", 'd', n_lc, &S.lc_lum);
+    ok = ok && alloc_output("lc.lumcmf", 'd', n_lc, &S.lc_lumcmf);
+    ok = ok && alloc_output("lc.gamma_lum", 'd', S.ntimesteps, &S.gamma_lc_lum);
+    ok = ok && alloc_output("lc.gamma_lumcmf", 'd', S.ntimesteps, &S.gamma_lc_lumcmf);
+    S.dirbin = nullptr;
+    if (spec_record_dirbin) {
+      ok = ok && alloc_output("spec.dirbin", 'i', npackets, &S.dirbin);
+    }
+    if (!ok) {
+      return fail("bin_escaped_packets: allocation of the spectra failed: " + be.last_error());
+    }
+    if (T.dev_error == nullptr) {
+      if (!alloc_output("dev_error", 'q', NDEVERROR, &T.dev_error)) {
+        return fail("bin_escaped_packets: allocation failed: " + be.last_error());
+      }
+    }
+    be.zero(T.dev_error, NDEVERROR * 8);
+    be.zero(S.flux, n_flux * 8);
+    if (n_em > 0) {
+      be.zero(S.emission, n_em * 8);
+      be.zero(S.trueemission, n_em * 8);
+      be.zero(S.absorption, n_abs * 8);
+    }
+    be.zero(S.lc_lum, n_lc * 8);
+    be.zero(S.lc_lumcmf, n_lc * 8);
+    be.zero(S.gamma_lc_lum, S.ntimesteps * 8);
+    be.zero(S.gamma_lc_lumcmf, S.ntimesteps * 8);
+    if (!be.bin_escaped_packets(T, S, npackets, &last_binning_ms)) {
+      return fail("bin_escaped_packets: " + be.last_error());
+    }
+    long long dev_error[NDEVERROR] = {0, 0, 0, 0};
+    if (!be.d2h(dev_error, T.dev_error, NDEVERROR * 8)) {
+      return fail("bin_escaped_packets: reading the device error record failed: " + be.last_error());
+    }
+    if (dev_error[0] != 0) {
+      return fail("bin_escaped_packets: packet " + std::to_string(dev_error[1]) +
+                  " carries a bound-free emission type beyond the continuum list (spectrum_lightcurve.cc:197)");
+    }
+    return 0;
   }
 
   int save_packets_device() {

@@ -184,6 +184,7 @@ enum : int {
   DEVERR_RPKT_CONTINUUM_BEYOND_SUM = 4,  // rpkt.cc:452 assert_always(chi_rnd < chi_escatter + chi_ff + chi_bf)
   DEVERR_PELLET_STATE = 5,               // update_packets.cc:251 unreachable pellet state
   DEVERR_UNKNOWN_PACKET_TYPE = 6,        // update_packets.cc:312 default of do_packet's switch
+  DEVERR_SPECTRA_EMISSIONTYPE = 7,       // spectrum_lightcurve.cc:197 assert_always(bfindex < globals::nbfcontinua)
 };
 constexpr int NDEVERROR = 4;
 

@@ -34,6 +34,8 @@ _SIGNATURES = {
                                                  ctypes.c_int64]),
     "artisb200_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "artisb200_commit_static": (ctypes.c_int, [ctypes.c_void_p]),
+    "artisb200_bin_escaped_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "artisb200_last_binning_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "artisb200_begin_timestep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "artisb200_upload_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "artisb200_download_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
@@ -58,7 +60,8 @@ EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 ESTIMATOR_NAMES = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.gamma", "est.bfheating", "est.dep_gamma",
                    "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "ts.pellet_decays", "counters", "diag"]
 OPTIONAL_ESTIMATOR_NAMES = ["est.bins_J_raw", "est.bins_nuJ_raw", "est.bfrate_raw"]  # MULTIBIN / DETAILED_BF presets only
-_OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "diag_stage": np.int64, "dev_error": np.int64, "built.cont_keepbits": np.uint64}
+_OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "diag_stage": np.int64, "dev_error": np.int64, "built.cont_keepbits": np.uint64,
+               "spec.lower_freq": np.float32, "spec.delta_freq": np.float32, "spec.dirbin": np.int32}
 
 
 def load_library(path):
@@ -161,6 +164,17 @@ class ArtisB200:
         """the drop-in call: host AoS packets in, propagated host AoS packets out (in place)"""
         self._check(self.lib.artisb200_update_packets_host(self.ctx, int(nts), aos_bytes.ctypes.data_as(ctypes.c_void_p),
                                                            npackets, stride), "update_packets_host")
+
+    def bin_escaped_packets(self, direction_bins=False, emission_absorption=0, nprocs_exspec=1):
+        """spectra and light curves of the device-resident packets in one pass (include/artis_b200.h); read the results
+        with get_array("spec.flux") ... or artis_b200.spectra.binned()"""
+        self._check(self.lib.artisb200_bin_escaped_packets(self.ctx, int(bool(direction_bins)), int(emission_absorption),
+                                                           int(nprocs_exspec)), "bin_escaped_packets")
+
+    def last_binning_ms(self):
+        ms = ctypes.c_double()
+        self.lib.artisb200_last_binning_ms(self.ctx, ctypes.byref(ms))
+        return ms.value
 
     def save_packets_device(self):
         self._check(self.lib.artisb200_save_packets_device(self.ctx), "save_packets_device")

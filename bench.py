@@ -250,6 +250,30 @@ def measured_peak_gbs():
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 
+def spectra_binning_leg(eng, n, peak):
+    """SURVEY 8f row 2, reported beside the headline (never part of the timed step): the spectra / light-curve binning of the
+    packets as the last step left them on the device, all 1 + 100 direction sets in one pass. Algorithmic bytes: the 32-byte
+    type sector of every packet + kinematics, energies, escape type and time (136 B) of every escaped one."""
+    try:
+        eng.set_option("spec_record_dirbin", 1)
+        eng.bin_escaped_packets(direction_bins=True, emission_absorption=0, nprocs_exspec=1)
+        escaped = int((eng.get_array("spec.dirbin") >= 0).sum())
+        eng.set_option("spec_record_dirbin", 0)
+        times = []
+        for _ in range(5):
+            eng.bin_escaped_packets(direction_bins=True, emission_absorption=0, nprocs_exspec=1)
+            times.append(eng.last_binning_ms())
+        ms = sorted(times)[len(times) // 2]
+        b_alg = 32 * n + 136 * escaped
+        filled = int((eng.get_array("spec.flux") != 0.).sum())
+        return {"kernel": "k_bin_escaped", "packets": int(n), "escaped": escaped, "direction_sets": 101, "ms": ms,
+                "algorithmic_bytes": b_alg, "bound": "hbm", "achieved": b_alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": b_alg / (ms * 1e-3) / 1e9 / peak, "flux_bins_filled": filled,
+                "reference_does": "1 + 100 passes over the host packets (spectrum_lightcurve.cc:316-337)"}
+    except Exception as e:  # an extra: it must never take the bench line down
+        return {"error": str(e)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -482,6 +506,7 @@ def run_ours(args):
         # gamma transport does not touch the reference's INTERACTIONS counter, so the gamma-only configuration
         # is quoted in physical gamma events (Compton / photoelectric / pair, gammapkt.cc:720-747) per second as well
         out["gamma_events_per_s"] = n_gamma_total / (t_step * 1e-3)
+        out["spectra_binning"] = spectra_binning_leg(eng, n, peak)
         out["table_windows"] = {"passes_per_step": int(diag_mean[12]), "cells": int(ncells),
                                 "note": "1 = the per-cell tables of every cell are resident; > 1 = cell-batched tables"}
         if not args.no_cpu_baseline and world == 1:

@@ -44,7 +44,7 @@
  *   groundcont.nu_edge 'd'[Ng] globals.h:266      bfestim.nu_edge 'd' globals.h:245
  *   lut.spontrecomb/corrphotoion/bfcooling 'd'[Nbf*TABLESIZE], lut.temperature_grid 'd'[TABLESIZE+1]  ratecoeff.cc:40-72
  *   cooling.type 'B', cooling.level 'i', cooling.phixstargetindex 'i' [ncoolingterms]        kpkt.cc:44-46
- *   timesteps.start/width/mid 'd'[ntimesteps]                                               globals.h:73-76
+ *   timesteps.start/width/mid 'd'[ntimesteps + 1]  (the last entry is the end marker: start = mid = tmax, input.cc:2292)  globals.h:73-76
  *  per-timestep cell state (set before artisb200_begin_timestep)
  *   cell.rho/Te/TJ/TR/W/nne/nnetot/kappagrey/clumpfactor 'f'[Nc], cell.thick 'i'[Nc]        grid.h:19-36
  *   cell.elem_massfracs 'f'[Nc*nelements] grid.h:45   cell.ion_groundlevelpops/ion_partfuncts 'f'[Nc*Nion] grid.h:47-48
@@ -87,7 +87,7 @@
  *   dev_error 'q'[4]: device-side stand-in for the reference's assert_always (mpi_logging.h:123-130): code of the first
  *     assertion that failed in the timestep (0 = none; 1-3 macro-atom selections without a target, macroatom.cc:290/502/320;
  *     4 continuum event beyond the opacity sum, rpkt.cc:452; 5 impossible pellet state, update_packets.cc:251; 6 unknown
- *     packet type, update_packets.cc:312), packet index, detail, number of failures. artisb200_update_packets[_host] returns
+ *     packet type, update_packets.cc:312; 7 emission type beyond the continuum list, spectrum_lightcurve.cc:197), packet index, detail, number of failures. artisb200_update_packets[_host] returns
  *     nonzero when it is set, and the binding logs and aborts like the reference.
  */
 #ifndef ARTIS_B200_H
@@ -219,6 +219,31 @@ int artisb200_unregister_host_buffer(artisb200_ctx* ctx, void* ptr);
 /* Device-resident snapshot/restore of the packet state, for benchmarks that replay one timestep. */
 int artisb200_save_packets_device(artisb200_ctx* ctx);
 int artisb200_restore_packets_device(artisb200_ctx* ctx);
+
+/* Spectra and light curves of the device-resident packets: the binning that the reference's
+ * write_partial_lightcurve_spectra (spectrum_lightcurve.cc:316-337, called at sn3d.cc after every timestep) and exspec
+ * (exspec.cc:60-200) do on the host with add_to_spec_res (spectrum_lightcurve.cc:544-661) and add_to_lc_res (691-718), one
+ * pass over all packets for the angle-averaged result and one more per direction bin. Here: ONE pass; every escaped
+ * packet adds to set 0 (angle-averaged, dirbin -1) and, with direction_bins != 0, to set 1 + get_escapedirectionbin(dir)
+ * (vectors.h:147-175; MABINS = 100 sets, solid-angle factor MABINS).
+ *   direction_bins       0 = set 0 only, 1 = 1 + MABINS sets
+ *   emission_absorption  0 = flux and light curves only, 1 = emission / true emission / absorption decomposition for set 0
+ *                        (WRITE_EMISSIONABSORPTION_SPEC_AT_END), 2 = for every set
+ *   nprocs_exspec        globals::nprocs_exspec: the number of ranks whose packets make up one spectrum
+ * Needs commit_static and packets on the device (after artisb200_update_packets[_host] or artisb200_upload_packets);
+ * timesteps.start/width hold the reference's ntimesteps + 1 entries (the last is the end marker, start = tmax, input.cc:2292).
+ * Results (artisb200_get_array; layouts of the reference's Spectra, spectrum_lightcurve.h:15-37, one set after the other):
+ *   spec.lower_freq / spec.delta_freq 'f'[MNUBINS]                  frequency grid NU_MIN_R..NU_MAX_R (spectrum_lightcurve.cc:489-504)
+ *   spec.flux 'd'[sets][MNUBINS][ntimesteps]                         fluxalltimesteps
+ *   spec.emission / spec.trueemission 'd'[sets'][MNUBINS][ntimesteps][2*nelements*max_nions+1]
+ *   spec.absorption 'd'[sets'][MNUBINS][ntimesteps][nelements*max_nions]
+ *   lc.lum / lc.lumcmf 'd'[sets][ntimesteps]   lc.gamma_lum / lc.gamma_lumcmf 'd'[ntimesteps] (escaped gamma packets, set 0 only)
+ *   spec.dirbin 'i'[npackets]  direction bin of every escaped packet, -1 for the others (option "spec_record_dirbin" = 1)
+ * Options: "spec_nnubins" (MNUBINS, exspec.h:8, default 1000). Sums over ranks: the caller all-reduces the arrays, as the
+ * reference does (spectrum_lightcurve.cc:293-310). The additions are floating-point atomics: the sums agree with the
+ * reference's to rounding of the summation order, not bit for bit. */
+int artisb200_bin_escaped_packets(artisb200_ctx* ctx, int direction_bins, int emission_absorption, int nprocs_exspec);
+int artisb200_last_binning_ms(artisb200_ctx* ctx, double* ms); /* device time of the last binning pass */
 
 /* One packed device buffer [J|nuJ|ffheating|colheating|gamma|bfheating|dep_*|ts.scalars|bins_J_raw|bins_nuJ_raw] of f64 for the
  * per-timestep all-reduce (replaces the MPI_Allreduce calls at sn3d.cc:565-625 and radfield.cc:988-1030).

@@ -51,6 +51,16 @@ void b200_nt_excitations(int& stride, std::vector<int>& count, std::vector<int>&
                          std::vector<float>& frac_excitation);
 }  // namespace nonthermal
 
+// spectra and light curves of a span of packets for one direction bin (-1 = angle-averaged), binned by the reference's own
+// add_to_lc_res / add_to_spec_res (ref_spectrum_lightcurve.cc); only linked into the oracle build's snapshot hooks
+struct Packet;
+struct B200BinnedPackets {
+  std::vector<float> lower_freq, delta_freq;
+  std::vector<double> flux, emission, trueemission, absorption;
+  std::vector<double> lc_lum, lc_lumcmf, gamma_lc_lum, gamma_lc_lumcmf;
+};
+void b200_bin_escaped_packets(std::span<const Packet> pkts, int dirbin, bool do_emission_absorption, B200BinnedPackets& out);
+
 namespace stats {
 void b200_add_counter(int i, std::ptrdiff_t n);
 }  // namespace stats

@@ -52,6 +52,7 @@
 #include "b200_access.h"
 #include "b200_snapshot.h"
 #include "decay.h"
+#include "exspec.h"
 #include "gammapkt.h"
 #include "globals.h"
 #include "grid.h"
@@ -65,6 +66,7 @@
 #include "rpkt.h"
 #include "stats.h"
 #include "update_packets.h"
+#include "vectors.h"
 
 namespace {
 
@@ -949,6 +951,50 @@ void emit_reference_cellcache(Sink& s) {
 }
 #endif
 
+#ifdef ARTISB200_WITH_REFERENCE
+// Known answers for the spectra / light-curve binning of the packets as update_packets leaves them:
+// the reference's own add_to_spec_res / add_to_lc_res (spectrum_lightcurve.cc:544-713) for the angle-averaged bin with the
+// emission / absorption decomposition, and flux + light curves for each of the MABINS direction bins.
+template <class Sink>
+void emit_reference_spectra(Sink& s, const std::span<const Packet> packets) {
+  B200BinnedPackets b;
+  b200_bin_escaped_packets(packets, -1, true, b);
+  s.i64("ref.spec.nnubins", static_cast<int64_t>(MNUBINS));
+  s.i64("ref.spec.mabins", static_cast<int64_t>(MABINS));
+  s.i64("ref.spec.nprocs_exspec", static_cast<int64_t>(globals::nprocs_exspec));
+  s.f64("ref.spec.nu_min", NU_MIN_R);
+  s.f64("ref.spec.nu_max", NU_MAX_R);
+  s.arr("ref.spec.lower_freq", b.lower_freq.data(), static_cast<int64_t>(b.lower_freq.size()));
+  s.arr("ref.spec.delta_freq", b.delta_freq.data(), static_cast<int64_t>(b.delta_freq.size()));
+  s.arr("ref.spec.flux", b.flux.data(), static_cast<int64_t>(b.flux.size()));
+  s.arr("ref.spec.emission", b.emission.data(), static_cast<int64_t>(b.emission.size()));
+  s.arr("ref.spec.trueemission", b.trueemission.data(), static_cast<int64_t>(b.trueemission.size()));
+  s.arr("ref.spec.absorption", b.absorption.data(), static_cast<int64_t>(b.absorption.size()));
+  s.arr("ref.lc.lum", b.lc_lum.data(), static_cast<int64_t>(b.lc_lum.size()));
+  s.arr("ref.lc.lumcmf", b.lc_lumcmf.data(), static_cast<int64_t>(b.lc_lumcmf.size()));
+  s.arr("ref.lc.gamma_lum", b.gamma_lc_lum.data(), static_cast<int64_t>(b.gamma_lc_lum.size()));
+  s.arr("ref.lc.gamma_lumcmf", b.gamma_lc_lumcmf.data(), static_cast<int64_t>(b.gamma_lc_lumcmf.size()));
+  std::vector<double> flux_res;
+  std::vector<double> lum_res;
+  std::vector<double> lumcmf_res;
+  for (int dirbin = 0; dirbin < MABINS; dirbin++) {
+    b200_bin_escaped_packets(packets, dirbin, false, b);
+    flux_res.insert(flux_res.end(), b.flux.begin(), b.flux.end());
+    lum_res.insert(lum_res.end(), b.lc_lum.begin(), b.lc_lum.end());
+    lumcmf_res.insert(lumcmf_res.end(), b.lc_lumcmf.begin(), b.lc_lumcmf.end());
+  }
+  s.arr("ref.spec.flux_res", flux_res.data(), static_cast<int64_t>(flux_res.size()));
+  s.arr("ref.lc.lum_res", lum_res.data(), static_cast<int64_t>(lum_res.size()));
+  s.arr("ref.lc.lumcmf_res", lumcmf_res.data(), static_cast<int64_t>(lumcmf_res.size()));
+  // the direction bin of every packet by the reference's get_escapedirectionbin (vectors.h:147-175): index parity
+  std::vector<int> dirbins(packets.size());
+  for (size_t i = 0; i < packets.size(); i++) {
+    dirbins[i] = (packets[i].type == TYPE_ESCAPE) ? get_escapedirectionbin(packets[i].dir) : -1;
+  }
+  s.arr("ref.spec.dirbin", dirbins.data(), static_cast<int64_t>(dirbins.size()));
+}
+#endif
+
 auto dump_requested(const int nts) -> bool {
   const char* dir = std::getenv("ARTISB200_DUMP_DIR");
   if (dir == nullptr) {
@@ -1011,6 +1057,9 @@ void update_packets(const int nts, std::span<Packet> packets) {
     if (mode == "ref_perpacket") {
       emit_reference_cellcache(w);
       emit_reference_kats(w, nts);
+    }
+    if (std::getenv("ARTISB200_DUMP_SPECTRA") != nullptr) {
+      emit_reference_spectra(w, packets);
     }
 #endif
   }

@@ -33,7 +33,7 @@ else
 endif
 
 # reference TUs compiled directly, except those wrapped by integration/ref_access (which #include them)
-WRAPPED := grid ratecoeff kpkt radfield stats nonthermal rpkt gammapkt
+WRAPPED := grid ratecoeff kpkt radfield stats nonthermal rpkt gammapkt spectrum_lightcurve
 PLAIN := $(filter-out $(WRAPPED) update_packets exspec unittests sn3d,$(basename $(notdir $(wildcard $(REF)/*.cc))))
 OBJS := $(addprefix $(OUT)/,$(addsuffix .o,$(PLAIN) sn3d $(addprefix ref_,$(WRAPPED)) update_packets_b200))
 

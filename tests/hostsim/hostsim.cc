@@ -104,6 +104,15 @@ struct HostBackend {
     return true;
   }
 
+  bool bin_escaped_packets(const ab::Tables& T, const ab::SpectraView& S, const long long n, double* ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long long ip = 0; ip < n; ip++) {
+      ab::bin_escaped_packet(T, S, ip, nullptr);
+    }
+    *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+  }
+
   bool run_test_kernel(ab::Tables& T, const int which, const int64_t n, const double* in_f64, const int* in_i32,
                        double* out_f64, int* out_i32) {
     std::vector<double> scratch(static_cast<size_t>(T.nbfcontinua_ground > 0 ? T.nbfcontinua_ground : 1));

@@ -1,5 +1,7 @@
 """Parity assertions shared by the host-simulation tests (CPU, this container) and the GPU tests (B200, through
 the C ABI). The checker is always the oracle fixture generated from the compiled reference (tests/golden)."""
+import os
+
 import numpy as np
 
 import compare_run
@@ -216,3 +218,76 @@ def check_bench_scale_histories(libpath, config, nts, options=None, tol=1e-9, es
     assert frac_ok == 1.0, f"{int(round((1 - frac_ok) * n))} of {n} packets differ from the oracle ({worst})"
     assert_aggregates(config, est, after, est_err, est_tol)
     return n, ncells
+
+
+def check_spectra(libpath, config, nts, device=0, rel=1e-12):
+    """spectra and light curves of the fixture's "after" packets binned by the library in ONE pass against the
+    reference's own add_to_spec_res / add_to_lc_res run once per direction bin (tests/golden/make_golden_spectra.py).
+    Bin indices (direction bin of every packet; which bins are filled) are exact; the sums agree to the rounding of the
+    summation order: every addend is formed in the reference's operation order."""
+    from artis_b200 import spectra as spectra_mod
+
+    fx = fixtures.load_golden(config, nts)
+    ref = dict(np.load(os.path.join(fixtures.GOLDEN_DIR, f"{config}_spectra_ts{nts}.npz")))
+    eng = fixtures.ablib.ArtisB200(libpath=libpath, device=device)
+    try:
+        eng.set_arrays(fx["static"])
+        eng.commit_static()
+        after = fx["after"]
+        n = int(after["packets.count"][0])
+        stride = int(after["packets.stride"][0])
+        eng.upload_packets(after["packets.aos"], n, stride)
+        eng.set_option("spec_nnubins", int(ref["ref.spec.nnubins"][0]))
+        eng.set_option("spec_record_dirbin", 1)
+        nprocs = int(ref["ref.spec.nprocs_exspec"][0])
+        mabins = int(ref["ref.spec.mabins"][0])
+        assert mabins == spectra_mod.MABINS
+
+        def close(name, got, want):
+            got = np.asarray(got, dtype=np.float64).ravel()
+            want = np.asarray(want, dtype=np.float64).ravel()
+            assert got.shape == want.shape, f"{config} ts{nts} {name}: shape {got.shape} vs {want.shape}"
+            assert np.array_equal(got != 0., want != 0.), f"{config} ts{nts} {name}: different bins are filled"
+            err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+            assert err.max(initial=0.) <= rel, f"{config} ts{nts} {name}: max relative error {err.max()}"
+
+        # (1) everything at once: all direction bins + the decomposition of the angle-averaged set
+        eng.bin_escaped_packets(direction_bins=True, emission_absorption=1, nprocs_exspec=nprocs)
+        b = spectra_mod.binned(eng)
+        assert np.array_equal(b["lower_freq"], ref["ref.spec.lower_freq"]) and np.array_equal(b["delta_freq"], ref["ref.spec.delta_freq"])
+        assert np.array_equal(b["dirbin"], ref["ref.spec.dirbin"]), f"{config} ts{nts}: direction bins differ"
+        assert b["flux"].shape[0] == 1 + mabins and b["emission"].shape[0] == 1
+        close("flux", b["flux"][0], ref["ref.spec.flux"])
+        close("flux_res", b["flux"][1:], ref["ref.spec.flux_res"])
+        close("emission", b["emission"][0], ref["ref.spec.emission"])
+        close("trueemission", b["trueemission"][0], ref["ref.spec.trueemission"])
+        close("absorption", b["absorption"][0], ref["ref.spec.absorption"])
+        close("lc_lum", b["lc_lum"][0], ref["ref.lc.lum"])
+        close("lc_lumcmf", b["lc_lumcmf"][0], ref["ref.lc.lumcmf"])
+        close("lc_lum_res", b["lc_lum"][1:], ref["ref.lc.lum_res"])
+        close("lc_lumcmf_res", b["lc_lumcmf"][1:], ref["ref.lc.lumcmf_res"])
+        close("gamma_lc_lum", b["gamma_lc_lum"], ref["ref.lc.gamma_lum"])
+        close("gamma_lc_lumcmf", b["gamma_lc_lumcmf"], ref["ref.lc.gamma_lumcmf"])
+        assert np.count_nonzero(b["flux"][0]) > 100
+        # size-independent properties: the direction-resolved sets average to the angle-averaged one
+        np.testing.assert_allclose(b["flux"][1:].sum(axis=0) / mabins, b["flux"][0], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(b["lc_lum"][1:].sum(axis=0) / mabins, b["lc_lum"][0], rtol=1e-12, atol=0)
+        # the emission columns of a bin add up to its flux (every escaped r-packet of these fixtures has an emission type)
+        np.testing.assert_allclose(b["emission"][0].sum(axis=-1), b["flux"][0], rtol=1e-12, atol=0)
+        # (2) angle-averaged only, no decomposition: same flux, smaller outputs
+        eng.bin_escaped_packets(direction_bins=False, emission_absorption=0, nprocs_exspec=nprocs)
+        b0 = spectra_mod.binned(eng)
+        assert b0["flux"].shape[0] == 1 and "emission" not in b0
+        close("flux (angle-averaged only)", b0["flux"][0], ref["ref.spec.flux"])
+        # (3) the decomposition for every direction bin: set 0 as before, the sets of the bins average to it
+        eng.bin_escaped_packets(direction_bins=True, emission_absorption=2, nprocs_exspec=nprocs)
+        b2 = spectra_mod.binned(eng)
+        assert b2["emission"].shape[0] == 1 + mabins
+        close("emission (all sets)", b2["emission"][0], ref["ref.spec.emission"])
+        np.testing.assert_allclose(b2["absorption"][1:].sum(axis=0) / mabins, b2["absorption"][0], rtol=1e-12, atol=0)
+        # (4) nprocs_exspec divides everything
+        eng.bin_escaped_packets(direction_bins=False, emission_absorption=0, nprocs_exspec=4 * nprocs)
+        np.testing.assert_allclose(spectra_mod.binned(eng)["flux"][0] * 4, b0["flux"][0], rtol=1e-15, atol=0)
+        return b
+    finally:
+        eng.close()
