@@ -992,6 +992,26 @@ void emit_reference_spectra(Sink& s, const std::span<const Packet> packets) {
     dirbins[i] = (packets[i].type == TYPE_ESCAPE) ? get_escapedirectionbin(packets[i].dir) : -1;
   }
   s.arr("ref.spec.dirbin", dirbins.data(), static_cast<int64_t>(dirbins.size()));
+
+  // timing of the reference's binning on a bench-sized packet array (tools/bench_spectra.py): the packets replicated
+  // ARTISB200_TIME_SPECTRA times, binned like write_partial_lightcurve_spectra does at the end of a multi-dimensional run
+  // (spectrum_lightcurve.cc:316-337: dirbin -1 and then each of the MABINS direction bins, all packets every pass)
+  if (const char* rep = std::getenv("ARTISB200_TIME_SPECTRA"); rep != nullptr) {
+    const auto replicas = static_cast<size_t>(std::atol(rep));
+    std::vector<Packet> many;
+    many.reserve(replicas * packets.size());
+    for (size_t r = 0; r < replicas; r++) {
+      many.insert(many.end(), packets.begin(), packets.end());
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    double checksum = 0.;
+    for (int dirbin = -1; dirbin < MABINS; dirbin++) {
+      b200_bin_escaped_packets(many, dirbin, false, b);
+      checksum += b.lc_lum[0] + b.flux[0];
+    }
+    const auto wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printlnlog("ARTISB200_SPECTRA_TIMING npackets {} passes {} wall_s {:.6f} checksum {:g}", many.size(), 1 + MABINS, wall, checksum);
+  }
 }
 #endif
 

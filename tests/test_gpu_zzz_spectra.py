@@ -19,6 +19,7 @@ from tests import fixtures, parity_checks
 
 sys.path.insert(0, os.path.join(fixtures.ROOT, "oracle"))
 import spectra_oracle  # noqa: E402
+from bench_spectra import synthetic_packets  # noqa: E402  (tools/)
 
 pytestmark = pytest.mark.gpu
 SPECTRA_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy_1d", 3), ("classic_detailedbf_toy", 3)]
@@ -27,37 +28,6 @@ SPECTRA_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy_1d", 3
 @pytest.mark.parametrize("config,nts", SPECTRA_CASES)
 def test_binning_matches_the_reference(config, nts):
     parity_checks.check_spectra(ablib.library_path(fixtures.PRESET_OF[config]), config, nts)
-
-
-def synthetic_packets(static, n, seed=11, stride=240):
-    """random final packets over every branch of add_to_spec_res / add_to_lc_res: escaped r-packets and gamma packets, packets
-    still in flight, arrival times and frequencies inside and outside the binned ranges, every kind of emission type"""
-    rng = np.random.default_rng(seed)
-    pk = np.zeros(n, dtype=snap.packet_dtype(stride))
-    ts_start = static["timesteps.start"]
-    tmin, tmax = float(static["scalar.tmin"][0]), float(ts_start[-1])
-    rmax = float(static["scalar.rmax"][0])
-    nlines = static["line.nu"].size
-    nbf = static["cont.nu_edge"].size
-    kind = rng.random(n)
-    pk["type"] = np.where(kind < 0.8, 32, np.where(kind < 0.9, 11, 100))
-    pk["escape_type"] = np.where(rng.random(n) < 0.85, 11, np.where(rng.random(n) < 0.8, 10, 12))
-    v = rng.normal(size=(n, 3))
-    pk["dir"] = v / np.linalg.norm(v, axis=1)[:, None] * (1. + 1e-9 * rng.normal(size=n))[:, None]  # not exactly normalised
-    pk["pos"] = rng.normal(size=(n, 3)) * rmax * (tmax / tmin) * 0.3
-    pk["escape_time"] = np.exp(rng.uniform(np.log(tmin * 0.8), np.log(tmax * 1.3), size=n)).astype(np.float32)
-    pk["nu_rf"] = np.exp(rng.uniform(np.log(0.7e14), np.log(7e15), size=n))
-    pk["e_rf"] = rng.uniform(0.5, 1.5, size=n) * 1e40
-    pk["e_cmf"] = pk["e_rf"] * rng.uniform(0.9, 1.1, size=n)
-    for field in ("emissiontype", "trueemissiontype"):
-        sel = rng.random(n)
-        et = rng.integers(0, nlines, size=n)
-        et = np.where(sel < 0.5, et, np.where(sel < 0.75, -1 - rng.integers(0, max(nbf, 1), size=n), np.where(sel < 0.9, -9999999, -9999000)))
-        pk[field] = et
-    pk["absorptiontype"] = np.where(rng.random(n) < 0.6, rng.integers(0, nlines, size=n), -1)
-    pk["absorptionfreq"] = np.exp(rng.uniform(np.log(0.7e14), np.log(7e15), size=n))
-    pk["number"] = np.arange(n)
-    return pk
 
 
 def test_two_million_synthetic_packets_against_the_numpy_oracle():
