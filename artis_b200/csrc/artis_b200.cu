@@ -119,6 +119,13 @@ __global__ void k_build_cooling(const __grid_constant__ Tables T) {
   }
 }
 
+__global__ void k_build_cooling_totals(const __grid_constant__ Tables T) {
+  const int cell = T.win_lo + (blockIdx.x * blockDim.x) + threadIdx.x;
+  if (cell < T.win_hi) {
+    ab::build_ion_cooling_totals_cell(T, cell);
+  }
+}
+
 // ---- cell-sorted packet queues: counting sort of the active packets by (stage, model cell) -------------------
 // Packets are handed to the kernels in this order, so that the lanes of a warp start in the same cell and on the
 // same kind of packet (coalesced/broadcast table loads, same branch); it mirrors the reference's own sort of the
@@ -799,6 +806,34 @@ __global__ void __launch_bounds__(256) k_bin_escaped(const __grid_constant__ ab:
   }
 }
 
+// LTE part of the grid update (gridupdate.h): temperatures per cell, partition functions and Saha factors per (cell, ion),
+// ion balance and electron density per cell
+__global__ void k_lte_temperatures(const __grid_constant__ ab::GridUpdateView G, const int ncells) {
+  const int cell = (blockIdx.x * blockDim.x) + threadIdx.x;
+  if (cell < ncells) {
+    ab::lte_temperatures_cell(G, cell);
+  }
+}
+template <int WHAT>
+__global__ void k_lte_perion(const __grid_constant__ ab::Tables T, const __grid_constant__ ab::GridUpdateView G) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  if (i < static_cast<long long>(T.ncells) * T.nions) {
+    const int cell = static_cast<int>(i / T.nions);
+    const int uion = static_cast<int>(i % T.nions);
+    if constexpr (WHAT == 0) {
+      ab::lte_partfunct_item(T, G, cell, uion);
+    } else {
+      ab::lte_phi_item(T, G, cell, uion);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_lte_ion_balance(const __grid_constant__ ab::Tables T, const __grid_constant__ ab::GridUpdateView G) {
+  const int cell = (blockIdx.x * blockDim.x) + threadIdx.x;
+  if (cell < T.ncells) {
+    ab::lte_ion_balance_cell(T, G, cell);
+  }
+}
+
 struct CudaBackend {
   std::string error;
   int device{-1};
@@ -998,6 +1033,9 @@ struct CudaBackend {
     const long long nci = nwin * T.nions;
     if (nci > 0) {
       k_build_cooling<<<blocks_for(nci, B), B, 0, stream>>>(T);
+      if (T.device_cooling_contribs != 0) {
+        k_build_cooling_totals<<<blocks_for(nwin, B), B, 0, stream>>>(T);
+      }
     }
     // stats::Counter::UPDATECELL counts one cell-cache fill per cell (update_packets.cc:399)
     const long long ncells = T.ncells;
@@ -1018,6 +1056,26 @@ struct CudaBackend {
     k_bin_escaped<<<blocks, 256, (use_local != 0) ? smem : 0, stream>>>(T, S, n, use_local);
     cudaEventRecord(ev_stop, stream);
     if (!ok(cudaStreamSynchronize(stream), "k_bin_escaped") || !ok(cudaGetLastError(), "k_bin_escaped")) {
+      return false;
+    }
+    float elapsed = 0.F;
+    cudaEventElapsedTime(&elapsed, ev_start, ev_stop);
+    *ms = static_cast<double>(elapsed);
+    return true;
+  }
+
+  bool update_grid_lte(const ab::Tables& T, const ab::GridUpdateView& G, double* ms) {
+    cudaSetDevice(device);
+    const long long nci = static_cast<long long>(T.ncells) * T.nions;
+    cudaEventRecord(ev_start, stream);
+    if (G.temperatures_from_J != 0) {
+      k_lte_temperatures<<<blocks_for(T.ncells, 128), 128, 0, stream>>>(G, T.ncells);
+    }
+    k_lte_perion<0><<<blocks_for(nci, 128), 128, 0, stream>>>(T, G);
+    k_lte_perion<1><<<blocks_for(nci, 128), 128, 0, stream>>>(T, G);
+    k_lte_ion_balance<<<blocks_for(T.ncells, 128), 128, 0, stream>>>(T, G);
+    cudaEventRecord(ev_stop, stream);
+    if (!ok(cudaStreamSynchronize(stream), "update_grid_lte") || !ok(cudaGetLastError(), "update_grid_lte")) {
       return false;
     }
     float elapsed = 0.F;

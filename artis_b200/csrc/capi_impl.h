@@ -123,6 +123,14 @@ int artisb200_last_binning_ms(artisb200_ctx* ctx, double* ms) {
   return 0;
 }
 
+int artisb200_update_grid_lte(artisb200_ctx* ctx, int temperatures_from_J, double mintemp, double maxtemp) {
+  return ctx->eng.update_grid_lte(temperatures_from_J, mintemp, maxtemp);
+}
+int artisb200_last_gridupdate_ms(artisb200_ctx* ctx, double* ms) {
+  *ms = ctx->eng.last_gridupdate_ms;
+  return 0;
+}
+
 int artisb200_save_packets_device(artisb200_ctx* ctx) { return ctx->eng.save_packets_device(); }
 int artisb200_restore_packets_device(artisb200_ctx* ctx) { return ctx->eng.restore_packets_device(); }
 

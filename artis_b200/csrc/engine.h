@@ -18,6 +18,7 @@
 #include "options.h"
 #include "packet.h"
 #include "spectra.h"
+#include "gridupdate.h"
 #include "tables.h"
 
 namespace ab {
@@ -202,6 +203,7 @@ class Engine {
   long long spec_nnubins{1000};    // [spec_nnubins] MNUBINS (exspec.h:8)
   bool spec_record_dirbin{false};  // [spec_record_dirbin] keep every packet's direction bin ("spec.dirbin")
   double last_binning_ms{0.};
+  double last_gridupdate_ms{0.};
 
   int fail(const std::string& msg) {
     err = msg;
@@ -342,7 +344,8 @@ class Engine {
       return 0;
     }
     const FieldDesc* f = find_field(name);
-    const bool binned = (name.rfind("spec.", 0) == 0 || name.rfind("lc.", 0) == 0);  // outputs of bin_escaped_packets
+    // outputs of bin_escaped_packets and update_grid_lte
+    const bool binned = (name.rfind("spec.", 0) == 0 || name.rfind("lc.", 0) == 0 || name.rfind("gridupdate.", 0) == 0);
     if (f == nullptr && !binned) {
       return fail("unknown array name '" + name + "'");
     }
@@ -453,6 +456,10 @@ class Engine {
     } else if (name == "line_tau_table_max_mb") {
       line_tau_table_max_mb = value;
       outputs_allocated = false;
+    } else if (name == "device_cooling_contribs") {
+      // 1 = cell.ion_cooling_contribs (kpkt::calculate_cooling_rates, kpkt.cc:281-303) is evaluated by the per-cell table build
+      // instead of being handed over by the host
+      T.device_cooling_contribs = (value != 0) ? 1 : 0;
     } else if (name == "spec_nnubins") {
       if (value < 1) {
         return fail("option spec_nnubins: at least one frequency bin");
@@ -800,6 +807,12 @@ class Engine {
                                      "cell.kappagrey", "cell.clumpfactor", "cell.thick", "cell.elem_massfracs",
                                      "cell.ion_groundlevelpops", "cell.ion_partfuncts", "cell.ion_cooling_contribs",
                                      "cell.corrphotoionrenorm"};
+    if (T.device_cooling_contribs != 0 && count_of("cell.ion_cooling_contribs") != static_cast<int64_t>(T.ncells) * T.nions) {
+      // written by the table build: the library allocates it (readable with get_array like a host-set array)
+      if (!alloc_output("cell.ion_cooling_contribs", 'd', static_cast<int64_t>(T.ncells) * T.nions, &T.ion_cooling_contribs)) {
+        return fail("begin_timestep: allocation of cell.ion_cooling_contribs failed: " + be.last_error());
+      }
+    }
     for (const char* name : required) {
       if (count_of(name) < 0) {
         return fail(std::string("begin_timestep: per-timestep array '") + name + "' has not been set");
@@ -1228,6 +1241,82 @@ class Engine {
     if (dev_error[0] != 0) {
       return fail("bin_escaped_packets: packet " + std::to_string(dev_error[1]) +
                   " carries a bound-free emission type beyond the continuum list (spectrum_lightcurve.cc:197)");
+    }
+    return 0;
+  }
+
+  // LTE part of update_grid_cell for every cell, on the device copies of the cell state (gridupdate.h): the cell.* arrays
+  // are updated in place, so that the next begin_timestep builds its tables from them without a host round trip.
+  //   temperatures_from_J != 0: T_R = T_e = T_J = (pi J / sigma)^(1/4) clamped to [mintemp, maxtemp], W = 1, from est.J of the
+  //   timestep just propagated (after the caller's all-reduce) and cell.estimator_normfactor_over4pi; 0: temperatures as set
+  int update_grid_lte(const int temperatures_from_J, const double mintemp, const double maxtemp) {
+    if (!static_committed) {
+      return fail("update_grid_lte: commit_static must be called first");
+    }
+    if constexpr (opt::HAS_NLTE_LEVELS) {
+      return fail("update_grid_lte: this preset has NLTE level populations; its partition functions read the NLTE solver's "
+                  "populations (ltepop.cc:177-197), which stay on the host");
+    }
+    const int64_t nc = T.ncells;
+    const struct { const char* name; int64_t count; } needed[] = {
+        {"cell.Te", nc}, {"cell.TJ", nc}, {"cell.TR", nc}, {"cell.W", nc}, {"cell.nne", nc}, {"cell.rho", nc},
+        {"cell.elem_massfracs", nc * T.nelements}, {"cell.elem_numberdens", nc * T.nelements},
+        {"cell.ion_partfuncts", nc * T.nions}, {"cell.ion_groundlevelpops", nc * T.nions}};
+    for (const auto& need : needed) {
+      if (count_of(need.name) != need.count) {
+        return fail(std::string("update_grid_lte: ") + need.name + " must be set with " + std::to_string(need.count) + " entries");
+      }
+    }
+    const auto* e_nions = host<int>("elem.nions");
+    for (int e = 0; e < T.nelements; e++) {
+      if (e_nions[e] > GRID_MAX_IONS) {
+        return fail("update_grid_lte: more than " + std::to_string(GRID_MAX_IONS) + " ions in one element");
+      }
+    }
+    GridUpdateView G{};
+    G.Te = const_cast<float*>(T.Te);
+    G.TJ = const_cast<float*>(T.TJ);
+    G.TR = const_cast<float*>(T.TR);
+    G.W = const_cast<float*>(T.W);
+    G.nne = const_cast<float*>(T.nne);
+    G.ion_partfuncts = const_cast<float*>(T.ion_partfuncts);
+    G.ion_groundlevelpops = const_cast<float*>(T.ion_groundlevelpops);
+    G.rho = T.rho;
+    G.elem_massfracs = T.elem_massfracs;
+    G.elem_numberdens = T.elem_numberdens;
+    G.mintemp = mintemp;
+    G.maxtemp = maxtemp;
+    G.temperatures_from_J = (temperatures_from_J != 0) ? 1 : 0;
+    if (G.temperatures_from_J != 0) {
+      if (!outputs_allocated || T.est_J == nullptr || count_of("cell.estimator_normfactor_over4pi") != nc) {
+        return fail("update_grid_lte: temperatures from J need the J estimator of a propagated timestep and "
+                    "cell.estimator_normfactor_over4pi [Nc]");
+      }
+      if (!(mintemp > 0.) || !(maxtemp > mintemp)) {
+        return fail("update_grid_lte: 0 < mintemp < maxtemp (MINTEMP / MAXTEMP of artisoptions.h)");
+      }
+      G.J = T.est_J;
+      G.J_normfactor = T.J_normfactor;
+    }
+    bool ok = true;
+    ok = ok && alloc_output("gridupdate.phi", 'd', nc * T.nions, &G.phi);
+    ok = ok && alloc_output("gridupdate.uppermost_ion", 'i', nc * T.nelements, &G.uppermost_ion);
+    ok = ok && alloc_output("gridupdate.status", 'i', nc, &G.status);
+    if (!ok) {
+      return fail("update_grid_lte: allocation failed: " + be.last_error());
+    }
+    if (!be.update_grid_lte(T, G, &last_gridupdate_ms)) {
+      return fail("update_grid_lte: " + be.last_error());
+    }
+    std::vector<int> status(static_cast<size_t>(nc));
+    if (!be.d2h(status.data(), G.status, nc * 4)) {
+      return fail("update_grid_lte: reading the status failed: " + be.last_error());
+    }
+    for (int64_t cell = 0; cell < nc; cell++) {
+      if (status[cell] == 1) {
+        return fail("update_grid_lte: cell " + std::to_string(cell) + ": no electron density in [0, rho / m_H] balances the "
+                    "ions (ltepop.cc:289 assert_always)");
+      }
     }
     return 0;
   }

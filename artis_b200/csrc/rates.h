@@ -420,4 +420,19 @@ AHD void build_cooling_ion(const Tables& T, const int cell, const int uion) {
   }
 }
 
+// kpkt.cc:281-303 calculate_cooling_rates, the part the packets read: the running sum over the cell's ions of their total
+// cooling rates (kpkt::do_kpkt picks the ion from it, kpkt.cc:470-490). An ion's total is the last entry of its cumulative
+// list, which build_cooling_ion has just written (every addition to C_ion above is followed by a store), so the host's own
+// pass over every level and transition of every cell per timestep is not needed (option device_cooling_contribs).
+AHD void build_ion_cooling_totals_cell(const Tables& T, const int cell) {
+  double* out = const_cast<double*>(T.ion_cooling_contribs) + (static_cast<long long>(cell) * T.nions);
+  const double* contribs = T.cell_cooling_contrib + (static_cast<long long>(cell) * T.ncoolingterms);
+  double cumulative_cooling = 0.;
+  for (int uion = 0; uion < T.nions; uion++) {
+    const int nterms = T.ion_ncoolingterms[uion];
+    cumulative_cooling += (nterms > 0) ? contribs[T.ion_coolingoffset[uion] + nterms - 1] : 0.;
+    out[uion] = cumulative_cooling;
+  }
+}
+
 }  // namespace ab

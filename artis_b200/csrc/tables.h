@@ -103,6 +103,7 @@ namespace ab {
   X(double, corrphotoioncoeff_host, "cell.corrphotoioncoeff")       \
   X(float, prev_bfrate_normed, "radfield.prev_bfrate_normed")       \
   X(double, elem_numberdens, "cell.elem_numberdens")                \
+  X(double, J_normfactor, "cell.estimator_normfactor_over4pi")      \
   X(int, xcom_zstart, "xcom.zstart")                                \
   X(double, xcom_energy, "xcom.energy")                             \
   X(double, xcom_sigma, "xcom.sigma")                               \
@@ -398,6 +399,7 @@ struct Tables {
   double* cell_marecord;
 
   // run options
+  int device_cooling_contribs;  // 1 = cell.ion_cooling_contribs is written by the table build (rates.h build_ion_cooling_totals_cell)
   int rng_mode;
   unsigned long long seed;
   RngSetup rng_setup;  // (rng_mode, seed, timestep) in the form the generators read; refreshed before every propagation

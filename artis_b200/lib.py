@@ -36,6 +36,8 @@ _SIGNATURES = {
     "artisb200_commit_static": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_bin_escaped_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "artisb200_last_binning_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "artisb200_update_grid_lte": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
+    "artisb200_last_gridupdate_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "artisb200_begin_timestep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "artisb200_upload_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "artisb200_download_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
@@ -61,6 +63,9 @@ ESTIMATOR_NAMES = ["est.J", "est.nuJ", "est.ffheating", "est.colheating", "est.g
                    "est.dep_positron", "est.dep_electron", "est.dep_alpha", "ts.scalars", "ts.pellet_decays", "counters", "diag"]
 OPTIONAL_ESTIMATOR_NAMES = ["est.bins_J_raw", "est.bins_nuJ_raw", "est.bfrate_raw"]  # MULTIBIN / DETAILED_BF presets only
 _OUT_DTYPES = {"ts.pellet_decays": np.int64, "counters": np.int64, "diag": np.int64, "diag_stage": np.int64, "dev_error": np.int64, "built.cont_keepbits": np.uint64,
+               "gridupdate.uppermost_ion": np.int32, "gridupdate.status": np.int32,
+               "cell.Te": np.float32, "cell.TJ": np.float32, "cell.TR": np.float32, "cell.W": np.float32, "cell.nne": np.float32,
+               "cell.ion_partfuncts": np.float32, "cell.ion_groundlevelpops": np.float32,
                "spec.lower_freq": np.float32, "spec.delta_freq": np.float32, "spec.dirbin": np.int32}
 
 
@@ -174,6 +179,18 @@ class ArtisB200:
     def last_binning_ms(self):
         ms = ctypes.c_double()
         self.lib.artisb200_last_binning_ms(self.ctx, ctypes.byref(ms))
+        return ms.value
+
+    def update_grid_lte(self, temperatures_from_J=False, mintemp=0., maxtemp=0.):
+        """LTE part of update_grid_cell on the device copies of the cell state (include/artis_b200.h): partition functions,
+        Saha ion balance, electron density; optionally the temperatures from the J estimator first. Read the results with
+        get_array("cell.nne") / "cell.ion_groundlevelpops" / "cell.ion_partfuncts" / "cell.Te" / "gridupdate.uppermost_ion"."""
+        self._check(self.lib.artisb200_update_grid_lte(self.ctx, int(bool(temperatures_from_J)), float(mintemp), float(maxtemp)),
+                    "update_grid_lte")
+
+    def last_gridupdate_ms(self):
+        ms = ctypes.c_double()
+        self.lib.artisb200_last_gridupdate_ms(self.ctx, ctypes.byref(ms))
         return ms.value
 
     def save_packets_device(self):

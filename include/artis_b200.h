@@ -245,6 +245,25 @@ int artisb200_restore_packets_device(artisb200_ctx* ctx);
 int artisb200_bin_escaped_packets(artisb200_ctx* ctx, int direction_bins, int emission_absorption, int nprocs_exspec);
 int artisb200_last_binning_ms(artisb200_ctx* ctx, double* ms); /* device time of the last binning pass */
 
+/* LTE part of the per-cell grid update for every cell, on the device copies of the cell state: what
+ * update_grid_cell does in an LTE timestep / for a cell treated grey (update_grid.cc:520-545):
+ *   temperatures_from_J != 0:  T_R = T_e = T_J = (pi J / sigma)^(1/4) clamped to [mintemp, maxtemp] (MINTEMP / MAXTEMP of
+ *       artisoptions.h), W = 1 (radfield::get_T_J_from_J, radfield.cc:956-979), from est.J of the timestep just propagated
+ *       (all-reduced by the caller) times cell.estimator_normfactor_over4pi 'd'[Nc] = 1 / (4 pi dV dt nprocs)
+ *       (update_grid.cc:478-479, radfield::normalise_J); 0: the temperatures stay as set
+ *   partition functions of every ion (calculate_cellpartfuncts, ltepop.cc:204-240, 426-431)
+ *   Saha ionisation balance and electron density (calculate_ion_balance_nne with force_saha, ltepop.cc:475-532: uppermost
+ *       ions 308-355, electron density by TOMS 748 to 1e-3 like the reference 282-304, ground-level populations 433-473,
+ *       nne from the stored populations 242-250)
+ * Inputs beyond the per-timestep cell state: cell.elem_numberdens 'd'[Nc*nelements] (grid::get_elem_numberdens, grid.cc:1693).
+ * cell.Te/TJ/TR/W/nne/ion_partfuncts/ion_groundlevelpops are updated IN PLACE on the device (read them back with
+ * artisb200_get_array; the next artisb200_begin_timestep builds its tables from them without a host round trip);
+ * gridupdate.uppermost_ion 'i'[Nc*nelements] (grid::elements_uppermost_ion_allcells), gridupdate.status 'i'[Nc] (2 = the
+ * root find used all 50 evaluations: the reference warns and carries on). Fails like the reference's assert_always
+ * (ltepop.cc:289) when no electron density in [0, rho/m_H] balances a cell. Presets with NLTE level populations are refused. */
+int artisb200_update_grid_lte(artisb200_ctx* ctx, int temperatures_from_J, double mintemp, double maxtemp);
+int artisb200_last_gridupdate_ms(artisb200_ctx* ctx, double* ms); /* device time of the last grid update */
+
 /* One packed device buffer [J|nuJ|ffheating|colheating|gamma|bfheating|dep_*|ts.scalars|bins_J_raw|bins_nuJ_raw] of f64 for the
  * per-timestep all-reduce (replaces the MPI_Allreduce calls at sn3d.cc:565-625 and radfield.cc:988-1030).
  * The caller (torch.distributed / NCCL) reduces it in place. */

@@ -56,6 +56,7 @@
 #include "gammapkt.h"
 #include "globals.h"
 #include "grid.h"
+#include "ltepop.h"
 #include "kpkt.h"
 #include "mpi_logging.h"
 #include "nltepop.h"
@@ -1015,6 +1016,108 @@ void emit_reference_spectra(Sink& s, const std::span<const Packet> packets) {
 }
 #endif
 
+#ifdef ARTISB200_WITH_REFERENCE
+// Known answers for the LTE part of update_grid_cell (update_grid.cc:520-545): for every cell the
+// reference's own radfield::get_T_J_from_J on a ladder of J values, and calculate_cellpartfuncts + calculate_ion_balance_nne
+// (ltepop.cc:426-532) in Saha mode on the cell state as it is (temperatures, density, composition). The cell state is put back.
+template <class Sink>
+void emit_reference_lte_gridupdate(Sink& s) {
+  const auto nc = static_cast<int64_t>(grid::get_nonempty_npts_model());
+  const int nelements = get_nelements();
+  const auto nions = static_cast<int64_t>(get_includedions());
+  std::vector<double> numberdens(nc * nelements);
+  for (int64_t cell = 0; cell < nc; cell++) {
+    for (int e = 0; e < nelements; e++) {
+      numberdens[(cell * nelements) + e] = grid::get_elem_numberdens(cell, e);
+    }
+  }
+  s.arr("cell.elem_numberdens", numberdens.data(), nc * nelements);
+  s.f64("ref.grid.mintemp", MINTEMP);
+  s.f64("ref.grid.maxtemp", MAXTEMP);
+
+  auto J = radfield::b200_J();
+  std::vector<double> J_test(nc);
+  std::vector<float> T_J(nc);
+  for (int64_t cell = 0; cell < nc; cell++) {
+    const double save = J[cell];
+    const double temperature = 800. * std::pow(400., static_cast<double>(cell) / static_cast<double>(nc > 1 ? nc - 1 : 1));
+    J_test[cell] = (cell % 17 == 5) ? std::numeric_limits<double>::infinity() : STEBO / PI * std::pow(temperature, 4.);
+    J[cell] = J_test[cell];
+    T_J[cell] = radfield::get_T_J_from_J(static_cast<int>(cell));
+    J[cell] = save;
+  }
+  s.arr("ref.grid.J_test", J_test.data(), nc);
+  s.arr("ref.grid.T_J_from_J", T_J.data(), nc);
+
+  std::vector<float> save_nne(nc);
+  std::vector<float> save_ground(grid::ion_groundlevelpops_allcells.data(), grid::ion_groundlevelpops_allcells.data() + (nc * nions));
+  std::vector<float> save_partf(grid::ion_partfuncts_allcells.data(), grid::ion_partfuncts_allcells.data() + (nc * nions));
+  std::vector<int> save_upper(nc * nelements);
+  for (int64_t cell = 0; cell < nc; cell++) {
+    save_nne[cell] = grid::get_nne(static_cast<int>(cell));
+    for (int e = 0; e < nelements; e++) {
+      save_upper[(cell * nelements) + e] = grid::get_elements_uppermost_ion(static_cast<int>(cell), e);
+    }
+  }
+  const bool save_lte = globals::lte_iteration;
+  globals::lte_iteration = true;
+  std::vector<float> ref_nne(nc);
+  std::vector<int> ref_upper(nc * nelements);
+  for (int64_t cell = 0; cell < nc; cell++) {
+    for (int e = 0; e < nelements; e++) {
+      calculate_cellpartfuncts(static_cast<int>(cell), e);
+    }
+    calculate_ion_balance_nne(static_cast<int>(cell));
+    ref_nne[cell] = grid::get_nne(static_cast<int>(cell));
+    for (int e = 0; e < nelements; e++) {
+      ref_upper[(cell * nelements) + e] = grid::get_elements_uppermost_ion(static_cast<int>(cell), e);
+    }
+  }
+  s.arr("ref.grid.nne", ref_nne.data(), nc);
+  s.arr("ref.grid.uppermost_ion", ref_upper.data(), nc * nelements);
+  s.arr("ref.grid.ion_partfuncts", grid::ion_partfuncts_allcells.data(), nc * nions);
+  s.arr("ref.grid.ion_groundlevelpops", grid::ion_groundlevelpops_allcells.data(), nc * nions);
+
+  // the same on a temperature ladder from 60 K to 150 000 K over the cells (densities and compositions as they are): the cold
+  // end overflows the Saha factors, which truncates the ion lists (ltepop.cc:343-352) and, at the very bottom, leaves only
+  // the lowest ion stages (set_groundlevelpops_neutral, ltepop.cc:254-278)
+  std::vector<float> save_Te(grid::Te_allcells.data(), grid::Te_allcells.data() + nc);
+  std::vector<float> save_TJ(grid::TJ_allcells.data(), grid::TJ_allcells.data() + nc);
+  std::vector<float> ladder(nc);
+  for (int64_t cell = 0; cell < nc; cell++) {
+    ladder[cell] = static_cast<float>(60. * std::pow(2500., static_cast<double>(cell) / static_cast<double>(nc > 1 ? nc - 1 : 1)));
+    grid::Te_allcells[cell] = ladder[cell];
+    grid::TJ_allcells[cell] = ladder[cell];
+  }
+  for (int64_t cell = 0; cell < nc; cell++) {
+    for (int e = 0; e < nelements; e++) {
+      calculate_cellpartfuncts(static_cast<int>(cell), e);
+    }
+    calculate_ion_balance_nne(static_cast<int>(cell));
+    ref_nne[cell] = grid::get_nne(static_cast<int>(cell));
+    for (int e = 0; e < nelements; e++) {
+      ref_upper[(cell * nelements) + e] = grid::get_elements_uppermost_ion(static_cast<int>(cell), e);
+    }
+  }
+  s.arr("ref.grid.ladder_T", ladder.data(), nc);
+  s.arr("ref.grid.ladder_nne", ref_nne.data(), nc);
+  s.arr("ref.grid.ladder_uppermost_ion", ref_upper.data(), nc * nelements);
+  s.arr("ref.grid.ladder_ion_partfuncts", grid::ion_partfuncts_allcells.data(), nc * nions);
+  s.arr("ref.grid.ladder_ion_groundlevelpops", grid::ion_groundlevelpops_allcells.data(), nc * nions);
+  std::copy(save_Te.begin(), save_Te.end(), grid::Te_allcells.data());
+  std::copy(save_TJ.begin(), save_TJ.end(), grid::TJ_allcells.data());
+  globals::lte_iteration = save_lte;
+  std::copy(save_ground.begin(), save_ground.end(), grid::ion_groundlevelpops_allcells.data());
+  std::copy(save_partf.begin(), save_partf.end(), grid::ion_partfuncts_allcells.data());
+  for (int64_t cell = 0; cell < nc; cell++) {
+    grid::set_nne(static_cast<int>(cell), save_nne[cell]);
+    for (int e = 0; e < nelements; e++) {
+      grid::set_elements_uppermost_ion(static_cast<int>(cell), e, save_upper[(cell * nelements) + e]);
+    }
+  }
+}
+#endif
+
 auto dump_requested(const int nts) -> bool {
   const char* dir = std::getenv("ARTISB200_DUMP_DIR");
   if (dir == nullptr) {
@@ -1049,6 +1152,11 @@ void update_packets(const int nts, std::span<Packet> packets) {
     emit_timestep_state(w, nts);
     emit_packets(w, packets);
     emit_estimators(w, nts);  // the pre-existing (normally zero) values, so that "after - before" is this call's work
+#ifdef ARTISB200_WITH_REFERENCE
+    if (std::getenv("ARTISB200_DUMP_GRID") != nullptr) {
+      emit_reference_lte_gridupdate(w);
+    }
+#endif
   }
 
   const auto t0 = std::chrono::steady_clock::now();

@@ -99,6 +99,9 @@ struct HostBackend {
       for (int uion = 0; uion < T.nions; uion++) {
         ab::build_cooling_ion(T, cell, uion);
       }
+      if (T.device_cooling_contribs != 0) {
+        ab::build_ion_cooling_totals_cell(T, cell);
+      }
     }
     T.counters[ab::CNT_UPDATECELL] = T.ncells;  // one cell-cache fill per cell (update_packets.cc:399)
     return true;
@@ -108,6 +111,24 @@ struct HostBackend {
     const auto t0 = std::chrono::steady_clock::now();
     for (long long ip = 0; ip < n; ip++) {
       ab::bin_escaped_packet(T, S, ip, nullptr);
+    }
+    *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+  }
+
+  bool update_grid_lte(const ab::Tables& T, const ab::GridUpdateView& G, double* ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int cell = 0; cell < T.ncells; cell++) {
+      if (G.temperatures_from_J != 0) {
+        ab::lte_temperatures_cell(G, cell);
+      }
+      for (int uion = 0; uion < T.nions; uion++) {
+        ab::lte_partfunct_item(T, G, cell, uion);
+      }
+      for (int uion = 0; uion < T.nions; uion++) {
+        ab::lte_phi_item(T, G, cell, uion);
+      }
+      ab::lte_ion_balance_cell(T, G, cell);
     }
     *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return true;

@@ -291,3 +291,133 @@ def check_spectra(libpath, config, nts, device=0, rel=1e-12):
         return b
     finally:
         eng.close()
+
+
+def _float_ulps(a, b):
+    """distance in float32 representable numbers"""
+    ia = np.asarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    ib = np.asarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+def check_grid_update_lte(libpath, config, nts, device=0, max_ulps=0):
+    """partition functions, Saha ion balance, electron density (TOMS 748 to 1e-3) and the temperatures from J
+    of every cell against the reference's own calculate_cellpartfuncts / calculate_ion_balance_nne / get_T_J_from_J
+    (tests/golden/make_golden_grid.py). The results are float32 like the reference's grid arrays: `max_ulps` float32 steps
+    (0 on the host build; the device's exp / pow differ from glibc's in the last bits of the double they are rounded from)."""
+    fx = fixtures.load_golden(config, nts)
+    ref = dict(np.load(os.path.join(fixtures.GOLDEN_DIR, f"{config}_grid_ts{nts}.npz")))
+    eng = fixtures.ablib.ArtisB200(libpath=libpath, device=device)
+    try:
+        eng.set_arrays(fx["static"])
+        eng.commit_static()
+        before = dict(fx["before"])
+        before["cell.elem_numberdens"] = ref["cell.elem_numberdens"]
+        nc = before["cell.Te"].size
+        # start from a state that the call has to overwrite: wrong electron densities and ground-level populations
+        before["cell.nne"] = np.full(nc, 1.0, dtype=np.float32)
+        eng.set_arrays(before)
+        eng.update_grid_lte()
+        got = {k: eng.get_array(k) for k in ("cell.nne", "cell.ion_partfuncts", "cell.ion_groundlevelpops", "cell.Te",
+                                             "gridupdate.uppermost_ion", "gridupdate.status")}
+        assert np.array_equal(got["cell.Te"], fx["before"]["cell.Te"])  # temperatures untouched in this mode
+        assert np.array_equal(got["gridupdate.uppermost_ion"], ref["ref.grid.uppermost_ion"]), "uppermost ions differ"
+        assert not np.any(got["gridupdate.status"] == 1)
+        for key, refkey in (("cell.ion_partfuncts", "ref.grid.ion_partfuncts"), ("cell.nne", "ref.grid.nne"),
+                            ("cell.ion_groundlevelpops", "ref.grid.ion_groundlevelpops")):
+            ulps = _float_ulps(got[key], ref[refkey])
+            assert ulps.max() <= max_ulps, f"{config} ts{nts} {key}: {np.count_nonzero(ulps > max_ulps)} of {ulps.size} values differ " \
+                                            f"by up to {ulps.max()} float32 steps"
+        # idempotence: the balance of a balanced state is the same state (the partition functions no longer change)
+        eng.update_grid_lte()
+        for key in ("cell.nne", "cell.ion_partfuncts", "cell.ion_groundlevelpops"):
+            assert _float_ulps(eng.get_array(key), got[key]).max() <= max(max_ulps, 1), key
+        # charge conservation of the result: nne = sum over ions of charge x population
+        nions = fx["static"]["ion.nlevels"].size
+        g0 = fx["static"]["level.statweight"][fx["static"]["ion.uniquelevelindexstart"]].astype(np.float64)
+        charge = np.concatenate([fx["static"]["elem.lowest_ionstage"][e] + np.arange(n) - 1
+                                 for e, n in enumerate(fx["static"]["elem.nions"])]).astype(np.float64)
+        pops = got["cell.ion_groundlevelpops"].astype(np.float64).reshape(nc, nions) * \
+            got["cell.ion_partfuncts"].astype(np.float64).reshape(nc, nions) / g0
+        np.testing.assert_allclose((pops * charge).sum(axis=1), got["cell.nne"], rtol=1e-6)
+
+        # the same on the reference's temperature ladder 60 K .. 150 000 K: truncated ion lists, lowest-stage-only cells
+        if "ref.grid.ladder_T" in ref:
+            eng.set_arrays(before)
+            eng.set_array("cell.Te", ref["ref.grid.ladder_T"])
+            eng.set_array("cell.TJ", ref["ref.grid.ladder_T"])
+            eng.update_grid_lte()
+            upper = eng.get_array("gridupdate.uppermost_ion")
+            assert np.array_equal(upper, ref["ref.grid.ladder_uppermost_ion"]), "ladder: uppermost ions differ"
+            assert upper.min() == 0 and len(np.unique(upper)) >= 2  # the truncation (and the neutral branch) is exercised
+            for key, refkey in (("cell.ion_partfuncts", "ref.grid.ladder_ion_partfuncts"), ("cell.nne", "ref.grid.ladder_nne"),
+                                ("cell.ion_groundlevelpops", "ref.grid.ladder_ion_groundlevelpops")):
+                ulps = _float_ulps(eng.get_array(key), ref[refkey])
+                assert ulps.max() <= max_ulps, f"{config} ts{nts} ladder {key}: {np.count_nonzero(ulps > max_ulps)} of {ulps.size} " \
+                                                f"values differ by up to {ulps.max()} float32 steps"
+
+        # temperatures from the J estimator (get_T_J_from_J): needs the estimator buffer of a timestep
+        eng.set_arrays(fx["before"])
+        eng.set_array("cell.elem_numberdens", ref["cell.elem_numberdens"])
+        eng.begin_timestep(nts)
+        n = int(fx["before"]["packets.count"][0])
+        stride = int(fx["before"]["packets.stride"][0])
+        aos = fx["before"]["packets.aos"].copy()
+        eng.set_option("rng_mode", 1)
+        eng.update_packets_host(nts, aos, n, stride)
+        J = eng.get_array("est.J")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            factor = np.where(J > 0, ref["ref.grid.J_test"] / J, np.inf)  # so that J x factor is the reference's test value
+        usable = np.isfinite(factor) | np.isinf(ref["ref.grid.J_test"])
+        eng.set_array("cell.estimator_normfactor_over4pi", np.where(np.isfinite(factor), factor, np.inf))
+        eng.update_grid_lte(temperatures_from_J=True, mintemp=float(ref["ref.grid.mintemp"][0]), maxtemp=float(ref["ref.grid.maxtemp"][0]))
+        T_J = eng.get_array("cell.TJ")
+        finite_target = np.isfinite(ref["ref.grid.J_test"]) & usable & (J > 0)
+        # J x (J_test / J) reproduces J_test to an ulp: one float32 step more than the kernel's own tolerance
+        ulps = _float_ulps(T_J[finite_target], ref["ref.grid.T_J_from_J"][finite_target])
+        assert finite_target.sum() > 0 and ulps.max() <= max_ulps + 1, f"T_J: up to {ulps.max()} float32 steps"
+        if finite_target.sum() > nc // 2:  # (the bench-scale fixture has 2000 packets for 3684 cells: most cells see no packet)
+            clamped = ref["ref.grid.T_J_from_J"][finite_target]
+            assert clamped.min() == ref["ref.grid.mintemp"][0] and clamped.max() == ref["ref.grid.maxtemp"][0]  # both clamps exercised
+        keep = np.isinf(ref["ref.grid.J_test"]) & (J > 0)
+        assert np.array_equal(T_J[keep], fx["before"]["cell.TJ"][keep])  # non-finite estimator: the old value is kept
+        assert np.array_equal(eng.get_array("cell.Te"), T_J) and np.array_equal(eng.get_array("cell.TR"), T_J)
+        assert np.all(eng.get_array("cell.W") == 1.)
+        return eng.last_gridupdate_ms()
+    finally:
+        eng.close()
+
+
+def check_device_cooling_contribs(libpath, config, nts, device=0, rel=REL_TOL, tol=1e-9, options=None):
+    """kpkt::calculate_cooling_rates (kpkt.cc:281-303) evaluated by the per-cell table build (option device_cooling_contribs)
+    instead of being handed over by the host: cell.ion_cooling_contribs against the reference's own values, and the packet
+    histories of the timestep (k-packets pick their ion from it) unchanged. The host array is zeroed to prove who wrote it."""
+    fx = fixtures.load_golden(config, nts)
+    want = fx["before"]["cell.ion_cooling_contribs"]
+    fx2 = dict(fx)
+    fx2["before"] = dict(fx["before"])
+    fx2["before"]["cell.ion_cooling_contribs"] = np.zeros_like(want)
+    opts = {"device_cooling_contribs": 1}
+    opts.update(options or {})
+    eng = fixtures.make_engine(libpath, fx2, rng="xoshiro", device=device, options=opts)
+    try:
+        def check_totals():
+            got = eng.get_array("cell.ion_cooling_contribs")
+            err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+            assert want.max() > 0 and err.max() <= rel, f"{config} ts{nts}: ion cooling contributions differ by {err.max()}"
+
+        windowed = "table_window_cells" in opts  # then a cell's totals are written by the pass that builds its tables
+        if not windowed:
+            check_totals()
+        n = int(fx["before"]["packets.count"][0])
+        stride = int(fx["before"]["packets.stride"][0])
+        aos = fx["before"]["packets.aos"].copy()
+        eng.update_packets_host(nts, aos, n, stride)
+        est = eng.estimators()
+        check_totals()
+        from artis_b200 import snapshot as snap
+        frac_ok, worst, est_err = compare_run.compare(aos.view(snap.packet_dtype(stride)), est, fx["after"], tol=tol, verbose=False)
+        assert frac_ok == 1.0, f"{config} ts{nts}: {100 * (1 - frac_ok):.3f} % of the packets differ with device-side cooling totals"
+        assert int(est["counters"][fixtures.INTERACTIONS]) == int(fx["after"]["counters"][fixtures.INTERACTIONS])
+    finally:
+        eng.close()
