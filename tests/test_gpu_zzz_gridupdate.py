@@ -1,7 +1,8 @@
 """GPU parity of the LTE grid update (artisb200_update_grid_lte): every cell's partition functions, Saha
 ion balance, electron density and temperature from J against the reference's own functions (tests/golden/*_grid_ts*.npz),
-toy grids and the bench-scale model (3 684 cells, 20 ions, 2 400 levels). One float32 step: the device's exp / pow are not
-glibc's (tests/test_gridupdate.py reproduces that on the host). Collected after the hot-path parity tests (file name)."""
+toy grids and the bench-scale model (3 684 cells, 20 ions, 2 400 levels). One float32 step for the partition functions (the
+device's exp / pow are not glibc's), four for the electron density and what follows from it (the reference takes that root to
+1e-3 only; tests/parity_checks.py check_grid_update_lte says why; tests/test_gridupdate.py reproduces both on the host). Collected after the hot-path parity tests (file name)."""
 import pytest
 
 from artis_b200 import lib as ablib
@@ -13,7 +14,7 @@ GRID_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy_1d", 3), 
 
 @pytest.mark.parametrize("config,nts", GRID_CASES)
 def test_lte_grid_update_matches_the_reference(config, nts):
-    ms = parity_checks.check_grid_update_lte(ablib.library_path(fixtures.PRESET_OF[config]), config, nts, max_ulps=1)
+    ms = parity_checks.check_grid_update_lte(ablib.library_path(fixtures.PRESET_OF[config]), config, nts, max_ulps=1, max_ulps_balance=4)
     print(f"[gridupdate] {config}: LTE update of all cells in {ms:.3f} ms on the device")
 
 

@@ -18,12 +18,13 @@ def test_lte_grid_update_matches_the_reference(config, nts):
     parity_checks.check_grid_update_lte(fixtures.hostsim_library(fixtures.PRESET_OF[config]), config, nts, max_ulps=0)
 
 
-@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4)])
+@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4), ("kilonova_2d_kat", 2)])
 def test_lte_grid_update_with_another_libm(config, nts):
-    # exp / pow moved by -1 / 0 / +1 ulp (tests/hostsim, ARTISB200_HOSTSIM_FUZZ_LIBM), as on the device: the electron density
-    # root (TOMS 748 to 1e-3) and the populations stay within one float32 step: the tolerance of the GPU test
+    # exp / pow moved by -1 / 0 / +1 ulp (tests/hostsim, ARTISB200_HOSTSIM_FUZZ_LIBM), as on the device: the partition functions
+    # stay within one float32 step, the electron density root (TOMS 748 to 1e-3) and the populations within four: the
+    # tolerances of the GPU test
     lib = fixtures.hostsim_library(fixtures.PRESET_OF[config], defines=("ARTISB200_HOSTSIM_FUZZ_LIBM",), tag="_fuzz")
-    parity_checks.check_grid_update_lte(lib, config, nts, max_ulps=1)
+    parity_checks.check_grid_update_lte(lib, config, nts, max_ulps=1, max_ulps_balance=4)
 
 
 def test_lte_grid_update_reports_misuse():
