@@ -126,6 +126,20 @@ __global__ void k_build_cooling_totals(const __grid_constant__ Tables T) {
   }
 }
 
+__global__ void k_build_expopac_bins(const __grid_constant__ Tables T) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(T.win_hi - T.win_lo) * ab::expopac_nbins;
+  if (idx < total) {
+    ab::build_expopac_bin(T, T.win_lo + static_cast<int>(idx / ab::expopac_nbins), static_cast<int>(idx % ab::expopac_nbins));
+  }
+}
+__global__ void k_build_expopac_planck(const __grid_constant__ Tables T) {
+  const int cell = T.win_lo + (blockIdx.x * blockDim.x) + threadIdx.x;
+  if (cell < T.win_hi) {
+    ab::build_expopac_planck_cell(T, cell, T.expansionopacities + (static_cast<long long>(cell) * ab::expopac_nbins));
+  }
+}
+
 // ---- cell-sorted packet queues: counting sort of the active packets by (stage, model cell) -------------------
 // Packets are handed to the kernels in this order, so that the lanes of a warp start in the same cell and on the
 // same kind of packet (coalesced/broadcast table loads, same branch); it mirrors the reference's own sort of the
@@ -1035,6 +1049,12 @@ struct CudaBackend {
       k_build_cooling<<<blocks_for(nci, B), B, 0, stream>>>(T);
       if (T.device_cooling_contribs != 0) {
         k_build_cooling_totals<<<blocks_for(nwin, B), B, 0, stream>>>(T);
+      }
+    }
+    if (T.device_expansion_opacities != 0 && nwin > 0) {
+      k_build_expopac_bins<<<blocks_for(nwin * ab::expopac_nbins, B), B, 0, stream>>>(T);
+      if constexpr (opt::HAS_BB_THERMALISATION_PROBABILITY) {
+        k_build_expopac_planck<<<blocks_for(nwin, 64), 64, 0, stream>>>(T);
       }
     }
     // stats::Counter::UPDATECELL counts one cell-cache fill per cell (update_packets.cc:399)

@@ -6,6 +6,7 @@
 
 #include "../../include/artis_b200.h"
 #include "engine.h"
+#include "packetio.h"
 
 struct artisb200_ctx {
   ab::Engine<ActiveBackend> eng;
@@ -129,6 +130,31 @@ int artisb200_update_grid_lte(artisb200_ctx* ctx, int temperatures_from_J, doubl
 int artisb200_last_gridupdate_ms(artisb200_ctx* ctx, double* ms) {
   *ms = ctx->eng.last_gridupdate_ms;
   return 0;
+}
+
+namespace {
+int packetio_result(artisb200_ctx* ctx, const std::string& error) {
+  if (error.empty()) {
+    return 0;
+  }
+  if (ctx != nullptr) {
+    return ctx->eng.fail(error);
+  }
+  g_create_error = error;
+  return 1;
+}
+}  // namespace
+
+int artisb200_write_text_packets(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes,
+                                 int keep_escaped_gammas) {
+  return packetio_result(ctx, ab::write_text_packets(filename, packets_aos, npackets, stride_bytes, opt::POL_ON, keep_escaped_gammas != 0));
+}
+int artisb200_write_temp_packetsfile(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes) {
+  return packetio_result(ctx, ab::write_temp_packetsfile(filename, packets_aos, npackets, stride_bytes));
+}
+int artisb200_read_temp_packetsfile(artisb200_ctx* ctx, const char* filename, void* packets_aos, int64_t capacity, int stride_bytes,
+                                    int64_t* npackets) {
+  return packetio_result(ctx, ab::read_temp_packetsfile(filename, packets_aos, capacity, stride_bytes, npackets));
 }
 
 int artisb200_save_packets_device(artisb200_ctx* ctx) { return ctx->eng.save_packets_device(); }

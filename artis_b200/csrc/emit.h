@@ -116,17 +116,8 @@ AHD double sample_planck_montecarlo(const double T, Rng& rng) {
 
 // ---- expansion-opacity wavelength grid (rpkt.h:23-44): bins of 20 Angstrom from 60 to 40000 Angstrom, ordered by
 // ascending wavelength = descending frequency
-// (the grid constants are in tables.h)
+// (the grid constants and the bin edges expopac_bin_nu_upper / expopac_bin_nu_lower are in tables.h)
 
-AHD double expopac_bin_nu_upper(const int binindex) {
-  const double lambda_lower = expopac_lambdamin + (static_cast<double>(binindex) * expopac_deltalambda);
-  return 1e8 * CLIGHT / lambda_lower;
-}
-
-AHD double expopac_bin_nu_lower(const int binindex) {
-  const double lambda_upper = expopac_lambdamin + (static_cast<double>(binindex + 1) * expopac_deltalambda);
-  return 1e8 * CLIGHT / lambda_upper;
-}
 
 // sn3d.h:115-122: floor((value - minvalue) / binwidth) as an integer (negative below the grid)
 AHD long long linearbinindex(const double value, const double minvalue, const double binwidth) {

@@ -262,7 +262,7 @@ class Engine {
 
   static bool keep_hostcopy(const std::string& name) {
     return name.rfind("elem.", 0) == 0 || name.rfind("ion.", 0) == 0 || name.rfind("level.", 0) == 0 || name.rfind("cont.", 0) == 0 ||
-           name.rfind("timesteps.", 0) == 0 || name == "lut.temperature_grid";
+           name.rfind("timesteps.", 0) == 0 || name == "lut.temperature_grid" || name == "line.nu";
   }
 
   template <class U>
@@ -270,6 +270,8 @@ class Engine {
     const auto it = arrays.find(name);
     return (it == arrays.end() || it->second.hostcopy.empty()) ? nullptr : reinterpret_cast<const U*>(it->second.hostcopy.data());
   }
+
+  const double* host_or_fetch_line_nu() const { return host<double>("line.nu"); }
 
   int64_t count_of(const std::string& name) const {
     const auto it = arrays.find(name);
@@ -460,6 +462,10 @@ class Engine {
       // 1 = cell.ion_cooling_contribs (kpkt::calculate_cooling_rates, kpkt.cc:281-303) is evaluated by the per-cell table build
       // instead of being handed over by the host
       T.device_cooling_contribs = (value != 0) ? 1 : 0;
+    } else if (name == "device_expansion_opacities") {
+      // 1 = cell.expansionopacities / cell.expopac_planck_cumulative (calculate_expansion_opacities, rpkt.cc:1071-1123) are
+      // evaluated by the per-cell table build instead of being handed over by the host
+      T.device_expansion_opacities = (value != 0) ? 1 : 0;
     } else if (name == "spec_nnubins") {
       if (value < 1) {
         return fail("option spec_nnubins: at least one frequency bin");
@@ -664,6 +670,29 @@ class Engine {
     if (!make_derived("derived.phixstarget_bfestimindex", phixstarget_bfestimindex, &T.phixstarget_bfestimindex)) {
       return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
     }
+    {
+      // first line of every expansion-opacity wavelength bin: the reference starts at the first line at or below the upper
+      // edge of bin 0 and gives bin b the lines down to its lower edge (rpkt.cc:1086-1098); static, the line list is sorted
+      const auto* l_nu = host_or_fetch_line_nu();
+      std::vector<int> binstart(static_cast<size_t>(expopac_nbins) + 1, T.nlines);
+      if (l_nu != nullptr) {
+        int lineindex = 0;
+        while (lineindex < T.nlines && l_nu[lineindex] > expopac_bin_nu_upper(0)) {
+          lineindex++;
+        }
+        for (int b = 0; b < expopac_nbins; b++) {
+          binstart[b] = lineindex;
+          const double nu_lower = expopac_bin_nu_lower(b);
+          while (lineindex < T.nlines && l_nu[lineindex] >= nu_lower) {
+            lineindex++;
+          }
+        }
+        binstart[expopac_nbins] = lineindex;
+      }
+      if (!make_derived("derived.expopac_binstart", binstart, &T.expopac_binstart)) {
+        return fail("commit_static: device allocation of derived tables failed: " + be.last_error());
+      }
+    }
     if (!make_derived("derived.ion_element", ion_element, &T.ion_element) ||
         !make_derived("derived.ion_index", ion_index, &T.ion_index) ||
         !make_derived("derived.elem_has_nlte_levels", elem_has_nlte, &T.elem_has_nlte_levels) ||
@@ -840,6 +869,23 @@ class Engine {
           count_of("cell.elem_numberdens") != static_cast<int64_t>(T.ncells) * T.nelements) {
         return fail("begin_timestep: xcom.zstart [101], xcom.energy / xcom.sigma and cell.elem_numberdens [ncells x nelements] "
                     "are required (USE_XCOM_GAMMAPHOTOION)");
+      }
+    }
+    if (T.device_expansion_opacities != 0) {
+      const int64_t want = static_cast<int64_t>(T.ncells) * expopac_nbins;
+      if constexpr (!opt::RPKT_USE_EXPANSION_OPACITIES && !opt::HAS_BB_THERMALISATION_PROBABILITY) {
+        return fail("begin_timestep: device_expansion_opacities is set, but this preset reads no expansion opacities");
+      }
+      // the bin opacities are needed in both modes (the cumulative is built from them); the library allocates what the host
+      // did not set
+      if (count_of("cell.expansionopacities") != want && !alloc_output("cell.expansionopacities", 'f', want, &T.expansionopacities)) {
+        return fail("begin_timestep: allocation of cell.expansionopacities failed: " + be.last_error());
+      }
+      if constexpr (opt::HAS_BB_THERMALISATION_PROBABILITY) {
+        if (count_of("cell.expopac_planck_cumulative") != want &&
+            !alloc_output("cell.expopac_planck_cumulative", 'd', want, &T.expopac_planck_cumulative)) {
+          return fail("begin_timestep: allocation of cell.expopac_planck_cumulative failed: " + be.last_error());
+        }
       }
     }
     if constexpr (opt::RPKT_USE_EXPANSION_OPACITIES) {

@@ -435,4 +435,55 @@ AHD void build_ion_cooling_totals_cell(const Tables& T, const int cell) {
   }
 }
 
+// rpkt.cc:1071-1123 calculate_expansion_opacities, one wavelength bin of one cell: the Sobolev optical depths of the bin's
+// lines (a static range of the frequency-sorted line list, Tables::expopac_binstart) combined in line order, like the
+// reference's running sum. Uses the cell's level populations / line table, which the table build has just written: the
+// host's pass over every line of every cell per timestep is not needed (option device_expansion_opacities).
+AHD void build_expopac_bin(const Tables& T, const int cell, const int binindex) {
+  const double t_mid = T.ts_mid[T.globals_timestep];
+  const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
+  const double* celllinetau = (T.cell_linetau != nullptr) ? T.cell_linetau + (static_cast<long long>(cell) * T.nlines) : nullptr;
+  double bin_linesum = 0.;
+  for (int lineindex = T.expopac_binstart[binindex]; lineindex < T.expopac_binstart[binindex + 1]; lineindex++) {
+    double tau_line = 0.;  // rpkt.cc:75-100
+    if (celllinetau != nullptr) {
+      tau_line = dmax(celllinetau[lineindex] * t_mid, 0.);
+    } else {
+      const double n_l = cellpops[T.line_lower[lineindex]];
+      const double n_u = cellpops[T.line_upper[lineindex]];
+      const double B_ul = T.line_B_ul[lineindex];
+      const double B_lu = T.line_B_lu[lineindex];
+      tau_line = dmax(((B_lu * n_l) - (B_ul * n_u)) * HCLIGHTOVERFOURPI * t_mid, 0.);
+    }
+    const double linelambda = 1e8 * CLIGHT / T.line_nu[lineindex];
+    bin_linesum += (linelambda / expopac_deltalambda) * -expm1(-tau_line);
+  }
+  const auto rho = T.rho[cell];
+  const_cast<float*>(T.expansionopacities)[(static_cast<long long>(cell) * expopac_nbins) + binindex] =
+      static_cast<float>(1. / (CLIGHT * t_mid * rho) * bin_linesum);
+}
+
+// the Planck-weighted cumulative opacity over the bins of one cell (rpkt.cc:1106-1118), after build_expopac_bin of the cell.
+// `kappa_bb`: the cell's row of bin opacities (cell.expansionopacities, or a scratch row when only the cumulative is kept)
+AHD void build_expopac_planck_cell(const Tables& T, const int cell, const float* kappa_bb) {
+  const auto rho = T.rho[cell];
+  const auto temperature = T.Te[cell];
+  const auto clumpednne_ = T.nne[cell] * T.clumpfactor[cell];
+  double* out = const_cast<double*>(T.expopac_planck_cumulative) + (static_cast<long long>(cell) * expopac_nbins);
+  double kappa_planck_cumulative = 0.;
+  for (int binindex = 0; binindex < expopac_nbins; binindex++) {
+    const double nu_lower = expopac_bin_nu_lower(binindex);
+    const double nu_upper = expopac_bin_nu_upper(binindex);
+    const double nu_mid = (nu_upper + nu_lower) / 2.;
+    // calculate_chi_ffheating (rpkt.cc:697-710)
+    const double chi_ff = T.cell_chi_ff_nnionpart[cell] / pow3(nu_mid) * clumpednne_ * (1 - exp(-HOVERKB * nu_mid / temperature));
+    const double bin_kappa_cont = chi_ff / rho;
+    const double planck_val = 2 * H * pow3(nu_mid) / pow2(CLIGHT) / expm1(HOVERKB * nu_mid / temperature);  // radfield.h:49-51
+    const double kappa_planck = (kappa_bb[binindex] + bin_kappa_cont) * planck_val;
+    const double delta_nu = nu_upper - nu_lower;
+    kappa_planck_cumulative += kappa_planck * delta_nu;
+    out[binindex] = kappa_planck_cumulative;
+  }
+}
+
 }  // namespace ab

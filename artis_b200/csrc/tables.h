@@ -194,6 +194,14 @@ constexpr double expopac_lambdamin = 60.;
 constexpr double expopac_lambdamax = 40000.;
 constexpr double expopac_deltalambda = 20.;
 constexpr int expopac_nbins = static_cast<int>((expopac_lambdamax - expopac_lambdamin) / expopac_deltalambda);
+AHD double expopac_bin_nu_upper(const int binindex) {  // rpkt.h:30-34
+  const double lambda_lower = expopac_lambdamin + (static_cast<double>(binindex) * expopac_deltalambda);
+  return 1e8 * CLIGHT / lambda_lower;
+}
+AHD double expopac_bin_nu_lower(const int binindex) {  // rpkt.h:36-40
+  const double lambda_upper = expopac_lambdamin + (static_cast<double>(binindex + 1) * expopac_deltalambda);
+  return 1e8 * CLIGHT / lambda_upper;
+}
 
 constexpr int NTSSCALARS = 10;  // ARTISB200_NTSSCALARS
 constexpr int NDIAG = 16;       // ARTISB200_NDIAG
@@ -375,6 +383,7 @@ struct Tables {
 
   // derived static tables (built by commit_static)
   const int* level_uniqueion;   // [nlevels] unique ion index of each level
+  const int* expopac_binstart;  // [expopac_nbins + 1] first line of every expansion-opacity wavelength bin (rpkt.cc:1086-1098)
   const int* ion_element;       // [nions]
   const int* ion_index;         // [nions] ion index within its element
   const int* elem_has_nlte_levels;  // [nelements]
@@ -400,6 +409,7 @@ struct Tables {
 
   // run options
   int device_cooling_contribs;  // 1 = cell.ion_cooling_contribs is written by the table build (rates.h build_ion_cooling_totals_cell)
+  int device_expansion_opacities;  // 1 = cell.expansionopacities / cell.expopac_planck_cumulative likewise (rates.h build_expopac_*)
   int rng_mode;
   unsigned long long seed;
   RngSetup rng_setup;  // (rng_mode, seed, timestep) in the form the generators read; refreshed before every propagation

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "artisb200_commit_static": (ctypes.c_int, [ctypes.c_void_p]),
     "artisb200_bin_escaped_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "artisb200_last_binning_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "artisb200_write_text_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "artisb200_write_temp_packetsfile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "artisb200_read_temp_packetsfile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                                       ctypes.POINTER(ctypes.c_int64)]),
     "artisb200_update_grid_lte": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
     "artisb200_last_gridupdate_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "artisb200_begin_timestep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -192,6 +196,28 @@ class ArtisB200:
         ms = ctypes.c_double()
         self.lib.artisb200_last_gridupdate_ms(self.ctx, ctypes.byref(ms))
         return ms.value
+
+    def write_text_packets(self, filename, aos_bytes, npackets, stride, keep_escaped_gammas=True):
+        """packets*.out of the reference (packet.cc:226-251) from the AoS packet array"""
+        aos_bytes = np.ascontiguousarray(aos_bytes)
+        self._check(self.lib.artisb200_write_text_packets(self.ctx, os.fsencode(filename), aos_bytes.ctypes.data_as(ctypes.c_void_p),
+                                                          int(npackets), int(stride), int(bool(keep_escaped_gammas))), "write_text_packets")
+
+    def write_temp_packetsfile(self, filename, aos_bytes, npackets, stride):
+        """binary restart file packets_<rank>_ts<N>.tmp of the reference (packet.cc:273-311)"""
+        aos_bytes = np.ascontiguousarray(aos_bytes)
+        self._check(self.lib.artisb200_write_temp_packetsfile(self.ctx, os.fsencode(filename), aos_bytes.ctypes.data_as(ctypes.c_void_p),
+                                                              int(npackets), int(stride)), "write_temp_packetsfile")
+
+    def read_temp_packetsfile(self, filename, stride):
+        """-> (raw AoS bytes, packet count) of a binary restart file (packet.cc:253-271)"""
+        n = ctypes.c_int64()
+        self._check(self.lib.artisb200_read_temp_packetsfile(self.ctx, os.fsencode(filename), None, 0, int(stride), ctypes.byref(n)),
+                    "read_temp_packetsfile")
+        out = np.empty(n.value * int(stride), dtype=np.uint8)
+        self._check(self.lib.artisb200_read_temp_packetsfile(self.ctx, os.fsencode(filename), out.ctypes.data_as(ctypes.c_void_p), n.value,
+                                                             int(stride), ctypes.byref(n)), "read_temp_packetsfile")
+        return out, n.value
 
     def save_packets_device(self):
         self._check(self.lib.artisb200_save_packets_device(self.ctx), "save_packets_device")

@@ -186,6 +186,14 @@ int artisb200_get_array_range(artisb200_ctx* ctx, const char* name, char dtype, 
  *   -1 (default) = on when the table takes at most line_tau_table_max_mb (default 8192). Read back as "built.line_taucoeff". */
 int artisb200_set_option(artisb200_ctx* ctx, const char* name, int64_t value);
 
+/* Per-timestep cell state that the per-cell table build can evaluate itself instead of taking it from the host (SURVEY §8f row 1;
+ * artisb200_set_option, default 0; the arrays stay readable with artisb200_get_array, and with cell-batched tables a cell's
+ * values are written by the pass that builds its tables):
+ *   "device_cooling_contribs"     cell.ion_cooling_contribs: kpkt::calculate_cooling_rates (kpkt.cc:281-303), the running sum
+ *                                 over the ions of their total cooling rates
+ *   "device_expansion_opacities"  cell.expansionopacities and (RPKT_BOUNDBOUND_THERMALISATION_PROBABILITY) cell.expopac_planck_
+ *                                 cumulative: calculate_expansion_opacities (rpkt.cc:1071-1123) at timesteps.mid[scalar.globals_timestep] */
+
 /* Validate that all required static tables are present and build derived static tables.
  * Replaces nothing in the reference; corresponds to the end of start-up (after sn3d.cc setup_cellcache). */
 int artisb200_commit_static(artisb200_ctx* ctx);
@@ -210,6 +218,20 @@ int artisb200_update_packets(artisb200_ctx* ctx, int nts);
  * others are still being propagated, and the array comes back PERMUTED (completion order) - which the caller of the
  * reference must be prepared for anyway: update_packets sorts the span it is given (update_packets.cc:363-394, 570). */
 int artisb200_update_packets_host(artisb200_ctx* ctx, int nts, void* packets_aos, int64_t npackets, int stride_bytes);
+
+/* Packet files of the reference, from / into the caller's AoS packet array (host memory; SURVEY.md §8f row 3, the I/O part).
+ * ctx may be NULL (errors are then read with artisb200_last_error(NULL)).
+ *   write_text_packets      packets<rank>_<seq>.out as sn3d writes it at the end of a run and exspec reads it: header line
+ *                           (packet.cc:38-50) + one line per packet, "{:g}" columns (packet.cc:226-251), Stokes columns with POL_ON
+ *                           (the library's preset); escaped gamma packets are left out unless keep_escaped_gammas
+ *                           (KEEP_ESCAPED_GAMMAS). Formatted by parallel threads, written in packet order: byte-identical files.
+ *   write/read_temp_packetsfile  the binary restart file packets_<rank>_ts<N>.tmp: int64 count + the Packet array
+ *                           (packet.cc:253-311); read with packets_aos == NULL returns the count only */
+int artisb200_write_text_packets(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes,
+                                 int keep_escaped_gammas);
+int artisb200_write_temp_packetsfile(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes);
+int artisb200_read_temp_packetsfile(artisb200_ctx* ctx, const char* filename, void* packets_aos, int64_t capacity, int stride_bytes,
+                                    int64_t* npackets);
 
 /* Page-lock the caller's packet array (cudaHostRegister) so that the transfers above run at full PCIe speed and
  * asynchronously; sn3d.cc allocates its std::vector<Packet> once (sn3d.cc:1089), the binding registers it once. */

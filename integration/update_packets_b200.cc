@@ -1063,6 +1063,7 @@ void emit_reference_lte_gridupdate(Sink& s) {
   globals::lte_iteration = true;
   std::vector<float> ref_nne(nc);
   std::vector<int> ref_upper(nc * nelements);
+  const auto t0 = std::chrono::steady_clock::now();
   for (int64_t cell = 0; cell < nc; cell++) {
     for (int e = 0; e < nelements; e++) {
       calculate_cellpartfuncts(static_cast<int>(cell), e);
@@ -1073,6 +1074,9 @@ void emit_reference_lte_gridupdate(Sink& s) {
       ref_upper[(cell * nelements) + e] = grid::get_elements_uppermost_ion(static_cast<int>(cell), e);
     }
   }
+  // machine-readable: the reference's own LTE update of all cells on one core (profiles/)
+  printlnlog("ARTISB200_GRID_TIMING cells {} ions {} wall_s {:.6f}", nc, nions,
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   s.arr("ref.grid.nne", ref_nne.data(), nc);
   s.arr("ref.grid.uppermost_ion", ref_upper.data(), nc * nelements);
   s.arr("ref.grid.ion_partfuncts", grid::ion_partfuncts_allcells.data(), nc * nions);

@@ -102,6 +102,14 @@ struct HostBackend {
       if (T.device_cooling_contribs != 0) {
         ab::build_ion_cooling_totals_cell(T, cell);
       }
+      if (T.device_expansion_opacities != 0) {
+        for (int b = 0; b < ab::expopac_nbins; b++) {
+          ab::build_expopac_bin(T, cell, b);
+        }
+        if constexpr (opt::HAS_BB_THERMALISATION_PROBABILITY) {
+          ab::build_expopac_planck_cell(T, cell, T.expansionopacities + (static_cast<long long>(cell) * ab::expopac_nbins));
+        }
+      }
     }
     T.counters[ab::CNT_UPDATECELL] = T.ncells;  // one cell-cache fill per cell (update_packets.cc:399)
     return true;

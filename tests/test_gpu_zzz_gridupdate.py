@@ -24,3 +24,11 @@ def test_ion_cooling_totals_from_the_table_build(config, nts):
     # histories unchanged (wavefront stage kernels)
     parity_checks.check_device_cooling_contribs(ablib.library_path(fixtures.PRESET_OF[config]), config, nts,
                                                 options={"schedule": 1, "wf_tail": 0})
+
+
+@pytest.mark.parametrize("config,nts", [("kilonova_expansionopac_toy", 4), ("kilonova_expopac_retrace_toy", 4), ("kilonova_bbtherm_toy", 4)])
+def test_expansion_opacities_from_the_table_build(config, nts):
+    # calculate_expansion_opacities (rpkt.cc:1071-1123) by the per-cell table build: float32 bin opacities within one step
+    # (device expm1), the Planck-weighted cumulative within 1e-12, packet histories unchanged
+    parity_checks.check_device_expansion_opacities(ablib.library_path(fixtures.PRESET_OF[config]), config, nts, max_ulps=1, rel=1e-12,
+                                                   options={"schedule": 1, "wf_tail": 0})

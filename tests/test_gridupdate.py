@@ -60,3 +60,18 @@ def test_ion_cooling_totals_from_the_table_build(config, nts, windows):
     # every packet history of the timestep unchanged; also with cell-batched tables
     options = {"schedule": 1, "wf_tail": 0, "table_window_cells": 11} if windows else None
     parity_checks.check_device_cooling_contribs(fixtures.hostsim_library(fixtures.PRESET_OF[config]), config, nts, rel=0., options=options)
+
+
+EXPOPAC_CASES = [("kilonova_expansionopac_toy", 2), ("kilonova_expansionopac_toy", 4), ("kilonova_expopac_retrace_toy", 4),
+                 ("kilonova_bbtherm_toy", 4)]
+
+
+@pytest.mark.parametrize("variant", ["resident", "windows", "no-line-table"])
+@pytest.mark.parametrize("config,nts", EXPOPAC_CASES)
+def test_expansion_opacities_from_the_table_build(config, nts, variant):
+    # calculate_expansion_opacities (rpkt.cc:1071-1123) on the device: the float32 bin opacities and the Planck-weighted
+    # cumulative are bit-identical to the reference's arrays on the host build and every packet history is unchanged; with
+    # resident and cell-batched tables, with and without the per-cell line table
+    options = {"resident": None, "windows": {"schedule": 1, "wf_tail": 0, "table_window_cells": 11},
+               "no-line-table": {"line_tau_table": 0}}[variant]
+    parity_checks.check_device_expansion_opacities(fixtures.hostsim_library(fixtures.PRESET_OF[config]), config, nts, options=options)
