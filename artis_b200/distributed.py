@@ -72,3 +72,28 @@ def allreduce_estimators_host(est, group=None):
             out[n] = flat_i[off:off + size].copy()
             off += size
     return out
+
+
+SPECTRA_SUMMED = ["flux", "emission", "trueemission", "absorption", "lc_lum", "lc_lumcmf", "gamma_lc_lum", "gamma_lc_lumcmf"]
+
+
+def allreduce_binned_host(binned, group=None):
+    """Sum the arrays of artis_b200.spectra.binned() over ranks with ONE packed f64 all-reduce: every rank bins the escaped
+    packets it owns (artisb200_bin_escaped_packets with nprocs_exspec = number of ranks), the sums are the spectra and light
+    curves of the run - the reference's MPI_Allreduce calls at spectrum_lightcurve.cc:293-310. The frequency grid and the
+    per-packet direction bins are rank-local and stay as they are."""
+    import torch
+    import torch.distributed as dist
+
+    names = [n for n in SPECTRA_SUMMED if n in binned]
+    packed = torch.from_numpy(np.concatenate([np.asarray(binned[n], dtype=np.float64).ravel() for n in names]))
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    out = dict(binned)
+    flat = packed.numpy()
+    off = 0
+    for n in names:
+        shape = np.asarray(binned[n]).shape
+        size = int(np.prod(shape))
+        out[n] = flat[off:off + size].reshape(shape).copy()
+        off += size
+    return out

@@ -274,6 +274,28 @@ def spectra_binning_leg(eng, n, peak):
         return {"error": str(e)}
 
 
+def grid_update_leg(eng, before):
+    """SURVEY 8f row 1, reported beside the headline (never part of the timed step): the LTE grid update of every cell on the
+    device copies of the cell state (partition functions, Saha ion balance, electron density). The workload's state was
+    balanced by the reference's own update_grid, so the electron densities must come back unchanged: `nne_max_rel_change` is a
+    parity property at bench scale (float32 steps are 6e-8)."""
+    try:
+        import numpy as np
+        if "cell.elem_numberdens" not in before:
+            return {"skipped": "the workload snapshot has no cell.elem_numberdens (older drop-in binary)"}
+        nne_before = eng.get_array("cell.nne", dtype=np.float32)
+        times = []
+        for _ in range(3):
+            eng.update_grid_lte()
+            times.append(eng.last_gridupdate_ms())
+        nne_after = eng.get_array("cell.nne", dtype=np.float32)
+        change = np.abs(nne_after.astype(np.float64) - nne_before) / np.maximum(np.abs(nne_before.astype(np.float64)), 1e-300)
+        return {"kernels": "k_lte_perion<partition functions>, k_lte_perion<Saha factors>, k_lte_ion_balance", "cells": int(nne_before.size),
+                "ms": sorted(times)[1], "nne_max_rel_change": float(change.max()), "cells_changed_more_than_1e-6": int((change > 1e-6).sum())}
+    except Exception as e:  # an extra: it must never take the bench line down
+        return {"error": str(e)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -507,6 +529,7 @@ def run_ours(args):
         # is quoted in physical gamma events (Compton / photoelectric / pair, gammapkt.cc:720-747) per second as well
         out["gamma_events_per_s"] = n_gamma_total / (t_step * 1e-3)
         out["spectra_binning"] = spectra_binning_leg(eng, n, peak)
+        out["grid_update_lte"] = grid_update_leg(eng, before)
         out["table_windows"] = {"passes_per_step": int(diag_mean[12]), "cells": int(ncells),
                                 "note": "1 = the per-cell tables of every cell are resident; > 1 = cell-batched tables"}
         if not args.no_cpu_baseline and world == 1:

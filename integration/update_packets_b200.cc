@@ -362,8 +362,9 @@ void emit_timestep_state(Sink& s, const int nts) {
       s.arr("cell.nt_frac_excitation", fracexc.data(), static_cast<int64_t>(fracexc.size()));
     }
   }
-  if constexpr (USE_XCOM_GAMMAPHOTOION) {
+  {
     // element number densities of the timestep (grid.cc:1693-1697), read by the XCOM photoelectric opacity (gammapkt.cc:456)
+    // and by the LTE ion balance on the device (artisb200_update_grid_lte)
     const int nel = get_nelements();
     std::vector<double> numberdens(static_cast<size_t>(nc) * static_cast<size_t>(nel));
     for (int64_t cell = 0; cell < nc; cell++) {
@@ -1025,13 +1026,7 @@ void emit_reference_lte_gridupdate(Sink& s) {
   const auto nc = static_cast<int64_t>(grid::get_nonempty_npts_model());
   const int nelements = get_nelements();
   const auto nions = static_cast<int64_t>(get_includedions());
-  std::vector<double> numberdens(nc * nelements);
-  for (int64_t cell = 0; cell < nc; cell++) {
-    for (int e = 0; e < nelements; e++) {
-      numberdens[(cell * nelements) + e] = grid::get_elem_numberdens(cell, e);
-    }
-  }
-  s.arr("cell.elem_numberdens", numberdens.data(), nc * nelements);
+  // (cell.elem_numberdens, the one input beyond the temperatures, density and composition, is part of emit_timestep_state)
   s.f64("ref.grid.mintemp", MINTEMP);
   s.f64("ref.grid.maxtemp", MAXTEMP);
 

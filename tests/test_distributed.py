@@ -85,3 +85,42 @@ def test_shard_bounds_cover_everything():
 def test_rank_seeds_are_distinct():
     seeds = {abdist.rank_seed(20260101, r) for r in range(8)}
     assert len(seeds) == 8
+
+
+def _spectra_worker(rank, world, port, lib, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ARTISB200_ALLOW_HOSTSIM="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from artis_b200 import spectra as spectra_mod
+        fx = fixtures.load_golden(CONFIG, NTS)
+        after = fx["after"]
+        n, stride = int(after["packets.count"][0]), int(after["packets.stride"][0])
+        begin, end = abdist.shard_bounds(n, rank, world)
+        eng = fixtures.ablib.ArtisB200(libpath=lib)
+        eng.set_arrays(fx["static"])
+        eng.commit_static()
+        eng.upload_packets(after["packets.aos"][begin * stride:end * stride].copy(), end - begin, stride)
+        eng.bin_escaped_packets(direction_bins=True, emission_absorption=1, nprocs_exspec=1)
+        total = abdist.allreduce_binned_host(spectra_mod.binned(eng))
+        eng.close()
+        if rank == 0:
+            np.savez(os.path.join(outdir, "binned.npz"), **total)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_bin_the_spectra_of_one(tmp_path):
+    # every rank bins the escaped packets it owns, one packed all-reduce sums the sets (spectrum_lightcurve.cc:293-310): the
+    # result is the reference's own binning of all packets (tests/golden/kilonova_toy_spectra_ts4.npz)
+    lib = fixtures.hostsim_library(fixtures.PRESET_OF[CONFIG])
+    world = 2
+    mp.start_processes(_spectra_worker, args=(world, _free_port(), lib, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    got = np.load(tmp_path / "binned.npz")
+    ref = np.load(os.path.join(fixtures.GOLDEN_DIR, f"{CONFIG}_spectra_ts{NTS}.npz"))
+    for key, sel, refkey in (("flux", 0, "ref.spec.flux"), ("emission", 0, "ref.spec.emission"), ("absorption", 0, "ref.spec.absorption"),
+                             ("lc_lum", 0, "ref.lc.lum"), ("lc_lumcmf", 0, "ref.lc.lumcmf"), ("gamma_lc_lum", None, "ref.lc.gamma_lum"),
+                             ("flux", slice(1, None), "ref.spec.flux_res"), ("lc_lum", slice(1, None), "ref.lc.lum_res")):
+        a = (got[key] if sel is None else got[key][sel]).ravel()
+        b = ref[refkey].ravel()
+        assert np.array_equal(a != 0., b != 0.), key
+        assert (np.abs(a - b) / np.maximum(np.abs(b), 1e-300)).max() <= 1e-12, key
