@@ -427,6 +427,13 @@ AHD void build_cooling_ion(const Tables& T, const int cell, const int uion) {
 AHD void build_ion_cooling_totals_cell(const Tables& T, const int cell) {
   double* out = const_cast<double*>(T.ion_cooling_contribs) + (static_cast<long long>(cell) * T.nions);
   const double* contribs = T.cell_cooling_contrib + (static_cast<long long>(cell) * T.ncoolingterms);
+  if (T.thick[cell] == CELL_THICK) {
+    // grey cells: the reference skips the calculation and flags the rates as invalid (update_grid.cc:629-633)
+    for (int uion = 0; uion < T.nions; uion++) {
+      out[uion] = -1.;
+    }
+    return;
+  }
   double cumulative_cooling = 0.;
   for (int uion = 0; uion < T.nions; uion++) {
     const int nterms = T.ion_ncoolingterms[uion];
@@ -440,6 +447,9 @@ AHD void build_ion_cooling_totals_cell(const Tables& T, const int cell) {
 // reference's running sum. Uses the cell's level populations / line table, which the table build has just written: the
 // host's pass over every line of every cell per timestep is not needed (option device_expansion_opacities).
 AHD void build_expopac_bin(const Tables& T, const int cell, const int binindex) {
+  if (T.thick[cell] == CELL_THICK) {
+    return;  // not evaluated for grey cells (update_grid.cc:656-660): their bins keep whatever they held
+  }
   const double t_mid = T.ts_mid[T.globals_timestep];
   const double* cellpops = T.cell_levelpops + (static_cast<long long>(cell) * T.nlevels);
   const double* celllinetau = (T.cell_linetau != nullptr) ? T.cell_linetau + (static_cast<long long>(cell) * T.nlines) : nullptr;
@@ -466,6 +476,9 @@ AHD void build_expopac_bin(const Tables& T, const int cell, const int binindex) 
 // the Planck-weighted cumulative opacity over the bins of one cell (rpkt.cc:1106-1118), after build_expopac_bin of the cell.
 // `kappa_bb`: the cell's row of bin opacities (cell.expansionopacities, or a scratch row when only the cumulative is kept)
 AHD void build_expopac_planck_cell(const Tables& T, const int cell, const float* kappa_bb) {
+  if (T.thick[cell] == CELL_THICK) {
+    return;
+  }
   const auto rho = T.rho[cell];
   const auto temperature = T.Te[cell];
   const auto clumpednne_ = T.nne[cell] * T.clumpfactor[cell];

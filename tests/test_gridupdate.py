@@ -49,7 +49,7 @@ def test_lte_grid_update_reports_misuse():
     eng.close()
 
 
-COOLING_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_nt_toy", 3), ("nltephot_toy", 3), ("classic_detailedbf_toy", 3),
+COOLING_CASES = [("classic3d_toy", 0), ("classic3d_toy", 2), ("classic3d_grey_toy", 2), ("kilonova_toy", 4), ("classic_nt_toy", 3), ("nltephot_toy", 3), ("classic_detailedbf_toy", 3),
                  ("classic_multibin_toy", 4), ("kilonova_expansionopac_toy", 4)]
 
 
@@ -57,7 +57,8 @@ COOLING_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_nt_toy", 3
 @pytest.mark.parametrize("config,nts", COOLING_CASES)
 def test_ion_cooling_totals_from_the_table_build(config, nts, windows):
     # kpkt::calculate_cooling_rates (kpkt.cc:281-303) on the device: bit-identical to the reference's array on the host build,
-    # every packet history of the timestep unchanged; also with cell-batched tables
+    # every packet history of the timestep unchanged; also with cell-batched tables. Grey cells carry the reference's -1
+    # (update_grid.cc:629-633): classic3d_toy timestep 0 mixes both kinds, classic3d_grey_toy is grey throughout
     options = {"schedule": 1, "wf_tail": 0, "table_window_cells": 11} if windows else None
     parity_checks.check_device_cooling_contribs(fixtures.hostsim_library(fixtures.PRESET_OF[config]), config, nts, rel=0., options=options)
 
