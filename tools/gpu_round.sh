@@ -38,6 +38,12 @@ for step in $STEPS; do
         python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_full.err; echo "full rc=$?"
       ARTISB200_BENCH_NPACKETS=2000000 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv -c 600 \
         --log-file gpurun_out/${TAG}_launches.csv python bench.py --one-step > /dev/null 2> gpurun_out/${TAG}_launches.err; echo "launches rc=$?" ;;
+    spectra)
+      # the spectra / light-curve binning kernel on 1e7 synthetic final packets, the reference's own binning
+      # timed beside it, and one full ncu capture of the kernel
+      timeout 300 python tools/bench_spectra.py --packets 10000000 --out gpurun_out/${TAG}_spectra_bench.json > gpurun_out/${TAG}_spectra_bench.log 2>&1; echo "spectra rc=$?"
+      timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_bin_escaped -c 1 -f -o gpurun_out/${TAG}_spectra_full \
+        python tools/bench_spectra.py --packets 4000000 --reference-replicas 0 --passes 1 --out gpurun_out/${TAG}_spectra_under_ncu.json > gpurun_out/${TAG}_spectra_ncu.log 2>&1; echo "spectra ncu rc=$?" ;;
     history)
       ARTISB200_OPTS="schedule=0" timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_history.json 2> gpurun_out/${TAG}_bench_history.err; echo "history rc=$?" ;;
     variants)
