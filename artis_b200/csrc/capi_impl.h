@@ -149,6 +149,10 @@ int artisb200_write_text_packets(artisb200_ctx* ctx, const char* filename, const
                                  int keep_escaped_gammas) {
   return packetio_result(ctx, ab::write_text_packets(filename, packets_aos, npackets, stride_bytes, opt::POL_ON, keep_escaped_gammas != 0));
 }
+int artisb200_read_text_packets(artisb200_ctx* ctx, const char* filename, void* packets_aos, int64_t capacity, int stride_bytes,
+                                int64_t* npackets) {
+  return packetio_result(ctx, ab::read_text_packets(filename, packets_aos, capacity, stride_bytes, opt::POL_ON, npackets));
+}
 int artisb200_write_temp_packetsfile(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes) {
   return packetio_result(ctx, ab::write_temp_packetsfile(filename, packets_aos, npackets, stride_bytes));
 }

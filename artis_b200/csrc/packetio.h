@@ -5,7 +5,9 @@
 // The text writer formats chunks of packets in parallel threads into buffers that are written in order: the reference's
 // single-threaded formatted output of 1e7 packets x 35 columns is minutes of a run's wall clock.
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -110,6 +112,225 @@ inline std::string write_text_packets(const char* filename, const void* aos, con
   }
   ok = (std::fclose(file) == 0) && ok;
   return ok ? std::string() : std::string("write_text_packets: writing ") + filename + " failed";
+}
+
+
+namespace packetio_detail {
+template <class U>
+inline void put(unsigned char* q, const int off, const U v) {
+  std::memcpy(q + off, &v, sizeof(U));
+}
+
+// a default-constructed reference Packet (packet.h:109-156) at q
+inline void packet_defaults(unsigned char* q) {
+  using L = AosLayout;
+  std::memset(q, 0, static_cast<size_t>(L::size));
+  const double nan = NAN;
+  put<double>(q, L::prop_time, -1.);
+  put<int>(q, L::next_trans, -1);
+  put<int>(q, L::emissiontype, EMTYPE_NOTSET);
+  put<int>(q, L::trueemissiontype, EMTYPE_NOTSET);
+  for (int k = 0; k < 3; k++) {
+    put<double>(q, L::em_pos + (8 * k), nan);
+    put<double>(q, L::trueem_pos + (8 * k), nan);
+  }
+  put<float>(q, L::em_time, -1.F);
+  put<float>(q, L::trueem_time, -1.F);
+  put<int>(q, L::cellindex, -1);
+  put<float>(q, L::escape_time, -1.F);
+  put<double>(q, L::tdecay, -1.);
+  put<int>(q, L::number, -1);
+  put<int>(q, L::pellet_decaytype, -1);
+  put<int>(q, L::pellet_nucindex, -1);
+}
+
+// The reference reads a row with stream extraction (packet.cc:183-214) and deliberately does not check the stream state:
+// extracting "nan" (a packet that never emitted or was never absorbed carries NAN there) stores 0 and sets failbit in
+// libstdc++, and every later field of the row keeps the default-constructed Packet's value. This cursor does the same.
+struct RowCursor {
+  const char* p;
+  bool failed{false};
+  const char* token(size_t& len) {
+    while (*p == ' ' || *p == '\t' || *p == '\r') {
+      p++;
+    }
+    const char* start = p;
+    while (*p != '\0' && *p != ' ' && *p != '\t' && *p != '\r' && *p != '\n') {
+      p++;
+    }
+    len = static_cast<size_t>(p - start);
+    return start;
+  }
+  bool integer(int& v) {
+    if (failed) {
+      return false;
+    }
+    size_t len = 0;
+    const char* t = token(len);
+    char* end = nullptr;
+    const long x = std::strtol(t, &end, 10);
+    if (len == 0 || end == t) {
+      failed = true;
+      v = 0;
+      return false;
+    }
+    v = static_cast<int>(x);
+    p = end;  // ("12.5" leaves ".5" for the next extraction, like the stream)
+    return true;
+  }
+  bool real(double& v) {
+    if (failed) {
+      return false;
+    }
+    size_t len = 0;
+    const char* t = token(len);
+    const char* digits = (len > 0 && (*t == '-' || *t == '+')) ? t + 1 : t;
+    const bool spelled = (len > 0) && ((*digits >= '0' && *digits <= '9') || *digits == '.');
+    char* end = nullptr;
+    const double x = spelled ? std::strtod(t, &end) : 0.;
+    if (!spelled || end == t) {  // nan, inf, empty
+      failed = true;
+      v = 0.;
+      return false;
+    }
+    v = x;
+    p = end;
+    return true;
+  }
+};
+
+inline void parse_packet_row(const char* line, unsigned char* q, const bool pol_on) {
+  using L = AosLayout;
+  packet_defaults(q);
+  RowCursor c{line};
+  int iv = 0;
+  double dv = 0.;
+  const auto read_int = [&](const int off) {
+    const bool was_failed = c.failed;
+    c.integer(iv);
+    if (!was_failed) {
+      put<int>(q, off, iv);  // (a failing extraction stores 0)
+    }
+  };
+  const auto read_double = [&](const int off) {
+    const bool was_failed = c.failed;
+    c.real(dv);
+    if (!was_failed) {
+      put<double>(q, off, dv);
+    }
+  };
+  const auto read_float = [&](const int off) {
+    const bool was_failed = c.failed;
+    c.real(dv);
+    if (!was_failed) {
+      put<float>(q, off, static_cast<float>(dv));
+    }
+  };
+  read_int(L::number);
+  read_int(L::cellindex);
+  read_int(L::type);
+  for (int k = 0; k < 3; k++) {
+    read_double(L::pos + (8 * k));
+  }
+  for (int k = 0; k < 3; k++) {
+    read_double(L::dir + (8 * k));
+  }
+  read_double(L::tdecay);
+  read_double(L::e_cmf);
+  read_double(L::e_rf);
+  read_double(L::nu_cmf);
+  read_double(L::nu_rf);
+  read_int(L::escape_type);
+  read_float(L::escape_time);
+  read_int(L::emissiontype);
+  read_int(L::trueemissiontype);
+  for (int k = 0; k < 3; k++) {
+    read_double(L::em_pos + (8 * k));
+  }
+  read_int(L::absorptiontype);
+  read_double(L::absorptionfreq);
+  read_int(L::nscatterings);
+  read_float(L::em_time);
+  if (pol_on) {
+    read_double(L::stokes_q);
+    read_double(L::stokes_u);
+  }
+  {
+    const bool was_failed = c.failed;
+    c.integer(iv);
+    if (!was_failed) {
+      put<unsigned char>(q, L::originated_from_particlenotgamma, static_cast<unsigned char>(iv != 0 ? 1 : 0));
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    read_double(L::trueem_pos + (8 * k));
+  }
+  read_float(L::trueem_time);
+  read_int(L::pellet_nucindex);
+  read_int(L::pellet_decaytype);
+}
+
+inline bool comment_only(const std::string& line) {  // input.h:192-202
+  for (const char ch : line) {
+    if (ch == '#') {
+      return true;
+    }
+    if (ch != ' ' && ch != '\t' && ch != '\r' && ch != '\n') {
+      return false;
+    }
+  }
+  return true;
+}
+}  // namespace packetio_detail
+
+// packet.cc:163-222: aos == nullptr -> only the packet count is returned. A 256-byte stride leaves the 16-byte rngstate prefix zero.
+inline std::string read_text_packets(const char* filename, void* aos, const int64_t capacity, const int stride, const bool pol_on,
+                                     int64_t* npackets) {
+  if (stride != AosLayout::size && stride != AosLayout::size + 16) {
+    return "read_text_packets: stride must be 240 or 256";
+  }
+  FILE* file = std::fopen(filename, "r");
+  if (file == nullptr) {
+    return std::string("read_text_packets: cannot open ") + filename;
+  }
+  std::string line;
+  const auto getline = [&]() {
+    line.clear();
+    char buf[4096];
+    while (std::fgets(buf, sizeof(buf), file) != nullptr) {
+      line += buf;
+      if (!line.empty() && line.back() == '\n') {
+        line.pop_back();
+        return true;
+      }
+    }
+    return !line.empty();
+  };
+  std::string error;
+  if (!getline() || line != packets_text_header(pol_on)) {
+    error = std::string("read_text_packets: the header line of ") + filename + " is not the one this preset writes (POL_ON?)";
+  }
+  int64_t count = 0;
+  const int base = stride - AosLayout::size;
+  auto* bytes = static_cast<unsigned char*>(aos);
+  while (error.empty() && getline()) {
+    if (packetio_detail::comment_only(line)) {
+      continue;
+    }
+    if (aos != nullptr) {
+      if (count >= capacity) {
+        error = std::string("read_text_packets: ") + filename + " holds more packets than the buffer";
+        break;
+      }
+      unsigned char* rec = bytes + (count * stride);
+      std::memset(rec, 0, static_cast<size_t>(stride));
+      packetio_detail::parse_packet_row(line.c_str(), rec + base, pol_on);
+    }
+    count++;
+  }
+  std::fclose(file);
+  *npackets = count;
+  return error;
 }
 
 // packet.cc:273-311: int64 packet count, then the Packet array as it is in memory

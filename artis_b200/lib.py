@@ -37,6 +37,8 @@ _SIGNATURES = {
     "artisb200_bin_escaped_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "artisb200_last_binning_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "artisb200_write_text_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "artisb200_read_text_packets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_int64)]),
     "artisb200_write_temp_packetsfile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "artisb200_read_temp_packetsfile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                                        ctypes.POINTER(ctypes.c_int64)]),
@@ -202,6 +204,16 @@ class ArtisB200:
         aos_bytes = np.ascontiguousarray(aos_bytes)
         self._check(self.lib.artisb200_write_text_packets(self.ctx, os.fsencode(filename), aos_bytes.ctypes.data_as(ctypes.c_void_p),
                                                           int(npackets), int(stride), int(bool(keep_escaped_gammas))), "write_text_packets")
+
+    def read_text_packets(self, filename, stride=240):
+        """-> (raw AoS bytes, packet count) of a packets*.out text file, read like exspec reads it (packet.cc:163-222)"""
+        n = ctypes.c_int64()
+        self._check(self.lib.artisb200_read_text_packets(self.ctx, os.fsencode(filename), None, 0, int(stride), ctypes.byref(n)),
+                    "read_text_packets")
+        out = np.zeros(n.value * int(stride), dtype=np.uint8)
+        self._check(self.lib.artisb200_read_text_packets(self.ctx, os.fsencode(filename), out.ctypes.data_as(ctypes.c_void_p), n.value,
+                                                         int(stride), ctypes.byref(n)), "read_text_packets")
+        return out, n.value
 
     def write_temp_packetsfile(self, filename, aos_bytes, npackets, stride):
         """binary restart file packets_<rank>_ts<N>.tmp of the reference (packet.cc:273-311)"""

@@ -69,10 +69,15 @@ def write_spectrum_file(path, timesteps_mid, lower_freq, delta_freq, flux, numti
 def write_columns_file(path, table, numtimesteps):
     """write_emission_spectrum_file / write_absorption_spectrum_file: one line per (frequency bin, timestep), one column per
     process / ion"""
+    zero_line = "0 " * table.shape[-1] + "\n"
+    nonzero = table.any(axis=-1)
     with open(path, "w") as f:
         for nnu in range(table.shape[0]):
+            if not nonzero[nnu, :numtimesteps].any():
+                f.write(zero_line * numtimesteps)
+                continue
             for nts in range(numtimesteps):
-                f.write("".join(_g(v) + " " for v in table[nnu, nts]) + "\n")
+                f.write("".join(_g(v) + " " for v in table[nnu, nts]) + "\n" if nonzero[nnu, nts] else zero_line)
 
 
 def write_partial_lightcurve_spectra(engine, nts, outdir, timesteps_mid, ntimesteps_finish=None, multidimensional=True,

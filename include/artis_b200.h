@@ -225,10 +225,15 @@ int artisb200_update_packets_host(artisb200_ctx* ctx, int nts, void* packets_aos
  *                           (packet.cc:38-50) + one line per packet, "{:g}" columns (packet.cc:226-251), Stokes columns with POL_ON
  *                           (the library's preset); escaped gamma packets are left out unless keep_escaped_gammas
  *                           (KEEP_ESCAPED_GAMMAS). Formatted by parallel threads, written in packet order: byte-identical files.
+ *   read_text_packets       the same file read back as exspec does (packet.cc:163-222), including the reference's behaviour at
+ *                           "nan" columns (the extraction fails there and the rest of the row keeps the values of a
+ *                           default-constructed Packet); packets_aos == NULL returns the count only
  *   write/read_temp_packetsfile  the binary restart file packets_<rank>_ts<N>.tmp: int64 count + the Packet array
  *                           (packet.cc:253-311); read with packets_aos == NULL returns the count only */
 int artisb200_write_text_packets(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes,
                                  int keep_escaped_gammas);
+int artisb200_read_text_packets(artisb200_ctx* ctx, const char* filename, void* packets_aos, int64_t capacity, int stride_bytes,
+                                int64_t* npackets);
 int artisb200_write_temp_packetsfile(artisb200_ctx* ctx, const char* filename, const void* packets_aos, int64_t npackets, int stride_bytes);
 int artisb200_read_temp_packetsfile(artisb200_ctx* ctx, const char* filename, void* packets_aos, int64_t capacity, int stride_bytes,
                                     int64_t* npackets);
