@@ -112,3 +112,29 @@ def test_files_of_a_complete_reference_run(config, tmp_path):
             np.testing.assert_allclose(row_b, row_a, rtol=2e-5, atol=0, err_msg=name)
         compared += sum(1 for row in a for v in row[1:] if v != 0.)
     assert compared > 100
+
+
+def test_synthetic_packets_over_every_branch_against_the_numpy_oracle():
+    """the device binning code (host build) on 60 000 random final packets - every kind of emission type, packets in flight,
+    arrival times and frequencies inside and outside the binned ranges, escaped gamma packets - against the pinned numpy
+    restatement; the same comparison runs with two million packets on the GPU (tests/test_gpu_zzz_spectra.py)"""
+    from bench_spectra import synthetic_packets  # tools/
+    static = fixtures.load_golden("classic3d_toy", 2)["static"]
+    n = 60_000
+    pk = synthetic_packets(static, n, seed=3)
+    eng = fixtures.ablib.ArtisB200(libpath=fixtures.hostsim_library("classic"))
+    eng.set_arrays(static)
+    eng.commit_static()
+    eng.upload_packets(pk.view(np.uint8), n, pk.dtype.itemsize)
+    eng.set_option("spec_record_dirbin", 1)
+    eng.bin_escaped_packets(direction_bins=True, emission_absorption=1, nprocs_exspec=2)
+    got = spectra_mod.binned(eng)
+    eng.close()
+    want = spectra_oracle.bin_packets(pk, static, 1e14, 5e15, nnubins=1000, nprocs_exspec=2)
+    assert np.array_equal(got["dirbin"], want["dirbin"])
+    for key in ("flux", "emission", "trueemission", "absorption", "lc_lum", "lc_lumcmf", "gamma_lc_lum", "gamma_lc_lumcmf"):
+        # one thread, packet order: the same additions in the same order as the oracle's
+        assert np.array_equal(got[key], want[key]), key
+    assert np.count_nonzero(got["emission"][0][:, :, -1]) > 0  # free-free column
+    nions = static["elem.anumber"].size * int(static["elem.nions"].max())
+    assert np.count_nonzero(got["emission"][0][:, :, nions:2 * nions]) > 0  # bound-free columns
