@@ -1299,11 +1299,15 @@ class Engine {
     if (!static_committed) {
       return fail("update_grid_lte: commit_static must be called first");
     }
-    if constexpr (opt::HAS_NLTE_LEVELS) {
-      return fail("update_grid_lte: this preset has NLTE level populations; its partition functions read the NLTE solver's "
-                  "populations (ltepop.cc:177-197), which stay on the host");
-    }
     const int64_t nc = T.ncells;
+    if constexpr (opt::HAS_NLTE_LEVELS) {
+      // the partition functions read the NLTE solver's populations where the host has them (ltepop.cc:177-197)
+      const int64_t n = count_of("cell.nltepops");
+      if (n <= 0 || (n % nc) != 0) {
+        return fail("update_grid_lte: cell.nltepops must be set with ncells x (NLTE level slots) entries for a preset with NLTE levels");
+      }
+      T.total_nlte_levels = static_cast<int>(n / nc);  // (as begin_timestep does)
+    }
     const struct { const char* name; int64_t count; } needed[] = {
         {"cell.Te", nc}, {"cell.TJ", nc}, {"cell.TR", nc}, {"cell.W", nc}, {"cell.nne", nc}, {"cell.rho", nc},
         {"cell.elem_massfracs", nc * T.nelements}, {"cell.elem_numberdens", nc * T.nelements},

@@ -15,8 +15,8 @@
 // ground-level populations. Everything a cell needs is [cell][ion] / [cell][element] rows: coalesced across a warp's cells
 // only per row, but the whole state of 1e6 cells x 20 ions is 160 MB and is read once.
 //
-// Presets with NLTE level populations are not handled here (their partition functions read the NLTE solver's populations,
-// ltepop.cc:177-197): the host call refuses them.
+// Presets with NLTE level populations: the partition functions read the NLTE solver's level and superlevel populations
+// (cell.nltepops) where the host has them, like the reference's (ltepop.cc:177-197); the Saha balance itself is the same.
 #pragma once
 #include "atomicdata.h"
 #include "hd.h"
@@ -85,8 +85,33 @@ AHD float lte_partfunct(const Tables& T, const GridUpdateView& G, const int cell
   const int nlevels = T.ion_nlevels[uion];
   double U = 1.;
   for (int level = 1; level < nlevels; level++) {
-    const double E_aboveground = epsilon(T, ustart + level) - epsilon(T, ustart);
-    const double nn = groundpop * statw(T, ustart + level) / statw(T, ustart) * exp(-E_aboveground / KB / T_exc);
+    double nn = 0.;
+    bool have = false;
+    if constexpr (opt::HAS_NLTE_LEVELS) {
+      // calculate_levelpop_nominpop (ltepop.cc:170-199): the NLTE solver's populations where the host has them
+      if (T.elem_has_nlte_levels[element] != 0) {
+        const int ion = T.ion_index[uion];
+        const int nexc = T.ion_nlevels_excited_nlte[uion];
+        const long long base = (static_cast<long long>(cell) * T.total_nlte_levels) + T.ion_allnltelevelsindexstart[uion];
+        if (level <= nexc) {  // is_nlte (atomic.h:304)
+          const double nltepop_over_rho = T.nltepops[base + level - 1];
+          if (nltepop_over_rho >= 0.) {
+            nn = nltepop_over_rho * G.rho[cell];
+            have = true;
+          }
+        } else if (T.ion_nlevels[uion] > (nexc + T.ion_nlevels_autoion[uion] + 1)) {  // ion_has_superlevel (atomic.h:448)
+          const double superlevelpop_over_rho = T.nltepops[base + nexc];
+          if (superlevelpop_over_rho >= 0.) {
+            nn = superlevelpop_over_rho * G.rho[cell] * superlevel_boltzmann(T, cell, element, ion, level);
+            have = true;
+          }
+        }
+      }
+    }
+    if (!have) {
+      const double E_aboveground = epsilon(T, ustart + level) - epsilon(T, ustart);
+      nn = groundpop * statw(T, ustart + level) / statw(T, ustart) * exp(-E_aboveground / KB / T_exc);
+    }
     U += nn / groundpop;
   }
   U *= statw(T, ustart);

@@ -287,7 +287,9 @@ int artisb200_last_binning_ms(artisb200_ctx* ctx, double* ms); /* device time of
  * artisb200_get_array; the next artisb200_begin_timestep builds its tables from them without a host round trip);
  * gridupdate.uppermost_ion 'i'[Nc*nelements] (grid::elements_uppermost_ion_allcells), gridupdate.status 'i'[Nc] (2 = the
  * root find used all 50 evaluations: the reference warns and carries on). Fails like the reference's assert_always
- * (ltepop.cc:289) when no electron density in [0, rho/m_H] balances a cell. Presets with NLTE level populations are refused. */
+ * (ltepop.cc:289) when no electron density in [0, rho/m_H] balances a cell. Presets with NLTE level populations: the partition
+ * functions read the NLTE solver's level and superlevel populations (cell.nltepops) where the host has them, like the reference's
+ * (ltepop.cc:177-197); the balance itself is Saha for every element, as in the reference's LTE / grey-cell branch. */
 int artisb200_update_grid_lte(artisb200_ctx* ctx, int temperatures_from_J, double mintemp, double maxtemp);
 int artisb200_last_gridupdate_ms(artisb200_ctx* ctx, double* ms); /* device time of the last grid update */
 

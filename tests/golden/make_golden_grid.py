@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import run_oracle  # noqa: E402
 from artis_b200 import snapshot as snap  # noqa: E402
 
-GOLDEN_GRID = {"classic3d_toy": 2, "kilonova_toy": 4, "classic_toy_1d": 3, "kilonova_2d_kat": 2}
+# (classic_nlte_toy: partition functions that read the NLTE solver's level and superlevel populations, ltepop.cc:177-197)
+GOLDEN_GRID = {"classic3d_toy": 2, "kilonova_toy": 4, "classic_toy_1d": 3, "kilonova_2d_kat": 2, "classic_nlte_toy": 4}
 EXTRA_ENV = {"kilonova_2d_kat": {"ARTISB200_DUMP_CELLS": "6"}}
 
 

@@ -9,7 +9,8 @@ import pytest
 
 from tests import fixtures, parity_checks
 
-GRID_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy_1d", 3), ("kilonova_2d_kat", 2)]
+# (classic_nlte_toy: partition functions that read the NLTE solver's level and superlevel populations)
+GRID_CASES = [("classic3d_toy", 2), ("kilonova_toy", 4), ("classic_toy_1d", 3), ("kilonova_2d_kat", 2), ("classic_nlte_toy", 4)]
 
 
 @pytest.mark.parametrize("config,nts", GRID_CASES)
@@ -39,12 +40,13 @@ def test_lte_grid_update_reports_misuse():
     with pytest.raises(fixtures.ablib.ArtisB200Error, match="estimator_normfactor_over4pi"):
         eng.update_grid_lte(temperatures_from_J=True, mintemp=3500., maxtemp=140000.)
     eng.close()
-    nlte = fixtures.load_golden("classic_nlte_toy", 2)
+    nlte = fixtures.load_golden("classic_nlte_toy", 4)
     eng = fixtures.ablib.ArtisB200(libpath=fixtures.hostsim_library("classic_nlte"))
     eng.set_arrays(nlte["static"])
     eng.commit_static()
-    eng.set_arrays(nlte["before"])
-    with pytest.raises(fixtures.ablib.ArtisB200Error, match="NLTE"):
+    eng.set_arrays({k: v for k, v in nlte["before"].items() if k != "cell.nltepops"})
+    eng.set_array("cell.elem_numberdens", np.ones(nlte["before"]["cell.elem_massfracs"].size))
+    with pytest.raises(fixtures.ablib.ArtisB200Error, match="cell.nltepops"):
         eng.update_grid_lte()
     eng.close()
 
