@@ -19,7 +19,7 @@ def test_lte_grid_update_matches_the_reference(config, nts):
     parity_checks.check_grid_update_lte(fixtures.hostsim_library(fixtures.PRESET_OF[config]), config, nts, max_ulps=0)
 
 
-@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4), ("kilonova_2d_kat", 2)])
+@pytest.mark.parametrize("config,nts", [("classic3d_toy", 2), ("kilonova_toy", 4), ("kilonova_2d_kat", 2), ("classic_nlte_toy", 4)])
 def test_lte_grid_update_with_another_libm(config, nts):
     # exp / pow moved by -1 / 0 / +1 ulp (tests/hostsim, ARTISB200_HOSTSIM_FUZZ_LIBM), as on the device: the partition functions
     # stay within one float32 step, the electron density root (TOMS 748 to 1e-3) and the populations within four: the
