@@ -202,6 +202,8 @@ class Engine {
   SpectraView S{};
   long long spec_nnubins{1000};    // [spec_nnubins] MNUBINS (exspec.h:8)
   bool spec_record_dirbin{false};  // [spec_record_dirbin] keep every packet's direction bin ("spec.dirbin")
+  bool spec_stokes{false};         // [spec_stokes] Stokes Q / U spectra beside every I array (exspec with POL_ON)
+  bool spec_gamma_spectrum{false}; // [spec_gamma_spectrum] spectrum of the escaped gamma packets (exspec's gamma_spec.out)
   double last_binning_ms{0.};
   double last_gridupdate_ms{0.};
 
@@ -473,6 +475,10 @@ class Engine {
       spec_nnubins = value;
     } else if (name == "spec_record_dirbin") {
       spec_record_dirbin = (value != 0);
+    } else if (name == "spec_stokes") {
+      spec_stokes = (value != 0);
+    } else if (name == "spec_gamma_spectrum") {
+      spec_gamma_spectrum = (value != 0);
     } else if (name == "rank") {
       rank = static_cast<int>(value);
     } else if (name == "nranks") {
@@ -1258,6 +1264,47 @@ class Engine {
     if (spec_record_dirbin) {
       ok = ok && alloc_output("spec.dirbin", 'i', npackets, &S.dirbin);
     }
+    S.flux_q = S.flux_u = S.emission_q = S.emission_u = S.absorption_q = S.absorption_u = nullptr;
+    // optional outputs of an earlier call that this call does not produce are retired (count 0; the memory is kept)
+    const auto retire = [this](const char* name) {
+      const auto it = arrays.find(name);
+      if (it != arrays.end()) {
+        it->second.count = 0;
+      }
+    };
+    if (!spec_stokes) {
+      for (const char* name : {"spec.flux_q", "spec.flux_u", "spec.emission_q", "spec.emission_u", "spec.absorption_q", "spec.absorption_u"}) {
+        retire(name);
+      }
+    }
+    if (!spec_gamma_spectrum) {
+      retire("spec.gamma_flux");
+    }
+    if (!spec_record_dirbin) {
+      retire("spec.dirbin");
+    }
+    if (spec_stokes) {
+      ok = ok && alloc_output("spec.flux_q", 'd', n_flux, &S.flux_q) && alloc_output("spec.flux_u", 'd', n_flux, &S.flux_u);
+      ok = ok && alloc_output("spec.emission_q", 'd', n_em, &S.emission_q) && alloc_output("spec.emission_u", 'd', n_em, &S.emission_u);
+      ok = ok && alloc_output("spec.absorption_q", 'd', n_abs, &S.absorption_q) && alloc_output("spec.absorption_u", 'd', n_abs, &S.absorption_u);
+    }
+    S.gamma_flux = nullptr;
+    S.gamma_delta_freq = nullptr;
+    if (spec_gamma_spectrum) {
+      // exspec.cc:61-64: the same number of logarithmic bins between 0.05 and 4 MeV
+      S.gamma_nu_min = 0.05 * MEV / H;
+      S.gamma_nu_max = 4. * MEV / H;
+      S.gamma_dlognu = (std::log(S.gamma_nu_max) - std::log(S.gamma_nu_min)) / static_cast<double>(S.nnubins);
+      std::vector<float> g_lower(static_cast<size_t>(S.nnubins));
+      std::vector<float> g_delta(static_cast<size_t>(S.nnubins));
+      for (int nnu = 0; nnu < S.nnubins; nnu++) {
+        g_lower[nnu] = static_cast<float>(std::exp(std::log(S.gamma_nu_min) + (static_cast<double>(nnu) * S.gamma_dlognu)));
+        g_delta[nnu] = static_cast<float>(std::exp(std::log(S.gamma_nu_min) + (static_cast<double>(nnu + 1) * S.gamma_dlognu)) - g_lower[nnu]);
+      }
+      const float* d_glower = nullptr;
+      ok = ok && make_derived("spec.gamma_lower_freq", g_lower, &d_glower) && make_derived("spec.gamma_delta_freq", g_delta, &S.gamma_delta_freq);
+      ok = ok && alloc_output("spec.gamma_flux", 'd', fluxsize, &S.gamma_flux);
+    }
     if (!ok) {
       return fail("bin_escaped_packets: allocation of the spectra failed: " + be.last_error());
     }
@@ -1272,6 +1319,19 @@ class Engine {
       be.zero(S.emission, n_em * 8);
       be.zero(S.trueemission, n_em * 8);
       be.zero(S.absorption, n_abs * 8);
+    }
+    if (spec_stokes) {
+      be.zero(S.flux_q, n_flux * 8);
+      be.zero(S.flux_u, n_flux * 8);
+      if (n_em > 0) {
+        be.zero(S.emission_q, n_em * 8);
+        be.zero(S.emission_u, n_em * 8);
+        be.zero(S.absorption_q, n_abs * 8);
+        be.zero(S.absorption_u, n_abs * 8);
+      }
+    }
+    if (spec_gamma_spectrum) {
+      be.zero(S.gamma_flux, fluxsize * 8);
     }
     be.zero(S.lc_lum, n_lc * 8);
     be.zero(S.lc_lumcmf, n_lc * 8);

@@ -57,6 +57,20 @@ struct SpectraView {
   double* lc_lumcmf;     // [set][nts]
   double* gamma_lc_lum;  // [nts]   (escaped gamma packets: angle-averaged only, spectrum_lightcurve.cc:284)
   double* gamma_lc_lumcmf;
+  // optional (null = off): Stokes Q and U spectra with the layouts of flux / emission / absorption (exspec.cc:52-59, POL_ON:
+  // every addend of the I arrays times the packet's stokes_q / stokes_u, spectrum_lightcurve.cc:567-624), and the spectrum of
+  // the escaped gamma packets on its own frequency grid, angle-averaged only (exspec.cc:61-64, 83-86)
+  double* flux_q;
+  double* flux_u;
+  double* emission_q;
+  double* emission_u;
+  double* absorption_q;
+  double* absorption_u;
+  double* gamma_flux;             // [nnubins][nts]
+  const float* gamma_delta_freq;  // [nnubins]
+  double gamma_nu_min;
+  double gamma_nu_max;
+  double gamma_dlognu;
   int* dirbin;           // [npackets] direction bin of every escaped packet, -1 for the others (or null)
 };
 
@@ -203,6 +217,13 @@ AHD void bin_escaped_packet(const Tables& T, const SpectraView& S, const long lo
     }
   }
   if (!is_rpkt) {
+    // add_to_spec_res for the gamma-ray spectrum (exspec.cc:83-86): flux only, angle-averaged only
+    if (S.gamma_flux != nullptr && arrives && nu_rf > S.gamma_nu_min && nu_rf < S.gamma_nu_max) {
+      const int nnu = log_bin_index(nu_rf, S.gamma_nu_min, S.gamma_dlognu, S.nnubins);
+      const double deltaE = e_rf / S.ts_width[nts] / static_cast<double>(S.gamma_delta_freq[nnu]) / 4.e12 / PI / PARSEC / PARSEC /
+                            S.nprocs_exspec * 1.;
+      atomic_add(&S.gamma_flux[(nnu * static_cast<long long>(S.ntimesteps)) + nts], deltaE);
+    }
     return;
   }
 
@@ -219,6 +240,17 @@ AHD void bin_escaped_packet(const Tables& T, const SpectraView& S, const long lo
   atomic_add(&S.flux[fluxindex], deltaE_unit * 1.);
   if (S.nsets > 1) {
     atomic_add(&S.flux[((1 + dirbin) * fluxsize) + fluxindex], deltaE_unit * mabins);
+  }
+  const bool stokes = (S.flux_q != nullptr);
+  const double stokes_q = stokes ? hb.stokes_q : 0.;
+  const double stokes_u = stokes ? hb.stokes_u : 0.;
+  if (stokes) {
+    atomic_add(&S.flux_q[fluxindex], stokes_q * (deltaE_unit * 1.));
+    atomic_add(&S.flux_u[fluxindex], stokes_u * (deltaE_unit * 1.));
+    if (S.nsets > 1) {
+      atomic_add(&S.flux_q[((1 + dirbin) * fluxsize) + fluxindex], stokes_q * (deltaE_unit * mabins));
+      atomic_add(&S.flux_u[((1 + dirbin) * fluxsize) + fluxindex], stokes_u * (deltaE_unit * mabins));
+    }
   }
   if (S.nsets_emabs == 0) {
     return;
@@ -239,6 +271,14 @@ AHD void bin_escaped_packet(const Tables& T, const SpectraView& S, const long lo
     atomic_add(&S.emission[emindex_base + nproc], deltaE_unit * 1.);
     if (emabs_res) {
       atomic_add(&S.emission[((1 + dirbin) * emsize) + emindex_base + nproc], deltaE_unit * mabins);
+    }
+    if (stokes) {
+      atomic_add(&S.emission_q[emindex_base + nproc], stokes_q * (deltaE_unit * 1.));
+      atomic_add(&S.emission_u[emindex_base + nproc], stokes_u * (deltaE_unit * 1.));
+      if (emabs_res) {
+        atomic_add(&S.emission_q[((1 + dirbin) * emsize) + emindex_base + nproc], stokes_q * (deltaE_unit * mabins));
+        atomic_add(&S.emission_u[((1 + dirbin) * emsize) + emindex_base + nproc], stokes_u * (deltaE_unit * mabins));
+      }
     }
   }
   if (bad) {
@@ -268,6 +308,14 @@ AHD void bin_escaped_packet(const Tables& T, const SpectraView& S, const long lo
       atomic_add(&S.absorption[absindex], deltaE_abs_unit * 1.);
       if (emabs_res) {
         atomic_add(&S.absorption[((1 + dirbin) * abssize) + absindex], deltaE_abs_unit * mabins);
+      }
+      if (stokes) {
+        atomic_add(&S.absorption_q[absindex], stokes_q * (deltaE_abs_unit * 1.));
+        atomic_add(&S.absorption_u[absindex], stokes_u * (deltaE_abs_unit * 1.));
+        if (emabs_res) {
+          atomic_add(&S.absorption_q[((1 + dirbin) * abssize) + absindex], stokes_q * (deltaE_abs_unit * mabins));
+          atomic_add(&S.absorption_u[((1 + dirbin) * abssize) + absindex], stokes_u * (deltaE_abs_unit * mabins));
+        }
       }
     }
   }

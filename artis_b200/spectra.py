@@ -43,6 +43,16 @@ def binned(engine, ntimesteps=None):
         out["absorption"] = ab.reshape(sets_em, nnu, nts, -1)
     if engine.array_count("spec.dirbin") > 0:
         out["dirbin"] = engine.get_array("spec.dirbin")
+    if engine.array_count("spec.flux_q") == flux.size:  # option spec_stokes
+        for stokes in ("q", "u"):
+            out[f"flux_{stokes}"] = engine.get_array(f"spec.flux_{stokes}").reshape(nsets, nnu, nts)
+            if "emission" in out and engine.array_count(f"spec.emission_{stokes}") == out["emission"].size:
+                out[f"emission_{stokes}"] = engine.get_array(f"spec.emission_{stokes}").reshape(out["emission"].shape)
+                out[f"absorption_{stokes}"] = engine.get_array(f"spec.absorption_{stokes}").reshape(out["absorption"].shape)
+    if engine.array_count("spec.gamma_flux") == nnu * nts:  # option spec_gamma_spectrum
+        out["gamma_flux"] = engine.get_array("spec.gamma_flux").reshape(nnu, nts)
+        out["gamma_lower_freq"] = engine.get_array("spec.gamma_lower_freq", dtype=np.float32)
+        out["gamma_delta_freq"] = engine.get_array("spec.gamma_delta_freq", dtype=np.float32)
     return out
 
 
@@ -78,6 +88,30 @@ def write_columns_file(path, table, numtimesteps):
                 continue
             for nts in range(numtimesteps):
                 f.write("".join(_g(v) + " " for v in table[nnu, nts]) + "\n" if nonzero[nnu, nts] else zero_line)
+
+
+def write_specpol(path, emission_path, absorption_path, timesteps_mid, lower_freq, delta_freq, fluxes, emissions=None, absorptions=None):
+    """write_specpol (spectrum_lightcurve.cc:426-485): I, Q and U spectra side by side for ALL timesteps; with the
+    decomposition, one line per (frequency bin, Stokes component, timestep) in the emission / absorption files.
+    fluxes / emissions / absorptions: the (I, Q, U) arrays of one set"""
+    ntimesteps = fluxes[0].shape[1]
+    centre = lower_freq.astype(np.float32) + (delta_freq.astype(np.float32) / np.float32(2))
+    em_file = open(emission_path, "w") if emissions is not None else None
+    ab_file = open(absorption_path, "w") if absorptions is not None else None
+    with open(path, "w") as f:
+        f.write("0" + "".join(" " + _g(timesteps_mid[p] / DAY) for p in range(ntimesteps)) * 3 + "\n")
+        for nnu in range(fluxes[0].shape[0]):
+            row = [_g(centre[nnu])]
+            for k in range(3):
+                row.extend(_g(v) for v in fluxes[k][nnu, :ntimesteps])
+                if em_file is not None:
+                    for nts in range(ntimesteps):
+                        em_file.write(" ".join(_g(v) for v in emissions[k][nnu, nts]) + "\n")
+                        ab_file.write(" ".join(_g(v) for v in absorptions[k][nnu, nts]) + "\n")
+            f.write(" ".join(row) + "\n")
+    for extra in (em_file, ab_file):
+        if extra is not None:
+            extra.close()
 
 
 def write_partial_lightcurve_spectra(engine, nts, outdir, timesteps_mid, ntimesteps_finish=None, multidimensional=True,

@@ -266,6 +266,11 @@ int artisb200_restore_packets_device(artisb200_ctx* ctx);
  *   spec.absorption 'd'[sets'][MNUBINS][ntimesteps][nelements*max_nions]
  *   lc.lum / lc.lumcmf 'd'[sets][ntimesteps]   lc.gamma_lum / lc.gamma_lumcmf 'd'[ntimesteps] (escaped gamma packets, set 0 only)
  *   spec.dirbin 'i'[npackets]  direction bin of every escaped packet, -1 for the others (option "spec_record_dirbin" = 1)
+ *   with option "spec_stokes" = 1 (exspec with POL_ON, exspec.cc:52-59): spec.flux_q/_u, spec.emission_q/_u, spec.absorption_q/_u,
+ *       the Stokes Q and U counterparts of the I arrays (every addend times the packet's stokes_q / stokes_u,
+ *       spectrum_lightcurve.cc:567-624)
+ *   with option "spec_gamma_spectrum" = 1 (exspec.cc:61-64, 83-86): spec.gamma_flux 'd'[MNUBINS][ntimesteps], the spectrum of the
+ *       escaped gamma packets between 0.05 and 4 MeV (angle-averaged), spec.gamma_lower_freq / spec.gamma_delta_freq 'f'[MNUBINS]
  * Options: "spec_nnubins" (MNUBINS, exspec.h:8, default 1000). Sums over ranks: the caller all-reduces the arrays, as the
  * reference does (spectrum_lightcurve.cc:293-310). The additions are floating-point atomics: the sums agree with the
  * reference's to rounding of the summation order, not bit for bit. */

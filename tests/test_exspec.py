@@ -55,12 +55,14 @@ def test_exspec_files_of_a_reference_run(config, tmp_path):
     assert np.array_equal(pk["trueemissiontype"][no_em], mem["trueemissiontype"][no_em])  # columns before the nan are read
 
     out = tmp_path / "mine"
-    exspec_mod.exspec(eng, static, rundir, outdir=str(out), nprocs_exspec=1, only_dirbins={0, 7, 18, 42, 63, 99})
+    exspec_mod.exspec(eng, static, rundir, outdir=str(out), nprocs_exspec=1, only_dirbins={0, 7, 18, 42, 63, 99}, pol_on=True)
     eng.close()
-    files = ["spec.out", "light_curve.out", "gamma_light_curve.out", "emission.out", "emissiontrue.out", "absorption.out"]
+    files = ["spec.out", "light_curve.out", "gamma_light_curve.out", "emission.out", "emissiontrue.out", "absorption.out",
+             "specpol.out", "emissionpol.out", "absorptionpol.out", "gamma_spec.out"]
     res = spectra_mod.OUTDIR_RESFILES
     files += [os.path.join(res, f) for f in ("spec_res_00.out", "spec_res_42.out", "spec_res_99.out", "light_curve_res_07.out",
-                                             "emission_res_63.out", "absorption_res_18.out")]
+                                             "emission_res_63.out", "absorption_res_18.out", "specpol_res_42.out", "emissionpol_res_07.out",
+                                             "absorptionpol_res_99.out")]
     compared = 0
     for name in files:
         theirs = os.path.join(rundir, name)

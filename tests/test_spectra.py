@@ -138,3 +138,8 @@ def test_synthetic_packets_over_every_branch_against_the_numpy_oracle():
     assert np.count_nonzero(got["emission"][0][:, :, -1]) > 0  # free-free column
     nions = static["elem.anumber"].size * int(static["elem.nions"].max())
     assert np.count_nonzero(got["emission"][0][:, :, nions:2 * nions]) > 0  # bound-free columns
+
+
+def test_stokes_spectra_and_gamma_ray_spectrum_properties():
+    from tests import stokes_gamma_checks
+    stokes_gamma_checks.check_stokes_and_gamma_spectrum(fixtures.hostsim_library("classic"))
