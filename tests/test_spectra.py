@@ -142,4 +142,4 @@ def test_synthetic_packets_over_every_branch_against_the_numpy_oracle():
 
 def test_stokes_spectra_and_gamma_ray_spectrum_properties():
     from tests import stokes_gamma_checks
-    stokes_gamma_checks.check_stokes_and_gamma_spectrum(fixtures.hostsim_library("classic"))
+    stokes_gamma_checks.check_stokes_and_gamma_spectrum(fixtures.hostsim_library("classic"), n=12_000)
